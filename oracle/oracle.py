@@ -1,0 +1,142 @@
+"""ctypes binding of the CPU oracle (oracle/svo_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module; the product package (sparsevoxeloctree_b200) never does.
+PARITY UNPINNED -- see oracle/svo_oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libsvo_oracle.so")
+
+CENTER, CONSERVATIVE_EXACT = 0, 1
+
+DRAW_DTYPE = np.dtype([("first_index", "<u4"), ("index_count", "<u4"), ("texture_id", "<u4"), ("albedo_rgba8", "<u4")])
+FRAG_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("z", "<u4"), ("rgb", "<u4")])
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (oracle/Makefile)."""
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("svo_oracle.c", "svo_oracle.h", "Makefile"))
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < src_m:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_pack_fragment.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)]
+        L.orc_pack_fragment.restype = None
+        L.orc_unpack_fragment.argtypes = [C.POINTER(C.c_uint32)] + [C.POINTER(C.c_uint32)] * 4
+        L.orc_unpack_fragment.restype = None
+        L.orc_octree_entry_num.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_octree_entry_num.restype = C.c_uint32
+        L.orc_voxelize.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.orc_voxelize.restype = C.c_int64
+        L.orc_build.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
+        L.orc_build.restype = C.c_int64
+        L.orc_canonicalise.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_canonicalise.restype = C.c_int64
+        L.orc_morton.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_morton.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+def pack_fragment(x, y, z, colour):
+    out = (C.c_uint32 * 2)()
+    lib().orc_pack_fragment(x, y, z, colour, out)
+    return int(out[0]), int(out[1])
+
+
+def unpack_fragment(lo, hi):
+    a = (C.c_uint32 * 2)(lo, hi)
+    x, y, z, c = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib().orc_unpack_fragment(a, C.byref(x), C.byref(y), C.byref(z), C.byref(c))
+    return x.value, y.value, z.value, c.value
+
+
+def octree_entry_num(fragment_count, level):
+    return int(lib().orc_octree_entry_num(fragment_count, level))
+
+
+def morton(x, y, z, level):
+    return int(lib().orc_morton(x, y, z, level))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def voxelize(positions, indices, draws, level, mode=CENTER, shard=None, nthreads=1, count_only=False):
+    """positions: float32 [V,3] (or [V,5] pos+uv like the reference Vertex); indices uint32; draws DRAW_DTYPE.
+    Returns a FRAG_DTYPE array (emission order when nthreads == 1)."""
+    positions = np.ascontiguousarray(positions, dtype=np.float32)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    draws = np.ascontiguousarray(draws, dtype=DRAW_DTYPE)
+    stride = positions.shape[1] * 4
+    lo = hi = None
+    if shard is not None:
+        lo = np.ascontiguousarray(shard[0], dtype=np.uint32)
+        hi = np.ascontiguousarray(shard[1], dtype=np.uint32)
+    L = lib()
+    n = L.orc_voxelize(_ptr(positions), stride, _ptr(indices), _ptr(draws), len(draws), level, mode, _ptr(lo), _ptr(hi),
+                       None, 0, nthreads)
+    if n < 0:
+        raise ValueError(f"orc_voxelize failed ({n})")
+    if count_only:
+        return int(n)
+    out = np.zeros(n, dtype=FRAG_DTYPE)
+    n2 = L.orc_voxelize(_ptr(positions), stride, _ptr(indices), _ptr(draws), len(draws), level, mode, _ptr(lo), _ptr(hi),
+                        _ptr(out), n, nthreads)
+    assert n2 == n
+    return out
+
+
+def build_octree(frags, level, cap_words=None, nthreads=1):
+    """The reference level loop.  Returns (words[:range/4] uint32, range_bytes)."""
+    frags = np.ascontiguousarray(frags, dtype=FRAG_DTYPE)
+    if cap_words is None:
+        # exact upper bound for the literal loop: one 8-word block per non-leaf node plus the root block
+        n = max(1, len(frags))
+        cap_words = 8 * (1 + sum(min(8 ** d, n) for d in range(1, level)))
+        cap_words = min(cap_words, 1 << 30)
+    words = np.zeros(cap_words, dtype=np.uint32)
+    r = lib().orc_build(_ptr(frags), len(frags), level, _ptr(words), cap_words, nthreads)
+    if r < 0:
+        raise MemoryError("octree buffer too small (the reference would write out of bounds)")
+    return words[: r // 4].copy(), int(r)
+
+
+def canonicalise(words, level):
+    """Morton-DFS canonical form: (depth uint8[], morton uint64[], word uint32[])."""
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    L = lib()
+    n = L.orc_canonicalise(_ptr(words), len(words), level, None, None, None, 0)
+    if n < 0:
+        raise ValueError(f"malformed octree ({n})")
+    depth = np.zeros(n, dtype=np.uint8)
+    mort = np.zeros(n, dtype=np.uint64)
+    word = np.zeros(n, dtype=np.uint32)
+    n2 = L.orc_canonicalise(_ptr(words), len(words), level, _ptr(depth), _ptr(mort), _ptr(word), n)
+    assert n2 == n
+    return depth, mort, word
+
+
+def frags_from_xyzc(x, y, z, rgb):
+    out = np.zeros(len(x), dtype=FRAG_DTYPE)
+    out["x"], out["y"], out["z"], out["rgb"] = x, y, z, rgb
+    return out

@@ -1,0 +1,487 @@
+/*
+ * oracle/svo_oracle.c -- CPU ORACLE. TEST INFRASTRUCTURE ONLY (see svo_oracle.h).
+ *
+ * PARITY UNPINNED: no reference fixture exists for this path; pinned by hand-derived
+ * KATs only (tests/test_oracle_kat.py).  Every function cites the reference file:line
+ * (relative to /root/reference) that it restates.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
+ * -ffp-contract=off matters: the pinned arithmetic below is "one IEEE operation per
+ * written operator", fp32 where the shaders are fp32.
+ */
+#include "svo_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Fragment packing: voxelizer.frag:40-42 / octree_tag_node.comp:38-39
+ * ---------------------------------------------------------------------------------------- */
+void orc_pack_fragment(uint32_t x, uint32_t y, uint32_t z, uint32_t colour, uint32_t out[2]) {
+	out[0] = x | (y << 12u) | ((z & 0xffu) << 24u);
+	out[1] = ((z >> 8u) << 28u) | (colour & 0x00ffffffu);
+}
+void orc_unpack_fragment(const uint32_t in[2], uint32_t *x, uint32_t *y, uint32_t *z, uint32_t *rgb) {
+	*x = in[0] & 0xfffu;
+	*y = (in[0] >> 12u) & 0xfffu;
+	*z = (in[0] >> 24u) | ((in[1] >> 28u) << 8u);
+	*rgb = in[1] & 0xffffffu;
+}
+
+/* OctreeBuilder.cpp:42-45 with Config.hpp:20-21 (u32 arithmetic, integer level/3). */
+uint32_t orc_octree_entry_num(uint32_t fragment_count, uint32_t level) {
+	const uint32_t kOctreeNodeNumMin = 1000000u, kOctreeNodeNumMax = 500000000u;
+	uint32_t ratio = level / 3u;
+	uint32_t n = fragment_count * ratio;
+	if (n < kOctreeNodeNumMin)
+		n = kOctreeNodeNumMin;
+	if (n > kOctreeNodeNumMax)
+		n = kOctreeNodeNumMax;
+	return n;
+}
+
+uint64_t orc_morton(uint32_t x, uint32_t y, uint32_t z, uint32_t level) {
+	uint64_t m = 0;
+	for (uint32_t b = 0; b < level; ++b) {
+		m |= (uint64_t)((x >> b) & 1u) << (3u * b);
+		m |= (uint64_t)((y >> b) & 1u) << (3u * b + 1u);
+		m |= (uint64_t)((z >> b) & 1u) << (3u * b + 2u);
+	}
+	return m;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Voxelizer
+ * ---------------------------------------------------------------------------------------- */
+
+/* GLSL uint(float): truncation toward zero; negative / NaN are undefined in GLSL and are
+ * pinned to 0 here, too-large saturates. */
+static uint32_t f2u(float f) {
+	if (!(f > 0.0f))
+		return 0u;
+	if (f >= 4294967296.0f)
+		return 0xffffffffu;
+	return (uint32_t)f;
+}
+static float fmin3(float a, float b, float c) {
+	float m = c < b ? c : b; /* GLSL min(x,y) = y < x ? y : x */
+	return m < a ? m : a;
+}
+static float fmax3(float a, float b, float c) {
+	float m = b < c ? c : b;
+	return a < m ? m : a;
+}
+
+typedef struct {
+	uint32_t axis;
+	int32_t X[3], Y[3]; /* snapped window coordinates, 1/256 pixel */
+	float zf[3];        /* depth in [0,1] */
+	uint32_t aabb[4];   /* gAABB  (voxelizer.geom:39-40) */
+	uint32_t zr[2];     /* gDepthRange (voxelizer.geom:41-42) */
+	int64_t area2;      /* > 0 after orientation normalisation; 0 = degenerate */
+	int valid;
+} orc_tri;
+
+/* voxelizer.vert:8-11 (pass-through) + voxelizer.geom:15-42 + viewport transform
+ * (Voxelizer.cpp:115-116: viewport (0,0,res,res), depth 0..1, no y flip). */
+static void orc_tri_setup(const float *p0, const float *p1, const float *p2, uint32_t res, orc_tri *t) {
+	const float *p[3] = {p0, p1, p2};
+	float e1[3], e2[3], n[3], w[3];
+	for (int k = 0; k < 3; ++k) {
+		e1[k] = p1[k] - p0[k];
+		e2[k] = p2[k] - p0[k];
+	}
+	/* voxelizer.geom:28 cross(pos1 - pos0, pos2 - pos0) */
+	n[0] = e1[1] * e2[2] - e1[2] * e2[1];
+	n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+	n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+	for (int k = 0; k < 3; ++k)
+		w[k] = fabsf(n[k]);
+	/* voxelizer.geom:30-32 */
+	t->axis = (w[0] > w[1] && w[0] > w[2]) ? 0u : ((w[1] > w[2]) ? 1u : 2u);
+
+	float q[3][3];
+	t->valid = 1;
+	for (int i = 0; i < 3; ++i) {
+		/* Project(): axis 0 -> v.yzx, axis 1 -> v.zxy, axis 2 -> v.xyz; z = (z+1)*0.5  (voxelizer.geom:15-19) */
+		if (t->axis == 0u) {
+			q[i][0] = p[i][1], q[i][1] = p[i][2], q[i][2] = p[i][0];
+		} else if (t->axis == 1u) {
+			q[i][0] = p[i][2], q[i][1] = p[i][0], q[i][2] = p[i][1];
+		} else {
+			q[i][0] = p[i][0], q[i][1] = p[i][1], q[i][2] = p[i][2];
+		}
+		q[i][2] = (q[i][2] + 1.0f) * 0.5f;
+		t->zf[i] = q[i][2];
+		for (int k = 0; k < 3; ++k)
+			if (!(fabsf(p[i][k]) <= 2.0f)) /* guard band; also rejects NaN/Inf */
+				t->valid = 0;
+	}
+	const float fres = (float)res;
+	/* voxelizer.geom:39-42 */
+	t->aabb[0] = f2u((fmin3(q[0][0], q[1][0], q[2][0]) + 1.0f) * 0.5f * fres);
+	t->aabb[1] = f2u((fmin3(q[0][1], q[1][1], q[2][1]) + 1.0f) * 0.5f * fres);
+	t->aabb[2] = f2u((fmax3(q[0][0], q[1][0], q[2][0]) + 1.0f) * 0.5f * fres);
+	t->aabb[3] = f2u((fmax3(q[0][1], q[1][1], q[2][1]) + 1.0f) * 0.5f * fres);
+	t->zr[0] = f2u(fmin3(q[0][2], q[1][2], q[2][2]) * fres);
+	t->zr[1] = f2u(fmax3(q[0][2], q[1][2], q[2][2]) * fres);
+	if (!t->valid)
+		return;
+	/* viewport transform x_f = (x+1)*res/2 (identical to the AABB expression) and snapping
+	 * to 8 sub-pixel bits, round-half-even (pinned). */
+	for (int i = 0; i < 3; ++i) {
+		float xf = (q[i][0] + 1.0f) * 0.5f * fres;
+		float yf = (q[i][1] + 1.0f) * 0.5f * fres;
+		t->X[i] = (int32_t)rintf(xf * 256.0f);
+		t->Y[i] = (int32_t)rintf(yf * 256.0f);
+	}
+	int64_t a2 = (int64_t)(t->X[1] - t->X[0]) * (int64_t)(t->Y[2] - t->Y[0]) -
+	             (int64_t)(t->X[2] - t->X[0]) * (int64_t)(t->Y[1] - t->Y[0]);
+	if (a2 < 0) { /* CULL_NONE: both windings rasterize (Voxelizer.cpp:117-118); normalise to a2 > 0 */
+		int32_t ti;
+		float tf;
+		ti = t->X[1], t->X[1] = t->X[2], t->X[2] = ti;
+		ti = t->Y[1], t->Y[1] = t->Y[2], t->Y[2] = ti;
+		tf = t->zf[1], t->zf[1] = t->zf[2], t->zf[2] = tf;
+		a2 = -a2;
+	}
+	t->area2 = a2;
+}
+
+static int64_t edge_fn(const orc_tri *t, int a, int b, int64_t px, int64_t py) {
+	return (int64_t)(t->X[b] - t->X[a]) * (py - t->Y[a]) - (int64_t)(t->Y[b] - t->Y[a]) * (px - t->X[a]);
+}
+static int64_t iabs64(int64_t v) { return v < 0 ? -v : v; }
+
+/* Coverage of pixel (px,py) -- the rasterizer the reference configures at Voxelizer.cpp:112-129.
+ * mode ORC_CENTER: centre sample + top-left rule (Vulkan spec, basic polygon rasterization).
+ * mode ORC_CONSERVATIVE_EXACT: VK_CONSERVATIVE_RASTERIZATION_MODE_OVERESTIMATE with
+ *   extraPrimitiveOverestimationSize 0 (Voxelizer.cpp:120-127): every pixel square that
+ *   touches the (snapped) triangle, closed-set separating-axis test. */
+static int covered(const orc_tri *t, int mode, int32_t px, int32_t py) {
+	static const int EA[3] = {1, 2, 0}, EB[3] = {2, 0, 1};
+	const int64_t cx = (int64_t)px * 256 + 128, cy = (int64_t)py * 256 + 128;
+	if (mode == ORC_CENTER) {
+		if (t->area2 == 0)
+			return 0;
+		for (int i = 0; i < 3; ++i) {
+			int64_t A = -(int64_t)(t->Y[EB[i]] - t->Y[EA[i]]), B = (int64_t)(t->X[EB[i]] - t->X[EA[i]]);
+			int64_t e = edge_fn(t, EA[i], EB[i], cx, cy);
+			int top_left = (A > 0) || (A == 0 && B > 0);
+			if (e < 0 || (e == 0 && !top_left))
+				return 0;
+		}
+		return 1;
+	}
+	/* conservative: box axes first */
+	int32_t xmin = t->X[0], xmax = t->X[0], ymin = t->Y[0], ymax = t->Y[0];
+	for (int i = 1; i < 3; ++i) {
+		if (t->X[i] < xmin) xmin = t->X[i];
+		if (t->X[i] > xmax) xmax = t->X[i];
+		if (t->Y[i] < ymin) ymin = t->Y[i];
+		if (t->Y[i] > ymax) ymax = t->Y[i];
+	}
+	if ((int64_t)px * 256 > xmax || (int64_t)px * 256 + 256 < xmin)
+		return 0;
+	if ((int64_t)py * 256 > ymax || (int64_t)py * 256 + 256 < ymin)
+		return 0;
+	if (t->area2 > 0) {
+		for (int i = 0; i < 3; ++i) {
+			int64_t A = -(int64_t)(t->Y[EB[i]] - t->Y[EA[i]]), B = (int64_t)(t->X[EB[i]] - t->X[EA[i]]);
+			int64_t e = edge_fn(t, EA[i], EB[i], cx, cy);
+			if (e + 128 * (iabs64(A) + iabs64(B)) < 0)
+				return 0;
+		}
+		return 1;
+	}
+	/* zero snapped area: a segment or a point (degenerateTrianglesRasterized behaviour, pinned):
+	 * the longest edge is the segment; squares touching it are covered. */
+	static const int SA[3] = {0, 1, 2}, SB[3] = {1, 2, 0};
+	int best = 0;
+	int64_t best_d = -1;
+	for (int i = 0; i < 3; ++i) {
+		int64_t dx = t->X[SB[i]] - t->X[SA[i]], dy = t->Y[SB[i]] - t->Y[SA[i]];
+		int64_t d = dx * dx + dy * dy;
+		if (d > best_d)
+			best_d = d, best = i;
+	}
+	int64_t A = -(int64_t)(t->Y[SB[best]] - t->Y[SA[best]]), B = (int64_t)(t->X[SB[best]] - t->X[SA[best]]);
+	int64_t e = edge_fn(t, SA[best], SB[best], cx, cy);
+	return iabs64(e) <= 128 * (iabs64(A) + iabs64(B));
+}
+
+/* Depth at the pixel centre: the triangle's plane through the snapped vertices evaluated in
+ * fp64 (pinned); extrapolated when the centre is outside (conservative mode). */
+typedef struct {
+	double dzdx, dzdy, z0;
+	int32_t X0, Y0;
+} orc_plane;
+static void plane_setup(const orc_tri *t, orc_plane *pl) {
+	pl->X0 = t->X[0], pl->Y0 = t->Y[0];
+	pl->z0 = (double)t->zf[0];
+	if (t->area2 == 0) { /* provoking-vertex depth for degenerate primitives */
+		pl->dzdx = pl->dzdy = 0.0;
+		return;
+	}
+	double dz1 = (double)t->zf[1] - (double)t->zf[0], dz2 = (double)t->zf[2] - (double)t->zf[0];
+	double dx1 = (double)(t->X[1] - t->X[0]), dy1 = (double)(t->Y[1] - t->Y[0]);
+	double dx2 = (double)(t->X[2] - t->X[0]), dy2 = (double)(t->Y[2] - t->Y[0]);
+	double a2 = (double)t->area2;
+	pl->dzdx = (dz1 * dy2 - dz2 * dy1) / a2;
+	pl->dzdy = (dz2 * dx1 - dz1 * dx2) / a2;
+}
+
+/* voxelizer.frag:17-25 GetVoxePos for pixel (px,py); returns 0 when the fragment is discarded. */
+static int frag_voxel(const orc_tri *t, const orc_plane *pl, uint32_t res, int32_t px, int32_t py, uint32_t v[3]) {
+	int32_t cx = px * 256 + 128, cy = py * 256 + 128;
+	double z = fma(pl->dzdx, (double)(cx - pl->X0), fma(pl->dzdy, (double)(cy - pl->Y0), pl->z0));
+	double zs = z * (double)res; /* v.z *= float(kVoxelResolution) */
+	uint32_t uz = !(zs > 0.0) ? 0u : (zs >= (double)res ? res - 1u : (uint32_t)zs); /* clamp(uvec3(v),0,res-1) */
+	uint32_t ux = (uint32_t)px, uy = (uint32_t)py;
+	/* voxelizer.frag:21-22 */
+	if (ux < t->aabb[0] || ux > t->aabb[2] || uy < t->aabb[1] || uy > t->aabb[3])
+		return 0;
+	/* voxelizer.frag:23 clamp(u.z, lo, hi) = min(max(u.z, lo), hi) */
+	if (uz < t->zr[0]) uz = t->zr[0];
+	if (uz > t->zr[1]) uz = t->zr[1];
+	/* pinned deviation: a depth of exactly 1.0 yields zr = res; the reference's traversal treats
+	 * coordinate res like res-1 for L < 12 and corrupts the packing at L = 12. */
+	if (uz > res - 1u) uz = res - 1u;
+	/* voxelizer.frag:24 */
+	if (t->axis == 0u)
+		v[0] = uz, v[1] = ux, v[2] = uy;
+	else if (t->axis == 1u)
+		v[0] = uy, v[1] = uz, v[2] = ux;
+	else
+		v[0] = ux, v[1] = uy, v[2] = uz;
+	return 1;
+}
+
+static int32_t floor_div256(int32_t v) { return v >> 8; } /* arithmetic shift = floor for negatives */
+
+int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uint32_t *indices,
+                     const orc_draw *draws, uint32_t n_draws, uint32_t level, int mode,
+                     const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out, int64_t cap,
+                     int nthreads) {
+	if (level < 1 || level > 16 || (mode != ORC_CENTER && mode != ORC_CONSERVATIVE_EXACT))
+		return -1;
+	for (uint32_t d = 0; d < n_draws; ++d)
+		if (draws[d].texture_id != 0xffffffffu)
+			return -2; /* textured materials are outside the built path */
+	const uint32_t res = 1u << level;
+	const unsigned char *pbase = (const unsigned char *)positions;
+	int64_t counter = 0; /* uCounter (voxelizer.frag:5,37) */
+	if (nthreads < 1)
+		nthreads = 1;
+
+	for (uint32_t d = 0; d < n_draws; ++d) { /* Scene::CmdDraw: one draw per material (Scene.cpp:450-463) */
+		const uint32_t ntri = draws[d].index_count / 3u;
+		const uint32_t colour = draws[d].albedo_rgba8 & 0xffffffu;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) if (nthreads > 1)
+		for (uint32_t k = 0; k < ntri; ++k) {
+			const uint32_t *ix = indices + draws[d].first_index + 3u * k;
+			orc_tri t;
+			orc_tri_setup((const float *)(pbase + (size_t)ix[0] * pos_stride_bytes),
+			              (const float *)(pbase + (size_t)ix[1] * pos_stride_bytes),
+			              (const float *)(pbase + (size_t)ix[2] * pos_stride_bytes), res, &t);
+			if (!t.valid)
+				continue;
+			if (t.area2 == 0 && mode == ORC_CENTER)
+				continue;
+			orc_plane pl;
+			plane_setup(&t, &pl);
+			int32_t xmin = t.X[0], xmax = t.X[0], ymin = t.Y[0], ymax = t.Y[0];
+			for (int i = 1; i < 3; ++i) {
+				if (t.X[i] < xmin) xmin = t.X[i];
+				if (t.X[i] > xmax) xmax = t.X[i];
+				if (t.Y[i] < ymin) ymin = t.Y[i];
+				if (t.Y[i] > ymax) ymax = t.Y[i];
+			}
+			/* generous candidate range; every pixel is put through the full rule. Viewport/scissor
+			 * (Voxelizer.cpp:115-116) limits pixels to [0,res). */
+			int32_t px0 = floor_div256(xmin) - 1, px1 = floor_div256(xmax) + 1;
+			int32_t py0 = floor_div256(ymin) - 1, py1 = floor_div256(ymax) + 1;
+			if (px0 < 0) px0 = 0;
+			if (py0 < 0) py0 = 0;
+			if (px1 > (int32_t)res - 1) px1 = (int32_t)res - 1;
+			if (py1 > (int32_t)res - 1) py1 = (int32_t)res - 1;
+			for (int32_t py = py0; py <= py1; ++py)
+				for (int32_t px = px0; px <= px1; ++px) {
+					if (!covered(&t, mode, px, py))
+						continue;
+					uint32_t v[3];
+					if (!frag_voxel(&t, &pl, res, px, py, v))
+						continue;
+					if (shard_lo && shard_hi) {
+						if (v[0] < shard_lo[0] || v[0] >= shard_hi[0] || v[1] < shard_lo[1] ||
+						    v[1] >= shard_hi[1] || v[2] < shard_lo[2] || v[2] >= shard_hi[2])
+							continue;
+					}
+					int64_t cur; /* uint cur = atomicAdd(uCounter, 1u)  (voxelizer.frag:37) */
+					if (nthreads > 1)
+						cur = __atomic_fetch_add(&counter, 1, __ATOMIC_RELAXED);
+					else
+						cur = counter++;
+					if (out && cur < cap) { /* uCountOnly == 0 (voxelizer.frag:39-43) */
+						out[cur].x = v[0], out[cur].y = v[1], out[cur].z = v[2];
+						out[cur].rgb = colour;
+					}
+				}
+		}
+	}
+	return counter;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * OctreeBuilder
+ * ---------------------------------------------------------------------------------------- */
+
+/* octree_tag_node.comp:10-16 */
+static void leaf_to_uvec4(uint32_t val, uint32_t v[4]) {
+	v[0] = val & 0xffu, v[1] = (val >> 8u) & 0xffu, v[2] = (val >> 16u) & 0xffu, v[3] = (val >> 24u) & 0x3fu;
+}
+static uint32_t uvec4_to_leaf(const uint32_t v[4]) {
+	uint32_t w = v[3] < 0x3fu ? v[3] : 0x3fu;
+	return (w << 24u) | (v[0] & 0xffu) | ((v[1] & 0xffu) << 8u) | ((v[2] & 0xffu) << 16u) | 0xC0000000u;
+}
+
+/* octree_tag_node.comp:18-31 TraverseOctree */
+static uint32_t traverse_octree(const uint32_t *octree, uint32_t res, const uint32_t voxel_pos[3], int *is_leaf) {
+	uint32_t level_dim = res;
+	uint32_t pos[3] = {voxel_pos[0], voxel_pos[1], voxel_pos[2]};
+	uint32_t idx = 0u, cur = 0u;
+	do {
+		level_dim >>= 1;
+		uint32_t cx = pos[0] >= level_dim, cy = pos[1] >= level_dim, cz = pos[2] >= level_dim;
+		idx = cur | cx | (cy << 1u) | (cz << 2u);
+		cur = __atomic_load_n(&octree[idx], __ATOMIC_RELAXED) & 0x3fffffffu;
+		pos[0] -= cx * level_dim, pos[1] -= cy * level_dim, pos[2] -= cz * level_dim;
+	} while (cur != 0u && level_dim > 1u);
+	*is_leaf = level_dim == 1u;
+	return idx;
+}
+
+/* octree_tag_node.comp:33-60 main(), one invocation */
+static void tag_node(uint32_t *octree, uint32_t res, const orc_frag *f) {
+	uint32_t pos[3] = {f->x, f->y, f->z};
+	int is_leaf;
+	uint32_t idx = traverse_octree(octree, res, pos, &is_leaf);
+	if (is_leaf) {
+		uint32_t prev_val = 0u, cur_val, new_val = 0xC1000000u | (f->rgb & 0xffffffu);
+		uint32_t rgba[4];
+		leaf_to_uvec4(new_val, rgba);
+		for (;;) { /* atomicCompSwap loop (octree_tag_node.comp:50) */
+			uint32_t expected = prev_val;
+			if (__atomic_compare_exchange_n(&octree[idx], &expected, new_val, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+				break;
+			cur_val = expected;
+			prev_val = cur_val;
+			uint32_t prev_rgba[4], cur_rgba[4];
+			leaf_to_uvec4(prev_val, prev_rgba);
+			for (int c = 0; c < 3; ++c)
+				prev_rgba[c] *= prev_rgba[3];
+			for (int c = 0; c < 4; ++c)
+				cur_rgba[c] = prev_rgba[c] + rgba[c];
+			for (int c = 0; c < 3; ++c)
+				cur_rgba[c] /= cur_rgba[3];
+			new_val = uvec4_to_leaf(cur_rgba);
+		}
+	} else
+		__atomic_store_n(&octree[idx], 0x80000000u, __ATOMIC_RELAXED); /* plain store, benign race */
+}
+
+int64_t orc_build(const orc_frag *frags, int64_t n_frags, uint32_t level, uint32_t *words,
+                  uint64_t cap_words, int nthreads) {
+	if (level < 1 || level > 16)
+		return -1;
+	const uint32_t res = 1u << level;
+	if (nthreads < 1)
+		nthreads = 1;
+	/* OctreeBuilder.cpp:27-31 build_info = {allocBegin 0, allocNum 8}; Counter reset 0 (:14-15) */
+	uint64_t alloc_begin = 0, alloc_num = 8;
+	uint32_t counter = 0;
+	for (uint32_t i = 1; i <= level; ++i) { /* OctreeBuilder.cpp:167 */
+		if (alloc_begin + alloc_num > cap_words)
+			return -1;
+		/* octree_init_node.comp:7-11 */
+		memset(words + alloc_begin, 0, (size_t)alloc_num * sizeof(uint32_t));
+		/* octree_tag_node.comp, ceil(F/64) groups (OctreeBuilder.cpp:163,177-178) */
+#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+		for (int64_t f = 0; f < n_frags; ++f)
+			tag_node(words, res, &frags[f]);
+		if (i != level) {
+			/* octree_alloc_node.comp:9-23 (one atomicAdd per flagged word; the subgroup
+			 * aggregation changes only which id a word gets, which is arbitrary anyway) */
+#pragma omp parallel for schedule(static) num_threads(nthreads) if (nthreads > 1)
+			for (uint64_t k = alloc_begin; k < alloc_begin + alloc_num; ++k) {
+				if (words[k] & 0x80000000u) {
+					uint32_t cur = nthreads > 1 ? __atomic_fetch_add(&counter, 1u, __ATOMIC_RELAXED) : counter++;
+					words[k] = ((cur + 1u) << 3u) | 0x80000000u;
+				}
+			}
+			/* octree_modify_arg.comp:9-13 */
+			alloc_begin += alloc_num;
+			alloc_num = ((uint64_t)counter << 3u) - alloc_begin + 8u;
+		}
+	}
+	/* OctreeBuilder.cpp:212-214 */
+	return ((int64_t)counter + 1) * 8 * (int64_t)sizeof(uint32_t);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Canonical form (test helper; layout per octree.glsl:87-110)
+ * ---------------------------------------------------------------------------------------- */
+int64_t orc_canonicalise(const uint32_t *words, uint64_t n_words, uint32_t level, uint8_t *out_depth,
+                         uint64_t *out_morton, uint32_t *out_word, int64_t cap) {
+	if (level < 1 || level > 16 || n_words < 8)
+		return -1;
+	/* explicit DFS stack: (block word index, next slot, morton prefix) per depth */
+	uint32_t blk[17];
+	uint32_t slot[17];
+	uint64_t pre[17];
+	int64_t n = 0;
+	int d = 1;
+	blk[1] = 0, slot[1] = 0, pre[1] = 0;
+	while (d >= 1) {
+		if (slot[d] == 8u) {
+			--d;
+			continue;
+		}
+		uint32_t s = slot[d]++;
+		uint32_t w = words[blk[d] + s];
+		if (w == 0u)
+			continue;
+		if (!(w & 0x80000000u))
+			return -4;
+		uint64_t m = (pre[d] << 3u) | s;
+		if (w & 0x40000000u) { /* leaf */
+			if ((uint32_t)d != level)
+				return -2;
+			if (n < cap) {
+				if (out_depth) out_depth[n] = (uint8_t)d;
+				if (out_morton) out_morton[n] = m;
+				if (out_word) out_word[n] = w;
+			}
+			++n;
+		} else {
+			if ((uint32_t)d == level)
+				return -3;
+			uint32_t ptr = w & 0x3fffffffu;
+			if (ptr == 0u || (ptr & 7u) || (uint64_t)ptr + 8u > n_words)
+				return -1;
+			if (n < cap) {
+				if (out_depth) out_depth[n] = (uint8_t)d;
+				if (out_morton) out_morton[n] = m;
+				if (out_word) out_word[n] = 0x80000000u;
+			}
+			++n;
+			++d;
+			blk[d] = ptr, slot[d] = 0, pre[d] = m;
+		}
+	}
+	return n;
+}

@@ -1,0 +1,89 @@
+/*
+ * oracle/svo_oracle.h -- CPU ORACLE. TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the reference's SVO construction path
+ * (AdamYuan/SparseVoxelOctree: Voxelizer + OctreeBuilder).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library, and there only as the checker / the CPU baseline.  The
+ * product (sparsevoxeloctree_b200/) never links, imports or calls it.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
+ * this path, and its shaders cannot be executed in this image (no
+ * Vulkan ICD), so this oracle is pinned only against hand-derived known-answer
+ * tests read off the shader sources (tests/test_oracle_kat.py) -- see DESIGN.md.
+ * The fixed-function rasterizer arithmetic lives in the Vulkan driver, not in
+ * the reference tree; the arithmetic used here for coverage and depth is the
+ * "pinned arithmetic" stated in DESIGN.md section 3.
+ */
+#ifndef SVO_ORACLE_H
+#define SVO_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One draw per material: mirrors Scene::DrawCmd (src/Scene.hpp:28-34, Scene.cpp:157-170). */
+typedef struct {
+	uint32_t first_index, index_count;
+	uint32_t texture_id;   /* 0xffffffff = untextured (voxelizer.frag:35) */
+	uint32_t albedo_rgba8; /* packUnorm4x8(vec4(albedo,0)), R in bits 0-7 (Scene.cpp:164) */
+} orc_draw;
+
+/* An unpacked voxel fragment (voxelizer.frag:17-25 voxel position + colour & 0xffffff). */
+typedef struct {
+	uint32_t x, y, z, rgb;
+} orc_frag;
+
+enum { ORC_CENTER = 0, ORC_CONSERVATIVE_EXACT = 1, ORC_CONSERVATIVE_DILATE = 2 };
+
+/* voxelizer.frag:40-42 packing and octree_tag_node.comp:38-39 unpacking (levels <= 12). */
+void orc_pack_fragment(uint32_t x, uint32_t y, uint32_t z, uint32_t colour, uint32_t out[2]);
+void orc_unpack_fragment(const uint32_t in[2], uint32_t *x, uint32_t *y, uint32_t *z, uint32_t *rgb);
+
+/* OctreeBuilder.cpp:42-45: the reference's octree buffer size guess, in 32-bit words. */
+uint32_t orc_octree_entry_num(uint32_t fragment_count, uint32_t level);
+
+/*
+ * Voxelize (voxelizer.vert + voxelizer.geom + rasterizer state at Voxelizer.cpp:112-129 +
+ * voxelizer.frag).  Positions are read with a byte stride (20 for the reference's Vertex,
+ * 12 for tight float3).  shard_lo/hi (may be NULL) is a half-open voxel box; fragments
+ * outside it are dropped (used by the octant-sharding tests).  Fragments are written in
+ * draw order, triangle order, then row-major pixel order when nthreads == 1; with
+ * nthreads > 1 the order is arbitrary (atomic append, like voxelizer.frag:37).
+ * Returns the fragment count (also when it exceeds cap; only cap entries are written).
+ */
+int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uint32_t *indices,
+                     const orc_draw *draws, uint32_t n_draws, uint32_t level, int mode,
+                     const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out, int64_t cap,
+                     int nthreads);
+
+/*
+ * The OctreeBuilder level loop (OctreeBuilder.cpp:142-210 driving octree_init_node /
+ * octree_tag_node / octree_alloc_node / octree_modify_arg).  Fragments are tagged in
+ * input order and nodes allocated in window order when nthreads == 1.
+ * Returns the octree range in bytes ((counter+1)*32, OctreeBuilder.cpp:212-214), or -1
+ * if the build would write past cap_words (the reference would write out of bounds).
+ */
+int64_t orc_build(const orc_frag *frags, int64_t n_frags, uint32_t level, uint32_t *words,
+                  uint64_t cap_words, int nthreads);
+
+/*
+ * Canonicalise a node buffer by Morton depth-first traversal from the root block
+ * (node word layout by use in octree.glsl:87-110, octree_tag_node.comp:26,48,59).
+ * Emits every non-empty node as (depth, morton at that depth, word with the child
+ * pointer masked out of internal nodes).  Returns the node count (also when > cap),
+ * or a negative code when the buffer violates the layout:
+ *  -1 pointer not a multiple of 8 / out of range / zero, -2 leaf above the last level,
+ *  -3 internal node at the last level, -4 non-empty word without bit 31.
+ */
+int64_t orc_canonicalise(const uint32_t *words, uint64_t n_words, uint32_t level, uint8_t *out_depth,
+                         uint64_t *out_morton, uint32_t *out_word, int64_t cap);
+
+/* Morton code of a voxel: child slot = x | y<<1 | z<<2 per level, MSB first (tag_node.comp:24-25). */
+uint64_t orc_morton(uint32_t x, uint32_t y, uint32_t z, uint32_t level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
