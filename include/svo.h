@@ -1,0 +1,170 @@
+/*
+ * include/svo.h -- the drop-in boundary of svo-b200: a C ABI (plain pointers and sizes, no
+ * C++ / torch types) over the hand-written sm_100a CUDA implementation of the reference's SVO
+ * construction path (AdamYuan/SparseVoxelOctree Voxelizer + OctreeBuilder).
+ *
+ * The reference has no FFI for this path; its boundary is two C++ classes with one caller
+ * (src/LoaderThread.cpp:53-54,64,74) and one consumer (src/Octree.cpp:24-27).  Each entry point
+ * below cites the reference interface it replaces (paths relative to the reference tree).  The C++
+ * mirror classes with the reference's method names live in sparsevoxeloctree_b200/host/, the
+ * Python (ctypes) mirror in sparsevoxeloctree_b200/api.py, and the binding a reference maintainer
+ * would add is shown in INTEGRATION.md.
+ *
+ * Conventions: caller owns handles, the library owns device memory; no exceptions cross the ABI;
+ * every call returns SVO_OK (0) or a negative svo_status, with a message in svo_last_error()
+ * (thread-local).  A handle is used by one thread at a time.  All device work is enqueued on the
+ * `stream` argument (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * There is no CPU fallback anywhere behind this ABI: without a CUDA device calls fail.
+ */
+#ifndef SVO_B200_H
+#define SVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SVO_API
+#else
+#define SVO_API __attribute__((visibility("default")))
+#endif
+
+typedef enum svo_status {
+	SVO_OK = 0,
+	SVO_ERR_INVALID_ARGUMENT = -1,
+	SVO_ERR_CUDA = -2,           /* a CUDA runtime call failed; svo_last_error() has the cudaError string */
+	SVO_ERR_UNSUPPORTED = -3,    /* e.g. textured draws (not on the built path yet) */
+	SVO_ERR_CAPACITY = -4,       /* > 2^32-1 fragments, or an octree of >= 2^30 words (30-bit node pointers) */
+	SVO_ERR_NOT_READY = -5       /* result queried before the producing call */
+} svo_status;
+
+/* Rasterization rule.  The stock reference is always conservative: Mode A when
+ * VK_EXT_conservative_rasterization exists (src/Voxelizer.cpp:92-99,120-127).  SVO_CENTER is
+ * BASELINE.json's "non-conservative raster". */
+typedef enum svo_raster_mode {
+	SVO_CENTER = 0,            /* centre sample + top-left rule on the undilated triangle */
+	SVO_CONSERVATIVE_EXACT = 1 /* every pixel square touching the triangle (exact 2-D SAT) = reference Mode A */
+} svo_raster_mode;
+
+/* One draw per material: Scene::DrawCmd (src/Scene.hpp:28-34; filled at src/Scene.cpp:157-170,
+ * consumed by Scene::CmdDraw src/Scene.cpp:450-463). */
+typedef struct svo_draw {
+	uint32_t first_index, index_count;
+	uint32_t texture_id;   /* 0xffffffff = untextured (shader/voxelizer.frag:35) */
+	uint32_t albedo_rgba8; /* glm::packUnorm4x8(vec4(albedo, 0)), R in bits 0-7 (src/Scene.cpp:164) */
+} svo_draw;
+
+/* The mesh hand-off that Scene keeps private (src/Scene.hpp:26,35-40): the vertex buffer
+ * (struct Vertex {vec3 pos; vec2 uv}, stride 20, src/Scene.cpp:16-19; a tight float3 array with
+ * stride 12 is accepted too), the u32 index buffer and the draw list.  Positions must already be
+ * normalised to [-1,1]^3 (src/Scene.cpp:90-99). */
+typedef struct svo_mesh {
+	const void *positions;          /* first vertex position; HOST pointer unless on_device != 0 */
+	uint32_t position_stride_bytes; /* >= 12, multiple of 4 */
+	uint32_t on_device;             /* 1: positions/indices are device pointers (borrowed, must outlive the scene) */
+	const uint32_t *indices;
+	uint64_t n_vertices, n_indices;
+	const svo_draw *draws; /* always a host pointer */
+	uint32_t n_draws;
+} svo_mesh;
+
+/* A power-of-two sub-cube of the grid (octant sharding): the cube of side
+ * 2^(level - shard_level) voxels whose origin is cube_index * side.  Fragments are emitted in
+ * cube-local coordinates; the builder then builds the (level - shard_level)-deep subtree. */
+typedef struct svo_shard {
+	uint32_t shard_level;   /* 0 = whole grid */
+	uint32_t cube_index[3]; /* each < 2^shard_level */
+} svo_shard;
+
+typedef struct svo_scene svo_scene;
+typedef struct svo_voxelizer svo_voxelizer;
+typedef struct svo_builder svo_builder;
+
+/* ---- library ------------------------------------------------------------------------------- */
+SVO_API const char *svo_last_error(void);
+SVO_API const char *svo_version(void);
+SVO_API int svo_device_count(void); /* < 0: CUDA unavailable */
+
+/* ---- Scene (input side) -------------------------------------------------------------------
+ * Replaces the GPU-buffer half of Scene::Create / load_buffers_and_draw_cmd
+ * (src/Scene.cpp:145-223,387-417): uploads (or borrows) vertex/index buffers and keeps the draw
+ * list.  Host pointers may be released when the call returns if they are pageable; pinned host
+ * memory must stay valid until the stream has run the copy. */
+SVO_API int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene **out);
+SVO_API void svo_scene_destroy(svo_scene *scene);
+SVO_API uint64_t svo_scene_triangle_count(const svo_scene *scene);
+
+/* ---- Voxelizer ----------------------------------------------------------------------------
+ * svo_voxelizer_create = Voxelizer::Create (src/Voxelizer.hpp:43-45, src/Voxelizer.cpp:5-26):
+ * synchronous; runs the count pass (src/Voxelizer.cpp:134-165) and allocates the exact-size
+ * fragment list, so svo_voxelizer_fragment_count() is final when it returns.
+ * shard may be NULL (whole grid). */
+SVO_API int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, void *stream,
+                                 svo_voxelizer **out);
+SVO_API void svo_voxelizer_destroy(svo_voxelizer *vox);
+/* Voxelizer::CmdVoxelize (src/Voxelizer.hpp:49, src/Voxelizer.cpp:167-179): enqueues the fragment
+ * emission on the stream (the reference records it into a command buffer). */
+SVO_API int svo_voxelizer_voxelize(svo_voxelizer *vox, void *stream);
+SVO_API uint32_t svo_voxelizer_level(const svo_voxelizer *vox);            /* Voxelizer::GetLevel */
+SVO_API uint32_t svo_voxelizer_resolution(const svo_voxelizer *vox);       /* Voxelizer::GetVoxelResolution */
+SVO_API uint64_t svo_voxelizer_fragment_count(const svo_voxelizer *vox);   /* Voxelizer::GetVoxelFragmentCount */
+/* Voxelizer::GetVoxelFragmentList (src/Voxelizer.hpp:52): DEVICE pointer to fragment_count 64-bit
+ * fragments, (morton(x,y,z) << 24) | rgb, morton slot order x | y<<1 | z<<2 per level
+ * (shader/octree_tag_node.comp:24-25), in triangle order. */
+SVO_API const uint64_t *svo_voxelizer_fragments(const svo_voxelizer *vox);
+/* The reference's own fragment packing (shader/voxelizer.frag:40-42, uvec2 per fragment, levels
+ * <= 12): converts the fragment list into d_out (DEVICE, fragment_count * 8 bytes) on the stream. */
+SVO_API int svo_voxelizer_export_reference_fragments(const svo_voxelizer *vox, uint32_t *d_out, void *stream);
+
+/* ---- OctreeBuilder ------------------------------------------------------------------------
+ * svo_builder_create = OctreeBuilder::Create (src/OctreeBuilder.hpp:36-37, src/OctreeBuilder.cpp:8-22). */
+SVO_API int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out);
+SVO_API void svo_builder_destroy(svo_builder *b);
+/* OctreeBuilder::CmdBuild (src/OctreeBuilder.hpp:41, src/OctreeBuilder.cpp:142-210): enqueues sort,
+ * de-duplication and the level build.  The octree buffer is sized exactly, which costs one
+ * internal stream synchronisation mid-build (the reference guesses the size, OctreeBuilder.cpp:42-45). */
+SVO_API int svo_builder_build(svo_builder *b, void *stream);
+SVO_API uint32_t svo_builder_level(const svo_builder *b); /* OctreeBuilder::GetLevel */
+/* OctreeBuilder::GetOctreeRange (src/OctreeBuilder.hpp:42, src/OctreeBuilder.cpp:212-214): bytes. */
+SVO_API uint64_t svo_builder_octree_range_bytes(const svo_builder *b);
+/* OctreeBuilder::GetOctree (src/OctreeBuilder.hpp:43): DEVICE pointer to the node words in the
+ * reference layout (shader/octree.glsl:87-110): 0 empty; 0x80000000|child_block_word_index
+ * internal; 0xC0000000|min(n,63)<<24|BGR leaf; root block at word 0; levels in contiguous windows
+ * top-down, Morton order inside a level. */
+SVO_API const uint32_t *svo_builder_octree(const svo_builder *b);
+SVO_API uint64_t svo_builder_leaf_count(const svo_builder *b);
+/* node counts per depth: out[d] = non-empty nodes at depth d, d = 0..level (out[0] = 1 if any) */
+SVO_API int svo_builder_level_counts(const svo_builder *b, uint64_t *out, uint32_t n_out);
+/* Multi-GPU stitch support: add `base_words` to every internal node's child pointer
+ * while copying the subtree's blocks 1.. (the subtree's root block excluded: its 8 words become the
+ * parent's child block) -- see sparsevoxeloctree_b200/sharded.py.  dst may be peer (P2P/IPC) memory. */
+SVO_API int svo_builder_rebase_copy(const svo_builder *b, uint32_t *d_dst, uint64_t dst_word_offset,
+                                    uint32_t base_words, void *stream);
+
+/* ---- timing (LoaderThread.cpp:57-97 writes 4 GPU timestamps around CmdVoxelize / CmdBuild) -- */
+enum { SVO_PHASE_RASTER = 0, SVO_PHASE_SORT = 1, SVO_PHASE_REDUCE = 2, SVO_PHASE_LEVELS = 3, SVO_PHASE_EMIT = 4,
+       SVO_PHASE_COUNT = 5 };
+/* Milliseconds of the last voxelize (RASTER) / build (others), from cudaEvents on the call's stream.
+ * Synchronises on the recorded events.  sort_passes receives the number of radix passes. */
+SVO_API int svo_voxelizer_last_ms(svo_voxelizer *vox, float *raster_ms);
+SVO_API int svo_builder_last_ms(svo_builder *b, float *phase_ms /*[SVO_PHASE_COUNT]*/, uint32_t *sort_passes);
+
+/* ---- single kernels, exposed so the parity tests can exercise them in isolation ------------- */
+/* Stable LSD radix sort of n 64-bit keys on bits [begin_bit, end_bit); d_keys is sorted in place
+ * (d_tmp: n keys of scratch). */
+SVO_API int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_bit, uint32_t end_bit,
+                         int device, void *stream);
+
+/* ---- plain device memory helpers for callers without a CUDA binding (tests, ctypes) --------- */
+SVO_API int svo_device_malloc(int device, uint64_t bytes, void **out);
+SVO_API int svo_device_free(int device, void *ptr);
+SVO_API int svo_memcpy_h2d(int device, void *d_dst, const void *h_src, uint64_t bytes, void *stream);
+SVO_API int svo_memcpy_d2h(int device, void *h_dst, const void *d_src, uint64_t bytes, void *stream);
+SVO_API int svo_stream_synchronize(int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H */

@@ -1,0 +1,402 @@
+"""Host-side Python mirror of the reference's SVO construction classes, over the C ABI of include/svo.h.
+
+Class and method names follow the reference (src/Scene.hpp, src/Voxelizer.hpp:43-52,
+src/OctreeBuilder.hpp:36-48, src/Octree.hpp:18-33) so that callers -- and the parity tests -- read like
+the reference's own loader (src/LoaderThread.cpp:51-89):
+
+    scene     = Scene.Create(mesh)
+    voxelizer = Voxelizer.Create(scene, octree_level)
+    builder   = OctreeBuilder.Create(voxelizer)
+    voxelizer.CmdVoxelize(stream); builder.CmdBuild(stream)
+    octree.Update(builder)
+
+All compute happens in libsvo_b200.so (hand-written sm_100a CUDA).  There is no Python or CPU fallback:
+if the library is missing or no CUDA device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
+
+CENTER, CONSERVATIVE_EXACT = 0, 1
+PHASES = ("raster", "sort", "reduce", "levels", "emit")
+
+
+class SvoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"svo error {code}: {msg}")
+        self.code = code
+
+
+class svo_draw(C.Structure):
+    _fields_ = [("first_index", C.c_uint32), ("index_count", C.c_uint32), ("texture_id", C.c_uint32),
+                ("albedo_rgba8", C.c_uint32)]
+
+
+class svo_mesh(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("position_stride_bytes", C.c_uint32), ("on_device", C.c_uint32),
+                ("indices", C.c_void_p), ("n_vertices", C.c_uint64), ("n_indices", C.c_uint64),
+                ("draws", C.POINTER(svo_draw)), ("n_draws", C.c_uint32)]
+
+
+class svo_shard(C.Structure):
+    _fields_ = [("shard_level", C.c_uint32), ("cube_index", C.c_uint32 * 3)]
+
+
+# every symbol include/svo.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ("svo_last_error", C.c_char_p, []),
+    ("svo_version", C.c_char_p, []),
+    ("svo_device_count", C.c_int, []),
+    ("svo_scene_create", C.c_int, [C.POINTER(svo_mesh), C.c_int, _P, C.POINTER(_P)]),
+    ("svo_scene_destroy", None, [_P]),
+    ("svo_scene_triangle_count", C.c_uint64, [_P]),
+    ("svo_voxelizer_create", C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(svo_shard), _P, C.POINTER(_P)]),
+    ("svo_voxelizer_destroy", None, [_P]),
+    ("svo_voxelizer_voxelize", C.c_int, [_P, _P]),
+    ("svo_voxelizer_level", C.c_uint32, [_P]),
+    ("svo_voxelizer_resolution", C.c_uint32, [_P]),
+    ("svo_voxelizer_fragment_count", C.c_uint64, [_P]),
+    ("svo_voxelizer_fragments", _P, [_P]),
+    ("svo_voxelizer_export_reference_fragments", C.c_int, [_P, _P, _P]),
+    ("svo_builder_create", C.c_int, [_P, _P, C.POINTER(_P)]),
+    ("svo_builder_destroy", None, [_P]),
+    ("svo_builder_build", C.c_int, [_P, _P]),
+    ("svo_builder_level", C.c_uint32, [_P]),
+    ("svo_builder_octree_range_bytes", C.c_uint64, [_P]),
+    ("svo_builder_octree", _P, [_P]),
+    ("svo_builder_leaf_count", C.c_uint64, [_P]),
+    ("svo_builder_level_counts", C.c_int, [_P, C.POINTER(C.c_uint64), C.c_uint32]),
+    ("svo_builder_rebase_copy", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P]),
+    ("svo_voxelizer_last_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
+    ("svo_builder_last_ms", C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    ("svo_sort_u64", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P]),
+    ("svo_device_malloc", C.c_int, [C.c_int, C.c_uint64, C.POINTER(_P)]),
+    ("svo_device_free", C.c_int, [C.c_int, _P]),
+    ("svo_memcpy_h2d", C.c_int, [C.c_int, _P, _P, C.c_uint64, _P]),
+    ("svo_memcpy_d2h", C.c_int, [C.c_int, _P, _P, C.c_uint64, _P]),
+    ("svo_stream_synchronize", C.c_int, [C.c_int, _P]),
+]
+
+
+class Library:
+    """A loaded libsvo_b200.so with typed prototypes."""
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, res, args in SYMBOLS:
+            fn = getattr(self.dll, name)  # AttributeError = ABI symbol missing
+            fn.restype, fn.argtypes = res, args
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise SvoError(rc, self.dll.svo_last_error().decode())
+
+    # --- raw device memory helpers (tests / callers without a CUDA binding) ---
+    def malloc(self, nbytes: int, device: int = 0) -> int:
+        p = _P()
+        self.check(self.dll.svo_device_malloc(device, nbytes, C.byref(p)))
+        return p.value or 0
+
+    def free(self, ptr: int, device: int = 0):
+        self.check(self.dll.svo_device_free(device, ptr))
+
+    def to_device(self, arr: np.ndarray, device: int = 0, stream: int = 0) -> int:
+        arr = np.ascontiguousarray(arr)
+        p = self.malloc(max(arr.nbytes, 1), device)
+        if arr.nbytes:
+            self.check(self.dll.svo_memcpy_h2d(device, p, arr.ctypes.data, arr.nbytes, stream))
+            self.check(self.dll.svo_stream_synchronize(device, stream))
+        return p
+
+    def to_host(self, ptr: int, dtype, count: int, device: int = 0, stream: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        if count:
+            self.check(self.dll.svo_memcpy_d2h(device, out.ctypes.data, ptr, out.nbytes, stream))
+        return out
+
+    def sort_u64(self, keys: np.ndarray, begin_bit: int, end_bit: int, device: int = 0) -> np.ndarray:
+        """svo_sort_u64 on a host array (test helper)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        d = self.to_device(keys, device)
+        t = self.malloc(max(keys.nbytes, 8), device)
+        try:
+            self.check(self.dll.svo_sort_u64(d, t, len(keys), begin_bit, end_bit, device, 0))
+            return self.to_host(d, np.uint64, len(keys), device)
+        finally:
+            self.free(d, device)
+            self.free(t, device)
+
+
+_default = None
+
+
+def get_library() -> Library:
+    """The in-tree CUDA library.  Raises when it has not been built -- the product never substitutes anything."""
+    global _default
+    if _default is None:
+        _default = Library(LIB_PATH)
+    return _default
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        return 0
+    if hasattr(stream, "cuda_stream"):  # torch.cuda.Stream
+        return int(stream.cuda_stream)
+    return int(stream)
+
+
+class Scene:
+    """Mesh hand-off standing in for the reference Scene (src/Scene.hpp): vertex/index buffers + draw list on the
+    device.  `positions` may be [V,3] (tight) or [V,5] (pos+uv, the reference Vertex of src/Scene.cpp:16-19)."""
+
+    def __init__(self):
+        self._h = None
+
+    @staticmethod
+    def Create(mesh_or_positions, indices=None, draws=None, device: int = 0, stream=None, lib: Library | None = None):
+        lib = lib or get_library()
+        if indices is None:
+            m = mesh_or_positions
+            positions, indices, draws = m.positions, m.indices, m.draws
+        else:
+            positions = mesh_or_positions
+        self = Scene()
+        self.lib, self.device = lib, device
+        self._positions = np.ascontiguousarray(positions, dtype=np.float32)
+        self._indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        d = np.ascontiguousarray(draws)
+        self._draws = (svo_draw * len(d))(*[svo_draw(int(r["first_index"]), int(r["index_count"]), int(r["texture_id"]),
+                                                     int(r["albedo_rgba8"])) for r in d])
+        if self._positions.ndim != 2 or self._positions.shape[1] < 3:
+            raise ValueError("positions must be [V, >=3] float32")
+        m = svo_mesh(self._positions.ctypes.data, self._positions.shape[1] * 4, 0, self._indices.ctypes.data,
+                     len(self._positions), len(self._indices), self._draws, len(d))
+        h = _P()
+        lib.check(lib.dll.svo_scene_create(C.byref(m), device, _stream_ptr(stream), C.byref(h)))
+        self._h = h
+        return self
+
+    @staticmethod
+    def CreateFromDevice(d_positions: int, stride: int, n_vertices: int, d_indices: int, n_indices: int, draws,
+                         device: int = 0, stream=None, lib: Library | None = None):
+        """Borrow vertex/index buffers that already live on the device (e.g. torch tensors' data_ptr())."""
+        lib = lib or get_library()
+        self = Scene()
+        self.lib, self.device = lib, device
+        d = np.ascontiguousarray(draws)
+        self._draws = (svo_draw * len(d))(*[svo_draw(int(r["first_index"]), int(r["index_count"]), int(r["texture_id"]),
+                                                     int(r["albedo_rgba8"])) for r in d])
+        m = svo_mesh(d_positions, stride, 1, d_indices, n_vertices, n_indices, self._draws, len(d))
+        h = _P()
+        lib.check(lib.dll.svo_scene_create(C.byref(m), device, _stream_ptr(stream), C.byref(h)))
+        self._h = h
+        return self
+
+    def GetTriangleCount(self) -> int:
+        return int(self.lib.dll.svo_scene_triangle_count(self._h))
+
+    def Destroy(self):
+        if self._h:
+            self.lib.dll.svo_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Destroy()
+        except Exception:
+            pass
+
+
+class Voxelizer:
+    """src/Voxelizer.hpp.  Create() runs the count pass and sizes the fragment list (Voxelizer.cpp:134-165);
+    CmdVoxelize() enqueues the fragment emission (Voxelizer.cpp:167-179)."""
+
+    def __init__(self):
+        self._h = None
+
+    @staticmethod
+    def Create(scene: Scene, octree_level: int, mode: int = CONSERVATIVE_EXACT, shard=None, stream=None):
+        self = Voxelizer()
+        self.lib, self.device, self._scene = scene.lib, scene.device, scene
+        sh = None
+        if shard is not None:
+            lvl, (cx, cy, cz) = shard
+            sh = svo_shard(lvl, (C.c_uint32 * 3)(cx, cy, cz))
+        h = _P()
+        self.lib.check(self.lib.dll.svo_voxelizer_create(scene._h, octree_level, mode, C.byref(sh) if sh else None,
+                                                         _stream_ptr(stream), C.byref(h)))
+        self._h = h
+        self.shard = shard
+        return self
+
+    def GetScenePtr(self) -> Scene:
+        return self._scene
+
+    def GetLevel(self) -> int:
+        return int(self.lib.dll.svo_voxelizer_level(self._h))
+
+    def GetVoxelResolution(self) -> int:
+        return int(self.lib.dll.svo_voxelizer_resolution(self._h))
+
+    def GetVoxelFragmentCount(self) -> int:
+        return int(self.lib.dll.svo_voxelizer_fragment_count(self._h))
+
+    def GetVoxelFragmentList(self) -> int:
+        """Device pointer to GetVoxelFragmentCount() 64-bit fragments: morton << 24 | rgb."""
+        return int(self.lib.dll.svo_voxelizer_fragments(self._h) or 0)
+
+    def CmdVoxelize(self, stream=None):
+        self.lib.check(self.lib.dll.svo_voxelizer_voxelize(self._h, _stream_ptr(stream)))
+
+    def LastMs(self) -> float:
+        ms = C.c_float()
+        self.lib.check(self.lib.dll.svo_voxelizer_last_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    # --- test / debugging helpers -------------------------------------------------------------------------
+    def fragments_to_host(self, stream=None) -> np.ndarray:
+        return self.lib.to_host(self.GetVoxelFragmentList(), np.uint64, self.GetVoxelFragmentCount(), self.device,
+                                _stream_ptr(stream))
+
+    def reference_fragments_to_host(self, stream=None) -> np.ndarray:
+        """The fragment list in the reference's uvec2 packing (voxelizer.frag:40-42): uint32 [F, 2]."""
+        n = self.GetVoxelFragmentCount()
+        d = self.lib.malloc(max(n * 8, 8), self.device)
+        try:
+            self.lib.check(self.lib.dll.svo_voxelizer_export_reference_fragments(self._h, d, _stream_ptr(stream)))
+            return self.lib.to_host(d, np.uint32, n * 2, self.device, _stream_ptr(stream)).reshape(n, 2)
+        finally:
+            self.lib.free(d, self.device)
+
+    def Destroy(self):
+        if self._h:
+            self.lib.dll.svo_voxelizer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Destroy()
+        except Exception:
+            pass
+
+
+class OctreeBuilder:
+    """src/OctreeBuilder.hpp.  CmdBuild() enqueues sort + reduce + level build; GetOctreeRange() is the byte
+    range of the node buffer (OctreeBuilder.cpp:212-214), GetOctree() the device pointer the tracer binds."""
+
+    def __init__(self):
+        self._h = None
+
+    @staticmethod
+    def Create(voxelizer: Voxelizer, stream=None):
+        self = OctreeBuilder()
+        self.lib, self.device, self._vox = voxelizer.lib, voxelizer.device, voxelizer
+        h = _P()
+        self.lib.check(self.lib.dll.svo_builder_create(voxelizer._h, _stream_ptr(stream), C.byref(h)))
+        self._h = h
+        return self
+
+    def GetVoxelizerPtr(self) -> Voxelizer:
+        return self._vox
+
+    def GetLevel(self) -> int:
+        return int(self.lib.dll.svo_builder_level(self._h))
+
+    def CmdBuild(self, stream=None):
+        self.lib.check(self.lib.dll.svo_builder_build(self._h, _stream_ptr(stream)))
+
+    def GetOctreeRange(self) -> int:
+        return int(self.lib.dll.svo_builder_octree_range_bytes(self._h))
+
+    def GetOctree(self) -> int:
+        return int(self.lib.dll.svo_builder_octree(self._h) or 0)
+
+    def CmdTransferOctreeOwnership(self, *args, **kwargs):
+        """Queue-family ownership transfer (OctreeBuilder.cpp:215-220): nothing to do for a CUDA-produced buffer
+        (external memory is acquired from VK_QUEUE_FAMILY_EXTERNAL on the Vulkan side)."""
+        return None
+
+    def GetLeafCount(self) -> int:
+        return int(self.lib.dll.svo_builder_leaf_count(self._h))
+
+    def GetLevelCounts(self):
+        n = self.GetLevel() + 1
+        out = (C.c_uint64 * n)()
+        self.lib.check(self.lib.dll.svo_builder_level_counts(self._h, out, n))
+        return [int(v) for v in out]
+
+    def LastMs(self):
+        ms = (C.c_float * len(PHASES))()
+        np_ = C.c_uint32()
+        self.lib.check(self.lib.dll.svo_builder_last_ms(self._h, ms, C.byref(np_)))
+        return {k: float(ms[i]) for i, k in enumerate(PHASES)}, int(np_.value)
+
+    def RebaseCopy(self, d_dst: int, dst_word_offset: int, base_words: int, stream=None):
+        self.lib.check(self.lib.dll.svo_builder_rebase_copy(self._h, d_dst, dst_word_offset, base_words, _stream_ptr(stream)))
+
+    def octree_to_host(self, stream=None) -> np.ndarray:
+        return self.lib.to_host(self.GetOctree(), np.uint32, self.GetOctreeRange() // 4, self.device, _stream_ptr(stream))
+
+    def Destroy(self):
+        if self._h:
+            self.lib.dll.svo_builder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Destroy()
+        except Exception:
+            pass
+
+
+class Octree:
+    """src/Octree.hpp: the hand-off object the tracers read.  Update() takes the builder's buffer, range and level
+    (Octree.cpp:22-35); the builder is kept alive because it owns the device allocation."""
+
+    def __init__(self):
+        self.m_buffer, self.m_range, self.m_level, self._builder = 0, 0, 0, None
+
+    @staticmethod
+    def Create():
+        return Octree()
+
+    def Update(self, builder: OctreeBuilder):
+        self._builder = builder
+        self.m_buffer = builder.GetOctree()
+        self.m_level = builder.GetLevel()
+        self.m_range = builder.GetOctreeRange()
+
+    def Empty(self) -> bool:
+        return self.m_buffer == 0
+
+    def GetBuffer(self) -> int:
+        return self.m_buffer
+
+    def GetLevel(self) -> int:
+        return self.m_level
+
+    def GetRange(self) -> int:
+        return self.m_range
+
+
+def build_svo(mesh, level: int, mode: int = CONSERVATIVE_EXACT, device: int = 0, stream=None, lib: Library | None = None):
+    """The loader sequence of src/LoaderThread.cpp:51-89 in one call. Returns (scene, voxelizer, builder)."""
+    scene = Scene.Create(mesh, device=device, stream=stream, lib=lib)
+    vox = Voxelizer.Create(scene, level, mode, stream=stream)
+    builder = OctreeBuilder.Create(vox, stream=stream)
+    vox.CmdVoxelize(stream)
+    builder.CmdBuild(stream)
+    return scene, vox, builder

@@ -1,0 +1,251 @@
+// raster.cuh -- the Voxelizer kernels: triangle-parallel fixed-point rasterization into 64-bit Morton
+// fragments with count -> scan -> emit (no per-fragment global atomic; deterministic order).
+//
+// Replaces voxelizer.vert/.geom/.frag + the fixed-function rasterizer + the count pass
+// (src/Voxelizer.cpp:134-179).  Two work classes, decided per triangle from its candidate rectangle:
+//   small (area <= SMALL_AREA pixels): one thread walks the rectangle with exact integer edge tests;
+//   large: one warp computes exact per-row spans (integer division, no per-pixel tests); emission is
+//          output-parallel over the span pixels (load-balanced row search), so huge wall/floor triangles
+//          are spread over the whole GPU and stored with fully coalesced 8-byte writes.
+// Fragment order: all small-triangle fragments in triangle order, then all large-triangle fragments in
+// triangle / row / x order.  A voxel receives at most one fragment per triangle, so together with the
+// stable sort this fixes the colour-averaging order per voxel: (class, triangle id).
+#pragma once
+#include "scan.cuh"
+#include "svo_math.cuh"
+
+namespace svo {
+
+constexpr int64_t SMALL_AREA = 256; // candidate-rectangle pixels handled by a single thread
+constexpr int RASTER_BLOCK = 128;
+constexpr int EMIT_BLOCK = 256, EMIT_ITEMS = 8, EMIT_TILE = EMIT_BLOCK * EMIT_ITEMS;
+
+struct DrawRec {
+	uint32_t first_index, tri_base, tri_count, rgb;
+};
+struct SceneView {
+	const unsigned char *pos;
+	uint32_t stride;
+	const uint32_t *idx;
+	const DrawRec *draws;
+	uint32_t n_draws;
+	uint64_t n_tri;
+};
+struct RasterParams {
+	uint32_t res;       // 1 << level (full grid)
+	int mode;
+	ShardBox sb;        // voxel window, full-grid coordinates
+	uint32_t origin[3]; // sb.lo: fragments are emitted in shard-local coordinates
+};
+
+SVO_DEV uint32_t find_draw(const SceneView &sv, uint64_t t) {
+	uint32_t lo = 0, hi = sv.n_draws; // last draw with tri_base <= t
+	while (hi - lo > 1) {
+		uint32_t mid = (lo + hi) >> 1;
+		if (sv.draws[mid].tri_base <= t) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
+SVO_DEV bool load_and_setup(const SceneView &sv, const RasterParams &rp, uint64_t t, TriSetup &ts, uint32_t &rgb) {
+	const uint32_t d = find_draw(sv, t);
+	const DrawRec dr = sv.draws[d];
+	const uint32_t *ix = sv.idx + dr.first_index + 3u * (uint32_t)(t - dr.tri_base);
+	float p[3][3];
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		const float *v = reinterpret_cast<const float *>(sv.pos + (size_t)__ldg(ix + i) * sv.stride);
+		p[i][0] = __ldg(v), p[i][1] = __ldg(v + 1), p[i][2] = __ldg(v + 2);
+	}
+	rgb = dr.rgb;
+	return tri_setup(p[0], p[1], p[2], rp.res, rp.mode, rp.sb, ts);
+}
+
+SVO_DEV uint64_t make_fragment(const TriSetup &ts, const RasterParams &rp, int32_t px, int32_t py, uint32_t uz, uint32_t rgb) {
+	uint32_t vx, vy, vz;
+	unswizzle(ts.axis, (uint32_t)px, (uint32_t)py, uz, vx, vy, vz);
+	return (morton3(vx - rp.origin[0], vy - rp.origin[1], vz - rp.origin[2]) << 24) | (uint64_t)(rgb & 0xffffffu);
+}
+
+// ---- pass 1: classify + count small ------------------------------------------------------------------
+// cnt_small[t]  = fragments of a small triangle (0 for large / culled)
+// packed[t]     = (is_large << 40) | rows of a large triangle
+__global__ void __launch_bounds__(RASTER_BLOCK)
+    k_classify_count(SceneView sv, RasterParams rp, uint32_t *__restrict__ cnt_small, uint64_t *__restrict__ packed) {
+	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
+	if (t >= sv.n_tri) return;
+	TriSetup ts;
+	uint32_t rgb;
+	uint32_t cnt = 0;
+	uint64_t pk = 0;
+	if (load_and_setup(sv, rp, t, ts, rgb)) {
+		if (ts.full_area <= SMALL_AREA) {
+			for (int32_t py = ts.py0; py <= ts.py1; ++py)
+				for (int32_t px = ts.px0; px <= ts.px1; ++px)
+					if (pixel_covered(ts, px, py)) {
+						if (!ts.cull_depth || depth_in_window(ts, pixel_depth(ts, rp.res, px, py))) ++cnt;
+					}
+		} else
+			pk = (1ull << 40) | (uint64_t)(ts.py1 - ts.py0 + 1);
+	}
+	cnt_small[t] = cnt;
+	packed[t] = pk;
+}
+
+// ---- pass 1b: large triangles ---------------------------------------------------------------------------
+struct LargeTri {
+	TriSetup ts;
+	uint32_t rgb;
+	uint32_t tri;      // triangle id
+	uint32_t row_base; // first row in the (sparse) row arrays
+	uint32_t pad;
+};
+
+// gather the large triangles into a dense list (order = triangle order)
+__global__ void __launch_bounds__(RASTER_BLOCK)
+    k_large_collect(uint64_t n_tri, const uint64_t *__restrict__ packed, const uint64_t *__restrict__ lprefix,
+                    LargeTri *__restrict__ large) {
+	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
+	if (t >= n_tri) return;
+	if (packed[t] >> 40) {
+		const uint64_t p = lprefix[t];
+		LargeTri &lt = large[p >> 40];
+		lt.tri = (uint32_t)t;
+		lt.row_base = (uint32_t)(p & ((1ull << 40) - 1));
+	}
+}
+
+// one warp per large triangle: exact row spans.  row_pk[r] = (nonempty << 40) | len ; row_x0[r] = first pixel
+__global__ void __launch_bounds__(RASTER_BLOCK)
+    k_large_rows(SceneView sv, RasterParams rp, uint32_t n_large, LargeTri *__restrict__ large, uint64_t *__restrict__ row_pk,
+                 uint32_t *__restrict__ row_x0) {
+	const uint32_t li = (blockIdx.x * RASTER_BLOCK + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (li >= n_large) return; // whole warp leaves together
+	LargeTri &lt = large[li];
+	TriSetup ts;
+	uint32_t rgb;
+	load_and_setup(sv, rp, lt.tri, ts, rgb); // true by construction (classified large)
+	if (lane == 0) {
+		lt.ts = ts;
+		lt.rgb = rgb;
+	}
+	const int32_t h = ts.py1 - ts.py0 + 1;
+	for (int32_t r = lane; r < h; r += 32) {
+		int32_t x_lo, x_hi;
+		row_span(ts, ts.py0 + r, x_lo, x_hi);
+		row_span_depth_window(ts, rp.res, ts.py0 + r, x_lo, x_hi);
+		const uint32_t len = x_hi >= x_lo ? (uint32_t)(x_hi - x_lo + 1) : 0u;
+		row_pk[lt.row_base + r] = len ? ((1ull << 40) | len) : 0ull;
+		row_x0[lt.row_base + r] = (uint32_t)x_lo;
+	}
+}
+
+// dense non-empty rows: off (first large-fragment ordinal), x0 | y << 16, owning large triangle
+struct DenseRows {
+	uint32_t *off; // n_rows + 1
+	uint32_t *xy;
+	uint32_t *li;
+};
+__global__ void __launch_bounds__(RASTER_BLOCK)
+    k_rows_compact(uint32_t n_large, const LargeTri *__restrict__ large, const uint64_t *__restrict__ row_pk,
+                   const uint32_t *__restrict__ row_x0, const uint64_t *__restrict__ rprefix, uint64_t n_rows_sparse,
+                   DenseRows out) {
+	// one warp per large triangle again, so that a row knows its triangle without a search
+	const uint32_t li = (blockIdx.x * RASTER_BLOCK + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (li >= n_large) return;
+	const LargeTri &lt = large[li];
+	const int32_t h = lt.ts.py1 - lt.ts.py0 + 1;
+	for (int32_t r = lane; r < h; r += 32) {
+		const uint64_t s = (uint64_t)lt.row_base + r;
+		if (row_pk[s] >> 40) {
+			const uint64_t p = rprefix[s];
+			const uint32_t k = (uint32_t)(p >> 40);
+			out.off[k] = (uint32_t)(p & ((1ull << 40) - 1));
+			out.xy[k] = row_x0[s] | ((uint32_t)(lt.ts.py0 + r) << 16);
+			out.li[k] = li;
+		}
+	}
+	if (li == 0 && lane == 0) {
+		const uint64_t tot = rprefix[n_rows_sparse];
+		out.off[tot >> 40] = (uint32_t)(tot & ((1ull << 40) - 1));
+	}
+}
+
+// ---- pass 2: emit ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RASTER_BLOCK)
+    k_emit_small(SceneView sv, RasterParams rp, const uint64_t *__restrict__ tri_off, uint64_t *__restrict__ frags) {
+	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
+	if (t >= sv.n_tri) return;
+	const uint64_t o0 = tri_off[t], o1 = tri_off[t + 1];
+	if (o0 == o1) return; // large, culled or empty
+	TriSetup ts;
+	uint32_t rgb;
+	if (!load_and_setup(sv, rp, t, ts, rgb)) return;
+	uint64_t o = o0;
+	for (int32_t py = ts.py0; py <= ts.py1; ++py)
+		for (int32_t px = ts.px0; px <= ts.px1; ++px)
+			if (pixel_covered(ts, px, py)) {
+				const uint32_t uz = pixel_depth(ts, rp.res, px, py);
+				if (depth_in_window(ts, uz)) frags[o++] = make_fragment(ts, rp, px, py, uz, rgb);
+			}
+}
+
+// output-parallel expansion of the dense row spans: fragment ordinal j -> (row, x)
+__global__ void __launch_bounds__(EMIT_BLOCK)
+    k_emit_large(RasterParams rp, const LargeTri *__restrict__ large, DenseRows rows, uint32_t n_rows, uint64_t n_frag_large,
+                 uint64_t *__restrict__ frags /* already offset to the large region */) {
+	__shared__ uint32_t s_off[EMIT_TILE + 2];
+	__shared__ uint32_t s_first;
+	const uint64_t c0 = (uint64_t)blockIdx.x * EMIT_TILE;
+	const uint64_t c1 = c0 + EMIT_TILE < n_frag_large ? c0 + EMIT_TILE : n_frag_large;
+	if (threadIdx.x == 0) {
+		// last row with off <= c0 (rows are non-empty, so it contains fragment c0)
+		uint32_t lo = 0, hi = n_rows;
+		while (hi - lo > 1) {
+			uint32_t mid = lo + ((hi - lo) >> 1);
+			if (rows.off[mid] <= c0) lo = mid; else hi = mid;
+		}
+		s_first = lo;
+	}
+	__syncthreads();
+	const uint32_t r_first = s_first;
+	// stage the offsets of the rows that intersect [c0, c1): at most EMIT_TILE rows (+1 end sentinel)
+	for (uint32_t i = threadIdx.x; i < EMIT_TILE + 1; i += EMIT_BLOCK) {
+		const uint32_t r = r_first + i;
+		s_off[i] = r <= n_rows ? rows.off[r] : 0xffffffffu;
+	}
+	__syncthreads();
+#pragma unroll 1
+	for (int it = 0; it < EMIT_ITEMS; ++it) {
+		const uint64_t j = c0 + (uint64_t)it * EMIT_BLOCK + threadIdx.x;
+		if (j >= c1) break;
+		// last staged row with off <= j
+		uint32_t lo = 0, hi = EMIT_TILE + 1;
+		while (hi - lo > 1) {
+			uint32_t mid = (lo + hi) >> 1;
+			if (s_off[mid] <= j) lo = mid; else hi = mid;
+		}
+		const uint32_t r = r_first + lo;
+		const uint32_t xy = rows.xy[r];
+		const LargeTri &lt = large[rows.li[r]];
+		const int32_t px = (int32_t)(xy & 0xffffu) + (int32_t)(j - s_off[lo]);
+		const int32_t py = (int32_t)(xy >> 16);
+		const uint32_t uz = pixel_depth(lt.ts, rp.res, px, py);
+		frags[j] = make_fragment(lt.ts, rp, px, py, uz, lt.rgb);
+	}
+}
+
+// voxelizer.frag:40-42 packing of our fragments (levels <= 12), for consumers of the reference format
+__global__ void __launch_bounds__(256)
+    k_export_reference_fragments(const uint64_t *__restrict__ frags, uint64_t n, uint2 *__restrict__ out) {
+	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t f = frags[i];
+	const uint64_t m = f >> 24;
+	const uint32_t x = compact1by2(m), y = compact1by2(m >> 1), z = compact1by2(m >> 2);
+	out[i] = make_uint2(x | (y << 12) | ((z & 0xffu) << 24), ((z >> 8) << 28) | (uint32_t)(f & 0xffffffu));
+}
+
+} // namespace svo

@@ -1,0 +1,629 @@
+// svo_b200.cu -- the C ABI of include/svo.h over the sm_100a kernels (single translation unit).
+//
+// Host-side orchestration only: it owns device buffers, enqueues the kernels of raster.cuh / sort.cuh /
+// build.cuh on the caller's stream and reads back the few scalars that size the next allocation.
+// There is no CPU implementation of any phase here: without a CUDA device every entry point fails.
+#include "../../include/svo.h"
+
+#include <stdarg.h>
+
+#include <new>
+#include <vector>
+
+#include "build.cuh"
+#include "raster.cuh"
+#include "sort.cuh"
+
+namespace svo {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+int dev_alloc(void **p, uint64_t bytes, cudaStream_t s) {
+	SVO_CUDA_TRY(cudaMallocAsync(p, bytes, s));
+	return 0;
+}
+void dev_free(void *p, cudaStream_t s) {
+	if (p) cudaFreeAsync(p, s);
+}
+
+#ifndef SVO_EMU
+int configure_device_pool(int device) {
+	static bool done[64] = {};
+	if (device < 0 || device >= 64 || done[device]) return 0;
+	cudaMemPool_t pool;
+	SVO_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+	uint64_t thr = UINT64_MAX; // keep freed blocks cached: build/destroy cycles do not hit the driver allocator
+	SVO_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	done[device] = true;
+	return 0;
+}
+int sm_count(int device) {
+	int n = 0;
+	if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 148;
+	return n;
+}
+#else
+int configure_device_pool(int) { return 0; }
+int sm_count(int) { return 4; }
+#endif
+
+struct DeviceGuard {
+	int prev = -1;
+	bool ok = true;
+	explicit DeviceGuard(int dev) {
+		if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+		if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+	}
+	~DeviceGuard() {
+		if (prev >= 0) cudaSetDevice(prev);
+	}
+};
+
+struct Timer {
+	cudaEvent_t a = nullptr, b = nullptr;
+	bool recorded = false;
+	int init() {
+		if (!a) {
+			SVO_CUDA_TRY(cudaEventCreate(&a));
+			SVO_CUDA_TRY(cudaEventCreate(&b));
+		}
+		return 0;
+	}
+	void destroy() {
+		if (a) cudaEventDestroy(a);
+		if (b) cudaEventDestroy(b);
+		a = b = nullptr;
+	}
+};
+
+} // namespace svo
+
+using namespace svo;
+
+struct svo_scene {
+	int device = 0;
+	SceneView view{};
+	std::vector<DrawRec> draws;
+	DevBuf<unsigned char> pos;
+	DevBuf<uint32_t> idx;
+	DevBuf<DrawRec> d_draws;
+	uint64_t n_vertices = 0;
+};
+
+struct svo_voxelizer {
+	svo_scene *scene = nullptr;
+	int device = 0;
+	uint32_t level = 0;       // full-grid level
+	uint32_t key_level = 0;   // level of the emitted (shard-local) keys
+	RasterParams rp{};
+	uint64_t n_frag = 0, n_frag_small = 0, n_frag_large = 0;
+	uint32_t n_large = 0, n_rows = 0;
+	DevBuf<uint64_t> tri_off; // n_tri + 1, small-class fragment offsets
+	DevBuf<LargeTri> large;
+	DevBuf<uint32_t> row_off, row_xy, row_li;
+	DevBuf<uint64_t> frags;
+	bool voxelized = false;
+	Timer t_raster;
+};
+
+struct svo_builder {
+	svo_voxelizer *vox = nullptr;
+	int device = 0;
+	uint32_t level = 0;
+	DevBuf<uint64_t> tmp;      // sort ping-pong partner of the fragment list
+	DevBuf<uint32_t> leaf;     // leaf words
+	DevBuf<uint32_t> first;    // pooled per-level first-child arrays
+	DevBuf<unsigned char> mask;
+	DevBuf<uint64_t> counts;   // device: node count per depth 0..level
+	DevBuf<uint64_t> lb_state;
+	DevBuf<uint32_t> tickets;
+	DevBuf<uint32_t> octree;
+	SortScratch sort_scratch;
+	uint64_t h_counts[MAX_LEVEL + 1] = {};
+	uint64_t range_bytes = 0;
+	uint32_t sort_passes = 0;
+	bool built = false;
+	cudaEvent_t ev[SVO_PHASE_COUNT + 1] = {};
+};
+
+static int fail(int code, const char *msg) {
+	set_error("%s", msg);
+	return code;
+}
+
+extern "C" {
+
+const char *svo_last_error(void) { return get_error(); }
+const char *svo_version(void) {
+#ifdef SVO_EMU
+	return "svo-b200 0.1 (CPU kernel-logic emulation build: tests only)";
+#else
+	return "svo-b200 0.1 (sm_100a)";
+#endif
+}
+int svo_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
+	return n;
+}
+
+// ------------------------------------------------------------------------------------------------------
+int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene **out) {
+	if (!mesh || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: null argument");
+	*out = nullptr;
+	if (mesh->position_stride_bytes < 12 || (mesh->position_stride_bytes & 3))
+		return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: position stride must be >= 12 and a multiple of 4");
+	if (mesh->n_indices % 3) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: index count is not a multiple of 3");
+	if ((mesh->n_indices && (!mesh->indices || !mesh->positions)) || (mesh->n_draws && !mesh->draws))
+		return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: null buffer");
+	DeviceGuard guard(device);
+	if (!guard.ok) return fail(SVO_ERR_CUDA, "svo_scene_create: cudaSetDevice failed (no CUDA device?)");
+	SVO_TRY(configure_device_pool(device));
+	cudaStream_t s = (cudaStream_t)stream;
+	svo_scene *sc = new (std::nothrow) svo_scene();
+	if (!sc) return fail(SVO_ERR_CUDA, "out of host memory");
+	sc->device = device;
+	sc->n_vertices = mesh->n_vertices;
+	uint64_t tri_base = 0;
+	for (uint32_t d = 0; d < mesh->n_draws; ++d) {
+		const svo_draw &dr = mesh->draws[d];
+		if (dr.texture_id != 0xffffffffu) {
+			delete sc;
+			return fail(SVO_ERR_UNSUPPORTED, "textured draws are not on the built path (SURVEY.md section 8 row f2)");
+		}
+		if ((uint64_t)dr.first_index + dr.index_count > mesh->n_indices || dr.index_count % 3) {
+			delete sc;
+			return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: draw range outside the index buffer");
+		}
+		if (dr.index_count == 0) continue;
+		DrawRec r;
+		r.first_index = dr.first_index;
+		r.tri_base = (uint32_t)tri_base;
+		r.tri_count = dr.index_count / 3;
+		r.rgb = dr.albedo_rgba8 & 0xffffffu;
+		sc->draws.push_back(r);
+		tri_base += r.tri_count;
+	}
+	if (tri_base >= (1ull << 32)) {
+		delete sc;
+		return fail(SVO_ERR_CAPACITY, "more than 2^32-1 triangles");
+	}
+	int rc = 0;
+	do {
+		if (mesh->on_device) {
+			sc->view.pos = (const unsigned char *)mesh->positions;
+			sc->view.idx = mesh->indices;
+		} else {
+			const uint64_t pbytes = mesh->n_vertices * (uint64_t)mesh->position_stride_bytes;
+			if ((rc = sc->pos.alloc(pbytes, s))) break;
+			if ((rc = sc->idx.alloc(mesh->n_indices, s))) break;
+			if (pbytes && cudaMemcpyAsync(sc->pos.p, mesh->positions, pbytes, cudaMemcpyHostToDevice, s) != cudaSuccess) rc = SVO_ERR_CUDA;
+			if (mesh->n_indices &&
+			    cudaMemcpyAsync(sc->idx.p, mesh->indices, mesh->n_indices * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+				rc = SVO_ERR_CUDA;
+			if (rc) {
+				set_error("svo_scene_create: host to device copy failed");
+				break;
+			}
+			sc->view.pos = sc->pos.p;
+			sc->view.idx = sc->idx.p;
+		}
+		if ((rc = sc->d_draws.alloc(sc->draws.size(), s))) break;
+		if (!sc->draws.empty() && cudaMemcpyAsync(sc->d_draws.p, sc->draws.data(), sc->draws.size() * sizeof(DrawRec),
+		                                          cudaMemcpyHostToDevice, s) != cudaSuccess) {
+			rc = fail(SVO_ERR_CUDA, "svo_scene_create: draw list copy failed");
+			break;
+		}
+		// the draw list is staged from a host vector owned by the scene: make the copy complete before returning
+		if (cudaStreamSynchronize(s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "svo_scene_create: stream sync failed");
+	} while (0);
+	if (rc) {
+		svo_scene_destroy(sc);
+		return rc;
+	}
+	sc->view.stride = mesh->position_stride_bytes;
+	sc->view.draws = sc->d_draws.p;
+	sc->view.n_draws = (uint32_t)sc->draws.size();
+	sc->view.n_tri = tri_base;
+	*out = sc;
+	return SVO_OK;
+}
+
+void svo_scene_destroy(svo_scene *sc) {
+	if (!sc) return;
+	DeviceGuard guard(sc->device);
+	sc->pos.release(0);
+	sc->idx.release(0);
+	sc->d_draws.release(0);
+	delete sc;
+}
+uint64_t svo_scene_triangle_count(const svo_scene *sc) { return sc ? sc->view.n_tri : 0; }
+
+// ------------------------------------------------------------------------------------------------------
+int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, void *stream, svo_voxelizer **out) {
+	if (!scene || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_create: null argument");
+	*out = nullptr;
+	if (mode != SVO_CENTER && mode != SVO_CONSERVATIVE_EXACT) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown raster mode");
+	uint32_t sl = shard ? shard->shard_level : 0;
+	if (level < 1 || level > 14 || sl >= level) return fail(SVO_ERR_INVALID_ARGUMENT, "level must be 1..14 and shard_level < level");
+	const uint32_t key_level = level - sl;
+	if (3 * key_level + 24 > 64) return fail(SVO_ERR_CAPACITY, "3*(level - shard_level) + 24 colour bits must fit 64-bit fragments: shard levels >= 14");
+	if (shard)
+		for (int k = 0; k < 3; ++k)
+			if (shard->cube_index[k] >= (1u << sl)) return fail(SVO_ERR_INVALID_ARGUMENT, "shard cube index out of range");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return fail(SVO_ERR_CUDA, "cudaSetDevice failed");
+	cudaStream_t s = (cudaStream_t)stream;
+	svo_voxelizer *v = new (std::nothrow) svo_voxelizer();
+	if (!v) return fail(SVO_ERR_CUDA, "out of host memory");
+	v->scene = scene;
+	v->device = scene->device;
+	v->level = level;
+	v->key_level = key_level;
+	v->rp.res = 1u << level;
+	v->rp.mode = mode == SVO_CENTER ? MODE_CENTER : MODE_CONSERVATIVE;
+	const uint32_t side = 1u << key_level;
+	for (int k = 0; k < 3; ++k) {
+		const uint32_t ci = shard ? shard->cube_index[k] : 0;
+		v->rp.sb.lo[k] = ci * side;
+		v->rp.sb.hi[k] = ci * side + side;
+		v->rp.origin[k] = ci * side;
+	}
+
+	// ---- the count pass (Voxelizer::count_and_create_fragment_list, src/Voxelizer.cpp:134-165) ----
+	const uint64_t T = scene->view.n_tri;
+	DevBuf<uint32_t> cnt_small, row_x0;
+	DevBuf<uint64_t> packed, lprefix, row_pk, rprefix;
+	ScanScratch ss;
+	int rc = 0;
+	do {
+		if ((rc = v->t_raster.init())) break;
+		if ((rc = v->tri_off.alloc(T + 1, s))) break;
+		if (T == 0) {
+			if (cudaMemsetAsync(v->tri_off.p, 0, sizeof(uint64_t), s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "memset failed");
+			break;
+		}
+		if ((rc = cnt_small.alloc(T, s)) || (rc = packed.alloc(T, s)) || (rc = lprefix.alloc(T + 1, s))) break;
+		const uint32_t tgrid = div_up(T, RASTER_BLOCK);
+		SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count, scene->view, v->rp, cnt_small.p, packed.p);
+		if ((rc = exclusive_scan((const uint32_t *)cnt_small.p, v->tri_off.p, T, ss, s))) break;
+		// (is_large << 40 | rows) scanned as one 64-bit word: large-triangle index and first row together
+		if ((rc = exclusive_scan((const uint64_t *)packed.p, lprefix.p, T, ss, s))) break;
+		uint64_t h_small = 0, h_lp = 0;
+		if (cudaMemcpyAsync(&h_small, v->tri_off.p + T, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+		    cudaMemcpyAsync(&h_lp, lprefix.p + T, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+		    cudaStreamSynchronize(s) != cudaSuccess) {
+			rc = fail(SVO_ERR_CUDA, "count pass failed");
+			set_error("count pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+		v->n_frag_small = h_small;
+		v->n_large = (uint32_t)(h_lp >> 40);
+		const uint64_t rows_sparse = h_lp & ((1ull << 40) - 1);
+		if (v->n_large) {
+			if (rows_sparse >= (1ull << 32)) {
+				rc = fail(SVO_ERR_CAPACITY, "too many rows");
+				break;
+			}
+			if ((rc = v->large.alloc(v->n_large, s)) || (rc = row_pk.alloc(rows_sparse, s)) || (rc = row_x0.alloc(rows_sparse, s)) ||
+			    (rc = rprefix.alloc(rows_sparse + 1, s)))
+				break;
+			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_large_collect, T, (const uint64_t *)packed.p, (const uint64_t *)lprefix.p, v->large.p);
+			const uint32_t wgrid = div_up((uint64_t)v->n_large * 32, RASTER_BLOCK);
+			SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_large_rows, scene->view, v->rp, v->n_large, v->large.p, row_pk.p, row_x0.p);
+			if ((rc = exclusive_scan((const uint64_t *)row_pk.p, rprefix.p, rows_sparse, ss, s))) break;
+			uint64_t h_rp = 0;
+			if (cudaMemcpyAsync(&h_rp, rprefix.p + rows_sparse, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+			    cudaStreamSynchronize(s) != cudaSuccess) {
+				rc = fail(SVO_ERR_CUDA, "row pass failed");
+				break;
+			}
+			v->n_rows = (uint32_t)(h_rp >> 40);
+			v->n_frag_large = h_rp & ((1ull << 40) - 1);
+			if ((rc = v->row_off.alloc((uint64_t)v->n_rows + 1, s)) || (rc = v->row_xy.alloc(v->n_rows, s)) ||
+			    (rc = v->row_li.alloc(v->n_rows, s)))
+				break;
+			DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
+			SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_rows_compact, v->n_large, (const LargeTri *)v->large.p, (const uint64_t *)row_pk.p,
+			                 (const uint32_t *)row_x0.p, (const uint64_t *)rprefix.p, rows_sparse, dr);
+		}
+		v->n_frag = v->n_frag_small + v->n_frag_large;
+		if (v->n_frag >= 0xffffffffull) {
+			rc = fail(SVO_ERR_CAPACITY, "more than 2^32-2 fragments (the reference's counter is 32-bit too)");
+			break;
+		}
+	} while (0);
+	if (!rc) rc = v->frags.alloc(v->n_frag, s);
+	if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(SVO_ERR_CUDA, "voxelizer count pass: kernel launch failed");
+	cnt_small.release(s), row_x0.release(s), packed.release(s), lprefix.release(s), row_pk.release(s), rprefix.release(s);
+	ss.state.release(s), ss.ticket.release(s);
+	if (rc) {
+		svo_voxelizer_destroy(v);
+		return rc;
+	}
+	*out = v;
+	return SVO_OK;
+}
+
+void svo_voxelizer_destroy(svo_voxelizer *v) {
+	if (!v) return;
+	DeviceGuard guard(v->device);
+	v->tri_off.release(0), v->large.release(0), v->row_off.release(0), v->row_xy.release(0), v->row_li.release(0), v->frags.release(0);
+	v->t_raster.destroy();
+	delete v;
+}
+
+int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
+	if (!v) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_voxelize: null handle");
+	DeviceGuard guard(v->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	const SceneView &sv = v->scene->view;
+	SVO_CUDA_TRY(cudaEventRecord(v->t_raster.a, s));
+	if (v->n_frag_small) {
+		SVO_LAUNCH_INDEP(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, s, k_emit_small, sv, v->rp, (const uint64_t *)v->tri_off.p, v->frags.p);
+	}
+	if (v->n_frag_large) {
+		DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
+		SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large, v->rp, (const LargeTri *)v->large.p, dr, v->n_rows,
+		           v->n_frag_large, v->frags.p + v->n_frag_small);
+	}
+	SVO_CUDA_TRY(cudaEventRecord(v->t_raster.b, s));
+	SVO_CUDA_TRY(cudaGetLastError());
+	v->t_raster.recorded = true;
+	v->voxelized = true;
+	return SVO_OK;
+}
+
+uint32_t svo_voxelizer_level(const svo_voxelizer *v) { return v ? v->level : 0; }
+uint32_t svo_voxelizer_resolution(const svo_voxelizer *v) { return v ? 1u << v->level : 0; }
+uint64_t svo_voxelizer_fragment_count(const svo_voxelizer *v) { return v ? v->n_frag : 0; }
+const uint64_t *svo_voxelizer_fragments(const svo_voxelizer *v) { return v ? v->frags.p : nullptr; }
+
+int svo_voxelizer_export_reference_fragments(const svo_voxelizer *v, uint32_t *d_out, void *stream) {
+	if (!v || !d_out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (v->key_level > 12) return fail(SVO_ERR_UNSUPPORTED, "the reference fragment packing holds 12 bits per axis (voxelizer.frag:40-42)");
+	if (!v->voxelized) return fail(SVO_ERR_NOT_READY, "voxelize first");
+	DeviceGuard guard(v->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	if (v->n_frag)
+		SVO_LAUNCH_INDEP(div_up(v->n_frag, 256), 256, s, k_export_reference_fragments, (const uint64_t *)v->frags.p, v->n_frag,
+		                 reinterpret_cast<uint2 *>(d_out));
+	SVO_CUDA_TRY(cudaGetLastError());
+	return SVO_OK;
+}
+
+int svo_voxelizer_last_ms(svo_voxelizer *v, float *raster_ms) {
+	if (!v || !raster_ms) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (!v->t_raster.recorded) return fail(SVO_ERR_NOT_READY, "voxelize first");
+	DeviceGuard guard(v->device);
+	SVO_CUDA_TRY(cudaEventSynchronize(v->t_raster.b));
+	SVO_CUDA_TRY(cudaEventElapsedTime(raster_ms, v->t_raster.a, v->t_raster.b));
+	return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
+	if (!vox || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_create: null argument");
+	*out = nullptr;
+	DeviceGuard guard(vox->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	svo_builder *b = new (std::nothrow) svo_builder();
+	if (!b) return fail(SVO_ERR_CUDA, "out of host memory");
+	b->vox = vox;
+	b->device = vox->device;
+	b->level = vox->key_level;
+	int rc = 0;
+	do {
+		for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
+			if (cudaEventCreate(&b->ev[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
+		if (rc) break;
+		const uint64_t F = vox->n_frag;
+		if ((rc = b->tmp.alloc(F, s)) || (rc = b->leaf.alloc(F, s)) || (rc = b->counts.alloc(MAX_LEVEL + 2, s))) break;
+		// pooled per-level arrays: the window of depth-d nodes has one entry per depth-(d-1) node, at most min(F, 8^(d-1))
+		uint64_t pool = 0;
+		for (uint32_t d = 1; d <= b->level; ++d) {
+			const uint64_t cap8 = d - 1 >= 11 ? UINT64_MAX : (1ull << (3 * (d - 1)));
+			pool += F < cap8 ? F : cap8;
+		}
+		if ((rc = b->first.alloc(pool, s)) || (rc = b->mask.alloc(pool, s))) break;
+		const uint64_t tiles = (F + CMP_TILE - 1) / CMP_TILE + 1;
+		if ((rc = b->lb_state.alloc(tiles * (b->level + 1), s)) || (rc = b->tickets.alloc(b->level + 2, s))) break;
+	} while (0);
+	if (rc) {
+		svo_builder_destroy(b);
+		return rc;
+	}
+	*out = b;
+	return SVO_OK;
+}
+
+void svo_builder_destroy(svo_builder *b) {
+	if (!b) return;
+	DeviceGuard guard(b->device);
+	b->tmp.release(0), b->leaf.release(0), b->first.release(0), b->mask.release(0), b->counts.release(0), b->lb_state.release(0);
+	b->tickets.release(0), b->octree.release(0);
+	b->sort_scratch.hist.release(0), b->sort_scratch.ticket.release(0), b->sort_scratch.state.release(0);
+	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
+		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+	delete b;
+}
+
+int svo_builder_build(svo_builder *b, void *stream) {
+	if (!b) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_build: null handle");
+	svo_voxelizer *v = b->vox;
+	if (!v->voxelized) return fail(SVO_ERR_NOT_READY, "svo_builder_build: voxelize first");
+	DeviceGuard guard(b->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	const uint64_t F = v->n_frag;
+	const uint32_t L = b->level;
+	const int n_sm = sm_count(b->device);
+	b->built = false;
+
+	// ---- sort by Morton code (stable) ----
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
+	uint64_t *sorted = v->frags.p;
+	SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, n_sm, s, &sorted, &b->sort_passes));
+	uint64_t *other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[1], s));
+
+	// ---- de-duplicate + colour reduce: keys of depth L ----
+	const uint64_t tiles_f = (F + CMP_TILE - 1) / CMP_TILE + 1;
+	SVO_CUDA_TRY(cudaMemsetAsync(b->lb_state.p, 0, tiles_f * (L + 1) * sizeof(uint64_t), s));
+	SVO_CUDA_TRY(cudaMemsetAsync(b->tickets.p, 0, (L + 2) * sizeof(uint32_t), s));
+	SVO_CUDA_TRY(cudaMemsetAsync(b->counts.p, 0, (MAX_LEVEL + 2) * sizeof(uint64_t), s));
+	uint32_t pgrid = (uint32_t)n_sm * 4u;
+	{
+		uint32_t g = (uint32_t)(tiles_f < pgrid ? tiles_f : pgrid);
+		SVO_LAUNCH(g, CMP_BLOCK, 0, s, k_dedup_reduce, (const uint64_t *)sorted, F, other, b->leaf.p, b->lb_state.p, b->tickets.p, b->counts.p + L);
+	}
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
+
+	// ---- levels L..1: unique parents, first child, child mask ----
+	// key buffers ping-pong between the two fragment-sized buffers (the sorted fragments are dead after the reduce)
+	uint64_t *kin = other, *kout = sorted;
+	uint64_t pool_off[MAX_LEVEL + 2] = {};
+	{
+		uint64_t off = 0;
+		for (uint32_t d = L; d >= 1; --d) {
+			pool_off[d] = off;
+			const uint64_t cap8 = d - 1 >= 11 ? UINT64_MAX : (1ull << (3 * (d - 1)));
+			const uint64_t cap = F < cap8 ? F : cap8;
+			const uint64_t in_cap8 = d >= 11 ? UINT64_MAX : (1ull << (3 * d));
+			const uint64_t in_cap = F < in_cap8 ? F : in_cap8;
+			const uint64_t tiles = (in_cap + CMP_TILE - 1) / CMP_TILE + 1;
+			uint32_t g = (uint32_t)(tiles < pgrid ? tiles : pgrid);
+			SVO_LAUNCH(g, CMP_BLOCK, 0, s, k_parent_compact, (const uint64_t *)kin, (const uint64_t *)(b->counts.p + d), kout,
+			           b->first.p + off, b->mask.p + off, b->lb_state.p + tiles_f * (L - d + 1), b->tickets.p + (L - d + 1), b->counts.p + d - 1);
+			off += cap;
+			uint64_t *t = kin;
+			kin = kout;
+			kout = t;
+		}
+	}
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
+
+	// ---- exact sizing: the one host round trip of the build ----
+	SVO_CUDA_TRY(cudaMemcpyAsync(b->h_counts, b->counts.p, (L + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+	SVO_CUDA_TRY(cudaStreamSynchronize(s));
+	EmitParams ep{};
+	ep.level = L;
+	uint64_t blocks = 1;
+	ep.block_base[1] = 0;
+	for (uint32_t d = 2; d <= L + 1; ++d) {
+		ep.block_base[d] = blocks;
+		if (d <= L) blocks += b->h_counts[d - 1];
+	}
+	ep.total_blocks = blocks;
+	if (blocks * 8 >= (1ull << 30)) return fail(SVO_ERR_CAPACITY, "octree needs >= 2^30 words: 30-bit child pointers (octree.glsl:110) cannot address it");
+	for (uint32_t d = 1; d <= L; ++d) {
+		ep.first[d] = b->first.p + pool_off[d];
+		ep.mask[d] = b->mask.p + pool_off[d];
+	}
+	ep.leaf = b->leaf.p;
+	SVO_TRY(b->octree.reserve(blocks * 8, s));
+	if (b->h_counts[L] == 0) {
+		SVO_CUDA_TRY(cudaMemsetAsync(b->octree.p, 0, 8 * sizeof(uint32_t), s)); // empty scene: a zeroed root block
+	} else {
+		SVO_LAUNCH_INDEP(div_up(blocks, 256), 256, s, k_emit_octree, ep, b->octree.p);
+	}
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[4], s));
+	SVO_CUDA_TRY(cudaGetLastError());
+	b->range_bytes = blocks * 8 * sizeof(uint32_t); // (counter + 1) * 8 * 4, src/OctreeBuilder.cpp:212-214
+	b->built = true;
+	return SVO_OK;
+}
+
+uint32_t svo_builder_level(const svo_builder *b) { return b ? b->level : 0; }
+uint64_t svo_builder_octree_range_bytes(const svo_builder *b) { return (b && b->built) ? b->range_bytes : 0; }
+const uint32_t *svo_builder_octree(const svo_builder *b) { return (b && b->built) ? b->octree.p : nullptr; }
+uint64_t svo_builder_leaf_count(const svo_builder *b) { return (b && b->built) ? b->h_counts[b->level] : 0; }
+int svo_builder_level_counts(const svo_builder *b, uint64_t *out, uint32_t n_out) {
+	if (!b || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (!b->built) return fail(SVO_ERR_NOT_READY, "build first");
+	for (uint32_t d = 0; d < n_out; ++d) out[d] = d <= b->level ? b->h_counts[d] : 0;
+	return SVO_OK;
+}
+
+int svo_builder_rebase_copy(const svo_builder *b, uint32_t *d_dst, uint64_t dst_word_offset, uint32_t base_words, void *stream) {
+	if (!b || !d_dst) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (!b->built) return fail(SVO_ERR_NOT_READY, "build first");
+	if ((dst_word_offset & 3) || (base_words & 7)) return fail(SVO_ERR_INVALID_ARGUMENT, "offsets must keep 8-word block alignment");
+	DeviceGuard guard(b->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	const uint64_t n_vec = b->range_bytes / 16;
+	SVO_LAUNCH_INDEP(div_up(n_vec, 256), 256, s, k_rebase_copy, reinterpret_cast<const uint4 *>(b->octree.p),
+	                 reinterpret_cast<uint4 *>(d_dst + dst_word_offset), n_vec, base_words);
+	SVO_CUDA_TRY(cudaGetLastError());
+	return SVO_OK;
+}
+
+int svo_builder_last_ms(svo_builder *b, float *phase_ms, uint32_t *sort_passes) {
+	if (!b || !phase_ms) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (!b->built) return fail(SVO_ERR_NOT_READY, "build first");
+	DeviceGuard guard(b->device);
+	SVO_CUDA_TRY(cudaEventSynchronize(b->ev[4]));
+	phase_ms[SVO_PHASE_RASTER] = 0.f;
+	if (b->vox->t_raster.recorded) SVO_CUDA_TRY(cudaEventElapsedTime(&phase_ms[SVO_PHASE_RASTER], b->vox->t_raster.a, b->vox->t_raster.b));
+	for (int i = 0; i < 4; ++i) SVO_CUDA_TRY(cudaEventElapsedTime(&phase_ms[SVO_PHASE_SORT + i], b->ev[i], b->ev[i + 1]));
+	if (sort_passes) *sort_passes = b->sort_passes;
+	return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_bit, uint32_t end_bit, int device, void *stream) {
+	if ((n && (!d_keys || !d_tmp)) || begin_bit > end_bit || end_bit > 64) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_sort_u64: bad argument");
+	DeviceGuard guard(device);
+	if (!guard.ok) return fail(SVO_ERR_CUDA, "cudaSetDevice failed");
+	SVO_TRY(configure_device_pool(device));
+	cudaStream_t s = (cudaStream_t)stream;
+	SortScratch sc;
+	uint64_t *res = d_keys;
+	uint32_t np = 0;
+	int rc = radix_sort_u64(d_keys, d_tmp, n, begin_bit, end_bit, sc, sm_count(device), s, &res, &np);
+	if (!rc && res != d_keys && cudaMemcpyAsync(d_keys, res, n * 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "copy back failed");
+	sc.hist.release(s), sc.ticket.release(s), sc.state.release(s);
+	return rc;
+}
+
+int svo_device_malloc(int device, uint64_t bytes, void **out) {
+	if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	DeviceGuard guard(device);
+	if (!guard.ok) return fail(SVO_ERR_CUDA, "cudaSetDevice failed");
+	SVO_CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+	return SVO_OK;
+}
+int svo_device_free(int device, void *ptr) {
+	DeviceGuard guard(device);
+	SVO_CUDA_TRY(cudaFree(ptr));
+	return SVO_OK;
+}
+int svo_memcpy_h2d(int device, void *d_dst, const void *h_src, uint64_t bytes, void *stream) {
+	DeviceGuard guard(device);
+	SVO_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+	return SVO_OK;
+}
+int svo_memcpy_d2h(int device, void *h_dst, const void *d_src, uint64_t bytes, void *stream) {
+	DeviceGuard guard(device);
+	SVO_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	SVO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+	return SVO_OK;
+}
+int svo_stream_synchronize(int device, void *stream) {
+	DeviceGuard guard(device);
+	SVO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+	return SVO_OK;
+}
+
+#ifdef SVO_EMU
+// test hook of the emulation build only (see scan.cuh)
+SVO_API void svo_emu_set_lookback_aggregate_only(int on) { svo::g_emu_lookback_aggregate_only = on; }
+#endif
+
+} // extern "C"

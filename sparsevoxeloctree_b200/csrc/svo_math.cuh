@@ -1,0 +1,348 @@
+// svo_math.cuh -- per-triangle / per-fragment arithmetic of the voxelizer and the leaf colour rule,
+// written once as __host__ __device__ so that the same code is compiled into the sm_100a kernels and
+// into the CPU kernel-logic emulator used by the CPU-only tests (tests/cpu_emu; never a product path).
+//
+// This is the "pinned arithmetic" of DESIGN.md section 3: one IEEE operation per written operator
+// (explicit _rn intrinsics on the device, -ffp-contract=off on the host), fp32 where the reference
+// shaders are fp32, exact integers for coverage, fp64 for the depth plane.
+#pragma once
+#include "common.cuh"
+
+namespace svo {
+
+// ---- no-contraction fp helpers -------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+SVO_HD inline float fmul(float a, float b) { return __fmul_rn(a, b); }
+SVO_HD inline float fadd(float a, float b) { return __fadd_rn(a, b); }
+SVO_HD inline float fsub(float a, float b) { return __fsub_rn(a, b); }
+SVO_HD inline double dmul(double a, double b) { return __dmul_rn(a, b); }
+SVO_HD inline double dsub(double a, double b) { return __dsub_rn(a, b); }
+SVO_HD inline double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+SVO_HD inline double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+#else
+SVO_HD inline float fmul(float a, float b) { return a * b; }
+SVO_HD inline float fadd(float a, float b) { return a + b; }
+SVO_HD inline float fsub(float a, float b) { return a - b; }
+SVO_HD inline double dmul(double a, double b) { return a * b; }
+SVO_HD inline double dsub(double a, double b) { return a - b; }
+SVO_HD inline double ddiv(double a, double b) { return a / b; }
+SVO_HD inline double dfma(double a, double b, double c) { return fma(a, b, c); }
+#endif
+
+// GLSL uint(float): truncation; negative / NaN pinned to 0, too large saturates.
+SVO_HD inline uint32_t f2u_sat(float f) {
+	if (!(f > 0.0f)) return 0u;
+	if (f >= 4294967296.0f) return 0xffffffffu;
+	return (uint32_t)f;
+}
+SVO_HD inline float glsl_min(float x, float y) { return y < x ? y : x; }
+SVO_HD inline float glsl_max(float x, float y) { return x < y ? y : x; }
+
+template <class T> SVO_HD inline T tmin(T a, T b) { return b < a ? b : a; }
+template <class T> SVO_HD inline T tmax(T a, T b) { return a < b ? b : a; }
+SVO_HD inline int64_t iabs64(int64_t v) { return v < 0 ? -v : v; }
+
+// floor(n / d) for d > 0, exact
+SVO_HD inline int64_t floor_div(int64_t n, int64_t d) {
+	int64_t q = n / d;
+	if ((n % d != 0) && (n < 0)) --q;
+	return q;
+}
+SVO_HD inline int64_t ceil_div(int64_t n, int64_t d) { return -floor_div(-n, d); }
+
+// ---- Morton --------------------------------------------------------------------------------------
+// spread the low 10 bits of v to every third bit
+SVO_HD inline uint32_t part1by2_10(uint32_t v) {
+	v &= 0x3ffu;
+	v = (v | (v << 16)) & 0x030000ffu;
+	v = (v | (v << 8)) & 0x0300f00fu;
+	v = (v | (v << 4)) & 0x030c30c3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+// spread up to 20 bits (levels <= 20) : low 30 Morton bits from the low 10 coordinate bits, rest above
+SVO_HD inline uint64_t part1by2(uint32_t v) {
+	return (uint64_t)part1by2_10(v) | ((uint64_t)part1by2_10(v >> 10) << 30);
+}
+// child slot = x | y<<1 | z<<2 per level, most significant level first (octree_tag_node.comp:24-25)
+SVO_HD inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+	return part1by2(x) | (part1by2(y) << 1) | (part1by2(z) << 2);
+}
+SVO_HD inline uint32_t compact1by2_10(uint32_t v) {
+	v &= 0x09249249u;
+	v = (v | (v >> 2)) & 0x030c30c3u;
+	v = (v | (v >> 4)) & 0x0300f00fu;
+	v = (v | (v >> 8)) & 0x030000ffu;
+	v = (v | (v >> 16)) & 0x3ffu;
+	return v;
+}
+SVO_HD inline uint32_t compact1by2(uint64_t m) {
+	return compact1by2_10((uint32_t)(m & 0x3fffffffu)) | (compact1by2_10((uint32_t)((m >> 30) & 0x3fffffffu)) << 10);
+}
+
+// ---- triangle setup ------------------------------------------------------------------------------
+// voxelizer.vert:8-11 + voxelizer.geom:15-42 + the viewport transform configured at Voxelizer.cpp:115-116.
+struct TriSetup {
+	// coverage: pixel (px,py) is covered iff ea[i]*px + eb[i]*py + ec[i] >= 0 for i = 0..2, inside the
+	// pixel rectangle [px0,px1] x [py0,py1] (already intersected with gAABB, the viewport and the shard).
+	int64_t ea[3], eb[3], ec[3];
+	int32_t px0, px1, py0, py1; // empty when px0 > px1 or py0 > py1
+	// depth plane through the snapped vertices, fp64
+	double dzdx, dzdy, z0;
+	int32_t X0, Y0;
+	uint32_t zr_lo, zr_hi; // gDepthRange (voxelizer.geom:41-42)
+	uint32_t axis;         // gAxis
+	// size of the candidate rectangle BEFORE the shard window is applied: the small/large work
+	// classification uses it so that a triangle is classified identically in every shard
+	int64_t full_area;
+	// shard window along the depth axis (fragments outside are dropped); cull_depth = window is a strict subset
+	uint32_t zs_lo, zs_hi;
+	bool cull_depth;
+};
+
+enum { MODE_CENTER = 0, MODE_CONSERVATIVE = 1 };
+
+// Shard window in voxel coordinates (half-open), used to clip the pixel rectangle early and to cull
+// fragments by depth; whole grid: lo = 0, hi = res.
+struct ShardBox {
+	uint32_t lo[3], hi[3];
+};
+
+// returns false when the triangle cannot produce a fragment
+SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, uint32_t res, int mode, const ShardBox &sb,
+                             TriSetup &t) {
+	const float *p[3] = {p0, p1, p2};
+	bool valid = true;
+	for (int i = 0; i < 3; ++i)
+		for (int k = 0; k < 3; ++k)
+			if (!(fabsf(p[i][k]) <= 2.0f)) valid = false; // guard band, rejects NaN / Inf
+	float e1[3], e2[3];
+	for (int k = 0; k < 3; ++k) {
+		e1[k] = fsub(p1[k], p0[k]);
+		e2[k] = fsub(p2[k], p0[k]);
+	}
+	// voxelizer.geom:28-32
+	float nx = fabsf(fsub(fmul(e1[1], e2[2]), fmul(e1[2], e2[1])));
+	float ny = fabsf(fsub(fmul(e1[2], e2[0]), fmul(e1[0], e2[2])));
+	float nz = fabsf(fsub(fmul(e1[0], e2[1]), fmul(e1[1], e2[0])));
+	uint32_t axis = (nx > ny && nx > nz) ? 0u : ((ny > nz) ? 1u : 2u);
+	t.axis = axis;
+	if (!valid) return false;
+
+	// Project (voxelizer.geom:15-19): axis 0 -> v.yzx, 1 -> v.zxy, 2 -> v.xyz ; z = (z+1)*0.5
+	const int sx = axis == 0u ? 1 : (axis == 1u ? 2 : 0);
+	const int sy = axis == 0u ? 2 : (axis == 1u ? 0 : 1);
+	const int sz = axis == 0u ? 0 : (axis == 1u ? 1 : 2);
+	const float fres = (float)res;
+	float qx[3], qy[3], qz[3];
+	for (int i = 0; i < 3; ++i) {
+		qx[i] = p[i][sx];
+		qy[i] = p[i][sy];
+		qz[i] = fmul(fadd(p[i][sz], 1.0f), 0.5f);
+	}
+	// gAABB / gDepthRange (voxelizer.geom:39-42)
+	uint32_t ax0 = f2u_sat(fmul(fmul(fadd(glsl_min(qx[0], glsl_min(qx[1], qx[2])), 1.0f), 0.5f), fres));
+	uint32_t ay0 = f2u_sat(fmul(fmul(fadd(glsl_min(qy[0], glsl_min(qy[1], qy[2])), 1.0f), 0.5f), fres));
+	uint32_t ax1 = f2u_sat(fmul(fmul(fadd(glsl_max(qx[0], glsl_max(qx[1], qx[2])), 1.0f), 0.5f), fres));
+	uint32_t ay1 = f2u_sat(fmul(fmul(fadd(glsl_max(qy[0], glsl_max(qy[1], qy[2])), 1.0f), 0.5f), fres));
+	t.zr_lo = f2u_sat(fmul(glsl_min(qz[0], glsl_min(qz[1], qz[2])), fres));
+	t.zr_hi = f2u_sat(fmul(glsl_max(qz[0], glsl_max(qz[1], qz[2])), fres));
+
+	// window coordinates, snapped to 1/256 pixel (round half even)
+	int32_t X[3], Y[3];
+	float zf[3];
+	for (int i = 0; i < 3; ++i) {
+		float xf = fmul(fmul(fadd(qx[i], 1.0f), 0.5f), fres);
+		float yf = fmul(fmul(fadd(qy[i], 1.0f), 0.5f), fres);
+		X[i] = (int32_t)rintf(fmul(xf, 256.0f));
+		Y[i] = (int32_t)rintf(fmul(yf, 256.0f));
+		zf[i] = qz[i];
+	}
+	int64_t a2 = (int64_t)(X[1] - X[0]) * (int64_t)(Y[2] - Y[0]) - (int64_t)(X[2] - X[0]) * (int64_t)(Y[1] - Y[0]);
+	if (a2 < 0) { // CULL_NONE (Voxelizer.cpp:117-118): normalise the winding
+		int32_t ti;
+		float tf;
+		ti = X[1], X[1] = X[2], X[2] = ti;
+		ti = Y[1], Y[1] = Y[2], Y[2] = ti;
+		tf = zf[1], zf[1] = zf[2], zf[2] = tf;
+		a2 = -a2;
+	}
+	if (a2 == 0 && mode == MODE_CENTER) return false;
+
+	const int32_t xmin = tmin(X[0], tmin(X[1], X[2])), xmax = tmax(X[0], tmax(X[1], X[2]));
+	const int32_t ymin = tmin(Y[0], tmin(Y[1], Y[2])), ymax = tmax(Y[0], tmax(Y[1], Y[2]));
+
+	// edges: E_i(P) = (Xb-Xa)*(Py-Ya) - (Yb-Ya)*(Px-Xa) = A*Px + B*Py + C ; interior E_i > 0 when a2 > 0
+	if (a2 > 0) {
+		const int EA[3] = {1, 2, 0}, EB[3] = {2, 0, 1};
+		for (int i = 0; i < 3; ++i) {
+			int64_t A = -(int64_t)(Y[EB[i]] - Y[EA[i]]), B = (int64_t)(X[EB[i]] - X[EA[i]]);
+			int64_t Cc = -(A * (int64_t)X[EA[i]] + B * (int64_t)Y[EA[i]]);
+			int64_t slack;
+			if (mode == MODE_CENTER) {
+				bool top_left = (A > 0) || (A == 0 && B > 0);
+				slack = top_left ? 0 : -1; // E > 0  <=>  E - 1 >= 0
+			} else
+				slack = 128 * (iabs64(A) + iabs64(B)); // max of E over the pixel square >= 0
+			// centre of pixel (px,py) = (256px+128, 256py+128)
+			t.ea[i] = 256 * A;
+			t.eb[i] = 256 * B;
+			t.ec[i] = Cc + 128 * (A + B) + slack;
+		}
+	} else {
+		// zero snapped area (conservative only): the longest edge as a segment, |E| <= support
+		const int SA[3] = {0, 1, 2}, SB[3] = {1, 2, 0};
+		int best = 0;
+		int64_t best_d = -1;
+		for (int i = 0; i < 3; ++i) {
+			int64_t dx = X[SB[i]] - X[SA[i]], dy = Y[SB[i]] - Y[SA[i]];
+			int64_t d = dx * dx + dy * dy;
+			if (d > best_d) best_d = d, best = i;
+		}
+		int64_t A = -(int64_t)(Y[SB[best]] - Y[SA[best]]), B = (int64_t)(X[SB[best]] - X[SA[best]]);
+		int64_t Cc = -(A * (int64_t)X[SA[best]] + B * (int64_t)Y[SA[best]]);
+		int64_t sup = 128 * (iabs64(A) + iabs64(B));
+		t.ea[0] = 256 * A, t.eb[0] = 256 * B, t.ec[0] = Cc + 128 * (A + B) + sup;
+		t.ea[1] = -256 * A, t.eb[1] = -256 * B, t.ec[1] = -(Cc + 128 * (A + B)) + sup;
+		t.ea[2] = 0, t.eb[2] = 0, t.ec[2] = 0;
+	}
+
+	// candidate pixel rectangle
+	int64_t px0, px1, py0, py1;
+	if (mode == MODE_CENTER) { // centres inside the closed snapped bounding box
+		px0 = ceil_div((int64_t)xmin - 128, 256), px1 = floor_div((int64_t)xmax - 128, 256);
+		py0 = ceil_div((int64_t)ymin - 128, 256), py1 = floor_div((int64_t)ymax - 128, 256);
+	} else { // closed squares [256p, 256p+256] touching the closed bounding box
+		px0 = ceil_div((int64_t)xmin, 256) - 1, px1 = floor_div((int64_t)xmax, 256);
+		py0 = ceil_div((int64_t)ymin, 256) - 1, py1 = floor_div((int64_t)ymax, 256);
+	}
+	// viewport / scissor (Voxelizer.cpp:115-116), gAABB discard (voxelizer.frag:21-22)
+	px0 = tmax(px0, (int64_t)0), py0 = tmax(py0, (int64_t)0);
+	px1 = tmin(px1, (int64_t)res - 1), py1 = tmin(py1, (int64_t)res - 1);
+	px0 = tmax(px0, (int64_t)ax0), py0 = tmax(py0, (int64_t)ay0);
+	px1 = tmin(px1, (int64_t)ax1), py1 = tmin(py1, (int64_t)ay1);
+	t.full_area = (px0 > px1 || py0 > py1) ? 0 : (px1 - px0 + 1) * (py1 - py0 + 1);
+	// shard window on the two screen axes: voxel = axis 0: (uz, px, py); 1: (py, uz, px); 2: (px, py, uz)
+	const int wx = axis == 0u ? 1 : (axis == 1u ? 2 : 0); // world axis of screen x
+	const int wy = axis == 0u ? 2 : (axis == 1u ? 0 : 1);
+	px0 = tmax(px0, (int64_t)sb.lo[wx]), px1 = tmin(px1, (int64_t)sb.hi[wx] - 1);
+	py0 = tmax(py0, (int64_t)sb.lo[wy]), py1 = tmin(py1, (int64_t)sb.hi[wy] - 1);
+	t.px0 = (int32_t)px0, t.px1 = (int32_t)px1, t.py0 = (int32_t)py0, t.py1 = (int32_t)py1;
+	if (px0 > px1 || py0 > py1) return false;
+	// depth range vs shard along the depth axis (fragments are clamped into [zr_lo, zr_hi])
+	{
+		uint32_t zlo = tmin(t.zr_lo, res - 1u), zhi = tmin(t.zr_hi, res - 1u);
+		if (zhi < sb.lo[sz] || zlo >= sb.hi[sz]) return false;
+		t.zs_lo = sb.lo[sz], t.zs_hi = sb.hi[sz];
+		t.cull_depth = zlo < sb.lo[sz] || zhi >= sb.hi[sz];
+	}
+
+	// depth plane (fp64)
+	t.X0 = X[0], t.Y0 = Y[0];
+	t.z0 = (double)zf[0];
+	if (a2 == 0) {
+		t.dzdx = 0.0, t.dzdy = 0.0; // provoking-vertex depth for degenerate primitives
+	} else {
+		double dz1 = dsub((double)zf[1], (double)zf[0]), dz2 = dsub((double)zf[2], (double)zf[0]);
+		double dx1 = (double)(X[1] - X[0]), dy1 = (double)(Y[1] - Y[0]);
+		double dx2 = (double)(X[2] - X[0]), dy2 = (double)(Y[2] - Y[0]);
+		double da2 = (double)a2;
+		t.dzdx = ddiv(dsub(dmul(dz1, dy2), dmul(dz2, dy1)), da2);
+		t.dzdy = ddiv(dsub(dmul(dz2, dx1), dmul(dz1, dx2)), da2);
+	}
+	return true;
+}
+
+SVO_HD inline bool pixel_covered(const TriSetup &t, int32_t px, int32_t py) {
+	bool in = true;
+#pragma unroll
+	for (int i = 0; i < 3; ++i) in = in && (t.ea[i] * (int64_t)px + t.eb[i] * (int64_t)py + t.ec[i] >= 0);
+	return in;
+}
+
+// Row span [x_lo, x_hi] of covered pixels of row py inside [px0, px1]; empty when x_lo > x_hi.
+// Exact: solves ea*px + (eb*py + ec) >= 0 for px with integer floor/ceil division.
+SVO_HD inline void row_span(const TriSetup &t, int32_t py, int32_t &x_lo, int32_t &x_hi) {
+	int64_t lo = t.px0, hi = t.px1;
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		const int64_t r = t.eb[i] * (int64_t)py + t.ec[i];
+		const int64_t a = t.ea[i];
+		if (a > 0) {
+			lo = tmax(lo, ceil_div(-r, a));
+		} else if (a < 0) {
+			hi = tmin(hi, floor_div(r, -a));
+		} else if (r < 0) {
+			hi = lo - 1;
+		}
+	}
+	if (hi < lo) hi = lo - 1;
+	x_lo = (int32_t)lo, x_hi = (int32_t)hi;
+}
+
+// depth voxel of pixel (px,py): voxelizer.frag:18-20,23 (+ the pinned final clamp to res-1)
+SVO_HD inline uint32_t pixel_depth(const TriSetup &t, uint32_t res, int32_t px, int32_t py) {
+	const int32_t cx = px * 256 + 128, cy = py * 256 + 128;
+	double z = dfma(t.dzdx, (double)(cx - t.X0), dfma(t.dzdy, (double)(cy - t.Y0), t.z0));
+	double zs = dmul(z, (double)res);
+	uint32_t uz = !(zs > 0.0) ? 0u : (zs >= (double)res ? res - 1u : (uint32_t)zs);
+	uz = tmax(uz, t.zr_lo);
+	uz = tmin(uz, t.zr_hi);
+	uz = tmin(uz, res - 1u);
+	return uz;
+}
+
+// Narrow a row span to the pixels whose depth voxel lies inside the shard's depth window.  The depth voxel
+// is a monotone function of px along a row (one fma with a fixed slope, then monotone clamps), so the
+// surviving pixels form one interval whose ends are found by bisection with the exact per-pixel depth.
+SVO_HD inline void row_span_depth_window(const TriSetup &t, uint32_t res, int32_t py, int32_t &x_lo, int32_t &x_hi) {
+	if (!t.cull_depth || x_lo > x_hi) return;
+	const bool rising = !(t.dzdx < 0.0);
+	// predicate "too low" holds on a prefix (rising) or suffix (falling); "too high" the other way round
+	auto below = [&](int32_t px) { return pixel_depth(t, res, px, py) < t.zs_lo; };
+	auto above = [&](int32_t px) { return pixel_depth(t, res, px, py) >= t.zs_hi; };
+	int32_t lo = x_lo, hi = x_hi;
+	if (rising) {
+		// first px that is not below
+		int32_t a = lo, b = hi + 1;
+		while (a < b) { int32_t m = a + (b - a) / 2; if (below(m)) a = m + 1; else b = m; }
+		lo = a;
+		// last px that is not above
+		a = lo, b = hi + 1;
+		while (a < b) { int32_t m = a + (b - a) / 2; if (!above(m)) a = m + 1; else b = m; }
+		hi = a - 1;
+	} else {
+		int32_t a = lo, b = hi + 1;
+		while (a < b) { int32_t m = a + (b - a) / 2; if (above(m)) a = m + 1; else b = m; }
+		lo = a;
+		a = lo, b = hi + 1;
+		while (a < b) { int32_t m = a + (b - a) / 2; if (!below(m)) a = m + 1; else b = m; }
+		hi = a - 1;
+	}
+	x_lo = lo, x_hi = hi;
+}
+SVO_HD inline bool depth_in_window(const TriSetup &t, uint32_t uz) { return !t.cull_depth || (uz >= t.zs_lo && uz < t.zs_hi); }
+
+// un-swizzle (voxelizer.frag:24): axis 0 -> u.zxy, 1 -> u.yzx, 2 -> u.xyz
+SVO_HD inline void unswizzle(uint32_t axis, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t &vx, uint32_t &vy, uint32_t &vz) {
+	if (axis == 0u)
+		vx = uz, vy = ux, vz = uy;
+	else if (axis == 1u)
+		vx = uy, vy = uz, vz = ux;
+	else
+		vx = ux, vy = uy, vz = uz;
+}
+
+// ---- leaf colour: octree_tag_node.comp:10-16,48-57 ------------------------------------------------
+// first writer: 0xC1000000 | rgb ; later writers: running integer average, count saturating at 63
+SVO_HD inline uint32_t leaf_first(uint32_t rgb) { return 0xC1000000u | (rgb & 0xffffffu); }
+SVO_HD inline uint32_t leaf_accumulate(uint32_t prev, uint32_t rgb) {
+	uint32_t w = (prev >> 24) & 0x3fu;
+	uint32_t r = ((prev & 0xffu) * w + (rgb & 0xffu)) / (w + 1u);
+	uint32_t g = (((prev >> 8) & 0xffu) * w + ((rgb >> 8) & 0xffu)) / (w + 1u);
+	uint32_t b = (((prev >> 16) & 0xffu) * w + ((rgb >> 16) & 0xffu)) / (w + 1u);
+	uint32_t nw = tmin(w + 1u, 0x3fu);
+	return (nw << 24) | (r & 0xffu) | ((g & 0xffu) << 8) | ((b & 0xffu) << 16) | 0xC0000000u;
+}
+
+} // namespace svo

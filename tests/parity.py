@@ -1,0 +1,98 @@
+"""Shared parity checker: the CUDA path (through the C ABI / api.py) against the CPU oracle."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle
+from sparsevoxeloctree_b200 import api
+
+
+def morton_np(x, y, z, level):
+    m = np.zeros(len(x), dtype=np.uint64)
+    x, y, z = (np.asarray(v).astype(np.uint64) for v in (x, y, z))
+    for b in range(level):
+        m |= ((x >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b)
+        m |= ((y >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + 1)
+        m |= ((z >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + 2)
+    return m
+
+
+def demorton_np(m, level):
+    out = []
+    for s in range(3):
+        c = np.zeros(len(m), dtype=np.uint32)
+        for b in range(level):
+            c |= ((m >> np.uint64(3 * b + s)) & np.uint64(1)).astype(np.uint32) << np.uint32(b)
+        out.append(c)
+    return out
+
+
+def oracle_fragment_keys(mesh, level, mode, shard_box=None, origin=(0, 0, 0), key_level=None):
+    """The oracle's fragments as 64-bit keys (morton << 24 | rgb), in oracle emission order."""
+    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, mode, shard=shard_box)
+    kl = level if key_level is None else key_level
+    m = morton_np(fr["x"] - np.uint32(origin[0]), fr["y"] - np.uint32(origin[1]), fr["z"] - np.uint32(origin[2]), kl)
+    return (m << np.uint64(24)) | fr["rgb"].astype(np.uint64)
+
+
+def keys_to_oracle_frags(keys, level):
+    x, y, z = demorton_np(keys >> np.uint64(24), level)
+    return oracle.frags_from_xyzc(x, y, z, (keys & np.uint64(0xFFFFFF)).astype(np.uint32))
+
+
+def assert_same_tree(words_a, words_b, level):
+    da, ma, wa = oracle.canonicalise(words_a, level)
+    db, mb, wb = oracle.canonicalise(words_b, level)
+    assert len(da) == len(db), f"node count {len(da)} != {len(db)}"
+    assert (da == db).all() and (ma == mb).all(), "topology / occupancy differs"
+    assert (wa == wb).all(), "leaf words differ"
+    return da, ma, wa
+
+
+def check_layout_invariants(words, level, level_counts):
+    """The reference layout: root block at 0, level windows top-down, pointers inside the next window."""
+    words = np.asarray(words)
+    assert len(words) % 8 == 0
+    internal = (words & np.uint32(0xC0000000)) == np.uint32(0x80000000)
+    leaf = (words & np.uint32(0xC0000000)) == np.uint32(0xC0000000)
+    assert ((words == 0) | internal | leaf).all()
+    ptr = words[internal] & np.uint32(0x3FFFFFFF)
+    assert (ptr % 8 == 0).all() and (ptr > 0).all() and (ptr.astype(np.int64) + 8 <= len(words)).all()
+    # every block except the root is pointed to exactly once
+    assert len(np.unique(ptr)) == len(ptr) == len(words) // 8 - 1
+    blocks = 1 + sum(level_counts[1:level])
+    assert len(words) == 8 * blocks
+    assert int(leaf.sum()) == level_counts[level]
+
+
+def check_against_oracle(lib, mesh, level, mode, shard=None, device=0, stream=None):
+    """Full-path parity: (1) fragment multiset == oracle voxelizer's; (2) octree built by CUDA ==
+    oracle level loop fed with the same fragment order, after Morton canonicalisation (bit exact, colours
+    included); (3) range and layout invariants."""
+    scene = api.Scene.Create(mesh, device=device, stream=stream, lib=lib)
+    vox = api.Voxelizer.Create(scene, level, mode, shard=shard, stream=stream)
+    builder = api.OctreeBuilder.Create(vox, stream=stream)
+    vox.CmdVoxelize(stream)
+    frags = vox.fragments_to_host(stream)
+    key_level = builder.GetLevel()
+    box, origin = None, (0, 0, 0)
+    if shard is not None:
+        sl, ci = shard
+        side = 1 << (level - sl)
+        origin = tuple(c * side for c in ci)
+        box = (origin, tuple(o + side for o in origin))
+    okeys = oracle_fragment_keys(mesh, level, mode, box, origin, key_level)
+    assert len(frags) == len(okeys) == vox.GetVoxelFragmentCount(), (len(frags), len(okeys))
+    assert (np.sort(frags) == np.sort(okeys)).all(), "fragment multiset differs from the oracle"
+    builder.CmdBuild(stream)
+    words = builder.octree_to_host(stream)
+    rng = builder.GetOctreeRange()
+    ow, orng = oracle.build_octree(keys_to_oracle_frags(frags, key_level), key_level)
+    assert rng == orng == len(words) * 4, (rng, orng)
+    d, m, w = assert_same_tree(words, ow, key_level)
+    counts = builder.GetLevelCounts()
+    check_layout_invariants(words, key_level, counts)
+    assert counts[key_level] == builder.GetLeafCount() == int((d == key_level).sum())
+    info = dict(fragments=len(frags), leaves=counts[key_level], range=rng, counts=counts)
+    builder.Destroy(), vox.Destroy(), scene.Destroy()
+    return info

@@ -1,0 +1,135 @@
+"""Parity tests proper: the sm_100a CUDA path, called through the C ABI, against the CPU oracle.
+Bit-exact bar (integer / index work): fragment multisets, octree range, canonicalised node words."""
+import numpy as np
+import pytest
+
+from sparsevoxeloctree_b200 import api, scenes
+from tests.parity import check_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = api.get_library()  # raises if libsvo_b200.so is missing: no fallback
+    assert L.dll.svo_device_count() >= 1, "no CUDA device"
+    assert b"sm_100a" in L.dll.svo_version()
+    return L
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 4095, 4096, 4097, 100_000, 3_000_001])
+@pytest.mark.parametrize("bits", [(24, 48), (24, 60), (0, 64), (24, 29)])
+def test_onesweep_sort_matches_stable_numpy(lib, n, bits):
+    rng = np.random.default_rng(n + bits[1])
+    k = rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    out = lib.sort_u64(k, *bits)
+    width = bits[1] - bits[0]
+    key = (k >> np.uint64(bits[0])) & np.uint64((1 << width) - 1 if width < 64 else 0xFFFFFFFFFFFFFFFF)
+    assert (out == k[np.argsort(key, kind="stable")]).all()
+
+
+def test_onesweep_sort_clustered_keys(lib):
+    # spatially coherent keys (few distinct upper digits, long runs): the warp-uniform histogram path and
+    # long equal-digit runs in the ranking
+    rng = np.random.default_rng(5)
+    n = 1_000_003
+    k = (np.repeat(rng.integers(0, 1 << 36, n // 1000 + 1, dtype=np.uint64), 1000)[:n] << np.uint64(24)) | \
+        rng.integers(0, 1 << 24, n, dtype=np.uint64)
+    out = lib.sort_u64(k, 24, 60)
+    assert (out == k[np.argsort(k >> np.uint64(24), kind="stable")]).all()
+
+
+@pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT])
+def test_config1_heightfield_level8(lib, mode):
+    # BASELINE.json configs[0]: 10k-triangle heightfield, level 8
+    info = check_against_oracle(lib, scenes.heightfield(), 8, mode)
+    assert info["fragments"] > 50_000
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 5, 9, 10])
+@pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT])
+def test_random_soup_levels(lib, level, mode):
+    # mixed triangle sizes: exercises both work classes (single-thread walk and row spans)
+    check_against_oracle(lib, scenes.random_soup(400, 100 + level, 0.002, 1.2), level, mode)
+
+
+def test_large_triangles_level11(lib):
+    # huge triangles only: the row-span / output-parallel path at a high level
+    m = scenes.living_room_like(n_boxes=3, n_small=50)
+    info = check_against_oracle(lib, m, 9, api.CONSERVATIVE_EXACT)
+    assert info["fragments"] > 1_000_000
+
+
+@pytest.mark.parametrize("cube", [(0, 0, 0), (1, 0, 1), (1, 1, 1)])
+def test_octant_shard(lib, cube):
+    # one top-level octant in cube-local coordinates
+    check_against_oracle(lib, scenes.random_soup(300, 11, 0.01, 1.0), 7, api.CONSERVATIVE_EXACT, shard=(1, cube))
+
+
+def test_empty_and_degenerate_scenes(lib):
+    # no triangles at all
+    m = scenes.Mesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), np.zeros(0, scenes.DRAW_DTYPE), "empty")
+    info = check_against_oracle(lib, m, 5, api.CENTER)
+    assert info["fragments"] == 0 and info["range"] == 32
+    # zero-area triangles: nothing in centre mode, segments / points in conservative mode
+    pos = np.array([[-0.5, 0.1, 0.2], [0.0, 0.1, 0.2], [0.5, 0.1, 0.2], [0.3, 0.3, 0.3]], np.float32)
+    idx = np.array([0, 1, 2, 3, 3, 3], np.uint32)
+    draws = np.array([(0, 6, 0xFFFFFFFF, 0x00FF00)], scenes.DRAW_DTYPE)
+    m = scenes.Mesh(pos, idx, draws, "degenerate")
+    assert check_against_oracle(lib, m, 6, api.CENTER)["fragments"] == 0
+    assert check_against_oracle(lib, m, 6, api.CONSERVATIVE_EXACT)["fragments"] > 0
+
+
+def test_colour_average_many_fragments_per_voxel(lib):
+    # 200 coincident small triangles of alternating materials in one voxel: count saturates at 63 and the
+    # running average is order dependent (octree_tag_node.comp:48-57)
+    base = np.array([[0.101, 0.101, 0.101], [0.104, 0.101, 0.101], [0.101, 0.104, 0.101]], np.float32)
+    pos = np.tile(base, (200, 1))
+    idx = np.arange(600, dtype=np.uint32)
+    draws = np.array([(0, 300, 0xFFFFFFFF, 0x0000FF), (300, 300, 0xFFFFFFFF, 0xFF0000)], scenes.DRAW_DTYPE)
+    info = check_against_oracle(lib, scenes.Mesh(pos, idx, draws, "pile"), 4, api.CONSERVATIVE_EXACT)
+    assert info["leaves"] >= 1
+
+
+def test_reference_fragment_packing(lib):
+    # GetVoxelFragmentList in the reference's uvec2 packing (voxelizer.frag:40-42)
+    from oracle import oracle
+    m = scenes.heightfield(31)
+    scene = api.Scene.Create(m, lib=lib)
+    vox = api.Voxelizer.Create(scene, 7, api.CENTER)
+    vox.CmdVoxelize()
+    packed = vox.reference_fragments_to_host()
+    ofr = oracle.voxelize(m.positions, m.indices, m.draws, 7, oracle.CENTER)
+    exp = np.array([oracle.pack_fragment(int(f["x"]), int(f["y"]), int(f["z"]), int(f["rgb"])) for f in ofr], dtype=np.uint32)
+    a = packed[np.lexsort((packed[:, 1], packed[:, 0]))]
+    b = exp[np.lexsort((exp[:, 1], exp[:, 0]))]
+    assert (a == b).all()
+
+
+def test_stride20_reference_vertex_layout(lib):
+    # the reference's interleaved Vertex {vec3 pos; vec2 uv} (Scene.cpp:16-19), stride 20
+    m = scenes.heightfield(31)
+    v5 = np.zeros((len(m.positions), 5), np.float32)
+    v5[:, :3] = m.positions
+    v5[:, 3:] = 0.25
+    a = check_against_oracle(lib, scenes.Mesh(v5, m.indices, m.draws, "stride20"), 7, api.CENTER)
+    b = check_against_oracle(lib, m, 7, api.CENTER)
+    assert a == b
+
+
+def test_error_behaviour(lib):
+    m = scenes.heightfield(11)
+    scene = api.Scene.Create(m, lib=lib)
+    with pytest.raises(api.SvoError):
+        api.Voxelizer.Create(scene, 0)  # level below kOctreeLevelMin (Config.hpp:18)
+    with pytest.raises(api.SvoError):
+        api.Voxelizer.Create(scene, 15)
+    vox = api.Voxelizer.Create(scene, 5)
+    b = api.OctreeBuilder.Create(vox)
+    with pytest.raises(api.SvoError):
+        b.CmdBuild()  # fragments not emitted yet
+    assert b.GetOctreeRange() == 0 and b.GetOctree() == 0
+    draws = m.draws.copy()
+    draws["texture_id"][0] = 3
+    with pytest.raises(api.SvoError):
+        api.Scene.Create(m.positions, m.indices, draws, lib=lib)  # textured draws: not on the built path
