@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- SVO build throughput on B200(s): `python bench.py --gpus N --steps K --warmup W`.
+
+A step = one pass of the hot path over one synthetic scene: Voxelizer::CmdVoxelize + OctreeBuilder::CmdBuild,
+the span the reference times with its 4 GPU timestamps (src/LoaderThread.cpp:57-97, "SVO build time" of the
+README).  Workload = BASELINE.json configs[3]: the Living-Room-scale synthetic scene at level 12 (2^12 is
+the resolution BASELINE.json's metric is quoted on; it fits one GPU).  metric = leaf voxels / s (and
+ms_per_step = build ms).  N > 1: the same scene octant-sharded over N ranks with the NVLink subtree gather
+(strong scaling; one process per GPU under torchrun).
+
+`--impl reference` times the reference algorithm's CPU port (oracle/, all host threads) on a bounded sample
+of the same workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "svo_build_leaf_voxels_per_s", "leaf voxels/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--level", type=int, default=0, help="override the workload's level")
+    ap.add_argument("--mode", default="", choices=["", "center", "conservative"])
+    ap.add_argument("--no-ipc", action="store_true", help="multi-GPU: NCCL send/recv instead of P2P stores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from sparsevoxeloctree_b200 import scenes
+    cfg = scenes.CONFIGS[args.workload]
+    level = args.level or cfg["level"]
+    mode_name = args.mode or cfg["mode"]
+    mesh = cfg["gen"]()
+    return mesh, level, mode_name
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])), mx.append(float(parts[1])), pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v == "Active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(mesh, level, mode_name, steps, warmup, budget_s=25.0):
+    """The reference algorithm's CPU port (oracle/, OpenMP over all host threads) on a bounded sample of the
+    workload: the fragments of ONE top-level octant of the scene at the full level (so the tree is as deep as
+    the real one).  Returns per-step seconds and leaf counts."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    mode = oracle.CENTER if mode_name == "center" else oracle.CONSERVATIVE_EXACT
+    res = 1 << level
+    half = res // 2
+    box = ((0, 0, 0), (half, half, half))
+    times, leaves, frags_n = [], 0, 0
+    t_start = time.perf_counter()
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        frags = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, mode, shard=box, nthreads=cores)
+        words, rng = oracle.build_octree(frags, level, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        if it == 0:
+            d, _, _ = oracle.canonicalise(words, level)
+            leaves, frags_n = int((d == level).sum()), len(frags)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    sample = (f"octant (0,0,0) of the {mesh.name} scene at level {level} ({frags_n} fragments, {leaves} leaves), "
+              f"oracle port (literal level loop), OpenMP {cores} threads, {len(times)} timed runs")
+    return times, leaves, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mesh, level, mode_name = workload(args)
+    times, leaves, cores, sample = cpu_reference_run(mesh, level, mode_name, max(1, args.steps), min(args.warmup, 1),
+                                                     budget_s=120.0)
+    sec = float(np.mean(times))
+    value = leaves / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} {mesh.name} level {level} {mode_name}", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sparsevoxeloctree_b200 import api, sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = api.get_library()  # raises without the CUDA library: no fallback
+    mesh, level, mode_name = workload(args)
+    mode = api.CENTER if mode_name == "center" else api.CONSERVATIVE_EXACT
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # -------- device-resident arm: inputs already in HBM, handles created (count pass done) ----------------
+    phases_acc = {k: 0.0 for k in api.PHASES}
+    sort_passes = 0
+    if world == 1:
+        scene = api.Scene.Create(mesh, device=local_rank, stream=stream, lib=lib)
+        vox = api.Voxelizer.Create(scene, level, mode, stream=stream)
+        builder = api.OctreeBuilder.Create(vox, stream=stream)
+
+        def step():
+            vox.CmdVoxelize(stream)
+            builder.CmdBuild(stream)
+    else:
+        sh = sharded.ShardedSVO(torch, dist, mesh, level, mode, local_rank, lib=lib, use_ipc=not args.no_ipc)
+
+        def step():
+            sh.step(stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = int(lib.dll.svo_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        if world == 1:  # per-phase cudaEvent times recorded by the library on the same stream
+            ms, sort_passes = builder.LastMs()
+            for k in api.PHASES:
+                phases_acc[k] += ms[k]
+    e1.record(stream)
+    barrier()
+    launches = int(lib.dll.svo_launch_count()) - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+
+    if world == 1:
+        leaves, frags = builder.GetLeafCount(), vox.GetVoxelFragmentCount()
+        octree_bytes = builder.GetOctreeRange()
+    else:
+        c = torch.tensor([sh.leaf_count_local(), sh.fragment_count_local()], dtype=torch.int64, device=dev)
+        dist.all_reduce(c)
+        leaves, frags = int(c[0].item()), int(c[1].item())
+        octree_bytes = sh.total_words * 4
+    value = leaves / (ms_per_step * 1e-3)
+
+    # -------- end-to-end arm: host (pinned) mesh -> handles -> build -> result read-back, every step --------
+    pos_pin = torch.from_numpy(np.ascontiguousarray(mesh.positions)).pin_memory()
+    idx_pin = torch.from_numpy(mesh.indices.astype(np.int32)).pin_memory()
+    h2d = pos_pin.numel() * 4 + idx_pin.numel() * 4 + mesh.draws.nbytes
+    d2h = 8 + 32 + 8 * (level + 1)
+
+    def e2e_step():
+        pm = mesh.__class__(pos_pin.numpy(), idx_pin.numpy().view(np.uint32), mesh.draws, mesh.name)
+        if world == 1:
+            s = api.Scene.Create(pm, device=local_rank, stream=stream, lib=lib)
+            v = api.Voxelizer.Create(s, level, mode, stream=stream)
+            b = api.OctreeBuilder.Create(v, stream=stream)
+            v.CmdVoxelize(stream)
+            b.CmdBuild(stream)
+            rng = b.GetOctreeRange()
+            root = lib.to_host(b.GetOctree(), np.uint32, 8, local_rank, int(stream.cuda_stream))  # D2H + sync
+            counts = b.GetLevelCounts()
+            b.Destroy(), v.Destroy(), s.Destroy()
+            return rng, root, counts
+        s2 = sharded.ShardedSVO(torch, dist, pm, level, mode, local_rank, lib=lib, use_ipc=not args.no_ipc)
+        rng = s2.step(stream)
+        root = lib.to_host(s2.final, np.uint32, 8, local_rank) if rank == 0 else None
+        s2.destroy()
+        return rng, root, None
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        roofline = None
+        if world == 1 and sort_passes:
+            per_launch_ms = phases_acc["sort_passes"] / args.steps / sort_passes
+            alg_bytes = 16.0 * frags  # one read + one write of every 8-byte fragment per onesweep pass
+            achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                try:
+                    with open(tp) as f:
+                        traffic = json.load(f).get("k_onesweep_pass", {}).get("dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            roofline = {"bound": "hbm", "kernel": "k_onesweep_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
+                        "launches_per_step": sort_passes}
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            times, cl, cores, sample = cpu_reference_run(mesh, level, mode_name, 3, 0, budget_s=25.0)
+            cpu_baseline = {"value": cl / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} {mesh.name} level {level} {mode_name}", "level": level,
+                       "triangles": mesh.n_triangles, "fragments": frags, "leaf_voxels": leaves,
+                       "octree_bytes": octree_bytes, "raster_mode": mode_name,
+                       "l2": "no flush needed: every step streams the fragment list (8 B x fragments, > 126 MB L2)",
+                       "parallelism": "single GPU" if world == 1 else f"octant-sharded x{world}, NVLink subtree gather"
+                                      f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})"},
+            "build_ms": ms_per_step,
+            "phases_ms": {k: v / args.steps for k, v in phases_acc.items()} if world == 1 else None,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": leaves / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "note": "host wall clock around pinned-host mesh -> Scene/Voxelizer(count pass)/OctreeBuilder create -> "
+                            "voxelize -> build -> read-back of range, root block and level counts -> destroy"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        sh.destroy()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,7 @@ typedef struct svo_builder svo_builder;
 SVO_API const char *svo_last_error(void);
 SVO_API const char *svo_version(void);
 SVO_API int svo_device_count(void); /* < 0: CUDA unavailable */
+SVO_API uint64_t svo_launch_count(void); /* kernels launched by this library since it was loaded */
 
 /* ---- Scene (input side) -------------------------------------------------------------------
  * Replaces the GPU-buffer half of Scene::Create / load_buffers_and_draw_cmd
@@ -137,15 +138,22 @@ SVO_API const uint32_t *svo_builder_octree(const svo_builder *b);
 SVO_API uint64_t svo_builder_leaf_count(const svo_builder *b);
 /* node counts per depth: out[d] = non-empty nodes at depth d, d = 0..level (out[0] = 1 if any) */
 SVO_API int svo_builder_level_counts(const svo_builder *b, uint64_t *out, uint32_t n_out);
-/* Multi-GPU stitch support: add `base_words` to every internal node's child pointer
- * while copying the subtree's blocks 1.. (the subtree's root block excluded: its 8 words become the
- * parent's child block) -- see sparsevoxeloctree_b200/sharded.py.  dst may be peer (P2P/IPC) memory. */
+/* Multi-GPU stitch support: copy the whole node buffer to d_dst + dst_word_offset while
+ * adding `base_words` to every internal node's child pointer (leaves untouched), so that the subtree can
+ * live at word offset base_words of a larger buffer whose root block points at it -- see
+ * sparsevoxeloctree_b200/sharded.py.  d_dst may be peer (P2P / CUDA-IPC mapped) memory: the rebase is
+ * fused with the NVLink transfer. */
 SVO_API int svo_builder_rebase_copy(const svo_builder *b, uint32_t *d_dst, uint64_t dst_word_offset,
                                     uint32_t base_words, void *stream);
 
 /* ---- timing (LoaderThread.cpp:57-97 writes 4 GPU timestamps around CmdVoxelize / CmdBuild) -- */
-enum { SVO_PHASE_RASTER = 0, SVO_PHASE_SORT = 1, SVO_PHASE_REDUCE = 2, SVO_PHASE_LEVELS = 3, SVO_PHASE_EMIT = 4,
-       SVO_PHASE_COUNT = 5 };
+enum { SVO_PHASE_RASTER = 0,      /* fragment emission (CmdVoxelize) */
+       SVO_PHASE_SORT_HIST = 1,   /* digit histograms of all passes + bin scan */
+       SVO_PHASE_SORT_PASSES = 2, /* the onesweep passes (sort_passes launches of one kernel) */
+       SVO_PHASE_REDUCE = 3,      /* de-duplicate + colour reduce */
+       SVO_PHASE_LEVELS = 4,      /* bottom-up parent compaction, one launch per level */
+       SVO_PHASE_EMIT = 5,        /* size read-back + node word emission */
+       SVO_PHASE_COUNT = 6 };
 /* Milliseconds of the last voxelize (RASTER) / build (others), from cudaEvents on the call's stream.
  * Synchronises on the recorded events.  sort_passes receives the number of radix passes. */
 SVO_API int svo_voxelizer_last_ms(svo_voxelizer *vox, float *raster_ms);
@@ -162,7 +170,16 @@ SVO_API int svo_device_malloc(int device, uint64_t bytes, void **out);
 SVO_API int svo_device_free(int device, void *ptr);
 SVO_API int svo_memcpy_h2d(int device, void *d_dst, const void *h_src, uint64_t bytes, void *stream);
 SVO_API int svo_memcpy_d2h(int device, void *h_dst, const void *d_src, uint64_t bytes, void *stream);
+SVO_API int svo_memcpy_d2d(int device, void *d_dst, const void *d_src, uint64_t bytes, void *stream);
 SVO_API int svo_stream_synchronize(int device, void *stream);
+
+/* ---- CUDA IPC: lets the other ranks (one process per GPU) store their subtrees straight into rank 0's
+ * stitched node buffer over NVLink (svo_builder_rebase_copy with a mapped peer pointer).  The buffer
+ * must come from svo_device_malloc (cudaMalloc), not from a stream-ordered pool. */
+#define SVO_IPC_HANDLE_BYTES 64
+SVO_API int svo_ipc_export(int device, void *d_ptr, unsigned char handle[SVO_IPC_HANDLE_BYTES]);
+SVO_API int svo_ipc_open(int device, const unsigned char handle[SVO_IPC_HANDLE_BYTES], void **out);
+SVO_API int svo_ipc_close(int device, void *d_ptr);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
 
 CENTER, CONSERVATIVE_EXACT = 0, 1
-PHASES = ("raster", "sort", "reduce", "levels", "emit")
+PHASES = ("raster", "sort_hist", "sort_passes", "reduce", "levels", "emit")
 
 
 class SvoError(RuntimeError):
@@ -54,6 +54,7 @@ SYMBOLS = [
     ("svo_last_error", C.c_char_p, []),
     ("svo_version", C.c_char_p, []),
     ("svo_device_count", C.c_int, []),
+    ("svo_launch_count", C.c_uint64, []),
     ("svo_scene_create", C.c_int, [C.POINTER(svo_mesh), C.c_int, _P, C.POINTER(_P)]),
     ("svo_scene_destroy", None, [_P]),
     ("svo_scene_triangle_count", C.c_uint64, [_P]),
@@ -81,7 +82,11 @@ SYMBOLS = [
     ("svo_device_free", C.c_int, [C.c_int, _P]),
     ("svo_memcpy_h2d", C.c_int, [C.c_int, _P, _P, C.c_uint64, _P]),
     ("svo_memcpy_d2h", C.c_int, [C.c_int, _P, _P, C.c_uint64, _P]),
+    ("svo_memcpy_d2d", C.c_int, [C.c_int, _P, _P, C.c_uint64, _P]),
     ("svo_stream_synchronize", C.c_int, [C.c_int, _P]),
+    ("svo_ipc_export", C.c_int, [C.c_int, _P, C.c_char_p]),
+    ("svo_ipc_open", C.c_int, [C.c_int, C.c_char_p, C.POINTER(_P)]),
+    ("svo_ipc_close", C.c_int, [C.c_int, _P]),
 ]
 
 
@@ -125,6 +130,20 @@ class Library:
         if count:
             self.check(self.dll.svo_memcpy_d2h(device, out.ctypes.data, ptr, out.nbytes, stream))
         return out
+
+    # --- CUDA IPC (multi-process stitch over NVLink) ---
+    def ipc_export(self, ptr: int, device: int = 0) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.check(self.dll.svo_ipc_export(device, ptr, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes, device: int = 0) -> int:
+        p = _P()
+        self.check(self.dll.svo_ipc_open(device, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value or 0
+
+    def ipc_close(self, ptr: int, device: int = 0):
+        self.check(self.dll.svo_ipc_close(device, ptr))
 
     def sort_u64(self, keys: np.ndarray, begin_bit: int, end_bit: int, device: int = 0) -> np.ndarray:
         """svo_sort_u64 on a host array (test helper)."""

@@ -23,20 +23,25 @@
 #ifdef SVO_EMU
 // cooperative kernel (uses __syncthreads / warp collectives): one OS thread per CUDA thread
 #define SVO_LAUNCH(grid, block, smem, stream, kernel, ...) \
-	svo_emu::launch((grid), (block), (smem), true, [=]() { kernel(__VA_ARGS__); })
+	(++svo::g_launches, svo_emu::launch((grid), (block), (smem), true, [=]() { kernel(__VA_ARGS__); }))
 // independent-thread kernel (no barrier, no warp collective): threads are run one after another
 #define SVO_LAUNCH_INDEP(grid, block, stream, kernel, ...) \
-	svo_emu::launch((grid), (block), 0, false, [=]() { kernel(__VA_ARGS__); })
+	(++svo::g_launches, svo_emu::launch((grid), (block), 0, false, [=]() { kernel(__VA_ARGS__); }))
 #define SVO_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(svo_emu::tctx.dyn_smem)
 #else
-#define SVO_LAUNCH(grid, block, smem, stream, kernel, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define SVO_LAUNCH_INDEP(grid, block, stream, kernel, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define SVO_LAUNCH(grid, block, smem, stream, kernel, ...) \
+	(++svo::g_launches, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
+#define SVO_LAUNCH_INDEP(grid, block, stream, kernel, ...) \
+	(++svo::g_launches, kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__))
 #define SVO_DYN_SMEM(type, name)                               \
 	extern __shared__ __align__(16) unsigned char svo_dyn_smem_raw[]; \
 	type *name = reinterpret_cast<type *>(svo_dyn_smem_raw)
 #endif
 
 namespace svo {
+
+// kernels launched by this library since load (host-side count; the bench reports it as gpu_launches)
+inline uint64_t g_launches = 0;
 
 constexpr uint32_t FULL_MASK = 0xffffffffu;
 constexpr int WARP = 32;

@@ -248,11 +248,14 @@ constexpr int OS_BLOCK = 256, OS_ITEMS = 16;
 // Sorts n keys on bits [begin_bit, end_bit).  Ping-pongs between a and b; *result receives the buffer that
 // holds the sorted keys.  Stable.
 inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_bit, uint32_t end_bit, SortScratch &sc,
-                          int n_sm, cudaStream_t s, uint64_t **result, uint32_t *n_pass_out) {
+                          int n_sm, cudaStream_t s, uint64_t **result, uint32_t *n_pass_out, cudaEvent_t ev_after_hist) {
 	const SortPasses sp = make_passes(begin_bit, end_bit);
 	if (n_pass_out) *n_pass_out = sp.n_pass;
 	*result = a;
-	if (n <= 1 || sp.n_pass == 0) return 0;
+	if (n <= 1 || sp.n_pass == 0) {
+		if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
+		return 0;
+	}
 	constexpr int TILE = OS_BLOCK * OS_ITEMS;
 	const uint32_t tiles = div_up(n, TILE);
 	const bool wide = n >= (1ull << 30);
@@ -270,6 +273,7 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, k_radix_histogram, (const uint64_t *)a, n, sp, sc.hist.p);
 	SVO_LAUNCH(sp.n_pass, RADIX, 0, s, k_radix_scan_bins, sc.hist.p);
 	SVO_CUDA_TRY(cudaGetLastError());
+	if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
 
 	constexpr size_t smem = onesweep_smem_bytes<OS_BLOCK, OS_ITEMS>();
 	auto k32 = k_onesweep_pass<OS_BLOCK, OS_ITEMS, uint32_t>;

@@ -148,6 +148,7 @@ const char *svo_version(void) {
 	return "svo-b200 0.1 (sm_100a)";
 #endif
 }
+uint64_t svo_launch_count(void) { return svo::g_launches; }
 int svo_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
@@ -469,9 +470,9 @@ int svo_builder_build(svo_builder *b, void *stream) {
 	// ---- sort by Morton code (stable) ----
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
 	uint64_t *sorted = v->frags.p;
-	SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, n_sm, s, &sorted, &b->sort_passes));
+	SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, n_sm, s, &sorted, &b->sort_passes, b->ev[1]));
 	uint64_t *other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[1], s));
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
 
 	// ---- de-duplicate + colour reduce: keys of depth L ----
 	const uint64_t tiles_f = (F + CMP_TILE - 1) / CMP_TILE + 1;
@@ -483,7 +484,7 @@ int svo_builder_build(svo_builder *b, void *stream) {
 		uint32_t g = (uint32_t)(tiles_f < pgrid ? tiles_f : pgrid);
 		SVO_LAUNCH(g, CMP_BLOCK, 0, s, k_dedup_reduce, (const uint64_t *)sorted, F, other, b->leaf.p, b->lb_state.p, b->tickets.p, b->counts.p + L);
 	}
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 
 	// ---- levels L..1: unique parents, first child, child mask ----
 	// key buffers ping-pong between the two fragment-sized buffers (the sorted fragments are dead after the reduce)
@@ -507,7 +508,7 @@ int svo_builder_build(svo_builder *b, void *stream) {
 			kout = t;
 		}
 	}
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[4], s));
 
 	// ---- exact sizing: the one host round trip of the build ----
 	SVO_CUDA_TRY(cudaMemcpyAsync(b->h_counts, b->counts.p, (L + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -533,7 +534,7 @@ int svo_builder_build(svo_builder *b, void *stream) {
 	} else {
 		SVO_LAUNCH_INDEP(div_up(blocks, 256), 256, s, k_emit_octree, ep, b->octree.p);
 	}
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[4], s));
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], s));
 	SVO_CUDA_TRY(cudaGetLastError());
 	b->range_bytes = blocks * 8 * sizeof(uint32_t); // (counter + 1) * 8 * 4, src/OctreeBuilder.cpp:212-214
 	b->built = true;
@@ -568,10 +569,10 @@ int svo_builder_last_ms(svo_builder *b, float *phase_ms, uint32_t *sort_passes) 
 	if (!b || !phase_ms) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
 	if (!b->built) return fail(SVO_ERR_NOT_READY, "build first");
 	DeviceGuard guard(b->device);
-	SVO_CUDA_TRY(cudaEventSynchronize(b->ev[4]));
+	SVO_CUDA_TRY(cudaEventSynchronize(b->ev[5]));
 	phase_ms[SVO_PHASE_RASTER] = 0.f;
 	if (b->vox->t_raster.recorded) SVO_CUDA_TRY(cudaEventElapsedTime(&phase_ms[SVO_PHASE_RASTER], b->vox->t_raster.a, b->vox->t_raster.b));
-	for (int i = 0; i < 4; ++i) SVO_CUDA_TRY(cudaEventElapsedTime(&phase_ms[SVO_PHASE_SORT + i], b->ev[i], b->ev[i + 1]));
+	for (int i = 0; i < 5; ++i) SVO_CUDA_TRY(cudaEventElapsedTime(&phase_ms[SVO_PHASE_SORT_HIST + i], b->ev[i], b->ev[i + 1]));
 	if (sort_passes) *sort_passes = b->sort_passes;
 	return SVO_OK;
 }
@@ -586,7 +587,7 @@ int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_b
 	SortScratch sc;
 	uint64_t *res = d_keys;
 	uint32_t np = 0;
-	int rc = radix_sort_u64(d_keys, d_tmp, n, begin_bit, end_bit, sc, sm_count(device), s, &res, &np);
+	int rc = radix_sort_u64(d_keys, d_tmp, n, begin_bit, end_bit, sc, sm_count(device), s, &res, &np, nullptr);
 	if (!rc && res != d_keys && cudaMemcpyAsync(d_keys, res, n * 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "copy back failed");
 	sc.hist.release(s), sc.ticket.release(s), sc.state.release(s);
 	return rc;
@@ -615,6 +616,39 @@ int svo_memcpy_d2h(int device, void *h_dst, const void *d_src, uint64_t bytes, v
 	SVO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
 	return SVO_OK;
 }
+int svo_memcpy_d2d(int device, void *d_dst, const void *d_src, uint64_t bytes, void *stream) {
+	DeviceGuard guard(device);
+	SVO_CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+	return SVO_OK;
+}
+#ifndef SVO_EMU
+int svo_ipc_export(int device, void *d_ptr, unsigned char handle[SVO_IPC_HANDLE_BYTES]) {
+	static_assert(sizeof(cudaIpcMemHandle_t) == SVO_IPC_HANDLE_BYTES, "handle size");
+	if (!d_ptr || !handle) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	DeviceGuard guard(device);
+	cudaIpcMemHandle_t h;
+	SVO_CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+	memcpy(handle, &h, sizeof(h));
+	return SVO_OK;
+}
+int svo_ipc_open(int device, const unsigned char handle[SVO_IPC_HANDLE_BYTES], void **out) {
+	if (!out || !handle) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	DeviceGuard guard(device);
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof(h));
+	SVO_CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+	return SVO_OK;
+}
+int svo_ipc_close(int device, void *d_ptr) {
+	DeviceGuard guard(device);
+	SVO_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+	return SVO_OK;
+}
+#else
+int svo_ipc_export(int, void *, unsigned char *) { return fail(SVO_ERR_UNSUPPORTED, "no IPC in the emulation build"); }
+int svo_ipc_open(int, const unsigned char *, void **) { return fail(SVO_ERR_UNSUPPORTED, "no IPC in the emulation build"); }
+int svo_ipc_close(int, void *) { return fail(SVO_ERR_UNSUPPORTED, "no IPC in the emulation build"); }
+#endif
 int svo_stream_synchronize(int device, void *stream) {
 	DeviceGuard guard(device);
 	SVO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));

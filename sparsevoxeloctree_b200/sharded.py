@@ -1,0 +1,215 @@
+"""Octant-sharded SVO build over several GPUs -- one process per GPU, torch.distributed
+for the plumbing.
+
+The grid is split by the top-level octant bits (child slot x | y<<1 | z<<2 of the root block,
+shader/octree_tag_node.comp:24-25).  Octant o belongs to rank o % world_size, which is the x / xy / xyz
+split for 2 / 4 / 8 ranks.  Every rank voxelizes and builds the (level-1)-deep subtree of each of its
+octants in cube-local coordinates (svo_shard); the only exchange step is:
+
+  1. all_gather of the 8 subtree sizes (words)                         -- tiny collective
+  2. identical exclusive scan on every rank -> base word offset of each subtree
+  3. every rank adds its base to the child pointers of its subtrees WHILE storing them into rank 0's
+     buffer: k_rebase_copy writes straight through a CUDA-IPC mapping of that buffer (NVLink P2P), so the
+     pointer fix-up is fused with the transfer; without P2P it stages locally and NCCL send/recv moves it
+  4. rank 0 writes the 8 root words (0x80000000 | base_o, or 0 for an empty octant).
+
+The union of the shards' fragment sets equals the single-GPU fragment set exactly (fragments are culled
+against the half-open voxel window inside the raster kernels), so the stitched tree canonicalises to the
+single-GPU tree bit for bit.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ROOT_WORDS = 8
+
+
+def octants_of_rank(rank: int, world: int):
+    """Octant ids (x | y<<1 | z<<2) owned by `rank`."""
+    if world not in (1, 2, 4, 8):
+        raise ValueError("world size must be 1, 2, 4 or 8 (octant sharding)")
+    return [o for o in range(8) if o % world == rank]
+
+
+def octant_cube(o: int):
+    return (o & 1, (o >> 1) & 1, (o >> 2) & 1)
+
+
+def plan_offsets(words_per_octant):
+    """words_per_octant[o] = node words of octant o's subtree (0 when the octant is empty).
+    Returns (base word offset per octant, total words).  Subtrees are laid out after the root block in
+    octant order; every rank computes the same plan from the all-gathered sizes."""
+    base, run = [], ROOT_WORDS
+    for w in words_per_octant:
+        w = int(w)
+        if w % 8:
+            raise ValueError("subtree sizes are multiples of 8 words")
+        base.append(run if w else 0)
+        run += w
+    if run >= 1 << 30:
+        raise OverflowError("stitched octree needs >= 2^30 words: 30-bit child pointers cannot address it")
+    return base, run
+
+
+def root_block(bases, words_per_octant) -> np.ndarray:
+    """The 8 root words: an internal node pointing at each non-empty octant's subtree root block."""
+    out = np.zeros(ROOT_WORDS, dtype=np.uint32)
+    for o in range(8):
+        if int(words_per_octant[o]):
+            out[o] = np.uint32(0x80000000 | int(bases[o]))
+    return out
+
+
+def rebase_words_numpy(words: np.ndarray, base: int) -> np.ndarray:
+    """Host restatement of k_rebase_copy for the CPU (gloo) tests: add base to internal child pointers."""
+    w = np.asarray(words, dtype=np.uint32).copy()
+    internal = (w & np.uint32(0xC0000000)) == np.uint32(0x80000000)
+    w[internal] += np.uint32(base)
+    return w
+
+
+def exchange_sizes(torch, dist, local_sizes, world: int, device):
+    """all_gather of the per-octant subtree sizes; returns words[8] indexed by octant id (same on every rank)."""
+    local = torch.tensor([int(v) for v in local_sizes], dtype=torch.int64, device=device)
+    if world == 1:
+        return [int(v) for v in local_sizes]
+    out = torch.zeros(8, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, local)
+    # all_gather orders by rank; octant o is slot (o // world) of rank (o % world)
+    per_rank = out.view(world, 8 // world).cpu().numpy()
+    return [int(per_rank[o % world, o // world]) for o in range(8)]
+
+
+class ShardedSVO:
+    """Multi-GPU build driver.  `dist` is torch.distributed (initialised, backend nccl on GPUs); `torch` is
+    passed in so that this module imports without it.  With dist=None it runs all 8 octants on one GPU
+    ("virtual shards"): that is how a level-14 grid, whose 42 Morton bits + 24 colour bits do not fit one
+    64-bit fragment, is built on a single device."""
+
+    def __init__(self, torch, dist, mesh, level: int, mode: int, device: int, lib=None, use_ipc: bool = True):
+        from . import api
+        self.torch, self.dist, self.api = torch, dist, api
+        self.lib = lib or api.get_library()
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+        self.device, self.level, self.mode = device, level, mode
+        self.octants = octants_of_rank(self.rank, self.world)
+        self.scene = api.Scene.Create(mesh, device=device, lib=self.lib)
+        self.vox, self.builders = [], []
+        for o in self.octants:
+            v = api.Voxelizer.Create(self.scene, level, mode, shard=(1, octant_cube(o)))
+            self.vox.append(v)
+            self.builders.append(api.OctreeBuilder.Create(v))
+        self.tdev = torch.device("cuda", device) if torch is not None else None
+        self.final = None       # rank 0: the stitched node buffer (device pointer, cudaMalloc'ed)
+        self.final_cap = 0
+        self.peer_final = 0     # ranks > 0: rank 0's buffer mapped through CUDA IPC
+        self.use_ipc = use_ipc and self.world > 1
+        self.total_words = 0
+        self.bases = [0] * 8
+        self.words = [0] * 8
+        self.stage = None
+
+    # -- rank 0 owns a grow-only arena for the stitched tree (like the reference's up-front octree buffer) --
+    def _ensure_final(self, words: int):
+        torch, dist = self.torch, self.dist
+        need = int(words)
+        if self.world == 1:
+            if need <= self.final_cap:
+                return
+        else:
+            grow = torch.tensor([1 if (self.rank == 0 and need > self.final_cap) else 0], device=self.tdev)
+            dist.broadcast(grow, 0)
+            if int(grow.item()) == 0:
+                return
+        cap = max(need + need // 4, 1 << 20)
+        if self.rank == 0:
+            if self.final:
+                self.lib.free(self.final, self.device)
+            self.final = self.lib.malloc(cap * 4, self.device)
+            self.final_cap = cap
+        if self.use_ipc:
+            handle = [self.lib.ipc_export(self.final, self.device) if self.rank == 0 else None]
+            dist.broadcast_object_list(handle, 0)
+            if self.rank != 0:
+                if self.peer_final:
+                    self.lib.ipc_close(self.peer_final, self.device)
+                self.peer_final = self.lib.ipc_open(handle[0], self.device)
+                self.final_cap = cap
+
+    def step(self, stream=None):
+        """One sharded build: local subtrees, size exchange, fused rebase + gather, root block on rank 0."""
+        torch, dist = self.torch, self.dist
+        for v, b in zip(self.vox, self.builders):
+            v.CmdVoxelize(stream)
+            b.CmdBuild(stream)
+        local = [b.GetOctreeRange() // 4 if b.GetLeafCount() else 0 for b in self.builders]
+        words = exchange_sizes(torch, dist, local, self.world, self.tdev)
+        self.words = words
+        self.bases, self.total_words = plan_offsets(words)
+        self._ensure_final(self.total_words)
+        if self.rank == 0 or self.use_ipc:
+            dst = self.final if self.rank == 0 else self.peer_final
+            for o, b in zip(self.octants, self.builders):
+                if words[o]:
+                    b.RebaseCopy(dst, self.bases[o], self.bases[o], stream)
+        if self.world > 1 and not self.use_ipc:
+            self._gather_nccl(stream)
+        if self.rank == 0:
+            rb = root_block(self.bases, words)
+            self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, rb.ctypes.data, rb.nbytes, 0))
+        self.lib.check(self.lib.dll.svo_stream_synchronize(self.device, self.api._stream_ptr(stream)))
+        if self.world > 1:
+            dist.barrier()  # remote stores into rank 0's buffer are complete
+        return self.total_words * 4
+
+    def _gather_nccl(self, stream):
+        """Fallback without P2P mapping: rebase into a local staging tensor, NCCL send/recv to rank 0."""
+        torch, dist = self.torch, self.dist
+        if self.rank != 0:
+            n = sum(self.words[o] for o in self.octants)
+            if self.stage is None or self.stage.numel() < n:
+                self.stage = torch.empty(max(n, 8), dtype=torch.int32, device=self.tdev)
+            off = 0
+            for o, b in zip(self.octants, self.builders):
+                if self.words[o]:
+                    b.RebaseCopy(self.stage.data_ptr(), off, self.bases[o], stream)
+                    off += self.words[o]
+            torch.cuda.synchronize(self.tdev)
+            off = 0
+            for o in self.octants:
+                if self.words[o]:
+                    dist.send(self.stage[off:off + self.words[o]], 0)
+                    off += self.words[o]
+        else:
+            for o in range(8):
+                r = o % self.world
+                if r != 0 and self.words[o]:
+                    if self.stage is None or self.stage.numel() < self.words[o]:
+                        self.stage = torch.empty(self.words[o], dtype=torch.int32, device=self.tdev)
+                    buf = self.stage[: self.words[o]]
+                    dist.recv(buf, r)
+                    self.lib.check(self.lib.dll.svo_memcpy_d2d(self.device, self.final + self.bases[o] * 4, buf.data_ptr(),
+                                                               self.words[o] * 4, 0))
+
+    def leaf_count_local(self) -> int:
+        return sum(b.GetLeafCount() for b in self.builders)
+
+    def fragment_count_local(self) -> int:
+        return sum(v.GetVoxelFragmentCount() for v in self.vox)
+
+    def octree_to_host(self) -> np.ndarray:
+        assert self.rank == 0
+        return self.lib.to_host(self.final, np.uint32, self.total_words, self.device)
+
+    def destroy(self):
+        for b in self.builders:
+            b.Destroy()
+        for v in self.vox:
+            v.Destroy()
+        self.scene.Destroy()
+        if self.rank == 0 and self.final:
+            self.lib.free(self.final, self.device)
+            self.final = None
+        if self.peer_final:
+            self.lib.ipc_close(self.peer_final, self.device)
+            self.peer_final = 0

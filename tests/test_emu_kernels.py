@@ -1,0 +1,74 @@
+"""Kernel-LOGIC tests on the CPU: the product's .cu sources compiled against tests/cpu_emu/cuda_emu.h
+(one OS thread per CUDA thread) and driven through the same C ABI / api.py as on the GPU.
+This is test infrastructure only -- the product never loads this library.  Sizes are tiny: the emulator
+is slow; the real parity tests are tests/test_gpu_parity.py (-m gpu)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu_emu"))
+import build_emu  # noqa: E402
+
+from sparsevoxeloctree_b200 import api, scenes  # noqa: E402
+from tests.parity import check_against_oracle  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = api.Library(build_emu.build())
+    assert b"emulation" in L.dll.svo_version()
+    L.dll.svo_emu_set_lookback_aggregate_only(0)
+    return L
+
+
+@pytest.mark.parametrize("n", [0, 1, 33, 4096, 4097, 9000])
+def test_onesweep_logic(emu, n):
+    rng = np.random.default_rng(n)
+    k = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+    out = emu.sort_u64(k, 24, 24 + 21)
+    key = (k >> np.uint64(24)) & np.uint64((1 << 21) - 1)
+    assert (out == k[np.argsort(key, kind="stable")]).all()
+
+
+def test_onesweep_long_lookback_chain(emu):
+    # tiles publish aggregates only: every tile walks the full chain (the path sequential emulation never takes)
+    emu.dll.svo_emu_set_lookback_aggregate_only(1)
+    try:
+        rng = np.random.default_rng(3)
+        k = rng.integers(0, 1 << 40, 40000, dtype=np.uint64) << np.uint64(24)
+        out = emu.sort_u64(k, 24, 24 + 16)
+        key = (k >> np.uint64(24)) & np.uint64(0xFFFF)
+        assert (out == k[np.argsort(key, kind="stable")]).all()
+    finally:
+        emu.dll.svo_emu_set_lookback_aggregate_only(0)
+
+
+@pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT])
+def test_full_path_small_soup(emu, mode):
+    check_against_oracle(emu, scenes.random_soup(250, 7), 6, mode)
+
+
+def test_full_path_large_triangles_and_chained_scans(emu):
+    # big triangles -> row-span path; aggregate-only look-back -> 32-wide window walk in every chained scan
+    emu.dll.svo_emu_set_lookback_aggregate_only(1)
+    try:
+        info = check_against_oracle(emu, scenes.random_soup(120, 8, 0.2, 1.5), 7, api.CONSERVATIVE_EXACT)
+        assert info["fragments"] > 30000
+    finally:
+        emu.dll.svo_emu_set_lookback_aggregate_only(0)
+
+
+def test_full_path_shard(emu):
+    check_against_oracle(emu, scenes.random_soup(150, 9, 0.05, 1.0), 6, api.CONSERVATIVE_EXACT, shard=(1, (1, 0, 1)))
+
+
+def test_full_path_heightfield(emu):
+    check_against_oracle(emu, scenes.heightfield(21), 6, api.CENTER)
+
+
+def test_empty_scene(emu):
+    m = scenes.Mesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), np.zeros(0, scenes.DRAW_DTYPE), "empty")
+    info = check_against_oracle(emu, m, 4, api.CENTER)
+    assert info["range"] == 32 and info["fragments"] == 0
