@@ -70,9 +70,9 @@ def rebase_words_numpy(words: np.ndarray, base: int) -> np.ndarray:
 
 def exchange_sizes(torch, dist, local_sizes, world: int, device):
     """all_gather of the per-octant subtree sizes; returns words[8] indexed by octant id (same on every rank)."""
-    local = torch.tensor([int(v) for v in local_sizes], dtype=torch.int64, device=device)
     if world == 1:
         return [int(v) for v in local_sizes]
+    local = torch.tensor([int(v) for v in local_sizes], dtype=torch.int64, device=device)
     out = torch.zeros(8, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(out, local)
     # all_gather orders by rank; octant o is slot (o // world) of rank (o % world)
