@@ -28,7 +28,9 @@
 #define SVO_LAUNCH_INDEP(grid, block, stream, kernel, ...) \
 	(++svo::g_launches, svo_emu::launch((grid), (block), 0, false, [=]() { kernel(__VA_ARGS__); }))
 #define SVO_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(svo_emu::tctx.dyn_smem)
+#define SVO_EMU_WARP_ORDER() __syncwarp()
 #else
+#define SVO_EMU_WARP_ORDER() ((void)0)
 #define SVO_LAUNCH(grid, block, smem, stream, kernel, ...) \
 	(++svo::g_launches, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define SVO_LAUNCH_INDEP(grid, block, stream, kernel, ...) \

@@ -9,75 +9,98 @@
 //   k_radix_histogram : one read of the keys -> digit histograms of every pass (shared-memory bins)
 //   k_radix_scan_bins : exclusive scan of each pass's bins
 //   k_onesweep_pass   : per pass, ONE read + ONE write of the keys: per-tile ranking with
-//                       __match_any_sync, per-digit decoupled look-back across tiles (tiles numbered
-//                       by a ticket so predecessors are always running), shared-memory reorder,
-//                       coalesced run-wise scatter.
+//                       __match_any_sync + one shared-memory atomic per digit group, per-digit decoupled
+//                       look-back across tiles (tiles numbered by a ticket so predecessors are always
+//                       running; several predecessor states in flight per step), shared-memory reorder,
+//                       run-wise coalesced scatter.
+// Digits are up to 9 bits wide (512 bins): 36 Morton bits at level 12 take 4 passes.
 // Traffic: 8*F*(2P+1) bytes for P passes -- HBM bound by design.
 #pragma once
 #include "scan.cuh"
 
 namespace svo {
 
-constexpr int RADIX_BITS = 8, RADIX = 1 << RADIX_BITS;
+#ifndef SVO_MAX_RADIX_BITS
+#define SVO_MAX_RADIX_BITS 9
+#endif
+constexpr int MAX_RADIX_BITS = SVO_MAX_RADIX_BITS, MAX_RADIX = 512;
 constexpr int MAX_PASSES = 8;
 constexpr int HIST_BLOCK = 256, HIST_ITEMS = 16;
 
 struct SortPasses {
 	uint32_t n_pass;
+	uint32_t max_bits; // widest digit
 	uint32_t shift[MAX_PASSES];
+	uint32_t bits[MAX_PASSES];
 	uint32_t mask[MAX_PASSES];
 };
+// Fewest passes with digits <= MAX_RADIX_BITS, widths balanced (36 bits -> 9,9,9,9 ; 30 -> 8,8,7,7).
 inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit) {
 	SortPasses sp{};
+	const uint32_t total = end_bit - begin_bit;
+	if (total == 0) return sp;
+	uint32_t np = (total + MAX_RADIX_BITS - 1) / MAX_RADIX_BITS;
+	if (np > MAX_PASSES) np = MAX_PASSES; // 64 bits / 9 = 8 passes at most
 	uint32_t b = begin_bit;
-	while (b < end_bit && sp.n_pass < MAX_PASSES) {
-		uint32_t w = end_bit - b < (uint32_t)RADIX_BITS ? end_bit - b : (uint32_t)RADIX_BITS;
-		sp.shift[sp.n_pass] = b;
-		sp.mask[sp.n_pass] = (1u << w) - 1u;
-		++sp.n_pass;
+	for (uint32_t p = 0; p < np; ++p) {
+		const uint32_t left = end_bit - b, passes_left = np - p;
+		const uint32_t w = (left + passes_left - 1) / passes_left;
+		sp.shift[p] = b;
+		sp.bits[p] = w;
+		sp.mask[p] = (1u << w) - 1u;
+		if (w > sp.max_bits) sp.max_bits = w;
 		b += w;
 	}
+	sp.n_pass = np;
 	return sp;
 }
 
 // ---- histogram of every pass in one read ---------------------------------------------------------------
+// Spatially coherent fragments share their upper digits: one OR-reduction of (key ^ lane 0's key) tells, for
+// every pass at once, whether the whole warp falls into one bin -- then a single lane adds 32.
 __global__ void __launch_bounds__(HIST_BLOCK)
-    k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n, SortPasses sp, uint32_t *__restrict__ g_hist /*[pass][RADIX]*/) {
-	__shared__ uint32_t s_hist[MAX_PASSES * RADIX];
-	for (uint32_t i = threadIdx.x; i < sp.n_pass * RADIX; i += HIST_BLOCK) s_hist[i] = 0;
+    k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n, SortPasses sp, uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/) {
+	__shared__ uint32_t s_hist[MAX_PASSES * MAX_RADIX];
+	for (uint32_t i = threadIdx.x; i < sp.n_pass * MAX_RADIX; i += HIST_BLOCK) s_hist[i] = 0;
 	__syncthreads();
+	const int lane = threadIdx.x & 31;
 	const uint64_t per_block = (uint64_t)HIST_BLOCK * HIST_ITEMS;
 	for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < n; base += (uint64_t)gridDim.x * per_block) {
+		const bool full = base + per_block <= n;
 #pragma unroll 4
 		for (int i = 0; i < HIST_ITEMS; ++i) {
 			const uint64_t idx = base + (uint64_t)i * HIST_BLOCK + threadIdx.x;
-			const bool ok = idx < n;
+			const bool ok = full || idx < n;
 			const uint64_t k = ok ? keys[idx] : 0;
+			const uint64_t k0 = __shfl_sync(FULL_MASK, k, 0);
+			const uint64_t diff = (k ^ k0) | (ok ? 0ull : ~0ull);
+			const uint32_t dlo = __reduce_or_sync(FULL_MASK, (uint32_t)diff);
+			const uint32_t dhi = __reduce_or_sync(FULL_MASK, (uint32_t)(diff >> 32));
+			const uint64_t any_diff = ((uint64_t)dhi << 32) | dlo;
 			for (uint32_t p = 0; p < sp.n_pass; ++p) {
-				const uint32_t d = ok ? ((uint32_t)(k >> sp.shift[p]) & sp.mask[p]) : 0xffffffffu;
-				// spatially coherent fragments share their upper digits: one add per warp when uniform
-				const uint32_t d0 = __shfl_sync(FULL_MASK, d, 0);
-				if (__all_sync(FULL_MASK, d == d0)) {
-					if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&s_hist[p * RADIX + d], 32u);
+				const uint32_t d = (uint32_t)(k >> sp.shift[p]) & sp.mask[p];
+				const bool uniform = ((uint32_t)(any_diff >> sp.shift[p]) & sp.mask[p]) == 0u;
+				if (uniform) {
+					if (lane == 0) atomicAdd(&s_hist[p * MAX_RADIX + d], 32u);
 				} else if (ok)
-					atomicAdd(&s_hist[p * RADIX + d], 1u);
+					atomicAdd(&s_hist[p * MAX_RADIX + d], 1u);
 			}
 		}
 	}
 	__syncthreads();
-	for (uint32_t i = threadIdx.x; i < sp.n_pass * RADIX; i += HIST_BLOCK) {
+	for (uint32_t i = threadIdx.x; i < sp.n_pass * MAX_RADIX; i += HIST_BLOCK) {
 		const uint32_t c = s_hist[i];
 		if (c) atomicAdd(&g_hist[i], c);
 	}
 }
 
-// exclusive scan of each pass's RADIX bins, in place (grid = n_pass blocks of RADIX threads)
-__global__ void __launch_bounds__(RADIX) k_radix_scan_bins(uint32_t *g_hist) {
-	__shared__ uint32_t s_warp[RADIX / 32 + 1];
-	uint32_t *h = g_hist + blockIdx.x * RADIX;
+// exclusive scan of each pass's MAX_RADIX bins, in place (grid = n_pass blocks of MAX_RADIX threads)
+__global__ void __launch_bounds__(MAX_RADIX) k_radix_scan_bins(uint32_t *g_hist) {
+	__shared__ uint32_t s_warp[MAX_RADIX / 32 + 1];
+	uint32_t *h = g_hist + blockIdx.x * MAX_RADIX;
 	const uint32_t v = h[threadIdx.x];
 	uint32_t total;
-	const uint32_t e = block_exclusive_sum<RADIX, uint32_t>(v, total, s_warp);
+	const uint32_t e = block_exclusive_sum<MAX_RADIX, uint32_t>(v, total, s_warp);
 	h[threadIdx.x] = e;
 }
 
@@ -94,129 +117,207 @@ template <class StateT> struct LbCodec {
 	static SVO_DEV uint64_t value(StateT s) { return (uint64_t)(s & VMASK); }
 };
 
-template <int BLOCK, int ITEMS, class StateT>
-__global__ void __launch_bounds__(BLOCK)
+template <int BLOCK, int ITEMS, int RBITS> struct OnesweepCfg {
+	static constexpr int RADIX = 1 << RBITS;
+	static constexpr int NB = RADIX + 1; // bin RADIX collects the padding of the last tile
+	static constexpr int NW = BLOCK / 32;
+	static constexpr int TILE = BLOCK * ITEMS;
+	static constexpr int DPT = RADIX > BLOCK ? RADIX / BLOCK : 1; // consecutive digits per digit-thread
+	static constexpr int DTHREADS = RADIX / DPT;                  // threads that own digits
+	static constexpr int NBP = NB + (NB & 1);
+	static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)NW * NB * 4 + (size_t)NBP * 4 + (size_t)RADIX * 4 + 64;
+	static_assert(BLOCK % 32 == 0 && DTHREADS % 32 == 0 && DTHREADS <= BLOCK, "digit threads must be whole warps");
+	static_assert(((NW * NB + NBP) & 1) == 0 || true, "");
+};
+
+#ifndef SVO_OS_EXPERIMENT
+#define SVO_OS_EXPERIMENT 0 // timing experiments only (bit 0: linear writes, bit 1: no look-back); results are wrong when set
+#endif
+#ifndef SVO_OS_BALLOT
+#define SVO_OS_BALLOT 0
+#endif
+#ifndef SVO_OS_LOOKBACK_DEPTH
+#define SVO_OS_LOOKBACK_DEPTH 8
+#endif
+constexpr int LOOKBACK_DEPTH = SVO_OS_LOOKBACK_DEPTH; // predecessor states in flight per look-back step
+
+SVO_DEV void lb_backoff() {
+#if defined(__CUDA_ARCH__)
+	__nanosleep(64);
+#endif
+}
+
+// Tiles are numbered by blockIdx.x: thread blocks of a 1-D grid are dispatched in index order, so every
+// predecessor of a running tile has been started (and running blocks are never preempted) -- the forward
+// progress the look-back needs, without a ticket atomic in front of the tile's loads.
+template <int BLOCK, int ITEMS, int RBITS, int MINB, class StateT>
+__global__ void __launch_bounds__(BLOCK, MINB)
     k_onesweep_pass(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out, uint64_t n, uint32_t shift,
                     uint32_t mask, uint32_t pass, const uint32_t *__restrict__ g_bins /* exclusive, this pass */,
-                    StateT *state /*[tiles][RADIX]*/, uint32_t *ticket) {
-	static_assert(BLOCK % 32 == 0 && BLOCK >= RADIX, "one thread per digit is assumed");
-	constexpr int NW = BLOCK / 32;
-	constexpr int TILE = BLOCK * ITEMS;
-	constexpr int NB = RADIX + 1; // bin RADIX collects the padding of the last tile
+                    StateT *state /*[tiles][RADIX]*/) {
+	using C = OnesweepCfg<BLOCK, ITEMS, RBITS>;
+	constexpr int RADIX = C::RADIX, NB = C::NB, NW = C::NW, TILE = C::TILE, DPT = C::DPT, DTHREADS = C::DTHREADS;
 	using LB = LbCodec<StateT>;
-	SVO_DYN_SMEM(uint64_t, s_keys);                                     // TILE keys
-	uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_keys + TILE);     // NW * NB
-	uint32_t *s_tile_off = s_hist + NW * NB;                            // NB: first slot of each digit inside the tile
-	uint64_t *s_gofs = reinterpret_cast<uint64_t *>(s_tile_off + NB + (NB & 1)); // RADIX: global offset minus tile offset
-	__shared__ uint32_t s_scan[BLOCK / 32 + 1];
-	__shared__ uint32_t s_ticket;
+	SVO_DYN_SMEM(uint64_t, s_keys);                                  // TILE keys
+	uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_keys + TILE);  // NW * NB: per-warp digit counters, then slot bases
+	uint32_t *s_tile_off = s_hist + NW * NB;                         // NB: first slot of each digit inside the tile
+	uint32_t *s_gofs = s_tile_off + NB;                              // RADIX: global offset minus tile offset (mod 2^32)
+	__shared__ uint32_t s_wsum[RADIX / 32 + 1];
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t tile = take_ticket(ticket, &s_ticket);
+	const uint32_t tile = blockIdx.x;
 	const uint64_t tile_base = (uint64_t)tile * TILE;
 	const uint32_t tile_count = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
 
-	for (int i = threadIdx.x; i < NW * NB; i += BLOCK) s_hist[i] = 0;
-
 	// warp-striped load: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS), item i of lane l is element i*32 + l
 	uint64_t key[ITEMS];
-	uint32_t rank[ITEMS];
 	const uint32_t wbase = warp * 32 * ITEMS;
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
 		const uint32_t e = wbase + i * 32 + lane;
 		key[i] = e < tile_count ? keys_in[tile_base + e] : ~0ull;
 	}
+	for (int i = threadIdx.x; i < NW * NB; i += BLOCK) s_hist[i] = 0; // overlaps the loads in flight
 	__syncthreads();
 
-	// rank inside the warp, digit by digit group (stable: items in increasing i, lanes in increasing l)
+	// rank inside the warp.  Stable: items in increasing i, lanes in increasing l.  The leader (lowest lane) of
+	// each digit group bumps the warp's counter with ONE shared-memory atomic; a warp's atomics execute in
+	// program order, so no warp barrier is needed between items and the 3 stages pipeline across items.
 	uint32_t *wh = s_hist + warp * NB;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	uint32_t dig[ITEMS];
+	unsigned peers[ITEMS];
+	uint32_t rank[ITEMS];
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
 		const uint32_t e = wbase + i * 32 + lane;
-		const uint32_t d = e < tile_count ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
-		const unsigned peers = __match_any_sync(FULL_MASK, d);
-		const int leader = __ffs((int)peers) - 1;
-		uint32_t base = 0;
-		if (lane == leader) {
-			base = wh[d];
-			wh[d] = base + (uint32_t)__popc(peers);
+		dig[i] = e < tile_count ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
+#if SVO_OS_BALLOT
+		// multi-split by ballots: one vote per digit bit (MATCH.ANY serialises over the distinct values of the
+		// warp, ~32 for the low digits of a surface's Morton codes)
+		unsigned pm = FULL_MASK;
+#pragma unroll
+		for (int b = 0; b < RBITS; ++b) {
+			const uint32_t bit = (dig[i] >> b) & 1u;
+			const unsigned m = __ballot_sync(FULL_MASK, bit);
+			pm &= ~(m ^ (0u - bit));
 		}
-		base = __shfl_sync(FULL_MASK, base, leader);
-		rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-		__syncwarp();
+		if (tile_count < (uint32_t)TILE) { // padding exists only in the last tile (block-uniform branch)
+			const uint32_t bit = dig[i] >> RBITS;
+			const unsigned m = __ballot_sync(FULL_MASK, bit);
+			pm &= ~(m ^ (0u - bit));
+		}
+		peers[i] = pm;
+#else
+		peers[i] = __match_any_sync(FULL_MASK, dig[i]);
+#endif
+	}
+#pragma unroll
+	for (int i = 0; i < ITEMS; ++i) {
+		rank[i] = 0;
+		if ((peers[i] & lt_mask) == 0u) rank[i] = atomicAdd(&wh[dig[i]], (uint32_t)__popc(peers[i]));
+		SVO_EMU_WARP_ORDER(); // hardware issues a warp's atomics in program order; the emulator's lanes are free-running
+	}
+#pragma unroll
+	for (int i = 0; i < ITEMS; ++i) {
+		const int leader = __ffs((int)peers[i]) - 1;
+		rank[i] = __shfl_sync(FULL_MASK, rank[i], leader) + (uint32_t)__popc(peers[i] & lt_mask);
 	}
 	__syncthreads();
 
-	// per digit: exclusive prefix over the warps, tile total, look-back over the preceding tiles
-	uint32_t bin_total = 0;
-	if (threadIdx.x < NB) {
-		const uint32_t d = threadIdx.x;
-		uint32_t run = 0;
+	// per digit: exclusive prefix over the warps and the tile total; publish the aggregate right away
+	const uint32_t AGG = (2u * pass + 1u) & 3u, PRE = (2u * pass + 2u) & 3u;
+	uint32_t bin_total[DPT];
+	uint32_t my_sum = 0;
+	if (threadIdx.x < DTHREADS) {
 #pragma unroll
-		for (int w = 0; w < NW; ++w) {
-			const uint32_t c = s_hist[w * NB + d];
-			s_hist[w * NB + d] = run;
-			run += c;
+		for (int j = 0; j < DPT; ++j) {
+			const uint32_t d = threadIdx.x * DPT + j;
+			uint32_t run = 0;
+#pragma unroll
+			for (int w = 0; w < NW; ++w) {
+				const uint32_t c = s_hist[w * NB + d];
+				s_hist[w * NB + d] = run;
+				run += c;
+			}
+			bin_total[j] = run;
+			my_sum += run;
+			*reinterpret_cast<volatile StateT *>(state + (uint64_t)tile * RADIX + d) = LB::pack(tile == 0 ? PRE : AGG, run);
 		}
-		bin_total = run;
 	}
-	// BLOCK >= RADIX; the padding bin (d == RADIX) is handled by thread RADIX when BLOCK > RADIX, else folded below
-	uint32_t scan_in = threadIdx.x < RADIX ? bin_total : 0u;
-	uint32_t tile_total;
-	const uint32_t tile_off = block_exclusive_sum<BLOCK, uint32_t>(scan_in, tile_total, s_scan);
-	if (threadIdx.x < RADIX) s_tile_off[threadIdx.x] = tile_off;
-	if (threadIdx.x == 0) s_tile_off[RADIX] = tile_total; // padding sorts after every real key
-	if (BLOCK == RADIX && threadIdx.x == 0) {
-		// padding bin: prefix over warps (only the last tile has padding)
-		uint32_t run = 0;
+	// exclusive scan of the tile totals over the digits (digit threads are whole warps)
+	uint32_t inc = 0;
+	if (threadIdx.x < DTHREADS) {
+		inc = warp_inclusive_sum(my_sum, lane);
+		if (lane == 31) s_wsum[warp] = inc;
+	}
+	__syncthreads();
+	if (threadIdx.x < DTHREADS) {
+		uint32_t wpre = 0;
+#pragma unroll
+		for (int w = 0; w < DTHREADS / 32; ++w) wpre += w < warp ? s_wsum[w] : 0u;
+		uint32_t run = wpre + inc - my_sum; // first slot of this thread's first digit
+#pragma unroll
+		for (int j = 0; j < DPT; ++j) {
+			const uint32_t d = threadIdx.x * DPT + j;
+			s_tile_off[d] = run;
+#pragma unroll
+			for (int w = 0; w < NW; ++w) s_hist[w * NB + d] += run; // slot base of (warp, digit)
+			run += bin_total[j];
+		}
+	}
+	if (threadIdx.x == BLOCK - 1) { // padding bin (only the last tile has padding): after every real key
+		uint32_t run = tile_count;
 		for (int w = 0; w < NW; ++w) {
 			const uint32_t c = s_hist[w * NB + RADIX];
 			s_hist[w * NB + RADIX] = run;
 			run += c;
 		}
 	}
-
-	if (threadIdx.x < RADIX) {
-		const uint32_t d = threadIdx.x;
-		const uint32_t STALE = (2u * pass) & 3u, AGG = (2u * pass + 1u) & 3u, PRE = (2u * pass + 2u) & 3u;
-		(void)STALE;
-		StateT *my = state + (uint64_t)tile * RADIX + d;
-		uint64_t excl = 0;
-		if (tile == 0) {
-			*reinterpret_cast<volatile StateT *>(my) = LB::pack(PRE, bin_total);
-		} else {
-			*reinterpret_cast<volatile StateT *>(my) = LB::pack(AGG, bin_total);
-			int64_t t = (int64_t)tile - 1;
-			for (;;) {
-				const StateT s = *reinterpret_cast<const volatile StateT *>(state + (uint64_t)t * RADIX + d);
-				const uint32_t c = LB::code(s);
-				if (c == PRE) {
-					excl += LB::value(s);
-					break;
-				}
-				if (c == AGG) {
-					excl += LB::value(s);
-					--t; // t >= 0 always: tile 0 publishes PRE
-				}
-				// otherwise: not published yet in this pass, poll again
-			}
-#ifdef SVO_EMU
-			if (!g_emu_lookback_aggregate_only)
-#endif
-				*reinterpret_cast<volatile StateT *>(my) = LB::pack(PRE, excl + bin_total);
-		}
-		s_gofs[d] = (uint64_t)g_bins[d] + excl - (uint64_t)tile_off;
-	}
 	__syncthreads();
 
-	// reorder through shared memory
+	// reorder through shared memory (needs tile-local offsets only: runs while predecessors publish)
 #pragma unroll
-	for (int i = 0; i < ITEMS; ++i) {
-		const uint32_t e = wbase + i * 32 + lane;
-		const uint32_t d = e < tile_count ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
-		const uint32_t pos = s_tile_off[d] + s_hist[warp * NB + d] + rank[i];
-		s_keys[pos] = key[i];
+	for (int i = 0; i < ITEMS; ++i) s_keys[s_hist[warp * NB + dig[i]] + rank[i]] = key[i];
+
+	// decoupled look-back, per digit, LOOKBACK_DEPTH predecessor states in flight
+	if (threadIdx.x < DTHREADS) {
+#pragma unroll
+		for (int j = 0; j < DPT; ++j) {
+			const uint32_t d = threadIdx.x * DPT + j;
+			uint64_t excl = 0;
+			if (tile != 0 && !(SVO_OS_EXPERIMENT & 2)) {
+				int64_t t = (int64_t)tile - 1;
+				bool done = false;
+				while (!done) {
+					StateT s[LOOKBACK_DEPTH];
+#pragma unroll
+					for (int q = 0; q < LOOKBACK_DEPTH; ++q)
+						s[q] = t - q >= 0 ? *reinterpret_cast<const volatile StateT *>(state + (uint64_t)(t - q) * RADIX + d)
+						                  : LB::pack(PRE, 0);
+					int adv = 0;
+#pragma unroll
+					for (int q = 0; q < LOOKBACK_DEPTH; ++q) {
+						if (done || adv != q) continue; // stop at the first state that is not ready yet
+						const uint32_t c = LB::code(s[q]);
+						if (c == PRE) {
+							excl += LB::value(s[q]);
+							done = true;
+						} else if (c == AGG) {
+							excl += LB::value(s[q]);
+							++adv;
+						}
+					}
+					t -= adv;
+					if (!done && adv == 0) lb_backoff();
+				}
+#ifdef SVO_EMU
+				if (!g_emu_lookback_aggregate_only)
+#endif
+					*reinterpret_cast<volatile StateT *>(state + (uint64_t)tile * RADIX + d) = LB::pack(PRE, excl + bin_total[j]);
+			}
+			s_gofs[d] = (uint32_t)((uint64_t)g_bins[d] + excl) - s_tile_off[d];
+		}
 	}
 	__syncthreads();
 
@@ -227,23 +328,49 @@ __global__ void __launch_bounds__(BLOCK)
 		if (idx < tile_count) {
 			const uint64_t k = s_keys[idx];
 			const uint32_t d = (uint32_t)(k >> shift) & mask;
-			keys_out[s_gofs[d] + idx] = k;
+#if (SVO_OS_EXPERIMENT & 1)
+			keys_out[tile_base + idx] = k; (void)d;
+#else
+			keys_out[(uint32_t)(s_gofs[d] + idx)] = k;
+#endif
 		}
 	}
 }
 
-template <int BLOCK, int ITEMS> constexpr size_t onesweep_smem_bytes() {
-	return (size_t)BLOCK * ITEMS * 8 + (size_t)(BLOCK / 32) * (RADIX + 1) * 4 + (size_t)(RADIX + 2) * 4 + (size_t)RADIX * 8;
-}
-
 struct SortScratch {
-	DevBuf<uint32_t> hist;   // MAX_PASSES * RADIX
+	DevBuf<uint32_t> hist;   // MAX_PASSES * MAX_RADIX
 	DevBuf<uint32_t> ticket; // MAX_PASSES
 	DevBuf<unsigned char> state;
 	bool attr_set = false;
 };
 
-constexpr int OS_BLOCK = 256, OS_ITEMS = 16;
+// tuning point (tests/bench can override at compile time)
+#ifndef SVO_OS_BLOCK
+#define SVO_OS_BLOCK 512
+#endif
+#ifndef SVO_OS_ITEMS
+#define SVO_OS_ITEMS 12
+#endif
+#ifndef SVO_OS_MINB
+#define SVO_OS_MINB 2
+#endif
+constexpr int OS_BLOCK = SVO_OS_BLOCK, OS_ITEMS = SVO_OS_ITEMS, OS_MINB = SVO_OS_MINB;
+
+template <int RBITS, class StateT>
+inline int launch_onesweep_pass(uint32_t tiles, cudaStream_t s, const uint64_t *src, uint64_t *dst, uint64_t n, uint32_t shift,
+                                uint32_t mask, uint32_t pass, const uint32_t *bins, void *state) {
+	using C = OnesweepCfg<OS_BLOCK, OS_ITEMS, RBITS>;
+	auto k = k_onesweep_pass<OS_BLOCK, OS_ITEMS, RBITS, OS_MINB, StateT>;
+#ifndef SVO_EMU
+	static bool attr_set = false;
+	if (!attr_set) {
+		SVO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+		attr_set = true;
+	}
+#endif
+	SVO_LAUNCH(tiles, OS_BLOCK, C::SMEM, s, k, src, dst, n, shift, mask, pass, bins, reinterpret_cast<StateT *>(state));
+	return 0;
+}
 
 // Sorts n keys on bits [begin_bit, end_bit).  Ping-pongs between a and b; *result receives the buffer that
 // holds the sorted keys.  Stable.
@@ -256,14 +383,20 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 		if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
 		return 0;
 	}
+	if (n >= (1ull << 32)) {
+		set_error("radix_sort_u64: more than 2^32-1 keys");
+		return -4;
+	}
 	constexpr int TILE = OS_BLOCK * OS_ITEMS;
 	const uint32_t tiles = div_up(n, TILE);
 	const bool wide = n >= (1ull << 30);
-	const size_t state_bytes = (size_t)tiles * RADIX * (wide ? 8 : 4);
-	SVO_TRY(sc.hist.reserve(MAX_PASSES * RADIX, s));
+	const bool nine = sp.max_bits > 8;
+	const uint32_t radix = nine ? 512u : 256u;
+	const size_t state_bytes = (size_t)tiles * radix * (wide ? 8 : 4);
+	SVO_TRY(sc.hist.reserve(MAX_PASSES * MAX_RADIX, s));
 	SVO_TRY(sc.ticket.reserve(MAX_PASSES, s));
 	SVO_TRY(sc.state.reserve(state_bytes, s));
-	SVO_CUDA_TRY(cudaMemsetAsync(sc.hist.p, 0, MAX_PASSES * RADIX * sizeof(uint32_t), s));
+	SVO_CUDA_TRY(cudaMemsetAsync(sc.hist.p, 0, MAX_PASSES * MAX_RADIX * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, MAX_PASSES * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, state_bytes, s));
 
@@ -271,28 +404,21 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	const uint32_t hmax = (uint32_t)(n_sm > 0 ? n_sm : 148) * 8u;
 	if (hgrid > hmax) hgrid = hmax;
 	SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, k_radix_histogram, (const uint64_t *)a, n, sp, sc.hist.p);
-	SVO_LAUNCH(sp.n_pass, RADIX, 0, s, k_radix_scan_bins, sc.hist.p);
+	SVO_LAUNCH(sp.n_pass, MAX_RADIX, 0, s, k_radix_scan_bins, sc.hist.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
 
-	constexpr size_t smem = onesweep_smem_bytes<OS_BLOCK, OS_ITEMS>();
-	auto k32 = k_onesweep_pass<OS_BLOCK, OS_ITEMS, uint32_t>;
-	auto k64 = k_onesweep_pass<OS_BLOCK, OS_ITEMS, uint64_t>;
-#ifndef SVO_EMU
-	if (!sc.attr_set) {
-		SVO_CUDA_TRY(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		SVO_CUDA_TRY(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		sc.attr_set = true;
-	}
-#endif
 	uint64_t *src = a, *dst = b;
 	for (uint32_t p = 0; p < sp.n_pass; ++p) {
-		if (wide)
-			SVO_LAUNCH(tiles, OS_BLOCK, smem, s, k64, (const uint64_t *)src, dst, n, sp.shift[p], sp.mask[p], p,
-			           (const uint32_t *)(sc.hist.p + p * RADIX), reinterpret_cast<uint64_t *>(sc.state.p), sc.ticket.p + p);
+		const uint32_t *bins = sc.hist.p + p * MAX_RADIX;
+		int rc;
+		if (nine)
+			rc = wide ? launch_onesweep_pass<9, uint64_t>(tiles, s, src, dst, n, sp.shift[p], sp.mask[p], p, bins, sc.state.p)
+			          : launch_onesweep_pass<9, uint32_t>(tiles, s, src, dst, n, sp.shift[p], sp.mask[p], p, bins, sc.state.p);
 		else
-			SVO_LAUNCH(tiles, OS_BLOCK, smem, s, k32, (const uint64_t *)src, dst, n, sp.shift[p], sp.mask[p], p,
-			           (const uint32_t *)(sc.hist.p + p * RADIX), reinterpret_cast<uint32_t *>(sc.state.p), sc.ticket.p + p);
+			rc = wide ? launch_onesweep_pass<8, uint64_t>(tiles, s, src, dst, n, sp.shift[p], sp.mask[p], p, bins, sc.state.p)
+			          : launch_onesweep_pass<8, uint32_t>(tiles, s, src, dst, n, sp.shift[p], sp.mask[p], p, bins, sc.state.p);
+		if (rc) return rc;
 		uint64_t *t = src;
 		src = dst;
 		dst = t;

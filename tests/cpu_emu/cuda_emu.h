@@ -258,6 +258,15 @@ inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 	return r;
 }
 
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
+	const uint64_t *s = svo_emu::warp_publish(mask, v);
+	unsigned r = 0, live = svo_emu::tctx.warp->live_mask;
+	for (int i = 0; i < 32; ++i)
+		if ((live >> i) & 1u) r |= (unsigned)s[i];
+	svo_emu::warp_sync();
+	return r;
+}
+
 // ---- atomics (device-wide; blocks are sequential but threads of a block are concurrent) --------------
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
