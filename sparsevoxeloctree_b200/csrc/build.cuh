@@ -1,16 +1,19 @@
-// build.cuh -- the OctreeBuilder kernels: de-duplicate + colour-reduce the sorted fragments, compact one
-// level of unique Morton keys into its parents (bottom-up), then emit the node words.
+// build.cuh -- the OctreeBuilder kernels: de-duplicate + colour-reduce the sorted fragments, compact the
+// levels of unique Morton keys into their parents (bottom-up), then emit the node words.
 //
 // Replaces the reference level loop (src/OctreeBuilder.cpp:142-210: octree_init_node / octree_tag_node /
 // octree_alloc_node / octree_modify_arg, 4L-2 dependent dispatches, F*L fragment re-reads and F*L(L+1)/2
 // dependent pointer loads) with streaming passes over sorted keys:
-//   k_dedup_reduce   : runs of equal Morton code -> one leaf; colours folded with the reference's integer
-//                      running average in run (= emission) order (octree_tag_node.comp:48-57).
-//   k_parent_compact : keys of depth d -> unique parents (key >> 3) of depth d-1, with each parent's first
-//                      child index and 8-bit child mask.  Sizes stay on the device; persistent blocks draw
-//                      tiles from a ticket and chain their counts by decoupled look-back.
+//   k_reduce_fused   : ONE pass over the sorted fragments produces the three deepest levels at once:
+//                      runs of equal Morton code -> leaves (colours folded with the reference's integer
+//                      running average in run = emission order, octree_tag_node.comp:48-57), and the runs of
+//                      equal key>>3 / key>>6 -> the depth L-1 / L-2 nodes.
+//   k_parent_compact : keys of depth d -> unique parents (key >> 3) of depth d-1 (the small upper levels).
+//                      Sizes stay on the device; persistent blocks draw tiles from a ticket.
 //   k_emit_octree    : one thread per 8-word child block: 32 B written once, zeros included, so there is no
 //                      separate init pass (octree_init_node) and no allocation atomics (octree_alloc_node).
+// Per depth d the passes leave: slot[d][i] = child slot (key & 7) of node i, and first[d][j] = index of the
+// first depth-d child of depth-(d-1) node j; children of a node are contiguous (sorted order).
 // Layout produced = what the reference produces when its per-level allocation happens to run in Morton
 // order: root block at word 0, level windows top-down (octree_modify_arg.comp:9-13), child pointer =
 // word index of the child block (octree_alloc_node.comp:21).
@@ -23,68 +26,125 @@ namespace svo {
 constexpr int CMP_BLOCK = 256, CMP_ITEMS = 8, CMP_TILE = CMP_BLOCK * CMP_ITEMS;
 constexpr int MAX_LEVEL = 16;
 
-// ---- de-duplicate + colour reduce ----------------------------------------------------------------------
-__global__ void __launch_bounds__(CMP_BLOCK)
-    k_dedup_reduce(const uint64_t *__restrict__ frags, uint64_t n, uint64_t *__restrict__ out_keys,
-                   uint32_t *__restrict__ out_leaf, uint64_t *state, uint32_t *ticket, uint64_t *count_out) {
-	__shared__ uint64_t s_warp[CMP_BLOCK / 32 + 1];
-	__shared__ uint32_t s_ticket;
-	__shared__ uint64_t s_prefix;
-	const uint64_t n_tiles = (n + CMP_TILE - 1) / CMP_TILE;
-	if (n == 0) {
-		if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = 0;
-		return;
+// ---- de-duplicate + colour reduce + the deepest K-1 parent levels, fused ---------------------------------
+// K = min(3, level) granularities at once:
+//   j = 0: runs of equal Morton code (key >> 24) -> leaves (depth L)
+//   j = 1: runs of equal key >> 27               -> depth L-1 nodes
+//   j = 2: runs of equal key >> 30               -> depth L-2 nodes
+// One tile per thread block, tiles numbered by blockIdx.x (dispatch order), one chained scan per granularity
+// (warps 0..K-1 look back in parallel).  Elements are mapped to threads striped (element = row*BLOCK + tid), so
+// shared-memory traffic is conflict free and the in-warp ranks come from ballots.
+constexpr int RF_BLOCK = 256, RF_ITEMS = 8, RF_TILE = RF_BLOCK * RF_ITEMS, RF_NW = RF_BLOCK / 32;
+
+struct FusedOut {
+	uint32_t *leaf;           // [count0] leaf words
+	unsigned char *slot0;     // [count0] child slot of each leaf
+	uint32_t *first1;         // [count1] first leaf of each depth-(L-1) node
+	unsigned char *slot1;     // [count1] child slot of each depth-(L-1) node
+	uint32_t *first2;         // [count2] first depth-(L-1) child of each depth-(L-2) node
+	uint64_t *keys_top;       // keys (shifted) of granularity K-1, for the remaining levels
+	uint64_t *count[3];       // device scalars receiving the number of runs per granularity
+};
+
+template <int K>
+__global__ void __launch_bounds__(RF_BLOCK, 6)
+    k_reduce_fused(const uint64_t *__restrict__ frags, uint64_t n, FusedOut out, uint64_t *state /* K chains of `tiles` words */,
+                   uint32_t tiles) {
+	__shared__ uint64_t s_keys[RF_TILE + 2]; // [0] = the element before the tile, [TILE+1] = the one after
+	__shared__ uint32_t s_cnt[3][RF_ITEMS * RF_NW];
+	__shared__ uint64_t s_prefix[3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	const uint32_t tile = blockIdx.x;
+	const uint64_t tile_base = (uint64_t)tile * RF_TILE;
+	const uint64_t last = frags[n - 1];
+
+	// Out-of-range slots repeat the last fragment (no run starts there); the element "before" fragment 0
+	// differs from it in every bit, so fragment 0 starts a run at every granularity.
+#pragma unroll
+	for (int i = 0; i < RF_ITEMS; ++i) {
+		const uint32_t e = i * RF_BLOCK + threadIdx.x;
+		s_keys[e + 1] = tile_base + e < n ? frags[tile_base + e] : last;
 	}
-	for (;;) {
-		const uint32_t tile = take_ticket(ticket, &s_ticket);
-		if (tile >= n_tiles) break;
-		const uint64_t base = (uint64_t)tile * CMP_TILE + (uint64_t)threadIdx.x * CMP_ITEMS;
-		uint64_t k[CMP_ITEMS];
-		bool head[CMP_ITEMS];
-		uint64_t prev = (base > 0 && base < n) ? frags[base - 1] : 0;
-		uint32_t cnt = 0;
+	if (threadIdx.x == 0) s_keys[0] = tile_base > 0 ? frags[tile_base - 1] : ~frags[0];
+	if (threadIdx.x == 32) s_keys[RF_TILE + 1] = tile_base + RF_TILE < n ? frags[tile_base + RF_TILE] : ~last;
+	__syncthreads();
+
+	// run-start flags + in-warp ranks
+	uint32_t packed[RF_ITEMS]; // per row: flags (bits 0..2) and the lane's exclusive rank per granularity (5 bits each)
 #pragma unroll
-		for (int i = 0; i < CMP_ITEMS; ++i) {
-			const uint64_t idx = base + i;
-			k[i] = idx < n ? frags[idx] : 0;
-			const bool first = idx == 0;
-			head[i] = idx < n && (first || (k[i] >> 24) != (prev >> 24));
-			prev = k[i];
-			cnt += head[i] ? 1u : 0u;
-		}
-		uint64_t total;
-		const uint64_t excl = block_exclusive_sum<CMP_BLOCK, uint64_t>((uint64_t)cnt, total, s_warp);
-		if (threadIdx.x < 32) {
-			const uint64_t p = lookback_exclusive(state, tile, total, threadIdx.x);
-			if (threadIdx.x == 0) {
-				s_prefix = p;
-				if (tile == n_tiles - 1) *count_out = p + total;
-			}
-		}
-		__syncthreads();
-		uint64_t u = s_prefix + excl;
+	for (int i = 0; i < RF_ITEMS; ++i) {
+		const uint32_t e = i * RF_BLOCK + threadIdx.x;
+		const uint64_t x = s_keys[e + 1] ^ s_keys[e];
+		uint32_t pk = 0;
 #pragma unroll
-		for (int i = 0; i < CMP_ITEMS; ++i) {
-			if (!head[i]) continue;
-			const uint64_t key = k[i] >> 24;
-			uint32_t acc = leaf_first((uint32_t)(k[i] & 0xffffffu));
-			for (uint64_t j = base + i + 1; j < n; ++j) {
-				const uint64_t kk = frags[j];
-				if ((kk >> 24) != key) break;
+		for (int j = 0; j < K; ++j) {
+			const bool f = (x >> (24 + 3 * j)) != 0;
+			const unsigned b = __ballot_sync(FULL_MASK, f);
+			pk |= (f ? 1u : 0u) << j;
+			pk |= (uint32_t)__popc(b & lt_mask) << (3 + 5 * j);
+			if (lane == 0) s_cnt[j][i * RF_NW + warp] = (uint32_t)__popc(b);
+		}
+		packed[i] = pk;
+	}
+	__syncthreads();
+
+	// warps 0..K-1: exclusive scan of the 64 (row, warp) counts of one granularity, then the chained look-back
+	if (warp < K) {
+		const int j = warp;
+		const uint32_t c0 = s_cnt[j][2 * lane], c1 = s_cnt[j][2 * lane + 1];
+		const uint32_t inc = warp_inclusive_sum(c0 + c1, lane);
+		const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
+		s_cnt[j][2 * lane] = inc - c0 - c1;
+		s_cnt[j][2 * lane + 1] = inc - c1;
+		const uint64_t p = lookback_exclusive(state + (uint64_t)j * tiles, tile, (uint64_t)total, lane);
+		if (lane == 0) {
+			s_prefix[j] = p;
+			if (tile == tiles - 1) *out.count[j] = p + total;
+		}
+	}
+	__syncthreads();
+
+	// run owners write their node
+	const uint64_t p0 = s_prefix[0], p1 = K >= 2 ? s_prefix[1] : 0, p2 = K >= 3 ? s_prefix[2] : 0;
+#pragma unroll
+	for (int i = 0; i < RF_ITEMS; ++i) {
+		const uint32_t pk = packed[i];
+		if (!(pk & 1u)) continue;
+		const uint32_t e = i * RF_BLOCK + threadIdx.x;
+		const uint64_t key = s_keys[e + 1];
+		const uint64_t u0 = p0 + s_cnt[0][i * RF_NW + warp] + ((pk >> 3) & 31u);
+		uint32_t acc = leaf_first((uint32_t)(key & 0xffffffu));
+		if (((s_keys[e + 2] ^ key) >> 24) == 0) { // the voxel has more fragments: fold them in emission order
+			for (uint64_t q = (uint64_t)e + 1; tile_base + q < n; ++q) {
+				const uint64_t kk = q < RF_TILE ? s_keys[q + 1] : frags[tile_base + q];
+				if ((kk >> 24) != (key >> 24)) break;
 				acc = leaf_accumulate(acc, (uint32_t)(kk & 0xffffffu));
 			}
-			out_keys[u] = key;
-			out_leaf[u] = acc;
-			++u;
 		}
-		__syncthreads(); // s_prefix is rewritten by the next tile
+		out.leaf[u0] = acc;
+		out.slot0[u0] = (unsigned char)((key >> 24) & 7u);
+		if (K == 1) out.keys_top[u0] = key >> 24;
+		if (K >= 2 && (pk & 2u)) {
+			const uint64_t u1 = p1 + s_cnt[1][i * RF_NW + warp] + ((pk >> 8) & 31u);
+			out.first1[u1] = (uint32_t)u0;
+			out.slot1[u1] = (unsigned char)((key >> 27) & 7u);
+			if (K == 2) out.keys_top[u1] = key >> 27;
+			if (K >= 3 && (pk & 4u)) {
+				const uint64_t u2 = p2 + s_cnt[2][i * RF_NW + warp] + ((pk >> 13) & 31u);
+				out.first2[u2] = (uint32_t)u1;
+				out.keys_top[u2] = key >> 30;
+			}
+		}
 	}
 }
 
-// ---- one level up ----------------------------------------------------------------------------------------
+// ---- one level up (upper levels: small) ----------------------------------------------------------------------
+// keys_in: n = *n_ptr sorted unique keys of depth d.  Writes slot_in[i] = key & 7 for every node, and for every
+// run of equal key >> 3: keys_out[u] = parent key, first_out[u] = index of the run's first node; *n_out = runs.
 __global__ void __launch_bounds__(CMP_BLOCK)
     k_parent_compact(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ n_ptr, uint64_t *__restrict__ keys_out,
-                     uint32_t *__restrict__ first_out, unsigned char *__restrict__ mask_out, uint64_t *state, uint32_t *ticket,
+                     uint32_t *__restrict__ first_out, unsigned char *__restrict__ slot_in, uint64_t *state, uint32_t *ticket,
                      uint64_t *n_out) {
 	__shared__ uint64_t s_warp[CMP_BLOCK / 32 + 1];
 	__shared__ uint32_t s_ticket;
@@ -110,6 +170,7 @@ __global__ void __launch_bounds__(CMP_BLOCK)
 			head[i] = idx < n && (idx == 0 || (k[i] >> 3) != (prev >> 3));
 			prev = k[i];
 			cnt += head[i] ? 1u : 0u;
+			if (idx < n) slot_in[idx] = (unsigned char)(k[i] & 7u);
 		}
 		uint64_t total;
 		const uint64_t excl = block_exclusive_sum<CMP_BLOCK, uint64_t>((uint64_t)cnt, total, s_warp);
@@ -125,16 +186,8 @@ __global__ void __launch_bounds__(CMP_BLOCK)
 #pragma unroll
 		for (int i = 0; i < CMP_ITEMS; ++i) {
 			if (!head[i]) continue;
-			const uint64_t parent = k[i] >> 3;
-			uint32_t m = 1u << (uint32_t)(k[i] & 7u);
-			for (uint64_t j = base + i + 1; j < n; ++j) { // at most 7 more children
-				const uint64_t kk = keys_in[j];
-				if ((kk >> 3) != parent) break;
-				m |= 1u << (uint32_t)(kk & 7u);
-			}
-			keys_out[u] = parent;
+			keys_out[u] = k[i] >> 3;
 			first_out[u] = (uint32_t)(base + i);
-			mask_out[u] = (unsigned char)m;
 			++u;
 		}
 		__syncthreads();
@@ -145,10 +198,11 @@ __global__ void __launch_bounds__(CMP_BLOCK)
 struct EmitParams {
 	uint32_t level;
 	uint64_t total_blocks;
-	uint64_t block_base[MAX_LEVEL + 2];      // block_base[d], d = 1..level+1: first 8-word block of the window of depth-d nodes
-	const uint32_t *first[MAX_LEVEL + 1];    // [d]: per depth-(d-1) node, index of its first child among the depth-d nodes
-	const unsigned char *mask[MAX_LEVEL + 1];
-	const uint32_t *leaf;                    // leaf words of the depth-`level` nodes
+	uint64_t block_base[MAX_LEVEL + 2];       // block_base[d], d = 1..level+1: first 8-word block of the window of depth-d nodes
+	uint64_t count[MAX_LEVEL + 1];            // nodes per depth
+	const uint32_t *first[MAX_LEVEL + 1];     // [d]: per depth-(d-1) node, index of its first child among the depth-d nodes
+	const unsigned char *slot[MAX_LEVEL + 1]; // [d]: per depth-d node, its child slot
+	const uint32_t *leaf;                     // leaf words of the depth-`level` nodes
 };
 
 __global__ void __launch_bounds__(256) k_emit_octree(EmitParams ep, uint32_t *__restrict__ words) {
@@ -158,10 +212,18 @@ __global__ void __launch_bounds__(256) k_emit_octree(EmitParams ep, uint32_t *__
 #pragma unroll 1
 	while (d < ep.level && g >= ep.block_base[d + 1]) ++d;
 	const uint64_t j = g - ep.block_base[d];
-	uint32_t c = ep.first[d][j];
-	const uint32_t m = ep.mask[d][j];
+	const uint32_t *first = ep.first[d];
+	const unsigned char *slot = ep.slot[d];
+	const uint32_t c0 = first[j];
+	const uint32_t c1 = j + 1 < ep.count[d - 1] ? first[j + 1] : (uint32_t)ep.count[d];
+	const uint32_t nc = c1 - c0; // 1..8 children, contiguous, slots ascending
+	uint32_t m = 0;
+#pragma unroll
+	for (int q = 0; q < 8; ++q)
+		if ((uint32_t)q < nc) m |= 1u << slot[c0 + q];
 	const bool leaf_level = d == ep.level;
 	const uint64_t child_base = ep.block_base[d + 1];
+	uint32_t c = c0;
 	uint32_t w[8];
 #pragma unroll
 	for (int s = 0; s < 8; ++s) {
@@ -176,7 +238,7 @@ __global__ void __launch_bounds__(256) k_emit_octree(EmitParams ep, uint32_t *__
 	o[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// Multi-GPU stitch: copy blocks [1, total) of a built subtree to dst (possibly peer memory), adding
+// Multi-GPU stitch: copy a built subtree to dst (possibly peer memory mapped through CUDA IPC), adding
 // base_words to every internal child pointer (leaves untouched).  One uint4 per thread.
 __global__ void __launch_bounds__(256)
     k_rebase_copy(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t n_vec, uint32_t base_words) {

@@ -120,7 +120,7 @@ struct svo_builder {
 	DevBuf<uint64_t> tmp;      // sort ping-pong partner of the fragment list
 	DevBuf<uint32_t> leaf;     // leaf words
 	DevBuf<uint32_t> first;    // pooled per-level first-child arrays
-	DevBuf<unsigned char> mask;
+	DevBuf<unsigned char> slot;     // pooled per-depth child-slot arrays
 	DevBuf<uint64_t> counts;   // device: node count per depth 0..level
 	DevBuf<uint64_t> lb_state;
 	DevBuf<uint32_t> tickets;
@@ -132,6 +132,12 @@ struct svo_builder {
 	bool built = false;
 	cudaEvent_t ev[SVO_PHASE_COUNT + 1] = {};
 };
+
+// at most min(F, 8^d) nodes at depth d
+static uint64_t node_cap(uint64_t F, uint32_t d) {
+	const uint64_t cap8 = d >= 11 ? UINT64_MAX : (1ull << (3 * d));
+	return F < cap8 ? F : cap8;
+}
 
 static int fail(int code, const char *msg) {
 	set_error("%s", msg);
@@ -427,15 +433,15 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 		if (rc) break;
 		const uint64_t F = vox->n_frag;
 		if ((rc = b->tmp.alloc(F, s)) || (rc = b->leaf.alloc(F, s)) || (rc = b->counts.alloc(MAX_LEVEL + 2, s))) break;
-		// pooled per-level arrays: the window of depth-d nodes has one entry per depth-(d-1) node, at most min(F, 8^(d-1))
-		uint64_t pool = 0;
+		// pooled arrays: first[d] has one entry per depth-(d-1) node (<= min(F, 8^(d-1))), slot[d] one per depth-d node
+		uint64_t pool_first = 0, pool_slot = 0;
 		for (uint32_t d = 1; d <= b->level; ++d) {
-			const uint64_t cap8 = d - 1 >= 11 ? UINT64_MAX : (1ull << (3 * (d - 1)));
-			pool += F < cap8 ? F : cap8;
+			pool_first += node_cap(F, d - 1);
+			pool_slot += node_cap(F, d);
 		}
-		if ((rc = b->first.alloc(pool, s)) || (rc = b->mask.alloc(pool, s))) break;
+		if ((rc = b->first.alloc(pool_first, s)) || (rc = b->slot.alloc(pool_slot, s))) break;
 		const uint64_t tiles = (F + CMP_TILE - 1) / CMP_TILE + 1;
-		if ((rc = b->lb_state.alloc(tiles * (b->level + 1), s)) || (rc = b->tickets.alloc(b->level + 2, s))) break;
+		if ((rc = b->lb_state.alloc(tiles * (b->level + 4), s)) || (rc = b->tickets.alloc(b->level + 2, s))) break;
 	} while (0);
 	if (rc) {
 		svo_builder_destroy(b);
@@ -448,7 +454,7 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 void svo_builder_destroy(svo_builder *b) {
 	if (!b) return;
 	DeviceGuard guard(b->device);
-	b->tmp.release(0), b->leaf.release(0), b->first.release(0), b->mask.release(0), b->counts.release(0), b->lb_state.release(0);
+	b->tmp.release(0), b->leaf.release(0), b->first.release(0), b->slot.release(0), b->counts.release(0), b->lb_state.release(0);
 	b->tickets.release(0), b->octree.release(0);
 	b->sort_scratch.hist.release(0), b->sort_scratch.ticket.release(0), b->sort_scratch.state.release(0);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
@@ -474,39 +480,57 @@ int svo_builder_build(svo_builder *b, void *stream) {
 	uint64_t *other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
 
-	// ---- de-duplicate + colour reduce: keys of depth L ----
+	// ---- de-duplicate + colour reduce + the two deepest parent levels, fused (build.cuh) ----
+	const uint32_t K = L < 3 ? L : 3;
 	const uint64_t tiles_f = (F + CMP_TILE - 1) / CMP_TILE + 1;
-	SVO_CUDA_TRY(cudaMemsetAsync(b->lb_state.p, 0, tiles_f * (L + 1) * sizeof(uint64_t), s));
+	const uint32_t rf_tiles = div_up(F, RF_TILE);
+	SVO_CUDA_TRY(cudaMemsetAsync(b->lb_state.p, 0, tiles_f * (L + 4) * sizeof(uint64_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(b->tickets.p, 0, (L + 2) * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(b->counts.p, 0, (MAX_LEVEL + 2) * sizeof(uint64_t), s));
-	uint32_t pgrid = (uint32_t)n_sm * 4u;
+	uint64_t first_off[MAX_LEVEL + 2] = {}, slot_off[MAX_LEVEL + 2] = {};
 	{
-		uint32_t g = (uint32_t)(tiles_f < pgrid ? tiles_f : pgrid);
-		SVO_LAUNCH(g, CMP_BLOCK, 0, s, k_dedup_reduce, (const uint64_t *)sorted, F, other, b->leaf.p, b->lb_state.p, b->tickets.p, b->counts.p + L);
+		uint64_t fo = 0, so = 0;
+		for (uint32_t d = L; d >= 1; --d) {
+			first_off[d] = fo, slot_off[d] = so;
+			fo += node_cap(F, d - 1), so += node_cap(F, d);
+		}
+	}
+	if (F) {
+		FusedOut fo{};
+		fo.leaf = b->leaf.p;
+		fo.slot0 = b->slot.p + slot_off[L];
+		fo.first1 = b->first.p + first_off[L];
+		if (L >= 2) fo.slot1 = b->slot.p + slot_off[L - 1], fo.first2 = b->first.p + first_off[L - 1];
+		fo.keys_top = other;
+		for (uint32_t j = 0; j < K; ++j) fo.count[j] = b->counts.p + (L - j);
+		if (K == 1) {
+			auto k = k_reduce_fused<1>;
+			SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k, (const uint64_t *)sorted, F, fo, b->lb_state.p, rf_tiles);
+		} else if (K == 2) {
+			auto k = k_reduce_fused<2>;
+			SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k, (const uint64_t *)sorted, F, fo, b->lb_state.p, rf_tiles);
+		} else {
+			auto k = k_reduce_fused<3>;
+			SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k, (const uint64_t *)sorted, F, fo, b->lb_state.p, rf_tiles);
+		}
 	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 
-	// ---- levels L..1: unique parents, first child, child mask ----
+	// ---- remaining levels (L-K+1)..1: unique parents, first child, child mask (small from here on) ----
 	// key buffers ping-pong between the two fragment-sized buffers (the sorted fragments are dead after the reduce)
+	const uint32_t pgrid = (uint32_t)n_sm * 4u;
 	uint64_t *kin = other, *kout = sorted;
-	uint64_t pool_off[MAX_LEVEL + 2] = {};
-	{
-		uint64_t off = 0;
-		for (uint32_t d = L; d >= 1; --d) {
-			pool_off[d] = off;
-			const uint64_t cap8 = d - 1 >= 11 ? UINT64_MAX : (1ull << (3 * (d - 1)));
-			const uint64_t cap = F < cap8 ? F : cap8;
-			const uint64_t in_cap8 = d >= 11 ? UINT64_MAX : (1ull << (3 * d));
-			const uint64_t in_cap = F < in_cap8 ? F : in_cap8;
-			const uint64_t tiles = (in_cap + CMP_TILE - 1) / CMP_TILE + 1;
-			uint32_t g = (uint32_t)(tiles < pgrid ? tiles : pgrid);
-			SVO_LAUNCH(g, CMP_BLOCK, 0, s, k_parent_compact, (const uint64_t *)kin, (const uint64_t *)(b->counts.p + d), kout,
-			           b->first.p + off, b->mask.p + off, b->lb_state.p + tiles_f * (L - d + 1), b->tickets.p + (L - d + 1), b->counts.p + d - 1);
-			off += cap;
-			uint64_t *t = kin;
-			kin = kout;
-			kout = t;
-		}
+	for (uint32_t d = L - K + 1; d >= 1 && F; --d) {
+		const uint64_t in_cap8 = d >= 11 ? UINT64_MAX : (1ull << (3 * d));
+		const uint64_t in_cap = F < in_cap8 ? F : in_cap8;
+		const uint64_t tiles = (in_cap + CMP_TILE - 1) / CMP_TILE + 1;
+		uint32_t g = (uint32_t)(tiles < pgrid ? tiles : pgrid);
+		SVO_LAUNCH(g, CMP_BLOCK, 0, s, k_parent_compact, (const uint64_t *)kin, (const uint64_t *)(b->counts.p + d), kout,
+		           b->first.p + first_off[d], b->slot.p + slot_off[d], b->lb_state.p + tiles_f * (3 + L - d), b->tickets.p + (L - d + 1),
+		           b->counts.p + d - 1);
+		uint64_t *t = kin;
+		kin = kout;
+		kout = t;
 	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[4], s));
 
@@ -523,9 +547,10 @@ int svo_builder_build(svo_builder *b, void *stream) {
 	}
 	ep.total_blocks = blocks;
 	if (blocks * 8 >= (1ull << 30)) return fail(SVO_ERR_CAPACITY, "octree needs >= 2^30 words: 30-bit child pointers (octree.glsl:110) cannot address it");
+	for (uint32_t d = 0; d <= L; ++d) ep.count[d] = b->h_counts[d];
 	for (uint32_t d = 1; d <= L; ++d) {
-		ep.first[d] = b->first.p + pool_off[d];
-		ep.mask[d] = b->mask.p + pool_off[d];
+		ep.first[d] = b->first.p + first_off[d];
+		ep.slot[d] = b->slot.p + slot_off[d];
 	}
 	ep.leaf = b->leaf.p;
 	SVO_TRY(b->octree.reserve(blocks * 8, s));
