@@ -34,7 +34,18 @@ constexpr int MAX_LEVEL = 16;
 // One tile per thread block, tiles numbered by blockIdx.x (dispatch order), one chained scan per granularity
 // (warps 0..K-1 look back in parallel).  Elements are mapped to threads striped (element = row*BLOCK + tid), so
 // shared-memory traffic is conflict free and the in-warp ranks come from ballots.
-constexpr int RF_BLOCK = 256, RF_ITEMS = 8, RF_TILE = RF_BLOCK * RF_ITEMS, RF_NW = RF_BLOCK / 32;
+#ifndef SVO_RF_BLOCK
+#define SVO_RF_BLOCK 256
+#endif
+#ifndef SVO_RF_ITEMS
+#define SVO_RF_ITEMS 16
+#endif
+#ifndef SVO_RF_MINB
+#define SVO_RF_MINB 4
+#endif
+constexpr int RF_BLOCK = SVO_RF_BLOCK, RF_ITEMS = SVO_RF_ITEMS, RF_TILE = RF_BLOCK * RF_ITEMS, RF_NW = RF_BLOCK / 32;
+static_assert(RF_ITEMS * RF_NW <= 128 && (RF_ITEMS * RF_NW) % 32 == 0, "the (row, warp) count matrix is scanned by one warp");
+constexpr int RF_CPL = RF_ITEMS * RF_NW / 32; // counts per lane in that scan
 
 struct FusedOut {
 	uint32_t *leaf;           // [count0] leaf words
@@ -47,12 +58,14 @@ struct FusedOut {
 };
 
 template <int K>
-__global__ void __launch_bounds__(RF_BLOCK, 6)
-    k_reduce_fused(const uint64_t *__restrict__ frags, uint64_t n, FusedOut out, uint64_t *state /* K chains of `tiles` words */,
+__global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
+    k_reduce_fused(const uint64_t *__restrict__ frags, uint64_t n, FusedOut out, uint64_t *state /* [tiles][K] look-back words, zeroed */,
                    uint32_t tiles) {
 	__shared__ uint64_t s_keys[RF_TILE + 2]; // [0] = the element before the tile, [TILE+1] = the one after
 	__shared__ uint32_t s_cnt[3][RF_ITEMS * RF_NW];
-	__shared__ uint64_t s_prefix[3];
+	__shared__ uint32_t s_total[3];
+	__shared__ uint64_t s_red[RF_NW * 3];
+	__shared__ uint32_t s_idx[2 * RF_NW];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t tile = blockIdx.x;
@@ -89,24 +102,34 @@ __global__ void __launch_bounds__(RF_BLOCK, 6)
 	}
 	__syncthreads();
 
-	// warps 0..K-1: exclusive scan of the 64 (row, warp) counts of one granularity, then the chained look-back
+	// warps 0..K-1: exclusive scan of the (row, warp) counts of one granularity
 	if (warp < K) {
 		const int j = warp;
-		const uint32_t c0 = s_cnt[j][2 * lane], c1 = s_cnt[j][2 * lane + 1];
-		const uint32_t inc = warp_inclusive_sum(c0 + c1, lane);
-		const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
-		s_cnt[j][2 * lane] = inc - c0 - c1;
-		s_cnt[j][2 * lane + 1] = inc - c1;
-		const uint64_t p = lookback_exclusive(state + (uint64_t)j * tiles, tile, (uint64_t)total, lane);
-		if (lane == 0) {
-			s_prefix[j] = p;
-			if (tile == tiles - 1) *out.count[j] = p + total;
+		uint32_t c[RF_CPL], sum = 0;
+#pragma unroll
+		for (int q = 0; q < RF_CPL; ++q) sum += (c[q] = s_cnt[j][RF_CPL * lane + q]);
+		const uint32_t inc = warp_inclusive_sum(sum, lane);
+		uint32_t run = inc - sum;
+#pragma unroll
+		for (int q = 0; q < RF_CPL; ++q) {
+			s_cnt[j][RF_CPL * lane + q] = run;
+			run += c[q];
 		}
+		if (lane == 31) s_total[j] = inc;
 	}
 	__syncthreads();
+	// chained scan across tiles: the whole block looks back (BLOCK predecessors per round trip)
+	uint64_t agg[K], pre[K];
+#pragma unroll
+	for (int j = 0; j < K; ++j) agg[j] = s_total[j];
+	block_lookback<RF_BLOCK, K>(state, tile, agg, pre, s_red, s_idx);
+	if (tile == tiles - 1 && threadIdx.x == 0) {
+#pragma unroll
+		for (int j = 0; j < K; ++j) *out.count[j] = pre[j] + agg[j];
+	}
 
 	// run owners write their node
-	const uint64_t p0 = s_prefix[0], p1 = K >= 2 ? s_prefix[1] : 0, p2 = K >= 3 ? s_prefix[2] : 0;
+	const uint64_t p0 = pre[0], p1 = K >= 2 ? pre[K >= 2 ? 1 : 0] : 0, p2 = K >= 3 ? pre[K >= 3 ? 2 : 0] : 0;
 #pragma unroll
 	for (int i = 0; i < RF_ITEMS; ++i) {
 		const uint32_t pk = packed[i];

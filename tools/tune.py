@@ -52,7 +52,7 @@ def main():
         blk, items, minb = v.split(",")
         defs = [f"SVO_OS_BLOCK={blk}", f"SVO_OS_ITEMS={items}", f"SVO_OS_MINB={minb}"] + [d for d in args.extra.split(",") if d]
         try:
-            path = build_variant(f"{blk}_{items}_{minb}", defs)
+            path = build_variant(f"{blk}_{items}_{minb}_" + "_".join(args.extra.replace("=", "").split(",")), defs)
         except subprocess.CalledProcessError:
             print(f"variant {v}: does not compile", flush=True)
             continue
