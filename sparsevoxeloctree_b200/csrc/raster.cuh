@@ -192,22 +192,31 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 			}
 }
 
-// output-parallel expansion of the dense row spans: fragment ordinal j -> (row, x)
+// output-parallel expansion of the dense row spans: fragment ordinal j -> (row, x).  A block owns EMIT_TILE
+// consecutive fragments, a thread EMIT_ITEMS consecutive ones: one search per thread, then x advances by
+// incrementing the Morton-spread coordinate, the depth plane's row term is hoisted, and the fragments leave in
+// 16-byte stores.
 __global__ void __launch_bounds__(EMIT_BLOCK)
     k_emit_large(RasterParams rp, const LargeTri *__restrict__ large, DenseRows rows, uint32_t n_rows, uint64_t n_frag_large,
                  uint64_t *__restrict__ frags /* already offset to the large region */) {
 	__shared__ uint32_t s_off[EMIT_TILE + 2];
 	__shared__ uint32_t s_first;
+	const int lane = threadIdx.x & 31;
 	const uint64_t c0 = (uint64_t)blockIdx.x * EMIT_TILE;
 	const uint64_t c1 = c0 + EMIT_TILE < n_frag_large ? c0 + EMIT_TILE : n_frag_large;
-	if (threadIdx.x == 0) {
-		// last row with off <= c0 (rows are non-empty, so it contains fragment c0)
-		uint32_t lo = 0, hi = n_rows;
+	if (threadIdx.x < 32) {
+		// last row with off <= c0 (rows are non-empty, so it contains fragment c0): 32-ary search by one warp
+		uint32_t lo = 0, hi = n_rows; // invariant: off[lo] <= c0 < off[hi]
 		while (hi - lo > 1) {
-			uint32_t mid = lo + ((hi - lo) >> 1);
-			if (rows.off[mid] <= c0) lo = mid; else hi = mid;
+			const uint32_t step = (hi - lo + 31u) / 32u;
+			const uint32_t idx = lo + (uint32_t)lane * step;
+			const bool ok = idx < hi && rows.off[idx] <= c0; // monotone in the lane; lane 0 always holds
+			const unsigned b = __ballot_sync(FULL_MASK, ok);
+			const uint32_t k = 31u - (uint32_t)__clz((int)b);
+			lo += k * step;
+			hi = lo + step < hi ? lo + step : hi;
 		}
-		s_first = lo;
+		if (lane == 0) s_first = lo;
 	}
 	__syncthreads();
 	const uint32_t r_first = s_first;
@@ -217,23 +226,62 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 		s_off[i] = r <= n_rows ? rows.off[r] : 0xffffffffu;
 	}
 	__syncthreads();
-#pragma unroll 1
-	for (int it = 0; it < EMIT_ITEMS; ++it) {
-		const uint64_t j = c0 + (uint64_t)it * EMIT_BLOCK + threadIdx.x;
-		if (j >= c1) break;
-		// last staged row with off <= j
-		uint32_t lo = 0, hi = EMIT_TILE + 1;
-		while (hi - lo > 1) {
-			uint32_t mid = (lo + hi) >> 1;
-			if (s_off[mid] <= j) lo = mid; else hi = mid;
-		}
-		const uint32_t r = r_first + lo;
-		const uint32_t xy = rows.xy[r];
-		const LargeTri &lt = large[rows.li[r]];
-		const int32_t px = (int32_t)(xy & 0xffffu) + (int32_t)(j - s_off[lo]);
-		const int32_t py = (int32_t)(xy >> 16);
-		const uint32_t uz = pixel_depth(lt.ts, rp.res, px, py);
-		frags[j] = make_fragment(lt.ts, rp, px, py, uz, lt.rgb);
+
+	const uint64_t j0 = c0 + (uint64_t)threadIdx.x * EMIT_ITEMS;
+	if (j0 >= c1) return;
+	uint32_t lo = 0, hi = EMIT_TILE + 1; // last staged row with off <= j0
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (s_off[mid] <= j0) lo = mid; else hi = mid;
+	}
+	uint64_t out[EMIT_ITEMS];
+	uint32_t row_end = 0; // forces the row set-up on the first fragment
+	const LargeTri *lt = nullptr;
+	double row_term = 0.0;
+	uint64_t m_row = 0, m_x = 0;
+	uint32_t shx = 0, shz = 0, oz = 0, rgb = 0;
+	int32_t px = 0;
+	--lo;
+#pragma unroll
+	for (int k = 0; k < EMIT_ITEMS; ++k) {
+		const uint64_t j = j0 + k;
+		if (j < c1) {
+			if (j >= row_end) { // next row (the first one included)
+				++lo;
+				const uint32_t r = r_first + lo;
+				const uint32_t xy = rows.xy[r];
+				lt = &large[rows.li[r]];
+				row_end = s_off[lo + 1];
+				px = (int32_t)(xy & 0xffffu) + (int32_t)(j - s_off[lo]);
+				const int32_t py = (int32_t)(xy >> 16);
+				row_term = depth_row_term(lt->ts, py);
+				// voxel = axis 0: (uz, px, py); 1: (py, uz, px); 2: (px, py, uz)   (voxelizer.frag:24)
+				const uint32_t axis = lt->ts.axis;
+				const uint32_t wx = axis == 0u ? 1u : (axis == 1u ? 2u : 0u); // world axis of screen x
+				const uint32_t wy = axis == 0u ? 2u : (axis == 1u ? 0u : 1u);
+				const uint32_t wz = axis;
+				shx = wx, shz = wz;
+				oz = rp.origin[wz];
+				m_row = part1by2((uint32_t)py - rp.origin[wy]) << wy;
+				m_x = part1by2((uint32_t)px - rp.origin[wx]);
+				rgb = lt->rgb & 0xffffffu;
+			}
+			const uint32_t uz = pixel_depth_row(lt->ts, rp.res, px, row_term);
+			const uint64_t m = (m_x << shx) | (part1by2(uz - oz) << shz) | m_row;
+			out[k] = (m << 24) | (uint64_t)rgb;
+			m_x = part1by2_increment(m_x);
+			++px;
+		} else
+			out[k] = 0;
+	}
+	uint64_t *dst = frags + j0;
+	if (j0 + EMIT_ITEMS <= c1 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+		for (int k = 0; k < EMIT_ITEMS; k += 2) *reinterpret_cast<ulonglong2 *>(dst + k) = make_ulonglong2(out[k], out[k + 1]);
+	} else {
+#pragma unroll
+		for (int k = 0; k < EMIT_ITEMS; ++k)
+			if (j0 + k < c1) dst[k] = out[k];
 	}
 }
 

@@ -68,6 +68,11 @@ SVO_HD inline uint64_t part1by2(uint32_t v) {
 SVO_HD inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) {
 	return part1by2(x) | (part1by2(y) << 1) | (part1by2(z) << 2);
 }
+// x -> x + 1 directly in spread form (bits at positions 0, 3, 6, ...): fill the gaps with ones so the carry ripples
+SVO_HD inline uint64_t part1by2_increment(uint64_t m) {
+	const uint64_t mask = 0x1249249249249249ull;
+	return ((m | ~mask) + 1ull) & mask;
+}
 SVO_HD inline uint32_t compact1by2_10(uint32_t v) {
 	v &= 0x09249249u;
 	v = (v | (v >> 2)) & 0x030c30c3u;
@@ -280,16 +285,25 @@ SVO_HD inline void row_span(const TriSetup &t, int32_t py, int32_t &x_lo, int32_
 	x_lo = (int32_t)lo, x_hi = (int32_t)hi;
 }
 
-// depth voxel of pixel (px,py): voxelizer.frag:18-20,23 (+ the pinned final clamp to res-1)
-SVO_HD inline uint32_t pixel_depth(const TriSetup &t, uint32_t res, int32_t px, int32_t py) {
-	const int32_t cx = px * 256 + 128, cy = py * 256 + 128;
-	double z = dfma(t.dzdx, (double)(cx - t.X0), dfma(t.dzdy, (double)(cy - t.Y0), t.z0));
+// depth voxel of pixel (px,py): voxelizer.frag:18-20,23 (+ the pinned final clamp to res-1).
+// Split into the row term and the pixel term so that span kernels can hoist the row term: the operations
+// (and therefore the rounding) are identical whichever way it is called.
+SVO_HD inline double depth_row_term(const TriSetup &t, int32_t py) {
+	const int32_t cy = py * 256 + 128;
+	return dfma(t.dzdy, (double)(cy - t.Y0), t.z0);
+}
+SVO_HD inline uint32_t pixel_depth_row(const TriSetup &t, uint32_t res, int32_t px, double row_term) {
+	const int32_t cx = px * 256 + 128;
+	double z = dfma(t.dzdx, (double)(cx - t.X0), row_term);
 	double zs = dmul(z, (double)res);
 	uint32_t uz = !(zs > 0.0) ? 0u : (zs >= (double)res ? res - 1u : (uint32_t)zs);
 	uz = tmax(uz, t.zr_lo);
 	uz = tmin(uz, t.zr_hi);
 	uz = tmin(uz, res - 1u);
 	return uz;
+}
+SVO_HD inline uint32_t pixel_depth(const TriSetup &t, uint32_t res, int32_t px, int32_t py) {
+	return pixel_depth_row(t, res, px, depth_row_term(t, py));
 }
 
 // Narrow a row span to the pixels whose depth voxel lies inside the shard's depth window.  The depth voxel
