@@ -1,0 +1,53 @@
+// The reference loader sequence (src/LoaderThread.cpp:51-116) written against the C++ mirror classes:
+// Scene -> Voxelizer -> OctreeBuilder -> CmdVoxelize + CmdBuild -> Octree::Update, on a small procedural mesh.
+// Prints "fragments leaves_unknown range level root[0..7]"; tests/test_cpp_host.py compares it with the Python path.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../sparsevoxeloctree_b200/host/svo_host.hpp"
+
+using namespace svo_host;
+
+int main(int argc, char **argv) {
+	const uint32_t level = argc > 1 ? (uint32_t)atoi(argv[1]) : 7;
+	const int n = argc > 2 ? atoi(argv[2]) : 33;
+	MeshData mesh;
+	for (int i = 0; i < n; ++i)
+		for (int j = 0; j < n; ++j) {
+			float x = -1.f + 2.f * i / (n - 1), z = -1.f + 2.f * j / (n - 1);
+			float y = 0.4f * std::sin(3.f * x) * std::cos(2.f * z);
+			mesh.vertices.push_back({{x, y, z}, {0.f, 0.f}});
+		}
+	for (int i = 0; i + 1 < n; ++i)
+		for (int j = 0; j + 1 < n; ++j) {
+			uint32_t a = i * n + j, b = (i + 1) * n + j, c = (i + 1) * n + j + 1, d = i * n + j + 1;
+			for (uint32_t v : {a, b, c, a, c, d}) mesh.indices.push_back(v);
+		}
+	mesh.draws.push_back({0, (uint32_t)mesh.indices.size(), 0xffffffffu, 0x00C83C32u});
+
+	if (svo_device_count() < 1) {
+		fprintf(stderr, "no CUDA device\n");
+		return 2;
+	}
+	auto scene = Scene::Create(mesh);
+	if (!scene) return 1;
+	auto voxelizer = Voxelizer::Create(scene, level);
+	if (!voxelizer) return 1;
+	auto builder = OctreeBuilder::Create(voxelizer);
+	if (!builder) return 1;
+	voxelizer->CmdVoxelize();
+	if (builder->CmdBuild() != SVO_OK) {
+		fprintf(stderr, "CmdBuild: %s\n", svo_last_error());
+		return 1;
+	}
+	auto octree = Octree::Create();
+	octree->Update(builder);
+	uint32_t root[8];
+	svo_memcpy_d2h(0, root, octree->GetBuffer(), sizeof(root), nullptr);
+	printf("%llu %llu %u", (unsigned long long)voxelizer->GetVoxelFragmentCount(), (unsigned long long)octree->GetRange(), octree->GetLevel());
+	for (uint32_t w : root) printf(" %08x", w);
+	printf("\n");
+	fprintf(stderr, "Octree range: %llu (%f MB)\n", (unsigned long long)octree->GetRange(), octree->GetRange() / 1000000.0f);
+	return 0;
+}
