@@ -150,78 +150,46 @@ SVO_DEV void lb_backoff() {
 // Tiles are numbered by blockIdx.x: thread blocks of a 1-D grid are dispatched in index order, so every
 // predecessor of a running tile has been started (and running blocks are never preempted) -- the forward
 // progress the look-back needs, without a ticket atomic in front of the tile's loads.
-template <int BLOCK, int ITEMS, int RBITS, int MINB, class StateT>
-__global__ void __launch_bounds__(BLOCK, MINB)
-    k_onesweep_pass(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out, uint64_t n, uint32_t shift,
-                    uint32_t mask, uint32_t pass, const uint32_t *__restrict__ g_bins /* exclusive, this pass */,
-                    StateT *state /*[tiles][RADIX]*/) {
+// FULL = the tile holds TILE keys (every tile but possibly the last): no bounds checks, no padding bin.
+template <int BLOCK, int ITEMS, int RBITS, class StateT, bool FULL>
+SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out, uint32_t tile_count, uint32_t shift,
+                           uint32_t mask, uint32_t pass, const uint32_t *__restrict__ g_bins, StateT *state, uint64_t *s_keys,
+                           uint32_t *s_wsum) {
 	using C = OnesweepCfg<BLOCK, ITEMS, RBITS>;
 	constexpr int RADIX = C::RADIX, NB = C::NB, NW = C::NW, TILE = C::TILE, DPT = C::DPT, DTHREADS = C::DTHREADS;
 	using LB = LbCodec<StateT>;
-	SVO_DYN_SMEM(uint64_t, s_keys);                                  // TILE keys
-	uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_keys + TILE);  // NW * NB: per-warp digit counters, then slot bases
+	uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_keys + TILE);  // NW * NB: per-warp digit counters, then warp prefixes
 	uint32_t *s_tile_off = s_hist + NW * NB;                         // NB: first slot of each digit inside the tile
 	uint32_t *s_gofs = s_tile_off + NB;                              // RADIX: global offset minus tile offset (mod 2^32)
-	__shared__ uint32_t s_wsum[RADIX / 32 + 1];
-
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t tile = blockIdx.x;
-	const uint64_t tile_base = (uint64_t)tile * TILE;
-	const uint32_t tile_count = (uint32_t)(n - tile_base < (uint64_t)TILE ? n - tile_base : (uint64_t)TILE);
+	const uint32_t wbase = warp * 32 * ITEMS;
 
 	// warp-striped load: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS), item i of lane l is element i*32 + l
 	uint64_t key[ITEMS];
-	const uint32_t wbase = warp * 32 * ITEMS;
+	{
+		const uint64_t *src = keys_in + (uint64_t)tile * TILE + wbase + lane;
 #pragma unroll
-	for (int i = 0; i < ITEMS; ++i) {
-		const uint32_t e = wbase + i * 32 + lane;
-		key[i] = e < tile_count ? keys_in[tile_base + e] : ~0ull;
+		for (int i = 0; i < ITEMS; ++i) key[i] = (FULL || wbase + i * 32 + lane < tile_count) ? src[i * 32] : ~0ull;
 	}
 	for (int i = threadIdx.x; i < NW * NB; i += BLOCK) s_hist[i] = 0; // overlaps the loads in flight
 	__syncthreads();
 
 	// rank inside the warp.  Stable: items in increasing i, lanes in increasing l.  The leader (lowest lane) of
 	// each digit group bumps the warp's counter with ONE shared-memory atomic; a warp's atomics execute in
-	// program order, so no warp barrier is needed between items and the 3 stages pipeline across items.
+	// program order, so no warp barrier is needed between items and the stages pipeline across items.
 	uint32_t *wh = s_hist + warp * NB;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	uint32_t dig[ITEMS];
-	unsigned peers[ITEMS];
 	uint32_t rank[ITEMS];
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
-		const uint32_t e = wbase + i * 32 + lane;
-		dig[i] = e < tile_count ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
-#if SVO_OS_BALLOT
-		// multi-split by ballots: one vote per digit bit (MATCH.ANY serialises over the distinct values of the
-		// warp, ~32 for the low digits of a surface's Morton codes)
-		unsigned pm = FULL_MASK;
-#pragma unroll
-		for (int b = 0; b < RBITS; ++b) {
-			const uint32_t bit = (dig[i] >> b) & 1u;
-			const unsigned m = __ballot_sync(FULL_MASK, bit);
-			pm &= ~(m ^ (0u - bit));
-		}
-		if (tile_count < (uint32_t)TILE) { // padding exists only in the last tile (block-uniform branch)
-			const uint32_t bit = dig[i] >> RBITS;
-			const unsigned m = __ballot_sync(FULL_MASK, bit);
-			pm &= ~(m ^ (0u - bit));
-		}
-		peers[i] = pm;
-#else
-		peers[i] = __match_any_sync(FULL_MASK, dig[i]);
-#endif
-	}
-#pragma unroll
-	for (int i = 0; i < ITEMS; ++i) {
-		rank[i] = 0;
-		if ((peers[i] & lt_mask) == 0u) rank[i] = atomicAdd(&wh[dig[i]], (uint32_t)__popc(peers[i]));
+		const uint32_t d = (FULL || wbase + i * 32 + lane < tile_count) ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
+		const unsigned peers = __match_any_sync(FULL_MASK, d);
+		const uint32_t below = (uint32_t)__popc(peers & lt_mask);
+		uint32_t base = 0;
+		if (below == 0u) base = atomicAdd(&wh[d], (uint32_t)__popc(peers));
 		SVO_EMU_WARP_ORDER(); // hardware issues a warp's atomics in program order; the emulator's lanes are free-running
-	}
-#pragma unroll
-	for (int i = 0; i < ITEMS; ++i) {
-		const int leader = __ffs((int)peers[i]) - 1;
-		rank[i] = __shfl_sync(FULL_MASK, rank[i], leader) + (uint32_t)__popc(peers[i] & lt_mask);
+		rank[i] = __shfl_sync(FULL_MASK, base, __ffs((int)peers) - 1) + below;
 	}
 	__syncthreads();
 
@@ -245,6 +213,14 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 			*reinterpret_cast<volatile StateT *>(state + (uint64_t)tile * RADIX + d) = LB::pack(tile == 0 ? PRE : AGG, run);
 		}
 	}
+	if (!FULL && threadIdx.x == BLOCK - 1) { // padding bin of the last tile: prefix over the warps
+		uint32_t run = 0;
+		for (int w = 0; w < NW; ++w) {
+			const uint32_t c = s_hist[w * NB + RADIX];
+			s_hist[w * NB + RADIX] = run;
+			run += c;
+		}
+	}
 	// exclusive scan of the tile totals over the digits (digit threads are whole warps)
 	uint32_t inc = 0;
 	if (threadIdx.x < DTHREADS) {
@@ -259,64 +235,62 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 		uint32_t run = wpre + inc - my_sum; // first slot of this thread's first digit
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
-			const uint32_t d = threadIdx.x * DPT + j;
-			s_tile_off[d] = run;
-#pragma unroll
-			for (int w = 0; w < NW; ++w) s_hist[w * NB + d] += run; // slot base of (warp, digit)
+			s_tile_off[threadIdx.x * DPT + j] = run;
 			run += bin_total[j];
 		}
 	}
-	if (threadIdx.x == BLOCK - 1) { // padding bin (only the last tile has padding): after every real key
-		uint32_t run = tile_count;
-		for (int w = 0; w < NW; ++w) {
-			const uint32_t c = s_hist[w * NB + RADIX];
-			s_hist[w * NB + RADIX] = run;
-			run += c;
-		}
-	}
+	if (!FULL && threadIdx.x == 0) s_tile_off[RADIX] = tile_count; // padding sorts after every real key
 	__syncthreads();
 
 	// reorder through shared memory (needs tile-local offsets only: runs while predecessors publish)
 #pragma unroll
-	for (int i = 0; i < ITEMS; ++i) s_keys[s_hist[warp * NB + dig[i]] + rank[i]] = key[i];
+	for (int i = 0; i < ITEMS; ++i) {
+		const uint32_t d = (FULL || wbase + i * 32 + lane < tile_count) ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
+		s_keys[s_tile_off[d] + s_hist[warp * NB + d] + rank[i]] = key[i];
+	}
 
-	// decoupled look-back, per digit, LOOKBACK_DEPTH predecessor states in flight
+	// decoupled look-back, per digit.  Kept lean on purpose: every digit thread of every tile spins here, so
+	// the loop body is 32-bit pointer arithmetic with immediate offsets and 4 predecessor states in flight.
 	if (threadIdx.x < DTHREADS) {
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
 			const uint32_t d = threadIdx.x * DPT + j;
-			uint64_t excl = 0;
+			uint32_t excl = 0; // offsets are taken mod 2^32 (n < 2^32)
 			if (tile != 0 && !(SVO_OS_EXPERIMENT & 2)) {
-				int64_t t = (int64_t)tile - 1;
-				bool done = false;
-				while (!done) {
-					StateT s[LOOKBACK_DEPTH];
-#pragma unroll
-					for (int q = 0; q < LOOKBACK_DEPTH; ++q)
-						s[q] = t - q >= 0 ? *reinterpret_cast<const volatile StateT *>(state + (uint64_t)(t - q) * RADIX + d)
-						                  : LB::pack(PRE, 0);
-					int adv = 0;
-#pragma unroll
-					for (int q = 0; q < LOOKBACK_DEPTH; ++q) {
-						if (done || adv != q) continue; // stop at the first state that is not ready yet
-						const uint32_t c = LB::code(s[q]);
-						if (c == PRE) {
-							excl += LB::value(s[q]);
-							done = true;
-						} else if (c == AGG) {
-							excl += LB::value(s[q]);
-							++adv;
-						}
+				const volatile StateT *p = state + (size_t)(tile - 1) * RADIX + d; // nearest predecessor not yet summed
+				uint32_t left = tile;                                            // predecessors from p backwards
+				for (;;) {
+					if (left >= 4u) {
+						const StateT s0 = p[0], s1 = p[-RADIX], s2 = p[-2 * RADIX], s3 = p[-3 * RADIX];
+						const uint32_t c0 = LB::code(s0), c1 = LB::code(s1), c2 = LB::code(s2), c3 = LB::code(s3);
+						if (c0 != PRE && c0 != AGG) { lb_backoff(); continue; }
+						excl += (uint32_t)LB::value(s0);
+						if (c0 == PRE) break;
+						if (c1 != PRE && c1 != AGG) { p -= RADIX, left -= 1u; continue; }
+						excl += (uint32_t)LB::value(s1);
+						if (c1 == PRE) break;
+						if (c2 != PRE && c2 != AGG) { p -= 2 * RADIX, left -= 2u; continue; }
+						excl += (uint32_t)LB::value(s2);
+						if (c2 == PRE) break;
+						if (c3 != PRE && c3 != AGG) { p -= 3 * RADIX, left -= 3u; continue; }
+						excl += (uint32_t)LB::value(s3);
+						if (c3 == PRE) break;
+						p -= 4 * RADIX, left -= 4u;
+					} else { // the first few tiles: one state at a time (tile 0 always holds a prefix)
+						const StateT s0 = p[0];
+						const uint32_t c0 = LB::code(s0);
+						if (c0 != PRE && c0 != AGG) { lb_backoff(); continue; }
+						excl += (uint32_t)LB::value(s0);
+						if (c0 == PRE) break;
+						p -= RADIX, left -= 1u;
 					}
-					t -= adv;
-					if (!done && adv == 0) lb_backoff();
 				}
 #ifdef SVO_EMU
 				if (!g_emu_lookback_aggregate_only)
 #endif
-					*reinterpret_cast<volatile StateT *>(state + (uint64_t)tile * RADIX + d) = LB::pack(PRE, excl + bin_total[j]);
+					*reinterpret_cast<volatile StateT *>(state + (size_t)tile * RADIX + d) = LB::pack(PRE, (uint64_t)excl + bin_total[j]);
 			}
-			s_gofs[d] = (uint32_t)((uint64_t)g_bins[d] + excl) - s_tile_off[d];
+			s_gofs[d] = g_bins[d] + excl - s_tile_off[d];
 		}
 	}
 	__syncthreads();
@@ -325,16 +299,32 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
 		const uint32_t idx = i * BLOCK + threadIdx.x;
-		if (idx < tile_count) {
+		if (FULL || idx < tile_count) {
 			const uint64_t k = s_keys[idx];
 			const uint32_t d = (uint32_t)(k >> shift) & mask;
 #if (SVO_OS_EXPERIMENT & 1)
-			keys_out[tile_base + idx] = k; (void)d;
+			keys_out[(uint64_t)tile * TILE + idx] = k; (void)d;
 #else
 			keys_out[(uint32_t)(s_gofs[d] + idx)] = k;
 #endif
 		}
 	}
+}
+
+template <int BLOCK, int ITEMS, int RBITS, int MINB, class StateT>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    k_onesweep_pass(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out, uint64_t n, uint32_t shift,
+                    uint32_t mask, uint32_t pass, const uint32_t *__restrict__ g_bins /* exclusive, this pass */,
+                    StateT *state /*[tiles][RADIX]*/) {
+	using C = OnesweepCfg<BLOCK, ITEMS, RBITS>;
+	SVO_DYN_SMEM(uint64_t, s_keys);
+	__shared__ uint32_t s_wsum[C::RADIX / 32 + 1];
+	const uint64_t tile_base = (uint64_t)blockIdx.x * C::TILE;
+	const uint32_t tile_count = (uint32_t)(n - tile_base < (uint64_t)C::TILE ? n - tile_base : (uint64_t)C::TILE);
+	if (tile_count == (uint32_t)C::TILE)
+		onesweep_tile<BLOCK, ITEMS, RBITS, StateT, true>(keys_in, keys_out, tile_count, shift, mask, pass, g_bins, state, s_keys, s_wsum);
+	else
+		onesweep_tile<BLOCK, ITEMS, RBITS, StateT, false>(keys_in, keys_out, tile_count, shift, mask, pass, g_bins, state, s_keys, s_wsum);
 }
 
 struct SortScratch {
