@@ -104,6 +104,12 @@ SVO_API uint64_t svo_scene_triangle_count(const svo_scene *scene);
  * shard may be NULL (whole grid). */
 SVO_API int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, void *stream,
                                  svo_voxelizer **out);
+/* A "pre-voxelized" source: a voxelizer whose fragment list is supplied by the caller (n 64-bit fragments,
+ * morton << 24 | rgb, any order; host pointer unless on_device).  Lets OctreeBuilder run on fragment lists
+ * produced elsewhere -- e.g. the reference's own voxelizer output (src/Voxelizer.hpp:52) re-packed -- and is
+ * what the SPIR-V golden tests use.  svo_voxelizer_voxelize() then just restores the list. */
+SVO_API int svo_voxelizer_create_from_fragments(int device, uint32_t level, const uint64_t *fragments, uint64_t n, int on_device,
+                                                void *stream, svo_voxelizer **out);
 SVO_API void svo_voxelizer_destroy(svo_voxelizer *vox);
 /* Voxelizer::CmdVoxelize (src/Voxelizer.hpp:49, src/Voxelizer.cpp:167-179): enqueues the fragment
  * emission on the stream (the reference records it into a command buffer). */

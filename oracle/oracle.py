@@ -2,7 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 import this module; the product package (sparsevoxeloctree_b200) never does.
-PARITY UNPINNED -- see oracle/svo_oracle.h.
+Parity status (pinned against the executed reference SPIR-V, rasterizer stage unpinned): see oracle/svo_oracle.h.
 """
 from __future__ import annotations
 
@@ -50,6 +50,11 @@ def lib() -> C.CDLL:
         L.orc_build.restype = C.c_int64
         L.orc_canonicalise.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_canonicalise.restype = C.c_int64
+        L.orc_debug_tri_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_debug_tri_setup.restype = None
+        L.orc_debug_raster_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int64]
+        L.orc_debug_raster_pixels.restype = C.c_int64
         L.orc_morton.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_morton.restype = C.c_uint64
         _lib = L
@@ -134,6 +139,25 @@ def canonicalise(words, level):
     n2 = L.orc_canonicalise(_ptr(words), len(words), level, _ptr(depth), _ptr(mort), _ptr(word), n)
     assert n2 == n
     return depth, mort, word
+
+
+def debug_tri_setup(p0, p1, p2, level):
+    """(axis, gAABB[4], gDepthRange[2]), snapped xy[3][2] of one triangle (geometry-stage outputs)."""
+    p = [np.ascontiguousarray(v, dtype=np.float32) for v in (p0, p1, p2)]
+    a = np.zeros(7, np.uint32)
+    xy = np.zeros(6, np.int32)
+    lib().orc_debug_tri_setup(_ptr(p[0]), _ptr(p[1]), _ptr(p[2]), level, _ptr(a), _ptr(xy))
+    return a, xy.reshape(3, 2)
+
+
+def debug_raster_pixels(p0, p1, p2, level, mode):
+    """Covered pixels (px, py) and the pinned fp64 depth of one triangle, row-major."""
+    p = [np.ascontiguousarray(v, dtype=np.float32) for v in (p0, p1, p2)]
+    L = lib()
+    n = L.orc_debug_raster_pixels(_ptr(p[0]), _ptr(p[1]), _ptr(p[2]), level, mode, None, None, None, 0)
+    px, py, z = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
+    L.orc_debug_raster_pixels(_ptr(p[0]), _ptr(p[1]), _ptr(p[2]), level, mode, _ptr(px), _ptr(py), _ptr(z), n)
+    return px, py, z
 
 
 def frags_from_xyzc(x, y, z, rgb):

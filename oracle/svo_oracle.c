@@ -1,9 +1,10 @@
 /*
  * oracle/svo_oracle.c -- CPU ORACLE. TEST INFRASTRUCTURE ONLY (see svo_oracle.h).
  *
- * PARITY UNPINNED: no reference fixture exists for this path; pinned by hand-derived
- * KATs only (tests/test_oracle_kat.py).  Every function cites the reference file:line
- * (relative to /root/reference) that it restates.
+ * PARITY STATUS: see svo_oracle.h -- pinned against the reference's own SPIR-V binaries executed
+ * by oracle/spirv_interp.py (tests/golden/spirv_*.npz) for everything the shaders define; the
+ * fixed-function rasterizer stage is unpinned (driver-defined) and uses DESIGN.md section 3.
+ * Every function cites the reference file:line (relative to /root/reference) that it restates.
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
  * -ffp-contract=off matters: the pinned arithmetic below is "one IEEE operation per
@@ -334,6 +335,50 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
 		}
 	}
 	return counter;
+}
+
+/* Debug views used by the SPIR-V cross-checks (tests/golden/make_spirv_golden.py): the geometry-stage
+ * outputs of one triangle, and its covered pixels with the pinned depth, before voxelizer.frag. */
+void orc_debug_tri_setup(const float *p0, const float *p1, const float *p2, uint32_t level, uint32_t out_axis_aabb_zr[7],
+                         int32_t out_xy_snapped[6]) {
+	orc_tri t;
+	orc_tri_setup(p0, p1, p2, 1u << level, &t);
+	out_axis_aabb_zr[0] = t.axis;
+	for (int i = 0; i < 4; ++i) out_axis_aabb_zr[1 + i] = t.aabb[i];
+	out_axis_aabb_zr[5] = t.zr[0], out_axis_aabb_zr[6] = t.zr[1];
+	for (int i = 0; i < 3; ++i) out_xy_snapped[2 * i] = t.valid ? t.X[i] : 0, out_xy_snapped[2 * i + 1] = t.valid ? t.Y[i] : 0;
+}
+int64_t orc_debug_raster_pixels(const float *p0, const float *p1, const float *p2, uint32_t level, int mode, int32_t *out_px,
+                                int32_t *out_py, double *out_z, int64_t cap) {
+	const uint32_t res = 1u << level;
+	orc_tri t;
+	orc_tri_setup(p0, p1, p2, res, &t);
+	if (!t.valid || (t.area2 == 0 && mode == ORC_CENTER)) return 0;
+	orc_plane pl;
+	plane_setup(&t, &pl);
+	int32_t xmin = t.X[0], xmax = t.X[0], ymin = t.Y[0], ymax = t.Y[0];
+	for (int i = 1; i < 3; ++i) {
+		if (t.X[i] < xmin) xmin = t.X[i];
+		if (t.X[i] > xmax) xmax = t.X[i];
+		if (t.Y[i] < ymin) ymin = t.Y[i];
+		if (t.Y[i] > ymax) ymax = t.Y[i];
+	}
+	int32_t px0 = floor_div256(xmin) - 1, px1 = floor_div256(xmax) + 1, py0 = floor_div256(ymin) - 1, py1 = floor_div256(ymax) + 1;
+	if (px0 < 0) px0 = 0;
+	if (py0 < 0) py0 = 0;
+	if (px1 > (int32_t)res - 1) px1 = (int32_t)res - 1;
+	if (py1 > (int32_t)res - 1) py1 = (int32_t)res - 1;
+	int64_t n = 0;
+	for (int32_t py = py0; py <= py1; ++py)
+		for (int32_t px = px0; px <= px1; ++px) {
+			if (!covered(&t, mode, px, py)) continue;
+			if (n < cap) {
+				out_px[n] = px, out_py[n] = py;
+				out_z[n] = fma(pl.dzdx, (double)(px * 256 + 128 - pl.X0), fma(pl.dzdy, (double)(py * 256 + 128 - pl.Y0), pl.z0));
+			}
+			++n;
+		}
+	return n;
 }
 
 /* ------------------------------------------------------------------------------------------

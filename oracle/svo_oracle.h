@@ -7,13 +7,16 @@
  * load this library, and there only as the checker / the CPU baseline.  The
  * product (sparsevoxeloctree_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
- * this path, and its shaders cannot be executed in this image (no
- * Vulkan ICD), so this oracle is pinned only against hand-derived known-answer
- * tests read off the shader sources (tests/test_oracle_kat.py) -- see DESIGN.md.
- * The fixed-function rasterizer arithmetic lives in the Vulkan driver, not in
- * the reference tree; the arithmetic used here for coverage and depth is the
- * "pinned arithmetic" stated in DESIGN.md section 3.
+ * PARITY STATUS: the reference ships no tests, golden vectors or fixtures for this path
+ *  and cannot run in this image (no Vulkan ICD).  What pins this oracle:
+ *  - PINNED to the reference's own code for everything its shaders define: the checked-in
+ *    SPIR-V binaries (shader/include/spirv/*.u32) are EXECUTED by oracle/spirv_interp.py and
+ *    their outputs committed (tests/golden/spirv_*.npz): orc_build equals the four compute
+ *    shaders word for word; the geometry and fragment stages equal voxelizer.geom / .frag
+ *    (tests/test_spirv_golden.py), plus hand-derived KATs (tests/test_oracle_kat.py).
+ *  - UNPINNED for the one stage the reference does not define: the fixed-function rasterizer
+ *    (coverage, snapping, depth interpolation live in the Vulkan driver).  The arithmetic used
+ *    here for that stage is the "pinned arithmetic" stated in DESIGN.md section 3.
  */
 #ifndef SVO_ORACLE_H
 #define SVO_ORACLE_H
@@ -57,6 +60,13 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
                      const orc_draw *draws, uint32_t n_draws, uint32_t level, int mode,
                      const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out, int64_t cap,
                      int nthreads);
+
+/* Debug views for the SPIR-V cross-checks: geometry-stage outputs {axis, gAABB[4], gDepthRange[2]} + snapped window
+ * coordinates of one triangle; and its covered pixels with the pinned fp64 depth (before voxelizer.frag). */
+void orc_debug_tri_setup(const float *p0, const float *p1, const float *p2, uint32_t level, uint32_t out_axis_aabb_zr[7],
+                         int32_t out_xy_snapped[6]);
+int64_t orc_debug_raster_pixels(const float *p0, const float *p1, const float *p2, uint32_t level, int mode, int32_t *out_px,
+                                int32_t *out_py, double *out_z, int64_t cap);
 
 /*
  * The OctreeBuilder level loop (OctreeBuilder.cpp:142-210 driving octree_init_node /

@@ -59,6 +59,7 @@ SYMBOLS = [
     ("svo_scene_destroy", None, [_P]),
     ("svo_scene_triangle_count", C.c_uint64, [_P]),
     ("svo_voxelizer_create", C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(svo_shard), _P, C.POINTER(_P)]),
+    ("svo_voxelizer_create_from_fragments", C.c_int, [C.c_int, C.c_uint32, _P, C.c_uint64, C.c_int, _P, C.POINTER(_P)]),
     ("svo_voxelizer_destroy", None, [_P]),
     ("svo_voxelizer_voxelize", C.c_int, [_P, _P]),
     ("svo_voxelizer_level", C.c_uint32, [_P]),
@@ -259,6 +260,18 @@ class Voxelizer:
                                                          _stream_ptr(stream), C.byref(h)))
         self._h = h
         self.shard = shard
+        return self
+
+    @staticmethod
+    def CreateFromFragments(fragments, octree_level: int, device: int = 0, stream=None, lib: Library | None = None):
+        """A pre-voxelized source: `fragments` = uint64 array of morton << 24 | rgb (host), any order."""
+        self = Voxelizer()
+        self.lib, self.device, self._scene, self.shard = lib or get_library(), device, None, None
+        self._ext = np.ascontiguousarray(fragments, dtype=np.uint64)
+        h = _P()
+        self.lib.check(self.lib.dll.svo_voxelizer_create_from_fragments(device, octree_level, self._ext.ctypes.data, len(self._ext), 0,
+                                                                        _stream_ptr(stream), C.byref(h)))
+        self._h = h
         return self
 
     def GetScenePtr(self) -> Scene:

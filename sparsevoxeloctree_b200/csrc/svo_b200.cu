@@ -109,6 +109,7 @@ struct svo_voxelizer {
 	DevBuf<LargeTri> large;
 	DevBuf<uint32_t> row_off, row_xy, row_li;
 	DevBuf<uint64_t> frags;
+	DevBuf<uint64_t> ext_frags; // svo_voxelizer_create_from_fragments: the caller's fragment list (voxelize re-copies it)
 	bool voxelized = false;
 	Timer t_raster;
 };
@@ -359,10 +360,41 @@ int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_s
 	return SVO_OK;
 }
 
+int svo_voxelizer_create_from_fragments(int device, uint32_t level, const uint64_t *fragments, uint64_t n, int on_device, void *stream,
+                                        svo_voxelizer **out) {
+	if (!out || (n && !fragments)) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_create_from_fragments: null argument");
+	*out = nullptr;
+	if (level < 1 || 3 * level + 24 > 64) return fail(SVO_ERR_INVALID_ARGUMENT, "level must be 1..13");
+	if (n >= 0xffffffffull) return fail(SVO_ERR_CAPACITY, "more than 2^32-2 fragments");
+	DeviceGuard guard(device);
+	if (!guard.ok) return fail(SVO_ERR_CUDA, "cudaSetDevice failed (no CUDA device?)");
+	SVO_TRY(configure_device_pool(device));
+	cudaStream_t s = (cudaStream_t)stream;
+	svo_voxelizer *v = new (std::nothrow) svo_voxelizer();
+	if (!v) return fail(SVO_ERR_CUDA, "out of host memory");
+	v->device = device;
+	v->level = v->key_level = level;
+	v->n_frag = n;
+	int rc = v->t_raster.init();
+	if (!rc) rc = v->frags.alloc(n, s);
+	if (!rc) rc = v->ext_frags.alloc(n, s);
+	if (!rc && n &&
+	    cudaMemcpyAsync(v->ext_frags.p, fragments, n * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s) != cudaSuccess)
+		rc = fail(SVO_ERR_CUDA, "fragment copy failed");
+	if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "stream sync failed");
+	if (rc) {
+		svo_voxelizer_destroy(v);
+		return rc;
+	}
+	*out = v;
+	return SVO_OK;
+}
+
 void svo_voxelizer_destroy(svo_voxelizer *v) {
 	if (!v) return;
 	DeviceGuard guard(v->device);
 	v->tri_off.release(0), v->large.release(0), v->row_off.release(0), v->row_xy.release(0), v->row_li.release(0), v->frags.release(0);
+	v->ext_frags.release(0);
 	v->t_raster.destroy();
 	delete v;
 }
@@ -371,6 +403,13 @@ int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
 	if (!v) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_voxelize: null handle");
 	DeviceGuard guard(v->device);
 	cudaStream_t s = (cudaStream_t)stream;
+	if (!v->scene) { // fragment list supplied by the caller: restore it (the builder sorts the list in place)
+		SVO_CUDA_TRY(cudaEventRecord(v->t_raster.a, s));
+		if (v->n_frag) SVO_CUDA_TRY(cudaMemcpyAsync(v->frags.p, v->ext_frags.p, v->n_frag * 8, cudaMemcpyDeviceToDevice, s));
+		SVO_CUDA_TRY(cudaEventRecord(v->t_raster.b, s));
+		v->t_raster.recorded = v->voxelized = true;
+		return SVO_OK;
+	}
 	const SceneView &sv = v->scene->view;
 	SVO_CUDA_TRY(cudaEventRecord(v->t_raster.a, s));
 	if (v->n_frag_small) {

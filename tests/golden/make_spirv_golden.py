@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Runs the REFERENCE'S OWN shader binaries (shader/include/spirv/*.u32 under /root/reference) through the small
+SPIR-V interpreter in oracle/spirv_interp.py and records their outputs as golden vectors.
+
+  part A (OctreeBuilder): octree_init_node / octree_tag_node / octree_alloc_node / octree_modify_arg, driven by
+          a restatement of the dispatch sequence of OctreeBuilder::CmdBuild (src/OctreeBuilder.cpp:142-210),
+          on fragment lists in the reference's uvec2 packing  ->  the node buffer, word for word.
+  part B (Voxelizer): voxelizer.geom per triangle (gAxis, gAABB, gDepthRange, projected vertices) and
+          voxelizer.frag per covered pixel (voxel position + packed fragment).  The pixel list and the depth at
+          the pixel centre come from the pinned rasterizer arithmetic (the fixed-function stage is the one thing
+          the shaders do not define); gl_FragCoord.z is that depth rounded to fp32, as a shader input would be.
+
+The interpreter needs /root/reference, which does not exist on the GPU box: the vectors are committed
+(tests/golden/spirv_*.npz) and tests/test_spirv_golden.py checks the oracle against them anywhere.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle, spirv_interp as si  # noqa: E402
+from sparsevoxeloctree_b200 import scenes  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SPV = "/root/reference/shader/include/spirv/"
+
+
+def gx64(x):  # group_x_64, src/OctreeBuilder.cpp:6
+    return (x >> 6) + (1 if x & 63 else 0)
+
+
+def spirv_build(frag_packed, level, cap_words):
+    """OctreeBuilder::CmdBuild with the reference's compute shaders (subgroup size 1, invocations in order)."""
+    F, res = len(frag_packed), 1 << level
+    init = si.Module.from_u32_file(SPV + "octree_init_node.comp.u32")
+    tag = si.Module.from_u32_file(SPV + "octree_tag_node.comp.u32", spec={0: res, 1: F})  # OctreeBuilder.cpp:102-104
+    alloc = si.Module.from_u32_file(SPV + "octree_alloc_node.comp.u32")
+    mod = si.Module.from_u32_file(SPV + "octree_modify_arg.comp.u32")
+    counter = np.zeros(1, np.uint32)                       # Counter::Reset(0), OctreeBuilder.cpp:14-15
+    octree = np.full(cap_words, 0xCDCDCDCD, np.uint32)     # uninitialised device memory
+    frags = np.ascontiguousarray(frag_packed, dtype=np.uint32).reshape(-1)
+    info = np.array([0, 8], np.uint32)                     # build_info staging, OctreeBuilder.cpp:27-31
+    indirect = np.array([1, 1, 1], np.uint32)              # indirect staging, :36-40
+    bufs = {(0, 0): counter, (0, 1): octree, (0, 2): frags, (0, 3): info, (0, 4): indirect}
+    for i in range(1, level + 1):                          # OctreeBuilder.cpp:167
+        for g in range(int(indirect[0]) * 64):
+            init.run({("builtin", 28): [g, 0, 0]}, bufs)
+        for g in range(gx64(F) * 64):
+            tag.run({("builtin", 28): [g, 0, 0]}, bufs)
+        if i != level:
+            for g in range(int(indirect[0]) * 64):
+                alloc.run({("builtin", 28): [g, 0, 0]}, bufs)
+            mod.run({}, bufs)
+    rng = (int(counter[0]) + 1) * 8 * 4                    # GetOctreeRange, OctreeBuilder.cpp:212-214
+    return octree[: rng // 4].copy(), rng
+
+
+BUILD_CASES = {
+    "soup200_L5_center": (lambda: scenes.random_soup(200, 6, 0.005, 0.6), 5, oracle.CENTER),
+    "soup60_L7_conservative": (lambda: scenes.random_soup(60, 9, 0.01, 0.5), 7, oracle.CONSERVATIVE_EXACT),
+    "heightfield11_L5_conservative": (lambda: scenes.heightfield(11), 5, oracle.CONSERVATIVE_EXACT),
+}
+
+
+def make_build_case(name):
+    gen, level, mode = BUILD_CASES[name]
+    mesh = gen()
+    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, mode)
+    packed = np.array([oracle.pack_fragment(int(f["x"]), int(f["y"]), int(f["z"]), int(f["rgb"])) for f in fr], np.uint32)
+    cap = 8 * (1 + sum(min(8 ** d, len(fr)) for d in range(1, level)))
+    words, rng = spirv_build(packed, level, cap)
+    return dict(level=level, packed=packed, words=words, range_bytes=rng)
+
+
+def voxelizer_triangles():
+    """A few hundred triangles: random soups of several size classes, a heightfield patch, axis ties, slivers."""
+    tris = []
+    for seed, lo, hi in ((11, 0.02, 0.3), (12, 0.2, 1.5), (13, 0.005, 0.05)):
+        m = scenes.random_soup(70, seed, lo, hi)
+        tris += [m.positions[m.indices[3 * k:3 * k + 3]] for k in range(m.n_triangles)]
+    m = scenes.heightfield(7)
+    tris += [m.positions[m.indices[3 * k:3 * k + 3]] for k in range(m.n_triangles)]
+    tris.append(np.array([[0.0, 0.0, 0.0], [0.5, -0.5, 0.0], [0.0, 0.0, 0.5]], np.float32))      # |nx| == |ny| tie
+    tris.append(np.array([[-0.9, 0.3, 0.1], [0.9, 0.3001, 0.1], [0.0, 0.3, 0.1003]], np.float32))  # sliver
+    tris.append(np.array([[0.25, -1.0, -1.0], [0.25, 1.0, -1.0], [0.25, -1.0, 1.0]], np.float32))  # big, axis 0
+    return [np.ascontiguousarray(t, dtype=np.float32) for t in tris]
+
+
+def make_voxelizer_case(level=6, mode=oracle.CONSERVATIVE_EXACT, albedo=0x00A1B2C3):
+    res = 1 << level
+    geom = si.Module.from_u32_file(SPV + "voxelizer.geom.u32", spec={0: res})
+    frag = si.Module.from_u32_file(SPV + "voxelizer.frag.u32", spec={0: res, 1: 1})
+    g_pos = next(v for v, (t, sc) in geom.vars.items() if sc == 3 and geom.types[geom.types[t][2]][0] == "struct")
+    g_axis, g_aabb, g_zr = (geom.var_by_location(k, 3) for k in (1, 2, 3))
+    f_axis, f_aabb, f_zr, f_uv = (frag.var_by_location(k, 1) for k in (1, 2, 3, 0))
+    tris = voxelizer_triangles()
+    geo_out, frag_in, frag_out = [], [], []
+    for t in tris:
+        emitted = []
+        null_vtx = geom._null(geom.types[geom.types[geom.vars[next(v for v, (tt, sc) in geom.vars.items() if sc == 1 and 30 not in geom.decor.get(v, {}))][0]][2]][1])
+        gl_in = []
+        for k in range(3):
+            v = [x if not isinstance(x, list) else list(x) for x in null_vtx]
+            v[0] = [np.float32(t[k][0]), np.float32(t[k][1]), np.float32(t[k][2]), np.float32(1.0)]  # voxelizer.vert:9
+            gl_in.append(v)
+        geom.run({"gl_in": gl_in, ("loc", 0): [[np.float32(0), np.float32(0)]] * 3}, {}, None, on_emit=emitted.append)
+        assert len(emitted) == 3
+        e = emitted[0]
+        axis, aabb, zr = int(e[g_axis]), [int(x) for x in e[g_aabb]], [int(x) for x in e[g_zr]]
+        ndc = np.array([[float(c) for c in em[g_pos][0][:3]] for em in emitted], np.float32)
+        geo_out.append([axis] + aabb + zr + [int(v) for v in ndc.view(np.uint32).reshape(-1)])
+        # fixed-function stage: the pinned rasterizer arithmetic (coverage + depth at the pixel centre)
+        px, py, z = oracle.debug_raster_pixels(t[0], t[1], t[2], level, mode)
+        for x, y, zz in zip(px, py, z):
+            counter = np.zeros(1, np.uint32)
+            flist = np.zeros(2, np.uint32)
+            fc = [np.float32(x + 0.5), np.float32(y + 0.5), np.float32(zz), np.float32(1.0)]
+            try:
+                frag.run({("builtin", 15): fc, f_axis: axis, f_aabb: aabb, f_zr: zr, f_uv: [np.float32(0), np.float32(0)]},
+                         {(0, 0): counter, (0, 1): flist}, [0, 0xFFFFFFFF, albedo])  # push: uCountOnly, uTextureId, uAlbedo
+                out = (1, int(flist[0]), int(flist[1]))
+            except si.Discard:
+                out = (0, 0, 0)
+            frag_in.append((len(geo_out) - 1, int(x), int(y), float(zz)))
+            frag_out.append(out)
+    fi = np.array(frag_in, dtype=[("tri", "<i4"), ("px", "<i4"), ("py", "<i4"), ("z", "<f8")])
+    return dict(level=level, mode=mode, albedo=albedo, triangles=np.stack(tris), geom_out=np.array(geo_out, np.uint32),
+                frag_in=fi, frag_out=np.array(frag_out, np.uint32))
+
+
+if __name__ == "__main__":
+    import time
+    for n in BUILD_CASES:
+        t = time.time()
+        o = make_build_case(n)
+        np.savez_compressed(os.path.join(HERE, "spirv_build_" + n + ".npz"), **o)
+        print("build", n, len(o["packed"]), "fragments ->", o["range_bytes"], "bytes", f"{time.time() - t:.0f}s", flush=True)
+    t = time.time()
+    o = make_voxelizer_case()
+    np.savez_compressed(os.path.join(HERE, "spirv_voxelizer_L6_conservative.npz"), **o)
+    print("voxelizer", len(o["triangles"]), "triangles", len(o["frag_in"]), "pixels", f"{time.time() - t:.0f}s")

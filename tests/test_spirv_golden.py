@@ -1,0 +1,101 @@
+"""The reference's own shader binaries, executed (tests/golden/make_spirv_golden.py + oracle/spirv_interp.py),
+versus the CPU oracle (CPU tests) and versus the CUDA builder (GPU tests).
+
+This is what pins the oracle to the reference itself rather than to a reading of its sources: everything except
+the fixed-function rasterizer is defined by these SPIR-V modules."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from sparsevoxeloctree_b200 import api
+from tests.parity import morton_np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = sorted(glob.glob(os.path.join(HERE, "golden", "spirv_build_*.npz")))
+VOX = os.path.join(HERE, "golden", "spirv_voxelizer_L6_conservative.npz")
+
+
+def unpack(packed):
+    x = packed[:, 0] & 0xFFF
+    y = (packed[:, 0] >> 12) & 0xFFF
+    z = (packed[:, 0] >> 24) | ((packed[:, 1] >> 28) << 8)
+    return x, y, z, packed[:, 1] & 0xFFFFFF
+
+
+@pytest.mark.parametrize("path", BUILD, ids=[os.path.basename(p) for p in BUILD])
+def test_oracle_level_loop_equals_reference_compute_shaders(path):
+    g = np.load(path)
+    level = int(g["level"])
+    x, y, z, c = unpack(g["packed"])
+    words, rng = oracle.build_octree(oracle.frags_from_xyzc(x, y, z, c), level)
+    # same invocation order, same allocation order -> the node BUFFER is identical word for word
+    assert rng == int(g["range_bytes"])
+    assert (words == g["words"]).all()
+
+
+def test_oracle_geometry_stage_equals_reference_geom_shader():
+    g = np.load(VOX)
+    level = int(g["level"])
+    res = 1 << level
+    for t, go in zip(g["triangles"], g["geom_out"]):
+        a, xy = oracle.debug_tri_setup(t[0], t[1], t[2], level)
+        assert a.tolist() == go[:7].tolist()          # gAxis, gAABB, gDepthRange  (voxelizer.geom:30-42)
+        ndc = go[7:].astype(np.uint32).view(np.float32).reshape(3, 3)
+        # the emitted gl_Position (Project(), voxelizer.geom:15-19) through the viewport transform + snapping
+        sx = np.rint((((ndc[:, 0] + np.float32(1)) * np.float32(0.5)) * np.float32(res)) * np.float32(256)).astype(np.int64)
+        sy = np.rint((((ndc[:, 1] + np.float32(1)) * np.float32(0.5)) * np.float32(res)) * np.float32(256)).astype(np.int64)
+        got = sorted(zip(sx.tolist(), sy.tolist()))
+        assert got == sorted(map(tuple, xy.tolist()))  # the oracle may have swapped two vertices (winding)
+
+
+def test_oracle_fragment_stage_equals_reference_frag_shader():
+    g = np.load(VOX)
+    level, mode = int(g["level"]), int(g["mode"])
+    res = 1 << level
+    fi, fo = g["frag_in"], g["frag_out"]
+    draws = np.array([(0, 3, 0xFFFFFFFF, int(g["albedo"]))], oracle.DRAW_DTYPE)
+    n_pix = n_emit = n_zdiff = 0
+    for ti, t in enumerate(g["triangles"]):
+        sel = fi["tri"] == ti
+        outs = fo[sel]
+        ofr = oracle.voxelize(t, np.array([0, 1, 2], np.uint32), draws, level, mode)
+        kept = outs[outs[:, 0] == 1]
+        # the discards (gAABB test, voxelizer.frag:21-22) agree: same number of surviving fragments, same order
+        assert len(kept) == len(ofr), (ti, len(kept), len(ofr))
+        x, y, z, c = unpack(kept[:, 1:3])
+        n_pix += int(sel.sum())
+        n_emit += len(kept)
+        assert (c == ofr["rgb"]).all()
+        axis = int(g["geom_out"][ti][0])
+        zax = {0: "x", 1: "y", 2: "z"}[axis]   # the depth axis carries fp32-vs-fp64 rounding of gl_FragCoord.z
+        for name, got in (("x", x), ("y", y), ("z", z)):
+            d = got.astype(np.int64) - ofr[name].astype(np.int64)
+            if name == zax:
+                n_zdiff += int((d != 0).sum())
+                assert (np.abs(d) <= 1).all()
+            else:
+                assert (d == 0).all()
+    # gl_FragCoord.z reaches the shader as fp32; the oracle floors the fp64 plane value.  They may differ by one
+    # voxel only where z*res is within an fp32 ulp of an integer: a handful of pixels
+    assert n_emit > 10000 and n_zdiff <= 1e-3 * n_emit, (n_emit, n_zdiff)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", BUILD, ids=[os.path.basename(p) for p in BUILD])
+def test_cuda_builder_equals_reference_compute_shaders(path):
+    """OctreeBuilder on the very fragment list the reference's shaders consumed: canonically identical tree,
+    colours included (the stable sort keeps the emission order that the running average depends on)."""
+    from tests.parity import assert_same_tree
+    g = np.load(path)
+    level = int(g["level"])
+    x, y, z, c = unpack(g["packed"])
+    keys = (morton_np(x, y, z, level) << np.uint64(24)) | c.astype(np.uint64)
+    vox = api.Voxelizer.CreateFromFragments(keys, level)
+    b = api.OctreeBuilder.Create(vox)
+    vox.CmdVoxelize()
+    b.CmdBuild()
+    assert b.GetOctreeRange() == int(g["range_bytes"])
+    assert_same_tree(b.octree_to_host(), g["words"], level)
