@@ -10,7 +10,7 @@
  * PARITY STATUS: the reference ships no tests, golden vectors or fixtures for this path
  *  and cannot run in this image (no Vulkan ICD).  What pins this oracle:
  *  - PINNED to the reference's own code for everything its shaders define: the checked-in
- *    SPIR-V binaries (shader/include/spirv/*.u32) are EXECUTED by oracle/spirv_interp.py and
+ *    SPIR-V binaries (shader/include/spirv/<name>.u32) are EXECUTED by oracle/spirv_interp.py and
  *    their outputs committed (tests/golden/spirv_*.npz): orc_build equals the four compute
  *    shaders word for word; the geometry and fragment stages equal voxelizer.geom / .frag
  *    (tests/test_spirv_golden.py), plus hand-derived KATs (tests/test_oracle_kat.py).
