@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(HIST_BLOCK)
 				if (uniform) {
 					if (lane == 0) atomicAdd(&s_hist[p * MAX_RADIX + d], 32u);
 				} else if (ok)
-					atomicAdd(&s_hist[p * MAX_RADIX + d], 1u);
+					atomicAdd(&s_hist[p * MAX_RADIX + d], 1u); // (grouping by __match_any_sync measured slower: MATCH costs more than the adds)
 			}
 		}
 	}

@@ -109,32 +109,31 @@ class ShardedSVO:
         self.words = [0] * 8
         self.stage = None
 
-    # -- rank 0 owns a grow-only arena for the stitched tree (like the reference's up-front octree buffer) --
+    # -- rank 0 owns a grow-only arena for the stitched tree (like the reference's up-front octree buffer).
+    #    It is cached per process and device, so a fresh ShardedSVO (the end-to-end path) reuses the allocation
+    #    and the IPC mapping.  Every rank sees the same total, so all ranks take the same branch: no collective
+    #    is needed unless the arena really has to grow.
+    _ARENA = {}  # device -> dict(ptr, cap, peer)
+
     def _ensure_final(self, words: int):
-        torch, dist = self.torch, self.dist
+        dist = self.dist
         need = int(words)
-        if self.world == 1:
-            if need <= self.final_cap:
-                return
-        else:
-            grow = torch.tensor([1 if (self.rank == 0 and need > self.final_cap) else 0], device=self.tdev)
-            dist.broadcast(grow, 0)
-            if int(grow.item()) == 0:
-                return
-        cap = max(need + need // 4, 1 << 20)
-        if self.rank == 0:
-            if self.final:
-                self.lib.free(self.final, self.device)
-            self.final = self.lib.malloc(cap * 4, self.device)
-            self.final_cap = cap
-        if self.use_ipc:
-            handle = [self.lib.ipc_export(self.final, self.device) if self.rank == 0 else None]
-            dist.broadcast_object_list(handle, 0)
-            if self.rank != 0:
-                if self.peer_final:
-                    self.lib.ipc_close(self.peer_final, self.device)
-                self.peer_final = self.lib.ipc_open(handle[0], self.device)
-                self.final_cap = cap
+        ar = ShardedSVO._ARENA.setdefault((self.device, self.world, self.use_ipc), dict(ptr=0, cap=0, peer=0))
+        if need > ar["cap"]:
+            cap = max(need + need // 4, 1 << 20)
+            if self.rank == 0:
+                if ar["ptr"]:
+                    self.lib.free(ar["ptr"], self.device)
+                ar["ptr"] = self.lib.malloc(cap * 4, self.device)
+            if self.use_ipc:
+                handle = [self.lib.ipc_export(ar["ptr"], self.device) if self.rank == 0 else None]
+                dist.broadcast_object_list(handle, 0)
+                if self.rank != 0:
+                    if ar["peer"]:
+                        self.lib.ipc_close(ar["peer"], self.device)
+                    ar["peer"] = self.lib.ipc_open(handle[0], self.device)
+            ar["cap"] = cap
+        self.final, self.final_cap, self.peer_final = (ar["ptr"] if self.rank == 0 else None), ar["cap"], ar["peer"]
 
     def step(self, stream=None):
         """One sharded build: local subtrees, size exchange, fused rebase + gather, root block on rank 0."""
@@ -207,9 +206,4 @@ class ShardedSVO:
         for v in self.vox:
             v.Destroy()
         self.scene.Destroy()
-        if self.rank == 0 and self.final:
-            self.lib.free(self.final, self.device)
-            self.final = None
-        if self.peer_final:
-            self.lib.ipc_close(self.peer_final, self.device)
-            self.peer_final = 0
+        self.final, self.peer_final = None, 0  # the stitched-tree arena is cached for the process (see _ARENA)
