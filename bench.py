@@ -192,7 +192,9 @@ def run_ours(args):
     # -------- device-resident arm: inputs already in HBM, handles created (count pass done) ----------------
     phases_acc = {k: 0.0 for k in api.PHASES}
     sort_passes = 0
-    if world == 1:
+    # one device holds levels <= 13 in a 64-bit fragment; level 14 runs as 8 cube-local octant builds ("virtual shards")
+    single = world == 1 and level <= 13
+    if single:
         scene = api.Scene.Create(mesh, device=local_rank, stream=stream, lib=lib)
         vox = api.Voxelizer.Create(scene, level, mode, stream=stream)
         builder = api.OctreeBuilder.Create(vox, stream=stream)
@@ -201,7 +203,8 @@ def run_ours(args):
             vox.CmdVoxelize(stream)
             builder.CmdBuild(stream)
     else:
-        sh = sharded.ShardedSVO(torch, dist, mesh, level, mode, local_rank, lib=lib, use_ipc=not args.no_ipc)
+        sh = sharded.ShardedSVO(torch if world > 1 else None, dist if world > 1 else None, mesh, level, mode, local_rank,
+                                lib=lib, use_ipc=not args.no_ipc)
 
         def step():
             sh.step(stream)
@@ -218,7 +221,7 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         step()
-        if world == 1:  # per-phase cudaEvent times recorded by the library on the same stream
+        if single:  # per-phase cudaEvent times recorded by the library on the same stream
             ms, sort_passes = builder.LastMs()
             for k in api.PHASES:
                 phases_acc[k] += ms[k]
@@ -232,12 +235,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
 
-    if world == 1:
+    if single:
         leaves, frags = builder.GetLeafCount(), vox.GetVoxelFragmentCount()
         octree_bytes = builder.GetOctreeRange()
     else:
         c = torch.tensor([sh.leaf_count_local(), sh.fragment_count_local()], dtype=torch.int64, device=dev)
-        dist.all_reduce(c)
+        if world > 1:
+            dist.all_reduce(c)
         leaves, frags = int(c[0].item()), int(c[1].item())
         octree_bytes = sh.total_words * 4
     value = leaves / (ms_per_step * 1e-3)
@@ -250,7 +254,7 @@ def run_ours(args):
 
     def e2e_step():
         pm = mesh.__class__(pos_pin.numpy(), idx_pin.numpy().view(np.uint32), mesh.draws, mesh.name)
-        if world == 1:
+        if single:
             s = api.Scene.Create(pm, device=local_rank, stream=stream, lib=lib)
             v = api.Voxelizer.Create(s, level, mode, stream=stream)
             b = api.OctreeBuilder.Create(v, stream=stream)
@@ -261,7 +265,8 @@ def run_ours(args):
             counts = b.GetLevelCounts()
             b.Destroy(), v.Destroy(), s.Destroy()
             return rng, root, counts
-        s2 = sharded.ShardedSVO(torch, dist, pm, level, mode, local_rank, lib=lib, use_ipc=not args.no_ipc)
+        s2 = sharded.ShardedSVO(torch if world > 1 else None, dist if world > 1 else None, pm, level, mode, local_rank, lib=lib,
+                                use_ipc=not args.no_ipc)
         rng = s2.step(stream)
         root = lib.to_host(s2.final, np.uint32, 8, local_rank) if rank == 0 else None
         s2.destroy()
@@ -284,7 +289,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = hbm_peak()
         roofline = None
-        if world == 1 and sort_passes:
+        if single and sort_passes:
             per_launch_ms = phases_acc["sort_passes"] / args.steps / sort_passes
             alg_bytes = 16.0 * frags  # one read + one write of every 8-byte fragment per onesweep pass
             achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
@@ -301,7 +306,7 @@ def run_ours(args):
                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
                         "launches_per_step": sort_passes}
         cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
+        if single and not args.no_cpu_baseline:
             times, cl, cores, sample = cpu_reference_run(mesh, level, mode_name, 3, 0, budget_s=25.0)
             cpu_baseline = {"value": cl / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         line = {
@@ -312,10 +317,11 @@ def run_ours(args):
                        "triangles": mesh.n_triangles, "fragments": frags, "leaf_voxels": leaves,
                        "octree_bytes": octree_bytes, "raster_mode": mode_name,
                        "l2": "no flush needed: every step streams the fragment list (8 B x fragments, > 126 MB L2)",
-                       "parallelism": "single GPU" if world == 1 else f"octant-sharded x{world}, NVLink subtree gather"
-                                      f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})"},
+                       "parallelism": "single GPU" if single else ("single GPU, 8 octant builds stitched (virtual shards)" if world == 1 else
+                                      f"octant-sharded x{world}, NVLink subtree gather")
+                                      + (f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})" if world > 1 else "")},
             "build_ms": ms_per_step,
-            "phases_ms": {k: v / args.steps for k, v in phases_acc.items()} if world == 1 else None,
+            "phases_ms": {k: v / args.steps for k, v in phases_acc.items()} if single else None,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": leaves / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -324,8 +330,9 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if not single:
         sh.destroy()
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 

@@ -250,8 +250,10 @@ def living_room_like(seed: int = 4, n_boxes: int = 40, n_small: int = 200000, le
 # ---------------------------------------------------------------------------------------------
 # C5: dense surface for level 14 (octant-sharded)
 # ---------------------------------------------------------------------------------------------
-def dense_surface(seed: int = 5, n: int = 4096, layers: int = 3) -> Mesh:
-    """Stacked wavy sheets: a dense surface whose leaf count scales with layers * res^2."""
+def dense_surface(seed: int = 5, n: int = 2048, layers: int = 1) -> Mesh:
+    """Stacked wavy sheets: a dense surface whose leaf count scales with layers * res^2.  One sheet at level
+    14 gives ~2.8e8 leaves and ~7.5e8 node words, which still fits the reference's 30-bit child pointers
+    (octree.glsl:110) when the octant subtrees are gathered into one buffer."""
     rng = SplitMix64(seed)
     g = np.linspace(-0.999, 0.999, n)
     x, z = np.meshgrid(g, g, indexing="ij")
@@ -280,5 +282,5 @@ CONFIGS = {
     "C2": dict(gen=sponza_like, level=10, mode="center"),
     "C3": dict(gen=san_miguel_like, level=11, mode="conservative"),
     "C4": dict(gen=living_room_like, level=12, mode="conservative"),
-    "C5": dict(gen=dense_surface, level=14, mode="center"),
+    "C5": dict(gen=dense_surface, level=14, mode="center"),  # 3*14 Morton bits + 24 colour bits > 64: octant shards
 }

@@ -166,3 +166,26 @@ def test_two_rank_nccl_stitch(lib):
                "--master-port", "29611", os.path.join(root, "tests", "multi_gpu_check.py")] + extra
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "STITCH_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_level14_virtual_shards_against_oracle(lib):
+    # 16384^3: 42 Morton bits + 24 colour bits exceed a 64-bit fragment, so the grid is built as 8 cube-local
+    # level-13 octants stitched under one root; checked against the oracle's whole-grid level-14 tree
+    from oracle import oracle
+    from sparsevoxeloctree_b200 import sharded
+    from tests.parity import assert_same_tree
+    mesh = scenes.random_soup(300, 77, 0.0005, 0.01)
+    level, mode = 14, api.CONSERVATIVE_EXACT
+    sh = sharded.ShardedSVO(None, None, mesh, level, mode, 0, lib=lib)
+    sh.step()
+    stitched = sh.octree_to_host()
+    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, oracle.CONSERVATIVE_EXACT)
+    assert len(fr) == sh.fragment_count_local()
+    ow, orng = oracle.build_octree(fr, level, cap_words=8 * (1 + len(fr) * (level - 1)))
+    d1, m1, w1 = oracle.canonicalise(stitched, level)
+    d2, m2, w2 = oracle.canonicalise(ow, level)
+    assert (d1 == d2).all() and (m1 == m2).all()          # occupancy and topology bit-exact
+    assert ((w1 >> 24) == (w2 >> 24)).all()               # flags and fragment counts exact
+    sh.destroy()
+    with pytest.raises(api.SvoError):                      # a single 64-bit fragment cannot hold level 14
+        api.Voxelizer.Create(api.Scene.Create(mesh, lib=lib), 14)
