@@ -45,7 +45,9 @@ typedef enum svo_status {
  * BASELINE.json's "non-conservative raster". */
 typedef enum svo_raster_mode {
 	SVO_CENTER = 0,            /* centre sample + top-left rule on the undilated triangle */
-	SVO_CONSERVATIVE_EXACT = 1 /* every pixel square touching the triangle (exact 2-D SAT) = reference Mode A */
+	SVO_CONSERVATIVE_EXACT = 1, /* every pixel square touching the triangle (exact 2-D SAT) = reference Mode A */
+	SVO_CONSERVATIVE_DILATE = 2 /* reference Mode B (no VK_EXT_conservative_rasterization): the triangle dilated by
+	                               shader/voxelizer_conservative.geom:46-87, then centre sampled, depth clipped */
 } svo_raster_mode;
 
 /* One draw per material: Scene::DrawCmd (src/Scene.hpp:28-34; filled at src/Scene.cpp:157-170,

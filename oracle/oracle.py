@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libsvo_oracle.so")
 
-CENTER, CONSERVATIVE_EXACT = 0, 1
+CENTER, CONSERVATIVE_EXACT, CONSERVATIVE_DILATE = 0, 1, 2
 
 DRAW_DTYPE = np.dtype([("first_index", "<u4"), ("index_count", "<u4"), ("texture_id", "<u4"), ("albedo_rgba8", "<u4")])
 FRAG_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("z", "<u4"), ("rgb", "<u4")])
@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
         L.orc_debug_raster_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_int64]
         L.orc_debug_raster_pixels.restype = C.c_int64
+        L.orc_debug_dilate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_debug_dilate.restype = None
         L.orc_morton.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_morton.restype = C.c_uint64
         _lib = L
@@ -148,6 +150,14 @@ def debug_tri_setup(p0, p1, p2, level):
     xy = np.zeros(6, np.int32)
     lib().orc_debug_tri_setup(_ptr(p[0]), _ptr(p[1]), _ptr(p[2]), level, _ptr(a), _ptr(xy))
     return a, xy.reshape(3, 2)
+
+
+def debug_dilate(p0, p1, p2, level):
+    """The three vertices voxelizer_conservative.geom emits (ndc x, ndc y, depth), float32 [3,3]."""
+    p = [np.ascontiguousarray(v, dtype=np.float32) for v in (p0, p1, p2)]
+    out = np.zeros(9, np.float32)
+    lib().orc_debug_dilate(_ptr(p[0]), _ptr(p[1]), _ptr(p[2]), level, _ptr(out))
+    return out.reshape(3, 3)
 
 
 def debug_raster_pixels(p0, p1, p2, level, mode):

@@ -1,5 +1,5 @@
 """A small SPIR-V interpreter, just large enough to EXECUTE the reference's own checked-in shader binaries for
-the SVO construction path (shader/include/spirv/{voxelizer.vert,voxelizer.geom,voxelizer.frag,
+the SVO construction path (shader/include/spirv/{voxelizer.geom,voxelizer_conservative.geom,voxelizer.frag,
 octree_init_node.comp,octree_tag_node.comp,octree_alloc_node.comp,octree_modify_arg.comp}.u32).
 
 TEST INFRASTRUCTURE ONLY.  It exists so that the CPU oracle (oracle/svo_oracle.c) can be pinned against outputs
@@ -10,8 +10,8 @@ commits the resulting vectors; the tests then only need the committed vectors.
 
 Semantics implemented: 32-bit int/uint/float scalars and vectors, structs / arrays / runtime arrays with
 explicit Offset / ArrayStride layout for buffer blocks, the structured control flow that glslang emits
-(Branch, BranchConditional, Switch, Phi), atomics, GLSL.std.450 {FAbs, FMin, FMax, UMin, UMax, UClamp, Cross,
-PackUnorm4x8}, geometry-shader EmitVertex, fragment Kill, and subgroup ops with subgroup size 1 (a legal
+(Branch, BranchConditional, Switch, Phi), atomics, MatrixTimesVector, GLSL.std.450 {FAbs, FMin, FMax, UMin, UMax,
+UClamp, Fma (one rounding), Cross, PackUnorm4x8}, geometry-shader EmitVertex, fragment Kill, and subgroup ops with subgroup size 1 (a legal
 implementation choice: every invocation is its own subgroup).  Floats are numpy.float32, one rounding per
 operation (no contraction) -- the same choice as the pinned arithmetic of DESIGN.md section 3.
 """
@@ -238,6 +238,7 @@ class Module:
         if inst == 38: return min(v[0], v[1])
         if inst == 41: return max(v[0], v[1])
         if inst == 44: return min(max(v[0], v[1]), v[2])          # UClamp
+        if inst == 50: return F32(np.float64(v[0]) * np.float64(v[1]) + np.float64(v[2]))  # Fma: one rounding
         raise NotImplementedError(f"GLSL.std.450 {inst}")
 
     # ---- execution ---------------------------------------------------------------------------------------
@@ -341,6 +342,14 @@ class Module:
                 val[a[1]] = comp
             elif op == 77: val[a[1]] = val[a[2]][val[a[3]]]
             elif op == 142: val[a[1]] = [F32(c * val[a[3]]) for c in val[a[2]]]
+            elif op == 145:  # MatrixTimesVector: sum_j column_j * v[j], one rounding per operation
+                cols, vec = val[a[2]], val[a[3]]
+                out = []
+                for r in range(len(cols[0])):
+                    acc = F32(cols[0][r] * vec[0])
+                    for j in range(1, len(cols)): acc = F32(acc + F32(cols[j][r] * vec[j]))
+                    out.append(acc)
+                val[a[1]] = out
             elif op == 148:
                 acc = F32(0)
                 for x, y in zip(val[a[2]], val[a[3]]): acc = F32(acc + F32(x * y))

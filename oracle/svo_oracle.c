@@ -85,11 +85,48 @@ typedef struct {
 	uint32_t zr[2];     /* gDepthRange (voxelizer.geom:41-42) */
 	int64_t area2;      /* > 0 after orientation normalisation; 0 = degenerate */
 	int valid;
+	int dilated;        /* Mode B: vertices come from voxelizer_conservative.geom; depth clip applies */
 } orc_tri;
+
+/* voxelizer_conservative.geom:46-87 -- the software-conservative dilation used when
+ * VK_EXT_conservative_rasterization is absent (Voxelizer.cpp:92-99).  q[i] = projected vertex
+ * (ndc x, ndc y, depth); normal_axis = normal[axis].  One fp32 rounding per operator, with the three
+ * fused multiply-adds exactly where the reference's compiled SPIR-V has them (GetBarycentric's
+ * numerators and denominator; checked against the executed binary, tests/test_spirv_golden.py).
+ * The dilated vertices (emit order) replace q. */
+static void dilate_mode_b(float q[3][3], float normal_axis, uint32_t res) {
+	float line[3][3];
+	const int LA[3] = {2, 0, 1}, LB[3] = {1, 2, 0}; /* line0 = cross(ndc2, ndc1), line1 = cross(ndc0, ndc2), line2 = cross(ndc1, ndc0) */
+	const float inv = 1.0f / (float)res;
+	for (int i = 0; i < 3; ++i) {
+		const float ax = q[LA[i]][0], ay = q[LA[i]][1], bx = q[LB[i]][0], by = q[LB[i]][1];
+		line[i][0] = ay * 1.0f - 1.0f * by;
+		line[i][1] = 1.0f * bx - ax * 1.0f;
+		line[i][2] = ax * by - ay * bx;
+		const float d = inv * fabsf(line[i][0]) + inv * fabsf(line[i][1]);
+		if (normal_axis < 0.0f) line[i][2] = line[i][2] + d; else line[i][2] = line[i][2] - d;
+	}
+	/* intersect0 = cross(line2, line1), intersect1 = cross(line0, line2), intersect2 = cross(line1, line0) */
+	const int IA[3] = {2, 0, 1}, IB[3] = {1, 2, 0};
+	float out[3][3];
+	const float ax = q[0][0], ay = q[0][1], bx = q[1][0], by = q[1][1], cx = q[2][0], cy = q[2][1];
+	const float den = fmaf(by - cy, ax - cx, (cx - bx) * (ay - cy));
+	for (int i = 0; i < 3; ++i) {
+		const float *u = line[IA[i]], *v = line[IB[i]];
+		const float ix = u[1] * v[2] - u[2] * v[1], iy = u[2] * v[0] - u[0] * v[2], iz = u[0] * v[1] - u[1] * v[0];
+		const float px = ix / iz, py = iy / iz;
+		const float l0 = fmaf(by - cy, px - cx, (cx - bx) * (py - cy)) / den;
+		const float l1 = fmaf(cy - ay, px - cx, (ax - cx) * (py - cy)) / den;
+		const float l2 = (1.0f - l0) - l1;
+		out[i][0] = px, out[i][1] = py;
+		out[i][2] = (l0 * q[0][2] + l1 * q[1][2]) + l2 * q[2][2];
+	}
+	memcpy(q, out, sizeof(out));
+}
 
 /* voxelizer.vert:8-11 (pass-through) + voxelizer.geom:15-42 + viewport transform
  * (Voxelizer.cpp:115-116: viewport (0,0,res,res), depth 0..1, no y flip). */
-static void orc_tri_setup(const float *p0, const float *p1, const float *p2, uint32_t res, orc_tri *t) {
+static void orc_tri_setup(const float *p0, const float *p1, const float *p2, uint32_t res, int mode, orc_tri *t) {
 	const float *p[3] = {p0, p1, p2};
 	float e1[3], e2[3], n[3], w[3];
 	for (int k = 0; k < 3; ++k) {
@@ -130,8 +167,20 @@ static void orc_tri_setup(const float *p0, const float *p1, const float *p2, uin
 	t->aabb[3] = f2u((fmax3(q[0][1], q[1][1], q[2][1]) + 1.0f) * 0.5f * fres);
 	t->zr[0] = f2u(fmin3(q[0][2], q[1][2], q[2][2]) * fres);
 	t->zr[1] = f2u(fmax3(q[0][2], q[1][2], q[2][2]) * fres);
+	t->dilated = 0;
 	if (!t->valid)
 		return;
+	if (mode == ORC_CONSERVATIVE_DILATE) { /* gAABB / gDepthRange above stay those of the ORIGINAL triangle (conservative.geom:69-74) */
+		dilate_mode_b(q, n[t->axis], res);
+		t->dilated = 1;
+		for (int i = 0; i < 3; ++i) {
+			t->zf[i] = q[i][2];
+			if (!(fabsf(q[i][0]) <= 4.0f) || !(fabsf(q[i][1]) <= 4.0f) || !(fabsf(q[i][2]) <= 1e6f)) /* NaN / Inf / far outside: */
+				t->valid = 0;                                                                    /* degenerate input, dropped */
+		}
+		if (!t->valid)
+			return;
+	}
 	/* viewport transform x_f = (x+1)*res/2 (identical to the AABB expression) and snapping
 	 * to 8 sub-pixel bits, round-half-even (pinned). */
 	for (int i = 0; i < 3; ++i) {
@@ -166,7 +215,7 @@ static int64_t iabs64(int64_t v) { return v < 0 ? -v : v; }
 static int covered(const orc_tri *t, int mode, int32_t px, int32_t py) {
 	static const int EA[3] = {1, 2, 0}, EB[3] = {2, 0, 1};
 	const int64_t cx = (int64_t)px * 256 + 128, cy = (int64_t)py * 256 + 128;
-	if (mode == ORC_CENTER) {
+	if (mode != ORC_CONSERVATIVE_EXACT) { /* centre sample + top-left rule: plain (Mode C) or on the dilated triangle (Mode B) */
 		if (t->area2 == 0)
 			return 0;
 		for (int i = 0; i < 3; ++i) {
@@ -240,6 +289,8 @@ static void plane_setup(const orc_tri *t, orc_plane *pl) {
 static int frag_voxel(const orc_tri *t, const orc_plane *pl, uint32_t res, int32_t px, int32_t py, uint32_t v[3]) {
 	int32_t cx = px * 256 + 128, cy = py * 256 + 128;
 	double z = fma(pl->dzdx, (double)(cx - pl->X0), fma(pl->dzdy, (double)(cy - pl->Y0), pl->z0));
+	if (t->dilated && !(z >= 0.0 && z <= 1.0))
+		return 0; /* depth clip (depthClampEnable = 0, dep/MyVK/src/GraphicsPipeline.cpp:45-50): the dilated vertices' extrapolated depth can leave [0,1] */
 	double zs = z * (double)res; /* v.z *= float(kVoxelResolution) */
 	uint32_t uz = !(zs > 0.0) ? 0u : (zs >= (double)res ? res - 1u : (uint32_t)zs); /* clamp(uvec3(v),0,res-1) */
 	uint32_t ux = (uint32_t)px, uy = (uint32_t)py;
@@ -268,7 +319,7 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
                      const orc_draw *draws, uint32_t n_draws, uint32_t level, int mode,
                      const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out, int64_t cap,
                      int nthreads) {
-	if (level < 1 || level > 16 || (mode != ORC_CENTER && mode != ORC_CONSERVATIVE_EXACT))
+	if (level < 1 || level > 16 || (mode != ORC_CENTER && mode != ORC_CONSERVATIVE_EXACT && mode != ORC_CONSERVATIVE_DILATE))
 		return -1;
 	for (uint32_t d = 0; d < n_draws; ++d)
 		if (draws[d].texture_id != 0xffffffffu)
@@ -288,10 +339,10 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
 			orc_tri t;
 			orc_tri_setup((const float *)(pbase + (size_t)ix[0] * pos_stride_bytes),
 			              (const float *)(pbase + (size_t)ix[1] * pos_stride_bytes),
-			              (const float *)(pbase + (size_t)ix[2] * pos_stride_bytes), res, &t);
+			              (const float *)(pbase + (size_t)ix[2] * pos_stride_bytes), res, mode, &t);
 			if (!t.valid)
 				continue;
-			if (t.area2 == 0 && mode == ORC_CENTER)
+			if (t.area2 == 0 && mode != ORC_CONSERVATIVE_EXACT)
 				continue;
 			orc_plane pl;
 			plane_setup(&t, &pl);
@@ -342,7 +393,7 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
 void orc_debug_tri_setup(const float *p0, const float *p1, const float *p2, uint32_t level, uint32_t out_axis_aabb_zr[7],
                          int32_t out_xy_snapped[6]) {
 	orc_tri t;
-	orc_tri_setup(p0, p1, p2, 1u << level, &t);
+	orc_tri_setup(p0, p1, p2, 1u << level, ORC_CONSERVATIVE_EXACT, &t);
 	out_axis_aabb_zr[0] = t.axis;
 	for (int i = 0; i < 4; ++i) out_axis_aabb_zr[1 + i] = t.aabb[i];
 	out_axis_aabb_zr[5] = t.zr[0], out_axis_aabb_zr[6] = t.zr[1];
@@ -352,8 +403,8 @@ int64_t orc_debug_raster_pixels(const float *p0, const float *p1, const float *p
                                 int32_t *out_py, double *out_z, int64_t cap) {
 	const uint32_t res = 1u << level;
 	orc_tri t;
-	orc_tri_setup(p0, p1, p2, res, &t);
-	if (!t.valid || (t.area2 == 0 && mode == ORC_CENTER)) return 0;
+	orc_tri_setup(p0, p1, p2, res, mode, &t);
+	if (!t.valid || (t.area2 == 0 && mode != ORC_CONSERVATIVE_EXACT)) return 0;
 	orc_plane pl;
 	plane_setup(&t, &pl);
 	int32_t xmin = t.X[0], xmax = t.X[0], ymin = t.Y[0], ymax = t.Y[0];
@@ -529,4 +580,25 @@ int64_t orc_canonicalise(const uint32_t *words, uint64_t n_words, uint32_t level
 		}
 	}
 	return n;
+}
+
+/* Debug view for the SPIR-V cross-check of Mode B: the three vertices voxelizer_conservative.geom emits
+ * (ndc x, ndc y, depth), in emit order, as fp32. */
+void orc_debug_dilate(const float *p0, const float *p1, const float *p2, uint32_t level, float out[9]) {
+	const float *p[3] = {p0, p1, p2};
+	float e1[3], e2[3], n[3], w[3], q[3][3];
+	for (int k = 0; k < 3; ++k) e1[k] = p1[k] - p0[k], e2[k] = p2[k] - p0[k];
+	n[0] = e1[1] * e2[2] - e1[2] * e2[1];
+	n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+	n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+	for (int k = 0; k < 3; ++k) w[k] = fabsf(n[k]);
+	const uint32_t axis = (w[0] > w[1] && w[0] > w[2]) ? 0u : ((w[1] > w[2]) ? 1u : 2u);
+	for (int i = 0; i < 3; ++i) {
+		if (axis == 0u) q[i][0] = p[i][1], q[i][1] = p[i][2], q[i][2] = p[i][0];
+		else if (axis == 1u) q[i][0] = p[i][2], q[i][1] = p[i][0], q[i][2] = p[i][1];
+		else q[i][0] = p[i][0], q[i][1] = p[i][1], q[i][2] = p[i][2];
+		q[i][2] = (q[i][2] + 1.0f) * 0.5f;
+	}
+	dilate_mode_b(q, n[axis], 1u << level);
+	memcpy(out, q, sizeof(q));
 }

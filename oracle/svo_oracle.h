@@ -68,6 +68,8 @@ void orc_debug_tri_setup(const float *p0, const float *p1, const float *p2, uint
 int64_t orc_debug_raster_pixels(const float *p0, const float *p1, const float *p2, uint32_t level, int mode, int32_t *out_px,
                                 int32_t *out_py, double *out_z, int64_t cap);
 
+void orc_debug_dilate(const float *p0, const float *p1, const float *p2, uint32_t level, float out[9]);
+
 /*
  * The OctreeBuilder level loop (OctreeBuilder.cpp:142-210 driving octree_init_node /
  * octree_tag_node / octree_alloc_node / octree_modify_arg).  Fragments are tagged in

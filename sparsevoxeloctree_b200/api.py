@@ -23,7 +23,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
 
-CENTER, CONSERVATIVE_EXACT = 0, 1
+CENTER, CONSERVATIVE_EXACT, CONSERVATIVE_DILATE = 0, 1, 2
 PHASES = ("raster", "sort_hist", "sort_passes", "reduce", "levels", "emit")
 
 

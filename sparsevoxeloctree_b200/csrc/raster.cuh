@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 			for (int32_t py = ts.py0; py <= ts.py1; ++py)
 				for (int32_t px = ts.px0; px <= ts.px1; ++px)
 					if (pixel_covered(ts, px, py)) {
-						if (!ts.cull_depth || depth_in_window(ts, pixel_depth(ts, rp.res, px, py))) ++cnt;
+						uint32_t uz;
+						if ((!ts.cull_depth && !ts.clip_z) || pixel_fragment(ts, rp.res, px, py, uz)) ++cnt;
 					}
 		} else
 			pk = (1ull << 40) | (uint64_t)(ts.py1 - ts.py0 + 1);
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	for (int32_t py = ts.py0; py <= ts.py1; ++py)
 		for (int32_t px = ts.px0; px <= ts.px1; ++px)
 			if (pixel_covered(ts, px, py)) {
-				const uint32_t uz = pixel_depth(ts, rp.res, px, py);
-				if (depth_in_window(ts, uz)) frags[o++] = make_fragment(ts, rp, px, py, uz, rgb);
+				uint32_t uz;
+				if (pixel_fragment(ts, rp.res, px, py, uz)) frags[o++] = make_fragment(ts, rp, px, py, uz, rgb);
 			}
 }
 

@@ -258,7 +258,8 @@ uint64_t svo_scene_triangle_count(const svo_scene *sc) { return sc ? sc->view.n_
 int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, void *stream, svo_voxelizer **out) {
 	if (!scene || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_create: null argument");
 	*out = nullptr;
-	if (mode != SVO_CENTER && mode != SVO_CONSERVATIVE_EXACT) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown raster mode");
+	if (mode != SVO_CENTER && mode != SVO_CONSERVATIVE_EXACT && mode != SVO_CONSERVATIVE_DILATE)
+		return fail(SVO_ERR_INVALID_ARGUMENT, "unknown raster mode");
 	uint32_t sl = shard ? shard->shard_level : 0;
 	if (level < 1 || level > 14 || sl >= level) return fail(SVO_ERR_INVALID_ARGUMENT, "level must be 1..14 and shard_level < level");
 	const uint32_t key_level = level - sl;
@@ -276,7 +277,7 @@ int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_s
 	v->level = level;
 	v->key_level = key_level;
 	v->rp.res = 1u << level;
-	v->rp.mode = mode == SVO_CENTER ? MODE_CENTER : MODE_CONSERVATIVE;
+	v->rp.mode = mode == SVO_CENTER ? MODE_CENTER : (mode == SVO_CONSERVATIVE_EXACT ? MODE_CONSERVATIVE : MODE_DILATE);
 	const uint32_t side = 1u << key_level;
 	for (int k = 0; k < 3; ++k) {
 		const uint32_t ci = shard ? shard->cube_index[k] : 0;

@@ -19,6 +19,8 @@ SVO_HD inline double dmul(double a, double b) { return __dmul_rn(a, b); }
 SVO_HD inline double dsub(double a, double b) { return __dsub_rn(a, b); }
 SVO_HD inline double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 SVO_HD inline double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+SVO_HD inline float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SVO_HD inline float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 #else
 SVO_HD inline float fmul(float a, float b) { return a * b; }
 SVO_HD inline float fadd(float a, float b) { return a + b; }
@@ -27,6 +29,8 @@ SVO_HD inline double dmul(double a, double b) { return a * b; }
 SVO_HD inline double dsub(double a, double b) { return a - b; }
 SVO_HD inline double ddiv(double a, double b) { return a / b; }
 SVO_HD inline double dfma(double a, double b, double c) { return fma(a, b, c); }
+SVO_HD inline float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+SVO_HD inline float fdiv(float a, float b) { return a / b; }
 #endif
 
 // GLSL uint(float): truncation; negative / NaN pinned to 0, too large saturates.
@@ -103,9 +107,47 @@ struct TriSetup {
 	// shard window along the depth axis (fragments outside are dropped); cull_depth = window is a strict subset
 	uint32_t zs_lo, zs_hi;
 	bool cull_depth;
+	// Mode B only: the dilated vertices' extrapolated depth can leave [0,1]; such fragments are depth-clipped
+	bool clip_z;
 };
 
-enum { MODE_CENTER = 0, MODE_CONSERVATIVE = 1 };
+enum { MODE_CENTER = 0, MODE_CONSERVATIVE = 1, MODE_DILATE = 2 };
+
+// voxelizer_conservative.geom:46-87 -- the software-conservative dilation the reference falls back to without
+// VK_EXT_conservative_rasterization (Voxelizer.cpp:92-99).  One fp32 rounding per operator, with fused
+// multiply-adds exactly where the reference's compiled SPIR-V has them (GetBarycentric's numerators and
+// denominator); bit-identical to the executed binary (tests/test_spirv_golden.py).  q = projected vertices
+// (ndc x, ndc y, depth); replaced by the three emitted vertices.
+SVO_HD inline void dilate_mode_b(float (&qx)[3], float (&qy)[3], float (&qz)[3], float normal_axis, uint32_t res) {
+	const int LA[3] = {2, 0, 1}, LB[3] = {1, 2, 0}; // line0 = cross(ndc2, ndc1), line1 = cross(ndc0, ndc2), line2 = cross(ndc1, ndc0)
+	const float inv = fdiv(1.0f, (float)res);
+	float lx[3], ly[3], lz[3];
+	for (int i = 0; i < 3; ++i) {
+		const float ax = qx[LA[i]], ay = qy[LA[i]], bx = qx[LB[i]], by = qy[LB[i]];
+		lx[i] = fsub(ay, by);
+		ly[i] = fsub(bx, ax);
+		lz[i] = fsub(fmul(ax, by), fmul(ay, bx));
+		const float d = fadd(fmul(inv, fabsf(lx[i])), fmul(inv, fabsf(ly[i])));
+		lz[i] = normal_axis < 0.0f ? fadd(lz[i], d) : fsub(lz[i], d);
+	}
+	const int IA[3] = {2, 0, 1}, IB[3] = {1, 2, 0}; // intersect0 = cross(line2, line1), 1 = cross(line0, line2), 2 = cross(line1, line0)
+	const float ax = qx[0], ay = qy[0], bx = qx[1], by = qy[1], cx = qx[2], cy = qy[2];
+	const float den = ffma(fsub(by, cy), fsub(ax, cx), fmul(fsub(cx, bx), fsub(ay, cy)));
+	float ox[3], oy[3], oz[3];
+	for (int i = 0; i < 3; ++i) {
+		const int u = IA[i], v = IB[i];
+		const float ix = fsub(fmul(ly[u], lz[v]), fmul(lz[u], ly[v]));
+		const float iy = fsub(fmul(lz[u], lx[v]), fmul(lx[u], lz[v]));
+		const float iz = fsub(fmul(lx[u], ly[v]), fmul(ly[u], lx[v]));
+		const float px = fdiv(ix, iz), py = fdiv(iy, iz);
+		const float l0 = fdiv(ffma(fsub(by, cy), fsub(px, cx), fmul(fsub(cx, bx), fsub(py, cy))), den);
+		const float l1 = fdiv(ffma(fsub(cy, ay), fsub(px, cx), fmul(fsub(ax, cx), fsub(py, cy))), den);
+		const float l2 = fsub(fsub(1.0f, l0), l1);
+		ox[i] = px, oy[i] = py;
+		oz[i] = fadd(fadd(fmul(l0, qz[0]), fmul(l1, qz[1])), fmul(l2, qz[2]));
+	}
+	for (int i = 0; i < 3; ++i) qx[i] = ox[i], qy[i] = oy[i], qz[i] = oz[i];
+}
 
 // Shard window in voxel coordinates (half-open), used to clip the pixel rectangle early and to cull
 // fragments by depth; whole grid: lo = 0, hi = res.
@@ -127,9 +169,10 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 		e2[k] = fsub(p2[k], p0[k]);
 	}
 	// voxelizer.geom:28-32
-	float nx = fabsf(fsub(fmul(e1[1], e2[2]), fmul(e1[2], e2[1])));
-	float ny = fabsf(fsub(fmul(e1[2], e2[0]), fmul(e1[0], e2[2])));
-	float nz = fabsf(fsub(fmul(e1[0], e2[1]), fmul(e1[1], e2[0])));
+	const float nsx = fsub(fmul(e1[1], e2[2]), fmul(e1[2], e2[1]));
+	const float nsy = fsub(fmul(e1[2], e2[0]), fmul(e1[0], e2[2]));
+	const float nsz = fsub(fmul(e1[0], e2[1]), fmul(e1[1], e2[0]));
+	const float nx = fabsf(nsx), ny = fabsf(nsy), nz = fabsf(nsz);
 	uint32_t axis = (nx > ny && nx > nz) ? 0u : ((ny > nz) ? 1u : 2u);
 	t.axis = axis;
 	if (!valid) return false;
@@ -153,6 +196,15 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 	t.zr_lo = f2u_sat(fmul(glsl_min(qz[0], glsl_min(qz[1], qz[2])), fres));
 	t.zr_hi = f2u_sat(fmul(glsl_max(qz[0], glsl_max(qz[1], qz[2])), fres));
 
+	// Mode B: rasterize the dilated triangle instead (gAABB / gDepthRange stay those of the original one)
+	const bool centre_rule = mode != MODE_CONSERVATIVE;
+	t.clip_z = mode == MODE_DILATE;
+	if (mode == MODE_DILATE) {
+		dilate_mode_b(qx, qy, qz, axis == 0u ? nsx : (axis == 1u ? nsy : nsz), res);
+		for (int i = 0; i < 3; ++i) // NaN / Inf / far outside: degenerate input, dropped
+			if (!(fabsf(qx[i]) <= 4.0f) || !(fabsf(qy[i]) <= 4.0f) || !(fabsf(qz[i]) <= 1e6f)) return false;
+	}
+
 	// window coordinates, snapped to 1/256 pixel (round half even)
 	int32_t X[3], Y[3];
 	float zf[3];
@@ -172,7 +224,7 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 		tf = zf[1], zf[1] = zf[2], zf[2] = tf;
 		a2 = -a2;
 	}
-	if (a2 == 0 && mode == MODE_CENTER) return false;
+	if (a2 == 0 && centre_rule) return false;
 
 	const int32_t xmin = tmin(X[0], tmin(X[1], X[2])), xmax = tmax(X[0], tmax(X[1], X[2]));
 	const int32_t ymin = tmin(Y[0], tmin(Y[1], Y[2])), ymax = tmax(Y[0], tmax(Y[1], Y[2]));
@@ -184,7 +236,7 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 			int64_t A = -(int64_t)(Y[EB[i]] - Y[EA[i]]), B = (int64_t)(X[EB[i]] - X[EA[i]]);
 			int64_t Cc = -(A * (int64_t)X[EA[i]] + B * (int64_t)Y[EA[i]]);
 			int64_t slack;
-			if (mode == MODE_CENTER) {
+			if (centre_rule) {
 				bool top_left = (A > 0) || (A == 0 && B > 0);
 				slack = top_left ? 0 : -1; // E > 0  <=>  E - 1 >= 0
 			} else
@@ -214,7 +266,7 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 
 	// candidate pixel rectangle
 	int64_t px0, px1, py0, py1;
-	if (mode == MODE_CENTER) { // centres inside the closed snapped bounding box
+	if (centre_rule) { // centres inside the closed snapped bounding box
 		px0 = ceil_div((int64_t)xmin - 128, 256), px1 = floor_div((int64_t)xmax - 128, 256);
 		py0 = ceil_div((int64_t)ymin - 128, 256), py1 = floor_div((int64_t)ymax - 128, 256);
 	} else { // closed squares [256p, 256p+256] touching the closed bounding box
@@ -292,9 +344,11 @@ SVO_HD inline double depth_row_term(const TriSetup &t, int32_t py) {
 	const int32_t cy = py * 256 + 128;
 	return dfma(t.dzdy, (double)(cy - t.Y0), t.z0);
 }
-SVO_HD inline uint32_t pixel_depth_row(const TriSetup &t, uint32_t res, int32_t px, double row_term) {
+SVO_HD inline double plane_z_row(const TriSetup &t, int32_t px, double row_term) {
 	const int32_t cx = px * 256 + 128;
-	double z = dfma(t.dzdx, (double)(cx - t.X0), row_term);
+	return dfma(t.dzdx, (double)(cx - t.X0), row_term);
+}
+SVO_HD inline uint32_t depth_voxel(const TriSetup &t, uint32_t res, double z) {
 	double zs = dmul(z, (double)res);
 	uint32_t uz = !(zs > 0.0) ? 0u : (zs >= (double)res ? res - 1u : (uint32_t)zs);
 	uz = tmax(uz, t.zr_lo);
@@ -302,27 +356,44 @@ SVO_HD inline uint32_t pixel_depth_row(const TriSetup &t, uint32_t res, int32_t 
 	uz = tmin(uz, res - 1u);
 	return uz;
 }
+SVO_HD inline uint32_t pixel_depth_row(const TriSetup &t, uint32_t res, int32_t px, double row_term) {
+	return depth_voxel(t, res, plane_z_row(t, px, row_term));
+}
 SVO_HD inline uint32_t pixel_depth(const TriSetup &t, uint32_t res, int32_t px, int32_t py) {
 	return pixel_depth_row(t, res, px, depth_row_term(t, py));
 }
+// Does the covered pixel (px,py) produce a fragment, and at which depth voxel?  Drops fragments that are depth
+// clipped (Mode B only: depthClampEnable = 0, dep/MyVK/src/GraphicsPipeline.cpp:45-50) or fall outside the
+// shard's depth window.
+SVO_HD inline bool pixel_fragment(const TriSetup &t, uint32_t res, int32_t px, int32_t py, uint32_t &uz) {
+	const double z = plane_z_row(t, px, depth_row_term(t, py));
+	if (t.clip_z && !(z >= 0.0 && z <= 1.0)) return false;
+	uz = depth_voxel(t, res, z);
+	return !t.cull_depth || (uz >= t.zs_lo && uz < t.zs_hi);
+}
 
-// Narrow a row span to the pixels whose depth voxel lies inside the shard's depth window.  The depth voxel
-// is a monotone function of px along a row (one fma with a fixed slope, then monotone clamps), so the
-// surviving pixels form one interval whose ends are found by bisection with the exact per-pixel depth.
+// Narrow a row span to the pixels that survive the depth clip / the shard's depth window.  Depth is a monotone
+// function of px along a row (one fma with a fixed slope, then monotone clamps), so the survivors form one
+// interval whose ends are found by bisection with the exact per-pixel depth.
 SVO_HD inline void row_span_depth_window(const TriSetup &t, uint32_t res, int32_t py, int32_t &x_lo, int32_t &x_hi) {
-	if (!t.cull_depth || x_lo > x_hi) return;
+	if ((!t.cull_depth && !t.clip_z) || x_lo > x_hi) return;
 	const bool rising = !(t.dzdx < 0.0);
-	// predicate "too low" holds on a prefix (rising) or suffix (falling); "too high" the other way round
-	auto below = [&](int32_t px) { return pixel_depth(t, res, px, py) < t.zs_lo; };
-	auto above = [&](int32_t px) { return pixel_depth(t, res, px, py) >= t.zs_hi; };
+	const double row_term = depth_row_term(t, py);
+	// "too low" holds on a prefix (rising) or suffix (falling) of the row; "too high" the other way round
+	auto below = [&](int32_t px) {
+		const double z = plane_z_row(t, px, row_term);
+		return (t.clip_z && z < 0.0) || (t.cull_depth && depth_voxel(t, res, z) < t.zs_lo);
+	};
+	auto above = [&](int32_t px) {
+		const double z = plane_z_row(t, px, row_term);
+		return (t.clip_z && z > 1.0) || (t.cull_depth && depth_voxel(t, res, z) >= t.zs_hi);
+	};
 	int32_t lo = x_lo, hi = x_hi;
 	if (rising) {
-		// first px that is not below
-		int32_t a = lo, b = hi + 1;
+		int32_t a = lo, b = hi + 1; // first px that is not below
 		while (a < b) { int32_t m = a + (b - a) / 2; if (below(m)) a = m + 1; else b = m; }
 		lo = a;
-		// last px that is not above
-		a = lo, b = hi + 1;
+		a = lo, b = hi + 1; // last px that is not above
 		while (a < b) { int32_t m = a + (b - a) / 2; if (!above(m)) a = m + 1; else b = m; }
 		hi = a - 1;
 	} else {
@@ -335,7 +406,6 @@ SVO_HD inline void row_span_depth_window(const TriSetup &t, uint32_t res, int32_
 	}
 	x_lo = lo, x_hi = hi;
 }
-SVO_HD inline bool depth_in_window(const TriSetup &t, uint32_t uz) { return !t.cull_depth || (uz >= t.zs_lo && uz < t.zs_hi); }
 
 // un-swizzle (voxelizer.frag:24): axis 0 -> u.zxy, 1 -> u.yzx, 2 -> u.xyz
 SVO_HD inline void unswizzle(uint32_t axis, uint32_t ux, uint32_t uy, uint32_t uz, uint32_t &vx, uint32_t &vy, uint32_t &vz) {

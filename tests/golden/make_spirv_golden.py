@@ -130,6 +130,31 @@ def make_voxelizer_case(level=6, mode=oracle.CONSERVATIVE_EXACT, albedo=0x00A1B2
                 frag_in=fi, frag_out=np.array(frag_out, np.uint32))
 
 
+def make_dilate_case(level=6):
+    """voxelizer_conservative.geom (reference Mode B, used without VK_EXT_conservative_rasterization): the three
+    emitted vertices (dilated ndc x, y and the barycentric-extrapolated depth) per triangle, as fp32 bit patterns."""
+    res = 1 << level
+    geom = si.Module.from_u32_file(SPV + "voxelizer_conservative.geom.u32", spec={0: res})
+    g_pos = next(v for v, (t, sc) in geom.vars.items() if sc == 3 and geom.types[geom.types[t][2]][0] == "struct")
+    in_var = next(v for v, (tt, sc) in geom.vars.items() if sc == 1 and 30 not in geom.decor.get(v, {}))
+    null_vtx = geom._null(geom.types[geom.types[geom.vars[in_var][0]][2]][1])
+    g_axis, g_aabb, g_zr = (geom.var_by_location(k, 3) for k in (1, 2, 3))
+    tris = voxelizer_triangles()
+    emitted_all, flat_all = [], []
+    for t in tris:
+        emitted, gl_in = [], []
+        for k in range(3):
+            v = [x if not isinstance(x, list) else list(x) for x in null_vtx]
+            v[0] = [np.float32(t[k][0]), np.float32(t[k][1]), np.float32(t[k][2]), np.float32(1.0)]
+            gl_in.append(v)
+        with np.errstate(all="ignore"):
+            geom.run({"gl_in": gl_in, ("loc", 0): [[np.float32(0), np.float32(0)]] * 3}, {}, None, on_emit=emitted.append)
+        e = emitted[0]
+        flat_all.append([int(e[g_axis])] + [int(x) for x in e[g_aabb]] + [int(x) for x in e[g_zr]])
+        emitted_all.append(np.array([[np.float32(c) for c in em[g_pos][0][:3]] for em in emitted], np.float32))
+    return dict(level=level, triangles=np.stack(tris), emitted=np.stack(emitted_all).view(np.uint32), flat=np.array(flat_all, np.uint32))
+
+
 if __name__ == "__main__":
     import time
     for n in BUILD_CASES:
@@ -137,6 +162,9 @@ if __name__ == "__main__":
         o = make_build_case(n)
         np.savez_compressed(os.path.join(HERE, "spirv_build_" + n + ".npz"), **o)
         print("build", n, len(o["packed"]), "fragments ->", o["range_bytes"], "bytes", f"{time.time() - t:.0f}s", flush=True)
+    o = make_dilate_case()
+    np.savez_compressed(os.path.join(HERE, "spirv_conservative_geom_L6.npz"), **o)
+    print("conservative geom", len(o["triangles"]), "triangles", flush=True)
     t = time.time()
     o = make_voxelizer_case()
     np.savez_compressed(os.path.join(HERE, "spirv_voxelizer_L6_conservative.npz"), **o)

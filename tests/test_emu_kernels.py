@@ -45,7 +45,7 @@ def test_onesweep_long_lookback_chain(emu):
         emu.dll.svo_emu_set_lookback_aggregate_only(0)
 
 
-@pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT])
+@pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT, api.CONSERVATIVE_DILATE])
 def test_full_path_small_soup(emu, mode):
     check_against_oracle(emu, scenes.random_soup(250, 7), 6, mode)
 

@@ -99,3 +99,22 @@ def test_cuda_builder_equals_reference_compute_shaders(path):
     b.CmdBuild()
     assert b.GetOctreeRange() == int(g["range_bytes"])
     assert_same_tree(b.octree_to_host(), g["words"], level)
+
+
+def test_oracle_mode_b_dilation_equals_reference_conservative_geom_shader():
+    """Reference Mode B (used when VK_EXT_conservative_rasterization is absent, Voxelizer.cpp:92-99): the dilated
+    vertices voxelizer_conservative.geom emits, bit for bit (incl. where its compiled SPIR-V fuses multiply-adds)."""
+    g = np.load(os.path.join(HERE, "golden", "spirv_conservative_geom_L6.npz"))
+    level = int(g["level"])
+    n_checked = 0
+    for t, em, flat in zip(g["triangles"], g["emitted"], g["flat"]):
+        a, _ = oracle.debug_tri_setup(t[0], t[1], t[2], level)
+        assert a.tolist() == flat.tolist()                       # gAxis / gAABB / gDepthRange: those of the ORIGINAL triangle
+        mine = oracle.debug_dilate(t[0], t[1], t[2], level).view(np.uint32)
+        ref = em.astype(np.uint32)
+        if np.isnan(ref.view(np.float32)).any():                 # degenerate input: both sides produce NaN
+            assert np.isnan(mine.view(np.float32)).any()
+            continue
+        assert (mine == ref).all()
+        n_checked += 1
+    assert n_checked > 250
