@@ -112,6 +112,10 @@ SVO_API int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, con
  * what the SPIR-V golden tests use.  svo_voxelizer_voxelize() then just restores the list. */
 SVO_API int svo_voxelizer_create_from_fragments(int device, uint32_t level, const uint64_t *fragments, uint64_t n, int on_device,
                                                 void *stream, svo_voxelizer **out);
+/* A window of the whole grid (half-open voxel box): only fragments inside it are produced, in GLOBAL coordinates at
+ * the full level.  Used by the multi-GPU slab split (each rank builds the part of the tree under its octants). */
+SVO_API int svo_voxelizer_create_windowed(svo_scene *scene, uint32_t level, int mode, const uint32_t window_lo[3],
+                                          const uint32_t window_hi[3], void *stream, svo_voxelizer **out);
 SVO_API void svo_voxelizer_destroy(svo_voxelizer *vox);
 /* Voxelizer::CmdVoxelize (src/Voxelizer.hpp:49, src/Voxelizer.cpp:167-179): enqueues the fragment
  * emission on the stream (the reference records it into a command buffer). */
@@ -135,6 +139,19 @@ SVO_API void svo_builder_destroy(svo_builder *b);
  * de-duplication and the level build.  The octree buffer is sized exactly, which costs one
  * internal stream synchronisation mid-build (the reference guesses the size, OctreeBuilder.cpp:42-45). */
 SVO_API int svo_builder_build(svo_builder *b, void *stream);
+/* The same build in two phases, for callers that place the node words themselves (multi-GPU stitch over NVLink,
+ * externally allocated / Vulkan-exported memory):
+ *   svo_builder_prepare  : sort + reduce + levels + the size read-back (one stream sync); afterwards
+ *                          svo_builder_octree_range_bytes / leaf_count / level_counts are valid;
+ *   svo_builder_emit_to  : writes the node words into d_dst (DEVICE memory of this or, through P2P / CUDA IPC, of
+ *                          another GPU).  skip_root = 0: the whole tree, child pointers = word index + bias.
+ *                          skip_root = 1: blocks 1.. are written from d_dst[0] on with pointers already valid for a
+ *                          buffer in which d_dst sits at word offset pointer_bias_words; the 8 root words are kept
+ *                          aside (svo_builder_root_words) so that the caller can merge several subtrees' roots.
+ * This is the fused "emit + transfer": the kernel that produces the words stores them across NVLink. */
+SVO_API int svo_builder_prepare(svo_builder *b, void *stream);
+SVO_API int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *stream);
+SVO_API int svo_builder_root_words(svo_builder *b, uint32_t out[8], void *stream);
 SVO_API uint32_t svo_builder_level(const svo_builder *b); /* OctreeBuilder::GetLevel */
 /* OctreeBuilder::GetOctreeRange (src/OctreeBuilder.hpp:42, src/OctreeBuilder.cpp:212-214): bytes. */
 SVO_API uint64_t svo_builder_octree_range_bytes(const svo_builder *b);

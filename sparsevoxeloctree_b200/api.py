@@ -60,6 +60,7 @@ SYMBOLS = [
     ("svo_scene_triangle_count", C.c_uint64, [_P]),
     ("svo_voxelizer_create", C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(svo_shard), _P, C.POINTER(_P)]),
     ("svo_voxelizer_create_from_fragments", C.c_int, [C.c_int, C.c_uint32, _P, C.c_uint64, C.c_int, _P, C.POINTER(_P)]),
+    ("svo_voxelizer_create_windowed", C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P, C.POINTER(_P)]),
     ("svo_voxelizer_destroy", None, [_P]),
     ("svo_voxelizer_voxelize", C.c_int, [_P, _P]),
     ("svo_voxelizer_level", C.c_uint32, [_P]),
@@ -70,6 +71,9 @@ SYMBOLS = [
     ("svo_builder_create", C.c_int, [_P, _P, C.POINTER(_P)]),
     ("svo_builder_destroy", None, [_P]),
     ("svo_builder_build", C.c_int, [_P, _P]),
+    ("svo_builder_prepare", C.c_int, [_P, _P]),
+    ("svo_builder_emit_to", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
+    ("svo_builder_root_words", C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
     ("svo_builder_level", C.c_uint32, [_P]),
     ("svo_builder_octree_range_bytes", C.c_uint64, [_P]),
     ("svo_builder_octree", _P, [_P]),
@@ -274,6 +278,17 @@ class Voxelizer:
         self._h = h
         return self
 
+    @staticmethod
+    def CreateWindowed(scene: Scene, octree_level: int, mode: int, window_lo, window_hi, stream=None):
+        """Only the fragments inside the half-open voxel box [window_lo, window_hi), in global coordinates."""
+        self = Voxelizer()
+        self.lib, self.device, self._scene, self.shard = scene.lib, scene.device, scene, None
+        lo, hi = (C.c_uint32 * 3)(*[int(v) for v in window_lo]), (C.c_uint32 * 3)(*[int(v) for v in window_hi])
+        h = _P()
+        self.lib.check(self.lib.dll.svo_voxelizer_create_windowed(scene._h, octree_level, mode, lo, hi, _stream_ptr(stream), C.byref(h)))
+        self._h = h
+        return self
+
     def GetScenePtr(self) -> Scene:
         return self._scene
 
@@ -349,6 +364,19 @@ class OctreeBuilder:
 
     def CmdBuild(self, stream=None):
         self.lib.check(self.lib.dll.svo_builder_build(self._h, _stream_ptr(stream)))
+
+    def Prepare(self, stream=None):
+        """Phase 1 of CmdBuild: everything but the node-word emission; sizes are known afterwards."""
+        self.lib.check(self.lib.dll.svo_builder_prepare(self._h, _stream_ptr(stream)))
+
+    def EmitTo(self, d_dst: int, pointer_bias_words: int = 0, skip_root: bool = False, stream=None):
+        """Phase 2: write the node words into caller-provided device memory (possibly a peer GPU's)."""
+        self.lib.check(self.lib.dll.svo_builder_emit_to(self._h, d_dst, pointer_bias_words, 1 if skip_root else 0, _stream_ptr(stream)))
+
+    def RootWords(self, stream=None) -> np.ndarray:
+        out = (C.c_uint32 * 8)()
+        self.lib.check(self.lib.dll.svo_builder_root_words(self._h, out, _stream_ptr(stream)))
+        return np.array(list(out), dtype=np.uint32)
 
     def GetOctreeRange(self) -> int:
         return int(self.lib.dll.svo_builder_octree_range_bytes(self._h))

@@ -130,7 +130,10 @@ struct svo_builder {
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
 	uint64_t range_bytes = 0;
 	uint32_t sort_passes = 0;
-	bool built = false;
+	bool built = false;     // the node words are in b->octree
+	bool prepared = false;  // sort / reduce / levels done, sizes known: ready for an emit
+	EmitParams ep{};
+	DevBuf<uint32_t> root_scratch; // svo_builder_emit_to(skip_root): the root block goes here
 	cudaEvent_t ev[SVO_PHASE_COUNT + 1] = {};
 };
 
@@ -255,7 +258,21 @@ void svo_scene_destroy(svo_scene *sc) {
 uint64_t svo_scene_triangle_count(const svo_scene *sc) { return sc ? sc->view.n_tri : 0; }
 
 // ------------------------------------------------------------------------------------------------------
+static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, const uint32_t *win_lo,
+                                 const uint32_t *win_hi, void *stream, svo_voxelizer **out);
+
 int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, void *stream, svo_voxelizer **out) {
+	return voxelizer_create_impl(scene, level, mode, shard, nullptr, nullptr, stream, out);
+}
+
+int svo_voxelizer_create_windowed(svo_scene *scene, uint32_t level, int mode, const uint32_t window_lo[3], const uint32_t window_hi[3],
+                                  void *stream, svo_voxelizer **out) {
+	if (!window_lo || !window_hi) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_create_windowed: null window");
+	return voxelizer_create_impl(scene, level, mode, nullptr, window_lo, window_hi, stream, out);
+}
+
+static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, const uint32_t *win_lo,
+                                 const uint32_t *win_hi, void *stream, svo_voxelizer **out) {
 	if (!scene || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_create: null argument");
 	*out = nullptr;
 	if (mode != SVO_CENTER && mode != SVO_CONSERVATIVE_EXACT && mode != SVO_CONSERVATIVE_DILATE)
@@ -284,6 +301,13 @@ int svo_voxelizer_create(svo_scene *scene, uint32_t level, int mode, const svo_s
 		v->rp.sb.lo[k] = ci * side;
 		v->rp.sb.hi[k] = ci * side + side;
 		v->rp.origin[k] = ci * side;
+		if (win_lo) { // a window of the whole grid: fragments keep their global coordinates
+			if (win_lo[k] >= win_hi[k] || win_hi[k] > (1u << level)) {
+				delete v;
+				return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_create_windowed: bad window");
+			}
+			v->rp.sb.lo[k] = win_lo[k], v->rp.sb.hi[k] = win_hi[k];
+		}
 	}
 
 	// ---- the count pass (Voxelizer::count_and_create_fragment_list, src/Voxelizer.cpp:134-165) ----
@@ -495,15 +519,15 @@ void svo_builder_destroy(svo_builder *b) {
 	if (!b) return;
 	DeviceGuard guard(b->device);
 	b->tmp.release(0), b->leaf.release(0), b->first.release(0), b->slot.release(0), b->counts.release(0), b->lb_state.release(0);
-	b->tickets.release(0), b->octree.release(0);
+	b->tickets.release(0), b->octree.release(0), b->root_scratch.release(0);
 	b->sort_scratch.hist.release(0), b->sort_scratch.ticket.release(0), b->sort_scratch.state.release(0);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
 	delete b;
 }
 
-int svo_builder_build(svo_builder *b, void *stream) {
-	if (!b) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_build: null handle");
+int svo_builder_prepare(svo_builder *b, void *stream) {
+	if (!b) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_prepare: null handle");
 	svo_voxelizer *v = b->vox;
 	if (!v->voxelized) return fail(SVO_ERR_NOT_READY, "svo_builder_build: voxelize first");
 	DeviceGuard guard(b->device);
@@ -511,7 +535,7 @@ int svo_builder_build(svo_builder *b, void *stream) {
 	const uint64_t F = v->n_frag;
 	const uint32_t L = b->level;
 	const int n_sm = sm_count(b->device);
-	b->built = false;
+	b->built = b->prepared = false;
 
 	// ---- sort by Morton code (stable) ----
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
@@ -577,7 +601,8 @@ int svo_builder_build(svo_builder *b, void *stream) {
 	// ---- exact sizing: the one host round trip of the build ----
 	SVO_CUDA_TRY(cudaMemcpyAsync(b->h_counts, b->counts.p, (L + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
 	SVO_CUDA_TRY(cudaStreamSynchronize(s));
-	EmitParams ep{};
+	EmitParams &ep = b->ep;
+	ep = EmitParams{};
 	ep.level = L;
 	uint64_t blocks = 1;
 	ep.block_base[1] = 0;
@@ -593,26 +618,73 @@ int svo_builder_build(svo_builder *b, void *stream) {
 		ep.slot[d] = b->slot.p + slot_off[d];
 	}
 	ep.leaf = b->leaf.p;
-	SVO_TRY(b->octree.reserve(blocks * 8, s));
-	if (b->h_counts[L] == 0) {
-		SVO_CUDA_TRY(cudaMemsetAsync(b->octree.p, 0, 8 * sizeof(uint32_t), s)); // empty scene: a zeroed root block
-	} else {
-		SVO_LAUNCH_INDEP(div_up(blocks, 256), 256, s, k_emit_octree, ep, b->octree.p);
-	}
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], s));
-	SVO_CUDA_TRY(cudaGetLastError());
 	b->range_bytes = blocks * 8 * sizeof(uint32_t); // (counter + 1) * 8 * 4, src/OctreeBuilder.cpp:212-214
+	b->prepared = true;
+	return SVO_OK;
+}
+
+// Emit the node words of a prepared build.  skip_root = 0: blocks 0.. go to d_dst[0..), child pointers are
+// block_index*8 + pointer_bias_words.  skip_root = 1 (multi-GPU stitch): blocks 1.. go to d_dst[0..) and the root
+// block to the builder's root scratch; child pointers are (block_index-1)*8 + pointer_bias_words, i.e. they are
+// already valid in a buffer where d_dst sits at word offset pointer_bias_words.  d_dst may be peer memory.
+static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_root, cudaStream_t s) {
+	EmitParams ep = b->ep;
+	ep.block_shift = skip_root ? 1u : 0u;
+	ep.ptr_bias = bias;
+	if (skip_root) {
+		SVO_TRY(b->root_scratch.reserve(8, s));
+		ep.root_dst = b->root_scratch.p;
+	}
+	if (b->h_counts[b->level] == 0) { // empty scene: a zeroed root block
+		SVO_CUDA_TRY(cudaMemsetAsync(skip_root ? b->root_scratch.p : d_dst, 0, 8 * sizeof(uint32_t), s));
+	} else {
+		auto k_direct = k_emit_octree<false>;
+		auto k_staged = k_emit_octree<true>;
+		if (skip_root) // stitched into another (usually a peer GPU's) buffer
+			SVO_LAUNCH(div_up(ep.total_blocks, 256), 256, 0, s, k_staged, ep, d_dst);
+		else
+			SVO_LAUNCH(div_up(ep.total_blocks, 256), 256, 0, s, k_direct, ep, d_dst);
+	}
+	SVO_CUDA_TRY(cudaGetLastError());
+	return SVO_OK;
+}
+
+int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *stream) {
+	if (!b || !d_dst) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_to: null argument");
+	if (!b->prepared) return fail(SVO_ERR_NOT_READY, "svo_builder_emit_to: prepare first");
+	if ((uint64_t)pointer_bias_words + b->range_bytes / 4 >= (1ull << 30))
+		return fail(SVO_ERR_CAPACITY, "biased child pointers would exceed 30 bits (octree.glsl:110)");
+	DeviceGuard guard(b->device);
+	return emit_into(b, d_dst, pointer_bias_words, skip_root, (cudaStream_t)stream);
+}
+
+int svo_builder_root_words(svo_builder *b, uint32_t out[8], void *stream) {
+	if (!b || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (!b->root_scratch.p) return fail(SVO_ERR_NOT_READY, "svo_builder_root_words: emit with skip_root first");
+	DeviceGuard guard(b->device);
+	SVO_CUDA_TRY(cudaMemcpyAsync(out, b->root_scratch.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	SVO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+	return SVO_OK;
+}
+
+int svo_builder_build(svo_builder *b, void *stream) {
+	SVO_TRY(svo_builder_prepare(b, stream));
+	DeviceGuard guard(b->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	SVO_TRY(b->octree.reserve(b->range_bytes / 4, s));
+	SVO_TRY(emit_into(b, b->octree.p, 0, 0, s));
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], s));
 	b->built = true;
 	return SVO_OK;
 }
 
 uint32_t svo_builder_level(const svo_builder *b) { return b ? b->level : 0; }
-uint64_t svo_builder_octree_range_bytes(const svo_builder *b) { return (b && b->built) ? b->range_bytes : 0; }
+uint64_t svo_builder_octree_range_bytes(const svo_builder *b) { return (b && (b->built || b->prepared)) ? b->range_bytes : 0; }
 const uint32_t *svo_builder_octree(const svo_builder *b) { return (b && b->built) ? b->octree.p : nullptr; }
-uint64_t svo_builder_leaf_count(const svo_builder *b) { return (b && b->built) ? b->h_counts[b->level] : 0; }
+uint64_t svo_builder_leaf_count(const svo_builder *b) { return (b && (b->built || b->prepared)) ? b->h_counts[b->level] : 0; }
 int svo_builder_level_counts(const svo_builder *b, uint64_t *out, uint32_t n_out) {
 	if (!b || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
-	if (!b->built) return fail(SVO_ERR_NOT_READY, "build first");
+	if (!b->built && !b->prepared) return fail(SVO_ERR_NOT_READY, "build first");
 	for (uint32_t d = 0; d < n_out; ++d) out[d] = d <= b->level ? b->h_counts[d] : 0;
 	return SVO_OK;
 }

@@ -35,6 +35,17 @@ def octant_cube(o: int):
     return (o & 1, (o >> 1) & 1, (o >> 2) & 1)
 
 
+def slab_window(rank: int, world: int, level: int):
+    """Voxel window (lo, hi) of the octants owned by `rank`: rank bit 0 selects the x half, bit 1 the y half,
+    bit 2 the z half (the x / xy / xyz split for 2 / 4 / 8 ranks)."""
+    res, half = 1 << level, 1 << (level - 1)
+    lo, hi = [0, 0, 0], [res, res, res]
+    for axis in range({1: 0, 2: 1, 4: 2, 8: 3}[world]):
+        bit = (rank >> axis) & 1
+        lo[axis], hi[axis] = bit * half, bit * half + half
+    return lo, hi
+
+
 def plan_offsets(words_per_octant):
     """words_per_octant[o] = node words of octant o's subtree (0 when the octant is empty).
     Returns (base word offset per octant, total words).  Subtrees are laid out after the root block in
@@ -95,10 +106,20 @@ class ShardedSVO:
         self.octants = octants_of_rank(self.rank, self.world)
         self.scene = api.Scene.Create(mesh, device=device, lib=self.lib)
         self.vox, self.builders = [], []
-        for o in self.octants:
-            v = api.Voxelizer.Create(self.scene, level, mode, shard=(1, octant_cube(o)))
+        # Slab mode (several ranks, and the full-level Morton code still fits a 64-bit fragment): each rank runs ONE
+        # build over the window made of its octants, in global coordinates, and emits its node words straight into
+        # rank 0's buffer.  Octant mode (level 14, or a single GPU): one cube-local build per octant.
+        self.slab = self.world > 1 and 3 * level + 24 <= 64 and use_ipc
+        if self.slab:
+            lo, hi = slab_window(self.rank, self.world, level)
+            v = api.Voxelizer.CreateWindowed(self.scene, level, mode, lo, hi)
             self.vox.append(v)
             self.builders.append(api.OctreeBuilder.Create(v))
+        else:
+            for o in self.octants:
+                v = api.Voxelizer.Create(self.scene, level, mode, shard=(1, octant_cube(o)))
+                self.vox.append(v)
+                self.builders.append(api.OctreeBuilder.Create(v))
         self.tdev = torch.device("cuda", device) if torch is not None else None
         self.final = None       # rank 0: the stitched node buffer (device pointer, cudaMalloc'ed)
         self.final_cap = 0
@@ -108,6 +129,8 @@ class ShardedSVO:
         self.bases = [0] * 8
         self.words = [0] * 8
         self.stage = None
+        self.push_stream = None
+        self.pipelined = True  # overlap the NVLink push of one octant with the build of the next (steady state)
 
     # -- rank 0 owns a grow-only arena for the stitched tree (like the reference's up-front octree buffer).
     #    It is cached per process and device, so a fresh ShardedSVO (the end-to-end path) reuses the allocation
@@ -135,8 +158,46 @@ class ShardedSVO:
             ar["cap"] = cap
         self.final, self.final_cap, self.peer_final = (ar["ptr"] if self.rank == 0 else None), ar["cap"], ar["peer"]
 
+    def _step_slab(self, stream):
+        """Slab mode: one build per rank; the emit kernel itself stores the node words into rank 0's buffer over
+        NVLink with final child pointers (fused emit + transfer); rank 0 merges the 8-word root blocks."""
+        torch, dist = self.torch, self.dist
+        v, b = self.vox[0], self.builders[0]
+        v.CmdVoxelize(stream)
+        b.Prepare(stream)
+        body = b.GetOctreeRange() // 4 - ROOT_WORDS if b.GetLeafCount() else 0   # node words below the root block
+        mine = torch.tensor([body], dtype=torch.int64, device=self.tdev)
+        bodies = torch.zeros(self.world, dtype=torch.int64, device=self.tdev)
+        dist.all_gather_into_tensor(bodies, mine)
+        bodies = [int(x) for x in bodies.cpu().tolist()]
+        base = ROOT_WORDS + sum(bodies[: self.rank])
+        total = ROOT_WORDS + sum(bodies)
+        if total >= 1 << 30:
+            raise OverflowError("stitched octree needs >= 2^30 words: 30-bit child pointers cannot address it")
+        self._ensure_final(total)
+        roots = torch.zeros(self.world * ROOT_WORDS, dtype=torch.int64, device=self.tdev)
+        my_root = np.zeros(ROOT_WORDS, dtype=np.uint32)
+        if body:
+            dst = (self.final if self.rank == 0 else self.peer_final) + base * 4
+            b.EmitTo(dst, base, True, stream)
+            my_root = b.RootWords(stream)
+        dist.all_gather_into_tensor(roots, torch.from_numpy(my_root.astype(np.int64)).to(self.tdev))
+        self.total_words, self.slab_bodies = total, bodies
+        if self.rank == 0:
+            rb = roots.cpu().numpy().reshape(self.world, ROOT_WORDS).sum(axis=0).astype(np.uint32)  # disjoint octants
+            self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, rb.ctypes.data, rb.nbytes, 0))
+        torch.cuda.synchronize(self.tdev)
+        dist.barrier()  # remote stores into rank 0's buffer are complete
+        return total * 4
+
     def step(self, stream=None):
         """One sharded build: local subtrees, size exchange, fused rebase + gather, root block on rank 0."""
+        if self.slab:
+            return self._step_slab(stream)
+        if self.world > 1 and self.use_ipc and self.total_words and self.pipelined:
+            done = self._step_pipelined(stream)
+            if done is not None:
+                return done
         torch, dist = self.torch, self.dist
         for v, b in zip(self.vox, self.builders):
             v.CmdVoxelize(stream)
@@ -159,6 +220,53 @@ class ShardedSVO:
         self.lib.check(self.lib.dll.svo_stream_synchronize(self.device, self.api._stream_ptr(stream)))
         if self.world > 1:
             dist.barrier()  # remote stores into rank 0's buffer are complete
+        return self.total_words * 4
+
+    def _step_pipelined(self, stream):
+        """Steady-state variant (the stitched-tree arena already exists): octants are built in rounds -- round r is
+        the r-th octant of every rank -- and as soon as a round's sizes are exchanged, each rank pushes that
+        subtree (rebase fused with the P2P store) on a second stream while it builds its next octant.  The layout
+        is the same as step()'s: subtrees in octant order after the root block.  Returns None (nothing pushed
+        yet) if the arena turns out too small, so that step() can take the sizing path."""
+        torch, dist = self.torch, self.dist
+        if self.push_stream is None:
+            self.push_stream = torch.cuda.Stream(self.tdev)
+        build_stream = stream if stream is not None else torch.cuda.current_stream(self.tdev)
+        n_rounds = 8 // self.world
+        words, bases, run = [0] * 8, [0] * 8, ROOT_WORDS
+        dst = self.final if self.rank == 0 else self.peer_final
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=self.tdev)
+        mine = torch.zeros(1, dtype=torch.int64, device=self.tdev)
+        pushed = False
+        for r in range(n_rounds):
+            v, b = self.vox[r], self.builders[r]
+            v.CmdVoxelize(build_stream)
+            b.CmdBuild(build_stream)
+            built = torch.cuda.Event()
+            built.record(build_stream)
+            mine.fill_(b.GetOctreeRange() // 4 if b.GetLeafCount() else 0)
+            dist.all_gather_into_tensor(sizes, mine)
+            round_sizes = sizes.cpu().tolist()
+            for k in range(self.world):
+                o = k + r * self.world
+                words[o] = int(round_sizes[k])
+                bases[o] = run if words[o] else 0
+                run += words[o]
+            if run > self.final_cap or run >= 1 << 30:
+                if pushed:
+                    raise OverflowError("stitched octree outgrew its arena mid-step")
+                return None
+            o = self.octants[r]
+            if words[o]:
+                self.push_stream.wait_event(built)
+                b.RebaseCopy(dst, bases[o], bases[o], self.push_stream)
+                pushed = True
+        self.words, self.bases, self.total_words = words, bases, run
+        if self.rank == 0:
+            rb = root_block(bases, words)
+            self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, rb.ctypes.data, rb.nbytes, 0))
+        torch.cuda.synchronize(self.tdev)
+        dist.barrier()  # remote stores into rank 0's buffer are complete
         return self.total_words * 4
 
     def _gather_nccl(self, stream):

@@ -206,3 +206,40 @@ def test_level14_virtual_shards_against_oracle(lib):
     sh.destroy()
     with pytest.raises(api.SvoError):                      # a single 64-bit fragment cannot hold level 14
         api.Voxelizer.Create(api.Scene.Create(mesh, lib=lib), 14)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_split_emit_to_assembles_the_whole_tree(lib, world):
+    # the multi-GPU slab path on ONE device: every "rank" builds the window of its octants in global coordinates
+    # (svo_voxelizer_create_windowed), prepares, and emits its node words with final pointers straight into a shared
+    # arena (svo_builder_emit_to, skip_root); the merged root + bodies must equal the whole-grid tree canonically
+    from sparsevoxeloctree_b200 import sharded
+    from tests.parity import assert_same_tree
+    mesh = scenes.random_soup(600, 51, 0.01, 1.2)
+    level, mode = 8, api.CONSERVATIVE_EXACT
+    scene = api.Scene.Create(mesh, lib=lib)
+    parts, bodies = [], []
+    for r in range(world):
+        lo, hi = sharded.slab_window(r, world, level)
+        v = api.Voxelizer.CreateWindowed(scene, level, mode, lo, hi)
+        b = api.OctreeBuilder.Create(v)
+        v.CmdVoxelize()
+        b.Prepare()
+        parts.append((v, b))
+        bodies.append(b.GetOctreeRange() // 4 - 8 if b.GetLeafCount() else 0)
+    total = 8 + sum(bodies)
+    arena = lib.malloc(total * 4)
+    root = np.zeros(8, np.uint64)
+    for r, (v, b) in enumerate(parts):
+        base = 8 + sum(bodies[:r])
+        if bodies[r]:
+            b.EmitTo(arena + base * 4, base, True)
+            root += b.RootWords().astype(np.uint64)
+    rb = root.astype(np.uint32)
+    lib.check(lib.dll.svo_memcpy_h2d(0, arena, rb.ctypes.data, 32, 0))
+    stitched = lib.to_host(arena, np.uint32, total)
+    _, vox, builder = api.build_svo(mesh, level, mode, lib=lib)
+    assert_same_tree(stitched, builder.octree_to_host(), level)
+    assert total * 4 == builder.GetOctreeRange()   # same node count: the split adds no blocks
+    assert sum(v.GetVoxelFragmentCount() for v, _ in parts) == vox.GetVoxelFragmentCount()
+    lib.free(arena)
