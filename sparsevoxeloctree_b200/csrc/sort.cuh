@@ -134,7 +134,7 @@ template <int BLOCK, int ITEMS, int RBITS> struct OnesweepCfg {
 #define SVO_OS_EXPERIMENT 0 // timing experiments only (bit 0: linear writes, bit 1: no look-back); results are wrong when set
 #endif
 #ifndef SVO_OS_BALLOT
-#define SVO_OS_BALLOT 0
+#define SVO_OS_BALLOT 1 // 1: warp multi-split by one vote per digit bit; 0: MATCH.ANY (measured slower on sm_100a)
 #endif
 #ifndef SVO_OS_LOOKBACK_DEPTH
 #define SVO_OS_LOOKBACK_DEPTH 8
@@ -173,6 +173,9 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 		for (int i = 0; i < ITEMS; ++i) key[i] = (FULL || wbase + i * 32 + lane < tile_count) ? src[i * 32] : ~0ull;
 	}
 	for (int i = threadIdx.x; i < NW * NB; i += BLOCK) s_hist[i] = 0; // overlaps the loads in flight
+	const uint32_t AGG = (2u * pass + 1u) & 3u, PRE = (2u * pass + 2u) & 3u;
+	uint32_t bin_total[DPT];
+	uint32_t my_sum = 0, inc = 0;
 	__syncthreads();
 
 	// rank inside the warp.  Stable: items in increasing i, lanes in increasing l.  The leader (lowest lane) of
@@ -184,7 +187,22 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
 		const uint32_t d = (FULL || wbase + i * 32 + lane < tile_count) ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
+#if (SVO_OS_EXPERIMENT & 4)
+		const unsigned peers = 1u << lane; // timing experiment: no MATCH (wrong ranks when digits repeat inside a row)
+#elif SVO_OS_BALLOT
+		unsigned peers = FULL_MASK; // multi-split by one vote per digit bit instead of MATCH.ANY
+#pragma unroll
+		for (int bb = 0; bb < RBITS; ++bb) {
+			const uint32_t bit = (d >> bb) & 1u;
+			peers &= ~(__ballot_sync(FULL_MASK, bit) ^ (0u - bit));
+		}
+		if (!FULL) {
+			const uint32_t bit = d >> RBITS;
+			peers &= ~(__ballot_sync(FULL_MASK, bit) ^ (0u - bit));
+		}
+#else
 		const unsigned peers = __match_any_sync(FULL_MASK, d);
+#endif
 		const uint32_t below = (uint32_t)__popc(peers & lt_mask);
 		uint32_t base = 0;
 		if (below == 0u) base = atomicAdd(&wh[d], (uint32_t)__popc(peers));
@@ -194,9 +212,6 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 	__syncthreads();
 
 	// per digit: exclusive prefix over the warps and the tile total; publish the aggregate right away
-	const uint32_t AGG = (2u * pass + 1u) & 3u, PRE = (2u * pass + 2u) & 3u;
-	uint32_t bin_total[DPT];
-	uint32_t my_sum = 0;
 	if (threadIdx.x < DTHREADS) {
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
@@ -222,7 +237,6 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 		}
 	}
 	// exclusive scan of the tile totals over the digits (digit threads are whole warps)
-	uint32_t inc = 0;
 	if (threadIdx.x < DTHREADS) {
 		inc = warp_inclusive_sum(my_sum, lane);
 		if (lane == 31) s_wsum[warp] = inc;
@@ -336,13 +350,13 @@ struct SortScratch {
 
 // tuning point (tests/bench can override at compile time)
 #ifndef SVO_OS_BLOCK
-#define SVO_OS_BLOCK 512
+#define SVO_OS_BLOCK 256
 #endif
 #ifndef SVO_OS_ITEMS
-#define SVO_OS_ITEMS 12
+#define SVO_OS_ITEMS 20
 #endif
 #ifndef SVO_OS_MINB
-#define SVO_OS_MINB 2
+#define SVO_OS_MINB 3
 #endif
 constexpr int OS_BLOCK = SVO_OS_BLOCK, OS_ITEMS = SVO_OS_ITEMS, OS_MINB = SVO_OS_MINB;
 

@@ -34,7 +34,8 @@ def run(lib, mesh, level, mode, reps=6):
         tot = sum(ms.values())
         if best is None or tot < best[0]:
             best = (tot, ms, npass)
-    info = (vox.GetVoxelFragmentCount(), b.GetLeafCount())
+    import zlib
+    info = (vox.GetVoxelFragmentCount(), b.GetLeafCount(), zlib.crc32(b.octree_to_host().tobytes()))
     b.Destroy(), vox.Destroy(), scene.Destroy()
     return best, info
 
@@ -57,11 +58,11 @@ def main():
             print(f"variant {v}: does not compile", flush=True)
             continue
         lib = api.Library(path)
-        (tot, ms, npass), (F, U) = run(lib, mesh, cfg["level"], mode)
+        (tot, ms, npass), (F, U, crc) = run(lib, mesh, cfg["level"], mode)
         per = ms["sort_passes"] / max(npass, 1)
         gbs = 16.0 * F / (per * 1e-3) / 1e9 if per > 0 else 0
         print(f"variant {v:12s} total {tot:7.3f} ms | " + " ".join(f"{k}={x:.3f}" for k, x in ms.items()) +
-              f" | passes={npass} per-pass {per:.3f} ms = {gbs:.0f} GB/s  (F={F} U={U})", flush=True)
+              f" | passes={npass} per-pass {per:.3f} ms = {gbs:.0f} GB/s  (F={F} U={U} crc={crc:08x})", flush=True)
 
 
 if __name__ == "__main__":
