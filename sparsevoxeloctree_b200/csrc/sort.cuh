@@ -58,28 +58,36 @@ inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit) {
 // ---- histogram of every pass in one read ---------------------------------------------------------------
 // Spatially coherent fragments share their upper digits: one OR-reduction of (key ^ lane 0's key) tells, for
 // every pass at once, whether the whole warp falls into one bin -- then a single lane adds 32.
+// The pass loop is unrolled (NPASS is a template parameter) and runs on the two 32-bit halves of
+// key >> shift[0], so a digit costs one funnel shift and one AND instead of a variable 64-bit shift.
+SVO_DEV uint32_t hist_digit(uint32_t lo, uint32_t hi, uint32_t r /*relative shift, uniform*/, uint32_t mask) {
+	return (r < 32u ? __funnelshift_r(lo, hi, r) : hi >> (r - 32u)) & mask;
+}
+template <int NPASS>
 __global__ void __launch_bounds__(HIST_BLOCK)
     k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n, SortPasses sp, uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/) {
-	__shared__ uint32_t s_hist[MAX_PASSES * MAX_RADIX];
-	for (uint32_t i = threadIdx.x; i < sp.n_pass * MAX_RADIX; i += HIST_BLOCK) s_hist[i] = 0;
+	__shared__ uint32_t s_hist[NPASS * MAX_RADIX];
+	for (uint32_t i = threadIdx.x; i < NPASS * MAX_RADIX; i += HIST_BLOCK) s_hist[i] = 0;
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
+	const uint32_t s0 = sp.shift[0];
 	const uint64_t per_block = (uint64_t)HIST_BLOCK * HIST_ITEMS;
 	for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < n; base += (uint64_t)gridDim.x * per_block) {
 		const bool full = base + per_block <= n;
-#pragma unroll 4
+#pragma unroll 8
 		for (int i = 0; i < HIST_ITEMS; ++i) {
 			const uint64_t idx = base + (uint64_t)i * HIST_BLOCK + threadIdx.x;
 			const bool ok = full || idx < n;
-			const uint64_t k = ok ? keys[idx] : 0;
-			const uint64_t k0 = __shfl_sync(FULL_MASK, k, 0);
-			const uint64_t diff = (k ^ k0) | (ok ? 0ull : ~0ull);
-			const uint32_t dlo = __reduce_or_sync(FULL_MASK, (uint32_t)diff);
-			const uint32_t dhi = __reduce_or_sync(FULL_MASK, (uint32_t)(diff >> 32));
-			const uint64_t any_diff = ((uint64_t)dhi << 32) | dlo;
-			for (uint32_t p = 0; p < sp.n_pass; ++p) {
-				const uint32_t d = (uint32_t)(k >> sp.shift[p]) & sp.mask[p];
-				const bool uniform = ((uint32_t)(any_diff >> sp.shift[p]) & sp.mask[p]) == 0u;
+			const uint64_t m = (ok ? keys[idx] : 0ull) >> s0;
+			const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+			const uint32_t pad = ok ? 0u : ~0u;
+			const uint32_t dlo = __reduce_or_sync(FULL_MASK, (lo ^ __shfl_sync(FULL_MASK, lo, 0)) | pad);
+			const uint32_t dhi = __reduce_or_sync(FULL_MASK, (hi ^ __shfl_sync(FULL_MASK, hi, 0)) | pad);
+#pragma unroll
+			for (int p = 0; p < NPASS; ++p) {
+				const uint32_t r = sp.shift[p] - s0;
+				const uint32_t d = hist_digit(lo, hi, r, sp.mask[p]);
+				const bool uniform = hist_digit(dlo, dhi, r, sp.mask[p]) == 0u;
 				if (uniform) {
 					if (lane == 0) atomicAdd(&s_hist[p * MAX_RADIX + d], 32u);
 				} else if (ok)
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(HIST_BLOCK)
 		}
 	}
 	__syncthreads();
-	for (uint32_t i = threadIdx.x; i < sp.n_pass * MAX_RADIX; i += HIST_BLOCK) {
+	for (uint32_t i = threadIdx.x; i < NPASS * MAX_RADIX; i += HIST_BLOCK) {
 		const uint32_t c = s_hist[i];
 		if (c) atomicAdd(&g_hist[i], c);
 	}
@@ -407,7 +415,13 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	uint32_t hgrid = div_up(n, (uint64_t)HIST_BLOCK * HIST_ITEMS);
 	const uint32_t hmax = (uint32_t)(n_sm > 0 ? n_sm : 148) * 8u;
 	if (hgrid > hmax) hgrid = hmax;
-	SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, k_radix_histogram, (const uint64_t *)a, n, sp, sc.hist.p);
+	switch (sp.n_pass) {
+#define SVO_HIST_CASE(NP) \
+	case NP: SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, k_radix_histogram<NP>, (const uint64_t *)a, n, sp, sc.hist.p); break;
+		SVO_HIST_CASE(1) SVO_HIST_CASE(2) SVO_HIST_CASE(3) SVO_HIST_CASE(4) SVO_HIST_CASE(5) SVO_HIST_CASE(6) SVO_HIST_CASE(7)
+		SVO_HIST_CASE(8)
+#undef SVO_HIST_CASE
+	}
 	SVO_LAUNCH(sp.n_pass, MAX_RADIX, 0, s, k_radix_scan_bins, sc.hist.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));

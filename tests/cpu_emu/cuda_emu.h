@@ -258,6 +258,10 @@ inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 	return r;
 }
 
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+	return (unsigned)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
+}
+
 inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
 	const uint64_t *s = svo_emu::warp_publish(mask, v);
 	unsigned r = 0, live = svo_emu::tctx.warp->live_mask;
