@@ -35,7 +35,7 @@ typedef enum svo_status {
 	SVO_OK = 0,
 	SVO_ERR_INVALID_ARGUMENT = -1,
 	SVO_ERR_CUDA = -2,           /* a CUDA runtime call failed; svo_last_error() has the cudaError string */
-	SVO_ERR_UNSUPPORTED = -3,    /* e.g. textured draws (not on the built path yet) */
+	SVO_ERR_UNSUPPORTED = -3,    /* e.g. IPC in a build without it */
 	SVO_ERR_CAPACITY = -4,       /* > 2^32-1 fragments, or an octree of >= 2^30 words (30-bit node pointers) */
 	SVO_ERR_NOT_READY = -5       /* result queried before the producing call */
 } svo_status;
@@ -62,14 +62,27 @@ typedef struct svo_draw {
  * (struct Vertex {vec3 pos; vec2 uv}, stride 20, src/Scene.cpp:16-19; a tight float3 array with
  * stride 12 is accepted too), the u32 index buffer and the draw list.  Positions must already be
  * normalised to [-1,1]^3 (src/Scene.cpp:90-99). */
+/* One texture as Scene::load_textures reads it (src/Scene.cpp:245-262): the stbi_load(..., 4) image, RGBA8 with
+ * sRGB-encoded colour (VK_FORMAT_R8G8B8A8_SRGB), row 0 first, tight rows; always a HOST pointer.  The library
+ * builds the mip chain on the device like CmdGenerateMipmap2D (linear blits, src/Scene.cpp:290-295). */
+typedef struct svo_texture {
+	const uint8_t *rgba8;
+	uint32_t width, height; /* 1..16384 */
+} svo_texture;
+
 typedef struct svo_mesh {
 	const void *positions;          /* first vertex position; HOST pointer unless on_device != 0 */
 	uint32_t position_stride_bytes; /* >= 12, multiple of 4 */
-	uint32_t on_device;             /* 1: positions/indices are device pointers (borrowed, must outlive the scene) */
+	uint32_t on_device;             /* 1: positions/texcoords/indices are device pointers (borrowed, must outlive the scene) */
 	const uint32_t *indices;
 	uint64_t n_vertices, n_indices;
 	const svo_draw *draws; /* always a host pointer */
 	uint32_t n_draws;
+	/* textured materials (shader/voxelizer.frag:27-36); all zero / NULL for untextured scenes */
+	uint32_t n_textures;
+	const svo_texture *textures;    /* host array; svo_draw.texture_id indexes it */
+	const void *texcoords;          /* first vertex's uv (2 floats); for the reference's Vertex: positions + 12, same stride */
+	uint32_t texcoord_stride_bytes; /* >= 8, multiple of 4 */
 } svo_mesh;
 
 /* A power-of-two sub-cube of the grid (octant sharding): the cube of side
@@ -98,6 +111,11 @@ SVO_API uint64_t svo_launch_count(void); /* kernels launched by this library sin
 SVO_API int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene **out);
 SVO_API void svo_scene_destroy(svo_scene *scene);
 SVO_API uint64_t svo_scene_triangle_count(const svo_scene *scene);
+/* One mip level of a texture as the scene holds it on the device (the images Scene::load_textures leaves after
+ * CmdGenerateMipmap2D, src/Scene.cpp:290-295): *d_texels = DEVICE pointer to width*height RGBA8 texels.
+ * Returns the texture's level count (ImageBase::QueryMipLevel) or a negative svo_status. */
+SVO_API int svo_scene_texture_level(const svo_scene *scene, uint32_t texture, uint32_t level, uint32_t *width, uint32_t *height,
+                                    const uint32_t **d_texels);
 
 /* ---- Voxelizer ----------------------------------------------------------------------------
  * svo_voxelizer_create = Voxelizer::Create (src/Voxelizer.hpp:43-45, src/Voxelizer.cpp:5-26):

@@ -46,6 +46,19 @@ def lib() -> C.CDLL:
         L.orc_voxelize.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         L.orc_voxelize.restype = C.c_int64
+        L.orc_texset_create.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_texset_create.restype = C.c_void_p
+        L.orc_texset_destroy.argtypes = [C.c_void_p]
+        L.orc_texset_destroy.restype = None
+        L.orc_texset_level.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_void_p)]
+        L.orc_texset_level.restype = C.c_int
+        L.orc_voxelize_textured.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                            C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int]
+        L.orc_voxelize_textured.restype = C.c_int64
+        L.orc_debug_sample.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
+        L.orc_debug_sample.restype = C.c_uint32
         L.orc_build.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
         L.orc_build.restype = C.c_int64
         L.orc_canonicalise.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -88,9 +101,57 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def voxelize(positions, indices, draws, level, mode=CENTER, shard=None, nthreads=1, count_only=False):
+class _orc_texture(C.Structure):
+    _fields_ = [("rgba8", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class TexSet:
+    """Textures with the mip chains Scene::load_textures builds.  images: list of uint8 [H,W,4] arrays (sRGB RGBA)."""
+
+    def __init__(self, images):
+        self.images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        arr = (_orc_texture * max(1, len(self.images)))()
+        for i, im in enumerate(self.images):
+            assert im.ndim == 3 and im.shape[2] == 4
+            arr[i] = _orc_texture(im.ctypes.data, im.shape[1], im.shape[0])
+        self._h = lib().orc_texset_create(C.cast(arr, C.c_void_p), len(self.images))
+        if not self._h:
+            raise ValueError("orc_texset_create failed")
+
+    def level(self, tex, level):
+        w, h, d = C.c_uint32(), C.c_uint32(), C.c_void_p()
+        n = lib().orc_texset_level(self._h, tex, level, C.byref(w), C.byref(h), C.byref(d))
+        if n < 0:
+            raise IndexError((tex, level))
+        buf = (C.c_uint8 * (w.value * h.value * 4)).from_address(d.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(h.value, w.value, 4).copy()
+
+    def level_count(self, tex):
+        w, h, d = C.c_uint32(), C.c_uint32(), C.c_void_p()
+        return lib().orc_texset_level(self._h, tex, 0, C.byref(w), C.byref(h), C.byref(d))
+
+    def sample(self, tex, tri_pos, tri_uv, level, px, py):
+        """(rgb or None when discarded, (hi, lo, delta*256)) of pixel (px,py) of one textured triangle."""
+        p = [np.ascontiguousarray(v, dtype=np.float32) for v in tri_pos]
+        t = [np.ascontiguousarray(v, dtype=np.float32) for v in tri_uv]
+        lod = np.zeros(3, np.uint32)
+        r = lib().orc_debug_sample(self._h, tex, _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), level,
+                                   px, py, _ptr(lod))
+        return (None if r == 0 else int(r & 0xffffff)), tuple(int(x) for x in lod)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_texset_destroy(self._h)
+            self._h = None
+
+
+def voxelize(positions, indices, draws, level, mode=CENTER, shard=None, nthreads=1, count_only=False, texcoords=None,
+             texset=None):
     """positions: float32 [V,3] (or [V,5] pos+uv like the reference Vertex); indices uint32; draws DRAW_DTYPE.
+    texcoords (float32 [V,2]) + texset (TexSet) enable textured draws.
     Returns a FRAG_DTYPE array (emission order when nthreads == 1)."""
+    if texset is not None or texcoords is not None:
+        return _voxelize_textured(positions, texcoords, indices, draws, texset, level, mode, shard, nthreads, count_only)
     positions = np.ascontiguousarray(positions, dtype=np.float32)
     indices = np.ascontiguousarray(indices, dtype=np.uint32)
     draws = np.ascontiguousarray(draws, dtype=DRAW_DTYPE)
@@ -110,6 +171,32 @@ def voxelize(positions, indices, draws, level, mode=CENTER, shard=None, nthreads
     n2 = L.orc_voxelize(_ptr(positions), stride, _ptr(indices), _ptr(draws), len(draws), level, mode, _ptr(lo), _ptr(hi),
                         _ptr(out), n, nthreads)
     assert n2 == n
+    return out
+
+
+def _voxelize_textured(positions, texcoords, indices, draws, texset, level, mode, shard, nthreads, count_only):
+    positions = np.ascontiguousarray(positions, dtype=np.float32)
+    texcoords = np.ascontiguousarray(texcoords, dtype=np.float32)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    draws = np.ascontiguousarray(draws, dtype=DRAW_DTYPE)
+    lo = hi = None
+    if shard is not None:
+        lo = np.ascontiguousarray(shard[0], dtype=np.uint32)
+        hi = np.ascontiguousarray(shard[1], dtype=np.uint32)
+    L = lib()
+
+    def call(out, cap):
+        return L.orc_voxelize_textured(_ptr(positions), positions.shape[1] * 4, _ptr(texcoords), texcoords.shape[1] * 4,
+                                       _ptr(indices), _ptr(draws), len(draws), texset._h if texset is not None else None, level,
+                                       mode, _ptr(lo), _ptr(hi), out, cap, nthreads)
+
+    n = call(None, 0)
+    if n < 0:
+        raise ValueError(f"orc_voxelize_textured failed ({n})")
+    if count_only:
+        return int(n)
+    out = np.zeros(n, dtype=FRAG_DTYPE)
+    assert call(_ptr(out), n) == n
     return out
 
 

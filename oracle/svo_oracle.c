@@ -315,37 +315,306 @@ static int frag_voxel(const orc_tri *t, const orc_plane *pl, uint32_t res, int32
 
 static int32_t floor_div256(int32_t v) { return v >> 8; } /* arithmetic shift = floor for negatives */
 
-int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uint32_t *indices,
-                     const orc_draw *draws, uint32_t n_draws, uint32_t level, int mode,
-                     const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out, int64_t cap,
-                     int nthreads) {
+/* ------------------------------------------------------------------------------------------
+ * Textures: voxelizer.frag:27-32 (texture(uTextures[id], gTexcoord), alpha < 0.5 discard,
+ * packUnorm4x8), images VK_FORMAT_R8G8B8A8_SRGB with a full mip chain generated by linear blits
+ * (Scene.cpp:262-296, dep/MyVK/src/CommandBuffer.cpp:338-393), sampler LINEAR / LINEAR mipmap /
+ * REPEAT, no anisotropy, no LOD clamp (Scene.cpp:409-411, dep/MyVK/src/Sampler.cpp:13-38).
+ *
+ * UNPINNED like the rasterizer: filtering precision, the LOD approximation and sRGB conversion are
+ * the Vulkan driver's.  The arithmetic below is the "ideal" formulas of the Vulkan spec (texel
+ * filtering, scale factor / LOD operation, blit image) with pinned rounding:
+ *  - sRGB decode through a 256-entry fp32 table; encode = nearest code in the sRGB domain, by
+ *    comparing with the decoded mid-points; alpha is linear (a / 255).
+ *  - texture coordinates: the affine map through the three ORIGINAL projected vertices (fp32 window
+ *    coordinates taken to fp64), evaluated at the pixel centre in fp64 -- for Mode B too, where the
+ *    reference extrapolates the same affine map to the dilated vertices (conservative.geom:21-27,76-86).
+ *  - LOD: constant per triangle (the map is affine): rho^2 = max(|d(uv*size)/dx|^2, |d(uv*size)/dy|^2),
+ *    lambda = log2(rho) floored to 1/256 with an exponent split and a 128-entry threshold table (no
+ *    transcendental at sample time); lambda <= 0 = magnification (level 0).
+ *  - bilinear weights from fp64 coordinates rounded to fp32, lerps in fp32, one rounding per operator.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+	uint32_t w, h;
+	uint8_t *px; /* RGBA8, sRGB-encoded colour, row-major */
+} orc_level;
+typedef struct {
+	uint32_t levels;
+	orc_level *lv;
+} orc_tex;
+struct orc_texset {
+	uint32_t n;
+	orc_tex *t;
+	float decode[256];   /* sRGB code -> linear */
+	float enc_thr[256];  /* linear value of the mid-point between codes c-1 and c */
+	double lod_thr[128]; /* 2^(k/128) */
+};
+
+static double srgb_to_linear(double x) { return x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4); }
+
+static uint32_t mip_level_count(uint32_t w, uint32_t h) { /* ImageBase::QueryMipLevel (dep/MyVK/include/myvk/ImageBase.hpp:10-17,49) */
+	uint32_t x = w | h, ret = 1;
+	if (x & 0x80000000u)
+		return 32u;
+	while (x >> ret)
+		++ret;
+	return ret;
+}
+
+static uint8_t encode_srgb(const orc_texset *s, float x) {
+	uint32_t c = 0;
+	for (uint32_t k = 1; k < 256; ++k)
+		if (s->enc_thr[k] <= x)
+			c = k;
+	return (uint8_t)c;
+}
+static float unorm_alpha(uint8_t a) { return (float)a / 255.0f; }
+static uint8_t pack_unorm8(float x) { /* packUnorm4x8: round(clamp(c, 0, 1) * 255), ties to even; NaN -> 0 */
+	if (!(x > 0.0f))
+		return 0;
+	if (x > 1.0f)
+		x = 1.0f;
+	return (uint8_t)rintf(x * 255.0f);
+}
+static float lerpf(float a, float b, float t) { return a + t * (b - a); }
+
+/* four texels of one level at integer columns i0,i1 / rows j0,j1, filtered: out = linear RGBA */
+static void filter4(const orc_texset *s, const orc_level *L, int64_t i0, int64_t i1, int64_t j0, int64_t j1, float a, float b,
+                    float out[4]) {
+	const uint8_t *t00 = L->px + 4 * ((size_t)j0 * L->w + (size_t)i0), *t10 = L->px + 4 * ((size_t)j0 * L->w + (size_t)i1);
+	const uint8_t *t01 = L->px + 4 * ((size_t)j1 * L->w + (size_t)i0), *t11 = L->px + 4 * ((size_t)j1 * L->w + (size_t)i1);
+	for (int c = 0; c < 4; ++c) {
+		float v00, v10, v01, v11;
+		if (c < 3)
+			v00 = s->decode[t00[c]], v10 = s->decode[t10[c]], v01 = s->decode[t01[c]], v11 = s->decode[t11[c]];
+		else
+			v00 = unorm_alpha(t00[c]), v10 = unorm_alpha(t10[c]), v01 = unorm_alpha(t01[c]), v11 = unorm_alpha(t11[c]);
+		out[c] = lerpf(lerpf(v00, v10, a), lerpf(v01, v11, a), b);
+	}
+}
+
+/* vkCmdBlitImage with VK_FILTER_LINEAR from level l-1 to level l (CommandBuffer.cpp:353-381): the source
+ * coordinate of a destination texel centre is scaled by the size ratio, then linearly filtered with
+ * clamp-to-edge; sRGB images filter in linear space and re-encode. */
+static void downsample(const orc_texset *s, const orc_level *src, orc_level *dst) {
+	const double sx = (double)src->w / (double)dst->w, sy = (double)src->h / (double)dst->h;
+	for (uint32_t j = 0; j < dst->h; ++j)
+		for (uint32_t i = 0; i < dst->w; ++i) {
+			const double U = ((double)i + 0.5) * sx - 0.5, V = ((double)j + 0.5) * sy - 0.5;
+			const double fu = floor(U), fv = floor(V);
+			const float a = (float)(U - fu), b = (float)(V - fv);
+			int64_t i0 = (int64_t)fu, i1 = i0 + 1, j0 = (int64_t)fv, j1 = j0 + 1;
+			if (i0 < 0) i0 = 0;
+			if (j0 < 0) j0 = 0;
+			if (i1 > (int64_t)src->w - 1) i1 = (int64_t)src->w - 1;
+			if (j1 > (int64_t)src->h - 1) j1 = (int64_t)src->h - 1;
+			if (i0 > (int64_t)src->w - 1) i0 = (int64_t)src->w - 1;
+			if (j0 > (int64_t)src->h - 1) j0 = (int64_t)src->h - 1;
+			float v[4];
+			filter4(s, src, i0, i1, j0, j1, a, b, v);
+			uint8_t *o = dst->px + 4 * ((size_t)j * dst->w + i);
+			for (int c = 0; c < 3; ++c)
+				o[c] = encode_srgb(s, v[c]);
+			o[3] = pack_unorm8(v[3]);
+		}
+}
+
+orc_texset *orc_texset_create(const orc_texture *tex, uint32_t n) {
+	orc_texset *s = (orc_texset *)calloc(1, sizeof(orc_texset));
+	if (!s)
+		return NULL;
+	for (int c = 0; c < 256; ++c) {
+		s->decode[c] = (float)srgb_to_linear((double)c / 255.0);
+		s->enc_thr[c] = c ? (float)srgb_to_linear(((double)c - 0.5) / 255.0) : 0.0f;
+	}
+	for (int k = 0; k < 128; ++k)
+		s->lod_thr[k] = exp2((double)k / 128.0);
+	s->n = n;
+	s->t = (orc_tex *)calloc(n ? n : 1, sizeof(orc_tex));
+	for (uint32_t i = 0; i < n; ++i) {
+		orc_tex *t = &s->t[i];
+		if (tex[i].width == 0 || tex[i].height == 0 || !tex[i].rgba8) {
+			orc_texset_destroy(s);
+			return NULL;
+		}
+		t->levels = mip_level_count(tex[i].width, tex[i].height);
+		t->lv = (orc_level *)calloc(t->levels, sizeof(orc_level));
+		uint32_t w = tex[i].width, h = tex[i].height;
+		for (uint32_t l = 0; l < t->levels; ++l) {
+			t->lv[l].w = w, t->lv[l].h = h;
+			t->lv[l].px = (uint8_t *)malloc((size_t)w * h * 4);
+			if (l == 0)
+				memcpy(t->lv[0].px, tex[i].rgba8, (size_t)w * h * 4);
+			else
+				downsample(s, &t->lv[l - 1], &t->lv[l]);
+			w = w / 2 ? w / 2 : 1; /* std::max(mip_width / 2, 1) (CommandBuffer.cpp:362-363) */
+			h = h / 2 ? h / 2 : 1;
+		}
+	}
+	return s;
+}
+void orc_texset_destroy(orc_texset *s) {
+	if (!s)
+		return;
+	for (uint32_t i = 0; i < s->n && s->t; ++i) {
+		for (uint32_t l = 0; l < s->t[i].levels && s->t[i].lv; ++l)
+			free(s->t[i].lv[l].px);
+		free(s->t[i].lv);
+	}
+	free(s->t);
+	free(s);
+}
+int orc_texset_level(const orc_texset *s, uint32_t tex, uint32_t level, uint32_t *w, uint32_t *h, const uint8_t **data) {
+	if (!s || tex >= s->n || level >= s->t[tex].levels)
+		return -1;
+	*w = s->t[tex].lv[level].w, *h = s->t[tex].lv[level].h, *data = s->t[tex].lv[level].px;
+	return (int)s->t[tex].levels;
+}
+
+/* the affine texture-coordinate map of one triangle and its (constant) level of detail */
+typedef struct {
+	double x0, y0, u0, v0, dudx, dudy, dvdx, dvdy;
+	uint32_t hi, lo; /* mip levels blended */
+	float delta;     /* weight of lo */
+} orc_uvmap;
+
+static void uvmap_setup(const orc_texset *s, const orc_tex *tex, const float *const p[3], const float *const uv[3], uint32_t axis,
+                        uint32_t res, orc_uvmap *m) {
+	const float fres = (float)res;
+	double x[3], y[3];
+	for (int i = 0; i < 3; ++i) { /* Project() (voxelizer.geom:15-19) + viewport, like orc_tri_setup */
+		const float qx = axis == 0u ? p[i][1] : (axis == 1u ? p[i][2] : p[i][0]);
+		const float qy = axis == 0u ? p[i][2] : (axis == 1u ? p[i][0] : p[i][1]);
+		x[i] = (double)((qx + 1.0f) * 0.5f * fres);
+		y[i] = (double)((qy + 1.0f) * 0.5f * fres);
+	}
+	m->x0 = x[0], m->y0 = y[0], m->u0 = (double)uv[0][0], m->v0 = (double)uv[0][1];
+	const double dx1 = x[1] - x[0], dy1 = y[1] - y[0], dx2 = x[2] - x[0], dy2 = y[2] - y[0];
+	const double det = dx1 * dy2 - dx2 * dy1;
+	m->dudx = m->dudy = m->dvdx = m->dvdy = 0.0;
+	if (det != 0.0 && isfinite(det)) {
+		const double du1 = (double)uv[1][0] - m->u0, du2 = (double)uv[2][0] - m->u0;
+		const double dv1 = (double)uv[1][1] - m->v0, dv2 = (double)uv[2][1] - m->v0;
+		m->dudx = (du1 * dy2 - du2 * dy1) / det;
+		m->dudy = (du2 * dx1 - du1 * dx2) / det;
+		m->dvdx = (dv1 * dy2 - dv2 * dy1) / det;
+		m->dvdy = (dv2 * dx1 - dv1 * dx2) / det;
+	}
+	const double W = (double)tex->lv[0].w, H = (double)tex->lv[0].h;
+	const double ax = m->dudx * W, ay = m->dvdx * H, bx = m->dudy * W, by = m->dvdy * H;
+	const double r2x = ax * ax + ay * ay, r2y = bx * bx + by * by;
+	const double r2 = r2y > r2x ? r2y : r2x;
+	const uint32_t q = tex->levels - 1u;
+	m->hi = m->lo = 0, m->delta = 0.0f;
+	if (!(r2 > 1.0))
+		return; /* lambda <= 0 (or NaN): magnification */
+	if (!isfinite(r2)) {
+		m->hi = m->lo = q;
+		return;
+	}
+	int E;
+	const double f2 = frexp(r2, &E) * 2.0; /* r2 = f2 * 2^(E-1), f2 in [1,2) */
+	int k = 0;
+	for (int i = 1; i < 128; ++i)
+		if (s->lod_thr[i] <= f2)
+			k = i;
+	const int64_t lam256 = 128 * (int64_t)(E - 1) + k; /* floor(256 * log2(rho)) = floor(128 * log2(r2)) */
+	const int64_t hi = lam256 >> 8;
+	if (hi >= (int64_t)q) {
+		m->hi = m->lo = q;
+		return;
+	}
+	m->hi = (uint32_t)hi, m->lo = (uint32_t)hi + 1u;
+	m->delta = (float)(lam256 & 255) / 256.0f;
+	if (m->delta == 0.0f)
+		m->lo = m->hi;
+}
+
+static void sample_level(const orc_texset *s, const orc_level *L, double u, double v, float out[4]) {
+	double U = u * (double)L->w - 0.5, V = v * (double)L->h - 0.5;
+	if (!(fabs(U) < 4503599627370496.0)) U = 0.0; /* non-finite / absurd coordinates: pinned to texel 0 */
+	if (!(fabs(V) < 4503599627370496.0)) V = 0.0;
+	const double fu = floor(U), fv = floor(V);
+	const float a = (float)(U - fu), b = (float)(V - fv);
+	int64_t i0 = (int64_t)fu % (int64_t)L->w, j0 = (int64_t)fv % (int64_t)L->h; /* VK_SAMPLER_ADDRESS_MODE_REPEAT */
+	if (i0 < 0) i0 += L->w;
+	if (j0 < 0) j0 += L->h;
+	const int64_t i1 = i0 + 1 == (int64_t)L->w ? 0 : i0 + 1, j1 = j0 + 1 == (int64_t)L->h ? 0 : j0 + 1;
+	filter4(s, L, i0, i1, j0, j1, a, b, out);
+}
+
+/* voxelizer.frag:27-36: returns 0 when the fragment is discarded (alpha < 0.5), else 1 and the packed colour */
+static int sample_colour(const orc_texset *s, const orc_tex *tex, const orc_uvmap *m, int32_t px, int32_t py, uint32_t *rgb) {
+	const double cx = (double)px + 0.5, cy = (double)py + 0.5;
+	const double u = fma(m->dudx, cx - m->x0, fma(m->dudy, cy - m->y0, m->u0));
+	const double v = fma(m->dvdx, cx - m->x0, fma(m->dvdy, cy - m->y0, m->v0));
+	float c[4];
+	sample_level(s, &tex->lv[m->hi], u, v, c);
+	if (m->lo != m->hi) {
+		float d[4];
+		sample_level(s, &tex->lv[m->lo], u, v, d);
+		for (int k = 0; k < 4; ++k)
+			c[k] = lerpf(c[k], d[k], m->delta);
+	}
+	if (c[3] < 0.5f)
+		return 0;
+	*rgb = (uint32_t)pack_unorm8(c[0]) | ((uint32_t)pack_unorm8(c[1]) << 8) | ((uint32_t)pack_unorm8(c[2]) << 16);
+	return 1;
+}
+
+uint32_t orc_debug_sample(const orc_texset *s, uint32_t tex, const float *p0, const float *p1, const float *p2, const float *uv0,
+                          const float *uv1, const float *uv2, uint32_t level, int32_t px, int32_t py, uint32_t lod_out[3]) {
+	orc_tri t;
+	orc_tri_setup(p0, p1, p2, 1u << level, ORC_CENTER, &t);
+	const float *const p[3] = {p0, p1, p2}, *const uv[3] = {uv0, uv1, uv2};
+	orc_uvmap m;
+	uvmap_setup(s, &s->t[tex], p, uv, t.axis, 1u << level, &m);
+	if (lod_out)
+		lod_out[0] = m.hi, lod_out[1] = m.lo, lod_out[2] = (uint32_t)(m.delta * 256.0f);
+	uint32_t rgb = 0;
+	return sample_colour(s, &s->t[tex], &m, px, py, &rgb) ? (0xff000000u | rgb) : 0u;
+}
+
+int64_t orc_voxelize_textured(const void *positions, uint32_t pos_stride_bytes, const void *texcoords, uint32_t uv_stride_bytes,
+                              const uint32_t *indices, const orc_draw *draws, uint32_t n_draws, const orc_texset *texset,
+                              uint32_t level, int mode, const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out,
+                              int64_t cap, int nthreads) {
 	if (level < 1 || level > 16 || (mode != ORC_CENTER && mode != ORC_CONSERVATIVE_EXACT && mode != ORC_CONSERVATIVE_DILATE))
 		return -1;
 	for (uint32_t d = 0; d < n_draws; ++d)
-		if (draws[d].texture_id != 0xffffffffu)
-			return -2; /* textured materials are outside the built path */
+		if (draws[d].texture_id != 0xffffffffu && (!texset || !texcoords || draws[d].texture_id >= texset->n))
+			return -2; /* a textured draw needs texture coordinates and its texture */
 	const uint32_t res = 1u << level;
-	const unsigned char *pbase = (const unsigned char *)positions;
+	const unsigned char *pbase = (const unsigned char *)positions, *tbase = (const unsigned char *)texcoords;
 	int64_t counter = 0; /* uCounter (voxelizer.frag:5,37) */
 	if (nthreads < 1)
 		nthreads = 1;
 
 	for (uint32_t d = 0; d < n_draws; ++d) { /* Scene::CmdDraw: one draw per material (Scene.cpp:450-463) */
 		const uint32_t ntri = draws[d].index_count / 3u;
-		const uint32_t colour = draws[d].albedo_rgba8 & 0xffffffu;
+		const uint32_t albedo = draws[d].albedo_rgba8 & 0xffffffu;
+		const orc_tex *tex = draws[d].texture_id != 0xffffffffu ? &texset->t[draws[d].texture_id] : NULL;
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) if (nthreads > 1)
 		for (uint32_t k = 0; k < ntri; ++k) {
 			const uint32_t *ix = indices + draws[d].first_index + 3u * k;
+			const float *const p[3] = {(const float *)(pbase + (size_t)ix[0] * pos_stride_bytes),
+			                           (const float *)(pbase + (size_t)ix[1] * pos_stride_bytes),
+			                           (const float *)(pbase + (size_t)ix[2] * pos_stride_bytes)};
 			orc_tri t;
-			orc_tri_setup((const float *)(pbase + (size_t)ix[0] * pos_stride_bytes),
-			              (const float *)(pbase + (size_t)ix[1] * pos_stride_bytes),
-			              (const float *)(pbase + (size_t)ix[2] * pos_stride_bytes), res, mode, &t);
+			orc_tri_setup(p[0], p[1], p[2], res, mode, &t);
 			if (!t.valid)
 				continue;
 			if (t.area2 == 0 && mode != ORC_CONSERVATIVE_EXACT)
 				continue;
 			orc_plane pl;
 			plane_setup(&t, &pl);
+			orc_uvmap um;
+			if (tex) {
+				const float *const uv[3] = {(const float *)(tbase + (size_t)ix[0] * uv_stride_bytes),
+				                            (const float *)(tbase + (size_t)ix[1] * uv_stride_bytes),
+				                            (const float *)(tbase + (size_t)ix[2] * uv_stride_bytes)};
+				uvmap_setup(texset, tex, p, uv, t.axis, res, &um);
+			}
 			int32_t xmin = t.X[0], xmax = t.X[0], ymin = t.Y[0], ymax = t.Y[0];
 			for (int i = 1; i < 3; ++i) {
 				if (t.X[i] < xmin) xmin = t.X[i];
@@ -373,6 +642,9 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
 						    v[1] >= shard_hi[1] || v[2] < shard_lo[2] || v[2] >= shard_hi[2])
 							continue;
 					}
+					uint32_t colour = albedo; /* voxelizer.frag:35 */
+					if (tex && !sample_colour(texset, tex, &um, px, py, &colour))
+						continue; /* voxelizer.frag:29-30 discard */
 					int64_t cur; /* uint cur = atomicAdd(uCounter, 1u)  (voxelizer.frag:37) */
 					if (nthreads > 1)
 						cur = __atomic_fetch_add(&counter, 1, __ATOMIC_RELAXED);
@@ -386,6 +658,14 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
 		}
 	}
 	return counter;
+}
+
+int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uint32_t *indices,
+                     const orc_draw *draws, uint32_t n_draws, uint32_t level, int mode,
+                     const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out, int64_t cap,
+                     int nthreads) {
+	return orc_voxelize_textured(positions, pos_stride_bytes, NULL, 0, indices, draws, n_draws, NULL, level, mode, shard_lo,
+	                             shard_hi, out, cap, nthreads);
 }
 
 /* Debug views used by the SPIR-V cross-checks (tests/golden/make_spirv_golden.py): the geometry-stage

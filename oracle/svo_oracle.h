@@ -61,6 +61,29 @@ int64_t orc_voxelize(const void *positions, uint32_t pos_stride_bytes, const uin
                      const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out, int64_t cap,
                      int nthreads);
 
+/*
+ * Textured materials (voxelizer.frag:27-36).  A texture is its base level as stbi_load(..., 4) returns it
+ * (Scene.cpp:247): RGBA8, sRGB-encoded colour, row 0 first, tight rows.  orc_texset_create builds the mip
+ * chains the way Scene::load_textures does (linear blits, Scene.cpp:262-296).  texcoords: 2 floats per
+ * vertex with a byte stride (the reference's Vertex: positions + 12, stride 20).
+ */
+typedef struct {
+	const uint8_t *rgba8;
+	uint32_t width, height;
+} orc_texture;
+typedef struct orc_texset orc_texset;
+orc_texset *orc_texset_create(const orc_texture *tex, uint32_t n);
+void orc_texset_destroy(orc_texset *s);
+/* level data of one texture (debug / tests); returns the level count or -1 */
+int orc_texset_level(const orc_texset *s, uint32_t tex, uint32_t level, uint32_t *w, uint32_t *h, const uint8_t **data);
+int64_t orc_voxelize_textured(const void *positions, uint32_t pos_stride_bytes, const void *texcoords, uint32_t uv_stride_bytes,
+                              const uint32_t *indices, const orc_draw *draws, uint32_t n_draws, const orc_texset *texset,
+                              uint32_t level, int mode, const uint32_t *shard_lo, const uint32_t *shard_hi, orc_frag *out,
+                              int64_t cap, int nthreads);
+/* colour of pixel (px,py) of one textured triangle: 0xff000000 | rgb, or 0 when discarded; lod_out = {hi, lo, delta*256} */
+uint32_t orc_debug_sample(const orc_texset *s, uint32_t tex, const float *p0, const float *p1, const float *p2, const float *uv0,
+                          const float *uv1, const float *uv2, uint32_t level, int32_t px, int32_t py, uint32_t lod_out[3]);
+
 /* Debug views for the SPIR-V cross-checks: geometry-stage outputs {axis, gAABB[4], gDepthRange[2]} + snapped window
  * coordinates of one triangle; and its covered pixels with the pinned fp64 depth (before voxelizer.frag). */
 void orc_debug_tri_setup(const float *p0, const float *p1, const float *p2, uint32_t level, uint32_t out_axis_aabb_zr[7],

@@ -38,10 +38,16 @@ class svo_draw(C.Structure):
                 ("albedo_rgba8", C.c_uint32)]
 
 
+class svo_texture(C.Structure):
+    _fields_ = [("rgba8", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
 class svo_mesh(C.Structure):
     _fields_ = [("positions", C.c_void_p), ("position_stride_bytes", C.c_uint32), ("on_device", C.c_uint32),
                 ("indices", C.c_void_p), ("n_vertices", C.c_uint64), ("n_indices", C.c_uint64),
-                ("draws", C.POINTER(svo_draw)), ("n_draws", C.c_uint32)]
+                ("draws", C.POINTER(svo_draw)), ("n_draws", C.c_uint32),
+                ("n_textures", C.c_uint32), ("textures", C.POINTER(svo_texture)),
+                ("texcoords", C.c_void_p), ("texcoord_stride_bytes", C.c_uint32)]
 
 
 class svo_shard(C.Structure):
@@ -58,6 +64,7 @@ SYMBOLS = [
     ("svo_scene_create", C.c_int, [C.POINTER(svo_mesh), C.c_int, _P, C.POINTER(_P)]),
     ("svo_scene_destroy", None, [_P]),
     ("svo_scene_triangle_count", C.c_uint64, [_P]),
+    ("svo_scene_texture_level", C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_P)]),
     ("svo_voxelizer_create", C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(svo_shard), _P, C.POINTER(_P)]),
     ("svo_voxelizer_create_from_fragments", C.c_int, [C.c_int, C.c_uint32, _P, C.c_uint64, C.c_int, _P, C.POINTER(_P)]),
     ("svo_voxelizer_create_windowed", C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P, C.POINTER(_P)]),
@@ -184,17 +191,22 @@ def _stream_ptr(stream) -> int:
 
 class Scene:
     """Mesh hand-off standing in for the reference Scene (src/Scene.hpp): vertex/index buffers + draw list on the
-    device.  `positions` may be [V,3] (tight) or [V,5] (pos+uv, the reference Vertex of src/Scene.cpp:16-19)."""
+    device.  `positions` may be [V,3] (tight) or [V,5] (pos+uv, the reference Vertex of src/Scene.cpp:16-19).
+    Textured materials (src/Scene.cpp:225-300): `textures` = list of uint8 [H,W,4] sRGB RGBA images (what stbi_load
+    returns), `texcoords` = float32 [V,2] (taken from columns 3:5 of a [V,5] vertex array when omitted)."""
 
     def __init__(self):
         self._h = None
 
     @staticmethod
-    def Create(mesh_or_positions, indices=None, draws=None, device: int = 0, stream=None, lib: Library | None = None):
+    def Create(mesh_or_positions, indices=None, draws=None, device: int = 0, stream=None, lib: Library | None = None,
+               texcoords=None, textures=None):
         lib = lib or get_library()
         if indices is None:
             m = mesh_or_positions
             positions, indices, draws = m.positions, m.indices, m.draws
+            texcoords = getattr(m, "texcoords", None) if texcoords is None else texcoords
+            textures = getattr(m, "textures", None) if textures is None else textures
         else:
             positions = mesh_or_positions
         self = Scene()
@@ -208,6 +220,21 @@ class Scene:
             raise ValueError("positions must be [V, >=3] float32")
         m = svo_mesh(self._positions.ctypes.data, self._positions.shape[1] * 4, 0, self._indices.ctypes.data,
                      len(self._positions), len(self._indices), self._draws, len(d))
+        if textures:
+            self._textures = [np.ascontiguousarray(t, dtype=np.uint8) for t in textures]
+            for t in self._textures:
+                if t.ndim != 3 or t.shape[2] != 4:
+                    raise ValueError("textures must be uint8 [H, W, 4]")
+            self._tex_arr = (svo_texture * len(self._textures))(*[svo_texture(t.ctypes.data, t.shape[1], t.shape[0])
+                                                                   for t in self._textures])
+            m.n_textures, m.textures = len(self._textures), self._tex_arr
+            if texcoords is not None:
+                self._texcoords = np.ascontiguousarray(texcoords, dtype=np.float32)
+                if self._texcoords.shape != (len(self._positions), 2):
+                    raise ValueError("texcoords must be [V, 2] float32")
+                m.texcoords, m.texcoord_stride_bytes = self._texcoords.ctypes.data, 8
+            elif self._positions.shape[1] >= 5:  # the reference's Vertex {vec3 pos; vec2 uv}
+                m.texcoords, m.texcoord_stride_bytes = self._positions.ctypes.data + 12, self._positions.shape[1] * 4
         h = _P()
         lib.check(lib.dll.svo_scene_create(C.byref(m), device, _stream_ptr(stream), C.byref(h)))
         self._h = h
@@ -231,6 +258,21 @@ class Scene:
 
     def GetTriangleCount(self) -> int:
         return int(self.lib.dll.svo_scene_triangle_count(self._h))
+
+    def texture_level_to_host(self, texture: int, level: int) -> np.ndarray:
+        """uint8 [H,W,4] copy of one mip level as built on the device (Scene.cpp:290-295)."""
+        w, h, d = C.c_uint32(), C.c_uint32(), _P()
+        rc = self.lib.dll.svo_scene_texture_level(self._h, texture, level, C.byref(w), C.byref(h), C.byref(d))
+        if rc < 0:
+            self.lib.check(rc)
+        return self.lib.to_host(d.value, np.uint8, w.value * h.value * 4, self.device).reshape(h.value, w.value, 4)
+
+    def texture_level_count(self, texture: int) -> int:
+        w, h, d = C.c_uint32(), C.c_uint32(), _P()
+        rc = self.lib.dll.svo_scene_texture_level(self._h, texture, 0, C.byref(w), C.byref(h), C.byref(d))
+        if rc < 0:
+            self.lib.check(rc)
+        return rc
 
     def Destroy(self):
         if self._h:

@@ -13,6 +13,7 @@
 #pragma once
 #include "scan.cuh"
 #include "svo_math.cuh"
+#include "texture.cuh"
 
 namespace svo {
 
@@ -22,6 +23,7 @@ constexpr int EMIT_BLOCK = 256, EMIT_ITEMS = 8, EMIT_TILE = EMIT_BLOCK * EMIT_IT
 
 struct DrawRec {
 	uint32_t first_index, tri_base, tri_count, rgb;
+	uint32_t tex; // 0xffffffff = untextured (voxelizer.frag:35)
 };
 struct SceneView {
 	const unsigned char *pos;
@@ -30,6 +32,9 @@ struct SceneView {
 	const DrawRec *draws;
 	uint32_t n_draws;
 	uint64_t n_tri;
+	const unsigned char *uv; // texture coordinates (2 floats per vertex), only read for textured draws
+	uint32_t uv_stride;
+	TexView tex;
 };
 struct RasterParams {
 	uint32_t res;       // 1 << level (full grid)
@@ -47,18 +52,43 @@ SVO_DEV uint32_t find_draw(const SceneView &sv, uint64_t t) {
 	return lo;
 }
 
-SVO_DEV bool load_and_setup(const SceneView &sv, const RasterParams &rp, uint64_t t, TriSetup &ts, uint32_t &rgb) {
+// How a triangle's fragments get their colour: the draw's albedo, or a texture sample through um.
+// alpha = the texture has texels that can fail the alpha test (voxelizer.frag:29-30), so fragments may be discarded.
+struct TriShade {
+	uint32_t rgb;
+	bool textured, alpha;
+	UvMap um;
+};
+
+// TEX = the scene has textured draws (the untextured instantiation carries no texture code at all)
+template <bool TEX>
+SVO_DEV bool load_and_setup(const SceneView &sv, const RasterParams &rp, uint64_t t, TriSetup &ts, TriShade &sh) {
 	const uint32_t d = find_draw(sv, t);
 	const DrawRec dr = sv.draws[d];
 	const uint32_t *ix = sv.idx + dr.first_index + 3u * (uint32_t)(t - dr.tri_base);
 	float p[3][3];
+	uint32_t vi[3];
 #pragma unroll
 	for (int i = 0; i < 3; ++i) {
-		const float *v = reinterpret_cast<const float *>(sv.pos + (size_t)__ldg(ix + i) * sv.stride);
+		vi[i] = __ldg(ix + i);
+		const float *v = reinterpret_cast<const float *>(sv.pos + (size_t)vi[i] * sv.stride);
 		p[i][0] = __ldg(v), p[i][1] = __ldg(v + 1), p[i][2] = __ldg(v + 2);
 	}
-	rgb = dr.rgb;
-	return tri_setup(p[0], p[1], p[2], rp.res, rp.mode, rp.sb, ts);
+	sh.rgb = dr.rgb;
+	sh.textured = sh.alpha = false;
+	const bool ok = tri_setup(p[0], p[1], p[2], rp.res, rp.mode, rp.sb, ts);
+	if (TEX && ok && dr.tex != 0xffffffffu) {
+		float uv[3][2];
+#pragma unroll
+		for (int i = 0; i < 3; ++i) {
+			const float *v = reinterpret_cast<const float *>(sv.uv + (size_t)vi[i] * sv.uv_stride);
+			uv[i][0] = __ldg(v), uv[i][1] = __ldg(v + 1);
+		}
+		uvmap_setup(sv.tex, dr.tex, p, uv, ts.axis, rp.res, sh.um);
+		sh.textured = true;
+		sh.alpha = sv.tex.desc[dr.tex].has_alpha != 0u;
+	}
+	return ok;
 }
 
 SVO_DEV uint64_t make_fragment(const TriSetup &ts, const RasterParams &rp, int32_t px, int32_t py, uint32_t uz, uint32_t rgb) {
@@ -70,21 +100,25 @@ SVO_DEV uint64_t make_fragment(const TriSetup &ts, const RasterParams &rp, int32
 // ---- pass 1: classify + count small ------------------------------------------------------------------
 // cnt_small[t]  = fragments of a small triangle (0 for large / culled)
 // packed[t]     = (is_large << 40) | rows of a large triangle
+// Triangles of an alpha-tested texture always take the small path: their fragment count depends on the samples
+// (voxelizer.frag:29-30 discards before the counter), which the span arithmetic of the large path cannot know.
+template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
     k_classify_count(SceneView sv, RasterParams rp, uint32_t *__restrict__ cnt_small, uint64_t *__restrict__ packed) {
 	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
 	if (t >= sv.n_tri) return;
 	TriSetup ts;
-	uint32_t rgb;
+	TriShade sh;
 	uint32_t cnt = 0;
 	uint64_t pk = 0;
-	if (load_and_setup(sv, rp, t, ts, rgb)) {
-		if (ts.full_area <= SMALL_AREA) {
+	if (load_and_setup<TEX>(sv, rp, t, ts, sh)) {
+		if (ts.full_area <= SMALL_AREA || (TEX && sh.alpha)) {
 			for (int32_t py = ts.py0; py <= ts.py1; ++py)
 				for (int32_t px = ts.px0; px <= ts.px1; ++px)
 					if (pixel_covered(ts, px, py)) {
-						uint32_t uz;
-						if ((!ts.cull_depth && !ts.clip_z) || pixel_fragment(ts, rp.res, px, py, uz)) ++cnt;
+						uint32_t uz, c;
+						if ((!ts.cull_depth && !ts.clip_z) || pixel_fragment(ts, rp.res, px, py, uz))
+							if (!(TEX && sh.alpha) || sample_colour(sv.tex, sh.um, px, py, c)) ++cnt;
 					}
 		} else
 			pk = (1ull << 40) | (uint64_t)(ts.py1 - ts.py0 + 1);
@@ -99,7 +133,7 @@ struct LargeTri {
 	uint32_t rgb;
 	uint32_t tri;      // triangle id
 	uint32_t row_base; // first row in the (sparse) row arrays
-	uint32_t pad;
+	uint32_t textured; // colour comes from luv[li] (textured scenes only)
 };
 
 // gather the large triangles into a dense list (order = triangle order)
@@ -117,19 +151,22 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 }
 
 // one warp per large triangle: exact row spans.  row_pk[r] = (nonempty << 40) | len ; row_x0[r] = first pixel
+template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
-    k_large_rows(SceneView sv, RasterParams rp, uint32_t n_large, LargeTri *__restrict__ large, uint64_t *__restrict__ row_pk,
-                 uint32_t *__restrict__ row_x0) {
+    k_large_rows(SceneView sv, RasterParams rp, uint32_t n_large, LargeTri *__restrict__ large, UvMap *__restrict__ luv,
+                 uint64_t *__restrict__ row_pk, uint32_t *__restrict__ row_x0) {
 	const uint32_t li = (blockIdx.x * RASTER_BLOCK + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (li >= n_large) return; // whole warp leaves together
 	LargeTri &lt = large[li];
 	TriSetup ts;
-	uint32_t rgb;
-	load_and_setup(sv, rp, lt.tri, ts, rgb); // true by construction (classified large)
+	TriShade sh;
+	load_and_setup<TEX>(sv, rp, lt.tri, ts, sh); // true by construction (classified large)
 	if (lane == 0) {
 		lt.ts = ts;
-		lt.rgb = rgb;
+		lt.rgb = sh.rgb;
+		lt.textured = sh.textured ? 1u : 0u;
+		if (TEX && sh.textured) luv[li] = sh.um;
 	}
 	const int32_t h = ts.py1 - ts.py0 + 1;
 	for (int32_t r = lane; r < h; r += 32) {
@@ -175,6 +212,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 }
 
 // ---- pass 2: emit ---------------------------------------------------------------------------------------
+template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
     k_emit_small(SceneView sv, RasterParams rp, const uint64_t *__restrict__ tri_off, uint64_t *__restrict__ frags) {
 	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
@@ -182,14 +220,15 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	const uint64_t o0 = tri_off[t], o1 = tri_off[t + 1];
 	if (o0 == o1) return; // large, culled or empty
 	TriSetup ts;
-	uint32_t rgb;
-	if (!load_and_setup(sv, rp, t, ts, rgb)) return;
+	TriShade sh;
+	if (!load_and_setup<TEX>(sv, rp, t, ts, sh)) return;
 	uint64_t o = o0;
 	for (int32_t py = ts.py0; py <= ts.py1; ++py)
 		for (int32_t px = ts.px0; px <= ts.px1; ++px)
 			if (pixel_covered(ts, px, py)) {
-				uint32_t uz;
-				if (pixel_fragment(ts, rp.res, px, py, uz)) frags[o++] = make_fragment(ts, rp, px, py, uz, rgb);
+				uint32_t uz, rgb = sh.rgb;
+				if (pixel_fragment(ts, rp.res, px, py, uz))
+					if (!(TEX && sh.textured) || sample_colour(sv.tex, sh.um, px, py, rgb)) frags[o++] = make_fragment(ts, rp, px, py, uz, rgb);
 			}
 }
 
@@ -197,9 +236,10 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 // consecutive fragments, a thread EMIT_ITEMS consecutive ones: one search per thread, then x advances by
 // incrementing the Morton-spread coordinate, the depth plane's row term is hoisted, and the fragments leave in
 // 16-byte stores.
+template <bool TEX>
 __global__ void __launch_bounds__(EMIT_BLOCK)
-    k_emit_large(RasterParams rp, const LargeTri *__restrict__ large, DenseRows rows, uint32_t n_rows, uint64_t n_frag_large,
-                 uint64_t *__restrict__ frags /* already offset to the large region */) {
+    k_emit_large(RasterParams rp, TexView tv, const LargeTri *__restrict__ large, const UvMap *__restrict__ luv, DenseRows rows,
+                 uint32_t n_rows, uint64_t n_frag_large, uint64_t *__restrict__ frags /* already offset to the large region */) {
 	__shared__ uint32_t s_off[EMIT_TILE + 2];
 	__shared__ uint32_t s_first;
 	const int lane = threadIdx.x & 31;
@@ -241,7 +281,8 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 	double row_term = 0.0;
 	uint64_t m_row = 0, m_x = 0;
 	uint32_t shx = 0, shz = 0, oz = 0, rgb = 0;
-	int32_t px = 0;
+	int32_t px = 0, py_tex = 0;
+	const UvMap *um = nullptr; // non-null: the row belongs to a textured triangle
 	--lo;
 #pragma unroll
 	for (int k = 0; k < EMIT_ITEMS; ++k) {
@@ -266,7 +307,12 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 				m_row = part1by2((uint32_t)py - rp.origin[wy]) << wy;
 				m_x = part1by2((uint32_t)px - rp.origin[wx]);
 				rgb = lt->rgb & 0xffffffu;
+				if (TEX) {
+					um = lt->textured ? &luv[rows.li[r]] : nullptr;
+					py_tex = py;
+				}
 			}
+			if (TEX && um) sample_colour(tv, *um, px, py_tex, rgb); // opaque texture (alpha-tested ones never come here)
 			const uint32_t uz = pixel_depth_row(lt->ts, rp.res, px, row_term);
 			const uint64_t m = (m_x << shx) | (part1by2(uz - oz) << shz) | m_row;
 			out[k] = (m << 24) | (uint64_t)rgb;

@@ -7,6 +7,8 @@
 
 #include <stdarg.h>
 
+#include <algorithm>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -95,6 +97,14 @@ struct svo_scene {
 	DevBuf<uint32_t> idx;
 	DevBuf<DrawRec> d_draws;
 	uint64_t n_vertices = 0;
+	// textured materials
+	bool textured = false; // some draw samples a texture: the voxelizer runs its TEX kernel variants
+	DevBuf<unsigned char> uv;
+	DevBuf<uint32_t> texels;
+	DevBuf<TexDesc> tex_desc;
+	DevBuf<float> tex_decode, tex_enc;
+	DevBuf<double> tex_lod;
+	std::vector<TexDesc> h_desc;
 };
 
 struct svo_voxelizer {
@@ -107,6 +117,7 @@ struct svo_voxelizer {
 	uint32_t n_large = 0, n_rows = 0;
 	DevBuf<uint64_t> tri_off; // n_tri + 1, small-class fragment offsets
 	DevBuf<LargeTri> large;
+	DevBuf<UvMap> large_uv; // textured scenes: texture-coordinate map of every large triangle
 	DevBuf<uint32_t> row_off, row_xy, row_li;
 	DevBuf<uint64_t> frags;
 	DevBuf<uint64_t> ext_frags; // svo_voxelizer_create_from_fragments: the caller's fragment list (voxelize re-copies it)
@@ -148,6 +159,74 @@ static int fail(int code, const char *msg) {
 	return code;
 }
 
+// Scene::load_textures (src/Scene.cpp:225-300): upload the base levels, build the mip chains on the device with
+// linear blits, and the lookup tables of texture.cuh.  Synchronous (host staging buffers live on this stack).
+static double srgb_to_linear(double x) { return x <= 0.04045 ? x / 12.92 : std::pow((x + 0.055) / 1.055, 2.4); }
+static int upload_textures(svo_scene *sc, const svo_mesh *mesh, cudaStream_t s) {
+	const uint32_t n = mesh->n_textures;
+	std::vector<TexDesc> desc(n);
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		const svo_texture &t = mesh->textures[i];
+		if (!t.rgba8 || t.width == 0 || t.height == 0 || t.width > TEX_MAX_SIZE || t.height > TEX_MAX_SIZE)
+			return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: texture must be 1..16384 texels wide and high");
+		TexDesc &d = desc[i];
+		d = TexDesc{};
+		d.w = t.width, d.h = t.height;
+		uint32_t levels = 1; // ImageBase::QueryMipLevel (dep/MyVK/include/myvk/ImageBase.hpp:10-17,49)
+		while ((t.width | t.height) >> levels) ++levels;
+		d.levels = levels;
+		for (uint32_t l = 0; l < levels; ++l) {
+			d.off[l] = (uint32_t)total;
+			total += (uint64_t)std::max(t.width >> l, 1u) * std::max(t.height >> l, 1u);
+		}
+		if (total >= (1ull << 32)) return fail(SVO_ERR_CAPACITY, "svo_scene_create: more than 2^32 texels");
+	}
+	std::vector<float> decode(256), enc(256);
+	std::vector<double> lod(128);
+	for (int c = 0; c < 256; ++c) {
+		decode[c] = (float)srgb_to_linear((double)c / 255.0);
+		enc[c] = c ? (float)srgb_to_linear(((double)c - 0.5) / 255.0) : 0.0f;
+	}
+	for (int k = 0; k < 128; ++k) lod[k] = std::exp2((double)k / 128.0);
+	SVO_TRY(sc->texels.alloc(total, s));
+	SVO_TRY(sc->tex_desc.alloc(n, s));
+	SVO_TRY(sc->tex_decode.alloc(256, s));
+	SVO_TRY(sc->tex_enc.alloc(256, s));
+	SVO_TRY(sc->tex_lod.alloc(128, s));
+	SVO_CUDA_TRY(cudaMemcpyAsync(sc->tex_desc.p, desc.data(), n * sizeof(TexDesc), cudaMemcpyHostToDevice, s));
+	SVO_CUDA_TRY(cudaMemcpyAsync(sc->tex_decode.p, decode.data(), 256 * sizeof(float), cudaMemcpyHostToDevice, s));
+	SVO_CUDA_TRY(cudaMemcpyAsync(sc->tex_enc.p, enc.data(), 256 * sizeof(float), cudaMemcpyHostToDevice, s));
+	SVO_CUDA_TRY(cudaMemcpyAsync(sc->tex_lod.p, lod.data(), 128 * sizeof(double), cudaMemcpyHostToDevice, s));
+	TexView tv{sc->texels.p, sc->tex_desc.p, sc->tex_decode.p, sc->tex_enc.p, sc->tex_lod.p, n};
+	for (uint32_t i = 0; i < n; ++i) {
+		const TexDesc &d = desc[i];
+		SVO_CUDA_TRY(cudaMemcpyAsync(sc->texels.p + d.off[0], mesh->textures[i].rgba8, (uint64_t)d.w * d.h * 4, cudaMemcpyHostToDevice, s));
+		SVO_LAUNCH_INDEP(std::min<uint32_t>(div_up((uint64_t)d.w * d.h, 256), 1024u), 256, s, k_tex_has_alpha, (const uint32_t *)sc->texels.p,
+		                 sc->tex_desc.p, i);
+		for (uint32_t l = 1; l < d.levels; ++l) {
+			const uint32_t ws = std::max(d.w >> (l - 1), 1u), hs = std::max(d.h >> (l - 1), 1u);
+			const uint32_t wd = std::max(d.w >> l, 1u), hd = std::max(d.h >> l, 1u);
+			SVO_LAUNCH_INDEP(div_up((uint64_t)wd * hd, 256), 256, s, k_mip_downsample, tv, sc->texels.p, d.off[l - 1], ws, hs, d.off[l], wd, hd);
+		}
+	}
+	SVO_CUDA_TRY(cudaGetLastError());
+	// texture coordinates
+	if (mesh->on_device) {
+		sc->view.uv = (const unsigned char *)mesh->texcoords;
+	} else {
+		const uint64_t bytes = mesh->n_vertices ? (mesh->n_vertices - 1) * (uint64_t)mesh->texcoord_stride_bytes + 8 : 0;
+		SVO_TRY(sc->uv.alloc(bytes, s));
+		if (bytes) SVO_CUDA_TRY(cudaMemcpyAsync(sc->uv.p, mesh->texcoords, bytes, cudaMemcpyHostToDevice, s));
+		sc->view.uv = sc->uv.p;
+	}
+	sc->view.uv_stride = mesh->texcoord_stride_bytes;
+	sc->view.tex = tv;
+	sc->h_desc = desc;
+	SVO_CUDA_TRY(cudaStreamSynchronize(s));
+	return SVO_OK;
+}
+
 extern "C" {
 
 const char *svo_last_error(void) { return get_error(); }
@@ -186,8 +265,12 @@ int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene *
 	for (uint32_t d = 0; d < mesh->n_draws; ++d) {
 		const svo_draw &dr = mesh->draws[d];
 		if (dr.texture_id != 0xffffffffu) {
-			delete sc;
-			return fail(SVO_ERR_UNSUPPORTED, "textured draws are not on the built path (SURVEY.md section 8 row f2)");
+			if (dr.texture_id >= mesh->n_textures || !mesh->textures || !mesh->texcoords || mesh->texcoord_stride_bytes < 8 ||
+			    (mesh->texcoord_stride_bytes & 3)) {
+				delete sc;
+				return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: a textured draw needs its texture and texture coordinates");
+			}
+			if (dr.index_count) sc->textured = true;
 		}
 		if ((uint64_t)dr.first_index + dr.index_count > mesh->n_indices || dr.index_count % 3) {
 			delete sc;
@@ -199,6 +282,7 @@ int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene *
 		r.tri_base = (uint32_t)tri_base;
 		r.tri_count = dr.index_count / 3;
 		r.rgb = dr.albedo_rgba8 & 0xffffffu;
+		r.tex = dr.texture_id;
 		sc->draws.push_back(r);
 		tri_base += r.tri_count;
 	}
@@ -226,6 +310,7 @@ int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene *
 			sc->view.pos = sc->pos.p;
 			sc->view.idx = sc->idx.p;
 		}
+		if (sc->textured && (rc = upload_textures(sc, mesh, s))) break;
 		if ((rc = sc->d_draws.alloc(sc->draws.size(), s))) break;
 		if (!sc->draws.empty() && cudaMemcpyAsync(sc->d_draws.p, sc->draws.data(), sc->draws.size() * sizeof(DrawRec),
 		                                          cudaMemcpyHostToDevice, s) != cudaSuccess) {
@@ -253,9 +338,21 @@ void svo_scene_destroy(svo_scene *sc) {
 	sc->pos.release(0);
 	sc->idx.release(0);
 	sc->d_draws.release(0);
+	sc->uv.release(0), sc->texels.release(0), sc->tex_desc.release(0), sc->tex_decode.release(0), sc->tex_enc.release(0);
+	sc->tex_lod.release(0);
 	delete sc;
 }
 uint64_t svo_scene_triangle_count(const svo_scene *sc) { return sc ? sc->view.n_tri : 0; }
+int svo_scene_texture_level(const svo_scene *sc, uint32_t texture, uint32_t level, uint32_t *width, uint32_t *height,
+                            const uint32_t **d_texels) {
+	if (!sc || !width || !height || !d_texels) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_texture_level: null argument");
+	if (texture >= sc->h_desc.size() || level >= sc->h_desc[texture].levels)
+		return fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_texture_level: no such texture level");
+	const TexDesc &d = sc->h_desc[texture];
+	*width = std::max(d.w >> level, 1u), *height = std::max(d.h >> level, 1u);
+	*d_texels = sc->texels.p + d.off[level];
+	return (int)d.levels;
+}
 
 // ------------------------------------------------------------------------------------------------------
 static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, const uint32_t *win_lo,
@@ -325,7 +422,10 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 		}
 		if ((rc = cnt_small.alloc(T, s)) || (rc = packed.alloc(T, s)) || (rc = lprefix.alloc(T + 1, s))) break;
 		const uint32_t tgrid = div_up(T, RASTER_BLOCK);
-		SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count, scene->view, v->rp, cnt_small.p, packed.p);
+		if (scene->textured)
+			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count<true>, scene->view, v->rp, cnt_small.p, packed.p);
+		else
+			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count<false>, scene->view, v->rp, cnt_small.p, packed.p);
 		if ((rc = exclusive_scan((const uint32_t *)cnt_small.p, v->tri_off.p, T, ss, s))) break;
 		// (is_large << 40 | rows) scanned as one 64-bit word: large-triangle index and first row together
 		if ((rc = exclusive_scan((const uint64_t *)packed.p, lprefix.p, T, ss, s))) break;
@@ -350,7 +450,13 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 				break;
 			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_large_collect, T, (const uint64_t *)packed.p, (const uint64_t *)lprefix.p, v->large.p);
 			const uint32_t wgrid = div_up((uint64_t)v->n_large * 32, RASTER_BLOCK);
-			SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_large_rows, scene->view, v->rp, v->n_large, v->large.p, row_pk.p, row_x0.p);
+			if (scene->textured) {
+				if ((rc = v->large_uv.alloc(v->n_large, s))) break;
+				SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_large_rows<true>, scene->view, v->rp, v->n_large, v->large.p, v->large_uv.p,
+				                 row_pk.p, row_x0.p);
+			} else
+				SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_large_rows<false>, scene->view, v->rp, v->n_large, v->large.p, (UvMap *)nullptr,
+				                 row_pk.p, row_x0.p);
 			if ((rc = exclusive_scan((const uint64_t *)row_pk.p, rprefix.p, rows_sparse, ss, s))) break;
 			uint64_t h_rp = 0;
 			if (cudaMemcpyAsync(&h_rp, rprefix.p + rows_sparse, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
@@ -418,6 +524,7 @@ int svo_voxelizer_create_from_fragments(int device, uint32_t level, const uint64
 void svo_voxelizer_destroy(svo_voxelizer *v) {
 	if (!v) return;
 	DeviceGuard guard(v->device);
+	v->large_uv.release(0);
 	v->tri_off.release(0), v->large.release(0), v->row_off.release(0), v->row_xy.release(0), v->row_li.release(0), v->frags.release(0);
 	v->ext_frags.release(0);
 	v->t_raster.destroy();
@@ -437,13 +544,23 @@ int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
 	}
 	const SceneView &sv = v->scene->view;
 	SVO_CUDA_TRY(cudaEventRecord(v->t_raster.a, s));
+	const bool tex = v->scene->textured;
 	if (v->n_frag_small) {
-		SVO_LAUNCH_INDEP(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, s, k_emit_small, sv, v->rp, (const uint64_t *)v->tri_off.p, v->frags.p);
+		if (tex)
+			SVO_LAUNCH_INDEP(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, s, k_emit_small<true>, sv, v->rp, (const uint64_t *)v->tri_off.p,
+			                 v->frags.p);
+		else
+			SVO_LAUNCH_INDEP(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, s, k_emit_small<false>, sv, v->rp, (const uint64_t *)v->tri_off.p,
+			                 v->frags.p);
 	}
 	if (v->n_frag_large) {
 		DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
-		SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large, v->rp, (const LargeTri *)v->large.p, dr, v->n_rows,
-		           v->n_frag_large, v->frags.p + v->n_frag_small);
+		if (tex)
+			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<true>, v->rp, sv.tex, (const LargeTri *)v->large.p,
+			           (const UvMap *)v->large_uv.p, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
+		else
+			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<false>, v->rp, sv.tex, (const LargeTri *)v->large.p,
+			           (const UvMap *)nullptr, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
 	}
 	SVO_CUDA_TRY(cudaEventRecord(v->t_raster.b, s));
 	SVO_CUDA_TRY(cudaGetLastError());

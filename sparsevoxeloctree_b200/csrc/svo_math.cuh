@@ -17,6 +17,7 @@ SVO_HD inline float fadd(float a, float b) { return __fadd_rn(a, b); }
 SVO_HD inline float fsub(float a, float b) { return __fsub_rn(a, b); }
 SVO_HD inline double dmul(double a, double b) { return __dmul_rn(a, b); }
 SVO_HD inline double dsub(double a, double b) { return __dsub_rn(a, b); }
+SVO_HD inline double dadd(double a, double b) { return __dadd_rn(a, b); }
 SVO_HD inline double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 SVO_HD inline double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 SVO_HD inline float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
@@ -27,6 +28,7 @@ SVO_HD inline float fadd(float a, float b) { return a + b; }
 SVO_HD inline float fsub(float a, float b) { return a - b; }
 SVO_HD inline double dmul(double a, double b) { return a * b; }
 SVO_HD inline double dsub(double a, double b) { return a - b; }
+SVO_HD inline double dadd(double a, double b) { return a + b; }
 SVO_HD inline double ddiv(double a, double b) { return a / b; }
 SVO_HD inline double dfma(double a, double b, double c) { return fma(a, b, c); }
 SVO_HD inline float ffma(float a, float b, float c) { return fmaf(a, b, c); }

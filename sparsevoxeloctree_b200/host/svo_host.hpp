@@ -37,10 +37,15 @@ struct Vertex { // src/Scene.cpp:16-19
 };
 
 // What Scene keeps private in the reference (src/Scene.hpp:26,35-40): vertex + index buffers and the draw list.
+struct TextureData { // one stbi_load(..., 4) image (src/Scene.cpp:245-262): RGBA8, sRGB colour
+	uint32_t width{}, height{};
+	std::vector<uint8_t> rgba8;
+};
 struct MeshData {
 	std::vector<Vertex> vertices;
 	std::vector<uint32_t> indices;
 	std::vector<svo_draw> draws;
+	std::vector<TextureData> textures; // indexed by svo_draw::texture_id
 };
 
 class Scene {
@@ -57,6 +62,14 @@ public:
 		m.n_indices = mesh.indices.size();
 		m.draws = mesh.draws.data();
 		m.n_draws = (uint32_t)mesh.draws.size();
+		std::vector<svo_texture> tex(mesh.textures.size());
+		for (size_t i = 0; i < tex.size(); ++i) tex[i] = svo_texture{mesh.textures[i].rgba8.data(), mesh.textures[i].width, mesh.textures[i].height};
+		if (!tex.empty() && !mesh.vertices.empty()) {
+			m.n_textures = (uint32_t)tex.size();
+			m.textures = tex.data();
+			m.texcoords = mesh.vertices[0].m_texcoord;
+			m.texcoord_stride_bytes = sizeof(Vertex);
+		}
 		auto ret = std::make_shared<Scene>();
 		if (svo_scene_create(&m, device, stream, &ret->m_handle) != SVO_OK) {
 			fprintf(stderr, "Scene::Create: %s\n", svo_last_error());

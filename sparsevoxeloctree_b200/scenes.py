@@ -29,6 +29,8 @@ class Mesh:
     indices: np.ndarray    # uint32 [3T]
     draws: np.ndarray      # DRAW_DTYPE [D]
     name: str = ""
+    texcoords: np.ndarray | None = None  # float32 [V,2] (only for textured draws)
+    textures: list | None = None         # uint8 [H,W,4] sRGB RGBA images, indexed by draws["texture_id"]
 
     @property
     def n_triangles(self) -> int:
@@ -275,6 +277,59 @@ def random_soup(n_tri: int, seed: int, size_lo: float = 0.005, size_hi: float = 
     cen = rng.uniform(3 * n_tri, -0.9, 0.9).reshape(n_tri, 3)
     p, t = _small_triangles(rng, n_tri, cen, size_lo, size_hi)
     return _assemble([(p, t, np.arange(n_tri) % n_mat)], f"soup{n_tri}_{seed}")
+
+
+def procedural_textures(seed: int = 7):
+    """Three small sRGB RGBA images: 64x64 opaque noise, 32(w)x16(h) with alpha holes (alpha-tested like the foliage
+    textures voxelizer.frag:29-30 exists for), 20x12 opaque (not a power of two: uneven blits in the mip chain)."""
+    rng = SplitMix64(seed)
+
+    def noise(h, w):
+        return (rng.u64(h * w * 4) >> np.uint64(56)).astype(np.uint8).reshape(h, w, 4)
+
+    a = noise(64, 64)
+    a[..., 3] = 255
+    b = noise(16, 32)
+    yy, xx = np.mgrid[0:16, 0:32]
+    b[..., 3] = np.where(((xx // 4) + (yy // 4)) % 2 == 0, 255, np.where(xx % 3 == 0, 120, 10)).astype(np.uint8)
+    c = noise(12, 20)
+    c[..., 3] = 200
+    return [a, b, c]
+
+
+def textured_soup(n_tri: int = 300, seed: int = 11, size_lo: float = 0.01, size_hi: float = 0.5, uv_scale_hi: float = 6.0,
+                  big_quads: bool = True) -> Mesh:
+    """Triangle soup over 4 materials: untextured, opaque texture, alpha-tested texture, non-power-of-two texture;
+    random texture coordinates whose scale spans magnification to several mip levels, plus (big_quads) two wall-sized
+    quads so the large-triangle path samples textures too."""
+    rng = SplitMix64(seed)
+    cen = rng.uniform(3 * n_tri, -0.9, 0.9).reshape(n_tri, 3)
+    pos, tri = _small_triangles(rng, n_tri, cen, size_lo, size_hi)
+    scale = np.exp(rng.uniform(n_tri, np.log(0.05), np.log(uv_scale_hi)))
+    uv = (rng.uniform(6 * n_tri, -1.0, 1.0).reshape(n_tri, 3, 2) * scale[:, None, None] + rng.uniform(2 * n_tri, -2, 2).reshape(n_tri, 1, 2))
+    uv = uv.reshape(-1, 2)
+    mat = np.arange(n_tri) % 4
+    parts_pos, parts_tri, parts_mat, parts_uv = [pos], [tri], [mat], [uv]
+    if big_quads:
+        for k, (m, z) in enumerate(((1, -0.31), (2, 0.47), (3, 0.13))):
+            q = np.array([[-0.8, -0.7, z], [0.75, -0.72, z + 0.2], [0.8, 0.77, z + 0.25], [-0.78, 0.7, z + 0.05]])
+            if k == 1:
+                q = q[:, [2, 0, 1]]
+            quv = np.array([[0.0, 0.0], [3.0 + k, 0.2], [3.3 + k, 2.5], [-0.1, 2.2]])
+            parts_pos.append(q), parts_tri.append(np.array([[0, 1, 2], [0, 2, 3]]) + sum(len(p) for p in parts_pos[:-1]))
+            parts_mat.append(np.array([m, m])), parts_uv.append(quv)
+    P = np.concatenate(parts_pos).astype(np.float32)
+    T = np.concatenate(parts_tri)
+    M = np.concatenate(parts_mat)
+    UV = np.concatenate(parts_uv).astype(np.float32)
+    idx, draws, first = [], [], 0
+    for m in (1, 0, 2, 3):  # any fixed draw order (the reference sorts by size, Scene.cpp:124-132)
+        t = T[M == m].reshape(-1)
+        idx.append(t)
+        draws.append((first, len(t), 0xFFFFFFFF if m == 0 else m - 1, pack_albedo(ALBEDOS[m])))
+        first += len(t)
+    return Mesh(P, np.concatenate(idx).astype(np.uint32), np.array(draws, dtype=DRAW_DTYPE), f"texsoup{n_tri}_{seed}",
+                texcoords=UV, textures=procedural_textures(seed + 1))
 
 
 CONFIGS = {

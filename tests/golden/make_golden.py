@@ -24,13 +24,17 @@ CASES = {
     "heightfield21_L6_conservative": (lambda: scenes.heightfield(21), 6, oracle.CONSERVATIVE_EXACT),
     "soup80_L7_conservative": (lambda: scenes.random_soup(80, 5, 0.01, 1.2), 7, oracle.CONSERVATIVE_EXACT),
     "soup200_L5_center": (lambda: scenes.random_soup(200, 6, 0.005, 0.6), 5, oracle.CENTER),
+    "texsoup120_L7_conservative": (lambda: scenes.textured_soup(120, 12, size_hi=0.35), 7, oracle.CONSERVATIVE_EXACT),
+    "texsoup60_L7_center": (lambda: scenes.textured_soup(60, 13, size_hi=0.35), 7, oracle.CENTER),
 }
 
 
 def make(name):
     gen, level, mode = CASES[name]
     mesh = gen()
-    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, mode)
+    texset = oracle.TexSet(mesh.textures) if mesh.textures else None
+    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, mode,
+                         texcoords=mesh.texcoords if texset is not None else None, texset=texset)
     keys = (morton_np(fr["x"], fr["y"], fr["z"], level) << np.uint64(24)) | fr["rgb"].astype(np.uint64)
     words, rng = oracle.build_octree(fr, level)
     d, m, w = oracle.canonicalise(words, level)

@@ -29,7 +29,9 @@ def demorton_np(m, level):
 
 def oracle_fragment_keys(mesh, level, mode, shard_box=None, origin=(0, 0, 0), key_level=None):
     """The oracle's fragments as 64-bit keys (morton << 24 | rgb), in oracle emission order."""
-    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, mode, shard=shard_box)
+    texset = oracle.TexSet(mesh.textures) if getattr(mesh, "textures", None) else None
+    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, mode, shard=shard_box,
+                         texcoords=mesh.texcoords if texset is not None else None, texset=texset)
     kl = level if key_level is None else key_level
     m = morton_np(fr["x"] - np.uint32(origin[0]), fr["y"] - np.uint32(origin[1]), fr["z"] - np.uint32(origin[2]), kl)
     return (m << np.uint64(24)) | fr["rgb"].astype(np.uint64)

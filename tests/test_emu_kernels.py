@@ -68,6 +68,14 @@ def test_full_path_heightfield(emu):
     check_against_oracle(emu, scenes.heightfield(21), 6, api.CENTER)
 
 
+@pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT])
+def test_full_path_textured(emu, mode):
+    """voxelizer.frag:27-36: trilinear sRGB sampling, alpha-test discard, packUnorm4x8 -- kernels vs oracle."""
+    m = scenes.textured_soup(60, 11, size_hi=0.3)
+    info = check_against_oracle(emu, m, 6, mode)
+    assert info["fragments"] > 500
+
+
 def test_empty_scene(emu):
     m = scenes.Mesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), np.zeros(0, scenes.DRAW_DTYPE), "empty")
     info = check_against_oracle(emu, m, 4, api.CENTER)

@@ -149,7 +149,49 @@ def test_error_behaviour(lib):
     draws = m.draws.copy()
     draws["texture_id"][0] = 3
     with pytest.raises(api.SvoError):
-        api.Scene.Create(m.positions, m.indices, draws, lib=lib)  # textured draws: not on the built path
+        api.Scene.Create(m.positions, m.indices, draws, lib=lib)  # a textured draw without its texture / texcoords
+
+
+# ---- textured materials (voxelizer.frag:27-36) ----------------------------------------------------------
+def test_mip_chain_matches_oracle(lib):
+    """Scene::load_textures' linear-blit mip chain (Scene.cpp:290-295), incl. non-power-of-two sizes."""
+    from oracle import oracle
+    rng = np.random.default_rng(3)
+    tex = scenes.procedural_textures(5) + [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for h, w in ((1, 7), (37, 3), (128, 96))]
+    m = scenes.textured_soup(8, 3, big_quads=False)
+    m.textures = tex
+    scene = api.Scene.Create(m, lib=lib)
+    ts = oracle.TexSet(tex)
+    for t in range(len(tex)):
+        n = scene.texture_level_count(t)
+        assert n == ts.level_count(t)
+        for lv in range(n):
+            assert (scene.texture_level_to_host(t, lv) == ts.level(t, lv)).all(), (t, lv)
+    scene.Destroy()
+
+
+@pytest.mark.parametrize("level", [6, 9, 11])
+@pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT, api.CONSERVATIVE_DILATE])
+def test_textured_soup(lib, level, mode):
+    """trilinear sRGB sampling at every LOD regime, alpha-test discards (count pass included), packUnorm4x8, on both
+    raster paths -- fragment multiset (colours included) and tree bit-exact against the oracle."""
+    info = check_against_oracle(lib, scenes.textured_soup(400, 20 + level, size_hi=0.3), level, mode)
+    assert info["fragments"] > 1000
+
+
+def test_textured_octant_shard(lib):
+    check_against_oracle(lib, scenes.textured_soup(300, 31, size_hi=0.4), 8, api.CONSERVATIVE_EXACT, shard=(1, (0, 1, 1)))
+
+
+def test_textured_reference_vertex_layout(lib):
+    # interleaved Vertex {vec3 pos; vec2 uv}, stride 20: texcoords taken from positions + 12 (Scene.cpp:16-19)
+    m = scenes.textured_soup(100, 32)
+    v5 = np.concatenate([m.positions, m.texcoords], axis=1).astype(np.float32)
+    a = check_against_oracle(lib, scenes.Mesh(v5, m.indices, m.draws, "tex20", texcoords=m.texcoords, textures=m.textures), 7,
+                             api.CENTER)
+    scene = api.Scene.Create(v5, m.indices, m.draws, lib=lib, textures=m.textures)  # no separate texcoords array
+    vox = api.Voxelizer.Create(scene, 7, api.CENTER)
+    assert vox.GetVoxelFragmentCount() == a["fragments"]
 
 
 def test_virtual_shards_stitch_equals_whole_grid(lib):
