@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
         L.orc_voxelize_textured.restype = C.c_int64
         L.orc_debug_sample.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_debug_sample.restype = C.c_uint32
+        L.orc_debug_shade.argtypes = [C.c_void_p]
+        L.orc_debug_shade.restype = C.c_uint32
         L.orc_build.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
         L.orc_build.restype = C.c_int64
         L.orc_canonicalise.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -255,6 +257,13 @@ def debug_raster_pixels(p0, p1, p2, level, mode):
     px, py, z = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
     L.orc_debug_raster_pixels(_ptr(p[0]), _ptr(p[1]), _ptr(p[2]), level, mode, _ptr(px), _ptr(py), _ptr(z), n)
     return px, py, z
+
+
+def debug_shade(rgba):
+    """voxelizer.frag's use of a texture sample: packed rgb (int) or None when the alpha test discards it."""
+    v = np.ascontiguousarray(rgba, dtype=np.float32)
+    r = lib().orc_debug_shade(_ptr(v))
+    return None if r == 0 else int(r & 0xFFFFFF)
 
 
 def frags_from_xyzc(x, y, z, rgb):

@@ -242,7 +242,7 @@ class Module:
         raise NotImplementedError(f"GLSL.std.450 {inst}")
 
     # ---- execution ---------------------------------------------------------------------------------------
-    def run(self, inputs=None, buffers=None, push=None, on_emit=None):
+    def run(self, inputs=None, buffers=None, push=None, on_emit=None, sampler=None):
         """Execute the entry point once.
         inputs : {variable id or BuiltIn number or ('loc', n): python value}
         buffers: {(set, binding): np.uint32 array}
@@ -308,7 +308,12 @@ class Module:
                 pointee = T[a[0]][2]
                 cell = [val[a[3]] if len(a) > 3 else self._null(pointee)]
                 val[a[1]] = Ptr("mem", cell, [0], pointee)
-            elif op == 61: val[a[1]] = load(val[a[2]])
+            elif op == 61:
+                p = val[a[2]]
+                if T[a[0]][0] == "opaque": val[a[1]] = ("tex", p.path[-1] if p.kind == "mem" else 0)  # a combined image sampler
+                else: val[a[1]] = load(p)
+            elif op == 87:  # ImageSampleImplicitLod: the driver's sampler -- supplied by the caller
+                val[a[1]] = [F32(x) for x in sampler(val[a[2]][1], val[a[3]])]
             elif op == 62: store(val[a[0]], val[a[1]])
             elif op in (65, 66):
                 base = val[a[2]]

@@ -543,6 +543,14 @@ static void sample_level(const orc_texset *s, const orc_level *L, double u, doub
 	filter4(s, L, i0, i1, j0, j1, a, b, out);
 }
 
+/* voxelizer.frag:28-30,35,42: x = texture(...); if (x.a < 0.5) discard; packUnorm4x8(x) & 0xffffff */
+static int shade(const float c[4], uint32_t *rgb) {
+	if (c[3] < 0.5f)
+		return 0;
+	*rgb = (uint32_t)pack_unorm8(c[0]) | ((uint32_t)pack_unorm8(c[1]) << 8) | ((uint32_t)pack_unorm8(c[2]) << 16);
+	return 1;
+}
+
 /* voxelizer.frag:27-36: returns 0 when the fragment is discarded (alpha < 0.5), else 1 and the packed colour */
 static int sample_colour(const orc_texset *s, const orc_tex *tex, const orc_uvmap *m, int32_t px, int32_t py, uint32_t *rgb) {
 	const double cx = (double)px + 0.5, cy = (double)py + 0.5;
@@ -556,10 +564,11 @@ static int sample_colour(const orc_texset *s, const orc_tex *tex, const orc_uvma
 		for (int k = 0; k < 4; ++k)
 			c[k] = lerpf(c[k], d[k], m->delta);
 	}
-	if (c[3] < 0.5f)
-		return 0;
-	*rgb = (uint32_t)pack_unorm8(c[0]) | ((uint32_t)pack_unorm8(c[1]) << 8) | ((uint32_t)pack_unorm8(c[2]) << 16);
-	return 1;
+	return shade(c, rgb);
+}
+uint32_t orc_debug_shade(const float rgba[4]) {
+	uint32_t rgb = 0;
+	return shade(rgba, &rgb) ? (0xff000000u | rgb) : 0u;
 }
 
 uint32_t orc_debug_sample(const orc_texset *s, uint32_t tex, const float *p0, const float *p1, const float *p2, const float *uv0,

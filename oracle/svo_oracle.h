@@ -14,9 +14,10 @@
  *    their outputs committed (tests/golden/spirv_*.npz): orc_build equals the four compute
  *    shaders word for word; the geometry and fragment stages equal voxelizer.geom / .frag
  *    (tests/test_spirv_golden.py), plus hand-derived KATs (tests/test_oracle_kat.py).
- *  - UNPINNED for the one stage the reference does not define: the fixed-function rasterizer
- *    (coverage, snapping, depth interpolation live in the Vulkan driver).  The arithmetic used
- *    here for that stage is the "pinned arithmetic" stated in DESIGN.md section 3.
+ *  - UNPINNED for the stages the reference does not define: the fixed-function rasterizer
+ *    (coverage, snapping, depth interpolation) and the texture unit (texture() filtering / LOD /
+ *    sRGB decode, and the linear blits that build the mip chains) live in the Vulkan driver.  The
+ *    arithmetic used here for them is the "pinned arithmetic" stated in DESIGN.md section 3.
  */
 #ifndef SVO_ORACLE_H
 #define SVO_ORACLE_H
@@ -83,6 +84,9 @@ int64_t orc_voxelize_textured(const void *positions, uint32_t pos_stride_bytes, 
 /* colour of pixel (px,py) of one textured triangle: 0xff000000 | rgb, or 0 when discarded; lod_out = {hi, lo, delta*256} */
 uint32_t orc_debug_sample(const orc_texset *s, uint32_t tex, const float *p0, const float *p1, const float *p2, const float *uv0,
                           const float *uv1, const float *uv2, uint32_t level, int32_t px, int32_t py, uint32_t lod_out[3]);
+
+/* voxelizer.frag:28-30,35,42 on a given sample value: 0xff000000 | (packUnorm4x8(x) & 0xffffff), or 0 when discarded */
+uint32_t orc_debug_shade(const float rgba[4]);
 
 /* Debug views for the SPIR-V cross-checks: geometry-stage outputs {axis, gAABB[4], gDepthRange[2]} + snapped window
  * coordinates of one triangle; and its covered pixels with the pinned fp64 depth (before voxelizer.frag). */

@@ -155,8 +155,46 @@ def make_dilate_case(level=6):
     return dict(level=level, triangles=np.stack(tris), emitted=np.stack(emitted_all).view(np.uint32), flat=np.array(flat_all, np.uint32))
 
 
+def make_textured_frag_case(level=6, n=600, seed=9):
+    """voxelizer.frag with uTextureId != 0xffffffff: what the shader does with the value texture() returns (alpha-test
+    discard, packUnorm4x8, & 0xffffff) -- texture() itself is the driver's sampler and is injected here."""
+    res = 1 << level
+    frag = si.Module.from_u32_file(SPV + "voxelizer.frag.u32", spec={0: res, 1: 4})  # kTextureNum = 4
+    f_axis, f_aabb, f_zr, f_uv = (frag.var_by_location(k, 1) for k in (1, 2, 3, 0))
+    rng = np.random.default_rng(seed)
+    vals = rng.uniform(-0.1, 1.1, (n, 4)).astype(np.float32)
+    vals[: n // 4, 3] = rng.choice(np.array([0.5, np.nextafter(np.float32(0.5), np.float32(0)), 0.4999, 0.5001, 0.0, 1.0], np.float32), n // 4)
+    k = np.arange(n // 4, n // 2)  # exact .5/255 ties of packUnorm4x8 and their neighbours
+    vals[k, 0] = ((k % 255) + 0.5).astype(np.float32) / np.float32(255.0)
+    vals[k, 1] = np.nextafter(vals[k, 0], np.float32(2))
+    vals[k, 2] = np.nextafter(vals[k, 0], np.float32(-1))
+    out, seen = [], []
+    for i, v in enumerate(vals):
+        counter, flist = np.zeros(1, np.uint32), np.zeros(2, np.uint32)
+        tex_id, uv = int(i % 4), [np.float32(0.25 + i), np.float32(-1.5)]
+
+        def sampler(t, coord, v=v):
+            seen.append((t, float(coord[0]), float(coord[1])))
+            return list(v)
+
+        try:
+            frag.run({("builtin", 15): [np.float32(3.5), np.float32(4.5), np.float32(0.3), np.float32(1.0)], f_axis: 2,
+                      f_aabb: [0, 0, res - 1, res - 1], f_zr: [0, res - 1], f_uv: uv}, {(0, 0): counter, (0, 1): flist},
+                     [0, tex_id, 0x00112233], sampler=sampler)
+            out.append((1, int(flist[1]) & 0xFFFFFF, int(counter[0])))
+        except si.Discard:
+            out.append((0, 0, int(counter[0])))
+        assert seen[-1] == (tex_id, float(uv[0]), float(uv[1]))  # texture(uTextures[uTextureId], gTexcoord)
+    return dict(values=vals.view(np.uint32), out=np.array(out, np.uint32))
+
+
 if __name__ == "__main__":
     import time
+    o = make_textured_frag_case()
+    np.savez_compressed(os.path.join(HERE, "spirv_frag_textured.npz"), **o)
+    print("textured frag", len(o["out"]), "samples,", int((o["out"][:, 0] == 0).sum()), "discarded", flush=True)
+    if "--textured-only" in sys.argv:
+        sys.exit(0)
     for n in BUILD_CASES:
         t = time.time()
         o = make_build_case(n)

@@ -83,6 +83,18 @@ def test_oracle_fragment_stage_equals_reference_frag_shader():
     assert n_emit > 10000 and n_zdiff <= 1e-3 * n_emit, (n_emit, n_zdiff)
 
 
+def test_oracle_textured_shading_equals_reference_frag_shader():
+    """voxelizer.frag:27-36 on injected texture() results: discard iff alpha < 0.5, colour = packUnorm4x8(x) & 0xffffff,
+    counter bumped only for surviving fragments."""
+    g = np.load(os.path.join(HERE, "golden", "spirv_frag_textured.npz"))
+    vals = g["values"].view(np.float32)
+    for v, (alive, rgb, counter) in zip(vals, g["out"]):
+        o = oracle.debug_shade(v)
+        assert (o is not None) == bool(alive) == bool(counter), v
+        if alive:
+            assert o == int(rgb), (v, hex(o), hex(int(rgb)))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", BUILD, ids=[os.path.basename(p) for p in BUILD])
 def test_cuda_builder_equals_reference_compute_shaders(path):
