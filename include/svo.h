@@ -208,6 +208,21 @@ SVO_API int svo_builder_last_ms(svo_builder *b, float *phase_ms /*[SVO_PHASE_COU
 SVO_API int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_bit, uint32_t end_bit,
                          int device, void *stream);
 
+/* ---- the consumer side, for verification ----------------------------------------------------
+ * Octree_RayMarchLeaf (shader/octree.glsl:179-340, the primary-ray traversal octree_tracer.frag:36 runs on the
+ * node buffer), one ray per thread: lets a built tree be checked / rendered without Vulkan.  The octree
+ * occupies [1,2]^3 (octree.glsl:53).  All pointers are DEVICE pointers; origins / dirs hold 3 floats per ray
+ * (dirs need not be normalised; camera rays: shader/camera.glsl:12-15). */
+typedef struct svo_ray_hit {
+	float pos[3];    /* o_pos: hit position, pushed just outside the entry face */
+	float colour[3]; /* o_color: unpackUnorm4x8(leaf).xyz */
+	float normal[3]; /* o_normal: axis-aligned entry-face normal */
+	uint32_t hit;    /* the function's return value */
+	uint32_t iter;   /* o_iter: traversal iterations (the tracer's "iteration" view) */
+} svo_ray_hit;
+SVO_API int svo_octree_raymarch_leaf(int device, const uint32_t *d_octree, uint64_t n_rays, const float *d_origins,
+                                     const float *d_dirs, svo_ray_hit *d_hits, void *stream);
+
 /* ---- plain device memory helpers for callers without a CUDA binding (tests, ctypes) --------- */
 SVO_API int svo_device_malloc(int device, uint64_t bytes, void **out);
 SVO_API int svo_device_free(int device, void *ptr);

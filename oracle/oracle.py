@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
         L.orc_voxelize_textured.restype = C.c_int64
         L.orc_debug_sample.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_debug_sample.restype = C.c_uint32
+        L.orc_raymarch_leaf.argtypes = [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)]
+        L.orc_raymarch_leaf.restype = C.c_int
         L.orc_debug_shade.argtypes = [C.c_void_p]
         L.orc_debug_shade.restype = C.c_uint32
         L.orc_build.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
@@ -257,6 +259,17 @@ def debug_raster_pixels(p0, p1, p2, level, mode):
     px, py, z = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
     L.orc_debug_raster_pixels(_ptr(p[0]), _ptr(p[1]), _ptr(p[2]), level, mode, _ptr(px), _ptr(py), _ptr(z), n)
     return px, py, z
+
+
+def raymarch_leaf(words, o, d):
+    """Octree_RayMarchLeaf (octree.glsl:179-340) -> (hit, pos[3], colour[3], normal[3], iterations)."""
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    o = np.ascontiguousarray(o, dtype=np.float32)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    pos, col, nrm = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+    it = C.c_uint32()
+    hit = lib().orc_raymarch_leaf(_ptr(words), _ptr(o), _ptr(d), _ptr(pos), _ptr(col), _ptr(nrm), C.byref(it))
+    return bool(hit), pos, col, nrm, int(it.value)
 
 
 def debug_shade(rgba):

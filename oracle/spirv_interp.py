@@ -205,6 +205,7 @@ class Module:
         if op == 182: return bool(a != b)
         if op == 184: return bool(a < b)
         if op == 186: return bool(a > b)
+        if op == 183: return bool(a != b)   # FUnordNotEqual (true for NaN, like python !=)
         if op == 188: return bool(a <= b)
         if op == 190: return bool(a >= b)
         if op == 109:  # ConvertFToU: truncation; negative / NaN are undefined in SPIR-V -> 0
@@ -223,6 +224,14 @@ class Module:
             a, b = v
             return [F32(F32(a[1] * b[2]) - F32(a[2] * b[1])), F32(F32(a[2] * b[0]) - F32(a[0] * b[2])),
                     F32(F32(a[0] * b[1]) - F32(a[1] * b[0]))]
+        if inst == 64:  # UnpackUnorm4x8
+            return [F32(F32((v[0] >> (8 * k)) & 0xff) / F32(255.0)) for k in range(4)]
+        if inst == 69:  # Normalize: x * inversesqrt(dot(x, x)) evaluated as x / sqrt(dot) (driver-defined precision)
+            acc = F32(0)
+            for c in v[0]: acc = F32(acc + F32(c * c))
+            return [F32(c / np.sqrt(acc)) for c in v[0]]
+        if inst == 75:  # FindUMsb
+            return (int(v[0]).bit_length() - 1) & M32
         if inst == 55:  # PackUnorm4x8
             out = 0
             for k, c in enumerate(v[0]):
@@ -239,10 +248,13 @@ class Module:
         if inst == 41: return max(v[0], v[1])
         if inst == 44: return min(max(v[0], v[1]), v[2])          # UClamp
         if inst == 50: return F32(np.float64(v[0]) * np.float64(v[1]) + np.float64(v[2]))  # Fma: one rounding
+        if inst == 43: return min(max(v[0], v[1]), v[2])          # FClamp
+        if inst == 13: return F32(np.sin(np.float64(v[0])))       # Sin / Pow: driver-defined precision
+        if inst == 26: return F32(np.power(np.float64(v[0]), np.float64(v[1])))
         raise NotImplementedError(f"GLSL.std.450 {inst}")
 
     # ---- execution ---------------------------------------------------------------------------------------
-    def run(self, inputs=None, buffers=None, push=None, on_emit=None, sampler=None):
+    def run(self, inputs=None, buffers=None, push=None, on_emit=None, sampler=None, on_ext=None):
         """Execute the entry point once.
         inputs : {variable id or BuiltIn number or ('loc', n): python value}
         buffers: {(set, binding): np.uint32 array}
@@ -323,7 +335,9 @@ class Module:
                     val[a[1]] = Ptr("buf", base.obj, base.path + off, tid)
                 else:
                     val[a[1]] = Ptr("mem", base.obj, base.path + idx, T[a[0]][2])
-            elif op == 12: val[a[1]] = self._ext(a[3], a[0], [val[x] for x in a[4:]])
+            elif op == 12:
+                val[a[1]] = self._ext(a[3], a[0], [val[x] for x in a[4:]])
+                if on_ext: on_ext(a[3], [val[x] for x in a[4:]], val[a[1]])
             elif op == 79:  # VectorShuffle
                 both = list(val[a[2]]) + list(val[a[3]])
                 val[a[1]] = [both[k] if k != M32 else self._null(T[a[0]][1]) for k in a[4:]]

@@ -891,3 +891,147 @@ void orc_debug_dilate(const float *p0, const float *p1, const float *p2, uint32_
 	dilate_mode_b(q, n[axis], 1u << level);
 	memcpy(out, q, sizeof(q));
 }
+
+/* ------------------------------------------------------------------------------------------
+ * The consumer side, for verification only: Octree_RayMarchLeaf (octree.glsl:179-340, the variant
+ * octree_tracer.frag:36 calls), the stack-based parametric octree traversal of Laine & Karras,
+ * "Efficient Sparse Voxel Octrees" (2010), which the reference adopts.  The octree occupies [1,2]^3
+ * and the ray is mirrored so that every direction component is negative; positions are handled as
+ * fp32 bit patterns, one mantissa bit per level (hence the 23-entry stack).  fp32, one rounding per
+ * operator, with fused multiply-adds exactly where the reference's compiled octree_tracer.frag has
+ * them (every "k * t_coef - t_bias" and "pos * t_coef - t_bias"), so that it is bit-identical to
+ * the executed binary (tests/golden/spirv_tracer_*.npz).
+ * ---------------------------------------------------------------------------------------- */
+static uint32_t f2bits(float f) {
+	uint32_t u;
+	memcpy(&u, &f, 4);
+	return u;
+}
+static float bits2f(uint32_t u) {
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+static float min3f(float a, float b, float c) { /* GLSL min(min(a,b),c), min(x,y) = y < x ? y : x */
+	float m = b < a ? b : a;
+	return c < m ? c : m;
+}
+static float max3f(float a, float b, float c) {
+	float m = a < b ? b : a;
+	return m < c ? c : m;
+}
+
+int orc_raymarch_leaf(const uint32_t *octree, const float o[3], const float d_in[3], float o_pos[3], float o_colour[3],
+                      float o_normal[3], uint32_t *o_iter) {
+	enum { STACK = 23 };            /* octree.glsl:43 */
+	const float EPS = 3.552713678800501e-15f; /* octree.glsl:44 */
+	uint32_t stack[STACK] = {0};
+	float d[3], t_coef[3], t_bias[3], pos[3] = {1.0f, 1.0f, 1.0f};
+	uint32_t oct_mask = 0u, iter = 0u;
+	for (int k = 0; k < 3; ++k) { /* octree.glsl:182-199 */
+		d[k] = fabsf(d_in[k]) > EPS ? d_in[k] : (d_in[k] >= 0 ? EPS : -EPS);
+		t_coef[k] = 1.0f / -fabsf(d[k]);
+		t_bias[k] = t_coef[k] * o[k];
+		if (d[k] > 0.0f) {
+			oct_mask ^= 1u << k;
+			t_bias[k] = fmaf(3.0f, t_coef[k], -t_bias[k]);
+		}
+	}
+	/* octree.glsl:201-205: the active span of t */
+	float t_min = max3f(fmaf(2.0f, t_coef[0], -t_bias[0]), fmaf(2.0f, t_coef[1], -t_bias[1]), fmaf(2.0f, t_coef[2], -t_bias[2]));
+	const float t_max = min3f(t_coef[0] - t_bias[0], t_coef[1] - t_bias[1], t_coef[2] - t_bias[2]);
+	t_min = t_min < 0.0f ? 0.0f : t_min;
+	float h = t_max;
+	uint32_t parent = 0u, cur = 0u, idx = 0u;
+	for (int k = 0; k < 3; ++k) /* octree.glsl:207-216: first child */
+		if (fmaf(1.5f, t_coef[k], -t_bias[k]) > t_min)
+			idx ^= 1u << k, pos[k] = 1.5f;
+	uint32_t scale = STACK - 1;
+	float scale_exp2 = 0.5f;
+
+	while (scale < STACK) { /* octree.glsl:221-302 */
+		++iter;
+		if (cur == 0u)
+			cur = octree[parent + (idx ^ oct_mask)];
+		float t_corner[3];
+		for (int k = 0; k < 3; ++k)
+			t_corner[k] = fmaf(pos[k], t_coef[k], -t_bias[k]);
+		const float tc_max = min3f(t_corner[0], t_corner[1], t_corner[2]);
+		if ((cur & 0x80000000u) != 0u && t_min <= t_max) {
+			const float half = scale_exp2 * 0.5f;
+			if ((cur & 0x40000000u) != 0u)
+				break; /* leaf */
+			if (tc_max < h) /* push */
+				stack[scale] = parent;
+			h = tc_max;
+			parent = cur & 0x3fffffffu;
+			idx = 0u;
+			--scale;
+			scale_exp2 = half;
+			for (int k = 0; k < 3; ++k)
+				if (half * t_coef[k] + t_corner[k] > t_min)
+					idx ^= 1u << k, pos[k] += scale_exp2;
+			cur = 0u;
+			continue;
+		}
+		/* advance */
+		uint32_t step_mask = 0u;
+		for (int k = 0; k < 3; ++k)
+			if (t_corner[k] <= tc_max)
+				step_mask ^= 1u << k, pos[k] -= scale_exp2;
+		t_min = tc_max;
+		idx ^= step_mask;
+		if ((idx & step_mask) != 0u) { /* pop: the highest differing mantissa bit names the level to return to */
+			uint32_t differing = 0u;
+			for (int k = 0; k < 3; ++k)
+				if (step_mask & (1u << k))
+					differing |= f2bits(pos[k]) ^ f2bits(pos[k] + scale_exp2);
+			int msb = -1; /* findMSB(0) = -1 -> scale = 0xffffffff >= STACK */
+			for (int b = 31; b >= 0; --b)
+				if (differing & (1u << b)) {
+					msb = b;
+					break;
+				}
+			scale = (uint32_t)msb;
+			if (scale >= STACK)
+				break;
+			scale_exp2 = bits2f((scale - STACK + 127u) << 23u);
+			parent = stack[scale];
+			uint32_t sh[3];
+			for (int k = 0; k < 3; ++k) {
+				sh[k] = f2bits(pos[k]) >> scale;
+				pos[k] = bits2f(sh[k] << scale);
+			}
+			idx = (sh[0] & 1u) | ((sh[1] & 1u) << 1u) | ((sh[2] & 1u) << 2u);
+			h = 0.0f;
+			cur = 0u;
+		}
+	}
+
+	/* octree.glsl:304-339: normal of the entry face, un-mirror, outputs */
+	float t_corner[3], norm[3] = {0.0f, 0.0f, 0.0f};
+	for (int k = 0; k < 3; ++k)
+		t_corner[k] = fmaf(t_coef[k], pos[k] + scale_exp2, -t_bias[k]);
+	const int axis = (t_corner[0] > t_corner[1] && t_corner[0] > t_corner[2]) ? 0 : (t_corner[1] > t_corner[2] ? 1 : 2);
+	norm[axis] = -1.0f;
+	for (int k = 0; k < 3; ++k) {
+		if ((oct_mask & (1u << k)) == 0u)
+			norm[k] = -norm[k];
+		else
+			pos[k] = 3.0f - scale_exp2 - pos[k];
+	}
+	for (int k = 0; k < 3; ++k) {
+		float p = o[k] + t_min * d[k];
+		const float lo = pos[k], hi = pos[k] + scale_exp2;
+		p = p < lo ? lo : p; /* clamp(x, lo, hi) = min(max(x, lo), hi) */
+		p = hi < p ? hi : p;
+		if (norm[k] != 0.0f)
+			p = norm[k] > 0.0f ? pos[k] + scale_exp2 + EPS * 2.0f : pos[k] - EPS;
+		o_pos[k] = p;
+		o_normal[k] = norm[k] == 0.0f ? 0.0f : norm[k]; /* no negative zero */
+		o_colour[k] = (float)((cur >> (8 * k)) & 0xffu) / 255.0f; /* unpackUnorm4x8(cur).xyz */
+	}
+	*o_iter = iter;
+	return scale < STACK && t_min <= t_max;
+}
+

@@ -119,6 +119,13 @@ int64_t orc_build(const orc_frag *frags, int64_t n_frags, uint32_t level, uint32
 int64_t orc_canonicalise(const uint32_t *words, uint64_t n_words, uint32_t level, uint8_t *out_depth,
                          uint64_t *out_morton, uint32_t *out_word, int64_t cap);
 
+/*
+ * Octree_RayMarchLeaf (octree.glsl:179-340): the reference's primary-ray traversal of the node buffer, restated
+ * for verification of built trees (the octree occupies [1,2]^3).  Returns hit; outputs as the shader's.
+ */
+int orc_raymarch_leaf(const uint32_t *octree, const float o[3], const float d[3], float o_pos[3], float o_colour[3],
+                      float o_normal[3], uint32_t *o_iter);
+
 /* Morton code of a voxel: child slot = x | y<<1 | z<<2 per level, MSB first (tag_node.comp:24-25). */
 uint64_t orc_morton(uint32_t x, uint32_t y, uint32_t z, uint32_t level);
 

@@ -90,6 +90,7 @@ SYMBOLS = [
     ("svo_voxelizer_last_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("svo_builder_last_ms", C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     ("svo_sort_u64", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P]),
+    ("svo_octree_raymarch_leaf", C.c_int, [C.c_int, _P, C.c_uint64, _P, _P, _P, _P]),
     ("svo_device_malloc", C.c_int, [C.c_int, C.c_uint64, C.POINTER(_P)]),
     ("svo_device_free", C.c_int, [C.c_int, _P]),
     ("svo_memcpy_h2d", C.c_int, [C.c_int, _P, _P, C.c_uint64, _P]),
@@ -492,6 +493,40 @@ class Octree:
 
     def GetRange(self) -> int:
         return self.m_range
+
+
+RAY_HIT_DTYPE = np.dtype([("pos", "<f4", 3), ("colour", "<f4", 3), ("normal", "<f4", 3), ("hit", "<u4"), ("iter", "<u4")])
+
+
+def raymarch_leaf(d_octree: int, origins, dirs, device: int = 0, stream=None, lib: Library | None = None) -> np.ndarray:
+    """Octree_RayMarchLeaf (shader/octree.glsl:179-340) on a device node buffer; origins/dirs float32 [N,3] on the host.
+    Returns a RAY_HIT_DTYPE array."""
+    lib = lib or get_library()
+    o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+    assert o.shape == d.shape
+    n = len(o)
+    d_o, d_d, d_h = lib.to_device(o, device), lib.to_device(d, device), lib.malloc(max(1, n) * RAY_HIT_DTYPE.itemsize, device)
+    try:
+        lib.check(lib.dll.svo_octree_raymarch_leaf(device, d_octree, n, d_o, d_d, d_h, _stream_ptr(stream)))
+        lib.check(lib.dll.svo_stream_synchronize(device, _stream_ptr(stream)))
+        raw = lib.to_host(d_h, np.uint8, n * RAY_HIT_DTYPE.itemsize, device)
+    finally:
+        lib.free(d_o, device), lib.free(d_d, device), lib.free(d_h, device)
+    return raw.view(RAY_HIT_DTYPE)
+
+
+def camera_rays(position, look, side, up, width: int, height: int):
+    """octree_tracer.frag:24 + Camera_GenRay (shader/camera.glsl:12-15): one primary ray per pixel, row-major.
+    (normalize() precision is the driver's; fp32 x / sqrt(dot) here.)"""
+    px, py = np.meshgrid(np.arange(width, dtype=np.float32), np.arange(height, dtype=np.float32))
+    cx = (px / np.float32(width)) * np.float32(2) - np.float32(1)
+    cy = (py / np.float32(height)) * np.float32(2) - np.float32(1)
+    look, side, up = (np.asarray(v, np.float32) for v in (look, side, up))
+    d = look[None, None, :] - side[None, None, :] * cx[..., None] - up[None, None, :] * cy[..., None]
+    d = (d / np.sqrt((d * d).sum(-1, keepdims=True, dtype=np.float32))).astype(np.float32)
+    o = np.broadcast_to(np.asarray(position, np.float32), d.shape)
+    return o.reshape(-1, 3).copy(), d.reshape(-1, 3)
 
 
 def build_svo(mesh, level: int, mode: int = CONSERVATIVE_EXACT, device: int = 0, stream=None, lib: Library | None = None):

@@ -14,6 +14,7 @@
 
 #include "build.cuh"
 #include "raster.cuh"
+#include "raymarch.cuh"
 #include "sort.cuh"
 
 namespace svo {
@@ -845,6 +846,20 @@ int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_b
 	if (!rc && res != d_keys && cudaMemcpyAsync(d_keys, res, n * 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "copy back failed");
 	sc.hist.release(s), sc.ticket.release(s), sc.state.release(s);
 	return rc;
+}
+
+static_assert(sizeof(svo_ray_hit) == sizeof(RayHit), "svo_ray_hit layout");
+int svo_octree_raymarch_leaf(int device, const uint32_t *d_octree, uint64_t n_rays, const float *d_origins, const float *d_dirs,
+                             svo_ray_hit *d_hits, void *stream) {
+	if (n_rays && (!d_octree || !d_origins || !d_dirs || !d_hits)) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_octree_raymarch_leaf: null argument");
+	if (n_rays >= (1ull << 38)) return fail(SVO_ERR_CAPACITY, "svo_octree_raymarch_leaf: too many rays");
+	DeviceGuard guard(device);
+	if (!guard.ok) return fail(SVO_ERR_CUDA, "cudaSetDevice failed");
+	if (n_rays == 0) return SVO_OK;
+	SVO_LAUNCH_INDEP(div_up(n_rays, 128), 128, (cudaStream_t)stream, k_raymarch_leaf, d_octree, n_rays, d_origins, d_dirs,
+	                 reinterpret_cast<RayHit *>(d_hits));
+	SVO_CUDA_TRY(cudaGetLastError());
+	return SVO_OK;
 }
 
 int svo_device_malloc(int device, uint64_t bytes, void **out) {

@@ -290,6 +290,8 @@ inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) {
 // ---- intrinsics --------------------------------------------------------------------------------------
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -188,8 +188,60 @@ def make_textured_frag_case(level=6, n=600, seed=9):
     return dict(values=vals.view(np.uint32), out=np.array(out, np.uint32))
 
 
+TRACER_CAMERAS = {  # position, look, side, up (Camera.cpp builds such a basis; the octree occupies [1,2]^3, octree.glsl:53)
+    "outside": ([1.35, 1.6, -0.4], [0.05, -0.1, 1.0], [0.45, 0.0, 0.0], [0.0, 0.45, 0.0]),
+    "inside": ([1.5, 1.52, 1.47], [0.7, 0.2, -0.68], [0.5, 0.0, 0.5], [-0.1, 0.6, 0.1]),
+}
+
+
+def make_tracer_case(build_case, size=28):
+    """octree_tracer.frag (the reference's primary-ray consumer of the node buffer: Octree_RayMarchLeaf,
+    octree.glsl:179-340) executed on a node buffer the reference's own builder shaders produced.  Per pixel: the
+    ray direction the shader derived (captured at its normalize()), and oColor for the view types 'normal' (1),
+    'position' (2), 'diffuse' (0), plus the iteration count behind the 'iteration' view (3)."""
+    g = np.load(os.path.join(HERE, "spirv_build_" + build_case + ".npz"))
+    words = g["words"].astype(np.uint32)
+    frag = si.Module.from_u32_file(SPV + "octree_tracer.frag.u32")
+    out_var = frag.var_by_location(0, 3)
+    rows = []
+    for cname, (pos, look, side, up) in TRACER_CAMERAS.items():
+        cam = np.zeros(16, np.float32)
+        cam[0:3], cam[4:7], cam[8:11], cam[12:15] = pos, look, side, up
+        for py in range(size):
+            for px in range(size):
+                rec = {}
+
+                def hook(inst, args, res, rec=rec):
+                    if inst == 69: rec["d"] = [np.float32(c) for c in res]
+                    if inst == 43 and not isinstance(args[0], list): rec["iter"] = int(round(float(args[0]) * 128.0))
+
+                outs = []
+                for vt in (1, 2, 0, 3):
+                    with np.errstate(all="ignore"):
+                        r = frag.run({("builtin", 15): [np.float32(px + 0.5), np.float32(py + 0.5), np.float32(0.5), np.float32(1)]},
+                                     {(0, 0): words, (1, 0): cam.view(np.uint32)},
+                                     [size, size, vt, 0, 0, 1, [np.float32(0.1), np.float32(0.2), np.float32(0.3)], np.float32(0)],
+                                     on_ext=hook)
+                    outs.append([np.float32(c) for c in r[out_var][:3]])
+                rows.append((list(TRACER_CAMERAS).index(cname), px, py, rec["d"], outs[0], outs[1], outs[2], rec["iter"]))
+    dt = np.dtype([("cam", "<i4"), ("px", "<i4"), ("py", "<i4"), ("d", "<f4", 3), ("normal", "<f4", 3), ("pos", "<f4", 3),
+                   ("colour", "<f4", 3), ("iter", "<i4")])
+    arr = np.array([(c, x, y, d, n, p, col, it) for c, x, y, d, n, p, col, it in rows], dtype=dt)
+    cams = np.array([np.concatenate([np.asarray(v, np.float32) for v in TRACER_CAMERAS[k]]) for k in TRACER_CAMERAS], np.float32)
+    return dict(build_case=build_case, size=size, cameras=cams, rays=arr)
+
+
 if __name__ == "__main__":
     import time
+    if "--tracer-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
+        for bc in ("soup60_L7_conservative", "heightfield11_L5_conservative"):
+            t = time.time()
+            o = make_tracer_case(bc)
+            np.savez_compressed(os.path.join(HERE, "spirv_tracer_" + bc + ".npz"), **o)
+            hit = (o["rays"]["normal"] != 0.5).any(axis=1)
+            print("tracer", bc, len(o["rays"]), "rays,", int(hit.sum()), "hits", f"{time.time() - t:.0f}s", flush=True)
+        if "--tracer-only" in sys.argv:
+            sys.exit(0)
     o = make_textured_frag_case()
     np.savez_compressed(os.path.join(HERE, "spirv_frag_textured.npz"), **o)
     print("textured frag", len(o["out"]), "samples,", int((o["out"][:, 0] == 0).sum()), "discarded", flush=True)

@@ -76,6 +76,12 @@ def test_full_path_textured(emu, mode):
     assert info["fragments"] > 500
 
 
+def test_raymarcher_and_builder_against_reference_tracer_golden(emu):
+    """Kernel logic of the builder + the ray marcher on the CPU emulator vs the executed octree_tracer.frag."""
+    from tests.test_spirv_golden import TRACER, cuda_tree_traced_like_reference
+    cuda_tree_traced_like_reference(emu, TRACER[0])
+
+
 def test_empty_scene(emu):
     m = scenes.Mesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), np.zeros(0, scenes.DRAW_DTYPE), "empty")
     info = check_against_oracle(emu, m, 4, api.CENTER)

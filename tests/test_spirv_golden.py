@@ -95,6 +95,62 @@ def test_oracle_textured_shading_equals_reference_frag_shader():
             assert o == int(rgb), (v, hex(o), hex(int(rgb)))
 
 
+TRACER = sorted(glob.glob(os.path.join(HERE, "golden", "spirv_tracer_*.npz")))
+
+
+def check_hits_against_tracer_golden(g, hit, pos, colour, normal, iters):
+    """The executed octree_tracer.frag wrote oColor for the views normal*0.5+0.5, pos-1, pow(colour, 1/2.2) (a miss
+    shows normal 0 and pos 1, octree_tracer.frag:37-41) and the iteration count."""
+    r = g["rays"]
+    ghit = (r["normal"] != 0.5).any(axis=1)
+    assert (hit == ghit).all(), "hit / miss differs from the reference tracer"
+    assert (iters == r["iter"]).all(), "iteration counts differ"
+    h = ghit
+    assert ((normal[h] * np.float32(0.5) + np.float32(0.5)) == r["normal"][h]).all()
+    assert ((pos[h] - np.float32(1.0)) == r["pos"][h]).all(), "hit positions differ (bit-exact expected)"
+    assert np.allclose(np.power(colour[h].astype(np.float64), 1.0 / 2.2), r["colour"][h], atol=1e-6)  # pow: driver precision
+    return int(h.sum())
+
+
+@pytest.mark.parametrize("path", TRACER, ids=[os.path.basename(p) for p in TRACER])
+def test_oracle_raymarch_equals_reference_tracer_shader(path):
+    """Octree_RayMarchLeaf as compiled into octree_tracer.frag, executed on a node buffer built by the reference's own
+    builder shaders, versus the oracle's restatement: hits, iteration counts, normals and positions bit for bit."""
+    g = np.load(path)
+    words = np.load(os.path.join(HERE, "golden", "spirv_build_" + str(g["build_case"]) + ".npz"))["words"]
+    r, cams = g["rays"], g["cameras"]
+    out = [oracle.raymarch_leaf(words, cams[c][:3], d) for c, d in zip(r["cam"], r["d"])]
+    n = check_hits_against_tracer_golden(g, np.array([o[0] for o in out]), np.array([o[1] for o in out]),
+                                         np.array([o[2] for o in out]), np.array([o[3] for o in out]),
+                                         np.array([o[4] for o in out]))
+    assert n > 100
+
+
+def cuda_tree_traced_like_reference(lib, path):
+    """The drop-in claim end to end: the tree the CUDA builder makes from the fragments the reference's shaders consumed,
+    traversed by the CUDA port of the reference's ray marcher, shows what the reference's tracer shows on the
+    reference-built tree -- although the two node buffers order their blocks differently."""
+    g = np.load(path)
+    b = np.load(os.path.join(HERE, "golden", "spirv_build_" + str(g["build_case"]) + ".npz"))
+    level = int(b["level"])
+    x, y, z, c = unpack(b["packed"])
+    keys = (morton_np(x, y, z, level) << np.uint64(24)) | c.astype(np.uint64)
+    vox = api.Voxelizer.CreateFromFragments(keys, level, lib=lib)
+    builder = api.OctreeBuilder.Create(vox)
+    vox.CmdVoxelize()
+    builder.CmdBuild()
+    r, cams = g["rays"], g["cameras"]
+    hits = api.raymarch_leaf(builder.GetOctree(), cams[r["cam"]][:, :3], r["d"], lib=lib)
+    n = check_hits_against_tracer_golden(g, hits["hit"] != 0, hits["pos"], hits["colour"], hits["normal"], hits["iter"])
+    assert n > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", TRACER, ids=[os.path.basename(p) for p in TRACER])
+def test_cuda_tree_and_raymarcher_equal_reference_tracer(path):
+    cuda_tree_traced_like_reference(api.get_library(), path)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", BUILD, ids=[os.path.basename(p) for p in BUILD])
 def test_cuda_builder_equals_reference_compute_shaders(path):
