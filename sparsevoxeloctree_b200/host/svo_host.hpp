@@ -19,8 +19,15 @@
 //
 // Header only; link against libsvo_b200.so.  No CPU fallback exists behind these calls.
 #pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <sstream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -47,6 +54,165 @@ struct MeshData {
 	std::vector<svo_draw> draws;
 	std::vector<TextureData> textures; // indexed by svo_draw::texture_id
 };
+
+// Scene::load_meshes (src/Scene.cpp:36-143) without tinyobjloader: Wavefront OBJ + MTL -> MeshData.
+// One mesh per material, vertices (position, (u, 1 - v)), positions normalised to [-1,1]^3 in fp32 (Scene.cpp:90-99),
+// empty meshes dropped, the rest sorted by size (Scene.cpp:123-132), one draw per mesh with
+// packUnorm4x8(vec4(Kd, 0)) and the texture id of map_Kd (ids in material order, Scene.cpp:101-121).
+// Polygons are triangulated as a fan.  Image decoding is the caller's: texture_filenames receives the paths
+// (Scene.cpp:139-142) and MeshData::textures is to be filled from them (the reference uses stb_image, Scene.cpp:247);
+// draws whose texture is not supplied must have texture_id reset to 0xffffffff.
+inline bool LoadObj(const std::string &filename, MeshData *out, std::vector<std::string> *texture_filenames) {
+	struct Material {
+		std::string name, map_kd;
+		float kd[3] = {0.f, 0.f, 0.f};
+		bool has_kd = false;
+		std::vector<Vertex> vertices;
+	};
+	const size_t slash = filename.find_last_of("/\\");
+	const std::string base_dir = slash == std::string::npos ? std::string() : filename.substr(0, slash + 1);
+	std::ifstream obj(filename);
+	if (!obj) {
+		fprintf(stderr, "Failed to load %s\n", filename.c_str());
+		return false;
+	}
+	std::vector<float> v, vt;
+	std::vector<Material> mats;
+	std::map<std::string, size_t> mat_index;
+	auto load_mtl = [&](const std::string &path) {
+		std::ifstream mtl(path);
+		std::string line;
+		Material *cur = nullptr;
+		while (std::getline(mtl, line)) {
+			line = line.substr(0, line.find('#'));
+			std::istringstream ls(line);
+			std::string tok;
+			if (!(ls >> tok)) continue;
+			if (tok == "newmtl") {
+				std::string name;
+				ls >> name;
+				if (mat_index.count(name)) {
+					cur = nullptr;
+					continue;
+				}
+				mat_index[name] = mats.size();
+				mats.emplace_back();
+				cur = &mats.back();
+				cur->name = name;
+			} else if (cur && tok == "Kd") {
+				ls >> cur->kd[0] >> cur->kd[1] >> cur->kd[2];
+				cur->has_kd = true;
+			} else if (cur && tok == "map_Kd") {
+				std::string w;
+				while (ls >> w) cur->map_kd = w; // options precede the file name
+				if (!cur->has_kd) cur->kd[0] = cur->kd[1] = cur->kd[2] = 0.6f;
+			}
+		}
+	};
+	long cur_mat = -1;
+	float pmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, pmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	std::string line;
+	while (std::getline(obj, line)) {
+		line = line.substr(0, line.find('#'));
+		std::istringstream ls(line);
+		std::string tok;
+		if (!(ls >> tok)) continue;
+		if (tok == "v") {
+			float x = 0, y = 0, z = 0;
+			ls >> x >> y >> z;
+			v.insert(v.end(), {x, y, z});
+		} else if (tok == "vt") {
+			float a = 0, b = 0;
+			ls >> a >> b;
+			vt.insert(vt.end(), {a, b});
+		} else if (tok == "mtllib") {
+			std::string name;
+			ls >> name;
+			load_mtl(base_dir + name);
+		} else if (tok == "usemtl") {
+			std::string name;
+			ls >> name;
+			auto it = mat_index.find(name);
+			cur_mat = it == mat_index.end() ? -1 : (long)it->second;
+		} else if (tok == "f") {
+			if (cur_mat < 0) {
+				fprintf(stderr, "face without a material\n");
+				return false;
+			}
+			std::vector<Vertex> corners;
+			std::string c;
+			while (ls >> c) {
+				long vi = strtol(c.c_str(), nullptr, 10), ti = 0;
+				const size_t s1 = c.find('/');
+				if (s1 != std::string::npos && s1 + 1 < c.size() && c[s1 + 1] != '/') ti = strtol(c.c_str() + s1 + 1, nullptr, 10);
+				vi = vi > 0 ? vi - 1 : (long)(v.size() / 3) + vi;
+				Vertex vert{};
+				for (int k = 0; k < 3; ++k) vert.m_position[k] = v[3 * vi + k];
+				if (ti != 0) {
+					ti = ti > 0 ? ti - 1 : (long)(vt.size() / 2) + ti;
+					vert.m_texcoord[0] = vt[2 * ti];
+					vert.m_texcoord[1] = 1.0f - vt[2 * ti + 1];
+				}
+				corners.push_back(vert);
+			}
+			for (size_t k = 1; k + 1 < corners.size(); ++k)
+				for (const Vertex &vert : {corners[0], corners[k], corners[k + 1]}) {
+					mats[cur_mat].vertices.push_back(vert);
+					for (int a = 0; a < 3; ++a) {
+						pmin[a] = std::min(pmin[a], vert.m_position[a]);
+						pmax[a] = std::max(pmax[a], vert.m_position[a]);
+					}
+				}
+		}
+	}
+	if (mats.empty()) {
+		fprintf(stderr, "No material found\n");
+		return false;
+	}
+	// normalize all the vertices to [-1, 1] (Scene.cpp:90-99)
+	const float extent = std::max(pmax[0] - pmin[0], std::max(pmax[1] - pmin[1], pmax[2] - pmin[2])) * 0.5f;
+	const float inv_extent = 1.0f / extent;
+	float center[3];
+	for (int a = 0; a < 3; ++a) center[a] = (pmax[a] + pmin[a]) * 0.5f;
+	std::map<std::string, uint32_t> tex_ids;
+	texture_filenames->clear();
+	std::vector<uint32_t> tex_of(mats.size(), 0xffffffffu);
+	for (size_t i = 0; i < mats.size(); ++i) {
+		if (mats[i].vertices.empty() || mats[i].map_kd.empty()) continue;
+		auto it = tex_ids.find(mats[i].map_kd);
+		if (it == tex_ids.end()) {
+			it = tex_ids.emplace(mats[i].map_kd, (uint32_t)tex_ids.size()).first;
+			std::string rel = mats[i].map_kd;
+			std::replace(rel.begin(), rel.end(), '\\', '/');
+			texture_filenames->push_back(base_dir + rel);
+		}
+		tex_of[i] = it->second;
+	}
+	std::vector<size_t> order;
+	for (size_t i = 0; i < mats.size(); ++i)
+		if (!mats[i].vertices.empty()) order.push_back(i);
+	if (order.empty()) {
+		fprintf(stderr, "Empty mesh\n");
+		return false;
+	}
+	std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return mats[l].vertices.size() > mats[r].vertices.size(); });
+	out->vertices.clear(), out->indices.clear(), out->draws.clear();
+	for (size_t i : order) {
+		auto pack = [](float c) { return (uint32_t)std::nearbyint(std::min(std::max(c, 0.f), 1.f) * 255.f); };
+		svo_draw d{};
+		d.first_index = (uint32_t)out->vertices.size();
+		d.index_count = (uint32_t)mats[i].vertices.size();
+		d.texture_id = tex_of[i];
+		d.albedo_rgba8 = pack(mats[i].kd[0]) | (pack(mats[i].kd[1]) << 8) | (pack(mats[i].kd[2]) << 16);
+		out->draws.push_back(d);
+		for (Vertex vert : mats[i].vertices) {
+			for (int a = 0; a < 3; ++a) vert.m_position[a] = (vert.m_position[a] - center[a]) * inv_extent;
+			out->indices.push_back((uint32_t)out->vertices.size());
+			out->vertices.push_back(vert);
+		}
+	}
+	return true;
+}
 
 class Scene {
 	svo_scene *m_handle{};

@@ -4,12 +4,28 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <string>
 
 #include "../../sparsevoxeloctree_b200/host/svo_host.hpp"
 
 using namespace svo_host;
 
 int main(int argc, char **argv) {
+	if (argc > 2 && std::string(argv[1]) == "--obj") { // dump what LoadObj makes of a file (no GPU needed)
+		MeshData mesh;
+		std::vector<std::string> tex;
+		if (!LoadObj(argv[2], &mesh, &tex)) return 1;
+		printf("%zu %zu %zu\n", mesh.vertices.size(), mesh.draws.size(), tex.size());
+		for (const svo_draw &d : mesh.draws) printf("d %u %u %u %u\n", d.first_index, d.index_count, d.texture_id, d.albedo_rgba8);
+		for (const Vertex &v : mesh.vertices) {
+			uint32_t b[5];
+			memcpy(b, &v, sizeof(b));
+			printf("v %08x %08x %08x %08x %08x\n", b[0], b[1], b[2], b[3], b[4]);
+		}
+		for (const std::string &t : tex) printf("t %s\n", t.c_str());
+		return 0;
+	}
 	const uint32_t level = argc > 1 ? (uint32_t)atoi(argv[1]) : 7;
 	const int n = argc > 2 ? atoi(argv[2]) : 33;
 	MeshData mesh;
