@@ -144,6 +144,9 @@ template <int BLOCK, int ITEMS, int RBITS> struct OnesweepCfg {
 #ifndef SVO_OS_BALLOT
 #define SVO_OS_BALLOT 1 // 1: warp multi-split by one vote per digit bit; 0: MATCH.ANY (measured slower on sm_100a)
 #endif
+#ifndef SVO_OS_BRANCHY_ATOMIC
+#define SVO_OS_BRANCHY_ATOMIC 0
+#endif
 #ifndef SVO_OS_LOOKBACK_DEPTH
 #define SVO_OS_LOOKBACK_DEPTH 8
 #endif
@@ -152,6 +155,37 @@ constexpr int LOOKBACK_DEPTH = SVO_OS_LOOKBACK_DEPTH; // predecessor states in f
 SVO_DEV void lb_backoff() {
 #if defined(__CUDA_ARCH__)
 	__nanosleep(64);
+#endif
+}
+
+// peers &= (lanes whose digit agrees with mine in one bit): test, vote, conditional complement, and -- 4 instructions
+SVO_DEV unsigned split_by_bit(unsigned peers, uint32_t d, uint32_t bitmask) {
+#if defined(__CUDA_ARCH__)
+	asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 t, p, 0xffffffff;\n\t"
+	    "@!p not.b32 t, t;\n\tand.b32 %0, %0, t;\n\t}"
+	    : "+r"(peers)
+	    : "r"(d), "r"(bitmask));
+	return peers;
+#else
+	const bool p = (d & bitmask) != 0u;
+	const unsigned b = __ballot_sync(FULL_MASK, p);
+	return peers & (p ? b : ~b);
+#endif
+}
+
+// Shared-memory atomic add executed by the group leaders only, as ONE predicated instruction: written as a branch
+// the compiler wraps it in a divergence region (BSSY / BRA / BSYNC) per item.
+SVO_DEV uint32_t leader_atomic_add(uint32_t *addr, uint32_t v, bool leader) {
+#if defined(__CUDA_ARCH__) && !SVO_OS_BRANCHY_ATOMIC
+	uint32_t old = 0;
+	const uint32_t a = (uint32_t)__cvta_generic_to_shared(addr);
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+	             : "+r"(old)
+	             : "r"(a), "r"(v), "r"((uint32_t)leader)
+	             : "memory");
+	return old;
+#else
+	return leader ? atomicAdd(addr, v) : 0u;
 #endif
 }
 
@@ -200,20 +234,13 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 #elif SVO_OS_BALLOT
 		unsigned peers = FULL_MASK; // multi-split by one vote per digit bit instead of MATCH.ANY
 #pragma unroll
-		for (int bb = 0; bb < RBITS; ++bb) {
-			const uint32_t bit = (d >> bb) & 1u;
-			peers &= ~(__ballot_sync(FULL_MASK, bit) ^ (0u - bit));
-		}
-		if (!FULL) {
-			const uint32_t bit = d >> RBITS;
-			peers &= ~(__ballot_sync(FULL_MASK, bit) ^ (0u - bit));
-		}
+		for (int bb = 0; bb < RBITS + (FULL ? 0 : 1); ++bb) // (bit RBITS: the padding bin of a partial tile)
+			peers = split_by_bit(peers, d, 1u << bb);
 #else
 		const unsigned peers = __match_any_sync(FULL_MASK, d);
 #endif
 		const uint32_t below = (uint32_t)__popc(peers & lt_mask);
-		uint32_t base = 0;
-		if (below == 0u) base = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+		const uint32_t base = leader_atomic_add(&wh[d], (uint32_t)__popc(peers), below == 0u);
 		SVO_EMU_WARP_ORDER(); // hardware issues a warp's atomics in program order; the emulator's lanes are free-running
 		rank[i] = __shfl_sync(FULL_MASK, base, __ffs((int)peers) - 1) + below;
 	}
@@ -273,6 +300,8 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 
 	// decoupled look-back, per digit.  Kept lean on purpose: every digit thread of every tile spins here, so
 	// the loop body is 32-bit pointer arithmetic with immediate offsets and 4 predecessor states in flight.
+	// (Measured: more states in flight per step -- 8, 16, 32, or both digits of a thread at once -- is SLOWER; the
+	// extra polling traffic costs more than the shorter walk saves.)
 	if (threadIdx.x < DTHREADS) {
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
