@@ -301,7 +301,8 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 	// decoupled look-back, per digit.  Kept lean on purpose: every digit thread of every tile spins here, so
 	// the loop body is 32-bit pointer arithmetic with immediate offsets and 4 predecessor states in flight.
 	// (Measured: more states in flight per step -- 8, 16, 32, or both digits of a thread at once -- is SLOWER; the
-	// extra polling traffic costs more than the shorter walk saves.)
+	// extra polling traffic costs more than the shorter walk saves; issuing the first window before the reorder
+	// loop is slower too -- the prefetched states are stale by the time they are looked at.)
 	if (threadIdx.x < DTHREADS) {
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
