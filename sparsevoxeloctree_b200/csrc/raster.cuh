@@ -241,46 +241,50 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
     k_emit_large(RasterParams rp, TexView tv, const LargeTri *__restrict__ large, const UvMap *__restrict__ luv, DenseRows rows,
                  uint32_t n_rows, uint64_t n_frag_large, uint64_t *__restrict__ frags /* already offset to the large region */) {
 	__shared__ uint32_t s_off[EMIT_TILE + 2];
-	__shared__ uint32_t s_first;
+	__shared__ uint32_t s_lut[1024]; // part1by2_10: Morton spread of 10 coordinate bits
+	__shared__ uint32_t s_first, s_last;
 	const int lane = threadIdx.x & 31;
 	const uint64_t c0 = (uint64_t)blockIdx.x * EMIT_TILE;
 	const uint64_t c1 = c0 + EMIT_TILE < n_frag_large ? c0 + EMIT_TILE : n_frag_large;
-	if (threadIdx.x < 32) {
-		// last row with off <= c0 (rows are non-empty, so it contains fragment c0): 32-ary search by one warp
-		uint32_t lo = 0, hi = n_rows; // invariant: off[lo] <= c0 < off[hi]
+	if (threadIdx.x < 64) {
+		// warp 0: last row with off <= c0 (rows are non-empty, so it contains fragment c0); warp 1: last row with
+		// off <= c1 - 1 (contains the tile's last fragment).  32-ary searches, one ballot per level.
+		const uint64_t target = threadIdx.x < 32 ? c0 : c1 - 1;
+		uint32_t lo = 0, hi = n_rows; // invariant: off[lo] <= target < off[hi]
 		while (hi - lo > 1) {
 			const uint32_t step = (hi - lo + 31u) / 32u;
 			const uint32_t idx = lo + (uint32_t)lane * step;
-			const bool ok = idx < hi && rows.off[idx] <= c0; // monotone in the lane; lane 0 always holds
+			const bool ok = idx < hi && rows.off[idx] <= target; // monotone in the lane; lane 0 always holds
 			const unsigned b = __ballot_sync(FULL_MASK, ok);
 			const uint32_t k = 31u - (uint32_t)__clz((int)b);
 			lo += k * step;
 			hi = lo + step < hi ? lo + step : hi;
 		}
-		if (lane == 0) s_first = lo;
+		if (lane == 0) (threadIdx.x < 32 ? s_first : s_last) = lo;
 	}
+	for (uint32_t i = threadIdx.x; i < 1024u; i += EMIT_BLOCK) s_lut[i] = part1by2_10(i);
 	__syncthreads();
-	const uint32_t r_first = s_first;
-	// stage the offsets of the rows that intersect [c0, c1): at most EMIT_TILE rows (+1 end sentinel)
-	for (uint32_t i = threadIdx.x; i < EMIT_TILE + 1; i += EMIT_BLOCK) {
-		const uint32_t r = r_first + i;
-		s_off[i] = r <= n_rows ? rows.off[r] : 0xffffffffu;
-	}
+	const uint32_t r_first = s_first, n_staged = s_last - s_first + 1u; // rows that intersect [c0, c1): at most EMIT_TILE
+	for (uint32_t i = threadIdx.x; i <= n_staged; i += EMIT_BLOCK) s_off[i] = rows.off[r_first + i]; // + the end of the last one
 	__syncthreads();
 
 	const uint64_t j0 = c0 + (uint64_t)threadIdx.x * EMIT_ITEMS;
 	if (j0 >= c1) return;
-	uint32_t lo = 0, hi = EMIT_TILE + 1; // last staged row with off <= j0
+	uint32_t lo = 0, hi = n_staged; // last staged row with off <= j0
 	while (hi - lo > 1) {
 		const uint32_t mid = (lo + hi) >> 1;
 		if (s_off[mid] <= j0) lo = mid; else hi = mid;
 	}
+	// Per row the thread keeps the depth plane and the Morton code of (x, y) in registers; per fragment it evaluates
+	// the depth (the same operations as pixel_depth_row), looks up the spread of the depth voxel, and steps x
+	// directly in spread form.  Keys are assembled as two 32-bit halves: the low 10 bits of the three coordinates
+	// make the low 30 Morton bits, bits 10.. (levels above 10 only) the rest.
+	const bool deep = rp.res > 1024u;
 	uint64_t out[EMIT_ITEMS];
 	uint32_t row_end = 0; // forces the row set-up on the first fragment
-	const LargeTri *lt = nullptr;
-	double row_term = 0.0;
-	uint64_t m_row = 0, m_x = 0;
-	uint32_t shx = 0, shz = 0, oz = 0, rgb = 0;
+	double row_term = 0.0, dzdx = 0.0, dx = 0.0;
+	uint32_t zr_lo = 0, zr_hi = 0, oz = 0, rgb = 0;
+	uint32_t xs = 0, xmask = 0, xone = 0, xl = 0, row_lo = 0, row_hi = 0, hi_xrow = 0, shx = 0, shz = 0;
 	int32_t px = 0, py_tex = 0;
 	const UvMap *um = nullptr; // non-null: the row belongs to a textured triangle
 	--lo;
@@ -292,20 +296,26 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 				++lo;
 				const uint32_t r = r_first + lo;
 				const uint32_t xy = rows.xy[r];
-				lt = &large[rows.li[r]];
+				const LargeTri *lt = &large[rows.li[r]];
 				row_end = s_off[lo + 1];
 				px = (int32_t)(xy & 0xffffu) + (int32_t)(j - s_off[lo]);
 				const int32_t py = (int32_t)(xy >> 16);
 				row_term = depth_row_term(lt->ts, py);
+				dzdx = lt->ts.dzdx, zr_lo = lt->ts.zr_lo, zr_hi = lt->ts.zr_hi;
+				dx = (double)((px * 256 + 128) - lt->ts.X0); // exact; advancing it by 256.0 per pixel stays exact
 				// voxel = axis 0: (uz, px, py); 1: (py, uz, px); 2: (px, py, uz)   (voxelizer.frag:24)
 				const uint32_t axis = lt->ts.axis;
 				const uint32_t wx = axis == 0u ? 1u : (axis == 1u ? 2u : 0u); // world axis of screen x
 				const uint32_t wy = axis == 0u ? 2u : (axis == 1u ? 0u : 1u);
-				const uint32_t wz = axis;
-				shx = wx, shz = wz;
-				oz = rp.origin[wz];
-				m_row = part1by2((uint32_t)py - rp.origin[wy]) << wy;
-				m_x = part1by2((uint32_t)px - rp.origin[wx]);
+				shx = wx, shz = axis;
+				oz = rp.origin[axis];
+				xl = (uint32_t)px - rp.origin[wx];
+				const uint32_t yl = (uint32_t)py - rp.origin[wy];
+				xmask = 0x09249249u << wx, xone = 1u << wx;
+				xs = s_lut[xl & 1023u] << wx;
+				row_lo = s_lut[yl & 1023u] << wy;
+				row_hi = s_lut[(yl >> 10) & 1023u] << wy;
+				hi_xrow = (s_lut[(xl >> 10) & 1023u] << wx) | row_hi;
 				rgb = lt->rgb & 0xffffffu;
 				if (TEX) {
 					um = lt->textured ? &luv[rows.li[r]] : nullptr;
@@ -313,11 +323,15 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 				}
 			}
 			if (TEX && um) sample_colour(tv, *um, px, py_tex, rgb); // opaque texture (alpha-tested ones never come here)
-			const uint32_t uz = pixel_depth_row(lt->ts, rp.res, px, row_term);
-			const uint64_t m = (m_x << shx) | (part1by2(uz - oz) << shz) | m_row;
-			out[k] = (m << 24) | (uint64_t)rgb;
-			m_x = part1by2_increment(m_x);
-			++px;
+			const uint32_t zl = depth_voxel_range(rp.res, dfma(dzdx, dx, row_term), zr_lo, zr_hi) - oz;
+			const uint32_t m_lo = xs | (s_lut[zl & 1023u] << shz) | row_lo;
+			uint32_t m_hi = 0;
+			if (deep) m_hi = hi_xrow | (s_lut[(zl >> 10) & 1023u] << shz);
+			out[k] = ((uint64_t)((m_lo >> 8) | (m_hi << 22)) << 32) | (uint64_t)((m_lo << 24) | rgb);
+			xs = ((xs | ~xmask) + xone) & xmask; // x + 1 in spread form: the gaps are filled so that the carry ripples
+			++xl, ++px;
+			dx += 256.0;
+			if (deep && xs == 0u) hi_xrow = (s_lut[(xl >> 10) & 1023u] << shx) | row_hi; // x crossed a multiple of 1024
 		} else
 			out[k] = 0;
 	}

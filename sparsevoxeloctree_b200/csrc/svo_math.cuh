@@ -350,14 +350,15 @@ SVO_HD inline double plane_z_row(const TriSetup &t, int32_t px, double row_term)
 	const int32_t cx = px * 256 + 128;
 	return dfma(t.dzdx, (double)(cx - t.X0), row_term);
 }
-SVO_HD inline uint32_t depth_voxel(const TriSetup &t, uint32_t res, double z) {
+SVO_HD inline uint32_t depth_voxel_range(uint32_t res, double z, uint32_t zr_lo, uint32_t zr_hi) {
 	double zs = dmul(z, (double)res);
 	uint32_t uz = !(zs > 0.0) ? 0u : (zs >= (double)res ? res - 1u : (uint32_t)zs);
-	uz = tmax(uz, t.zr_lo);
-	uz = tmin(uz, t.zr_hi);
+	uz = tmax(uz, zr_lo);
+	uz = tmin(uz, zr_hi);
 	uz = tmin(uz, res - 1u);
 	return uz;
 }
+SVO_HD inline uint32_t depth_voxel(const TriSetup &t, uint32_t res, double z) { return depth_voxel_range(res, z, t.zr_lo, t.zr_hi); }
 SVO_HD inline uint32_t pixel_depth_row(const TriSetup &t, uint32_t res, int32_t px, double row_term) {
 	return depth_voxel(t, res, plane_z_row(t, px, row_term));
 }
