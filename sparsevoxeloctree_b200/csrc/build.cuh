@@ -41,10 +41,10 @@ constexpr int MAX_LEVEL = 16;
 #define SVO_RF_ITEMS 16
 #endif
 #ifndef SVO_RF_MINB
-#define SVO_RF_MINB 4
+#define SVO_RF_MINB 3
 #endif
 constexpr int RF_BLOCK = SVO_RF_BLOCK, RF_ITEMS = SVO_RF_ITEMS, RF_TILE = RF_BLOCK * RF_ITEMS, RF_NW = RF_BLOCK / 32;
-static_assert(RF_ITEMS * RF_NW <= 128 && (RF_ITEMS * RF_NW) % 32 == 0, "the (row, warp) count matrix is scanned by one warp");
+static_assert(RF_ITEMS * RF_NW <= 512 && (RF_ITEMS * RF_NW) % 32 == 0, "the (row, warp) count matrix is scanned by one warp");
 constexpr int RF_CPL = RF_ITEMS * RF_NW / 32; // counts per lane in that scan
 
 struct FusedOut {
@@ -122,7 +122,29 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 	uint64_t agg[K], pre[K];
 #pragma unroll
 	for (int j = 0; j < K; ++j) agg[j] = s_total[j];
-	block_lookback<RF_BLOCK, K>(state, tile, agg, pre, s_red, s_idx);
+	block_lookback_publish<K>(state, tile, agg);
+
+	// the leaf words do not need the prefix: computing them here puts work between publishing this tile's
+	// aggregates and looking at the predecessors', which shortens the wait
+	uint32_t leaf_word[RF_ITEMS];
+#pragma unroll
+	for (int i = 0; i < RF_ITEMS; ++i) {
+		leaf_word[i] = 0;
+		if (!(packed[i] & 1u)) continue;
+		const uint32_t e = i * RF_BLOCK + threadIdx.x;
+		const uint64_t key = s_keys[e + 1];
+		uint32_t acc = leaf_first((uint32_t)(key & 0xffffffu));
+		if (((s_keys[e + 2] ^ key) >> 24) == 0) { // the voxel has more fragments: fold them in emission order
+			for (uint64_t q = (uint64_t)e + 1; tile_base + q < n; ++q) {
+				const uint64_t kk = q < RF_TILE ? s_keys[q + 1] : frags[tile_base + q];
+				if ((kk >> 24) != (key >> 24)) break;
+				acc = leaf_accumulate(acc, (uint32_t)(kk & 0xffffffu));
+			}
+		}
+		leaf_word[i] = acc;
+	}
+
+	block_lookback<RF_BLOCK, K>(state, tile, agg, pre, s_red, s_idx, true);
 	if (tile == tiles - 1 && threadIdx.x == 0) {
 #pragma unroll
 		for (int j = 0; j < K; ++j) *out.count[j] = pre[j] + agg[j];
@@ -137,14 +159,7 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 		const uint32_t e = i * RF_BLOCK + threadIdx.x;
 		const uint64_t key = s_keys[e + 1];
 		const uint64_t u0 = p0 + s_cnt[0][i * RF_NW + warp] + ((pk >> 3) & 31u);
-		uint32_t acc = leaf_first((uint32_t)(key & 0xffffffu));
-		if (((s_keys[e + 2] ^ key) >> 24) == 0) { // the voxel has more fragments: fold them in emission order
-			for (uint64_t q = (uint64_t)e + 1; tile_base + q < n; ++q) {
-				const uint64_t kk = q < RF_TILE ? s_keys[q + 1] : frags[tile_base + q];
-				if ((kk >> 24) != (key >> 24)) break;
-				acc = leaf_accumulate(acc, (uint32_t)(kk & 0xffffffu));
-			}
-		}
+		const uint32_t acc = leaf_word[i];
 		out.leaf[u0] = acc;
 		out.slot0[u0] = (unsigned char)((key >> 24) & 7u);
 		if (K == 1) out.keys_top[u0] = key >> 24;

@@ -98,17 +98,23 @@ SVO_DEV uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t agg
 // the kernel.  A tile seen half-way through its aggregate -> prefix upgrade is polled again.
 // All threads of the block must call.  Returns the K exclusive prefixes in excl[] on every thread and publishes
 // this tile's aggregates, then its inclusive prefixes.
+// The two halves can be called apart: publish the aggregates as soon as they are known, do whatever work does not
+// need the prefix, then look back -- the later the look-back, the less it has to wait for its neighbours.
+template <int K> SVO_DEV void block_lookback_publish(uint64_t *state, uint32_t tile, const uint64_t (&aggregate)[K]) {
+#pragma unroll
+	for (int j = 0; j < K; ++j)
+		if (threadIdx.x == (unsigned)j) lb_store(&state[(uint64_t)tile * K + j], lb_pack(tile == 0 ? LB_PREFIX : LB_AGGREGATE, aggregate[j]));
+}
 template <int BLOCK, int K>
 SVO_DEV void block_lookback(uint64_t *state, uint32_t tile, const uint64_t (&aggregate)[K], uint64_t (&excl)[K],
-                            uint64_t *s_red /* (BLOCK/32)*K words */, uint32_t *s_idx /* 2*(BLOCK/32) words */) {
+                            uint64_t *s_red /* (BLOCK/32)*K words */, uint32_t *s_idx /* 2*(BLOCK/32) words */,
+                            bool published = false) {
 	constexpr int NW = BLOCK / 32;
 	constexpr uint32_t NONE = 0xffffffffu;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (!published) block_lookback_publish<K>(state, tile, aggregate);
 #pragma unroll
-	for (int j = 0; j < K; ++j) {
-		excl[j] = 0;
-		if (threadIdx.x == (unsigned)j) lb_store(&state[(uint64_t)tile * K + j], lb_pack(tile == 0 ? LB_PREFIX : LB_AGGREGATE, aggregate[j]));
-	}
+	for (int j = 0; j < K; ++j) excl[j] = 0;
 	if (tile == 0) return; // block-uniform
 	int64_t base = (int64_t)tile - 1;
 	for (;;) {
