@@ -19,7 +19,13 @@ namespace svo {
 
 constexpr int64_t SMALL_AREA = 256; // candidate-rectangle pixels handled by a single thread
 constexpr int RASTER_BLOCK = 128;
-constexpr int EMIT_BLOCK = 256, EMIT_ITEMS = 8, EMIT_TILE = EMIT_BLOCK * EMIT_ITEMS;
+#ifndef SVO_EMIT_BLOCK
+#define SVO_EMIT_BLOCK 256
+#endif
+#ifndef SVO_EMIT_ITEMS
+#define SVO_EMIT_ITEMS 8
+#endif
+constexpr int EMIT_BLOCK = SVO_EMIT_BLOCK, EMIT_ITEMS = SVO_EMIT_ITEMS, EMIT_TILE = EMIT_BLOCK * EMIT_ITEMS;
 
 struct DrawRec {
 	uint32_t first_index, tri_base, tri_count, rgb;
