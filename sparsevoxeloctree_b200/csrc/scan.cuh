@@ -90,89 +90,6 @@ SVO_DEV uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t agg
 	return exclusive;
 }
 
-// Block-wide look-back for K chains at once.  The single-warp version above advances 32 tiles per L2 round
-// trip, which caps a chained kernel at 32 * tile_bytes / round_trip -- below HBM speed on B200 for 16-32 KB
-// tiles.  Here every thread of the block inspects one predecessor (BLOCK tiles per round trip): the block finds
-// the nearest predecessor that has published its K inclusive prefixes, waits until everything in front of it
-// has at least published its K aggregates, and sums.  state layout: [tile][K] words (lb_pack), zeroed before
-// the kernel.  A tile seen half-way through its aggregate -> prefix upgrade is polled again.
-// All threads of the block must call.  Returns the K exclusive prefixes in excl[] on every thread and publishes
-// this tile's aggregates, then its inclusive prefixes.
-// The two halves can be called apart: publish the aggregates as soon as they are known, do whatever work does not
-// need the prefix, then look back -- the later the look-back, the less it has to wait for its neighbours.
-template <int K> SVO_DEV void block_lookback_publish(uint64_t *state, uint32_t tile, const uint64_t (&aggregate)[K]) {
-#pragma unroll
-	for (int j = 0; j < K; ++j)
-		if (threadIdx.x == (unsigned)j) lb_store(&state[(uint64_t)tile * K + j], lb_pack(tile == 0 ? LB_PREFIX : LB_AGGREGATE, aggregate[j]));
-}
-template <int BLOCK, int K>
-SVO_DEV void block_lookback(uint64_t *state, uint32_t tile, const uint64_t (&aggregate)[K], uint64_t (&excl)[K],
-                            uint64_t *s_red /* (BLOCK/32)*K words */, uint32_t *s_idx /* 2*(BLOCK/32) words */,
-                            bool published = false) {
-	constexpr int NW = BLOCK / 32;
-	constexpr uint32_t NONE = 0xffffffffu;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (!published) block_lookback_publish<K>(state, tile, aggregate);
-#pragma unroll
-	for (int j = 0; j < K; ++j) excl[j] = 0;
-	if (tile == 0) return; // block-uniform
-	int64_t base = (int64_t)tile - 1;
-	for (;;) {
-		const int64_t idx = base - (int64_t)threadIdx.x;
-		uint64_t v[K];
-		uint32_t first_p, first_n;
-		for (;;) {
-			int n_pre = 0, n_agg = 0;
-#pragma unroll
-			for (int j = 0; j < K; ++j) {
-				const uint64_t s = idx >= 0 ? lb_load(&state[(uint64_t)idx * K + j]) : lb_pack(LB_PREFIX, 0);
-				v[j] = lb_value(s);
-				n_pre += lb_status(s) == LB_PREFIX ? 1 : 0;
-				n_agg += lb_status(s) == LB_AGGREGATE ? 1 : 0;
-			}
-			const unsigned pm = __ballot_sync(FULL_MASK, n_pre == K);
-			const unsigned nm = __ballot_sync(FULL_MASK, n_pre != K && n_agg != K);
-			if (lane == 0) {
-				s_idx[warp] = pm ? (uint32_t)(warp * 32 + __ffs((int)pm) - 1) : NONE;
-				s_idx[NW + warp] = nm ? (uint32_t)(warp * 32 + __ffs((int)nm) - 1) : NONE;
-			}
-			__syncthreads();
-			first_p = NONE, first_n = NONE;
-#pragma unroll
-			for (int w = 0; w < NW; ++w) {
-				first_p = s_idx[w] < first_p ? s_idx[w] : first_p;
-				first_n = s_idx[NW + w] < first_n ? s_idx[NW + w] : first_n;
-			}
-			__syncthreads();
-			if (first_n < first_p || (first_p == NONE && first_n != NONE)) continue; // somebody needed is not ready: poll again
-			break;
-		}
-		const bool take = first_p == NONE || threadIdx.x <= first_p;
-#pragma unroll
-		for (int j = 0; j < K; ++j) {
-			const uint64_t w = warp_sum(take ? v[j] : 0ull);
-			if (lane == 0) s_red[warp * K + j] = w;
-		}
-		__syncthreads();
-#pragma unroll
-		for (int j = 0; j < K; ++j) {
-			uint64_t t = 0;
-#pragma unroll
-			for (int w = 0; w < NW; ++w) t += s_red[w * K + j];
-			excl[j] += t;
-		}
-		__syncthreads();
-		if (first_p != NONE) break;
-		base -= BLOCK; // a whole window of aggregates: keep walking
-	}
-#ifdef SVO_EMU
-	if (g_emu_lookback_aggregate_only) return;
-#endif
-#pragma unroll
-	for (int j = 0; j < K; ++j)
-		if (threadIdx.x == (unsigned)j) lb_store(&state[(uint64_t)tile * K + j], lb_pack(LB_PREFIX, excl[j] + aggregate[j]));
-}
-
 // Dynamic tile ticket (tile ids in start order).  Returns the tile id on every thread.
 SVO_DEV uint32_t take_ticket(uint32_t *counter, uint32_t *s_ticket) {
 	if (threadIdx.x == 0) *s_ticket = atomicAdd(counter, 1u);

@@ -139,6 +139,8 @@ struct svo_builder {
 	DevBuf<uint32_t> tickets;
 	DevBuf<uint32_t> octree;
 	SortScratch sort_scratch;
+	ScanScratch scan_scratch;
+	DevBuf<uint64_t> rf_cnt01, rf_cnt2, rf_pre01, rf_pre2; // per reduce tile: run counts and their exclusive prefixes
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
 	uint64_t range_bytes = 0;
 	uint32_t sort_passes = 0;
@@ -639,6 +641,8 @@ void svo_builder_destroy(svo_builder *b) {
 	b->tmp.release(0), b->leaf.release(0), b->first.release(0), b->slot.release(0), b->counts.release(0), b->lb_state.release(0);
 	b->tickets.release(0), b->octree.release(0), b->root_scratch.release(0);
 	b->sort_scratch.hist.release(0), b->sort_scratch.ticket.release(0), b->sort_scratch.state.release(0);
+	b->scan_scratch.state.release(0), b->scan_scratch.ticket.release(0);
+	b->rf_cnt01.release(0), b->rf_cnt2.release(0), b->rf_pre01.release(0), b->rf_pre2.release(0);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
 	delete b;
@@ -685,16 +689,21 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 		if (L >= 2) fo.slot1 = b->slot.p + slot_off[L - 1], fo.first2 = b->first.p + first_off[L - 1];
 		fo.keys_top = other;
 		for (uint32_t j = 0; j < K; ++j) fo.count[j] = b->counts.p + (L - j);
-		if (K == 1) {
-			auto k = k_reduce_fused<1>;
-			SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k, (const uint64_t *)sorted, F, fo, b->lb_state.p, rf_tiles);
-		} else if (K == 2) {
-			auto k = k_reduce_fused<2>;
-			SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k, (const uint64_t *)sorted, F, fo, b->lb_state.p, rf_tiles);
-		} else {
-			auto k = k_reduce_fused<3>;
-			SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k, (const uint64_t *)sorted, F, fo, b->lb_state.p, rf_tiles);
-		}
+		// count the runs of every tile, scan over the tiles, then the big kernel: no tile waits for a neighbour
+		SVO_TRY(b->rf_cnt01.reserve(rf_tiles, s));
+		SVO_TRY(b->rf_cnt2.reserve(rf_tiles, s));
+		SVO_TRY(b->rf_pre01.reserve((uint64_t)rf_tiles + 1, s));
+		SVO_TRY(b->rf_pre2.reserve((uint64_t)rf_tiles + 1, s));
+		const uint64_t *p01 = b->rf_pre01.p, *p2 = b->rf_pre2.p;
+#define SVO_REDUCE_CASE(KK)                                                                                                        \
+	{                                                                                                                              \
+		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_count<KK>, (const uint64_t *)sorted, F, b->rf_cnt01.p, b->rf_cnt2.p);          \
+		SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt01.p, b->rf_pre01.p, rf_tiles, b->scan_scratch, s));                      \
+		if (KK >= 3) SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt2.p, b->rf_pre2.p, rf_tiles, b->scan_scratch, s));           \
+		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_fused<KK>, (const uint64_t *)sorted, F, fo, rf_tiles, p01, p2);                \
+	}
+		if (K == 1) SVO_REDUCE_CASE(1) else if (K == 2) SVO_REDUCE_CASE(2) else SVO_REDUCE_CASE(3)
+#undef SVO_REDUCE_CASE
 	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 
