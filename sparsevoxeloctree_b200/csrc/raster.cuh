@@ -19,6 +19,7 @@ namespace svo {
 
 constexpr int64_t SMALL_AREA = 256; // candidate-rectangle pixels handled by a single thread
 constexpr int RASTER_BLOCK = 128;
+constexpr int LARGE_ROW_CHUNK = 128; // rows of a large triangle handled by one warp before it strides on
 #ifndef SVO_EMIT_BLOCK
 #define SVO_EMIT_BLOCK 256
 #endif
@@ -161,6 +162,7 @@ template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
     k_large_rows(SceneView sv, RasterParams rp, uint32_t n_large, LargeTri *__restrict__ large, UvMap *__restrict__ luv,
                  uint64_t *__restrict__ row_pk, uint32_t *__restrict__ row_x0) {
+	// a triangle's rows are shared out in chunks of LARGE_ROW_CHUNK among gridDim.y warps (a wall has 4096 rows)
 	const uint32_t li = (blockIdx.x * RASTER_BLOCK + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (li >= n_large) return; // whole warp leaves together
@@ -168,14 +170,15 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	TriSetup ts;
 	TriShade sh;
 	load_and_setup<TEX>(sv, rp, lt.tri, ts, sh); // true by construction (classified large)
-	if (lane == 0) {
+	if (lane == 0 && blockIdx.y == 0) {
 		lt.ts = ts;
 		lt.rgb = sh.rgb;
 		lt.textured = sh.textured ? 1u : 0u;
 		if (TEX && sh.textured) luv[li] = sh.um;
 	}
 	const int32_t h = ts.py1 - ts.py0 + 1;
-	for (int32_t r = lane; r < h; r += 32) {
+	for (int32_t c = (int32_t)blockIdx.y * LARGE_ROW_CHUNK; c < h; c += (int32_t)gridDim.y * LARGE_ROW_CHUNK)
+	for (int32_t r = c + lane; r < h && r < c + LARGE_ROW_CHUNK; r += 32) {
 		int32_t x_lo, x_hi;
 		row_span(ts, ts.py0 + r, x_lo, x_hi);
 		row_span_depth_window(ts, rp.res, ts.py0 + r, x_lo, x_hi);
@@ -201,7 +204,8 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	if (li >= n_large) return;
 	const LargeTri &lt = large[li];
 	const int32_t h = lt.ts.py1 - lt.ts.py0 + 1;
-	for (int32_t r = lane; r < h; r += 32) {
+	for (int32_t c = (int32_t)blockIdx.y * LARGE_ROW_CHUNK; c < h; c += (int32_t)gridDim.y * LARGE_ROW_CHUNK)
+	for (int32_t r = c + lane; r < h && r < c + LARGE_ROW_CHUNK; r += 32) {
 		const uint64_t s = (uint64_t)lt.row_base + r;
 		if (row_pk[s] >> 40) {
 			const uint64_t p = rprefix[s];
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 			out.li[k] = li;
 		}
 	}
-	if (li == 0 && lane == 0) {
+	if (li == 0 && lane == 0 && blockIdx.y == 0) {
 		const uint64_t tot = rprefix[n_rows_sparse];
 		out.off[tot >> 40] = (uint32_t)(tot & ((1ull << 40) - 1));
 	}

@@ -453,12 +453,14 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 				break;
 			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_large_collect, T, (const uint64_t *)packed.p, (const uint64_t *)lprefix.p, v->large.p);
 			const uint32_t wgrid = div_up((uint64_t)v->n_large * 32, RASTER_BLOCK);
+			// few large triangles with thousands of rows each: spread a triangle's rows over up to 16 warps
+			const dim3 wgrid2(wgrid, v->n_large < 65536u ? std::min(16u, div_up((uint64_t)(1u << level), LARGE_ROW_CHUNK)) : 1u);
 			if (scene->textured) {
 				if ((rc = v->large_uv.alloc(v->n_large, s))) break;
-				SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_large_rows<true>, scene->view, v->rp, v->n_large, v->large.p, v->large_uv.p,
+				SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_large_rows<true>, scene->view, v->rp, v->n_large, v->large.p, v->large_uv.p,
 				                 row_pk.p, row_x0.p);
 			} else
-				SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_large_rows<false>, scene->view, v->rp, v->n_large, v->large.p, (UvMap *)nullptr,
+				SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_large_rows<false>, scene->view, v->rp, v->n_large, v->large.p, (UvMap *)nullptr,
 				                 row_pk.p, row_x0.p);
 			if ((rc = exclusive_scan((const uint64_t *)row_pk.p, rprefix.p, rows_sparse, ss, s))) break;
 			uint64_t h_rp = 0;
@@ -473,7 +475,7 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 			    (rc = v->row_li.alloc(v->n_rows, s)))
 				break;
 			DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
-			SVO_LAUNCH_INDEP(wgrid, RASTER_BLOCK, s, k_rows_compact, v->n_large, (const LargeTri *)v->large.p, (const uint64_t *)row_pk.p,
+			SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_rows_compact, v->n_large, (const LargeTri *)v->large.p, (const uint64_t *)row_pk.p,
 			                 (const uint32_t *)row_x0.p, (const uint64_t *)rprefix.p, rows_sparse, dr);
 		}
 		v->n_frag = v->n_frag_small + v->n_frag_large;
