@@ -8,11 +8,11 @@
 //
 //   k_radix_histogram : one read of the keys -> digit histograms of every pass (shared-memory bins)
 //   k_radix_scan_bins : exclusive scan of each pass's bins
-//   k_onesweep_pass   : per pass, ONE read + ONE write of the keys: per-tile ranking with
-//                       __match_any_sync + one shared-memory atomic per digit group, per-digit decoupled
-//                       look-back across tiles (tiles numbered by a ticket so predecessors are always
-//                       running; several predecessor states in flight per step), shared-memory reorder,
-//                       run-wise coalesced scatter.
+//   k_onesweep_pass   : per pass, ONE read + ONE write of the keys: per-tile ranking by one warp vote per
+//                       digit bit + one shared-memory atomic per digit group, per-digit decoupled look-back
+//                       across tiles (tiles numbered by blockIdx.x, which is dispatch order, so predecessors
+//                       are always running; 4 predecessor states in flight per step), shared-memory
+//                       reorder, run-wise coalesced scatter.
 // Digits are up to 9 bits wide (512 bins): 36 Morton bits at level 12 take 4 passes.
 // Traffic: 8*F*(2P+1) bytes for P passes -- HBM bound by design.
 #pragma once
@@ -381,7 +381,6 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 
 struct SortScratch {
 	DevBuf<uint32_t> hist;   // MAX_PASSES * MAX_RADIX
-	DevBuf<uint32_t> ticket; // MAX_PASSES
 	DevBuf<unsigned char> state;
 	bool attr_set = false;
 };
@@ -436,10 +435,8 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	const uint32_t radix = nine ? 512u : 256u;
 	const size_t state_bytes = (size_t)tiles * radix * (wide ? 8 : 4);
 	SVO_TRY(sc.hist.reserve(MAX_PASSES * MAX_RADIX, s));
-	SVO_TRY(sc.ticket.reserve(MAX_PASSES, s));
 	SVO_TRY(sc.state.reserve(state_bytes, s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.hist.p, 0, MAX_PASSES * MAX_RADIX * sizeof(uint32_t), s));
-	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, MAX_PASSES * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, state_bytes, s));
 
 	uint32_t hgrid = div_up(n, (uint64_t)HIST_BLOCK * HIST_ITEMS);

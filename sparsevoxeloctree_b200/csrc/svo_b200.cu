@@ -642,7 +642,7 @@ void svo_builder_destroy(svo_builder *b) {
 	DeviceGuard guard(b->device);
 	b->tmp.release(0), b->leaf.release(0), b->first.release(0), b->slot.release(0), b->counts.release(0), b->lb_state.release(0);
 	b->tickets.release(0), b->octree.release(0), b->root_scratch.release(0);
-	b->sort_scratch.hist.release(0), b->sort_scratch.ticket.release(0), b->sort_scratch.state.release(0);
+	b->sort_scratch.hist.release(0), b->sort_scratch.state.release(0);
 	b->scan_scratch.state.release(0), b->scan_scratch.ticket.release(0);
 	b->rf_cnt01.release(0), b->rf_cnt2.release(0), b->rf_pre01.release(0), b->rf_pre2.release(0);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
@@ -855,7 +855,7 @@ int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_b
 	uint32_t np = 0;
 	int rc = radix_sort_u64(d_keys, d_tmp, n, begin_bit, end_bit, sc, sm_count(device), s, &res, &np, nullptr);
 	if (!rc && res != d_keys && cudaMemcpyAsync(d_keys, res, n * 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "copy back failed");
-	sc.hist.release(s), sc.ticket.release(s), sc.state.release(s);
+	sc.hist.release(s), sc.state.release(s);
 	return rc;
 }
 
