@@ -390,7 +390,7 @@ struct SortScratch {
 #define SVO_OS_BLOCK 256
 #endif
 #ifndef SVO_OS_ITEMS
-#define SVO_OS_ITEMS 20
+#define SVO_OS_ITEMS 22
 #endif
 #ifndef SVO_OS_MINB
 #define SVO_OS_MINB 3

@@ -43,7 +43,7 @@ def run(lib, mesh, level, mode, reps=6):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="C4")
-    ap.add_argument("--variants", default="512,8,2")
+    ap.add_argument("--variants", default="256,22,3")
     ap.add_argument("--extra", default="", help="extra -D definitions, comma separated")
     args = ap.parse_args()
     cfg = scenes.CONFIGS[args.workload]
