@@ -37,10 +37,10 @@ constexpr int MAX_LEVEL = 16;
 #define SVO_RF_BLOCK 256
 #endif
 #ifndef SVO_RF_ITEMS
-#define SVO_RF_ITEMS 16
+#define SVO_RF_ITEMS 8
 #endif
 #ifndef SVO_RF_MINB
-#define SVO_RF_MINB 4
+#define SVO_RF_MINB 8
 #endif
 constexpr int RF_BLOCK = SVO_RF_BLOCK, RF_ITEMS = SVO_RF_ITEMS, RF_TILE = RF_BLOCK * RF_ITEMS, RF_NW = RF_BLOCK / 32;
 static_assert(RF_ITEMS * RF_NW <= 512 && (RF_ITEMS * RF_NW) % 32 == 0, "the (row, warp) count matrix is scanned by one warp");
