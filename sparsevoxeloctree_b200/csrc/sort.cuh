@@ -25,7 +25,16 @@ namespace svo {
 #endif
 constexpr int MAX_RADIX_BITS = SVO_MAX_RADIX_BITS, MAX_RADIX = 512;
 constexpr int MAX_PASSES = 8;
-constexpr int HIST_BLOCK = 256, HIST_ITEMS = 16;
+#ifndef SVO_HIST_BLOCK
+#define SVO_HIST_BLOCK 1024
+#endif
+#ifndef SVO_HIST_ITEMS
+#define SVO_HIST_ITEMS 8
+#endif
+#ifndef SVO_HIST_GRID
+#define SVO_HIST_GRID 2 // persistent blocks per SM
+#endif
+constexpr int HIST_BLOCK = SVO_HIST_BLOCK, HIST_ITEMS = SVO_HIST_ITEMS;
 
 struct SortPasses {
 	uint32_t n_pass;
@@ -440,7 +449,7 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, state_bytes, s));
 
 	uint32_t hgrid = div_up(n, (uint64_t)HIST_BLOCK * HIST_ITEMS);
-	const uint32_t hmax = (uint32_t)(n_sm > 0 ? n_sm : 148) * 8u;
+	const uint32_t hmax = (uint32_t)(n_sm > 0 ? n_sm : 148) * (uint32_t)SVO_HIST_GRID;
 	if (hgrid > hmax) hgrid = hmax;
 	switch (sp.n_pass) {
 #define SVO_HIST_CASE(NP) \
