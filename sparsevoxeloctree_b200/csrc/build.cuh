@@ -43,7 +43,7 @@ constexpr int MAX_LEVEL = 16;
 #define SVO_RF_MINB 8
 #endif
 constexpr int RF_BLOCK = SVO_RF_BLOCK, RF_ITEMS = SVO_RF_ITEMS, RF_TILE = RF_BLOCK * RF_ITEMS, RF_NW = RF_BLOCK / 32;
-static_assert(RF_ITEMS * RF_NW <= 512 && (RF_ITEMS * RF_NW) % 32 == 0, "the (row, warp) count matrix is scanned by one warp");
+static_assert(RF_TILE <= 65536 && RF_ITEMS * RF_NW <= 512 && (RF_ITEMS * RF_NW) % 32 == 0, "the (row, warp) count matrix is scanned by one warp");
 constexpr int RF_CPL = RF_ITEMS * RF_NW / 32; // counts per lane in that scan
 
 struct FusedOut {
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 	__shared__ uint64_t s_keys[RF_TILE + 2]; // [0] = the element before the tile, [TILE+1] = the one after
 	__shared__ uint32_t s_cnt[3][RF_ITEMS * RF_NW];
 	__shared__ uint32_t s_total[3];
+	__shared__ uint16_t s_start[RF_TILE]; // (tiles with many fragments per voxel) first element of every leaf run
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t tile = blockIdx.x;
@@ -172,15 +173,13 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 		for (int j = 0; j < K; ++j) *out.count[j] = pre[j] + agg[j];
 	}
 
-	// run owners write their node
+	// run owners write their node.  The colour fold of a voxel is sequential (the reference's running average is order
+	// dependent), one thread per voxel.  When most elements start a run (about one fragment per voxel) the owner folds
+	// in place; when voxels hold many fragments only a few lanes own runs, so the runs are first listed densely and
+	// then dealt out one per thread -- every lane folds (the San-Miguel-like workload: 3.7 fragments per voxel).
 	const uint64_t p0 = pre[0], p1 = K >= 2 ? pre[K >= 2 ? 1 : 0] : 0, p2 = K >= 3 ? pre[K >= 3 ? 2 : 0] : 0;
-#pragma unroll
-	for (int i = 0; i < RF_ITEMS; ++i) {
-		const uint32_t pk = packed[i];
-		if (!(pk & 1u)) continue;
-		const uint32_t e = i * RF_BLOCK + threadIdx.x;
-		const uint64_t key = s_keys[e + 1];
-		const uint64_t u0 = p0 + s_cnt[0][i * RF_NW + warp] + ((pk >> 3) & 31u);
+	const bool listed = s_total[0] * 4u <= (uint32_t)RF_TILE * 3u; // block-uniform
+	auto fold_leaf = [&](uint32_t e, uint64_t key) {
 		uint32_t acc = leaf_first((uint32_t)(key & 0xffffffu));
 		if (((s_keys[e + 2] ^ key) >> 24) == 0) { // the voxel has more fragments: fold them in emission order
 			for (uint64_t q = (uint64_t)e + 1; tile_base + q < n; ++q) {
@@ -189,9 +188,23 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 				acc = leaf_accumulate(acc, (uint32_t)(kk & 0xffffffu));
 			}
 		}
-		out.leaf[u0] = acc;
-		out.slot0[u0] = (unsigned char)((key >> 24) & 7u);
-		if (K == 1) out.keys_top[u0] = key >> 24;
+		return acc;
+	};
+#pragma unroll
+	for (int i = 0; i < RF_ITEMS; ++i) {
+		const uint32_t pk = packed[i];
+		if (!(pk & 1u)) continue;
+		const uint32_t e = i * RF_BLOCK + threadIdx.x;
+		const uint64_t key = s_keys[e + 1];
+		const uint32_t l0 = s_cnt[0][i * RF_NW + warp] + ((pk >> 3) & 31u); // index of the run inside the tile
+		const uint64_t u0 = p0 + l0;
+		if (listed)
+			s_start[l0] = (uint16_t)e;
+		else {
+			out.leaf[u0] = fold_leaf(e, key);
+			out.slot0[u0] = (unsigned char)((key >> 24) & 7u);
+			if (K == 1) out.keys_top[u0] = key >> 24;
+		}
 		if (K >= 2 && (pk & 2u)) {
 			const uint64_t u1 = p1 + s_cnt[1][i * RF_NW + warp] + ((pk >> 8) & 31u);
 			out.first1[u1] = (uint32_t)u0;
@@ -202,6 +215,16 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 				out.first2[u2] = (uint32_t)u1;
 				out.keys_top[u2] = key >> 30;
 			}
+		}
+	}
+	if (listed) {
+		__syncthreads();
+		for (uint32_t r = threadIdx.x; r < s_total[0]; r += RF_BLOCK) {
+			const uint32_t e = s_start[r];
+			const uint64_t key = s_keys[e + 1];
+			out.leaf[p0 + r] = fold_leaf(e, key);
+			out.slot0[p0 + r] = (unsigned char)((key >> 24) & 7u);
+			if (K == 1) out.keys_top[p0 + r] = key >> 24;
 		}
 	}
 }
