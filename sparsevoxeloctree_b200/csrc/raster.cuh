@@ -98,11 +98,54 @@ SVO_DEV bool load_and_setup(const SceneView &sv, const RasterParams &rp, uint64_
 	return ok;
 }
 
-SVO_DEV uint64_t make_fragment(const TriSetup &ts, const RasterParams &rp, int32_t px, int32_t py, uint32_t uz, uint32_t rgb) {
+// A fragment = morton(voxel) << 24 | rgb, with the Morton spread taken from a 1024-entry table in shared memory
+// (part1by2_10 of every 10-bit value): 6 lookups instead of ~90 ALU instructions.
+SVO_DEV void fill_spread_table(uint32_t *s_lut, int n_threads) {
+	for (uint32_t i = threadIdx.x; i < 1024u; i += (uint32_t)n_threads) s_lut[i] = part1by2_10(i);
+}
+SVO_DEV uint64_t make_fragment_lut(const TriSetup &ts, const RasterParams &rp, const uint32_t *s_lut, int32_t px, int32_t py, uint32_t uz,
+                                   uint32_t rgb) {
 	uint32_t vx, vy, vz;
 	unswizzle(ts.axis, (uint32_t)px, (uint32_t)py, uz, vx, vy, vz);
-	return (morton3(vx - rp.origin[0], vy - rp.origin[1], vz - rp.origin[2]) << 24) | (uint64_t)(rgb & 0xffffffu);
+	vx -= rp.origin[0], vy -= rp.origin[1], vz -= rp.origin[2];
+	const uint32_t m_lo = s_lut[vx & 1023u] | (s_lut[vy & 1023u] << 1) | (s_lut[vz & 1023u] << 2);
+	uint32_t m_hi = 0;
+	if (rp.res > 1024u) m_hi = s_lut[(vx >> 10) & 1023u] | (s_lut[(vy >> 10) & 1023u] << 1) | (s_lut[(vz >> 10) & 1023u] << 2);
+	return ((uint64_t)((m_lo >> 8) | (m_hi << 22)) << 32) | (uint64_t)((m_lo << 24) | (rgb & 0xffffffu));
 }
+
+// Row-major walk over the covered pixels of a small triangle's candidate rectangle.  The three edge functions are
+// stepped (one 64-bit add per edge and pixel) instead of re-evaluated, and the search for the next covered pixel is
+// a tight loop of its own: the lanes of a warp -- one triangle each, rectangles of different sizes -- meet again
+// before the expensive per-fragment work, so that work runs with most lanes active.
+struct SmallWalk {
+	int64_t e[3], erow[3];
+	int32_t px, py;
+	SVO_DEV void begin(const TriSetup &ts) {
+		px = ts.px0, py = ts.py0;
+#pragma unroll
+		for (int i = 0; i < 3; ++i) e[i] = erow[i] = ts.ea[i] * (int64_t)px + ts.eb[i] * (int64_t)py + ts.ec[i];
+	}
+	SVO_DEV void step(const TriSetup &ts) {
+		if (px < ts.px1) {
+			++px;
+#pragma unroll
+			for (int i = 0; i < 3; ++i) e[i] += ts.ea[i];
+		} else {
+			px = ts.px0, ++py;
+#pragma unroll
+			for (int i = 0; i < 3; ++i) e[i] = erow[i] += ts.eb[i];
+		}
+	}
+	// moves to the next covered pixel at or after the current one; false when the rectangle is exhausted
+	SVO_DEV bool next(const TriSetup &ts) {
+		while (py <= ts.py1) {
+			if ((e[0] | e[1] | e[2]) >= 0) return true; // pixel_covered: all three edge functions >= 0
+			step(ts);
+		}
+		return false;
+	}
+};
 
 // ---- pass 1: classify + count small ------------------------------------------------------------------
 // cnt_small[t]  = fragments of a small triangle (0 for large / culled)
@@ -120,13 +163,14 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	uint64_t pk = 0;
 	if (load_and_setup<TEX>(sv, rp, t, ts, sh)) {
 		if (ts.full_area <= SMALL_AREA || (TEX && sh.alpha)) {
-			for (int32_t py = ts.py0; py <= ts.py1; ++py)
-				for (int32_t px = ts.px0; px <= ts.px1; ++px)
-					if (pixel_covered(ts, px, py)) {
-						uint32_t uz, c;
-						if ((!ts.cull_depth && !ts.clip_z) || pixel_fragment(ts, rp.res, px, py, uz))
-							if (!(TEX && sh.alpha) || sample_colour(sv.tex, sh.um, px, py, c)) ++cnt;
-					}
+			SmallWalk wk;
+			wk.begin(ts);
+			while (wk.next(ts)) {
+				uint32_t uz, c;
+				if ((!ts.cull_depth && !ts.clip_z) || pixel_fragment(ts, rp.res, wk.px, wk.py, uz))
+					if (!(TEX && sh.alpha) || sample_colour(sv.tex, sh.um, wk.px, wk.py, c)) ++cnt;
+				wk.step(ts);
+			}
 		} else
 			pk = (1ull << 40) | (uint64_t)(ts.py1 - ts.py0 + 1);
 	}
@@ -225,6 +269,9 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
     k_emit_small(SceneView sv, RasterParams rp, const uint64_t *__restrict__ tri_off, uint64_t *__restrict__ frags) {
+	__shared__ uint32_t s_lut[1024];
+	fill_spread_table(s_lut, RASTER_BLOCK);
+	__syncthreads();
 	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
 	if (t >= sv.n_tri) return;
 	const uint64_t o0 = tri_off[t], o1 = tri_off[t + 1];
@@ -233,13 +280,15 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	TriShade sh;
 	if (!load_and_setup<TEX>(sv, rp, t, ts, sh)) return;
 	uint64_t o = o0;
-	for (int32_t py = ts.py0; py <= ts.py1; ++py)
-		for (int32_t px = ts.px0; px <= ts.px1; ++px)
-			if (pixel_covered(ts, px, py)) {
-				uint32_t uz, rgb = sh.rgb;
-				if (pixel_fragment(ts, rp.res, px, py, uz))
-					if (!(TEX && sh.textured) || sample_colour(sv.tex, sh.um, px, py, rgb)) frags[o++] = make_fragment(ts, rp, px, py, uz, rgb);
-			}
+	SmallWalk wk;
+	wk.begin(ts);
+	while (wk.next(ts)) {
+		uint32_t uz, rgb = sh.rgb;
+		if (pixel_fragment(ts, rp.res, wk.px, wk.py, uz))
+			if (!(TEX && sh.textured) || sample_colour(sv.tex, sh.um, wk.px, wk.py, rgb))
+				frags[o++] = make_fragment_lut(ts, rp, s_lut, wk.px, wk.py, uz, rgb);
+		wk.step(ts);
+	}
 }
 
 // output-parallel expansion of the dense row spans: fragment ordinal j -> (row, x).  A block owns EMIT_TILE

@@ -552,11 +552,11 @@ int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
 	const bool tex = v->scene->textured;
 	if (v->n_frag_small) {
 		if (tex)
-			SVO_LAUNCH_INDEP(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, s, k_emit_small<true>, sv, v->rp, (const uint64_t *)v->tri_off.p,
-			                 v->frags.p);
+			SVO_LAUNCH(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, 0, s, k_emit_small<true>, sv, v->rp, (const uint64_t *)v->tri_off.p,
+			           v->frags.p);
 		else
-			SVO_LAUNCH_INDEP(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, s, k_emit_small<false>, sv, v->rp, (const uint64_t *)v->tri_off.p,
-			                 v->frags.p);
+			SVO_LAUNCH(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, 0, s, k_emit_small<false>, sv, v->rp, (const uint64_t *)v->tri_off.p,
+			           v->frags.p);
 	}
 	if (v->n_frag_large) {
 		DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
