@@ -207,6 +207,9 @@ SVO_API int svo_builder_last_ms(svo_builder *b, float *phase_ms /*[SVO_PHASE_COU
  * (d_tmp: n keys of scratch). */
 SVO_API int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_bit, uint32_t end_bit,
                          int device, void *stream);
+/* Test switch: the sort keeps 32-bit look-back words below 2^30 keys and 64-bit ones above; on != 0 forces the
+ * 64-bit variant for every size so that the tests reach it without sorting a billion keys. */
+SVO_API void svo_debug_force_wide_sort_state(int on);
 
 /* ---- the consumer side, for verification ----------------------------------------------------
  * Octree_RayMarchLeaf (shader/octree.glsl:179-340, the primary-ray traversal octree_tracer.frag:36 runs on the

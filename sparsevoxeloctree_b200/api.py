@@ -90,6 +90,7 @@ SYMBOLS = [
     ("svo_voxelizer_last_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("svo_builder_last_ms", C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     ("svo_sort_u64", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P]),
+    ("svo_debug_force_wide_sort_state", None, [C.c_int]),
     ("svo_octree_raymarch_leaf", C.c_int, [C.c_int, _P, C.c_uint64, _P, _P, _P, _P]),
     ("svo_device_malloc", C.c_int, [C.c_int, C.c_uint64, C.POINTER(_P)]),
     ("svo_device_free", C.c_int, [C.c_int, _P]),

@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 		onesweep_tile<BLOCK, ITEMS, RBITS, StateT, false>(keys_in, keys_out, tile_count, shift, mask, pass, g_bins, state, s_keys, s_wsum);
 }
 
+inline bool g_force_wide_sort_state = false; // svo_debug_force_wide_sort_state (tests)
+
 struct SortScratch {
 	DevBuf<uint32_t> hist;   // MAX_PASSES * MAX_RADIX
 	DevBuf<unsigned char> state;
@@ -439,7 +441,7 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	}
 	constexpr int TILE = OS_BLOCK * OS_ITEMS;
 	const uint32_t tiles = div_up(n, TILE);
-	const bool wide = n >= (1ull << 30);
+	const bool wide = n >= (1ull << 30) || g_force_wide_sort_state;
 	const bool nine = sp.max_bits > 8;
 	const uint32_t radix = nine ? 512u : 256u;
 	const size_t state_bytes = (size_t)tiles * radix * (wide ? 8 : 4);

@@ -935,6 +935,8 @@ int svo_stream_synchronize(int device, void *stream) {
 	return SVO_OK;
 }
 
+void svo_debug_force_wide_sort_state(int on) { svo::g_force_wide_sort_state = on != 0; }
+
 #ifdef SVO_EMU
 // test hook of the emulation build only (see scan.cuh)
 SVO_API void svo_emu_set_lookback_aggregate_only(int on) { svo::g_emu_lookback_aggregate_only = on; }

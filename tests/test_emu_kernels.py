@@ -32,6 +32,18 @@ def test_onesweep_logic(emu, n):
     assert (out == k[np.argsort(key, kind="stable")]).all()
 
 
+def test_onesweep_wide_lookback_words(emu):
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, 1 << 62, 12000, dtype=np.uint64)
+    emu.dll.svo_debug_force_wide_sort_state(1)
+    try:
+        out = emu.sort_u64(k, 24, 24 + 18)
+    finally:
+        emu.dll.svo_debug_force_wide_sort_state(0)
+    key = (k >> np.uint64(24)) & np.uint64((1 << 18) - 1)
+    assert (out == k[np.argsort(key, kind="stable")]).all()
+
+
 def test_onesweep_long_lookback_chain(emu):
     # tiles publish aggregates only: every tile walks the full chain (the path sequential emulation never takes)
     emu.dll.svo_emu_set_lookback_aggregate_only(1)

@@ -39,6 +39,19 @@ def test_onesweep_sort_clustered_keys(lib):
     assert (out == k[np.argsort(k >> np.uint64(24), kind="stable")]).all()
 
 
+def test_onesweep_sort_wide_lookback_words(lib):
+    """The 64-bit look-back words the sort switches to at >= 2^30 keys, forced on at a testable size."""
+    rng = np.random.default_rng(6)
+    k = rng.integers(0, 1 << 63, 2_000_003, dtype=np.uint64)
+    lib.dll.svo_debug_force_wide_sort_state(1)
+    try:
+        out = lib.sort_u64(k, 24, 60)
+    finally:
+        lib.dll.svo_debug_force_wide_sort_state(0)
+    key = (k >> np.uint64(24)) & np.uint64((1 << 36) - 1)
+    assert (out == k[np.argsort(key, kind="stable")]).all()
+
+
 @pytest.mark.parametrize("mode", [api.CENTER, api.CONSERVATIVE_EXACT, api.CONSERVATIVE_DILATE])
 def test_config1_heightfield_level8(lib, mode):
     # BASELINE.json configs[0]: 10k-triangle heightfield, level 8
