@@ -352,7 +352,12 @@ SVO_HD inline double plane_z_row(const TriSetup &t, int32_t px, double row_term)
 }
 SVO_HD inline uint32_t depth_voxel_range(uint32_t res, double z, uint32_t zr_lo, uint32_t zr_hi) {
 	double zs = dmul(z, (double)res);
+#if defined(__CUDA_ARCH__)
+	// the conversion saturates (negative and NaN -> 0, huge -> 2^32-1), the last min() below does the rest
+	uint32_t uz = __double2uint_rz(zs);
+#else
 	uint32_t uz = !(zs > 0.0) ? 0u : (zs >= (double)res ? res - 1u : (uint32_t)zs);
+#endif
 	uz = tmax(uz, zr_lo);
 	uz = tmin(uz, zr_hi);
 	uz = tmin(uz, res - 1u);
