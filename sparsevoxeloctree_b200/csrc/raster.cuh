@@ -367,9 +367,9 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 				const uint32_t wx = axis == 0u ? 1u : (axis == 1u ? 2u : 0u); // world axis of screen x
 				const uint32_t wy = axis == 0u ? 2u : (axis == 1u ? 0u : 1u);
 				shx = wx, shz = axis;
-				oz = rp.origin[axis];
-				xl = (uint32_t)px - rp.origin[wx];
-				const uint32_t yl = (uint32_t)py - rp.origin[wy];
+				oz = pick3(rp.origin, axis);
+				xl = (uint32_t)px - pick3(rp.origin, wx);
+				const uint32_t yl = (uint32_t)py - pick3(rp.origin, wy);
 				xmask = 0x09249249u << wx, xone = 1u << wx;
 				xs = s_lut[xl & 1023u] << wx;
 				row_lo = s_lut[yl & 1023u] << wy;

@@ -44,6 +44,9 @@ SVO_HD inline uint32_t f2u_sat(float f) {
 SVO_HD inline float glsl_min(float x, float y) { return y < x ? y : x; }
 SVO_HD inline float glsl_max(float x, float y) { return x < y ? y : x; }
 
+// a[i] for i in 0..2 by selects: indexing a kernel-parameter array with a run-time index makes the compiler test
+// every possible constant-bank slot in turn (dozens of instructions)
+SVO_HD inline uint32_t pick3(const uint32_t (&a)[3], uint32_t i) { return i == 0u ? a[0] : (i == 1u ? a[1] : a[2]); }
 template <class T> SVO_HD inline T tmin(T a, T b) { return b < a ? b : a; }
 template <class T> SVO_HD inline T tmax(T a, T b) { return a < b ? b : a; }
 SVO_HD inline int64_t iabs64(int64_t v) { return v < 0 ? -v : v; }
@@ -185,10 +188,10 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 	const int sz = axis == 0u ? 0 : (axis == 1u ? 1 : 2);
 	const float fres = (float)res;
 	float qx[3], qy[3], qz[3];
-	for (int i = 0; i < 3; ++i) {
-		qx[i] = p[i][sx];
-		qy[i] = p[i][sy];
-		qz[i] = fmul(fadd(p[i][sz], 1.0f), 0.5f);
+	for (int i = 0; i < 3; ++i) { // (selects, not run-time indexing: the vertices stay in registers)
+		qx[i] = sx == 0 ? p[i][0] : (sx == 1 ? p[i][1] : p[i][2]);
+		qy[i] = sy == 0 ? p[i][0] : (sy == 1 ? p[i][1] : p[i][2]);
+		qz[i] = fmul(fadd(sz == 0 ? p[i][0] : (sz == 1 ? p[i][1] : p[i][2]), 1.0f), 0.5f);
 	}
 	// gAABB / gDepthRange (voxelizer.geom:39-42)
 	uint32_t ax0 = f2u_sat(fmul(fmul(fadd(glsl_min(qx[0], glsl_min(qx[1], qx[2])), 1.0f), 0.5f), fres));
@@ -250,16 +253,19 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 		}
 	} else {
 		// zero snapped area (conservative only): the longest edge as a segment, |E| <= support
+		// (selects instead of run-time indices, so that X / Y stay in registers)
 		const int SA[3] = {0, 1, 2}, SB[3] = {1, 2, 0};
-		int best = 0;
-		int64_t best_d = -1;
+		int64_t best_d = -1, A = 0, B = 0, Cc = 0;
+#pragma unroll
 		for (int i = 0; i < 3; ++i) {
-			int64_t dx = X[SB[i]] - X[SA[i]], dy = Y[SB[i]] - Y[SA[i]];
-			int64_t d = dx * dx + dy * dy;
-			if (d > best_d) best_d = d, best = i;
+			const int64_t dx = X[SB[i]] - X[SA[i]], dy = Y[SB[i]] - Y[SA[i]];
+			const int64_t d = dx * dx + dy * dy;
+			if (d > best_d) {
+				best_d = d;
+				A = -dy, B = dx;
+				Cc = -(A * (int64_t)X[SA[i]] + B * (int64_t)Y[SA[i]]);
+			}
 		}
-		int64_t A = -(int64_t)(Y[SB[best]] - Y[SA[best]]), B = (int64_t)(X[SB[best]] - X[SA[best]]);
-		int64_t Cc = -(A * (int64_t)X[SA[best]] + B * (int64_t)Y[SA[best]]);
 		int64_t sup = 128 * (iabs64(A) + iabs64(B));
 		t.ea[0] = 256 * A, t.eb[0] = 256 * B, t.ec[0] = Cc + 128 * (A + B) + sup;
 		t.ea[1] = -256 * A, t.eb[1] = -256 * B, t.ec[1] = -(Cc + 128 * (A + B)) + sup;
@@ -284,16 +290,17 @@ SVO_HD inline bool tri_setup(const float *p0, const float *p1, const float *p2, 
 	// shard window on the two screen axes: voxel = axis 0: (uz, px, py); 1: (py, uz, px); 2: (px, py, uz)
 	const int wx = axis == 0u ? 1 : (axis == 1u ? 2 : 0); // world axis of screen x
 	const int wy = axis == 0u ? 2 : (axis == 1u ? 0 : 1);
-	px0 = tmax(px0, (int64_t)sb.lo[wx]), px1 = tmin(px1, (int64_t)sb.hi[wx] - 1);
-	py0 = tmax(py0, (int64_t)sb.lo[wy]), py1 = tmin(py1, (int64_t)sb.hi[wy] - 1);
+	px0 = tmax(px0, (int64_t)pick3(sb.lo, wx)), px1 = tmin(px1, (int64_t)pick3(sb.hi, wx) - 1);
+	py0 = tmax(py0, (int64_t)pick3(sb.lo, wy)), py1 = tmin(py1, (int64_t)pick3(sb.hi, wy) - 1);
 	t.px0 = (int32_t)px0, t.px1 = (int32_t)px1, t.py0 = (int32_t)py0, t.py1 = (int32_t)py1;
 	if (px0 > px1 || py0 > py1) return false;
 	// depth range vs shard along the depth axis (fragments are clamped into [zr_lo, zr_hi])
 	{
 		uint32_t zlo = tmin(t.zr_lo, res - 1u), zhi = tmin(t.zr_hi, res - 1u);
-		if (zhi < sb.lo[sz] || zlo >= sb.hi[sz]) return false;
-		t.zs_lo = sb.lo[sz], t.zs_hi = sb.hi[sz];
-		t.cull_depth = zlo < sb.lo[sz] || zhi >= sb.hi[sz];
+		const uint32_t wlo = pick3(sb.lo, (uint32_t)sz), whi = pick3(sb.hi, (uint32_t)sz);
+		if (zhi < wlo || zlo >= whi) return false;
+		t.zs_lo = wlo, t.zs_hi = whi;
+		t.cull_depth = zlo < wlo || zhi >= whi;
 	}
 
 	// depth plane (fp64)
