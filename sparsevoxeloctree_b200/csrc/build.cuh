@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(256) k_emit_octree(EmitParams ep, uint32_t *__
 	const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	if (g < ep.total_blocks) {
-		uint32_t d = 1;
+		uint32_t d = ep.level; // the window of depth-d nodes' blocks that holds g: search from the deepest (largest) one
 #pragma unroll 1
-		while (d < ep.level && g >= ep.block_base[d + 1]) ++d;
+		while (d > 1u && g < ep.block_base[d]) --d;
 		const uint64_t j = g - ep.block_base[d];
 		const uint32_t *first = ep.first[d];
 		const unsigned char *slot = ep.slot[d];
