@@ -72,6 +72,27 @@ inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit) {
 SVO_DEV uint32_t hist_digit(uint32_t lo, uint32_t hi, uint32_t r /*relative shift, uniform*/, uint32_t mask) {
 	return (r < 32u ? __funnelshift_r(lo, hi, r) : hi >> (r - 32u)) & mask;
 }
+// Shared-memory add through a 32-bit shared-window address computed once per thread: taking &s_hist[i] as a generic
+// pointer makes the compiler rebuild the window base (S2UR SR_CgaCtaId, ...) in front of every atomic.
+SVO_DEV uint32_t shared_address(const void *p) {
+#if defined(__CUDA_ARCH__)
+	uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+	asm volatile("" : "+r"(a)); // opaque: otherwise the base is rematerialised (4 instructions) at every use
+	return a;
+#else
+	(void)p;
+	return 0u;
+#endif
+}
+SVO_DEV void shared_add(uint32_t addr, uint32_t *generic, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+	(void)generic;
+	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+#else
+	(void)addr;
+	atomicAdd(generic, v);
+#endif
+}
 template <int NPASS>
 __global__ void __launch_bounds__(HIST_BLOCK)
     k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n, SortPasses sp, uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/) {
@@ -80,6 +101,7 @@ __global__ void __launch_bounds__(HIST_BLOCK)
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
 	const uint32_t s0 = sp.shift[0];
+	const uint32_t s_base = shared_address(s_hist);
 	const uint64_t per_block = (uint64_t)HIST_BLOCK * HIST_ITEMS;
 	for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < n; base += (uint64_t)gridDim.x * per_block) {
 		const bool full = base + per_block <= n;
@@ -97,10 +119,11 @@ __global__ void __launch_bounds__(HIST_BLOCK)
 				const uint32_t r = sp.shift[p] - s0;
 				const uint32_t d = hist_digit(lo, hi, r, sp.mask[p]);
 				const bool uniform = hist_digit(dlo, dhi, r, sp.mask[p]) == 0u;
+				// (grouping by __match_any_sync measured slower: MATCH costs more than the adds)
 				if (uniform) {
-					if (lane == 0) atomicAdd(&s_hist[p * MAX_RADIX + d], 32u);
+					if (lane == 0) shared_add(s_base + ((p * MAX_RADIX + d) << 2), &s_hist[p * MAX_RADIX + d], 32u);
 				} else if (ok)
-					atomicAdd(&s_hist[p * MAX_RADIX + d], 1u); // (grouping by __match_any_sync measured slower: MATCH costs more than the adds)
+					shared_add(s_base + ((p * MAX_RADIX + d) << 2), &s_hist[p * MAX_RADIX + d], 1u);
 			}
 		}
 	}
