@@ -69,8 +69,9 @@ inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit) {
 // every pass at once, whether the whole warp falls into one bin -- then a single lane adds 32.
 // The pass loop is unrolled (NPASS is a template parameter) and runs on the two 32-bit halves of
 // key >> shift[0], so a digit costs one funnel shift and one AND instead of a variable 64-bit shift.
-SVO_DEV uint32_t hist_digit(uint32_t lo, uint32_t hi, uint32_t r /*relative shift, uniform*/, uint32_t mask) {
-	return (r < 32u ? __funnelshift_r(lo, hi, r) : hi >> (r - 32u)) & mask;
+// NARROW: every relative shift is below 32 (always the case for up to 4 passes of 9 bits): no second form needed
+template <bool NARROW> SVO_DEV uint32_t hist_digit(uint32_t lo, uint32_t hi, uint32_t r /*relative shift, uniform*/, uint32_t mask) {
+	return (NARROW || r < 32u ? __funnelshift_r(lo, hi, r) : hi >> (r - 32u)) & mask;
 }
 // Shared-memory add through a 32-bit shared-window address computed once per thread: taking &s_hist[i] as a generic
 // pointer makes the compiler rebuild the window base (S2UR SR_CgaCtaId, ...) in front of every atomic.
@@ -93,7 +94,7 @@ SVO_DEV void shared_add(uint32_t addr, uint32_t *generic, uint32_t v) {
 	atomicAdd(generic, v);
 #endif
 }
-template <int NPASS>
+template <int NPASS, bool NARROW>
 __global__ void __launch_bounds__(HIST_BLOCK)
     k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n, SortPasses sp, uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/) {
 	__shared__ uint32_t s_hist[NPASS * MAX_RADIX];
@@ -117,8 +118,8 @@ __global__ void __launch_bounds__(HIST_BLOCK)
 #pragma unroll
 			for (int p = 0; p < NPASS; ++p) {
 				const uint32_t r = sp.shift[p] - s0;
-				const uint32_t d = hist_digit(lo, hi, r, sp.mask[p]);
-				const bool uniform = hist_digit(dlo, dhi, r, sp.mask[p]) == 0u;
+				const uint32_t d = hist_digit<NARROW>(lo, hi, r, sp.mask[p]);
+				const bool uniform = hist_digit<NARROW>(dlo, dhi, r, sp.mask[p]) == 0u;
 				// (grouping by __match_any_sync measured slower: MATCH costs more than the adds)
 				if (uniform) {
 					if (lane == 0) shared_add(s_base + ((p * MAX_RADIX + d) << 2), &s_hist[p * MAX_RADIX + d], 32u);
@@ -476,9 +477,17 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	uint32_t hgrid = div_up(n, (uint64_t)HIST_BLOCK * HIST_ITEMS);
 	const uint32_t hmax = (uint32_t)(n_sm > 0 ? n_sm : 148) * (uint32_t)SVO_HIST_GRID;
 	if (hgrid > hmax) hgrid = hmax;
+	const bool narrow = sp.shift[sp.n_pass - 1] - sp.shift[0] < 32u;
 	switch (sp.n_pass) {
-#define SVO_HIST_CASE(NP) \
-	case NP: SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, k_radix_histogram<NP>, (const uint64_t *)a, n, sp, sc.hist.p); break;
+#define SVO_HIST_CASE(NP)                                                                                                \
+	case NP: {                                                                                                           \
+		if (narrow) {                                                                                                    \
+			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, true>), (const uint64_t *)a, n, sp, sc.hist.p);   \
+		} else {                                                                                                         \
+			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, false>), (const uint64_t *)a, n, sp, sc.hist.p);  \
+		}                                                                                                                \
+		break;                                                                                                           \
+	}
 		SVO_HIST_CASE(1) SVO_HIST_CASE(2) SVO_HIST_CASE(3) SVO_HIST_CASE(4) SVO_HIST_CASE(5) SVO_HIST_CASE(6) SVO_HIST_CASE(7)
 		SVO_HIST_CASE(8)
 #undef SVO_HIST_CASE
