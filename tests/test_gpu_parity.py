@@ -66,11 +66,47 @@ def test_random_soup_levels(lib, level, mode):
     check_against_oracle(lib, scenes.random_soup(400, 100 + level, 0.002, 1.2), level, mode)
 
 
-def test_large_triangles_level11(lib):
+def test_large_triangles_level9(lib):
     # huge triangles only: the row-span / output-parallel path at a high level
     m = scenes.living_room_like(n_boxes=3, n_small=50)
     info = check_against_oracle(lib, m, 9, api.CONSERVATIVE_EXACT)
     assert info["fragments"] > 1_000_000
+
+
+@pytest.mark.parametrize("level,seed", [(11, 41), (12, 42)])
+def test_big_triangles_above_level10(lib, level, seed):
+    """Levels above 10 take the two-table Morton path (coordinate bits 10.. are spread separately) and rows that cross
+    multiples of 1024 pixels; a few wall-sized triangles in general position plus some small ones, against the oracle."""
+    rng = np.random.default_rng(seed)
+    big = rng.uniform(-0.95, 0.95, (3 if level == 11 else 2, 3, 3))
+    small_c = rng.uniform(-0.9, 0.9, (40, 1, 3))
+    small = small_c + rng.uniform(-0.01, 0.01, (40, 3, 3))
+    pos = np.concatenate([big, small]).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(len(pos), dtype=np.uint32)
+    nb = 3 * len(big)
+    draws = np.array([(0, nb, 0xFFFFFFFF, 0x00204060), (nb, len(idx) - nb, 0xFFFFFFFF, 0x00A0B0C0)], scenes.DRAW_DTYPE)
+    info = check_against_oracle(lib, scenes.Mesh(pos, idx, draws, f"big{level}"), level, api.CONSERVATIVE_EXACT)
+    assert info["fragments"] > 500_000
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_random_configurations(lib, case):
+    """Seeded fuzz over scene size, triangle sizes, level, raster mode, sharding and texturing."""
+    rng = np.random.default_rng(1000 + case)
+    level = int(rng.integers(3, 11))
+    mode = [api.CENTER, api.CONSERVATIVE_EXACT, api.CONSERVATIVE_DILATE][int(rng.integers(0, 3))]
+    n = int(rng.integers(20, 600))
+    lo = float(np.exp(rng.uniform(np.log(0.002), np.log(0.05))))
+    hi = float(lo * np.exp(rng.uniform(np.log(2), np.log(60))))
+    if rng.random() < 0.4:
+        mesh = scenes.textured_soup(n, 2000 + case, size_lo=lo, size_hi=min(hi, 0.6), big_quads=bool(rng.integers(0, 2)))
+    else:
+        mesh = scenes.random_soup(n, 2000 + case, lo, min(hi, 1.5), n_mat=int(rng.integers(1, 5)))
+    shard = None
+    if level >= 4 and rng.random() < 0.35:
+        sl = int(rng.integers(1, 3))
+        shard = (sl, tuple(int(v) for v in rng.integers(0, 1 << sl, 3)))
+    check_against_oracle(lib, mesh, level, mode, shard=shard)
 
 
 @pytest.mark.parametrize("cube", [(0, 0, 0), (1, 0, 1), (1, 1, 1)])
