@@ -177,6 +177,9 @@ template <int BLOCK, int ITEMS, int RBITS> struct OnesweepCfg {
 #ifndef SVO_OS_BALLOT
 #define SVO_OS_BALLOT 1 // 1: warp multi-split by one vote per digit bit; 0: MATCH.ANY (measured slower on sm_100a)
 #endif
+#ifndef SVO_OS_SPLIT_SMEM
+#define SVO_OS_SPLIT_SMEM 1 // 0.873 -> 0.864 ms per pass
+#endif
 #ifndef SVO_OS_BRANCHY_ATOMIC
 #define SVO_OS_BRANCHY_ATOMIC 0
 #endif
@@ -328,7 +331,15 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
 		const uint32_t d = (FULL || wbase + i * 32 + lane < tile_count) ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
+#if SVO_OS_SPLIT_SMEM
+		{ // low and high halves in separate arrays: 32-bit stores to random slots conflict less than 64-bit ones
+			const uint32_t pos = s_tile_off[d] + s_hist[warp * NB + d] + rank[i];
+			reinterpret_cast<uint32_t *>(s_keys)[pos] = (uint32_t)key[i];
+			reinterpret_cast<uint32_t *>(s_keys)[TILE + pos] = (uint32_t)(key[i] >> 32);
+		}
+#else
 		s_keys[s_tile_off[d] + s_hist[warp * NB + d] + rank[i]] = key[i];
+#endif
 	}
 
 	// decoupled look-back, per digit.  Kept lean on purpose: every digit thread of every tile spins here, so
@@ -385,7 +396,12 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 	for (int i = 0; i < ITEMS; ++i) {
 		const uint32_t idx = i * BLOCK + threadIdx.x;
 		if (FULL || idx < tile_count) {
+#if SVO_OS_SPLIT_SMEM
+			const uint64_t k = (uint64_t)reinterpret_cast<const uint32_t *>(s_keys)[idx] |
+			                   ((uint64_t)reinterpret_cast<const uint32_t *>(s_keys)[TILE + idx] << 32);
+#else
 			const uint64_t k = s_keys[idx];
+#endif
 			const uint32_t d = (uint32_t)(k >> shift) & mask;
 #if (SVO_OS_EXPERIMENT & 1)
 			keys_out[(uint64_t)tile * TILE + idx] = k; (void)d;
