@@ -304,11 +304,15 @@ struct EmitParams {
 // HBM).  STAGED = true: the warp's 32 blocks (1 KB, contiguous) are transposed through shared memory so that every
 // store instruction writes 512 contiguous bytes -- full sectors, which is what counts when `words` is a peer GPU's
 // memory and the stores cross NVLink (450 -> 670 GB/s measured).
+#ifndef SVO_EMITO_BLOCK
+#define SVO_EMITO_BLOCK 128
+#endif
+constexpr int EMITO_BLOCK = SVO_EMITO_BLOCK;
 template <bool STAGED>
-__global__ void __launch_bounds__(256) k_emit_octree(EmitParams ep, uint32_t *__restrict__ words) {
-	__shared__ uint4 s_stage[256 * 2];
+__global__ void __launch_bounds__(EMITO_BLOCK) k_emit_octree(EmitParams ep, uint32_t *__restrict__ words) {
+	__shared__ uint4 s_stage[STAGED ? EMITO_BLOCK * 2 : 1];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	const uint64_t g = (uint64_t)blockIdx.x * EMITO_BLOCK + threadIdx.x;
 	uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	if (g < ep.total_blocks) {
 		uint32_t d = ep.level; // the window of depth-d nodes' blocks that holds g: search from the deepest (largest) one
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(256) k_emit_octree(EmitParams ep, uint32_t *__
 	ws[2 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
 	__syncwarp();
 	// the warp's blocks g0 .. g0+31 occupy 64 consecutive uint4; lane l stores vectors l and 32 + l
-	const uint64_t g0 = (uint64_t)blockIdx.x * 256 + warp * 32;
+	const uint64_t g0 = (uint64_t)blockIdx.x * EMITO_BLOCK + warp * 32;
 #pragma unroll
 	for (int h = 0; h < 2; ++h) {
 		const uint64_t blk = g0 + (uint64_t)((h * 32 + lane) >> 1); // block this vector belongs to

@@ -770,9 +770,9 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 		auto k_direct = k_emit_octree<false>;
 		auto k_staged = k_emit_octree<true>;
 		if (skip_root) // stitched into another (usually a peer GPU's) buffer
-			SVO_LAUNCH(div_up(ep.total_blocks, 256), 256, 0, s, k_staged, ep, d_dst);
+			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_staged, ep, d_dst);
 		else
-			SVO_LAUNCH(div_up(ep.total_blocks, 256), 256, 0, s, k_direct, ep, d_dst);
+			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_direct, ep, d_dst);
 	}
 	SVO_CUDA_TRY(cudaGetLastError());
 	return SVO_OK;
