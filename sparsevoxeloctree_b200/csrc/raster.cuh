@@ -18,7 +18,10 @@
 namespace svo {
 
 constexpr int64_t SMALL_AREA = 256; // candidate-rectangle pixels handled by a single thread
-constexpr int RASTER_BLOCK = 128;
+#ifndef SVO_RASTER_BLOCK
+#define SVO_RASTER_BLOCK 128
+#endif
+constexpr int RASTER_BLOCK = SVO_RASTER_BLOCK;
 constexpr int LARGE_ROW_CHUNK = 128; // rows of a large triangle handled by one warp before it strides on
 #ifndef SVO_EMIT_BLOCK
 #define SVO_EMIT_BLOCK 256
