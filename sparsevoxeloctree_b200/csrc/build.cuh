@@ -24,6 +24,7 @@
 namespace svo {
 
 constexpr int CMP_BLOCK = 256, CMP_ITEMS = 8, CMP_TILE = CMP_BLOCK * CMP_ITEMS;
+static_assert(CMP_ITEMS == 8, "k_parent_compact packs a thread's 8 slot bytes into one 64-bit store");
 constexpr int MAX_LEVEL = 16;
 
 // ---- de-duplicate + colour reduce + the deepest K-1 parent levels, fused ---------------------------------
@@ -253,14 +254,31 @@ __global__ void __launch_bounds__(CMP_BLOCK)
 		bool head[CMP_ITEMS];
 		uint64_t prev = (base > 0 && base < n) ? keys_in[base - 1] : 0;
 		uint32_t cnt = 0;
+		const bool whole = base + CMP_ITEMS <= n;
+		if (whole) { // 16-byte loads (base is a multiple of 8 keys)
+#pragma unroll
+			for (int i = 0; i < CMP_ITEMS; i += 2) {
+				const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(keys_in + base + i);
+				k[i] = v.x, k[i + 1] = v.y;
+			}
+		}
 #pragma unroll
 		for (int i = 0; i < CMP_ITEMS; ++i) {
 			const uint64_t idx = base + i;
-			k[i] = idx < n ? keys_in[idx] : 0;
+			if (!whole) k[i] = idx < n ? keys_in[idx] : 0;
 			head[i] = idx < n && (idx == 0 || (k[i] >> 3) != (prev >> 3));
 			prev = k[i];
 			cnt += head[i] ? 1u : 0u;
-			if (idx < n) slot_in[idx] = (unsigned char)(k[i] & 7u);
+		}
+		if (base + CMP_ITEMS <= n) { // the thread's 8 slot bytes in one aligned store (slot arrays are 8-byte aligned)
+			uint64_t packed = 0;
+#pragma unroll
+			for (int i = 0; i < CMP_ITEMS; ++i) packed |= (k[i] & 7ull) << (8 * i);
+			*reinterpret_cast<uint64_t *>(slot_in + base) = packed;
+		} else {
+#pragma unroll
+			for (int i = 0; i < CMP_ITEMS; ++i)
+				if (base + i < n) slot_in[base + i] = (unsigned char)(k[i] & 7u);
 		}
 		uint64_t total;
 		const uint64_t excl = block_exclusive_sum<CMP_BLOCK, uint64_t>((uint64_t)cnt, total, s_warp);

@@ -623,7 +623,7 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 		uint64_t pool_first = 0, pool_slot = 0;
 		for (uint32_t d = 1; d <= b->level; ++d) {
 			pool_first += node_cap(F, d - 1);
-			pool_slot += node_cap(F, d);
+			pool_slot += (node_cap(F, d) + 7) & ~7ull; // every depth's slot array starts 8-byte aligned (k_parent_compact stores 8 slots at once)
 		}
 		if ((rc = b->first.alloc(pool_first, s)) || (rc = b->slot.alloc(pool_slot, s))) break;
 		const uint64_t tiles = (F + CMP_TILE - 1) / CMP_TILE + 1;
@@ -680,7 +680,7 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 		uint64_t fo = 0, so = 0;
 		for (uint32_t d = L; d >= 1; --d) {
 			first_off[d] = fo, slot_off[d] = so;
-			fo += node_cap(F, d - 1), so += node_cap(F, d);
+			fo += node_cap(F, d - 1), so += (node_cap(F, d) + 7) & ~7ull;
 		}
 	}
 	if (F) {
