@@ -4,7 +4,9 @@
 // Replaces the reference level loop (src/OctreeBuilder.cpp:142-210: octree_init_node / octree_tag_node /
 // octree_alloc_node / octree_modify_arg, 4L-2 dependent dispatches, F*L fragment re-reads and F*L(L+1)/2
 // dependent pointer loads) with streaming passes over sorted keys:
-//   k_reduce_fused   : ONE pass over the sorted fragments produces the three deepest levels at once:
+//   k_reduce_count   : runs per tile at the three deepest granularities; a scan over the tiles then gives every
+//                      tile its position in the outputs, so that no tile waits for another one in
+//   k_reduce_fused   : one pass over the sorted fragments produces the three deepest levels at once:
 //                      runs of equal Morton code -> leaves (colours folded with the reference's integer
 //                      running average in run = emission order, octree_tag_node.comp:48-57), and the runs of
 //                      equal key>>3 / key>>6 -> the depth L-1 / L-2 nodes.

@@ -3,10 +3,16 @@
 //
 // Replaces voxelizer.vert/.geom/.frag + the fixed-function rasterizer + the count pass
 // (src/Voxelizer.cpp:134-179).  Two work classes, decided per triangle from its candidate rectangle:
-//   small (area <= SMALL_AREA pixels): one thread walks the rectangle with exact integer edge tests;
-//   large: one warp computes exact per-row spans (integer division, no per-pixel tests); emission is
-//          output-parallel over the span pixels (load-balanced row search), so huge wall/floor triangles
-//          are spread over the whole GPU and stored with fully coalesced 8-byte writes.
+//   small (area <= SMALL_AREA pixels, and every triangle of an alpha-tested texture): one thread walks the
+//          rectangle with exact integer edge functions, stepped per pixel; the search for the next covered
+//          pixel is a loop of its own so that the warp's lanes meet again before the per-fragment work;
+//   large: warps compute exact per-row spans (integer division, no per-pixel tests); emission is
+//          output-parallel over the span pixels (load-balanced row search, 8 consecutive fragments per thread
+//          with the depth plane and the (x, y) Morton code kept in registers), so huge wall/floor triangles
+//          are spread over the whole GPU and stored with fully coalesced 16-byte writes.
+// Morton codes come from a 1024-entry spread table in shared memory (two lookups per coordinate above level 10).
+// Textured draws (texture.cuh) sample per fragment; the TEX template parameter keeps the untextured kernels free
+// of that code.
 // Fragment order: all small-triangle fragments in triangle order, then all large-triangle fragments in
 // triangle / row / x order.  A voxel receives at most one fragment per triangle, so together with the
 // stable sort this fixes the colour-averaging order per voxel: (class, triangle id).
