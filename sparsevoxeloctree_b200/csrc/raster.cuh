@@ -3,7 +3,7 @@
 //
 // Replaces voxelizer.vert/.geom/.frag + the fixed-function rasterizer + the count pass
 // (src/Voxelizer.cpp:134-179).  Two work classes, decided per triangle from its candidate rectangle:
-//   small (area <= SMALL_AREA pixels, and every triangle of an alpha-tested texture): one thread walks the
+//   small (area <= SMALL_AREA pixels): one thread walks the
 //          rectangle with exact integer edge functions, stepped per pixel; the search for the next covered
 //          pixel is a loop of its own so that the warp's lanes meet again before the per-fragment work;
 //   large: warps compute exact per-row spans (integer division, no per-pixel tests); emission is
@@ -12,7 +12,7 @@
 //          are spread over the whole GPU and stored with fully coalesced 16-byte writes.
 // Morton codes come from a 1024-entry spread table in shared memory (two lookups per coordinate above level 10).
 // Textured draws (texture.cuh) sample per fragment; the TEX template parameter keeps the untextured kernels free
-// of that code.
+// of that code.  Large triangles of alpha-tested textures: rows counted by sampling, emitted by k_emit_alpha_rows.
 // Fragment order: all small-triangle fragments in triangle order, then all large-triangle fragments in
 // triangle / row / x order.  A voxel receives at most one fragment per triangle, so together with the
 // stable sort this fixes the colour-averaging order per voxel: (class, triangle id).
@@ -159,8 +159,9 @@ struct SmallWalk {
 // ---- pass 1: classify + count small ------------------------------------------------------------------
 // cnt_small[t]  = fragments of a small triangle (0 for large / culled)
 // packed[t]     = (is_large << 40) | rows of a large triangle
-// Triangles of an alpha-tested texture always take the small path: their fragment count depends on the samples
-// (voxelizer.frag:29-30 discards before the counter), which the span arithmetic of the large path cannot know.
+// Triangles of an alpha-tested texture produce a fragment only where the sample passes the alpha test
+// (voxelizer.frag:29-30 discards before the counter): small ones sample while they count; large ones get their rows
+// counted by sampling (k_large_rows) and emitted by k_emit_alpha_rows instead of the span arithmetic.
 template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
     k_classify_count(SceneView sv, RasterParams rp, uint32_t *__restrict__ cnt_small, uint64_t *__restrict__ packed) {
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	uint32_t cnt = 0;
 	uint64_t pk = 0;
 	if (load_and_setup<TEX>(sv, rp, t, ts, sh)) {
-		if (ts.full_area <= SMALL_AREA || (TEX && sh.alpha)) {
+		if (ts.full_area <= SMALL_AREA) {
 			SmallWalk wk;
 			wk.begin(ts);
 			while (wk.next(ts)) {
@@ -193,7 +194,7 @@ struct LargeTri {
 	uint32_t rgb;
 	uint32_t tri;      // triangle id
 	uint32_t row_base; // first row in the (sparse) row arrays
-	uint32_t textured; // colour comes from luv[li] (textured scenes only)
+	uint32_t textured; // bit 0: colour comes from luv[li] (textured scenes only); bit 1: alpha-tested texture
 };
 
 // gather the large triangles into a dense list (order = triangle order)
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	if (lane == 0 && blockIdx.y == 0) {
 		lt.ts = ts;
 		lt.rgb = sh.rgb;
-		lt.textured = sh.textured ? 1u : 0u;
+		lt.textured = (sh.textured ? 1u : 0u) | (sh.alpha ? 2u : 0u);
 		if (TEX && sh.textured) luv[li] = sh.um;
 	}
 	const int32_t h = ts.py1 - ts.py0 + 1;
@@ -235,7 +236,12 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 		int32_t x_lo, x_hi;
 		row_span(ts, ts.py0 + r, x_lo, x_hi);
 		row_span_depth_window(ts, rp.res, ts.py0 + r, x_lo, x_hi);
-		const uint32_t len = x_hi >= x_lo ? (uint32_t)(x_hi - x_lo + 1) : 0u;
+		uint32_t len = x_hi >= x_lo ? (uint32_t)(x_hi - x_lo + 1) : 0u;
+		if (TEX && sh.alpha && len) { // alpha-tested: the row holds as many fragments as samples survive
+			len = 0;
+			uint32_t c;
+			for (int32_t px = x_lo; px <= x_hi; ++px) len += sample_colour(sv.tex, sh.um, px, ts.py0 + r, c) ? 1u : 0u;
+		}
 		row_pk[lt.row_base + r] = len ? ((1ull << 40) | len) : 0ull;
 		row_x0[lt.row_base + r] = (uint32_t)x_lo;
 	}
@@ -386,7 +392,8 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 				hi_xrow = (s_lut[(xl >> 10) & 1023u] << wx) | row_hi;
 				rgb = lt->rgb & 0xffffffu;
 				if (TEX) {
-					um = lt->textured ? &luv[rows.li[r]] : nullptr;
+					um = (lt->textured & 1u) ? &luv[rows.li[r]] : nullptr;
+					if (lt->textured & 2u) um = nullptr; // alpha-tested rows are rewritten by k_emit_alpha_rows
 					py_tex = py;
 				}
 			}
@@ -411,6 +418,34 @@ __global__ void __launch_bounds__(EMIT_BLOCK)
 #pragma unroll
 		for (int k = 0; k < EMIT_ITEMS; ++k)
 			if (j0 + k < c1) dst[k] = out[k];
+	}
+}
+
+// Rows of large alpha-tested triangles: one thread per dense row walks the row's span, samples, and writes the
+// surviving fragments at the row's offset (the count pass counted them the same way).  Runs after k_emit_large,
+// whose span arithmetic does not apply to these rows (whatever it put at their ordinals is overwritten here).
+template <bool TEX>
+__global__ void __launch_bounds__(RASTER_BLOCK)
+    k_emit_alpha_rows(RasterParams rp, TexView tv, const LargeTri *__restrict__ large, const UvMap *__restrict__ luv, DenseRows rows,
+                      uint32_t n_rows, uint64_t *__restrict__ frags /* already offset to the large region */) {
+	__shared__ uint32_t s_lut[1024];
+	fill_spread_table(s_lut, RASTER_BLOCK);
+	__syncthreads();
+	const uint32_t r = blockIdx.x * RASTER_BLOCK + threadIdx.x;
+	if (!TEX || r >= n_rows) return;
+	const uint32_t li = rows.li[r];
+	const LargeTri &lt = large[li];
+	if (!(lt.textured & 2u)) return;
+	const int32_t py = (int32_t)(rows.xy[r] >> 16);
+	int32_t x_lo, x_hi;
+	row_span(lt.ts, py, x_lo, x_hi);
+	row_span_depth_window(lt.ts, rp.res, py, x_lo, x_hi);
+	uint64_t o = rows.off[r];
+	for (int32_t px = x_lo; px <= x_hi; ++px) {
+		uint32_t rgb, uz;
+		if (!sample_colour(tv, luv[li], px, py, rgb)) continue;
+		pixel_fragment(lt.ts, rp.res, px, py, uz); // inside the depth window by construction of the span
+		frags[o++] = make_fragment_lut(lt.ts, rp, s_lut, px, py, uz, rgb);
 	}
 }
 

@@ -561,8 +561,13 @@ int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
 	if (v->n_frag_large) {
 		DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
 		if (tex)
+		{
 			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<true>, v->rp, sv.tex, (const LargeTri *)v->large.p,
 			           (const UvMap *)v->large_uv.p, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
+			// rows of large alpha-tested triangles (none in most scenes: the kernel then exits at once)
+			SVO_LAUNCH(div_up(v->n_rows, RASTER_BLOCK), RASTER_BLOCK, 0, s, k_emit_alpha_rows<true>, v->rp, sv.tex,
+			           (const LargeTri *)v->large.p, (const UvMap *)v->large_uv.p, dr, v->n_rows, v->frags.p + v->n_frag_small);
+		}
 		else
 			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<false>, v->rp, sv.tex, (const LargeTri *)v->large.p,
 			           (const UvMap *)nullptr, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
