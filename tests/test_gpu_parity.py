@@ -228,6 +228,22 @@ def test_textured_soup(lib, level, mode):
     assert info["fragments"] > 1000
 
 
+def test_wall_sized_alpha_tested_quad(lib):
+    """A quad across the whole grid with an alpha-tested texture: the large path counts and emits its rows by sampling
+    (k_large_rows / k_emit_alpha_rows); about half of its pixels are discarded."""
+    import time
+    tex = scenes.procedural_textures(4)
+    pos = np.array([[-0.93, -0.9, 0.1], [0.95, -0.92, 0.3], [0.94, 0.91, 0.35], [-0.9, 0.93, 0.05]], np.float32)
+    uv = np.array([[0, 0], [7.3, 0.2], [7.1, 6.4], [-0.2, 6.1]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    draws = np.array([(0, 6, 1, 0x00808080)], scenes.DRAW_DTYPE)  # texture 1: the one with alpha holes
+    mesh = scenes.Mesh(pos, idx, draws, "alpha_wall", texcoords=uv, textures=tex)
+    t = time.time()
+    info = check_against_oracle(lib, mesh, 10, api.CONSERVATIVE_EXACT)
+    assert 200_000 < info["fragments"] < 900_000  # ~0.9 M covered pixels, a good part of them discarded
+    assert time.time() - t < 60
+
+
 def test_textured_octant_shard(lib):
     check_against_oracle(lib, scenes.textured_soup(300, 31, size_hi=0.4), 8, api.CONSERVATIVE_EXACT, shard=(1, (0, 1, 1)))
 
