@@ -239,15 +239,19 @@ def pipeline_mesh():
     return scenes.random_soup(c["n_tri"], c["seed"], c["size_lo"], c["size_hi"], c["n_mat"])
 
 
-def make_pipeline_case():
+def make_pipeline_case(mode=None, tag="soup260_L6"):
     """The whole reference path on one small multi-material scene, every programmable stage executed from the
     reference's binaries: voxelizer.geom per triangle -> [pinned rasterizer: covered pixels + depth] -> voxelizer.frag
     appending to ONE fragment list through its atomic counter (Scene::CmdDraw order: draw by draw, Scene.cpp:450-463)
     -> the four builder shaders (CmdBuild) -> octree_tracer.frag on the resulting node buffer."""
     c = PIPELINE_SCENE
-    level, mode, res = c["level"], c["mode"], 1 << c["level"]
+    level, res = c["level"], 1 << c["level"]
+    mode = c["mode"] if mode is None else mode
     mesh = pipeline_mesh()
-    geom = si.Module.from_u32_file(SPV + "voxelizer.geom.u32", spec={0: res})
+    # Mode B (no VK_EXT_conservative_rasterization, Voxelizer.cpp:92-99): the dilating geometry shader, then plain
+    # centre sampling of the dilated triangle with depth clipping (depthClampEnable = 0)
+    dilate = mode == oracle.CONSERVATIVE_DILATE
+    geom = si.Module.from_u32_file(SPV + ("voxelizer_conservative.geom.u32" if dilate else "voxelizer.geom.u32"), spec={0: res})
     frag = si.Module.from_u32_file(SPV + "voxelizer.frag.u32", spec={0: res, 1: 1})
     g_axis, g_aabb, g_zr = (geom.var_by_location(k, 3) for k in (1, 2, 3))
     f_axis, f_aabb, f_zr, f_uv = (frag.var_by_location(k, 1) for k in (1, 2, 3, 0))
@@ -264,11 +268,14 @@ def make_pipeline_case():
                 v = [x if not isinstance(x, list) else list(x) for x in null_vtx]
                 v[0] = [np.float32(t[q][0]), np.float32(t[q][1]), np.float32(t[q][2]), np.float32(1.0)]
                 gl_in.append(v)
-            geom.run({"gl_in": gl_in, ("loc", 0): [[np.float32(0), np.float32(0)]] * 3}, {}, None, on_emit=emitted.append)
+            with np.errstate(all="ignore"):
+                geom.run({"gl_in": gl_in, ("loc", 0): [[np.float32(0), np.float32(0)]] * 3}, {}, None, on_emit=emitted.append)
             e = emitted[0]
             axis, aabb, zr = int(e[g_axis]), [int(x) for x in e[g_aabb]], [int(x) for x in e[g_zr]]
             px, py, z = oracle.debug_raster_pixels(t[0], t[1], t[2], level, mode)
             for x, y, zz in zip(px, py, z):
+                if dilate and not (0.0 <= zz <= 1.0):
+                    continue  # depth clip happens before the fragment shader
                 try:
                     frag.run({("builtin", 15): [np.float32(x + 0.5), np.float32(y + 0.5), np.float32(zz), np.float32(1.0)],
                               f_axis: axis, f_aabb: aabb, f_zr: zr, f_uv: [np.float32(0), np.float32(0)]},
@@ -279,7 +286,7 @@ def make_pipeline_case():
     packed = flist[: 2 * F].reshape(F, 2).copy()
     words, rng = spirv_build(packed, level, 8 * (1 + sum(min(8 ** q, F) for q in range(1, level))))
     np.savez_compressed(os.path.join(HERE, "spirv_build_pipeline.npz"), level=level, packed=packed, words=words, range_bytes=rng)
-    rays = make_tracer_case("pipeline", size=24)
+    rays = make_tracer_case("pipeline", size=24 if not dilate else 12)
     return dict(level=level, mode=mode, packed=packed, words=words, range_bytes=rng, cameras=rays["cameras"], rays=rays["rays"])
 
 
@@ -287,10 +294,12 @@ if __name__ == "__main__":
     import time
     if "--pipeline-only" in sys.argv or len(sys.argv) == 1:
         t = time.time()
-        o = make_pipeline_case()
-        os.remove(os.path.join(HERE, "spirv_build_pipeline.npz"))  # (scratch for make_tracer_case)
-        np.savez_compressed(os.path.join(HERE, "spirv_pipeline_soup260_L6.npz"), **o)
-        print("pipeline", len(o["packed"]), "fragments ->", o["range_bytes"], "bytes,", len(o["rays"]), "rays", f"{time.time() - t:.0f}s", flush=True)
+        for mode, name in ((None, "spirv_pipeline_soup260_L6.npz"), (oracle.CONSERVATIVE_DILATE, "spirv_pipeline_soup260_L6_modeB.npz")):
+            o = make_pipeline_case(mode)
+            os.remove(os.path.join(HERE, "spirv_build_pipeline.npz"))  # (scratch for make_tracer_case)
+            np.savez_compressed(os.path.join(HERE, name), **o)
+            print("pipeline", name, len(o["packed"]), "fragments ->", o["range_bytes"], "bytes,", len(o["rays"]), "rays",
+                  f"{time.time() - t:.0f}s", flush=True)
         if "--pipeline-only" in sys.argv:
             sys.exit(0)
     if "--tracer-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:

@@ -94,9 +94,10 @@ def test_raymarcher_and_builder_against_reference_tracer_golden(emu):
     cuda_tree_traced_like_reference(emu, TRACER[0])
 
 
-def test_whole_path_against_reference_shaders_end_to_end(emu):
+@pytest.mark.parametrize("which", ["modeA", "modeB"])
+def test_whole_path_against_reference_shaders_end_to_end(emu, which):
     from tests.test_spirv_golden import cuda_whole_path_like_reference
-    cuda_whole_path_like_reference(emu)
+    cuda_whole_path_like_reference(emu, which)
 
 
 def test_empty_scene(emu):
