@@ -227,6 +227,10 @@ def run_ours(args):
             ms, sort_passes = builder.LastMs()
             for k in api.PHASES:
                 phases_acc[k] += ms[k]
+        elif rank == 0 and getattr(sh, "slab", False) and sh.builders and sh.builders[0].GetLeafCount():
+            ms, sort_passes = sh.builders[0].LastMs()  # rank 0's own slab (the roofline line below describes this rank)
+            for k in api.PHASES:
+                phases_acc[k] += ms[k]
     e1.record(stream)
     barrier()
     launches = int(lib.dll.svo_launch_count()) - launches0
@@ -291,9 +295,10 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = hbm_peak()
         roofline = None
-        if single and sort_passes:
+        if sort_passes and phases_acc["sort_passes"] > 0:
             per_launch_ms = phases_acc["sort_passes"] / args.steps / sort_passes
-            alg_bytes = 16.0 * frags  # one read + one write of every 8-byte fragment per onesweep pass
+            # one read + one write of every 8-byte fragment per onesweep pass (N > 1: the fragments of rank 0's slab)
+            alg_bytes = 16.0 * (frags if single else sh.fragment_count_local())
             achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -306,7 +311,9 @@ def run_ours(args):
             roofline = {"bound": "hbm", "kernel": "k_onesweep_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
-                        "launches_per_step": sort_passes}
+                        "launches_per_step": sort_passes, "rank": 0}
+            if not single:
+                roofline["traffic"] = None  # the ncu capture is of the single-GPU launch
         cpu_baseline = None
         if single and not args.no_cpu_baseline:
             times, cl, cores, sample = cpu_reference_run(mesh, level, mode_name, 3, 0, budget_s=25.0)
@@ -323,7 +330,7 @@ def run_ours(args):
                                       f"octant-sharded x{world}, NVLink subtree gather")
                                       + (f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})" if world > 1 else "")},
             "build_ms": ms_per_step,
-            "phases_ms": {k: v / args.steps for k, v in phases_acc.items()} if single else None,
+            "phases_ms": {k: v / args.steps for k, v in phases_acc.items()} if sort_passes else None,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": leaves / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,

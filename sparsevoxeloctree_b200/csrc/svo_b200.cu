@@ -146,6 +146,7 @@ struct svo_builder {
 	uint32_t sort_passes = 0;
 	bool built = false;     // the node words are in b->octree
 	bool prepared = false;  // sort / reduce / levels done, sizes known: ready for an emit
+	bool emitted = false;   // svo_builder_emit_to has run after the last prepare (phase times are complete)
 	EmitParams ep{};
 	DevBuf<uint32_t> root_scratch; // svo_builder_emit_to(skip_root): the root block goes here
 	cudaEvent_t ev[SVO_PHASE_COUNT + 1] = {};
@@ -664,7 +665,7 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	const uint64_t F = v->n_frag;
 	const uint32_t L = b->level;
 	const int n_sm = sm_count(b->device);
-	b->built = b->prepared = false;
+	b->built = b->prepared = b->emitted = false;
 
 	// ---- sort by Morton code (stable) ----
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
@@ -789,7 +790,10 @@ int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_w
 	if ((uint64_t)pointer_bias_words + b->range_bytes / 4 >= (1ull << 30))
 		return fail(SVO_ERR_CAPACITY, "biased child pointers would exceed 30 bits (octree.glsl:110)");
 	DeviceGuard guard(b->device);
-	return emit_into(b, d_dst, pointer_bias_words, skip_root, (cudaStream_t)stream);
+	SVO_TRY(emit_into(b, d_dst, pointer_bias_words, skip_root, (cudaStream_t)stream));
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], (cudaStream_t)stream)); // svo_builder_last_ms covers prepare + emit_to as well
+	b->emitted = true;
+	return SVO_OK;
 }
 
 int svo_builder_root_words(svo_builder *b, uint32_t out[8], void *stream) {
@@ -838,7 +842,7 @@ int svo_builder_rebase_copy(const svo_builder *b, uint32_t *d_dst, uint64_t dst_
 
 int svo_builder_last_ms(svo_builder *b, float *phase_ms, uint32_t *sort_passes) {
 	if (!b || !phase_ms) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
-	if (!b->built) return fail(SVO_ERR_NOT_READY, "build first");
+	if (!b->built && !b->emitted) return fail(SVO_ERR_NOT_READY, "build (or prepare + emit_to) first");
 	DeviceGuard guard(b->device);
 	SVO_CUDA_TRY(cudaEventSynchronize(b->ev[5]));
 	phase_ms[SVO_PHASE_RASTER] = 0.f;
