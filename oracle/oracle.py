@@ -61,6 +61,9 @@ def lib() -> C.CDLL:
         L.orc_debug_sample.restype = C.c_uint32
         L.orc_raymarch_leaf.argtypes = [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)]
         L.orc_raymarch_leaf.restype = C.c_int
+        L.orc_debug_texture_fetch.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p,
+                                                                                         C.c_void_p]
+        L.orc_debug_texture_fetch.restype = None
         L.orc_debug_shade.argtypes = [C.c_void_p]
         L.orc_debug_shade.restype = C.c_uint32
         L.orc_build.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
@@ -142,6 +145,15 @@ class TexSet:
         r = lib().orc_debug_sample(self._h, tex, _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), level,
                                    px, py, _ptr(lod))
         return (None if r == 0 else int(r & 0xffffff)), tuple(int(x) for x in lod)
+
+    def fetch(self, tex, tri_pos, tri_uv, level, px, py):
+        """(uv float64[2], rgba float32[4]) that reach voxelizer.frag for pixel (px,py) of one textured triangle."""
+        p = [np.ascontiguousarray(v, dtype=np.float32) for v in tri_pos]
+        t = [np.ascontiguousarray(v, dtype=np.float32) for v in tri_uv]
+        uv, rgba = np.zeros(2, np.float64), np.zeros(4, np.float32)
+        lib().orc_debug_texture_fetch(self._h, tex, _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), level,
+                                      px, py, _ptr(uv), _ptr(rgba))
+        return uv, rgba
 
     def __del__(self):
         if getattr(self, "_h", None):

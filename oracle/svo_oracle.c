@@ -552,11 +552,14 @@ static int shade(const float c[4], uint32_t *rgb) {
 }
 
 /* voxelizer.frag:27-36: returns 0 when the fragment is discarded (alpha < 0.5), else 1 and the packed colour */
-static int sample_colour(const orc_texset *s, const orc_tex *tex, const orc_uvmap *m, int32_t px, int32_t py, uint32_t *rgb) {
+/* texture(uTextures[id], gTexcoord) at the centre of pixel (px,py): the interpolated coordinates and the filtered value */
+static void sample_value(const orc_texset *s, const orc_tex *tex, const orc_uvmap *m, int32_t px, int32_t py, double uv_out[2],
+                         float c[4]) {
 	const double cx = (double)px + 0.5, cy = (double)py + 0.5;
 	const double u = fma(m->dudx, cx - m->x0, fma(m->dudy, cy - m->y0, m->u0));
 	const double v = fma(m->dvdx, cx - m->x0, fma(m->dvdy, cy - m->y0, m->v0));
-	float c[4];
+	if (uv_out)
+		uv_out[0] = u, uv_out[1] = v;
 	sample_level(s, &tex->lv[m->hi], u, v, c);
 	if (m->lo != m->hi) {
 		float d[4];
@@ -564,7 +567,23 @@ static int sample_colour(const orc_texset *s, const orc_tex *tex, const orc_uvma
 		for (int k = 0; k < 4; ++k)
 			c[k] = lerpf(c[k], d[k], m->delta);
 	}
+}
+static int sample_colour(const orc_texset *s, const orc_tex *tex, const orc_uvmap *m, int32_t px, int32_t py, uint32_t *rgb) {
+	float c[4];
+	sample_value(s, tex, m, px, py, NULL, c);
 	return shade(c, rgb);
+}
+/* debug view for the SPIR-V cross-check: what the fixed-function stages hand to voxelizer.frag for one pixel of a textured
+ * triangle -- the interpolated gTexcoord and the value texture() returns (pinned arithmetic) */
+void orc_debug_texture_fetch(const orc_texset *s, uint32_t tex, const float *p0, const float *p1, const float *p2, const float *uv0,
+                             const float *uv1, const float *uv2, uint32_t level, int32_t px, int32_t py, double uv_out[2],
+                             float rgba_out[4]) {
+	orc_tri t;
+	orc_tri_setup(p0, p1, p2, 1u << level, ORC_CENTER, &t);
+	const float *const p[3] = {p0, p1, p2}, *const uv[3] = {uv0, uv1, uv2};
+	orc_uvmap m;
+	uvmap_setup(s, &s->t[tex], p, uv, t.axis, 1u << level, &m);
+	sample_value(s, &s->t[tex], &m, px, py, uv_out, rgba_out);
 }
 uint32_t orc_debug_shade(const float rgba[4]) {
 	uint32_t rgb = 0;

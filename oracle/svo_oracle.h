@@ -85,6 +85,10 @@ int64_t orc_voxelize_textured(const void *positions, uint32_t pos_stride_bytes, 
 uint32_t orc_debug_sample(const orc_texset *s, uint32_t tex, const float *p0, const float *p1, const float *p2, const float *uv0,
                           const float *uv1, const float *uv2, uint32_t level, int32_t px, int32_t py, uint32_t lod_out[3]);
 
+/* the interpolated gTexcoord and the texture() value (before the alpha test / packing) of one pixel of a textured triangle */
+void orc_debug_texture_fetch(const orc_texset *s, uint32_t tex, const float *p0, const float *p1, const float *p2, const float *uv0,
+                             const float *uv1, const float *uv2, uint32_t level, int32_t px, int32_t py, double uv_out[2],
+                             float rgba_out[4]);
 /* voxelizer.frag:28-30,35,42 on a given sample value: 0xff000000 | (packUnorm4x8(x) & 0xffffff), or 0 when discarded */
 uint32_t orc_debug_shade(const float rgba[4]);
 

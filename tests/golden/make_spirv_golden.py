@@ -290,8 +290,82 @@ def make_pipeline_case(mode=None, tag="soup260_L6"):
     return dict(level=level, mode=mode, packed=packed, words=words, range_bytes=rng, cameras=rays["cameras"], rays=rays["rays"])
 
 
+TEXTURED_SCENE = dict(n_tri=160, seed=23, size_lo=0.02, size_hi=0.2, level=6, mode=oracle.CONSERVATIVE_EXACT)
+
+
+def textured_pipeline_mesh():
+    c = TEXTURED_SCENE
+    return scenes.textured_soup(c["n_tri"], c["seed"], size_lo=c["size_lo"], size_hi=c["size_hi"], big_quads=False)
+
+
+def make_textured_pipeline_case():
+    """The reference's geometry / fragment / builder shaders on a scene with textured and alpha-tested materials.  The two
+    fixed-function stages in between are the pinned ones: the rasterizer supplies the covered pixels, the depth and the
+    interpolated gTexcoord; the texture unit supplies the value of texture() -- the shaders do the rest (texture id from
+    the push constant, alpha-test discard, packUnorm4x8, counter, packing, tree)."""
+    c = TEXTURED_SCENE
+    level, mode, res = c["level"], c["mode"], 1 << c["level"]
+    mesh = textured_pipeline_mesh()
+    ts = oracle.TexSet(mesh.textures)
+    geom = si.Module.from_u32_file(SPV + "voxelizer.geom.u32", spec={0: res})
+    frag = si.Module.from_u32_file(SPV + "voxelizer.frag.u32", spec={0: res, 1: len(mesh.textures)})
+    g_axis, g_aabb, g_zr, g_uv = (geom.var_by_location(k, 3) for k in (1, 2, 3, 0))
+    f_axis, f_aabb, f_zr, f_uv = (frag.var_by_location(k, 1) for k in (1, 2, 3, 0))
+    in_var = next(v for v, (tt, sc) in geom.vars.items() if sc == 1 and 30 not in geom.decor.get(v, {}))
+    null_vtx = geom._null(geom.types[geom.types[geom.vars[in_var][0]][2]][1])
+    cap = 200000
+    counter, flist = np.zeros(1, np.uint32), np.zeros(2 * cap, np.uint32)
+    n_sampled = n_discarded = 0
+    for d in mesh.draws:
+        tex_id = int(d["texture_id"])
+        for k in range(int(d["index_count"]) // 3):
+            ix = mesh.indices[int(d["first_index"]) + 3 * k: int(d["first_index"]) + 3 * k + 3]
+            t, tuv = mesh.positions[ix], mesh.texcoords[ix]
+            emitted, gl_in = [], []
+            for q in range(3):
+                v = [x if not isinstance(x, list) else list(x) for x in null_vtx]
+                v[0] = [np.float32(t[q][0]), np.float32(t[q][1]), np.float32(t[q][2]), np.float32(1.0)]
+                gl_in.append(v)
+            geom.run({"gl_in": gl_in, ("loc", 0): [[np.float32(tuv[q][0]), np.float32(tuv[q][1])] for q in range(3)]}, {}, None,
+                     on_emit=emitted.append)
+            for q in range(3):  # voxelizer.geom passes the texture coordinates through (voxelizer.geom:46-52)
+                assert [float(x) for x in emitted[q][g_uv]] == [float(tuv[q][0]), float(tuv[q][1])]
+            e = emitted[0]
+            axis, aabb, zr = int(e[g_axis]), [int(x) for x in e[g_aabb]], [int(x) for x in e[g_zr]]
+            px, py, z = oracle.debug_raster_pixels(t[0], t[1], t[2], level, mode)
+            for x, y, zz in zip(px, py, z):
+                uv, rgba = (np.zeros(2), np.zeros(4, np.float32))
+                if tex_id != 0xFFFFFFFF:
+                    uv, rgba = ts.fetch(tex_id, t, tuv, level, int(x), int(y))
+
+                def sampler(tid, coord, rgba=rgba, uv=uv, tex_id=tex_id):
+                    assert tid == tex_id and abs(float(coord[0]) - uv[0]) < 1e-3 and abs(float(coord[1]) - uv[1]) < 1e-3
+                    return [np.float32(c_) for c_ in rgba]
+
+                before = int(counter[0])
+                try:
+                    frag.run({("builtin", 15): [np.float32(x + 0.5), np.float32(y + 0.5), np.float32(zz), np.float32(1.0)],
+                              f_axis: axis, f_aabb: aabb, f_zr: zr, f_uv: [np.float32(uv[0]), np.float32(uv[1])]},
+                             {(0, 0): counter, (0, 1): flist}, [0, tex_id, int(d["albedo_rgba8"])], sampler=sampler)
+                except si.Discard:
+                    n_discarded += tex_id != 0xFFFFFFFF and int(counter[0]) == before
+                n_sampled += tex_id != 0xFFFFFFFF
+    F = int(counter[0])
+    packed = flist[: 2 * F].reshape(F, 2).copy()
+    words, rng = spirv_build(packed, level, 8 * (1 + sum(min(8 ** q, F) for q in range(1, level))))
+    return dict(level=level, mode=mode, packed=packed, words=words, range_bytes=rng, sampled=n_sampled, discarded=n_discarded)
+
+
 if __name__ == "__main__":
     import time
+    if "--textured-pipeline-only" in sys.argv or len(sys.argv) == 1:
+        t = time.time()
+        o = make_textured_pipeline_case()
+        np.savez_compressed(os.path.join(HERE, "spirv_pipeline_texsoup160_L6.npz"), **o)
+        print("textured pipeline", len(o["packed"]), "fragments,", o["sampled"], "texture() calls,", o["discarded"], "alpha discards",
+              f"{time.time() - t:.0f}s", flush=True)
+        if "--textured-pipeline-only" in sys.argv:
+            sys.exit(0)
     if "--pipeline-only" in sys.argv or len(sys.argv) == 1:
         t = time.time()
         for mode, name in ((None, "spirv_pipeline_soup260_L6.npz"), (oracle.CONSERVATIVE_DILATE, "spirv_pipeline_soup260_L6_modeB.npz")):

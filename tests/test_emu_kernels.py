@@ -100,6 +100,11 @@ def test_whole_path_against_reference_shaders_end_to_end(emu, which):
     cuda_whole_path_like_reference(emu, which)
 
 
+def test_textured_path_against_reference_shaders_end_to_end(emu):
+    from tests.test_spirv_golden import cuda_textured_path_like_reference
+    cuda_textured_path_like_reference(emu)
+
+
 def test_empty_scene(emu):
     m = scenes.Mesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), np.zeros(0, scenes.DRAW_DTYPE), "empty")
     info = check_against_oracle(emu, m, 4, api.CENTER)

@@ -199,6 +199,51 @@ def cuda_whole_path_like_reference(lib, which="modeA"):
     assert check_hits_against_tracer_golden(g, hits["hit"] != 0, hits["pos"], hits["colour"], hits["normal"], hits["iter"]) > 40
 
 
+TEXTURED_PIPELINE = os.path.join(HERE, "golden", "spirv_pipeline_texsoup160_L6.npz")
+
+
+def textured_pipeline_mesh():
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_spirv_golden
+    return make_spirv_golden.textured_pipeline_mesh()
+
+
+def test_oracle_textured_path_equals_reference_shaders_end_to_end():
+    """Textured and alpha-tested materials through voxelizer.geom / voxelizer.frag / the builder shaders (the texture
+    unit's value injected from the pinned sampler): same fragment list in the same order, same node buffer."""
+    g = np.load(TEXTURED_PIPELINE)
+    assert int(g["discarded"]) > 20 and int(g["sampled"]) > 500
+    mesh = textured_pipeline_mesh()
+    level = int(g["level"])
+    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, level, int(g["mode"]), texcoords=mesh.texcoords,
+                         texset=oracle.TexSet(mesh.textures))
+    packed = np.array([oracle.pack_fragment(int(f["x"]), int(f["y"]), int(f["z"]), int(f["rgb"])) for f in fr], np.uint32)
+    assert packed.shape == g["packed"].shape and (packed == g["packed"]).all()
+    words, rng = oracle.build_octree(fr, level)
+    assert rng == int(g["range_bytes"]) and (words == g["words"]).all()
+
+
+def cuda_textured_path_like_reference(lib):
+    from tests.parity import assert_same_tree
+    g = np.load(TEXTURED_PIPELINE)
+    mesh = textured_pipeline_mesh()
+    level = int(g["level"])
+    scene = api.Scene.Create(mesh, lib=lib)
+    vox = api.Voxelizer.Create(scene, level, int(g["mode"]))
+    builder = api.OctreeBuilder.Create(vox)
+    vox.CmdVoxelize()
+    assert (vox.reference_fragments_to_host() == g["packed"]).all(), "textured fragment list differs (order included)"
+    builder.CmdBuild()
+    assert builder.GetOctreeRange() == int(g["range_bytes"])
+    assert_same_tree(builder.octree_to_host(), g["words"], level)
+
+
+@pytest.mark.gpu
+def test_cuda_textured_path_equals_reference_shaders_end_to_end():
+    cuda_textured_path_like_reference(api.get_library())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", sorted(PIPELINES))
 def test_cuda_whole_path_equals_reference_shaders_end_to_end(which):
