@@ -319,6 +319,12 @@ public:
 	const uint32_t *GetBuffer() const { return m_buffer; }
 	uint32_t GetLevel() const { return m_level; }
 	uint64_t GetRange() const { return m_range; }
+	// What OctreeTracer does with the buffer, for checks without Vulkan: Octree_RayMarchLeaf (shader/octree.glsl:179-340)
+	// over n rays; origins / dirs (3 floats per ray) and hits are DEVICE pointers.
+	int RayMarchLeaf(uint64_t n_rays, const float *d_origins, const float *d_dirs, svo_ray_hit *d_hits, int device = 0,
+	                 Stream stream = nullptr) const {
+		return svo_octree_raymarch_leaf(device, m_buffer, n_rays, d_origins, d_dirs, d_hits, stream);
+	}
 };
 
 } // namespace svo_host
