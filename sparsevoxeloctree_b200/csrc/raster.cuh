@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	row_span_depth_window(lt.ts, rp.res, py, x_lo, x_hi);
 	uint64_t o = rows.off[r];
 	for (int32_t px = x_lo; px <= x_hi; ++px) {
-		uint32_t rgb, uz;
+		uint32_t rgb, uz = 0;
 		if (!sample_colour(tv, luv[li], px, py, rgb)) continue;
 		pixel_fragment(lt.ts, rp.res, px, py, uz); // inside the depth window by construction of the span
 		frags[o++] = make_fragment_lut(lt.ts, rp, s_lut, px, py, uz, rgb);
