@@ -107,7 +107,11 @@ SVO_API uint64_t svo_launch_count(void); /* kernels launched by this library sin
  * Replaces the GPU-buffer half of Scene::Create / load_buffers_and_draw_cmd
  * (src/Scene.cpp:145-223,387-417): uploads (or borrows) vertex/index buffers and keeps the draw
  * list.  Host pointers may be released when the call returns if they are pageable; pinned host
- * memory must stay valid until the stream has run the copy. */
+ * memory must stay valid until the stream has run the copy.
+ * Positions must be normalised to [-1,1]^3 (what src/Scene.cpp:90-99 guarantees): a triangle with a non-finite
+ * vertex or a coordinate beyond +-2 is skipped, not clipped.  Every index must be < n_vertices
+ * (SVO_ERR_INVALID_ARGUMENT otherwise; checked on the device, so borrowed device buffers are covered too).
+ * svo_*_destroy() release device memory stream-ordered on the stream of the handle's last call. */
 SVO_API int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene **out);
 SVO_API void svo_scene_destroy(svo_scene *scene);
 SVO_API uint64_t svo_scene_triangle_count(const svo_scene *scene);
@@ -143,7 +147,11 @@ SVO_API uint32_t svo_voxelizer_resolution(const svo_voxelizer *vox);       /* Vo
 SVO_API uint64_t svo_voxelizer_fragment_count(const svo_voxelizer *vox);   /* Voxelizer::GetVoxelFragmentCount */
 /* Voxelizer::GetVoxelFragmentList (src/Voxelizer.hpp:52): DEVICE pointer to fragment_count 64-bit
  * fragments, (morton(x,y,z) << 24) | rgb, morton slot order x | y<<1 | z<<2 per level
- * (shader/octree_tag_node.comp:24-25), in triangle order. */
+ * (shader/octree_tag_node.comp:24-25), in triangle order.
+ * The list is valid between svo_voxelizer_voxelize() and the next svo_builder_build()/prepare() on this voxelizer:
+ * the build CONSUMES it (sorts it in place and reuses the storage), unlike the reference's CmdBuild, which only reads
+ * it.  After a build, svo_voxelizer_export_reference_fragments() and a second build return SVO_ERR_NOT_READY until
+ * svo_voxelizer_voxelize() has run again. */
 SVO_API const uint64_t *svo_voxelizer_fragments(const svo_voxelizer *vox);
 /* The reference's own fragment packing (shader/voxelizer.frag:40-42, uvec2 per fragment, levels
  * <= 12): converts the fragment list into d_out (DEVICE, fragment_count * 8 bytes) on the stream. */

@@ -59,6 +59,18 @@ struct RasterParams {
 	uint32_t origin[3]; // sb.lo: fragments are emitted in shard-local coordinates
 };
 
+// largest vertex index of the mesh (svo_scene_create validates it against the vertex count)
+__global__ void __launch_bounds__(256) k_max_index(const uint32_t *__restrict__ idx, uint64_t n, uint32_t *__restrict__ out) {
+	uint32_t m = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) m = idx[i] > m ? idx[i] : m;
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const uint32_t o = __shfl_xor_sync(FULL_MASK, m, d);
+		m = o > m ? o : m;
+	}
+	if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 SVO_DEV uint32_t find_draw(const SceneView &sv, uint64_t t) {
 	uint32_t lo = 0, hi = sv.n_draws; // last draw with tri_base <= t
 	while (hi - lo > 1) {
@@ -158,19 +170,18 @@ struct SmallWalk {
 
 // ---- pass 1: classify + count small ------------------------------------------------------------------
 // cnt_small[t]  = fragments of a small triangle (0 for large / culled)
-// packed[t]     = (is_large << 40) | rows of a large triangle
+// rows[t]       = candidate rows of a large triangle (>= 1), 0 for small / culled ones
 // Triangles of an alpha-tested texture produce a fragment only where the sample passes the alpha test
 // (voxelizer.frag:29-30 discards before the counter): small ones sample while they count; large ones get their rows
 // counted by sampling (k_large_rows) and emitted by k_emit_alpha_rows instead of the span arithmetic.
 template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
-    k_classify_count(SceneView sv, RasterParams rp, uint32_t *__restrict__ cnt_small, uint64_t *__restrict__ packed) {
+    k_classify_count(SceneView sv, RasterParams rp, uint32_t *__restrict__ cnt_small, uint32_t *__restrict__ rows) {
 	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
 	if (t >= sv.n_tri) return;
 	TriSetup ts;
 	TriShade sh;
-	uint32_t cnt = 0;
-	uint64_t pk = 0;
+	uint32_t cnt = 0, pk = 0;
 	if (load_and_setup<TEX>(sv, rp, t, ts, sh)) {
 		if (ts.full_area <= SMALL_AREA) {
 			SmallWalk wk;
@@ -182,10 +193,10 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 				wk.step(ts);
 			}
 		} else
-			pk = (1ull << 40) | (uint64_t)(ts.py1 - ts.py0 + 1);
+			pk = (uint32_t)(ts.py1 - ts.py0 + 1);
 	}
 	cnt_small[t] = cnt;
-	packed[t] = pk;
+	rows[t] = pk;
 }
 
 // ---- pass 1b: large triangles ---------------------------------------------------------------------------
@@ -199,23 +210,22 @@ struct LargeTri {
 
 // gather the large triangles into a dense list (order = triangle order)
 __global__ void __launch_bounds__(RASTER_BLOCK)
-    k_large_collect(uint64_t n_tri, const uint64_t *__restrict__ packed, const uint64_t *__restrict__ lprefix,
-                    LargeTri *__restrict__ large) {
+    k_large_collect(uint64_t n_tri, const uint32_t *__restrict__ rows, const uint64_t *__restrict__ large_index /* scan of rows != 0 */,
+                    const uint64_t *__restrict__ row_prefix /* scan of rows */, LargeTri *__restrict__ large) {
 	const uint64_t t = (uint64_t)blockIdx.x * RASTER_BLOCK + threadIdx.x;
 	if (t >= n_tri) return;
-	if (packed[t] >> 40) {
-		const uint64_t p = lprefix[t];
-		LargeTri &lt = large[p >> 40];
+	if (rows[t]) {
+		LargeTri &lt = large[large_index[t]];
 		lt.tri = (uint32_t)t;
-		lt.row_base = (uint32_t)(p & ((1ull << 40) - 1));
+		lt.row_base = (uint32_t)row_prefix[t]; // the host checks that all rows together stay below 2^32
 	}
 }
 
-// one warp per large triangle: exact row spans.  row_pk[r] = (nonempty << 40) | len ; row_x0[r] = first pixel
+// one warp per large triangle: exact row spans.  row_len[r] = fragments of the row (0: empty) ; row_x0[r] = first pixel
 template <bool TEX>
 __global__ void __launch_bounds__(RASTER_BLOCK)
     k_large_rows(SceneView sv, RasterParams rp, uint32_t n_large, LargeTri *__restrict__ large, UvMap *__restrict__ luv,
-                 uint64_t *__restrict__ row_pk, uint32_t *__restrict__ row_x0) {
+                 uint32_t *__restrict__ row_len, uint32_t *__restrict__ row_x0) {
 	// a triangle's rows are shared out in chunks of LARGE_ROW_CHUNK among gridDim.y warps (a wall has 4096 rows)
 	const uint32_t li = (blockIdx.x * RASTER_BLOCK + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 			uint32_t c;
 			for (int32_t px = x_lo; px <= x_hi; ++px) len += sample_colour(sv.tex, sh.um, px, ts.py0 + r, c) ? 1u : 0u;
 		}
-		row_pk[lt.row_base + r] = len ? ((1ull << 40) | len) : 0ull;
+		row_len[lt.row_base + r] = len;
 		row_x0[lt.row_base + r] = (uint32_t)x_lo;
 	}
 }
@@ -254,9 +264,9 @@ struct DenseRows {
 	uint32_t *li;
 };
 __global__ void __launch_bounds__(RASTER_BLOCK)
-    k_rows_compact(uint32_t n_large, const LargeTri *__restrict__ large, const uint64_t *__restrict__ row_pk,
-                   const uint32_t *__restrict__ row_x0, const uint64_t *__restrict__ rprefix, uint64_t n_rows_sparse,
-                   DenseRows out) {
+    k_rows_compact(uint32_t n_large, const LargeTri *__restrict__ large, const uint32_t *__restrict__ row_len,
+                   const uint32_t *__restrict__ row_x0, const uint64_t *__restrict__ dense_index /* scan of row_len != 0 */,
+                   const uint64_t *__restrict__ frag_prefix /* scan of row_len */, uint64_t n_rows_sparse, DenseRows out) {
 	// one warp per large triangle again, so that a row knows its triangle without a search
 	const uint32_t li = (blockIdx.x * RASTER_BLOCK + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
@@ -266,17 +276,15 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	for (int32_t c = (int32_t)blockIdx.y * LARGE_ROW_CHUNK; c < h; c += (int32_t)gridDim.y * LARGE_ROW_CHUNK)
 	for (int32_t r = c + lane; r < h && r < c + LARGE_ROW_CHUNK; r += 32) {
 		const uint64_t s = (uint64_t)lt.row_base + r;
-		if (row_pk[s] >> 40) {
-			const uint64_t p = rprefix[s];
-			const uint32_t k = (uint32_t)(p >> 40);
-			out.off[k] = (uint32_t)(p & ((1ull << 40) - 1));
+		if (row_len[s]) {
+			const uint32_t k = (uint32_t)dense_index[s];
+			out.off[k] = (uint32_t)frag_prefix[s];
 			out.xy[k] = row_x0[s] | ((uint32_t)(lt.ts.py0 + r) << 16);
 			out.li[k] = li;
 		}
 	}
 	if (li == 0 && lane == 0 && blockIdx.y == 0) {
-		const uint64_t tot = rprefix[n_rows_sparse];
-		out.off[tot >> 40] = (uint32_t)(tot & ((1ull << 40) - 1));
+		out.off[dense_index[n_rows_sparse]] = (uint32_t)frag_prefix[n_rows_sparse];
 	}
 }
 

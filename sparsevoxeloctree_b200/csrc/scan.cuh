@@ -102,9 +102,11 @@ SVO_DEV uint32_t take_ticket(uint32_t *counter, uint32_t *s_ticket) {
 // ---- device-wide exclusive scan of uint32 -> uint64 offsets ------------------------------------------
 constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
 
-// out[i] = sum_{j<i} in[j] (64-bit), out[n] = total.  state: tiles+1 words zeroed; ticket zeroed.
-// InT = uint32_t (counts) or uint64_t (two counters packed as hi << 40 | lo, scanned together).
-template <class InT>
+// out[i] = sum_{j<i} f(in[j]) (64-bit), out[n] = total.  state: tiles+1 words zeroed; ticket zeroed.
+// NONZERO = false: f(v) = v; NONZERO = true: f(v) = (v != 0), i.e. the scan numbers the non-zero entries.
+// (Two counters are never packed into one scanned word: the look-back keeps 62 value bits per tile, so a packed
+// count << 40 | sum silently wrapped at 2^22 counted entries.)
+template <class InT, bool NONZERO>
 __global__ void __launch_bounds__(SCAN_BLOCK)
     k_exclusive_scan(const InT *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket) {
 	__shared__ uint64_t s_warp[SCAN_BLOCK / 32 + 1];
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; ++i) {
 		v[i] = base + i < n ? in[base + i] : InT(0);
+		if (NONZERO) v[i] = v[i] != InT(0) ? InT(1) : InT(0);
 		sum += v[i];
 	}
 	uint64_t total;
@@ -143,13 +146,14 @@ struct ScanScratch {
 };
 
 // host wrapper; temp storage is grown on demand and reused
-template <class InT> inline int exclusive_scan(const InT *in, uint64_t *out, uint64_t n, ScanScratch &sc, cudaStream_t s) {
+template <class InT, bool NONZERO = false>
+inline int exclusive_scan(const InT *in, uint64_t *out, uint64_t n, ScanScratch &sc, cudaStream_t s) {
 	const uint32_t tiles = n ? div_up(n, SCAN_TILE) : 1;
 	SVO_TRY(sc.state.reserve(tiles + 1, s));
 	SVO_TRY(sc.ticket.reserve(1, s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (tiles + 1) * sizeof(uint64_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, sizeof(uint32_t), s));
-	auto k = k_exclusive_scan<InT>;
+	auto k = k_exclusive_scan<InT, NONZERO>;
 	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	return 0;

@@ -92,6 +92,7 @@ using namespace svo;
 
 struct svo_scene {
 	int device = 0;
+	cudaStream_t last_stream = nullptr; // stream of the last call that enqueued work: destroy frees on it
 	SceneView view{};
 	std::vector<DrawRec> draws;
 	DevBuf<unsigned char> pos;
@@ -111,6 +112,7 @@ struct svo_scene {
 struct svo_voxelizer {
 	svo_scene *scene = nullptr;
 	int device = 0;
+	cudaStream_t last_stream = nullptr;
 	uint32_t level = 0;       // full-grid level
 	uint32_t key_level = 0;   // level of the emitted (shard-local) keys
 	RasterParams rp{};
@@ -129,6 +131,7 @@ struct svo_voxelizer {
 struct svo_builder {
 	svo_voxelizer *vox = nullptr;
 	int device = 0;
+	cudaStream_t last_stream = nullptr;
 	uint32_t level = 0;
 	DevBuf<uint64_t> tmp;      // sort ping-pong partner of the fragment list
 	DevBuf<uint32_t> leaf;     // leaf words
@@ -264,6 +267,7 @@ int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene *
 	svo_scene *sc = new (std::nothrow) svo_scene();
 	if (!sc) return fail(SVO_ERR_CUDA, "out of host memory");
 	sc->device = device;
+	sc->last_stream = s;
 	sc->n_vertices = mesh->n_vertices;
 	uint64_t tri_base = 0;
 	for (uint32_t d = 0; d < mesh->n_draws; ++d) {
@@ -316,6 +320,16 @@ int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene *
 		}
 		if (sc->textured && (rc = upload_textures(sc, mesh, s))) break;
 		if ((rc = sc->d_draws.alloc(sc->draws.size(), s))) break;
+		// every index must address a vertex (a malformed mesh would make the raster kernels read out of bounds)
+		DevBuf<uint32_t> max_index;
+		uint32_t h_max = 0;
+		if (mesh->n_indices) {
+			if ((rc = max_index.alloc(1, s))) break;
+			if (cudaMemsetAsync(max_index.p, 0, sizeof(uint32_t), s) != cudaSuccess) rc = SVO_ERR_CUDA;
+			SVO_LAUNCH(std::min<uint32_t>(div_up(mesh->n_indices, 256 * 8), 1184u), 256, 0, s, k_max_index, sc->view.idx, mesh->n_indices,
+			           max_index.p);
+			if (cudaMemcpyAsync(&h_max, max_index.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = SVO_ERR_CUDA;
+		}
 		if (!sc->draws.empty() && cudaMemcpyAsync(sc->d_draws.p, sc->draws.data(), sc->draws.size() * sizeof(DrawRec),
 		                                          cudaMemcpyHostToDevice, s) != cudaSuccess) {
 			rc = fail(SVO_ERR_CUDA, "svo_scene_create: draw list copy failed");
@@ -323,6 +337,9 @@ int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene *
 		}
 		// the draw list is staged from a host vector owned by the scene: make the copy complete before returning
 		if (cudaStreamSynchronize(s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "svo_scene_create: stream sync failed");
+		max_index.release(s);
+		if (!rc && mesh->n_indices && h_max >= mesh->n_vertices)
+			rc = fail(SVO_ERR_INVALID_ARGUMENT, "svo_scene_create: an index is >= n_vertices");
 	} while (0);
 	if (rc) {
 		svo_scene_destroy(sc);
@@ -339,11 +356,12 @@ int svo_scene_create(const svo_mesh *mesh, int device, void *stream, svo_scene *
 void svo_scene_destroy(svo_scene *sc) {
 	if (!sc) return;
 	DeviceGuard guard(sc->device);
-	sc->pos.release(0);
-	sc->idx.release(0);
-	sc->d_draws.release(0);
-	sc->uv.release(0), sc->texels.release(0), sc->tex_desc.release(0), sc->tex_decode.release(0), sc->tex_enc.release(0);
-	sc->tex_lod.release(0);
+	const cudaStream_t s = sc->last_stream; // stream-ordered frees: after the work that may still read the buffers
+	sc->pos.release(s);
+	sc->idx.release(s);
+	sc->d_draws.release(s);
+	sc->uv.release(s), sc->texels.release(s), sc->tex_desc.release(s), sc->tex_decode.release(s), sc->tex_enc.release(s);
+	sc->tex_lod.release(s);
 	delete sc;
 }
 uint64_t svo_scene_triangle_count(const svo_scene *sc) { return sc ? sc->view.n_tri : 0; }
@@ -392,6 +410,8 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 	if (!v) return fail(SVO_ERR_CUDA, "out of host memory");
 	v->scene = scene;
 	v->device = scene->device;
+	v->last_stream = s;
+	scene->last_stream = s;
 	v->level = level;
 	v->key_level = key_level;
 	v->rp.res = 1u << level;
@@ -413,8 +433,8 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 
 	// ---- the count pass (Voxelizer::count_and_create_fragment_list, src/Voxelizer.cpp:134-165) ----
 	const uint64_t T = scene->view.n_tri;
-	DevBuf<uint32_t> cnt_small, row_x0;
-	DevBuf<uint64_t> packed, lprefix, row_pk, rprefix;
+	DevBuf<uint32_t> cnt_small, rows, row_len, row_x0;
+	DevBuf<uint64_t> large_index, row_prefix, dense_index, frag_prefix;
 	ScanScratch ss;
 	int rc = 0;
 	do {
@@ -424,60 +444,69 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 			if (cudaMemsetAsync(v->tri_off.p, 0, sizeof(uint64_t), s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "memset failed");
 			break;
 		}
-		if ((rc = cnt_small.alloc(T, s)) || (rc = packed.alloc(T, s)) || (rc = lprefix.alloc(T + 1, s))) break;
+		if ((rc = cnt_small.alloc(T, s)) || (rc = rows.alloc(T, s)) || (rc = large_index.alloc(T + 1, s)) || (rc = row_prefix.alloc(T + 1, s)))
+			break;
 		const uint32_t tgrid = div_up(T, RASTER_BLOCK);
 		if (scene->textured)
-			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count<true>, scene->view, v->rp, cnt_small.p, packed.p);
+			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count<true>, scene->view, v->rp, cnt_small.p, rows.p);
 		else
-			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count<false>, scene->view, v->rp, cnt_small.p, packed.p);
+			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_classify_count<false>, scene->view, v->rp, cnt_small.p, rows.p);
 		if ((rc = exclusive_scan((const uint32_t *)cnt_small.p, v->tri_off.p, T, ss, s))) break;
-		// (is_large << 40 | rows) scanned as one 64-bit word: large-triangle index and first row together
-		if ((rc = exclusive_scan((const uint64_t *)packed.p, lprefix.p, T, ss, s))) break;
-		uint64_t h_small = 0, h_lp = 0;
+		// large-triangle index and first row of every large triangle: two scans of rows[] (entries != 0, and the values)
+		if ((rc = exclusive_scan<uint32_t, true>((const uint32_t *)rows.p, large_index.p, T, ss, s))) break;
+		if ((rc = exclusive_scan((const uint32_t *)rows.p, row_prefix.p, T, ss, s))) break;
+		uint64_t h_small = 0, h_nlarge = 0, rows_sparse = 0;
 		if (cudaMemcpyAsync(&h_small, v->tri_off.p + T, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-		    cudaMemcpyAsync(&h_lp, lprefix.p + T, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+		    cudaMemcpyAsync(&h_nlarge, large_index.p + T, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+		    cudaMemcpyAsync(&rows_sparse, row_prefix.p + T, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
 		    cudaStreamSynchronize(s) != cudaSuccess) {
 			rc = fail(SVO_ERR_CUDA, "count pass failed");
 			set_error("count pass failed: %s", cudaGetErrorString(cudaGetLastError()));
 			break;
 		}
 		v->n_frag_small = h_small;
-		v->n_large = (uint32_t)(h_lp >> 40);
-		const uint64_t rows_sparse = h_lp & ((1ull << 40) - 1);
+		v->n_large = (uint32_t)h_nlarge;
 		if (v->n_large) {
 			if (rows_sparse >= (1ull << 32)) {
 				rc = fail(SVO_ERR_CAPACITY, "too many rows");
 				break;
 			}
-			if ((rc = v->large.alloc(v->n_large, s)) || (rc = row_pk.alloc(rows_sparse, s)) || (rc = row_x0.alloc(rows_sparse, s)) ||
-			    (rc = rprefix.alloc(rows_sparse + 1, s)))
+			if ((rc = v->large.alloc(v->n_large, s)) || (rc = row_len.alloc(rows_sparse, s)) || (rc = row_x0.alloc(rows_sparse, s)) ||
+			    (rc = dense_index.alloc(rows_sparse + 1, s)) || (rc = frag_prefix.alloc(rows_sparse + 1, s)))
 				break;
-			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_large_collect, T, (const uint64_t *)packed.p, (const uint64_t *)lprefix.p, v->large.p);
+			SVO_LAUNCH_INDEP(tgrid, RASTER_BLOCK, s, k_large_collect, T, (const uint32_t *)rows.p, (const uint64_t *)large_index.p,
+			                 (const uint64_t *)row_prefix.p, v->large.p);
 			const uint32_t wgrid = div_up((uint64_t)v->n_large * 32, RASTER_BLOCK);
 			// few large triangles with thousands of rows each: spread a triangle's rows over up to 16 warps
 			const dim3 wgrid2(wgrid, v->n_large < 65536u ? std::min(16u, div_up((uint64_t)(1u << level), LARGE_ROW_CHUNK)) : 1u);
 			if (scene->textured) {
 				if ((rc = v->large_uv.alloc(v->n_large, s))) break;
 				SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_large_rows<true>, scene->view, v->rp, v->n_large, v->large.p, v->large_uv.p,
-				                 row_pk.p, row_x0.p);
+				                 row_len.p, row_x0.p);
 			} else
 				SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_large_rows<false>, scene->view, v->rp, v->n_large, v->large.p, (UvMap *)nullptr,
-				                 row_pk.p, row_x0.p);
-			if ((rc = exclusive_scan((const uint64_t *)row_pk.p, rprefix.p, rows_sparse, ss, s))) break;
-			uint64_t h_rp = 0;
-			if (cudaMemcpyAsync(&h_rp, rprefix.p + rows_sparse, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+				                 row_len.p, row_x0.p);
+			if ((rc = exclusive_scan<uint32_t, true>((const uint32_t *)row_len.p, dense_index.p, rows_sparse, ss, s))) break;
+			if ((rc = exclusive_scan((const uint32_t *)row_len.p, frag_prefix.p, rows_sparse, ss, s))) break;
+			uint64_t h_rows = 0, h_frag = 0;
+			if (cudaMemcpyAsync(&h_rows, dense_index.p + rows_sparse, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+			    cudaMemcpyAsync(&h_frag, frag_prefix.p + rows_sparse, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
 			    cudaStreamSynchronize(s) != cudaSuccess) {
 				rc = fail(SVO_ERR_CUDA, "row pass failed");
 				break;
 			}
-			v->n_rows = (uint32_t)(h_rp >> 40);
-			v->n_frag_large = h_rp & ((1ull << 40) - 1);
+			v->n_rows = (uint32_t)h_rows;
+			v->n_frag_large = h_frag;
+			if (h_frag >= 0xffffffffull) {
+				rc = fail(SVO_ERR_CAPACITY, "more than 2^32-2 fragments (the reference's counter is 32-bit too)");
+				break;
+			}
 			if ((rc = v->row_off.alloc((uint64_t)v->n_rows + 1, s)) || (rc = v->row_xy.alloc(v->n_rows, s)) ||
 			    (rc = v->row_li.alloc(v->n_rows, s)))
 				break;
 			DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
-			SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_rows_compact, v->n_large, (const LargeTri *)v->large.p, (const uint64_t *)row_pk.p,
-			                 (const uint32_t *)row_x0.p, (const uint64_t *)rprefix.p, rows_sparse, dr);
+			SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_rows_compact, v->n_large, (const LargeTri *)v->large.p, (const uint32_t *)row_len.p,
+			                 (const uint32_t *)row_x0.p, (const uint64_t *)dense_index.p, (const uint64_t *)frag_prefix.p, rows_sparse, dr);
 		}
 		v->n_frag = v->n_frag_small + v->n_frag_large;
 		if (v->n_frag >= 0xffffffffull) {
@@ -487,7 +516,8 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 	} while (0);
 	if (!rc) rc = v->frags.alloc(v->n_frag, s);
 	if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(SVO_ERR_CUDA, "voxelizer count pass: kernel launch failed");
-	cnt_small.release(s), row_x0.release(s), packed.release(s), lprefix.release(s), row_pk.release(s), rprefix.release(s);
+	cnt_small.release(s), rows.release(s), row_len.release(s), row_x0.release(s);
+	large_index.release(s), row_prefix.release(s), dense_index.release(s), frag_prefix.release(s);
 	ss.state.release(s), ss.ticket.release(s);
 	if (rc) {
 		svo_voxelizer_destroy(v);
@@ -510,6 +540,7 @@ int svo_voxelizer_create_from_fragments(int device, uint32_t level, const uint64
 	svo_voxelizer *v = new (std::nothrow) svo_voxelizer();
 	if (!v) return fail(SVO_ERR_CUDA, "out of host memory");
 	v->device = device;
+	v->last_stream = s;
 	v->level = v->key_level = level;
 	v->n_frag = n;
 	int rc = v->t_raster.init();
@@ -530,9 +561,10 @@ int svo_voxelizer_create_from_fragments(int device, uint32_t level, const uint64
 void svo_voxelizer_destroy(svo_voxelizer *v) {
 	if (!v) return;
 	DeviceGuard guard(v->device);
-	v->large_uv.release(0);
-	v->tri_off.release(0), v->large.release(0), v->row_off.release(0), v->row_xy.release(0), v->row_li.release(0), v->frags.release(0);
-	v->ext_frags.release(0);
+	const cudaStream_t s = v->last_stream;
+	v->large_uv.release(s);
+	v->tri_off.release(s), v->large.release(s), v->row_off.release(s), v->row_xy.release(s), v->row_li.release(s), v->frags.release(s);
+	v->ext_frags.release(s);
 	v->t_raster.destroy();
 	delete v;
 }
@@ -541,6 +573,8 @@ int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
 	if (!v) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelizer_voxelize: null handle");
 	DeviceGuard guard(v->device);
 	cudaStream_t s = (cudaStream_t)stream;
+	v->last_stream = s;
+	if (v->scene) v->scene->last_stream = s;
 	if (!v->scene) { // fragment list supplied by the caller: restore it (the builder sorts the list in place)
 		SVO_CUDA_TRY(cudaEventRecord(v->t_raster.a, s));
 		if (v->n_frag) SVO_CUDA_TRY(cudaMemcpyAsync(v->frags.p, v->ext_frags.p, v->n_frag * 8, cudaMemcpyDeviceToDevice, s));
@@ -617,6 +651,7 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 	if (!b) return fail(SVO_ERR_CUDA, "out of host memory");
 	b->vox = vox;
 	b->device = vox->device;
+	b->last_stream = s;
 	b->level = vox->key_level;
 	int rc = 0;
 	do {
@@ -646,11 +681,12 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 void svo_builder_destroy(svo_builder *b) {
 	if (!b) return;
 	DeviceGuard guard(b->device);
-	b->tmp.release(0), b->leaf.release(0), b->first.release(0), b->slot.release(0), b->counts.release(0), b->lb_state.release(0);
-	b->tickets.release(0), b->octree.release(0), b->root_scratch.release(0);
-	b->sort_scratch.hist.release(0), b->sort_scratch.state.release(0);
-	b->scan_scratch.state.release(0), b->scan_scratch.ticket.release(0);
-	b->rf_cnt01.release(0), b->rf_cnt2.release(0), b->rf_pre01.release(0), b->rf_pre2.release(0);
+	const cudaStream_t s = b->last_stream;
+	b->tmp.release(s), b->leaf.release(s), b->first.release(s), b->slot.release(s), b->counts.release(s), b->lb_state.release(s);
+	b->tickets.release(s), b->octree.release(s), b->root_scratch.release(s);
+	b->sort_scratch.hist.release(s), b->sort_scratch.state.release(s);
+	b->scan_scratch.state.release(s), b->scan_scratch.ticket.release(s);
+	b->rf_cnt01.release(s), b->rf_cnt2.release(s), b->rf_pre01.release(s), b->rf_pre2.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
 	delete b;
@@ -662,10 +698,14 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	if (!v->voxelized) return fail(SVO_ERR_NOT_READY, "svo_builder_build: voxelize first");
 	DeviceGuard guard(b->device);
 	cudaStream_t s = (cudaStream_t)stream;
+	b->last_stream = v->last_stream = s;
 	const uint64_t F = v->n_frag;
 	const uint32_t L = b->level;
 	const int n_sm = sm_count(b->device);
 	b->built = b->prepared = b->emitted = false;
+	// The build consumes the fragment list: it is sorted in place and the two fragment-sized buffers then serve as key
+	// ping-pong buffers for the upper levels.  A second build (or a fragment export) needs a new CmdVoxelize first.
+	v->voxelized = false;
 
 	// ---- sort by Morton code (stable) ----
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
@@ -790,6 +830,7 @@ int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_w
 	if ((uint64_t)pointer_bias_words + b->range_bytes / 4 >= (1ull << 30))
 		return fail(SVO_ERR_CAPACITY, "biased child pointers would exceed 30 bits (octree.glsl:110)");
 	DeviceGuard guard(b->device);
+	b->last_stream = (cudaStream_t)stream;
 	SVO_TRY(emit_into(b, d_dst, pointer_bias_words, skip_root, (cudaStream_t)stream));
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], (cudaStream_t)stream)); // svo_builder_last_ms covers prepare + emit_to as well
 	b->emitted = true;

@@ -110,14 +110,15 @@ inline void fail(const char *msg) {
 }
 
 template <class F> void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, F fn) {
-	if (block.y != 1 || block.z != 1 || grid.y != 1 || grid.z != 1) fail("only 1-D launches are emulated");
+	if (block.y != 1 || block.z != 1 || grid.z != 1) fail("only 1-D blocks and 1-D / 2-D grids are emulated");
 	std::vector<unsigned char> dyn(smem + 16);
+	for (unsigned by = 0; by < grid.y; ++by)
 	for (unsigned b = 0; b < grid.x; ++b) {
 		memset(dyn.data(), 0xCD, dyn.size());
 		if (!cooperative) {
 			for (unsigned t = 0; t < block.x; ++t) {
 				tctx = ThreadCtx();
-				tctx.threadIdx = {t, 0, 0}, tctx.blockIdx = {b, 0, 0};
+				tctx.threadIdx = {t, 0, 0}, tctx.blockIdx = {b, by, 0};
 				tctx.blockDim = block, tctx.gridDim = grid;
 				tctx.dyn_smem = dyn.data();
 				tctx.lane = t % 32;
@@ -139,7 +140,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem, bool cooperat
 		for (unsigned t = 0; t < block.x; ++t) {
 			th.emplace_back([&, t]() {
 				tctx = ThreadCtx();
-				tctx.threadIdx = {t, 0, 0}, tctx.blockIdx = {b, 0, 0};
+				tctx.threadIdx = {t, 0, 0}, tctx.blockIdx = {b, by, 0};
 				tctx.blockDim = block, tctx.gridDim = grid;
 				tctx.dyn_smem = dyn.data();
 				tctx.blk = &bs, tctx.warp = &bs.warps[t / 32], tctx.lane = t % 32;

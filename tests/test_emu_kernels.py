@@ -109,3 +109,82 @@ def test_empty_scene(emu):
     m = scenes.Mesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), np.zeros(0, scenes.DRAW_DTYPE), "empty")
     info = check_against_oracle(emu, m, 4, api.CENTER)
     assert info["range"] == 32 and info["fragments"] == 0
+
+
+# ---- regression tests for the round-1 advisor findings ------------------------------------------------------
+def _voxelize_only_matches_oracle(lib, mesh, level, mode):
+    from tests.parity import oracle_fragment_keys
+    scene = api.Scene.Create(mesh, lib=lib)
+    vox = api.Voxelizer.Create(scene, level, mode)
+    vox.CmdVoxelize()
+    frags = vox.fragments_to_host()
+    okeys = oracle_fragment_keys(mesh, level, mode)
+    assert len(frags) == len(okeys) == vox.GetVoxelFragmentCount()
+    assert (np.sort(frags) == np.sort(okeys)).all()
+    vox.Destroy(), scene.Destroy()
+    return len(frags)
+
+
+def test_large_triangles_level8_two_dimensional_row_grid(emu):
+    """Large triangles at level >= 8 launch k_large_rows / k_rows_compact with gridDim.y > 1 (rows of a triangle
+    shared out in chunks among several warps): the blockIdx.y chunking against the oracle."""
+    rng = np.random.default_rng(21)
+    big = rng.uniform(-0.9, 0.9, (3, 3, 3))
+    pos = big.reshape(-1, 3).astype(np.float32)
+    idx = np.arange(len(pos), dtype=np.uint32)
+    draws = np.array([(0, len(idx), 0xFFFFFFFF, 0x00306090)], scenes.DRAW_DTYPE)
+    n = _voxelize_only_matches_oracle(emu, scenes.Mesh(pos, idx, draws, "big8"), 8, api.CONSERVATIVE_EXACT)
+    assert n > 20_000
+
+
+def test_more_than_2pow22_large_triangle_rows(emu):
+    """The large-triangle row table used to be numbered by a scan of (count << 40 | sum) words whose look-back keeps
+    62 bits, so the count wrapped at 2^22 rows.  ~100k thin large-class triangles of 49 rows each (4.9M rows)."""
+    level, res = 12, 4096
+    nx, ny, planes = 600, 83, 2
+    gx, gy, gz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(planes), indexing="ij")
+    x0 = (gx.ravel() * 6.5 + 20.25)
+    y0 = (gy.ravel() * 49.0 + 10.25)
+    z = (gz.ravel() * 700.0 + 1000.3)
+    def ndc(p):
+        return p / res * 2.0 - 1.0
+    v0 = np.stack([ndc(x0), ndc(y0), ndc(z)], 1)
+    v1 = np.stack([ndc(x0 + 5.4), ndc(y0 + 48.4), ndc(z)], 1)
+    v2 = np.stack([ndc(x0 + 1.3), ndc(y0 + 0.2), ndc(z + 0.4)], 1)
+    pos = np.stack([v0, v1, v2], 1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(len(pos), dtype=np.uint32)
+    draws = np.array([(0, len(idx), 0xFFFFFFFF, 0x00112233)], scenes.DRAW_DTYPE)
+    mesh = scenes.Mesh(pos, idx, draws, "slivers")
+    assert len(idx) // 3 * 49 > (1 << 22)
+    n = _voxelize_only_matches_oracle(emu, mesh, level, api.CENTER)
+    assert n > 1_000_000
+
+
+def test_build_consumes_the_fragment_list(emu):
+    """svo_builder_build sorts the fragment list in place: a second build or a fragment export without a new
+    CmdVoxelize must fail with SVO_ERR_NOT_READY instead of building a wrong tree."""
+    mesh = scenes.random_soup(250, 7)
+    scene = api.Scene.Create(mesh, lib=emu)
+    vox = api.Voxelizer.Create(scene, 6, api.CONSERVATIVE_EXACT)
+    b = api.OctreeBuilder.Create(vox)
+    vox.CmdVoxelize()
+    b.CmdBuild()
+    first = b.octree_to_host().copy()
+    with pytest.raises(api.SvoError) as e:
+        b.CmdBuild()
+    assert e.value.code == -5  # SVO_ERR_NOT_READY
+    with pytest.raises(api.SvoError):
+        vox.reference_fragments_to_host()
+    vox.CmdVoxelize()
+    b.CmdBuild()
+    assert (b.octree_to_host() == first).all()
+    b.Destroy(), vox.Destroy(), scene.Destroy()
+
+
+def test_index_out_of_range_is_rejected(emu):
+    mesh = scenes.random_soup(20, 3)
+    bad = mesh.indices.copy()
+    bad[7] = len(mesh.positions)
+    with pytest.raises(api.SvoError) as e:
+        api.Scene.Create(mesh.positions, bad, mesh.draws, lib=emu)
+    assert e.value.code == -1  # SVO_ERR_INVALID_ARGUMENT
