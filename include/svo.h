@@ -218,6 +218,11 @@ SVO_API int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t
 /* Test switch: the sort keeps 32-bit look-back words below 2^30 keys and 64-bit ones above; on != 0 forces the
  * 64-bit variant for every size so that the tests reach it without sorting a billion keys. */
 SVO_API void svo_debug_force_wide_sort_state(int on);
+/* Profiling switch: on != 0 makes every sort record a cudaEvent after each of its kernels (histogram, every radix
+ * pass, bucket sort); svo_builder_sort_step_ms then returns the milliseconds between consecutive events of the
+ * builder's last sort (out[0..n), n = return value <= cap; < 0: svo_status).  Off by default: no events, no cost. */
+SVO_API void svo_debug_profile_passes(int on);
+SVO_API int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap);
 
 /* ---- the consumer side, for verification ----------------------------------------------------
  * Octree_RayMarchLeaf (shader/octree.glsl:179-340, the primary-ray traversal octree_tracer.frag:36 runs on the

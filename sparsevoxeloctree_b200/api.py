@@ -91,6 +91,8 @@ SYMBOLS = [
     ("svo_builder_last_ms", C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     ("svo_sort_u64", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P]),
     ("svo_debug_force_wide_sort_state", None, [C.c_int]),
+    ("svo_debug_profile_passes", None, [C.c_int]),
+    ("svo_builder_sort_step_ms", C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
     ("svo_octree_raymarch_leaf", C.c_int, [C.c_int, _P, C.c_uint64, _P, _P, _P, _P]),
     ("svo_device_malloc", C.c_int, [C.c_int, C.c_uint64, C.POINTER(_P)]),
     ("svo_device_free", C.c_int, [C.c_int, _P]),
@@ -447,6 +449,14 @@ class OctreeBuilder:
         np_ = C.c_uint32()
         self.lib.check(self.lib.dll.svo_builder_last_ms(self._h, ms, C.byref(np_)))
         return {k: float(ms[i]) for i, k in enumerate(PHASES)}, int(np_.value)
+
+    def SortStepMs(self):
+        """Milliseconds of each kernel of the last sort (needs svo_debug_profile_passes(1) before the build)."""
+        out = (C.c_float * 32)()
+        n = self.lib.dll.svo_builder_sort_step_ms(self._h, out, 32)
+        if n < 0:
+            self.lib.check(n)
+        return [float(out[i]) for i in range(n)]
 
     def RebaseCopy(self, d_dst: int, dst_word_offset: int, base_words: int, stream=None):
         self.lib.check(self.lib.dll.svo_builder_rebase_copy(self._h, d_dst, dst_word_offset, base_words, _stream_ptr(stream)))

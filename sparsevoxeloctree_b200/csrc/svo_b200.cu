@@ -684,7 +684,7 @@ void svo_builder_destroy(svo_builder *b) {
 	const cudaStream_t s = b->last_stream;
 	b->tmp.release(s), b->leaf.release(s), b->first.release(s), b->slot.release(s), b->counts.release(s), b->lb_state.release(s);
 	b->tickets.release(s), b->octree.release(s), b->root_scratch.release(s);
-	b->sort_scratch.hist.release(s), b->sort_scratch.state.release(s);
+	b->sort_scratch.release(s);
 	b->scan_scratch.state.release(s), b->scan_scratch.ticket.release(s);
 	b->rf_cnt01.release(s), b->rf_cnt2.release(s), b->rf_pre01.release(s), b->rf_pre2.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
@@ -710,7 +710,7 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	// ---- sort by Morton code (stable) ----
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
 	uint64_t *sorted = v->frags.p;
-	SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, n_sm, s, &sorted, &b->sort_passes, b->ev[1]));
+	SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, b->device, n_sm, s, &sorted, &b->sort_passes, b->ev[1]));
 	uint64_t *other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
 
@@ -903,9 +903,9 @@ int svo_sort_u64(uint64_t *d_keys, uint64_t *d_tmp, uint64_t n, uint32_t begin_b
 	SortScratch sc;
 	uint64_t *res = d_keys;
 	uint32_t np = 0;
-	int rc = radix_sort_u64(d_keys, d_tmp, n, begin_bit, end_bit, sc, sm_count(device), s, &res, &np, nullptr);
+	int rc = radix_sort_u64(d_keys, d_tmp, n, begin_bit, end_bit, sc, device, sm_count(device), s, &res, &np, nullptr);
 	if (!rc && res != d_keys && cudaMemcpyAsync(d_keys, res, n * 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "copy back failed");
-	sc.hist.release(s), sc.state.release(s);
+	sc.release(s);
 	return rc;
 }
 
@@ -986,6 +986,18 @@ int svo_stream_synchronize(int device, void *stream) {
 }
 
 void svo_debug_force_wide_sort_state(int on) { svo::g_force_wide_sort_state = on != 0; }
+void svo_debug_profile_passes(int on) { svo::g_profile_passes = on != 0; }
+int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap) {
+	if (!b || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	DeviceGuard guard(b->device);
+	const SortScratch &sc = b->sort_scratch;
+	int n = 0;
+	for (int i = 0; i + 1 < sc.n_ev && (uint32_t)n < cap; ++i, ++n) {
+		SVO_CUDA_TRY(cudaEventSynchronize(sc.ev[i + 1]));
+		SVO_CUDA_TRY(cudaEventElapsedTime(&out[n], sc.ev[i], sc.ev[i + 1]));
+	}
+	return n;
+}
 
 #ifdef SVO_EMU
 // test hook of the emulation build only (see scan.cuh)

@@ -1,13 +1,19 @@
 #!/usr/bin/env python
 """Kernel tuning harness (run on the GPU box): builds variants of libsvo_b200.so with different compile-time
-tile shapes and prints the per-phase cudaEvent times of the C4 (or other) workload for each.
+switches and prints the per-phase cudaEvent times (and the time of every sort kernel) of a workload for each.
 
-  python tools/tune.py --workload C4 --variants "512,8,2;256,16,3;256,16,4;512,8,3;384,12,2"
+  python tools/tune.py --workload C4 --variants "SVO_OS_ITEMS=22;SVO_OS_ITEMS=18,SVO_OS_TMA=0,SVO_OS_MINB=3"
+
+A variant is a comma-separated list of -D definitions; "base" = no definition; "git:<rev>" builds the sources of a
+commit (the baseline to compare with).  All variants are compiled in parallel first.
 """
 import argparse
+import concurrent.futures as cf
 import os
 import subprocess
 import sys
+import tempfile
+import zlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,54 +21,82 @@ import __graft_entry__ as graft  # noqa: E402
 from sparsevoxeloctree_b200 import api, scenes  # noqa: E402
 
 
-def build_variant(tag, defs):
-    out = f"/tmp/libsvo_{tag}.so"
-    cmd = ["nvcc"] + graft.NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-o", out, os.path.join(graft.CSRC, "svo_b200.cu")]
-    subprocess.run(cmd, check=True, capture_output=True)
-    return out
+def build_variant(i, spec):
+    out = f"/tmp/libsvo_var{i}.so"
+    src = os.path.join(graft.CSRC, "svo_b200.cu")
+    defs = []
+    if spec.startswith("git:"):
+        rev = spec[4:]
+        d = tempfile.mkdtemp(prefix="svo_rev_")
+        subprocess.run(f"git -C {ROOT} archive {rev} sparsevoxeloctree_b200/csrc include | tar -x -C {d}", shell=True, check=True)
+        src = os.path.join(d, "sparsevoxeloctree_b200", "csrc", "svo_b200.cu")
+    elif spec != "base":
+        defs = [f"-D{x}" for x in spec.split(",") if x]
+    cmd = ["nvcc"] + graft.NVCC_FLAGS + defs + ["-o", out, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return out if r.returncode == 0 else None, r.stderr[-400:]
 
 
 def run(lib, mesh, level, mode, reps=6):
     scene = api.Scene.Create(mesh, lib=lib)
     vox = api.Voxelizer.Create(scene, level, mode)
     b = api.OctreeBuilder.Create(vox)
+    prof = hasattr(lib.dll, "svo_debug_profile_passes")
     best = None
-    for _ in range(reps):
+    for r in range(reps):
+        if prof:
+            lib.dll.svo_debug_profile_passes(1 if r == reps - 1 else 0)
         vox.CmdVoxelize()
         b.CmdBuild()
         ms, npass = b.LastMs()
         tot = sum(ms.values())
         if best is None or tot < best[0]:
             best = (tot, ms, npass)
-    import zlib
+    steps = b.SortStepMs() if prof else []
+    if prof:
+        lib.dll.svo_debug_profile_passes(0)
     info = (vox.GetVoxelFragmentCount(), b.GetLeafCount(), zlib.crc32(b.octree_to_host().tobytes()))
     b.Destroy(), vox.Destroy(), scene.Destroy()
-    return best, info
+    return best, steps, info
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="C4")
-    ap.add_argument("--variants", default="256,22,3")
-    ap.add_argument("--extra", default="", help="extra -D definitions, comma separated")
+    ap.add_argument("--variants", default="base")
+    ap.add_argument("--reps", type=int, default=6)
     args = ap.parse_args()
-    cfg = scenes.CONFIGS[args.workload]
-    mesh = cfg["gen"]()
-    mode = api.CENTER if cfg["mode"] == "center" else api.CONSERVATIVE_EXACT
-    for v in args.variants.split(";"):
-        blk, items, minb = v.split(",")
-        defs = [f"SVO_OS_BLOCK={blk}", f"SVO_OS_ITEMS={items}", f"SVO_OS_MINB={minb}"] + [d for d in args.extra.split(",") if d]
-        try:
-            path = build_variant(f"{blk}_{items}_{minb}_" + "_".join(args.extra.replace("=", "").split(",")), defs)
-        except subprocess.CalledProcessError:
-            print(f"variant {v}: does not compile", flush=True)
-            continue
-        lib = api.Library(path)
-        (tot, ms, npass), (F, U, crc) = run(lib, mesh, cfg["level"], mode)
-        per = ms["sort_passes"] / max(npass, 1)
-        gbs = 16.0 * F / (per * 1e-3) / 1e9 if per > 0 else 0
-        print(f"variant {v:12s} total {tot:7.3f} ms | " + " ".join(f"{k}={x:.3f}" for k, x in ms.items()) +
-              f" | passes={npass} per-pass {per:.3f} ms = {gbs:.0f} GB/s  (F={F} U={U} crc={crc:08x})", flush=True)
+    specs = [v for v in args.variants.split(";") if v]
+    with cf.ThreadPoolExecutor(max_workers=min(len(specs), os.cpu_count() or 4)) as ex:
+        built = list(ex.map(lambda t: build_variant(*t), enumerate(specs)))
+    for wl in args.workload.split(","):
+        cfg = scenes.CONFIGS[wl]
+        mesh = cfg["gen"]()
+        mode = api.CENTER if cfg["mode"] == "center" else api.CONSERVATIVE_EXACT
+        for spec, (path, err) in zip(specs, built):
+            if path is None:
+                print(f"{wl} variant {spec}: does not compile: {err}", flush=True)
+                continue
+            try:
+                if spec.startswith("git:"):  # an older ABI: bind only what this script calls
+                    lib = api.Library.__new__(api.Library)
+                    import ctypes as C
+                    lib.path, lib.dll = path, C.CDLL(path)
+                    for name, res, a in api.SYMBOLS:
+                        if hasattr(lib.dll, name):
+                            fn = getattr(lib.dll, name)
+                            fn.restype, fn.argtypes = res, a
+                else:
+                    lib = api.Library(path)
+                (tot, ms, npass), steps, (F, U, crc) = run(lib, mesh, cfg["level"], mode, args.reps)
+            except Exception as e:  # noqa: BLE001
+                print(f"{wl} variant {spec}: FAILED {e}", flush=True)
+                continue
+            per = ms["sort_passes"] / max(npass, 1)
+            gbs = 16.0 * F / (per * 1e-3) / 1e9 if per > 0 else 0
+            print(f"{wl} {spec:60s} total {tot:7.3f} ms | " + " ".join(f"{k}={x:.3f}" for k, x in ms.items()) +
+                  f" | passes={npass} per-pass {per:.3f} ms = {gbs:.0f} GB/s | sort kernels: " +
+                  " ".join(f"{x:.3f}" for x in steps) + f" | F={F} U={U} crc={crc:08x}", flush=True)
 
 
 if __name__ == "__main__":
