@@ -8,15 +8,11 @@
 //
 //   k_radix_histogram : one read of the keys -> digit histograms of every pass (shared-memory bins)
 //   k_radix_scan_bins : exclusive scan of each pass's bins
-//   k_onesweep_pass   : per pass, ONE read + ONE write of the keys.  Persistent thread blocks draw tiles from a
-//                       ticket (tile ids in start order: the forward progress the look-back needs, whatever order
-//                       the hardware dispatches blocks in); the next tile is pulled into shared memory by one bulk
-//                       asynchronous copy (cp.async.bulk + mbarrier) while the current one is ranked; ranking by
-//                       warp votes (one round per DISTINCT digit value in a row of 32 keys -- spatially coherent
-//                       fragments share their upper digits -- falling back to one vote per digit bit) + one
-//                       shared-memory atomic per digit group; decoupled look-back across tiles done by ONE warp
-//                       per tile with 16-byte loads of the predecessors' state rows; shared-memory reorder,
-//                       run-wise coalesced scatter.
+//   k_onesweep_pass   : per pass, ONE read + ONE write of the keys: per-tile ranking by one warp vote per
+//                       digit bit + one shared-memory atomic per digit group, per-digit decoupled look-back
+//                       across tiles (tiles numbered by a ticket, i.e. in start order, so predecessors are always
+//                       running; 4 predecessor states in flight per step), shared-memory reorder, run-wise
+//                       coalesced scatter.  (profiles/r02_onesweep_experiments.txt: what else was tried.)
 // Digits are up to 9 bits wide (512 bins): 36 Morton bits at level 12 take 4 passes.
 // Traffic: 8*F*(2P+1) bytes for P passes -- HBM bound by design.
 #pragma once
@@ -100,8 +96,11 @@ SVO_DEV void shared_add(uint32_t addr, uint32_t *generic, uint32_t v) {
 }
 template <int NPASS, bool NARROW>
 __global__ void __launch_bounds__(HIST_BLOCK)
-    k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n, SortPasses sp, uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/) {
+    k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n_host, const uint32_t *__restrict__ n_dev, SortPasses sp,
+                      uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/, const uint32_t *__restrict__ mode, uint32_t run_mask) {
 	__shared__ uint32_t s_hist[NPASS * MAX_RADIX];
+	if (!((run_mask >> (mode ? *mode : 0u)) & 1u)) return;
+	const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
 	for (uint32_t i = threadIdx.x; i < NPASS * MAX_RADIX; i += HIST_BLOCK) s_hist[i] = 0;
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
@@ -162,20 +161,14 @@ template <class StateT> struct LbCodec {
 	static SVO_DEV uint64_t value(StateT s) { return (uint64_t)(s & VMASK); }
 };
 
-#ifndef SVO_OS_TMA
-#define SVO_OS_TMA 1 // 1: the next tile is prefetched into shared memory by cp.async.bulk; 0: plain global loads
-#endif
-#ifndef SVO_OS_LB_WARP
-#define SVO_OS_LB_WARP 1 // 1: one warp per tile walks the predecessors with 16-byte loads; 0: one thread per digit
+#ifndef SVO_OS_TICKET
+#define SVO_OS_TICKET 1 // 1: tiles are numbered by a ticket (start order); 0: by blockIdx.x (relies on in-order dispatch)
 #endif
 #ifndef SVO_OS_LB_WINDOW
-#define SVO_OS_LB_WINDOW 2 // predecessor rows in flight per look-back step (warp look-back)
-#endif
-#ifndef SVO_OS_RANK_LOOP
-#define SVO_OS_RANK_LOOP 4 // rounds of the distinct-value ranking before the per-bit votes take over (0: votes only)
+#define SVO_OS_LB_WINDOW 4 // predecessor states in flight per look-back step (2: 0.931, 4: 0.891, 8: 0.908 ms per pass)
 #endif
 
-template <int BLOCK, int ITEMS, int RBITS, class StateT> struct OnesweepCfg {
+template <int BLOCK, int ITEMS, int RBITS> struct OnesweepCfg {
 	static constexpr int RADIX = 1 << RBITS;
 	static constexpr int NB = RADIX + 1; // bin RADIX collects the padding of the last tile
 	static constexpr int NW = BLOCK / 32;
@@ -183,20 +176,30 @@ template <int BLOCK, int ITEMS, int RBITS, class StateT> struct OnesweepCfg {
 	static constexpr int DPT = RADIX > BLOCK ? RADIX / BLOCK : 1; // consecutive digits per digit-thread
 	static constexpr int DTHREADS = RADIX / DPT;                  // threads that own digits
 	static constexpr int NBP = NB + (NB & 1);
-	static constexpr int DPL = RADIX / 32; // digits per lane of the look-back warp
-	// dynamic shared memory, in this order (every piece a multiple of 16 bytes)
-	static constexpr size_t OFF_STAGE = 0;                                           // TILE keys: bulk-copy landing buffer
-	static constexpr size_t OFF_KEYS = SVO_OS_TMA ? (size_t)TILE * 8 : 0;            // TILE keys: reorder buffer (two 32-bit halves)
-	static constexpr size_t OFF_HIST = OFF_KEYS + (size_t)TILE * 8;                  // NW * NB counters (+ pad)
-	static constexpr size_t HIST_BYTES = (((size_t)NW * NB * 4) + 15) & ~size_t(15);
-	static constexpr size_t OFF_TOFF = OFF_HIST + HIST_BYTES;                        // NBP
-	static constexpr size_t OFF_GOFS = OFF_TOFF + (((size_t)NBP * 4 + 15) & ~size_t(15)); // RADIX
-	static constexpr size_t OFF_TOTAL = OFF_GOFS + (size_t)RADIX * 4;                // RADIX
-	static constexpr size_t SMEM = OFF_TOTAL + (size_t)RADIX * 4;
+	static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)NW * NB * 4 + (size_t)NBP * 4 + (size_t)RADIX * 4 + 64;
 	static_assert(BLOCK % 32 == 0 && DTHREADS % 32 == 0 && DTHREADS <= BLOCK, "digit threads must be whole warps");
-	static_assert(DPL * sizeof(StateT) % 16 == 0, "a lane's states are read with 16-byte loads");
 };
 
+// SVO_OS_CLOCKS (experiments only): thread 0 of every tile adds the cycles it spent in each phase to g_os_clocks[]
+#ifndef SVO_OS_CLOCKS
+#define SVO_OS_CLOCKS 0
+#endif
+#if SVO_OS_CLOCKS && defined(__CUDACC__)
+__device__ unsigned long long g_os_clocks[8];
+__device__ unsigned long long g_os_walk[4]; // thread 0: look-back steps, states consumed, empty polls, walks
+#define SVO_CLK(i)                                                                     \
+	do {                                                                               \
+		if (threadIdx.x == 0) {                                                        \
+			const long long now = clock64();                                           \
+			atomicAdd(&g_os_clocks[i], (unsigned long long)(now - clk_prev));          \
+			clk_prev = now;                                                            \
+		}                                                                              \
+	} while (0)
+#define SVO_CLK_INIT long long clk_prev = clock64()
+#else
+#define SVO_CLK(i) ((void)0)
+#define SVO_CLK_INIT ((void)0)
+#endif
 #ifndef SVO_OS_EXPERIMENT
 #define SVO_OS_EXPERIMENT 0 // timing experiments only (bit 0: linear writes, bit 1: no look-back); results are wrong when set
 #endif
@@ -209,7 +212,7 @@ template <int BLOCK, int ITEMS, int RBITS, class StateT> struct OnesweepCfg {
 
 SVO_DEV void lb_backoff() {
 #if defined(__CUDA_ARCH__)
-	__nanosleep(40);
+	__nanosleep(64);
 #endif
 }
 
@@ -227,26 +230,13 @@ SVO_DEV unsigned split_by_bit(unsigned peers, uint32_t d, uint32_t bitmask) {
 	return peers & (p ? b : ~b);
 #endif
 }
-
-// The lanes of the warp whose digit equals mine.  Fragments arrive in raster order, so the 32 keys of a row mostly
-// share their upper digits: up to LOOP rounds of "take the first unmatched lane's value, vote on equality" (6
-// instructions per distinct value; the loop condition is warp-uniform) before falling back to one vote per digit bit
-// (4 instructions per bit, whatever the values).
-template <int NBITS, int LOOP> SVO_DEV unsigned warp_peers(uint32_t d) {
-	unsigned peers = 0, rem = FULL_MASK;
+// the lanes of the warp whose NBITS-bit digit equals mine: one vote per digit bit, straight-line code (rounds over the
+// distinct values of the row -- cheaper in instructions for coherent digits -- measured slower: their data-dependent
+// branches keep the compiler from interleaving the items of a thread)
+template <int NBITS> SVO_DEV unsigned warp_peers(uint32_t d) {
+	unsigned peers = FULL_MASK;
 #pragma unroll
-	for (int it = 0; it < LOOP; ++it) {
-		if (rem == 0u) break;
-		const uint32_t dv = __shfl_sync(FULL_MASK, d, __ffs((int)rem) - 1);
-		const unsigned m = __ballot_sync(FULL_MASK, d == dv);
-		if (d == dv) peers = m;
-		rem &= ~m;
-	}
-	if (rem != 0u) {
-		peers = FULL_MASK;
-#pragma unroll
-		for (int bb = 0; bb < NBITS; ++bb) peers = split_by_bit(peers, d, 1u << bb);
-	}
+	for (int bb = 0; bb < NBITS; ++bb) peers = split_by_bit(peers, d, 1u << bb);
 	return peers;
 }
 
@@ -266,116 +256,39 @@ SVO_DEV uint32_t leader_atomic_add(uint32_t *addr, uint32_t v, bool leader) {
 #endif
 }
 
-// ---- bulk asynchronous copy (TMA unit, 1-D) + mbarrier --------------------------------------------------------
-// global -> shared copy of `bytes` (a multiple of 16; both addresses 16-byte aligned) issued by ONE thread; completion
-// is signalled on an mbarrier as a transaction count.  The CPU emulator copies synchronously.
-SVO_DEV void mbar_init(uint64_t *mbar, uint32_t count) {
-#if defined(__CUDA_ARCH__)
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(count) : "memory");
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#else
-	*mbar = 0;
-	(void)count;
-#endif
-}
-SVO_DEV void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *mbar) {
-#if defined(__CUDA_ARCH__)
-	const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
-	const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
-	// the generic-proxy reads of the landing buffer (previous tile) are ordered before the async-proxy writes
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-	             "l"((uint64_t)__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"(bar)
-	             : "memory");
-#else
-	memcpy(smem_dst, gmem_src, bytes);
-	(void)mbar;
-#endif
-}
-SVO_DEV void mbar_wait(uint64_t *mbar, uint32_t parity) {
-#if defined(__CUDA_ARCH__)
-	const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
-	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
-	             "r"(parity)
-	             : "memory");
-#else
-	(void)mbar, (void)parity;
-#endif
-}
-
-// 16-byte loads / stores of look-back states that must not be served from a stale cache line
-template <class StateT> SVO_DEV void load_states16(const StateT *p, StateT *out /* 16 / sizeof(StateT) values */) {
-#if defined(__CUDA_ARCH__)
-	if (sizeof(StateT) == 4) {
-		uint32_t a, b, c, d;
-		asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
-		out[0] = (StateT)a, out[1] = (StateT)b, out[2] = (StateT)c, out[3] = (StateT)d;
-	} else {
-		uint64_t a, b;
-		asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-		out[0] = (StateT)a, out[1] = (StateT)b;
-	}
-#else
-	for (unsigned i = 0; i < 16 / sizeof(StateT); ++i) out[i] = *reinterpret_cast<const volatile StateT *>(p + i);
-#endif
-}
-template <class StateT> SVO_DEV void store_states16(StateT *p, const StateT *v) {
-#if defined(__CUDA_ARCH__)
-	if (sizeof(StateT) == 4)
-		asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)v[0]), "r"((uint32_t)v[1]), "r"((uint32_t)v[2]),
-		             "r"((uint32_t)v[3])
-		             : "memory");
-	else
-		asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((uint64_t)v[0]), "l"((uint64_t)v[1]) : "memory");
-#else
-	for (unsigned i = 0; i < 16 / sizeof(StateT); ++i) *reinterpret_cast<volatile StateT *>(p + i) = v[i];
-#endif
-}
-
 struct PassArgs {
 	const uint64_t *in;
 	uint64_t *out;
-	uint64_t n;
-	uint32_t tiles;
+	uint64_t n;            // number of keys ...
+	const uint32_t *n_dev; // ... or, when not null, read from device memory (n is then the capacity the grid was sized for)
 	uint32_t shift, mask;
 	const uint32_t *bins; // exclusive digit offsets of this pass
 	void *state;          // [tiles][RADIX] look-back words
 	uint32_t *ticket;     // zeroed; tiles are handed out in start order
-	// Device-side mode switch of the hybrid sort (bucket.cuh): *mode is 0 (hybrid) or 1 (classic: a bucket was too
-	// large); nullptr counts as 0.  The pass runs when bit *mode of run_mask is set, as pass number pass_in_mode[*mode]
-	// among the passes that run in that mode (the look-back status codes rotate with it).
+	// Device-side mode switch of the builder (bucket.cuh): *mode is 0 or 1; nullptr counts as 0.  The pass runs when bit
+	// *mode of run_mask is set, as pass number `pass` among the passes that run (the look-back status codes rotate with it).
 	const uint32_t *mode;
 	uint32_t run_mask;
-	uint32_t pass_in_mode[2];
-	uint32_t use_bulk; // the input is 16-byte aligned: whole tiles arrive by cp.async.bulk
+	uint32_t pass;
 };
 
 // One tile.  FULL = the tile holds TILE keys (every tile but possibly the last): no bounds checks, no padding bin.
-// STAGED = its keys already sit in the landing buffer s_stage (bulk copy), else they are loaded from global memory.
-// after_load() is called by every thread once the whole block has its keys in registers (the landing buffer is free).
-template <int BLOCK, int ITEMS, int RBITS, class StateT, bool FULL, class AfterLoad>
-SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out, uint32_t shift, uint32_t mask,
-                           const uint32_t *__restrict__ g_bins, StateT *state, uint32_t pass, uint32_t tile, uint32_t tile_count, bool staged,
-                           unsigned char *smem, uint32_t *s_wsum, AfterLoad after_load) {
-	using C = OnesweepCfg<BLOCK, ITEMS, RBITS, StateT>;
-	constexpr int RADIX = C::RADIX, NB = C::NB, NW = C::NW, TILE = C::TILE, DPT = C::DPT, DTHREADS = C::DTHREADS, DPL = C::DPL;
+template <int BLOCK, int ITEMS, int RBITS, class StateT, bool FULL>
+SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out, uint32_t tile, uint32_t tile_count,
+                           uint32_t shift, uint32_t mask, uint32_t pass, const uint32_t *__restrict__ g_bins, StateT *state,
+                           uint64_t *s_keys, uint32_t *s_wsum) {
+	using C = OnesweepCfg<BLOCK, ITEMS, RBITS>;
+	constexpr int RADIX = C::RADIX, NB = C::NB, NW = C::NW, TILE = C::TILE, DPT = C::DPT, DTHREADS = C::DTHREADS;
 	using LB = LbCodec<StateT>;
-	const uint64_t *s_stage = reinterpret_cast<const uint64_t *>(smem + C::OFF_STAGE);
-	uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem + C::OFF_KEYS);
-	uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);     // NW * NB: per-warp digit counters, then warp prefixes
-	uint32_t *s_tile_off = reinterpret_cast<uint32_t *>(smem + C::OFF_TOFF); // NB: first slot of each digit inside the tile
-	uint32_t *s_gofs = reinterpret_cast<uint32_t *>(smem + C::OFF_GOFS);     // RADIX: global offset minus tile offset (mod 2^32)
-	uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + C::OFF_TOTAL);   // RADIX: keys of each digit in this tile
+	uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_keys + TILE);  // NW * NB: per-warp digit counters, then warp prefixes
+	uint32_t *s_tile_off = s_hist + NW * NB;                         // NB: first slot of each digit inside the tile
+	uint32_t *s_gofs = s_tile_off + C::NBP;                          // RADIX: global offset minus tile offset (mod 2^32)
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t wbase = warp * 32 * ITEMS;
 
-	// warp-striped: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS), item i of lane l is element i*32 + l
+	// warp-striped load: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS), item i of lane l is element i*32 + l
 	uint64_t key[ITEMS];
-	if (SVO_OS_TMA && staged) {
-#pragma unroll
-		for (int i = 0; i < ITEMS; ++i) key[i] = s_stage[wbase + i * 32 + lane];
-	} else {
+	{
 		const uint64_t *src = keys_in + (uint64_t)tile * TILE + wbase + lane;
 #pragma unroll
 		for (int i = 0; i < ITEMS; ++i) key[i] = (FULL || wbase + i * 32 + lane < tile_count) ? src[i * 32] : ~0ull;
@@ -384,8 +297,9 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 	const uint32_t AGG = (2u * pass + 1u) & 3u, PRE = (2u * pass + 2u) & 3u;
 	uint32_t bin_total[DPT];
 	uint32_t my_sum = 0, inc = 0;
+	SVO_CLK_INIT;
 	__syncthreads();
-	after_load();
+	SVO_CLK(0);
 
 	// rank inside the warp.  Stable: items in increasing i, lanes in increasing l.  The leader (lowest lane) of
 	// each digit group bumps the warp's counter with ONE shared-memory atomic; a warp's atomics execute in
@@ -396,13 +310,15 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 #pragma unroll
 	for (int i = 0; i < ITEMS; ++i) {
 		const uint32_t d = (FULL || wbase + i * 32 + lane < tile_count) ? ((uint32_t)(key[i] >> shift) & mask) : (uint32_t)RADIX;
-		const unsigned peers = warp_peers<RBITS + (FULL ? 0 : 1), SVO_OS_RANK_LOOP>(d); // (bit RBITS: the padding bin of a partial tile)
+		const unsigned peers = warp_peers<RBITS + (FULL ? 0 : 1)>(d); // (bit RBITS: the padding bin of a partial tile)
 		const uint32_t below = (uint32_t)__popc(peers & lt_mask);
 		const uint32_t base = leader_atomic_add(&wh[d], (uint32_t)__popc(peers), below == 0u);
 		SVO_EMU_WARP_ORDER(); // hardware issues a warp's atomics in program order; the emulator's lanes are free-running
 		rank[i] = __shfl_sync(FULL_MASK, base, __ffs((int)peers) - 1) + below;
 	}
+	SVO_CLK(1);
 	__syncthreads();
+	SVO_CLK(2);
 
 	// per digit: exclusive prefix over the warps and the tile total; publish the aggregate right away
 	if (threadIdx.x < DTHREADS) {
@@ -418,7 +334,6 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 			}
 			bin_total[j] = run;
 			my_sum += run;
-			if (SVO_OS_LB_WARP) s_total[d] = run;
 			*reinterpret_cast<volatile StateT *>(state + (uint64_t)tile * RADIX + d) = LB::pack(tile == 0 ? PRE : AGG, run);
 		}
 	}
@@ -449,6 +364,7 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 	}
 	if (!FULL && threadIdx.x == 0) s_tile_off[RADIX] = tile_count; // padding sorts after every real key
 	__syncthreads();
+	SVO_CLK(3);
 
 	// reorder through shared memory (needs tile-local offsets only: runs while predecessors publish)
 #pragma unroll
@@ -464,74 +380,13 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 		s_keys[s_tile_off[d] + s_hist[warp * NB + d] + rank[i]] = key[i];
 #endif
 	}
+	SVO_CLK(4);
 
-#if SVO_OS_LB_WARP
-	// Decoupled look-back by ONE warp: lane l owns digits [l*DPL, (l+1)*DPL) and reads them from a predecessor's state
-	// row with 16-byte loads, SVO_OS_LB_WINDOW rows in flight.  A tile publishes a whole row at a time (aggregates after
-	// its ranking, prefixes after its own look-back), so rows are consumed whole: the walk stops at the first row that
-	// holds prefixes.  The other warps wait at the barrier below instead of polling.
-	if (warp == 0) {
-		constexpr int VPS = 16 / (int)sizeof(StateT); // states per 16-byte load
-		constexpr int W = SVO_OS_LB_WINDOW;
-		uint32_t excl[DPL];
-#pragma unroll
-		for (int j = 0; j < DPL; ++j) excl[j] = 0; // offsets are taken mod 2^32 (n < 2^32)
-		if (tile != 0 && !(SVO_OS_EXPERIMENT & 2)) {
-			uint32_t p = tile - 1;                                      // nearest predecessor not yet summed
-			uint32_t open = DPL == 32 ? ~0u : ((1u << DPL) - 1u);       // this lane's digits that still lack a prefix
-			bool walking = true;
-			while (walking) {
-				StateT st[W][DPL];
-#pragma unroll
-				for (int w = 0; w < W; ++w)
-					if ((uint32_t)w <= p) {
-						const StateT *row = state + (size_t)(p - w) * RADIX + lane * DPL;
-#pragma unroll
-						for (int j = 0; j < DPL; j += VPS) load_states16(row + j, &st[w][j]);
-					}
-				uint32_t consumed = 0;
-#pragma unroll
-				for (int w = 0; w < W; ++w) {
-					if (!walking || (uint32_t)w > p) break; // warp-uniform
-					bool ready = true;
-#pragma unroll
-					for (int j = 0; j < DPL; ++j) {
-						const uint32_t c = LB::code(st[w][j]);
-						ready = ready && (!((open >> j) & 1u) || c == AGG || c == PRE);
-					}
-					if (!__all_sync(FULL_MASK, ready)) break; // this row is still being published: poll it again
-#pragma unroll
-					for (int j = 0; j < DPL; ++j)
-						if ((open >> j) & 1u) {
-							excl[j] += (uint32_t)LB::value(st[w][j]);
-							if (LB::code(st[w][j]) == PRE) open &= ~(1u << j);
-						}
-					++consumed;
-					walking = __any_sync(FULL_MASK, open != 0u) != 0;
-				}
-				if (consumed == 0) lb_backoff();
-				p -= consumed; // never passes tile 0: its row holds prefixes, which close every digit
-			}
-			StateT mine[DPL];
-#pragma unroll
-			for (int j = 0; j < DPL; ++j) mine[j] = LB::pack(PRE, (uint64_t)excl[j] + s_total[lane * DPL + j]);
-#ifdef SVO_EMU
-			if (!g_emu_lookback_aggregate_only)
-#endif
-			{
-				StateT *row = state + (size_t)tile * RADIX + lane * DPL;
-#pragma unroll
-				for (int j = 0; j < DPL; j += VPS) store_states16(row + j, &mine[j]);
-			}
-		}
-#pragma unroll
-		for (int j = 0; j < DPL; ++j) {
-			const uint32_t d = lane * DPL + j;
-			s_gofs[d] = g_bins[d] + excl[j] - s_tile_off[d];
-		}
-	}
-#else
-	// decoupled look-back, one thread per digit, 4 predecessor states in flight
+	// Decoupled look-back, one thread per digit, SVO_OS_LB_WINDOW predecessor states in flight per step.  (Measured: the
+	// walks are short -- ~20 predecessors, 5 steps -- and never find an unpublished state; what they cost is the
+	// >1000 cycles every dependent global load takes on an SM whose memory queue is full of key traffic.  Starting the
+	// walk before the reorder, wider windows, one polling warp per tile and dedicated scanner blocks were all slower.)
+	constexpr int W = SVO_OS_LB_WINDOW;
 	if (threadIdx.x < DTHREADS) {
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
@@ -539,32 +394,33 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 			uint32_t excl = 0; // offsets are taken mod 2^32 (n < 2^32)
 			if (tile != 0 && !(SVO_OS_EXPERIMENT & 2)) {
 				const volatile StateT *p = state + (size_t)(tile - 1) * RADIX + d; // nearest predecessor not yet summed
-				uint32_t left = tile;                                            // predecessors from p backwards
+				uint32_t left = tile;                                            // predecessors from p backwards (>= 1)
 				for (;;) {
-					if (left >= 4u) {
-						const StateT s0 = p[0], s1 = p[-RADIX], s2 = p[-2 * RADIX], s3 = p[-3 * RADIX];
-						const uint32_t c0 = LB::code(s0), c1 = LB::code(s1), c2 = LB::code(s2), c3 = LB::code(s3);
-						if (c0 != PRE && c0 != AGG) { lb_backoff(); continue; }
-						excl += (uint32_t)LB::value(s0);
-						if (c0 == PRE) break;
-						if (c1 != PRE && c1 != AGG) { p -= RADIX, left -= 1u; continue; }
-						excl += (uint32_t)LB::value(s1);
-						if (c1 == PRE) break;
-						if (c2 != PRE && c2 != AGG) { p -= 2 * RADIX, left -= 2u; continue; }
-						excl += (uint32_t)LB::value(s2);
-						if (c2 == PRE) break;
-						if (c3 != PRE && c3 != AGG) { p -= 3 * RADIX, left -= 3u; continue; }
-						excl += (uint32_t)LB::value(s3);
-						if (c3 == PRE) break;
-						p -= 4 * RADIX, left -= 4u;
-					} else { // the first few tiles: one state at a time (tile 0 always holds a prefix)
-						const StateT s0 = p[0];
-						const uint32_t c0 = LB::code(s0);
-						if (c0 != PRE && c0 != AGG) { lb_backoff(); continue; }
-						excl += (uint32_t)LB::value(s0);
-						if (c0 == PRE) break;
-						p -= RADIX, left -= 1u;
+					StateT st[W];
+#pragma unroll
+					for (int q = 0; q < W; ++q)
+						if ((uint32_t)q < left) st[q] = p[-(ptrdiff_t)q * RADIX];
+					uint32_t used = 0;
+					bool done = false;
+#pragma unroll
+					for (int q = 0; q < W; ++q) {
+						if (done || (uint32_t)q >= left || used != (uint32_t)q) break;
+						const uint32_t c = LB::code(st[q]);
+						if (c != PRE && c != AGG) break; // not published yet: poll from here again
+						excl += (uint32_t)LB::value(st[q]);
+						++used;
+						done = c == PRE;
 					}
+#if SVO_OS_CLOCKS && defined(__CUDACC__)
+					if (threadIdx.x == 0) {
+						atomicAdd(&g_os_walk[0], 1ull), atomicAdd(&g_os_walk[1], (unsigned long long)used);
+						if (used == 0u) atomicAdd(&g_os_walk[2], 1ull);
+						if (done) atomicAdd(&g_os_walk[3], 1ull);
+					}
+#endif
+					if (done) break;
+					if (used == 0u) lb_backoff();
+					p -= (ptrdiff_t)used * RADIX, left -= used; // tile 0 always holds a prefix: left never reaches 0
 				}
 #ifdef SVO_EMU
 				if (!g_emu_lookback_aggregate_only)
@@ -574,8 +430,9 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 			s_gofs[d] = g_bins[d] + excl - s_tile_off[d];
 		}
 	}
-#endif
+	SVO_CLK(5);
 	__syncthreads();
+	SVO_CLK(6);
 
 	// scatter: slot idx of the tile goes to bins[d] + (keys of digit d in earlier tiles) + (idx - tile_off[d])
 #pragma unroll
@@ -596,69 +453,42 @@ SVO_DEV void onesweep_tile(const uint64_t *__restrict__ keys_in, uint64_t *__res
 #endif
 		}
 	}
+	SVO_CLK(7);
 }
 
-// Persistent blocks: each draws tiles from the ticket until none is left.  With SVO_OS_TMA the ticket for the NEXT tile
-// is drawn, and its bulk copy issued, as soon as the current tile's keys have left the landing buffer -- the copy
-// then has the whole ranking / look-back / scatter of the current tile to complete.  (Forward progress: the smallest
-// unfinished tile is always either being processed, or held by a block whose current tile is smaller and finished.)
+// Tiles are numbered in start order by a ticket, so every predecessor of a running tile has been started (and
+// running blocks are never preempted) -- the forward progress the look-back needs, without relying on the order in
+// which the hardware dispatches the blocks of a grid (+2.9 % per pass against numbering by blockIdx.x).
 template <int BLOCK, int ITEMS, int RBITS, int MINB, class StateT>
 __global__ void __launch_bounds__(BLOCK, MINB) k_onesweep_pass(PassArgs pa) {
-	using C = OnesweepCfg<BLOCK, ITEMS, RBITS, StateT>;
-	SVO_DYN_SMEM(unsigned char, smem);
+	using C = OnesweepCfg<BLOCK, ITEMS, RBITS>;
+	SVO_DYN_SMEM(uint64_t, s_keys);
 	__shared__ uint32_t s_wsum[C::RADIX / 32 + 1];
-	__shared__ uint32_t s_next;
-	__shared__ uint64_t s_mbar;
 	const uint32_t mode = pa.mode ? *pa.mode : 0u;
 	if (!((pa.run_mask >> mode) & 1u)) return;
-	const uint32_t pass = mode ? pa.pass_in_mode[1] : pa.pass_in_mode[0];
-	// (kernel parameters are copied into scalars: handing the struct to the tile function by reference put it on the stack)
-	const uint64_t *const keys_in = pa.in;
-	uint64_t *const keys_out = pa.out;
-	const uint32_t shift = pa.shift, mask = pa.mask;
-	const uint32_t *const g_bins = pa.bins;
-	StateT *const state = reinterpret_cast<StateT *>(pa.state);
-	uint32_t *const ticket = pa.ticket;
-	const uint32_t tiles = pa.tiles;
-	const uint32_t last_count = (uint32_t)(pa.n - (uint64_t)(tiles - 1) * C::TILE); // keys of the last tile (1..TILE)
-	const bool bulk = SVO_OS_TMA && pa.use_bulk;
-	uint32_t *const p_next = &s_next;
-	uint64_t *const p_mbar = &s_mbar;
-	auto tile_is_bulk = [=](uint32_t t) { return bulk && t < tiles && (t + 1 < tiles || last_count == (uint32_t)C::TILE); };
-	auto take_next = [=]() { // thread 0: draw the next tile and start its copy into the (free) landing buffer
-		if (threadIdx.x == 0) {
-			const uint32_t t = atomicAdd(ticket, 1u);
-			*p_next = t;
-			if (tile_is_bulk(t)) bulk_load(smem + C::OFF_STAGE, keys_in + (uint64_t)t * C::TILE, (uint32_t)C::TILE * 8u, p_mbar);
-		}
-	};
-	if (SVO_OS_TMA && threadIdx.x == 0) mbar_init(&s_mbar, 1);
-	take_next();
+	const uint64_t n = pa.n_dev ? (uint64_t)*pa.n_dev : pa.n;
+#if SVO_OS_TICKET
+	__shared__ uint32_t s_tile;
+	if (threadIdx.x == 0) s_tile = atomicAdd(pa.ticket, 1u);
 	__syncthreads();
-	uint32_t tile = s_next;
-	uint32_t phase = 0; // parity of the mbarrier: one completed copy per bulk-loaded tile
-	while (tile < tiles) {
-		const bool staged = tile_is_bulk(tile);
-		const uint32_t count = tile + 1 < tiles ? (uint32_t)C::TILE : last_count;
-		if (staged) {
-			mbar_wait(&s_mbar, phase);
-			phase ^= 1u;
-		}
-		if (count == (uint32_t)C::TILE)
-			onesweep_tile<BLOCK, ITEMS, RBITS, StateT, true>(keys_in, keys_out, shift, mask, g_bins, state, pass, tile, count, staged, smem, s_wsum,
-			                                                 take_next);
-		else
-			onesweep_tile<BLOCK, ITEMS, RBITS, StateT, false>(keys_in, keys_out, shift, mask, g_bins, state, pass, tile, count, false, smem, s_wsum,
-			                                                  take_next);
-		__syncthreads(); // the scatter has read the reorder buffer and s_gofs; s_next is visible
-		tile = s_next;
-	}
+	const uint32_t tile = s_tile;
+#else
+	const uint32_t tile = blockIdx.x;
+#endif
+	const uint64_t tile_base = (uint64_t)tile * C::TILE;
+	if (tile_base >= n) return; // (grid sized for a capacity: the blocks beyond the actual count have nothing to do)
+	const uint32_t tile_count = (uint32_t)(n - tile_base < (uint64_t)C::TILE ? n - tile_base : (uint64_t)C::TILE);
+	StateT *state = reinterpret_cast<StateT *>(pa.state);
+	if (tile_count == (uint32_t)C::TILE)
+		onesweep_tile<BLOCK, ITEMS, RBITS, StateT, true>(pa.in, pa.out, tile, tile_count, pa.shift, pa.mask, pa.pass, pa.bins, state, s_keys, s_wsum);
+	else
+		onesweep_tile<BLOCK, ITEMS, RBITS, StateT, false>(pa.in, pa.out, tile, tile_count, pa.shift, pa.mask, pa.pass, pa.bins, state, s_keys, s_wsum);
 }
 
 inline bool g_force_wide_sort_state = false; // svo_debug_force_wide_sort_state (tests)
-inline bool g_profile_passes = false;        // svo_debug_profile_passes: an event after every pass
+inline bool g_profile_passes = false;        // svo_debug_profile_passes: an event after every sort kernel
 
-constexpr int SORT_MAX_EVENTS = 2 * MAX_PASSES + 4;
+constexpr int SORT_MAX_EVENTS = 2 * MAX_PASSES + 8;
 struct SortScratch {
 	DevBuf<uint32_t> hist;    // MAX_PASSES * MAX_RADIX digit bins (+ tickets behind them)
 	DevBuf<unsigned char> state;
@@ -686,57 +516,48 @@ constexpr uint32_t SORT_HIST_WORDS = MAX_PASSES * MAX_RADIX, SORT_TICKETS = 16; 
 #define SVO_OS_ITEMS 22
 #endif
 #ifndef SVO_OS_MINB
-#define SVO_OS_MINB 2
+#define SVO_OS_MINB 3
 #endif
 constexpr int OS_BLOCK = SVO_OS_BLOCK, OS_ITEMS = SVO_OS_ITEMS, OS_MINB = SVO_OS_MINB, OS_TILE = OS_BLOCK * OS_ITEMS;
 
-// Persistent grid: as many blocks as fit on the device at once (per device: set the dynamic shared-memory limit and ask
-// the occupancy calculator once per kernel and device).
-template <int RBITS, class StateT> inline int launch_onesweep_pass(const PassArgs &pa, int device, int n_sm, cudaStream_t s) {
-	using C = OnesweepCfg<OS_BLOCK, OS_ITEMS, RBITS, StateT>;
+// grid = the tiles of pa.n keys (with pa.n_dev: of the capacity pa.n; surplus blocks exit at once)
+template <int RBITS, class StateT> inline int launch_onesweep_pass(const PassArgs &pa, int device, cudaStream_t s) {
+	using C = OnesweepCfg<OS_BLOCK, OS_ITEMS, RBITS>;
 	auto k = k_onesweep_pass<OS_BLOCK, OS_ITEMS, RBITS, OS_MINB, StateT>;
-	uint32_t grid;
 #ifndef SVO_EMU
-	static int per_sm[64] = {};
+	static bool attr_set[64] = {}; // per device: a single-process multi-GPU host launches on every device
 	const int di = device >= 0 && device < 64 ? device : 0;
-	if (!per_sm[di]) {
+	if (!attr_set[di]) {
 		SVO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-		int nb = 0;
-		SVO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, OS_BLOCK, C::SMEM));
-		if (nb < 1) {
-			set_error("k_onesweep_pass does not fit on an SM (%zu bytes of shared memory)", (size_t)C::SMEM);
-			return -2;
-		}
-		per_sm[di] = nb;
+		attr_set[di] = true;
 	}
-	grid = (uint32_t)per_sm[di] * (uint32_t)(n_sm > 0 ? n_sm : 148);
 #else
-	(void)device, (void)n_sm;
-	grid = 3;
+	(void)device;
 #endif
-	if (grid > pa.tiles) grid = pa.tiles;
-	SVO_LAUNCH(grid, OS_BLOCK, C::SMEM, s, k, pa);
+	SVO_LAUNCH(div_up(pa.n, OS_TILE), OS_BLOCK, C::SMEM, s, k, pa);
 	return 0;
 }
-inline int launch_onesweep(bool nine, bool wide, const PassArgs &pa, int device, int n_sm, cudaStream_t s) {
-	if (nine) return wide ? launch_onesweep_pass<9, uint64_t>(pa, device, n_sm, s) : launch_onesweep_pass<9, uint32_t>(pa, device, n_sm, s);
-	return wide ? launch_onesweep_pass<8, uint64_t>(pa, device, n_sm, s) : launch_onesweep_pass<8, uint32_t>(pa, device, n_sm, s);
+inline int launch_onesweep(bool nine, bool wide, const PassArgs &pa, int device, cudaStream_t s) {
+	if (nine) return wide ? launch_onesweep_pass<9, uint64_t>(pa, device, s) : launch_onesweep_pass<9, uint32_t>(pa, device, s);
+	return wide ? launch_onesweep_pass<8, uint64_t>(pa, device, s) : launch_onesweep_pass<8, uint32_t>(pa, device, s);
 }
 
-inline int launch_radix_histogram(const uint64_t *keys, uint64_t n, const SortPasses &sp, uint32_t *hist, int n_sm, cudaStream_t s) {
+// gate: the kernel runs only when *mode has its bit set in run_mask (nullptr: always); n_dev: see PassArgs
+inline int launch_radix_histogram(const uint64_t *keys, uint64_t n, const uint32_t *n_dev, const SortPasses &sp, uint32_t *hist,
+                                  const uint32_t *mode, uint32_t run_mask, int n_sm, cudaStream_t s) {
 	uint32_t hgrid = div_up(n, (uint64_t)HIST_BLOCK * HIST_ITEMS);
 	const uint32_t hmax = (uint32_t)(n_sm > 0 ? n_sm : 148) * (uint32_t)SVO_HIST_GRID;
 	if (hgrid > hmax) hgrid = hmax;
 	const bool narrow = sp.shift[sp.n_pass - 1] - sp.shift[0] < 32u;
 	switch (sp.n_pass) {
-#define SVO_HIST_CASE(NP)                                                                              \
-	case NP: {                                                                                         \
-		if (narrow) {                                                                                  \
-			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, true>), keys, n, sp, hist);     \
-		} else {                                                                                       \
-			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, false>), keys, n, sp, hist);    \
-		}                                                                                              \
-		break;                                                                                         \
+#define SVO_HIST_CASE(NP)                                                                                                   \
+	case NP: {                                                                                                              \
+		if (narrow) {                                                                                                       \
+			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, true>), keys, n, n_dev, sp, hist, mode, run_mask);   \
+		} else {                                                                                                            \
+			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, false>), keys, n, n_dev, sp, hist, mode, run_mask);  \
+		}                                                                                                                   \
+		break;                                                                                                              \
 	}
 		SVO_HIST_CASE(1) SVO_HIST_CASE(2) SVO_HIST_CASE(3) SVO_HIST_CASE(4) SVO_HIST_CASE(5) SVO_HIST_CASE(6) SVO_HIST_CASE(7)
 		SVO_HIST_CASE(8)
@@ -745,14 +566,21 @@ inline int launch_radix_histogram(const uint64_t *keys, uint64_t n, const SortPa
 	return 0;
 }
 
+// Device-side switches of a sort that is one of two alternative paths of a build (bucket.cuh); all null / zero for a plain sort.
+struct SortGate {
+	const uint32_t *mode = nullptr; // *mode selects the path (0 / 1)
+	uint32_t run_mask = 1u;         // this sort runs when bit *mode is set
+	const uint32_t *n_dev = nullptr; // key count in device memory (the host's n is then a capacity)
+};
+
 // Sorts n keys on bits [begin_bit, end_bit).  Ping-pongs between a and b; *result receives the buffer that
 // holds the sorted keys.  Stable.
 inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_bit, uint32_t end_bit, SortScratch &sc, int device,
-                          int n_sm, cudaStream_t s, uint64_t **result, uint32_t *n_pass_out, cudaEvent_t ev_after_hist) {
+                          int n_sm, cudaStream_t s, uint64_t **result, uint32_t *n_pass_out, cudaEvent_t ev_after_hist,
+                          const SortGate &gate = SortGate()) {
 	const SortPasses sp = make_passes(begin_bit, end_bit);
 	if (n_pass_out) *n_pass_out = sp.n_pass;
 	*result = a;
-	sc.n_ev = 0;
 	if (n <= 1 || sp.n_pass == 0) {
 		if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
 		return 0;
@@ -771,7 +599,7 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.hist.p, 0, (SORT_HIST_WORDS + SORT_TICKETS) * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, state_bytes, s));
 	SVO_TRY(sc.mark(s));
-	SVO_TRY(launch_radix_histogram(a, n, sp, sc.hist.p, n_sm, s));
+	SVO_TRY(launch_radix_histogram(a, n, gate.n_dev, sp, sc.hist.p, gate.mode, gate.run_mask, n_sm, s));
 	SVO_LAUNCH(sp.n_pass, MAX_RADIX, 0, s, k_radix_scan_bins, sc.hist.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
@@ -780,14 +608,13 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	uint64_t *src = a, *dst = b;
 	for (uint32_t p = 0; p < sp.n_pass; ++p) {
 		PassArgs pa{};
-		pa.in = src, pa.out = dst, pa.n = n, pa.tiles = tiles;
+		pa.in = src, pa.out = dst, pa.n = n, pa.n_dev = gate.n_dev;
 		pa.shift = sp.shift[p], pa.mask = sp.mask[p];
 		pa.bins = sc.hist.p + p * MAX_RADIX;
 		pa.state = sc.state.p;
 		pa.ticket = sc.hist.p + SORT_HIST_WORDS + p;
-		pa.mode = nullptr, pa.run_mask = 1u, pa.pass_in_mode[0] = pa.pass_in_mode[1] = p;
-		pa.use_bulk = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? 1u : 0u;
-		SVO_TRY(launch_onesweep(nine, wide, pa, device, n_sm, s));
+		pa.mode = gate.mode, pa.run_mask = gate.run_mask, pa.pass = p;
+		SVO_TRY(launch_onesweep(nine, wide, pa, device, s));
 		SVO_TRY(sc.mark(s));
 		uint64_t *t = src;
 		src = dst;

@@ -987,6 +987,19 @@ int svo_stream_synchronize(int device, void *stream) {
 
 void svo_debug_force_wide_sort_state(int on) { svo::g_force_wide_sort_state = on != 0; }
 void svo_debug_profile_passes(int on) { svo::g_profile_passes = on != 0; }
+#if SVO_OS_CLOCKS
+// experiment builds only (not declared in svo.h): per-phase cycle sums of the onesweep tiles; reset != 0 clears them
+SVO_API int svo_debug_onesweep_clocks(unsigned long long out[12], int reset) {
+	if (cudaMemcpyFromSymbol(out, svo::g_os_clocks, sizeof(unsigned long long) * 8) != cudaSuccess) return -2;
+	if (cudaMemcpyFromSymbol(out + 8, svo::g_os_walk, sizeof(unsigned long long) * 4) != cudaSuccess) return -2;
+	if (reset) {
+		unsigned long long z[8] = {};
+		if (cudaMemcpyToSymbol(svo::g_os_clocks, z, sizeof(z)) != cudaSuccess) return -2;
+		if (cudaMemcpyToSymbol(svo::g_os_walk, z, sizeof(unsigned long long) * 4) != cudaSuccess) return -2;
+	}
+	return 0;
+}
+#endif
 int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap) {
 	if (!b || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
 	DeviceGuard guard(b->device);

@@ -12,7 +12,6 @@ import concurrent.futures as cf
 import os
 import subprocess
 import sys
-import tempfile
 import zlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,8 +26,10 @@ def build_variant(i, spec):
     defs = []
     if spec.startswith("git:"):
         rev = spec[4:]
-        d = tempfile.mkdtemp(prefix="svo_rev_")
-        subprocess.run(f"git -C {ROOT} archive {rev} sparsevoxeloctree_b200/csrc include | tar -x -C {d}", shell=True, check=True)
+        d = os.path.join(ROOT, ".baseline_src", rev)  # exported beforehand (the GPU box has no .git):
+        if not os.path.isdir(d):                      #   git archive <rev> sparsevoxeloctree_b200/csrc include | tar -x -C .baseline_src/<rev>
+            os.makedirs(d)
+            subprocess.run(f"git -C {ROOT} archive {rev} sparsevoxeloctree_b200/csrc include | tar -x -C {d}", shell=True, check=True)
         src = os.path.join(d, "sparsevoxeloctree_b200", "csrc", "svo_b200.cu")
     elif spec != "base":
         defs = [f"-D{x}" for x in spec.split(",") if x]
@@ -53,6 +54,19 @@ def run(lib, mesh, level, mode, reps=6):
         if best is None or tot < best[0]:
             best = (tot, ms, npass)
     steps = b.SortStepMs() if prof else []
+    if hasattr(lib.dll, "svo_debug_onesweep_clocks"):  # -DSVO_OS_CLOCKS=1 builds: cycles per phase and tile
+        import ctypes as C
+        clk = (C.c_ulonglong * 12)()
+        lib.dll.svo_debug_onesweep_clocks(clk, 1)
+        vox.CmdVoxelize()
+        b.CmdBuild()
+        lib.dll.svo_stream_synchronize(0, None)
+        lib.dll.svo_debug_onesweep_clocks(clk, 1)
+        tiles = -(-vox.GetVoxelFragmentCount() // 5632) * b.LastMs()[1]
+        names = ["load", "rank(w0)", "rank(all)", "digit scan", "reorder", "lookback(t0)", "lookback(all)", "scatter"]
+        print("   cycles per tile: " + "  ".join(f"{n}={c / tiles:.0f}" for n, c in zip(names, clk)), flush=True)
+        print(f"   thread 0 walks per tile: steps={clk[8] / tiles:.1f} states={clk[9] / tiles:.1f} empty polls={clk[10] / tiles:.1f} "
+              f"walks={clk[11] / tiles:.2f}", flush=True)
     if prof:
         lib.dll.svo_debug_profile_passes(0)
     info = (vox.GetVoxelFragmentCount(), b.GetLeafCount(), zlib.crc32(b.octree_to_host().tobytes()))
