@@ -44,11 +44,13 @@ struct SortPasses {
 	uint32_t mask[MAX_PASSES];
 };
 // Fewest passes with digits <= MAX_RADIX_BITS, widths balanced (36 bits -> 9,9,9,9 ; 30 -> 8,8,7,7).
-inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit) {
+// even_passes: round the pass count up to an even number, so that the sorted keys end in the buffer they started in
+inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit, bool even_passes = false) {
 	SortPasses sp{};
 	const uint32_t total = end_bit - begin_bit;
 	if (total == 0) return sp;
 	uint32_t np = (total + MAX_RADIX_BITS - 1) / MAX_RADIX_BITS;
+	if (even_passes && (np & 1u) && total >= np + 1) ++np;
 	if (np > MAX_PASSES) np = MAX_PASSES; // 64 bits / 9 = 8 passes at most
 	uint32_t b = begin_bit;
 	for (uint32_t p = 0; p < np; ++p) {
@@ -488,23 +490,27 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_onesweep_pass(PassArgs pa) {
 inline bool g_force_wide_sort_state = false; // svo_debug_force_wide_sort_state (tests)
 inline bool g_profile_passes = false;        // svo_debug_profile_passes: an event after every sort kernel
 
-constexpr int SORT_MAX_EVENTS = 2 * MAX_PASSES + 8;
-struct SortScratch {
-	DevBuf<uint32_t> hist;    // MAX_PASSES * MAX_RADIX digit bins (+ tickets behind them)
-	DevBuf<unsigned char> state;
+// profiling (svo_debug_profile_passes): an event after every kernel of the sort phases of a build
+constexpr int SORT_MAX_EVENTS = 32;
+struct SortProf {
 	cudaEvent_t ev[SORT_MAX_EVENTS] = {};
-	int n_ev = 0; // events recorded by the last sort (profiling only)
-	void release(cudaStream_t s) {
-		hist.release(s), state.release(s);
+	int n_ev = 0;
+	void reset() { n_ev = 0; }
+	void release() {
 		for (auto &e : ev)
 			if (e) cudaEventDestroy(e), e = nullptr;
 	}
-	int mark(cudaStream_t s) { // profiling: one more event on the stream
+	int mark(cudaStream_t s) {
 		if (!g_profile_passes || n_ev >= SORT_MAX_EVENTS) return 0;
 		if (!ev[n_ev]) SVO_CUDA_TRY(cudaEventCreate(&ev[n_ev]));
 		SVO_CUDA_TRY(cudaEventRecord(ev[n_ev++], s));
 		return 0;
 	}
+};
+struct SortScratch {
+	DevBuf<uint32_t> hist;    // MAX_PASSES * MAX_RADIX digit bins (+ tickets behind them)
+	DevBuf<unsigned char> state;
+	void release(cudaStream_t s) { hist.release(s), state.release(s); }
 };
 constexpr uint32_t SORT_HIST_WORDS = MAX_PASSES * MAX_RADIX, SORT_TICKETS = 16; // tickets live behind the bins
 
@@ -577,8 +583,8 @@ struct SortGate {
 // holds the sorted keys.  Stable.
 inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_bit, uint32_t end_bit, SortScratch &sc, int device,
                           int n_sm, cudaStream_t s, uint64_t **result, uint32_t *n_pass_out, cudaEvent_t ev_after_hist,
-                          const SortGate &gate = SortGate()) {
-	const SortPasses sp = make_passes(begin_bit, end_bit);
+                          const SortGate &gate = SortGate(), SortProf *prof = nullptr, bool even_passes = false) {
+	const SortPasses sp = make_passes(begin_bit, end_bit, even_passes);
 	if (n_pass_out) *n_pass_out = sp.n_pass;
 	*result = a;
 	if (n <= 1 || sp.n_pass == 0) {
@@ -598,12 +604,12 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	SVO_TRY(sc.state.reserve(state_bytes, s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.hist.p, 0, (SORT_HIST_WORDS + SORT_TICKETS) * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, state_bytes, s));
-	SVO_TRY(sc.mark(s));
+	if (prof) SVO_TRY(prof->mark(s));
 	SVO_TRY(launch_radix_histogram(a, n, gate.n_dev, sp, sc.hist.p, gate.mode, gate.run_mask, n_sm, s));
 	SVO_LAUNCH(sp.n_pass, MAX_RADIX, 0, s, k_radix_scan_bins, sc.hist.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
-	SVO_TRY(sc.mark(s));
+	if (prof) SVO_TRY(prof->mark(s));
 
 	uint64_t *src = a, *dst = b;
 	for (uint32_t p = 0; p < sp.n_pass; ++p) {
@@ -615,7 +621,7 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 		pa.ticket = sc.hist.p + SORT_HIST_WORDS + p;
 		pa.mode = gate.mode, pa.run_mask = gate.run_mask, pa.pass = p;
 		SVO_TRY(launch_onesweep(nine, wide, pa, device, s));
-		SVO_TRY(sc.mark(s));
+		if (prof) SVO_TRY(prof->mark(s));
 		uint64_t *t = src;
 		src = dst;
 		dst = t;
