@@ -221,12 +221,6 @@ SVO_API void svo_debug_force_wide_sort_state(int on);
 /* Profiling switch: on != 0 makes every sort record a cudaEvent after each of its kernels (histogram, every radix
  * pass, bucket sort); svo_builder_sort_step_ms then returns the milliseconds between consecutive events of the
  * builder's last sort (out[0..n), n = return value <= cap; < 0: svo_status).  Off by default: no events, no cost. */
-/* The builder has two paths through sort + reduce: the main one sorts run records and finishes
- * bucket by bucket in shared memory; the classic one sorts every fragment with onesweep passes.  The device picks per
- * build (incoherent input or an oversized bucket -> classic).  svo_builder_path: 0 main / 1 classic path of the last
- * build (one small read-back).  svo_debug_use_bucket_path(0) forces the classic path for the builds that follow. */
-SVO_API int svo_builder_path(const svo_builder *b, void *stream);
-SVO_API void svo_debug_use_bucket_path(int on);
 SVO_API void svo_debug_profile_passes(int on);
 SVO_API int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap);
 

@@ -92,8 +92,6 @@ SYMBOLS = [
     ("svo_sort_u64", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P]),
     ("svo_debug_force_wide_sort_state", None, [C.c_int]),
     ("svo_debug_profile_passes", None, [C.c_int]),
-    ("svo_debug_use_bucket_path", None, [C.c_int]),
-    ("svo_builder_path", C.c_int, [_P, _P]),
     ("svo_builder_sort_step_ms", C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
     ("svo_octree_raymarch_leaf", C.c_int, [C.c_int, _P, C.c_uint64, _P, _P, _P, _P]),
     ("svo_device_malloc", C.c_int, [C.c_int, C.c_uint64, C.POINTER(_P)]),
@@ -451,13 +449,6 @@ class OctreeBuilder:
         np_ = C.c_uint32()
         self.lib.check(self.lib.dll.svo_builder_last_ms(self._h, ms, C.byref(np_)))
         return {k: float(ms[i]) for i, k in enumerate(PHASES)}, int(np_.value)
-
-    def Path(self, stream=None) -> int:
-        """0: the last build took the run-record / bucket path, 1: the classic full sort (see include/svo.h)."""
-        r = self.lib.dll.svo_builder_path(self._h, _stream_ptr(stream))
-        if r < 0:
-            self.lib.check(r)
-        return r
 
     def SortStepMs(self):
         """Milliseconds of each kernel of the last sort (needs svo_debug_profile_passes(1) before the build)."""

@@ -68,10 +68,8 @@ struct FusedOut {
 // runs per tile and granularity: cnt01[tile] = runs of equal key>>24 | runs of equal key>>27 << 32, cnt2[tile] = key>>30
 template <int K>
 __global__ void __launch_bounds__(RF_BLOCK)
-    k_reduce_count(const uint64_t *__restrict__ frags, uint64_t n, uint64_t *__restrict__ cnt01, uint64_t *__restrict__ cnt2,
-                   const uint32_t *__restrict__ mode, uint32_t run_mask) {
+    k_reduce_count(const uint64_t *__restrict__ frags, uint64_t n, uint64_t *__restrict__ cnt01, uint64_t *__restrict__ cnt2) {
 	__shared__ uint32_t s_c[3];
-	if (!((run_mask >> (mode ? *mode : 0u)) & 1u)) return; // device-side path switch of the builder (bucket.cuh)
 	const int lane = threadIdx.x & 31;
 	const uint64_t tile_base = (uint64_t)blockIdx.x * RF_TILE;
 	if (threadIdx.x < 3) s_c[threadIdx.x] = 0;
@@ -106,9 +104,8 @@ __global__ void __launch_bounds__(RF_BLOCK)
 template <int K>
 __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
     k_reduce_fused(const uint64_t *__restrict__ frags, uint64_t n, FusedOut out, uint32_t tiles, const uint64_t *__restrict__ pre01,
-                   const uint64_t *__restrict__ pre2, const uint32_t *__restrict__ mode, uint32_t run_mask) {
+                   const uint64_t *__restrict__ pre2) {
 	__shared__ uint64_t s_keys[RF_TILE + 2]; // [0] = the element before the tile, [TILE+1] = the one after
-	if (!((run_mask >> (mode ? *mode : 0u)) & 1u)) return;
 	__shared__ uint32_t s_cnt[3][RF_ITEMS * RF_NW];
 	__shared__ uint32_t s_total[3];
 	__shared__ uint16_t s_start[RF_TILE]; // (tiles with many fragments per voxel) first element of every leaf run

@@ -108,10 +108,8 @@ constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_IT
 // count << 40 | sum silently wrapped at 2^22 counted entries.)
 template <class InT, bool NONZERO>
 __global__ void __launch_bounds__(SCAN_BLOCK)
-    k_exclusive_scan(const InT *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket,
-                     const uint32_t *__restrict__ mode, uint32_t run_mask) {
+    k_exclusive_scan(const InT *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket) {
 	__shared__ uint64_t s_warp[SCAN_BLOCK / 32 + 1];
-	if (!((run_mask >> (mode ? *mode : 0u)) & 1u)) return; // device-side path switch of the builder (bucket.cuh)
 	__shared__ uint32_t s_ticket;
 	__shared__ uint64_t s_prefix;
 	const uint32_t tile = take_ticket(ticket, &s_ticket);
@@ -149,15 +147,14 @@ struct ScanScratch {
 
 // host wrapper; temp storage is grown on demand and reused
 template <class InT, bool NONZERO = false>
-inline int exclusive_scan(const InT *in, uint64_t *out, uint64_t n, ScanScratch &sc, cudaStream_t s, const uint32_t *mode = nullptr,
-                          uint32_t run_mask = 1u) {
+inline int exclusive_scan(const InT *in, uint64_t *out, uint64_t n, ScanScratch &sc, cudaStream_t s) {
 	const uint32_t tiles = n ? div_up(n, SCAN_TILE) : 1;
 	SVO_TRY(sc.state.reserve(tiles + 1, s));
 	SVO_TRY(sc.ticket.reserve(1, s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (tiles + 1) * sizeof(uint64_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, sizeof(uint32_t), s));
 	auto k = k_exclusive_scan<InT, NONZERO>;
-	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p, mode, run_mask);
+	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	return 0;
 }

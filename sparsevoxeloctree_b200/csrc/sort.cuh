@@ -44,13 +44,11 @@ struct SortPasses {
 	uint32_t mask[MAX_PASSES];
 };
 // Fewest passes with digits <= MAX_RADIX_BITS, widths balanced (36 bits -> 9,9,9,9 ; 30 -> 8,8,7,7).
-// even_passes: round the pass count up to an even number, so that the sorted keys end in the buffer they started in
-inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit, bool even_passes = false) {
+inline SortPasses make_passes(uint32_t begin_bit, uint32_t end_bit) {
 	SortPasses sp{};
 	const uint32_t total = end_bit - begin_bit;
 	if (total == 0) return sp;
 	uint32_t np = (total + MAX_RADIX_BITS - 1) / MAX_RADIX_BITS;
-	if (even_passes && (np & 1u) && total >= np + 1) ++np;
 	if (np > MAX_PASSES) np = MAX_PASSES; // 64 bits / 9 = 8 passes at most
 	uint32_t b = begin_bit;
 	for (uint32_t p = 0; p < np; ++p) {
@@ -98,11 +96,8 @@ SVO_DEV void shared_add(uint32_t addr, uint32_t *generic, uint32_t v) {
 }
 template <int NPASS, bool NARROW>
 __global__ void __launch_bounds__(HIST_BLOCK)
-    k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n_host, const uint32_t *__restrict__ n_dev, SortPasses sp,
-                      uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/, const uint32_t *__restrict__ mode, uint32_t run_mask) {
+    k_radix_histogram(const uint64_t *__restrict__ keys, uint64_t n, SortPasses sp, uint32_t *__restrict__ g_hist /*[pass][MAX_RADIX]*/) {
 	__shared__ uint32_t s_hist[NPASS * MAX_RADIX];
-	if (!((run_mask >> (mode ? *mode : 0u)) & 1u)) return;
-	const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
 	for (uint32_t i = threadIdx.x; i < NPASS * MAX_RADIX; i += HIST_BLOCK) s_hist[i] = 0;
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
@@ -261,17 +256,12 @@ SVO_DEV uint32_t leader_atomic_add(uint32_t *addr, uint32_t v, bool leader) {
 struct PassArgs {
 	const uint64_t *in;
 	uint64_t *out;
-	uint64_t n;            // number of keys ...
-	const uint32_t *n_dev; // ... or, when not null, read from device memory (n is then the capacity the grid was sized for)
+	uint64_t n;
 	uint32_t shift, mask;
 	const uint32_t *bins; // exclusive digit offsets of this pass
 	void *state;          // [tiles][RADIX] look-back words
 	uint32_t *ticket;     // zeroed; tiles are handed out in start order
-	// Device-side mode switch of the builder (bucket.cuh): *mode is 0 or 1; nullptr counts as 0.  The pass runs when bit
-	// *mode of run_mask is set, as pass number `pass` among the passes that run (the look-back status codes rotate with it).
-	const uint32_t *mode;
-	uint32_t run_mask;
-	uint32_t pass;
+	uint32_t pass;        // pass number (the look-back status codes rotate with it)
 };
 
 // One tile.  FULL = the tile holds TILE keys (every tile but possibly the last): no bounds checks, no padding bin.
@@ -466,9 +456,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_onesweep_pass(PassArgs pa) {
 	using C = OnesweepCfg<BLOCK, ITEMS, RBITS>;
 	SVO_DYN_SMEM(uint64_t, s_keys);
 	__shared__ uint32_t s_wsum[C::RADIX / 32 + 1];
-	const uint32_t mode = pa.mode ? *pa.mode : 0u;
-	if (!((pa.run_mask >> mode) & 1u)) return;
-	const uint64_t n = pa.n_dev ? (uint64_t)*pa.n_dev : pa.n;
+	const uint64_t n = pa.n;
 #if SVO_OS_TICKET
 	__shared__ uint32_t s_tile;
 	if (threadIdx.x == 0) s_tile = atomicAdd(pa.ticket, 1u);
@@ -478,7 +466,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_onesweep_pass(PassArgs pa) {
 	const uint32_t tile = blockIdx.x;
 #endif
 	const uint64_t tile_base = (uint64_t)tile * C::TILE;
-	if (tile_base >= n) return; // (grid sized for a capacity: the blocks beyond the actual count have nothing to do)
 	const uint32_t tile_count = (uint32_t)(n - tile_base < (uint64_t)C::TILE ? n - tile_base : (uint64_t)C::TILE);
 	StateT *state = reinterpret_cast<StateT *>(pa.state);
 	if (tile_count == (uint32_t)C::TILE)
@@ -490,27 +477,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_onesweep_pass(PassArgs pa) {
 inline bool g_force_wide_sort_state = false; // svo_debug_force_wide_sort_state (tests)
 inline bool g_profile_passes = false;        // svo_debug_profile_passes: an event after every sort kernel
 
-// profiling (svo_debug_profile_passes): an event after every kernel of the sort phases of a build
-constexpr int SORT_MAX_EVENTS = 32;
-struct SortProf {
+constexpr int SORT_MAX_EVENTS = 2 * MAX_PASSES + 8;
+struct SortScratch {
+	DevBuf<uint32_t> hist;    // MAX_PASSES * MAX_RADIX digit bins (+ tickets behind them)
+	DevBuf<unsigned char> state;
 	cudaEvent_t ev[SORT_MAX_EVENTS] = {};
-	int n_ev = 0;
-	void reset() { n_ev = 0; }
-	void release() {
+	int n_ev = 0; // events recorded by the last sort (profiling only)
+	void release(cudaStream_t s) {
+		hist.release(s), state.release(s);
 		for (auto &e : ev)
 			if (e) cudaEventDestroy(e), e = nullptr;
 	}
-	int mark(cudaStream_t s) {
+	int mark(cudaStream_t s) { // profiling: one more event on the stream
 		if (!g_profile_passes || n_ev >= SORT_MAX_EVENTS) return 0;
 		if (!ev[n_ev]) SVO_CUDA_TRY(cudaEventCreate(&ev[n_ev]));
 		SVO_CUDA_TRY(cudaEventRecord(ev[n_ev++], s));
 		return 0;
 	}
-};
-struct SortScratch {
-	DevBuf<uint32_t> hist;    // MAX_PASSES * MAX_RADIX digit bins (+ tickets behind them)
-	DevBuf<unsigned char> state;
-	void release(cudaStream_t s) { hist.release(s), state.release(s); }
 };
 constexpr uint32_t SORT_HIST_WORDS = MAX_PASSES * MAX_RADIX, SORT_TICKETS = 16; // tickets live behind the bins
 
@@ -526,7 +509,6 @@ constexpr uint32_t SORT_HIST_WORDS = MAX_PASSES * MAX_RADIX, SORT_TICKETS = 16; 
 #endif
 constexpr int OS_BLOCK = SVO_OS_BLOCK, OS_ITEMS = SVO_OS_ITEMS, OS_MINB = SVO_OS_MINB, OS_TILE = OS_BLOCK * OS_ITEMS;
 
-// grid = the tiles of pa.n keys (with pa.n_dev: of the capacity pa.n; surplus blocks exit at once)
 template <int RBITS, class StateT> inline int launch_onesweep_pass(const PassArgs &pa, int device, cudaStream_t s) {
 	using C = OnesweepCfg<OS_BLOCK, OS_ITEMS, RBITS>;
 	auto k = k_onesweep_pass<OS_BLOCK, OS_ITEMS, RBITS, OS_MINB, StateT>;
@@ -548,9 +530,7 @@ inline int launch_onesweep(bool nine, bool wide, const PassArgs &pa, int device,
 	return wide ? launch_onesweep_pass<8, uint64_t>(pa, device, s) : launch_onesweep_pass<8, uint32_t>(pa, device, s);
 }
 
-// gate: the kernel runs only when *mode has its bit set in run_mask (nullptr: always); n_dev: see PassArgs
-inline int launch_radix_histogram(const uint64_t *keys, uint64_t n, const uint32_t *n_dev, const SortPasses &sp, uint32_t *hist,
-                                  const uint32_t *mode, uint32_t run_mask, int n_sm, cudaStream_t s) {
+inline int launch_radix_histogram(const uint64_t *keys, uint64_t n, const SortPasses &sp, uint32_t *hist, int n_sm, cudaStream_t s) {
 	uint32_t hgrid = div_up(n, (uint64_t)HIST_BLOCK * HIST_ITEMS);
 	const uint32_t hmax = (uint32_t)(n_sm > 0 ? n_sm : 148) * (uint32_t)SVO_HIST_GRID;
 	if (hgrid > hmax) hgrid = hmax;
@@ -559,9 +539,9 @@ inline int launch_radix_histogram(const uint64_t *keys, uint64_t n, const uint32
 #define SVO_HIST_CASE(NP)                                                                                                   \
 	case NP: {                                                                                                              \
 		if (narrow) {                                                                                                       \
-			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, true>), keys, n, n_dev, sp, hist, mode, run_mask);   \
+			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, true>), keys, n, sp, hist);   \
 		} else {                                                                                                            \
-			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, false>), keys, n, n_dev, sp, hist, mode, run_mask);  \
+			SVO_LAUNCH(hgrid, HIST_BLOCK, 0, s, (k_radix_histogram<NP, false>), keys, n, sp, hist);  \
 		}                                                                                                                   \
 		break;                                                                                                              \
 	}
@@ -572,19 +552,11 @@ inline int launch_radix_histogram(const uint64_t *keys, uint64_t n, const uint32
 	return 0;
 }
 
-// Device-side switches of a sort that is one of two alternative paths of a build (bucket.cuh); all null / zero for a plain sort.
-struct SortGate {
-	const uint32_t *mode = nullptr; // *mode selects the path (0 / 1)
-	uint32_t run_mask = 1u;         // this sort runs when bit *mode is set
-	const uint32_t *n_dev = nullptr; // key count in device memory (the host's n is then a capacity)
-};
-
 // Sorts n keys on bits [begin_bit, end_bit).  Ping-pongs between a and b; *result receives the buffer that
 // holds the sorted keys.  Stable.
 inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_bit, uint32_t end_bit, SortScratch &sc, int device,
-                          int n_sm, cudaStream_t s, uint64_t **result, uint32_t *n_pass_out, cudaEvent_t ev_after_hist,
-                          const SortGate &gate = SortGate(), SortProf *prof = nullptr, bool even_passes = false) {
-	const SortPasses sp = make_passes(begin_bit, end_bit, even_passes);
+                          int n_sm, cudaStream_t s, uint64_t **result, uint32_t *n_pass_out, cudaEvent_t ev_after_hist) {
+	const SortPasses sp = make_passes(begin_bit, end_bit);
 	if (n_pass_out) *n_pass_out = sp.n_pass;
 	*result = a;
 	if (n <= 1 || sp.n_pass == 0) {
@@ -604,24 +576,24 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, uint32_t begin_b
 	SVO_TRY(sc.state.reserve(state_bytes, s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.hist.p, 0, (SORT_HIST_WORDS + SORT_TICKETS) * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, state_bytes, s));
-	if (prof) SVO_TRY(prof->mark(s));
-	SVO_TRY(launch_radix_histogram(a, n, gate.n_dev, sp, sc.hist.p, gate.mode, gate.run_mask, n_sm, s));
+	SVO_TRY(sc.mark(s));
+	SVO_TRY(launch_radix_histogram(a, n, sp, sc.hist.p, n_sm, s));
 	SVO_LAUNCH(sp.n_pass, MAX_RADIX, 0, s, k_radix_scan_bins, sc.hist.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	if (ev_after_hist) SVO_CUDA_TRY(cudaEventRecord(ev_after_hist, s));
-	if (prof) SVO_TRY(prof->mark(s));
+	SVO_TRY(sc.mark(s));
 
 	uint64_t *src = a, *dst = b;
 	for (uint32_t p = 0; p < sp.n_pass; ++p) {
 		PassArgs pa{};
-		pa.in = src, pa.out = dst, pa.n = n, pa.n_dev = gate.n_dev;
+		pa.in = src, pa.out = dst, pa.n = n;
 		pa.shift = sp.shift[p], pa.mask = sp.mask[p];
 		pa.bins = sc.hist.p + p * MAX_RADIX;
 		pa.state = sc.state.p;
 		pa.ticket = sc.hist.p + SORT_HIST_WORDS + p;
-		pa.mode = gate.mode, pa.run_mask = gate.run_mask, pa.pass = p;
+		pa.pass = p;
 		SVO_TRY(launch_onesweep(nine, wide, pa, device, s));
-		if (prof) SVO_TRY(prof->mark(s));
+		SVO_TRY(sc.mark(s));
 		uint64_t *t = src;
 		src = dst;
 		dst = t;

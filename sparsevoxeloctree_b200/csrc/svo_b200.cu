@@ -12,7 +12,6 @@
 #include <new>
 #include <vector>
 
-#include "bucket.cuh"
 #include "build.cuh"
 #include "raster.cuh"
 #include "raymarch.cuh"
@@ -143,17 +142,6 @@ struct svo_builder {
 	DevBuf<uint32_t> tickets;
 	DevBuf<uint32_t> octree;
 	SortScratch sort_scratch;
-	SortProf prof; // svo_debug_profile_passes: events after the kernels of the sort / reduce phases
-	// run-record path (bucket.cuh)
-	SortScratch rec_scratch;
-	DevBuf<uint64_t> rec;           // 2 * rec_cap run records (sort ping-pong)
-	DevBuf<uint32_t> run_u32;       // roff | head_pos | head_run (rec_cap + 1 each) | cell_pos, cell_run, last_pos, last_run
-	DevBuf<uint64_t> bucket_state;  // look-back words of k_runs, k_run_scan and k_bucket_sort_reduce
-	DevBuf<uint32_t> bucket_tab;    // per persistent block: bucket ids of the segment in hand
-	DevBuf<BucketCtl> bucket_ctl;
-	bool use_buckets = false;
-	BucketSortArgs bucket_args{};
-	uint32_t bucket_grid = 0;
 	ScanScratch scan_scratch;
 	DevBuf<uint64_t> rf_cnt01, rf_cnt2, rf_pre01, rf_pre2; // per reduce tile: run counts and their exclusive prefixes
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
@@ -696,8 +684,7 @@ void svo_builder_destroy(svo_builder *b) {
 	const cudaStream_t s = b->last_stream;
 	b->tmp.release(s), b->leaf.release(s), b->first.release(s), b->slot.release(s), b->counts.release(s), b->lb_state.release(s);
 	b->tickets.release(s), b->octree.release(s), b->root_scratch.release(s);
-	b->sort_scratch.release(s), b->rec_scratch.release(s), b->prof.release();
-	b->rec.release(s), b->run_u32.release(s), b->bucket_state.release(s), b->bucket_tab.release(s), b->bucket_ctl.release(s);
+	b->sort_scratch.release(s);
 	b->scan_scratch.state.release(s), b->scan_scratch.ticket.release(s);
 	b->rf_cnt01.release(s), b->rf_cnt2.release(s), b->rf_pre01.release(s), b->rf_pre2.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
@@ -720,6 +707,14 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	// ping-pong buffers for the upper levels.  A second build (or a fragment export) needs a new CmdVoxelize first.
 	v->voxelized = false;
 
+	// ---- sort by Morton code (stable) ----
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
+	uint64_t *sorted = v->frags.p;
+	SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, b->device, n_sm, s, &sorted, &b->sort_passes, b->ev[1]));
+	uint64_t *other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
+
+	// ---- de-duplicate + colour reduce + the two deepest parent levels, fused (build.cuh) ----
 	const uint32_t K = L < 3 ? L : 3;
 	const uint64_t tiles_f = (F + CMP_TILE - 1) / CMP_TILE + 1;
 	const uint32_t rf_tiles = div_up(F, RF_TILE);
@@ -734,95 +729,14 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 			fo += node_cap(F, d - 1), so += (node_cap(F, d) + 7) & ~7ull;
 		}
 	}
-	FusedOut fo{};
-	fo.leaf = b->leaf.p;
-	fo.slot0 = b->slot.p + slot_off[L];
-	fo.first1 = b->first.p + first_off[L];
-	if (L >= 2) fo.slot1 = b->slot.p + slot_off[L - 1], fo.first2 = b->first.p + first_off[L - 1];
-	for (uint32_t j = 0; j < K; ++j) fo.count[j] = b->counts.p + (L - j);
-	b->prof.reset();
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
-
-	// ---- main path: runs of fragments -> sorted run records -> per-bucket sort + reduce on chip (bucket.cuh) ----
-	// Levels below 4 (fewer than 12 Morton bits, fewer than 3 reduce granularities) take the classic path only.
-	// Every kernel of both paths is enqueued; ctl->mode (0 main, 1 classic), decided on the device, tells them which run.
-	const bool buckets = g_use_buckets && L >= 4 && F > 0;
-	b->use_buckets = buckets;
-	const uint32_t *mode = nullptr;
-	if (buckets) {
-		const uint32_t low_bits = bucket_low_bits(L), hb = 3 * L - low_bits;
-		const uint32_t rec_cap = (uint32_t)(F / 4 + 1);
-		const uint32_t n_cells = (uint32_t)(F / BS_T + 1);
-		const uint32_t run_tiles = div_up(F, RUN_TILE), rs_tiles = div_up(rec_cap, RS_TILE);
-		const uint64_t st_runs = run_tiles + 1, st_scan = rs_tiles + 1, st_local = 3ull * 2 * n_cells;
-		SVO_TRY(b->rec.reserve(2ull * rec_cap, s));
-		SVO_TRY(b->run_u32.reserve(3ull * (rec_cap + 1) + 4ull * (n_cells + 1), s));
-		SVO_TRY(b->bucket_state.reserve(st_runs + st_scan + st_local, s));
-		SVO_TRY(b->bucket_ctl.reserve(1, s));
-		const uint32_t local_grid = std::min<uint32_t>(n_cells, 2u * (uint32_t)n_sm);
-		SVO_TRY(b->bucket_tab.reserve((uint64_t)local_grid * BS_CAP, s));
-		SVO_CUDA_TRY(cudaMemsetAsync(b->bucket_state.p, 0, (st_runs + st_scan + st_local) * sizeof(uint64_t), s));
-		SVO_CUDA_TRY(cudaMemsetAsync(b->bucket_ctl.p, 0, sizeof(BucketCtl), s));
-		BucketCtl *ctl = b->bucket_ctl.p;
-		mode = &ctl->mode;
-		uint64_t *rec_a = b->rec.p, *rec_b = b->rec.p + rec_cap;
-		uint32_t *roff = b->run_u32.p, *head_pos = roff + (rec_cap + 1), *head_run = head_pos + (rec_cap + 1);
-		CellPlan cp{};
-		cp.cell_pos = head_run + (rec_cap + 1), cp.cell_run = cp.cell_pos + (n_cells + 1);
-		cp.last_pos = cp.cell_run + (n_cells + 1), cp.last_run = cp.last_pos + (n_cells + 1);
-		cp.n_cells = n_cells;
-		SVO_TRY(b->prof.mark(s));
-		SVO_LAUNCH(run_tiles, RUN_BLOCK, 0, s, k_runs, (const uint64_t *)v->frags.p, F, 24u + low_bits, rec_a, rec_cap, b->bucket_state.p, ctl);
-		SVO_TRY(b->prof.mark(s));
-		uint64_t *rec_sorted = rec_a;
-		if (hb) {
-			SortGate g;
-			g.mode = mode, g.run_mask = 1u, g.n_dev = &ctl->n_runs;
-			SVO_TRY(radix_sort_u64(rec_a, rec_b, rec_cap, REC_BUCKET_SHIFT, REC_BUCKET_SHIFT + hb, b->rec_scratch, b->device, n_sm, s, &rec_sorted,
-			                       nullptr, nullptr, g, &b->prof));
-		}
-		SVO_LAUNCH(std::min<uint32_t>(rs_tiles, 4u * (uint32_t)n_sm), RS_BLOCK, 0, s, k_run_scan, (const uint64_t *)rec_sorted, roff, head_pos,
-		           head_run, b->bucket_state.p + st_runs, ctl);
-		SVO_LAUNCH(2u * (uint32_t)n_sm, 256, 0, s, k_bucket_plan, (const uint32_t *)head_pos, (const uint32_t *)head_run, cp, ctl);
-		SVO_TRY(b->prof.mark(s));
-		SVO_CUDA_TRY(cudaEventRecord(b->ev[1], s));
-		// (the segment kernel is enqueued after the classic sort below: both read the fragment list, only one of them runs)
-		BucketSortArgs ba{};
-		ba.frags = v->frags.p, ba.rec = rec_sorted, ba.roff = roff, ba.cp = cp, ba.low_bits = low_bits;
-		ba.bucket_tab = b->bucket_tab.p, ba.state = b->bucket_state.p + st_runs + st_scan, ba.out = fo, ba.ctl = ctl;
-		ba.out.keys_top = b->tmp.p;
-		b->bucket_args = ba, b->bucket_grid = local_grid;
-	}
-
-	// ---- classic path: stable onesweep sort of all fragments by Morton code (the only path when !buckets) ----
-	uint64_t *sorted = v->frags.p;
-	{
-		SortGate g;
-		g.mode = mode, g.run_mask = buckets ? 2u : 1u;
-		// (with the main path in front, an even number of passes: both paths then leave the parents' keys in b->tmp)
-		SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, b->device, n_sm, s, &sorted, &b->sort_passes,
-		                       buckets ? nullptr : b->ev[1], g, &b->prof, buckets));
-	}
-	uint64_t *other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
-	if (buckets) {
-		if (other != b->tmp.p) return fail(SVO_ERR_CUDA, "internal: the classic sort must end in the fragment buffer");
-#ifndef SVO_EMU
-		static bool attr_set[64] = {};
-		const int di = b->device >= 0 && b->device < 64 ? b->device : 0;
-		if (!attr_set[di]) {
-			SVO_CUDA_TRY(cudaFuncSetAttribute(k_bucket_sort_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BsSmem::BYTES));
-			attr_set[di] = true;
-		}
-#endif
-		SVO_LAUNCH(b->bucket_grid, BS_BLOCK, BsSmem::BYTES, s, k_bucket_sort_reduce, b->bucket_args);
-		SVO_TRY(b->prof.mark(s));
-	}
-
-	// ---- classic path: de-duplicate + colour reduce + the two deepest parent levels, fused (build.cuh) ----
 	if (F) {
+		FusedOut fo{};
+		fo.leaf = b->leaf.p;
+		fo.slot0 = b->slot.p + slot_off[L];
+		fo.first1 = b->first.p + first_off[L];
+		if (L >= 2) fo.slot1 = b->slot.p + slot_off[L - 1], fo.first2 = b->first.p + first_off[L - 1];
 		fo.keys_top = other;
-		const uint32_t rmask = buckets ? 2u : 1u;
+		for (uint32_t j = 0; j < K; ++j) fo.count[j] = b->counts.p + (L - j);
 		// count the runs of every tile, scan over the tiles, then the big kernel: no tile waits for a neighbour
 		SVO_TRY(b->rf_cnt01.reserve(rf_tiles, s));
 		SVO_TRY(b->rf_cnt2.reserve(rf_tiles, s));
@@ -831,10 +745,10 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 		const uint64_t *p01 = b->rf_pre01.p, *p2 = b->rf_pre2.p;
 #define SVO_REDUCE_CASE(KK)                                                                                                        \
 	{                                                                                                                              \
-		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_count<KK>, (const uint64_t *)sorted, F, b->rf_cnt01.p, b->rf_cnt2.p, mode, rmask); \
-		SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt01.p, b->rf_pre01.p, rf_tiles, b->scan_scratch, s, mode, rmask));          \
-		if (KK >= 3) SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt2.p, b->rf_pre2.p, rf_tiles, b->scan_scratch, s, mode, rmask)); \
-		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_fused<KK>, (const uint64_t *)sorted, F, fo, rf_tiles, p01, p2, mode, rmask);   \
+		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_count<KK>, (const uint64_t *)sorted, F, b->rf_cnt01.p, b->rf_cnt2.p);          \
+		SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt01.p, b->rf_pre01.p, rf_tiles, b->scan_scratch, s));                      \
+		if (KK >= 3) SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt2.p, b->rf_pre2.p, rf_tiles, b->scan_scratch, s));           \
+		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_fused<KK>, (const uint64_t *)sorted, F, fo, rf_tiles, p01, p2);                \
 	}
 		if (K == 1) SVO_REDUCE_CASE(1) else if (K == 2) SVO_REDUCE_CASE(2) else SVO_REDUCE_CASE(3)
 #undef SVO_REDUCE_CASE
@@ -1073,17 +987,6 @@ int svo_stream_synchronize(int device, void *stream) {
 
 void svo_debug_force_wide_sort_state(int on) { svo::g_force_wide_sort_state = on != 0; }
 void svo_debug_profile_passes(int on) { svo::g_profile_passes = on != 0; }
-void svo_debug_use_bucket_path(int on) { svo::g_use_buckets = on != 0; }
-int svo_builder_path(const svo_builder *b, void *stream) {
-	if (!b) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
-	if (!b->built && !b->prepared) return fail(SVO_ERR_NOT_READY, "build first");
-	if (!b->use_buckets) return 1;
-	DeviceGuard guard(b->device);
-	BucketCtl h{};
-	SVO_CUDA_TRY(cudaMemcpyAsync(&h, b->bucket_ctl.p, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-	SVO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-	return (int)h.mode;
-}
 #if SVO_OS_CLOCKS
 // experiment builds only (not declared in svo.h): per-phase cycle sums of the onesweep tiles; reset != 0 clears them
 SVO_API int svo_debug_onesweep_clocks(unsigned long long out[12], int reset) {
@@ -1100,7 +1003,7 @@ SVO_API int svo_debug_onesweep_clocks(unsigned long long out[12], int reset) {
 int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap) {
 	if (!b || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
 	DeviceGuard guard(b->device);
-	const SortProf &sc = b->prof;
+	const SortScratch &sc = b->sort_scratch;
 	int n = 0;
 	for (int i = 0; i + 1 < sc.n_ev && (uint32_t)n < cap; ++i, ++n) {
 		SVO_CUDA_TRY(cudaEventSynchronize(sc.ev[i + 1]));

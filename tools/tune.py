@@ -56,13 +56,13 @@ def run(lib, mesh, level, mode, reps=6):
     steps = b.SortStepMs() if prof else []
     if hasattr(lib.dll, "svo_debug_onesweep_clocks"):  # -DSVO_OS_CLOCKS=1 builds: cycles per phase and tile
         import ctypes as C
-        clk = (C.c_ulonglong * 12)()
+        clk = (C.c_ulonglong * 20)()
         lib.dll.svo_debug_onesweep_clocks(clk, 1)
         vox.CmdVoxelize()
         b.CmdBuild()
         lib.dll.svo_stream_synchronize(0, None)
         lib.dll.svo_debug_onesweep_clocks(clk, 1)
-        tiles = -(-vox.GetVoxelFragmentCount() // 5632) * b.LastMs()[1]
+        tiles = -(-vox.GetVoxelFragmentCount() // 5632) * max(b.LastMs()[1], 1)
         names = ["load", "rank(w0)", "rank(all)", "digit scan", "reorder", "lookback(t0)", "lookback(all)", "scatter"]
         print("   cycles per tile: " + "  ".join(f"{n}={c / tiles:.0f}" for n, c in zip(names, clk)), flush=True)
         print(f"   thread 0 walks per tile: steps={clk[8] / tiles:.1f} states={clk[9] / tiles:.1f} empty polls={clk[10] / tiles:.1f} "
