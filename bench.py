@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--mode", default="", choices=["", "center", "conservative"])
     ap.add_argument("--no-ipc", action="store_true", help="multi-GPU: NCCL send/recv instead of P2P stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stitch-check", action="store_true", help="multi-GPU: skip the stitched-vs-single-GPU tree comparison")
     return ap.parse_args()
 
 
@@ -114,16 +115,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(mesh, level, mode_name, steps, warmup, budget_s=25.0):
-    """The reference algorithm's CPU port (oracle/, OpenMP over all host threads) on a bounded sample of the
-    workload: the fragments of ONE top-level octant of the scene at the full level (so the tree is as deep as
-    the real one).  Returns per-step seconds and leaf counts."""
+def sample_box(level):
+    """The bounded sample of the in-line cpu_baseline: one top-level octant of the grid at the full level."""
+    half = (1 << level) // 2
+    return ((0, 0, 0), (half, half, half))
+
+
+def cpu_reference_run(mesh, level, mode_name, steps, warmup, budget_s=25.0, whole_scene=False, keep=None):
+    """The reference algorithm's CPU port (oracle/, OpenMP over all host threads): voxelize + the literal level loop.
+    whole_scene: the workload itself (the --impl reference arm); otherwise a bounded sample of it, the fragments of ONE
+    top-level octant at the full level (so the tree is as deep as the real one).  Stops early once budget_s is spent
+    (at least one timed run).  keep: dict that receives the first run's fragments and node words (parity check)."""
     from oracle import oracle
     cores = os.cpu_count() or 1
     mode = oracle.CENTER if mode_name == "center" else oracle.CONSERVATIVE_EXACT
-    res = 1 << level
-    half = res // 2
-    box = ((0, 0, 0), (half, half, half))
+    box = None if whole_scene or level > 12 else sample_box(level)
     times, leaves, frags_n = [], 0, 0
     t_start = time.perf_counter()
     for it in range(warmup + steps):
@@ -136,11 +142,51 @@ def cpu_reference_run(mesh, level, mode_name, steps, warmup, budget_s=25.0):
         if it == 0:
             d, _, _ = oracle.canonicalise(words, level)
             leaves, frags_n = int((d == level).sum()), len(frags)
+            if keep is not None:
+                keep["words"], keep["n_frags"] = words, len(frags)
+        del frags, words
         if time.perf_counter() - t_start > budget_s and len(times) >= 1:
             break
-    sample = (f"octant (0,0,0) of the {mesh.name} scene at level {level} ({frags_n} fragments, {leaves} leaves), "
+    what = "the whole scene" if box is None else "octant (0,0,0) of the scene"
+    sample = (f"{what} {mesh.name} at level {level} ({frags_n} fragments, {leaves} leaves), "
               f"oracle port (literal level loop), OpenMP {cores} threads, {len(times)} timed runs")
     return times, leaves, cores, sample
+
+
+def parity_check_sample(lib, api, mesh, level, mode, mode_name, device, stream, keep):
+    """The oracle tree of the cpu_baseline sample against a CUDA build of the same voxel window: fragment count,
+    topology and occupancy bit exact; then the oracle's level loop is run once more on the CUDA fragment order (the
+    reference's colour average depends on the order its atomics resolve in) and every leaf word must agree."""
+    from oracle import oracle
+    from tests.parity import keys_to_oracle_frags
+    lo, hi = sample_box(level)
+    scene = api.Scene.Create(mesh, device=device, stream=stream, lib=lib)
+    vox = api.Voxelizer.CreateWindowed(scene, level, mode, lo, hi, stream=stream)
+    b = api.OctreeBuilder.Create(vox, stream=stream)
+    vox.CmdVoxelize(stream)
+    frags = vox.fragments_to_host(stream)
+    b.CmdBuild(stream)
+    words = b.octree_to_host(stream)
+    b.Destroy(), vox.Destroy(), scene.Destroy()
+    out = {"window": [list(lo), list(hi)], "fragments": int(len(frags))}
+    if len(frags) != keep["n_frags"]:
+        out["result"] = f"FAILED: {len(frags)} fragments, oracle {keep['n_frags']}"
+        return out
+    d1, m1, w1 = oracle.canonicalise(words, level)
+    d2, m2, w2 = oracle.canonicalise(keep["words"], level)
+    keep.clear()
+    if len(d1) != len(d2) or not ((d1 == d2).all() and (m1 == m2).all()):
+        out["result"] = "FAILED: topology / occupancy differs from the oracle's tree"
+        return out
+    if not ((w1 >> 24) == (w2 >> 24)).all():
+        out["result"] = "FAILED: leaf flags / fragment counts differ"
+        return out
+    ow, _ = oracle.build_octree(keys_to_oracle_frags(frags, level), level, nthreads=os.cpu_count() or 1)
+    d3, m3, w3 = oracle.canonicalise(ow, level)
+    ok = len(d3) == len(d1) and (d3 == d1).all() and (m3 == m1).all() and (w3 == w1).all()
+    out.update(nodes=int(len(d1)), leaves=int((d1 == level).sum()),
+               result="ok" if ok else "FAILED: leaf colours differ from the oracle fed with the same fragment order")
+    return out
 
 
 def run_reference(args):
@@ -148,10 +194,10 @@ def run_reference(args):
     if rank != 0:
         return
     mesh, level, mode_name = workload(args)
-    # every step is the same bounded sample (~6 s on 16 cores for C4's octant): K steps and up to 2 warm-ups fit the
-    # "few minutes" the contract allows for K <= ~40; beyond the budget the run stops early and reports the steps it timed
-    warm = min(args.warmup, 2)
-    times, leaves, cores, sample = cpu_reference_run(mesh, level, mode_name, max(1, args.steps), warm, budget_s=300.0)
+    # the workload itself (same config as our arm): ~30 s per step for C4 on 16 cores, so one warm-up and as many of the K
+    # steps as fit a 4-minute budget (the line's "steps" says how many were timed)
+    warm = min(args.warmup, 1)
+    times, leaves, cores, sample = cpu_reference_run(mesh, level, mode_name, max(1, args.steps), warm, budget_s=240.0, whole_scene=True)
     sec = float(np.mean(times))
     value = leaves / sec
     line = {
@@ -292,6 +338,30 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
 
+    # -------- N > 1: the stitched tree on rank 0 against a single-GPU build of the same scene (canonical compare) --------
+    stitch = None
+    if not single and world > 1 and not args.no_stitch_check:
+        sh.step(stream)
+        if rank == 0 and level <= 13:
+            from oracle import oracle  # the canonicaliser (checker only)
+            t0 = time.perf_counter()
+            stitched = sh.octree_to_host()
+            sc1 = api.Scene.Create(mesh, device=local_rank, stream=stream, lib=lib)
+            v1 = api.Voxelizer.Create(sc1, level, mode, stream=stream)
+            b1 = api.OctreeBuilder.Create(v1, stream=stream)
+            v1.CmdVoxelize(stream)
+            b1.CmdBuild(stream)
+            whole = b1.octree_to_host(stream)
+            b1.Destroy(), v1.Destroy(), sc1.Destroy()
+            d1, m1, w1 = oracle.canonicalise(stitched, level)
+            d2, m2, w2 = oracle.canonicalise(whole, level)
+            same = len(d1) == len(d2) and (d1 == d2).all() and (m1 == m2).all() and (w1 == w2).all()
+            stitch = {"result": "ok" if same else "FAILED: the stitched tree differs from the single-GPU tree",
+                      "nodes": int(len(d1)), "words_stitched": int(len(stitched)), "words_single": int(len(whole)),
+                      "seconds": round(time.perf_counter() - t0, 1)}
+            del stitched, whole, d1, m1, w1, d2, m2, w2
+        barrier()
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         roofline = None
@@ -314,10 +384,13 @@ def run_ours(args):
                         "launches_per_step": sort_passes, "rank": 0}
             if not single:
                 roofline["traffic"] = None  # the ncu capture is of the single-GPU launch
-        cpu_baseline = None
+        cpu_baseline, parity = None, None
         if single and not args.no_cpu_baseline:
-            times, cl, cores, sample = cpu_reference_run(mesh, level, mode_name, 3, 0, budget_s=25.0)
+            keep = {}
+            times, cl, cores, sample = cpu_reference_run(mesh, level, mode_name, 3, 0, budget_s=25.0, keep=keep)
             cpu_baseline = {"value": cl / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            if level <= 12:
+                parity = parity_check_sample(lib, api, mesh, level, mode, mode_name, local_rank, stream, keep)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -331,7 +404,7 @@ def run_ours(args):
                                       + (f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})" if world > 1 else "")},
             "build_ms": ms_per_step,
             "phases_ms": {k: v / args.steps for k, v in phases_acc.items()} if sort_passes else None,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_check": parity, "stitch_check": stitch,
             "e2e": {"value": leaves / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "note": "host wall clock around pinned-host mesh -> Scene/Voxelizer(count pass)/OctreeBuilder create -> "

@@ -1,6 +1,8 @@
 // The reference loader sequence (src/LoaderThread.cpp:51-116) written against the C++ mirror classes:
 // Scene -> Voxelizer -> OctreeBuilder -> CmdVoxelize + CmdBuild -> Octree::Update, on a small procedural mesh.
-// Prints "fragments leaves_unknown range level root[0..7]"; tests/test_cpp_host.py compares it with the Python path.
+// Prints "fragments range level root[0..7]".  With --mesh <in.bin> <level> <mode> <out.bin> the mesh comes from a file
+// (u64 nv, ni, nd; nv*3 floats; ni u32 indices; nd svo_draw) and the whole node buffer goes to out.bin (u64 fragments,
+// u64 range, words): tests/test_cpp_host.py feeds both hosts the same bytes and compares the buffers word for word.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,21 +28,39 @@ int main(int argc, char **argv) {
 		for (const std::string &t : tex) printf("t %s\n", t.c_str());
 		return 0;
 	}
-	const uint32_t level = argc > 1 ? (uint32_t)atoi(argv[1]) : 7;
+	uint32_t level = argc > 1 ? (uint32_t)atoi(argv[1]) : 7;
 	const int n = argc > 2 ? atoi(argv[2]) : 33;
 	MeshData mesh;
-	for (int i = 0; i < n; ++i)
+	const bool from_file = argc > 5 && std::string(argv[1]) == "--mesh";
+	int mode = SVO_CONSERVATIVE_EXACT;
+	if (from_file) {
+		FILE *f = fopen(argv[2], "rb");
+		if (!f) return 1;
+		uint64_t hdr[3];
+		if (fread(hdr, 8, 3, f) != 3) return 1;
+		std::vector<float> pos(hdr[0] * 3);
+		mesh.indices.resize(hdr[1]);
+		mesh.draws.resize(hdr[2]);
+		if (fread(pos.data(), 4, pos.size(), f) != pos.size() || fread(mesh.indices.data(), 4, hdr[1], f) != hdr[1] ||
+		    fread(mesh.draws.data(), sizeof(svo_draw), hdr[2], f) != hdr[2])
+			return 1;
+		fclose(f);
+		for (uint64_t i = 0; i < hdr[0]; ++i) mesh.vertices.push_back({{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}, {0.f, 0.f}});
+		level = (uint32_t)atoi(argv[3]);
+		mode = atoi(argv[4]);
+	}
+	for (int i = 0; i < n && !from_file; ++i)
 		for (int j = 0; j < n; ++j) {
 			float x = -1.f + 2.f * i / (n - 1), z = -1.f + 2.f * j / (n - 1);
 			float y = 0.4f * std::sin(3.f * x) * std::cos(2.f * z);
 			mesh.vertices.push_back({{x, y, z}, {0.f, 0.f}});
 		}
-	for (int i = 0; i + 1 < n; ++i)
+	for (int i = 0; i + 1 < n && !from_file; ++i)
 		for (int j = 0; j + 1 < n; ++j) {
 			uint32_t a = i * n + j, b = (i + 1) * n + j, c = (i + 1) * n + j + 1, d = i * n + j + 1;
 			for (uint32_t v : {a, b, c, a, c, d}) mesh.indices.push_back(v);
 		}
-	mesh.draws.push_back({0, (uint32_t)mesh.indices.size(), 0xffffffffu, 0x00C83C32u});
+	if (!from_file) mesh.draws.push_back({0, (uint32_t)mesh.indices.size(), 0xffffffffu, 0x00C83C32u});
 
 	if (svo_device_count() < 1) {
 		fprintf(stderr, "no CUDA device\n");
@@ -48,7 +68,7 @@ int main(int argc, char **argv) {
 	}
 	auto scene = Scene::Create(mesh);
 	if (!scene) return 1;
-	auto voxelizer = Voxelizer::Create(scene, level);
+	auto voxelizer = Voxelizer::Create(scene, level, nullptr, mode);
 	if (!voxelizer) return 1;
 	auto builder = OctreeBuilder::Create(voxelizer);
 	if (!builder) return 1;
@@ -65,5 +85,15 @@ int main(int argc, char **argv) {
 	for (uint32_t w : root) printf(" %08x", w);
 	printf("\n");
 	fprintf(stderr, "Octree range: %llu (%f MB)\n", (unsigned long long)octree->GetRange(), octree->GetRange() / 1000000.0f);
+	if (from_file) {
+		std::vector<uint32_t> words(octree->GetRange() / 4);
+		svo_memcpy_d2h(0, words.data(), octree->GetBuffer(), octree->GetRange(), nullptr);
+		FILE *f = fopen(argv[5], "wb");
+		if (!f) return 1;
+		const uint64_t hdr[2] = {voxelizer->GetVoxelFragmentCount(), octree->GetRange()};
+		fwrite(hdr, 8, 2, f);
+		fwrite(words.data(), 4, words.size(), f);
+		fclose(f);
+	}
 	return 0;
 }

@@ -67,17 +67,25 @@ def check_layout_invariants(words, level, level_counts):
     assert int(leaf.sum()) == level_counts[level]
 
 
-def check_against_oracle(lib, mesh, level, mode, shard=None, device=0, stream=None):
+def check_against_oracle(lib, mesh, level, mode, shard=None, device=0, stream=None, window=None):
     """Full-path parity: (1) fragment multiset == oracle voxelizer's; (2) octree built by CUDA ==
     oracle level loop fed with the same fragment order, after Morton canonicalisation (bit exact, colours
-    included); (3) range and layout invariants."""
+    included); (3) range and layout invariants.
+    shard = (shard_level, cube index): one cube of the grid in cube-local coordinates (level - shard_level deep);
+    window = (lo, hi): a half-open voxel box of the whole grid in global coordinates (full level deep) -- how the
+    BASELINE configs that are too large for the CPU oracle are checked piecewise."""
     scene = api.Scene.Create(mesh, device=device, stream=stream, lib=lib)
-    vox = api.Voxelizer.Create(scene, level, mode, shard=shard, stream=stream)
+    if window is not None:
+        vox = api.Voxelizer.CreateWindowed(scene, level, mode, window[0], window[1], stream=stream)
+    else:
+        vox = api.Voxelizer.Create(scene, level, mode, shard=shard, stream=stream)
     builder = api.OctreeBuilder.Create(vox, stream=stream)
     vox.CmdVoxelize(stream)
     frags = vox.fragments_to_host(stream)
     key_level = builder.GetLevel()
     box, origin = None, (0, 0, 0)
+    if window is not None:
+        box = (tuple(int(v) for v in window[0]), tuple(int(v) for v in window[1]))
     if shard is not None:
         sl, ci = shard
         side = 1 << (level - sl)

@@ -41,3 +41,13 @@ def test_device_arm_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] <= d["value"] * 1.001
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
+
+
+@pytest.mark.gpu
+def test_device_arm_parity_check():
+    """The bench compares the oracle tree it computes for cpu_baseline with a CUDA build of the same voxel window."""
+    d = run_bench("--steps", "3", "--warmup", "3", "--workload", "C2")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    pc = d["parity_check"]
+    assert pc["result"] == "ok" and pc["fragments"] > 100_000 and pc["leaves"] > 0
+    assert d["stitch_check"] is None  # single GPU: nothing is stitched

@@ -65,28 +65,24 @@ def test_obj_scene_builds_like_the_oracle():
 
 
 @pytest.mark.gpu
-def test_cpp_loader_matches_python_path():
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cpp_loader_matches_python_path(tmp_path, mode):
+    """The reference's loader sequence written in C++ (tests/cpp/loader_example.cpp over host/svo_host.hpp) and the
+    Python mirror, fed the same mesh bytes: identical fragment count, range and node buffer, word for word."""
     from sparsevoxeloctree_b200 import api, scenes
     exe = build_example()
-    r = subprocess.run([exe, "7", "33"], capture_output=True, text=True, timeout=120)
+    mesh = scenes.random_soup(700, 61, 0.004, 0.9)
+    level = 8
+    fin, fout = tmp_path / "mesh.bin", tmp_path / "tree.bin"
+    with open(fin, "wb") as f:
+        np.array([len(mesh.positions), len(mesh.indices), len(mesh.draws)], np.uint64).tofile(f)
+        np.ascontiguousarray(mesh.positions, np.float32).tofile(f)
+        np.ascontiguousarray(mesh.indices, np.uint32).tofile(f)
+        np.ascontiguousarray(mesh.draws).tofile(f)
+    r = subprocess.run([exe, "--mesh", str(fin), str(level), str(mode), str(fout)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
-    tok = r.stdout.split()
-    frags, rng, level = int(tok[0]), int(tok[1]), int(tok[2])
-    root = [int(t, 16) for t in tok[3:11]]
-    # the same mesh through the Python mirror
-    n = 33
-    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
-    x = (-1.0 + 2.0 * i / (n - 1)).astype(np.float32)
-    z = (-1.0 + 2.0 * j / (n - 1)).astype(np.float32)
-    y = (np.float32(0.4) * np.sin(np.float32(3.0) * x) * np.cos(np.float32(2.0) * z)).astype(np.float32)
-    # the C++ example evaluates sin/cos in float via std::sin(float): compare sizes and the root block shape only
-    pos = np.stack([x, y, z], -1).reshape(-1, 3)
-    a, b, c, d = i[:-1, :-1] * n + j[:-1, :-1], (i[:-1, :-1] + 1) * n + j[:-1, :-1], (i[:-1, :-1] + 1) * n + j[:-1, :-1] + 1, i[:-1, :-1] * n + j[:-1, :-1] + 1
-    idx = np.stack([a, b, c, a, c, d], -1).reshape(-1).astype(np.uint32)
-    draws = np.array([(0, len(idx), 0xFFFFFFFF, 0x00C83C32)], scenes.DRAW_DTYPE)
-    scene, vox, builder = api.build_svo(scenes.Mesh(pos, idx, draws, "cpp"), 7)
-    assert level == 7
-    assert abs(frags - vox.GetVoxelFragmentCount()) <= frags * 0.01
-    assert abs(rng - builder.GetOctreeRange()) <= rng * 0.01
-    proot = builder.octree_to_host()[:8]
-    assert [(w != 0) for w in root] == [(int(w) != 0) for w in proot]
+    hdr = np.fromfile(fout, np.uint64, 2)
+    words = np.fromfile(fout, np.uint32, offset=16)
+    scene, vox, builder = api.build_svo(mesh, level, mode)
+    assert int(hdr[0]) == vox.GetVoxelFragmentCount() and int(hdr[1]) == builder.GetOctreeRange() == 4 * len(words)
+    assert (words == builder.octree_to_host()).all()
