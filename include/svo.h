@@ -255,6 +255,24 @@ SVO_API int svo_ipc_export(int device, void *d_ptr, unsigned char handle[SVO_IPC
 SVO_API int svo_ipc_open(int device, const unsigned char handle[SVO_IPC_HANDLE_BYTES], void **out);
 SVO_API int svo_ipc_close(int device, void *d_ptr);
 
+/* ---- hand-off to Vulkan: the node buffer as an external-memory file descriptor -------------------------------
+ * What Octree::Update (src/Octree.cpp:22-35) takes from OctreeBuilder::GetOctree() (src/OctreeBuilder.hpp:43) is a
+ * myvk::Buffer; a CUDA-built tree reaches the unmodified OctreeTracer / PathTracer through VK_KHR_external_memory_fd.
+ * svo_builder_export_fd puts the node words of a prepared (svo_builder_prepare) or built builder into memory
+ * allocated with cuMemCreate(CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) -- a prepared builder emits straight into it,
+ * no copy -- and returns a file descriptor (cuMemExportToShareableHandle) plus the allocation size (the range rounded
+ * up to the allocation granularity: the size vkAllocateMemory must be given).  The Vulkan side imports it with
+ * VkImportMemoryFdInfoKHR{handleType = OPAQUE_FD} (INTEGRATION.md has the myvk::BufferBase subclass); the import takes
+ * the descriptor over, otherwise the caller closes it.  The memory stays alive until svo_builder_destroy and every
+ * importer has released it.  *d_ptr (may be NULL) receives the CUDA address of the exported buffer. */
+SVO_API int svo_builder_export_fd(svo_builder *b, int *fd, uint64_t *alloc_size, const uint32_t **d_ptr, void *stream);
+/* The importing side restated in CUDA, for verification without a Vulkan driver: maps `size` bytes of an exported
+ * descriptor (cudaImportExternalMemory + cudaExternalMemoryGetMappedBuffer -- the calls a CUDA consumer of a Vulkan
+ * allocation makes; where the driver refuses a CUDA-exported descriptor there, cuMemImportFromShareableHandle).
+ * Returns 1 / 2 for the path that mapped it, or a negative svo_status.  The import consumes the descriptor. */
+SVO_API int svo_external_memory_import_fd(int device, int fd, uint64_t size, void **import_handle, void **d_ptr);
+SVO_API int svo_external_memory_release(int device, void *import_handle);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,9 @@ SYMBOLS = [
     ("svo_ipc_export", C.c_int, [C.c_int, _P, C.c_char_p]),
     ("svo_ipc_open", C.c_int, [C.c_int, C.c_char_p, C.POINTER(_P)]),
     ("svo_ipc_close", C.c_int, [C.c_int, _P]),
+    ("svo_builder_export_fd", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(_P), _P]),
+    ("svo_external_memory_import_fd", C.c_int, [C.c_int, C.c_int, C.c_uint64, C.POINTER(_P), C.POINTER(_P)]),
+    ("svo_external_memory_release", C.c_int, [C.c_int, _P]),
 ]
 
 
@@ -457,6 +460,12 @@ class OctreeBuilder:
         if n < 0:
             self.lib.check(n)
         return [float(out[i]) for i in range(n)]
+
+    def ExportFd(self, stream=None):
+        """The node buffer as a VK_KHR_external_memory_fd-importable file descriptor: (fd, allocation size, CUDA address)."""
+        fd, size, ptr = C.c_int(-1), C.c_uint64(0), _P()
+        self.lib.check(self.lib.dll.svo_builder_export_fd(self._h, C.byref(fd), C.byref(size), C.byref(ptr), _stream_ptr(stream)))
+        return fd.value, int(size.value), int(ptr.value or 0)
 
     def RebaseCopy(self, d_dst: int, dst_word_offset: int, base_words: int, stream=None):
         self.lib.check(self.lib.dll.svo_builder_rebase_copy(self._h, d_dst, dst_word_offset, base_words, _stream_ptr(stream)))

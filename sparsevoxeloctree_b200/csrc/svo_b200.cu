@@ -7,6 +7,11 @@
 
 #include <stdarg.h>
 
+#ifndef SVO_EMU
+#include <cuda.h> // driver API types; the entry points are looked up at run time (no link dependency on libcuda)
+#include <unistd.h>
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -152,6 +157,8 @@ struct svo_builder {
 	bool emitted = false;   // svo_builder_emit_to has run after the last prepare (phase times are complete)
 	EmitParams ep{};
 	DevBuf<uint32_t> root_scratch; // svo_builder_emit_to(skip_root): the root block goes here
+	// svo_builder_export_fd: the node words in exportable (cuMemCreate) memory
+	unsigned long long export_va = 0, export_handle = 0, export_size = 0;
 	cudaEvent_t ev[SVO_PHASE_COUNT + 1] = {};
 };
 
@@ -234,6 +241,78 @@ static int upload_textures(svo_scene *sc, const svo_mesh *mesh, cudaStream_t s) 
 	return SVO_OK;
 }
 
+// ---- exportable memory (driver API virtual memory management, entry points resolved through the runtime) ----------
+#ifndef SVO_EMU
+namespace {
+template <class F> F driver_fn(const char *name) {
+	void *p = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+	return reinterpret_cast<F>(p);
+}
+struct Vmm {
+	CUresult (*granularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+	CUresult (*create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+	CUresult (*reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+	CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+	CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+	CUresult (*export_handle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+	CUresult (*import_handle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+	CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+	CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+	CUresult (*address_free)(CUdeviceptr, size_t) = nullptr;
+	bool ok = false;
+	Vmm() {
+		granularity = driver_fn<decltype(granularity)>("cuMemGetAllocationGranularity");
+		create = driver_fn<decltype(create)>("cuMemCreate");
+		reserve = driver_fn<decltype(reserve)>("cuMemAddressReserve");
+		map = driver_fn<decltype(map)>("cuMemMap");
+		set_access = driver_fn<decltype(set_access)>("cuMemSetAccess");
+		export_handle = driver_fn<decltype(export_handle)>("cuMemExportToShareableHandle");
+		import_handle = driver_fn<decltype(import_handle)>("cuMemImportFromShareableHandle");
+		unmap = driver_fn<decltype(unmap)>("cuMemUnmap");
+		release = driver_fn<decltype(release)>("cuMemRelease");
+		address_free = driver_fn<decltype(address_free)>("cuMemAddressFree");
+		ok = granularity && create && reserve && map && set_access && export_handle && import_handle && unmap && release && address_free;
+	}
+};
+const Vmm &vmm() {
+	static Vmm v;
+	return v;
+}
+CUmemAllocationProp export_prop(int device) {
+	CUmemAllocationProp prop{};
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	prop.location.id = device;
+	prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+	return prop;
+}
+} // namespace
+static void release_export(svo_builder *b) {
+	if (!b->export_va) return;
+	const Vmm &v = vmm();
+	cudaStreamSynchronize(b->last_stream);
+	v.unmap((CUdeviceptr)b->export_va, b->export_size);
+	v.release((CUmemGenericAllocationHandle)b->export_handle);
+	v.address_free((CUdeviceptr)b->export_va, b->export_size);
+	b->export_va = b->export_handle = b->export_size = 0;
+}
+#else
+static void release_export(svo_builder *) {}
+#endif
+
+#ifndef SVO_EMU
+namespace {
+struct ImportedMemory {
+	int path = 0; // 1: cudaImportExternalMemory, 2: cuMemImportFromShareableHandle
+	cudaExternalMemory_t ext = nullptr;
+	CUmemGenericAllocationHandle handle = 0;
+	CUdeviceptr va = 0;
+	size_t size = 0;
+};
+} // namespace
+#endif
 extern "C" {
 
 const char *svo_last_error(void) { return get_error(); }
@@ -689,6 +768,7 @@ void svo_builder_destroy(svo_builder *b) {
 	b->rf_cnt01.release(s), b->rf_cnt2.release(s), b->rf_pre01.release(s), b->rf_pre2.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+	release_export(b);
 	delete b;
 }
 
@@ -891,6 +971,129 @@ int svo_builder_last_ms(svo_builder *b, float *phase_ms, uint32_t *sort_passes) 
 	for (int i = 0; i < 5; ++i) SVO_CUDA_TRY(cudaEventElapsedTime(&phase_ms[SVO_PHASE_SORT_HIST + i], b->ev[i], b->ev[i + 1]));
 	if (sort_passes) *sort_passes = b->sort_passes;
 	return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_root, cudaStream_t s);
+int svo_builder_export_fd(svo_builder *b, int *fd, uint64_t *alloc_size, const uint32_t **d_ptr, void *stream) {
+	if (!b || !fd || !alloc_size) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_export_fd: null argument");
+	if (!b->prepared && !b->built) return fail(SVO_ERR_NOT_READY, "svo_builder_export_fd: prepare or build first");
+#ifdef SVO_EMU
+	(void)d_ptr, (void)stream;
+	return fail(SVO_ERR_UNSUPPORTED, "no external memory in the emulation build");
+#else
+	DeviceGuard guard(b->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	b->last_stream = s;
+	const Vmm &v = vmm();
+	if (!v.ok) return fail(SVO_ERR_UNSUPPORTED, "the CUDA driver lacks the virtual memory management entry points");
+	release_export(b);
+	const CUmemAllocationProp prop = export_prop(b->device);
+	size_t gran = 0;
+	if (v.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+		return fail(SVO_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+	const size_t size = (b->range_bytes + gran - 1) / gran * gran;
+	CUmemGenericAllocationHandle h = 0;
+	CUdeviceptr va = 0;
+	if (v.create(&h, size, &prop, 0) != CUDA_SUCCESS) return fail(SVO_ERR_CUDA, "cuMemCreate (exportable allocation) failed");
+	if (v.reserve(&va, size, 0, 0, 0) != CUDA_SUCCESS) {
+		v.release(h);
+		return fail(SVO_ERR_CUDA, "cuMemAddressReserve failed");
+	}
+	CUmemAccessDesc acc{};
+	acc.location = prop.location;
+	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	if (v.map(va, size, 0, h, 0) != CUDA_SUCCESS || v.set_access(va, size, &acc, 1) != CUDA_SUCCESS) {
+		v.release(h);
+		v.address_free(va, size);
+		return fail(SVO_ERR_CUDA, "cuMemMap / cuMemSetAccess failed");
+	}
+	b->export_va = va, b->export_handle = h, b->export_size = size;
+	uint32_t *dst = reinterpret_cast<uint32_t *>(va);
+	if (b->built) // already emitted into the builder's own buffer: one device copy
+		SVO_CUDA_TRY(cudaMemcpyAsync(dst, b->octree.p, b->range_bytes, cudaMemcpyDeviceToDevice, s));
+	else { // prepared: the emit kernel writes the exported memory directly
+		SVO_TRY(emit_into(b, dst, 0, 0, s));
+		SVO_CUDA_TRY(cudaEventRecord(b->ev[5], s));
+		b->emitted = true;
+	}
+	if (size > b->range_bytes) SVO_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<unsigned char *>(dst) + b->range_bytes, 0, size - b->range_bytes, s));
+	SVO_CUDA_TRY(cudaStreamSynchronize(s)); // the importer may read as soon as it holds the descriptor
+	int out_fd = -1;
+	if (v.export_handle(&out_fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS || out_fd < 0)
+		return fail(SVO_ERR_CUDA, "cuMemExportToShareableHandle failed");
+	*fd = out_fd, *alloc_size = size;
+	if (d_ptr) *d_ptr = dst;
+	return SVO_OK;
+#endif
+}
+
+int svo_external_memory_import_fd(int device, int fd, uint64_t size, void **import_handle, void **d_ptr) {
+	if (!import_handle || !d_ptr || fd < 0 || size == 0) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_external_memory_import_fd: bad argument");
+#ifdef SVO_EMU
+	(void)device;
+	return fail(SVO_ERR_UNSUPPORTED, "no external memory in the emulation build");
+#else
+	DeviceGuard guard(device);
+	if (!guard.ok) return fail(SVO_ERR_CUDA, "cudaSetDevice failed");
+	ImportedMemory *im = new (std::nothrow) ImportedMemory();
+	if (!im) return fail(SVO_ERR_CUDA, "out of host memory");
+	im->size = size;
+	// what a CUDA consumer of a Vulkan allocation does (and the mirror image of vkImportMemoryFdKHR on this descriptor)
+	cudaExternalMemoryHandleDesc hd{};
+	hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+	hd.handle.fd = dup(fd); // a successful import owns its descriptor; keep ours for the second path
+	hd.size = size;
+	void *ptr = nullptr;
+	if (cudaImportExternalMemory(&im->ext, &hd) == cudaSuccess) {
+		cudaExternalMemoryBufferDesc bd{};
+		bd.offset = 0, bd.size = size;
+		if (cudaExternalMemoryGetMappedBuffer(&ptr, im->ext, &bd) == cudaSuccess) {
+			im->path = 1;
+			close(fd);
+			*import_handle = im, *d_ptr = ptr;
+			return 1;
+		}
+		cudaDestroyExternalMemory(im->ext);
+		im->ext = nullptr;
+	} else
+		close(hd.handle.fd);
+	(void)cudaGetLastError();
+	const Vmm &v = vmm();
+	CUmemAccessDesc acc{};
+	acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE, acc.location.id = device;
+	acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	if (v.ok && v.import_handle(&im->handle, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS &&
+	    v.reserve(&im->va, size, 0, 0, 0) == CUDA_SUCCESS && v.map(im->va, size, 0, im->handle, 0) == CUDA_SUCCESS &&
+	    v.set_access(im->va, size, &acc, 1) == CUDA_SUCCESS) {
+		im->path = 2;
+		close(fd);
+		*import_handle = im, *d_ptr = reinterpret_cast<void *>(im->va);
+		return 2;
+	}
+	delete im;
+	return fail(SVO_ERR_CUDA, "neither cudaImportExternalMemory nor cuMemImportFromShareableHandle accepted the descriptor");
+#endif
+}
+int svo_external_memory_release(int device, void *import_handle) {
+	if (!import_handle) return SVO_OK;
+#ifdef SVO_EMU
+	(void)device;
+	return SVO_OK;
+#else
+	DeviceGuard guard(device);
+	ImportedMemory *im = static_cast<ImportedMemory *>(import_handle);
+	if (im->path == 1)
+		cudaDestroyExternalMemory(im->ext);
+	else if (im->path == 2) {
+		const Vmm &v = vmm();
+		v.unmap(im->va, im->size);
+		v.release(im->handle);
+		v.address_free(im->va, im->size);
+	}
+	delete im;
+	return SVO_OK;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -350,3 +350,38 @@ def test_slab_split_emit_to_assembles_the_whole_tree(lib, world):
     assert total * 4 == builder.GetOctreeRange()   # same node count: the split adds no blocks
     assert sum(v.GetVoxelFragmentCount() for v, _ in parts) == vox.GetVoxelFragmentCount()
     lib.free(arena)
+
+
+def test_export_fd_roundtrip(lib):
+    """Row f1 (src/Octree.cpp:22-35 takes the builder's buffer): the node words in exportable memory, handed over as a
+    file descriptor the way VK_KHR_external_memory_fd takes it, re-imported and compared with the builder's own buffer.
+    Both a prepared builder (the emit kernel writes the exported memory directly) and a built one (device copy)."""
+    import ctypes as C
+    import os
+    from tests.parity import assert_same_tree
+    mesh = scenes.random_soup(500, 91, 0.01, 1.0)
+    level = 8
+    scene, vox, built = api.build_svo(mesh, level, api.CONSERVATIVE_EXACT, lib=lib)
+    ref_words = built.octree_to_host()
+    for prepared_only in (True, False):
+        v = api.Voxelizer.Create(scene, level, api.CONSERVATIVE_EXACT)
+        b = api.OctreeBuilder.Create(v)
+        v.CmdVoxelize()
+        if prepared_only:
+            b.Prepare()
+        else:
+            b.CmdBuild()
+        fd, size, d_ptr = b.ExportFd()
+        assert fd >= 0 and size >= b.GetOctreeRange() and size % 4096 == 0 and d_ptr
+        assert os.fstat(fd).st_mode  # a live descriptor
+        own = lib.to_host(d_ptr, np.uint32, b.GetOctreeRange() // 4)
+        assert (own == ref_words).all()
+        handle, mapped = C.c_void_p(), C.c_void_p()
+        path = lib.dll.svo_external_memory_import_fd(0, fd, size, C.byref(handle), C.byref(mapped))
+        assert path in (1, 2), lib.dll.svo_last_error()
+        imported = lib.to_host(mapped.value, np.uint32, size // 4)
+        assert (imported[: len(ref_words)] == ref_words).all() and not imported[len(ref_words):].any()
+        assert_same_tree(imported[: len(ref_words)], ref_words, level)
+        lib.check(lib.dll.svo_external_memory_release(0, handle))
+        print(f"export_fd: {size} bytes, imported through path {path} (1 = cudaImportExternalMemory, 2 = cuMemImportFromShareableHandle)")
+        b.Destroy(), v.Destroy()
