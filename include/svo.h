@@ -273,6 +273,25 @@ SVO_API int svo_builder_export_fd(svo_builder *b, int *fd, uint64_t *alloc_size,
 SVO_API int svo_external_memory_import_fd(int device, int fd, uint64_t size, void **import_handle, void **d_ptr);
 SVO_API int svo_external_memory_release(int device, void *import_handle);
 
+/* ---- the whole loader sequence on several GPUs of one process ------------------------------------------------
+ * svo_build_sharded replaces, for a C/C++ host, the reference's single-device sequence Scene::Create ->
+ * Voxelizer::Create -> OctreeBuilder::Create -> CmdVoxelize + CmdBuild (src/LoaderThread.cpp:51-89) by the
+ * octant-sharded build of SURVEY.md section 8e: the mesh (host memory) is uploaded to every device, device k
+ * voxelizes and builds the subtrees of its octants (x / xy / xyz split for 2 / 4 / 8 devices), and the node words
+ * are stored over NVLink peer access into ONE buffer on devices[0], stitched under a shared root -- the buffer
+ * Octree::Update would take.  Synchronous.  n_devices = 1, 2, 4 or 8 (a device may be listed more than once);
+ * level 14 is built as 8 cube-local level-13 octants.  The stitched tree must stay below 2^30 words. */
+typedef struct svo_sharded svo_sharded;
+SVO_API int svo_build_sharded(const svo_mesh *mesh, uint32_t level, int mode, const int *devices, uint32_t n_devices,
+                              svo_sharded **out);
+SVO_API int svo_sharded_rebuild(svo_sharded *sh); /* voxelize + build + stitch again (same scene, same buffers) */
+SVO_API const uint32_t *svo_sharded_octree(const svo_sharded *sh);       /* DEVICE pointer on devices[0] */
+SVO_API uint64_t svo_sharded_octree_range_bytes(const svo_sharded *sh);
+SVO_API uint64_t svo_sharded_leaf_count(const svo_sharded *sh);
+SVO_API uint64_t svo_sharded_fragment_count(const svo_sharded *sh);
+SVO_API float svo_sharded_last_ms(const svo_sharded *sh);                /* host wall clock of the last build + stitch */
+SVO_API void svo_sharded_destroy(svo_sharded *sh);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,14 @@ SYMBOLS = [
     ("svo_ipc_export", C.c_int, [C.c_int, _P, C.c_char_p]),
     ("svo_ipc_open", C.c_int, [C.c_int, C.c_char_p, C.POINTER(_P)]),
     ("svo_ipc_close", C.c_int, [C.c_int, _P]),
+    ("svo_build_sharded", C.c_int, [C.POINTER(svo_mesh), C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_uint32, C.POINTER(_P)]),
+    ("svo_sharded_rebuild", C.c_int, [_P]),
+    ("svo_sharded_octree", _P, [_P]),
+    ("svo_sharded_octree_range_bytes", C.c_uint64, [_P]),
+    ("svo_sharded_leaf_count", C.c_uint64, [_P]),
+    ("svo_sharded_fragment_count", C.c_uint64, [_P]),
+    ("svo_sharded_last_ms", C.c_float, [_P]),
+    ("svo_sharded_destroy", None, [_P]),
     ("svo_builder_export_fd", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(_P), _P]),
     ("svo_external_memory_import_fd", C.c_int, [C.c_int, C.c_int, C.c_uint64, C.POINTER(_P), C.POINTER(_P)]),
     ("svo_external_memory_release", C.c_int, [C.c_int, _P]),
@@ -476,6 +484,62 @@ class OctreeBuilder:
     def Destroy(self):
         if self._h:
             self.lib.dll.svo_builder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Destroy()
+        except Exception:
+            pass
+
+
+class ShardedBuild:
+    """svo_build_sharded: the whole loader sequence on several GPUs of this process (include/svo.h); the stitched node
+    buffer lives on devices[0]."""
+
+    def __init__(self):
+        self._h = None
+
+    @staticmethod
+    def Create(mesh, level: int, mode: int = CONSERVATIVE_EXACT, devices=(0,), lib: Library | None = None):
+        self = ShardedBuild()
+        self.lib, self.devices, self.level = lib or get_library(), list(devices), level
+        pos = np.ascontiguousarray(mesh.positions, dtype=np.float32)
+        idx = np.ascontiguousarray(mesh.indices, dtype=np.uint32)
+        d = np.ascontiguousarray(mesh.draws)
+        draws = (svo_draw * len(d))(*[svo_draw(int(r["first_index"]), int(r["index_count"]), int(r["texture_id"]), int(r["albedo_rgba8"]))
+                                      for r in d])
+        m = svo_mesh(pos.ctypes.data, pos.shape[1] * 4, 0, idx.ctypes.data, len(pos), len(idx), draws, len(d))
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        h = _P()
+        self.lib.check(self.lib.dll.svo_build_sharded(C.byref(m), level, mode, devs, len(self.devices), C.byref(h)))
+        self._h = h
+        return self
+
+    def Rebuild(self):
+        self.lib.check(self.lib.dll.svo_sharded_rebuild(self._h))
+
+    def GetOctree(self) -> int:
+        return int(self.lib.dll.svo_sharded_octree(self._h) or 0)
+
+    def GetOctreeRange(self) -> int:
+        return int(self.lib.dll.svo_sharded_octree_range_bytes(self._h))
+
+    def GetLeafCount(self) -> int:
+        return int(self.lib.dll.svo_sharded_leaf_count(self._h))
+
+    def GetVoxelFragmentCount(self) -> int:
+        return int(self.lib.dll.svo_sharded_fragment_count(self._h))
+
+    def LastMs(self) -> float:
+        return float(self.lib.dll.svo_sharded_last_ms(self._h))
+
+    def octree_to_host(self) -> np.ndarray:
+        return self.lib.to_host(self.GetOctree(), np.uint32, self.GetOctreeRange() // 4, self.devices[0])
+
+    def Destroy(self):
+        if self._h:
+            self.lib.dll.svo_sharded_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -13,8 +13,10 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "build.cuh"
@@ -1221,3 +1223,5 @@ SVO_API void svo_emu_set_lookback_aggregate_only(int on) { svo::g_emu_lookback_a
 #endif
 
 } // extern "C"
+
+#include "sharded.inl"

@@ -66,6 +66,36 @@ int main(int argc, char **argv) {
 		fprintf(stderr, "no CUDA device\n");
 		return 2;
 	}
+	if (from_file && getenv("SVO_DEVICES")) { // the same mesh through svo_build_sharded on the listed devices ("0,1,2,3")
+		std::vector<int> devices;
+		for (const char *p = getenv("SVO_DEVICES"); *p;) {
+			devices.push_back(atoi(p));
+			while (*p && *p != ',') ++p;
+			if (*p == ',') ++p;
+		}
+		svo_mesh m{};
+		m.positions = mesh.vertices.data(), m.position_stride_bytes = sizeof(Vertex);
+		m.indices = mesh.indices.data(), m.n_vertices = mesh.vertices.size(), m.n_indices = mesh.indices.size();
+		m.draws = mesh.draws.data(), m.n_draws = (uint32_t)mesh.draws.size();
+		svo_sharded *sh = nullptr;
+		if (svo_build_sharded(&m, level, mode, devices.data(), (uint32_t)devices.size(), &sh) != SVO_OK) {
+			fprintf(stderr, "svo_build_sharded: %s\n", svo_last_error());
+			return 1;
+		}
+		const uint64_t range = svo_sharded_octree_range_bytes(sh);
+		std::vector<uint32_t> words(range / 4);
+		svo_memcpy_d2h(devices[0], words.data(), svo_sharded_octree(sh), range, nullptr);
+		printf("%llu %llu %u sharded x%zu %.3f ms\n", (unsigned long long)svo_sharded_fragment_count(sh), (unsigned long long)range, level,
+		       devices.size(), svo_sharded_last_ms(sh));
+		FILE *f = fopen(argv[5], "wb");
+		if (!f) return 1;
+		const uint64_t hdr[2] = {svo_sharded_fragment_count(sh), range};
+		fwrite(hdr, 8, 2, f);
+		fwrite(words.data(), 4, words.size(), f);
+		fclose(f);
+		svo_sharded_destroy(sh);
+		return 0;
+	}
 	auto scene = Scene::Create(mesh);
 	if (!scene) return 1;
 	auto voxelizer = Voxelizer::Create(scene, level, nullptr, mode);

@@ -86,3 +86,32 @@ def test_cpp_loader_matches_python_path(tmp_path, mode):
     scene, vox, builder = api.build_svo(mesh, level, mode)
     assert int(hdr[0]) == vox.GetVoxelFragmentCount() and int(hdr[1]) == builder.GetOctreeRange() == 4 * len(words)
     assert (words == builder.octree_to_host()).all()
+
+
+@pytest.mark.gpu
+def test_cpp_host_builds_sharded_over_all_gpus(tmp_path):
+    """A C++ host calls svo_build_sharded (one process, every GPU of the box -- or GPU 0 twice when there is only one):
+    the stitched tree is canonically the single-GPU tree."""
+    from sparsevoxeloctree_b200 import api, scenes
+    from tests.parity import assert_same_tree
+    exe = build_example()
+    lib = api.get_library()
+    n = lib.dll.svo_device_count()
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    devices = ",".join(str(k % n) for k in range(world))
+    mesh = scenes.random_soup(900, 62, 0.004, 0.9)
+    level = 9
+    fin, fout = tmp_path / "mesh.bin", tmp_path / "tree.bin"
+    with open(fin, "wb") as f:
+        np.array([len(mesh.positions), len(mesh.indices), len(mesh.draws)], np.uint64).tofile(f)
+        np.ascontiguousarray(mesh.positions, np.float32).tofile(f)
+        np.ascontiguousarray(mesh.indices, np.uint32).tofile(f)
+        np.ascontiguousarray(mesh.draws).tofile(f)
+    env = dict(os.environ, SVO_DEVICES=devices)
+    r = subprocess.run([exe, "--mesh", str(fin), str(level), "1", str(fout)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    hdr = np.fromfile(fout, np.uint64, 2)
+    words = np.fromfile(fout, np.uint32, offset=16)
+    scene, vox, builder = api.build_svo(mesh, level, 1)
+    assert int(hdr[0]) == vox.GetVoxelFragmentCount() and int(hdr[1]) == builder.GetOctreeRange()
+    assert_same_tree(words, builder.octree_to_host(), level)

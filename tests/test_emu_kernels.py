@@ -188,3 +188,15 @@ def test_index_out_of_range_is_rejected(emu):
     with pytest.raises(api.SvoError) as e:
         api.Scene.Create(mesh.positions, bad, mesh.draws, lib=emu)
     assert e.value.code == -1  # SVO_ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("n_dev", [2, 8])
+def test_build_sharded_c_abi_logic(emu, n_dev):
+    """svo_build_sharded's host logic (slab windows, offsets, emit into one buffer, merged root) on the emulator."""
+    from tests.parity import assert_same_tree
+    mesh = scenes.random_soup(200, 17, 0.02, 0.9)
+    sh = api.ShardedBuild.Create(mesh, 6, api.CONSERVATIVE_EXACT, devices=[0] * n_dev, lib=emu)
+    _, vox, builder = api.build_svo(mesh, 6, api.CONSERVATIVE_EXACT, lib=emu)
+    assert sh.GetOctreeRange() == builder.GetOctreeRange() and sh.GetLeafCount() == builder.GetLeafCount()
+    assert_same_tree(sh.octree_to_host(), builder.octree_to_host(), 6)
+    sh.Destroy()

@@ -385,3 +385,34 @@ def test_export_fd_roundtrip(lib):
         lib.check(lib.dll.svo_external_memory_release(0, handle))
         print(f"export_fd: {size} bytes, imported through path {path} (1 = cudaImportExternalMemory, 2 = cuMemImportFromShareableHandle)")
         b.Destroy(), v.Destroy()
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_build_sharded_c_abi_on_one_device(lib, n_dev):
+    """svo_build_sharded (the multi-GPU build behind the C ABI) with every 'device' = GPU 0: the slab split, the emit into
+    one stitched buffer and the merged root must give the single-build tree, canonically, colours included."""
+    from tests.parity import assert_same_tree
+    mesh = scenes.random_soup(600, 52, 0.01, 1.2)
+    level, mode = 8, api.CONSERVATIVE_EXACT
+    sh = api.ShardedBuild.Create(mesh, level, mode, devices=[0] * n_dev, lib=lib)
+    _, vox, builder = api.build_svo(mesh, level, mode, lib=lib)
+    assert sh.GetOctreeRange() == builder.GetOctreeRange()
+    assert sh.GetLeafCount() == builder.GetLeafCount() and sh.GetVoxelFragmentCount() == vox.GetVoxelFragmentCount()
+    assert_same_tree(sh.octree_to_host(), builder.octree_to_host(), level)
+    sh.Rebuild()  # same buffers again
+    assert_same_tree(sh.octree_to_host(), builder.octree_to_host(), level)
+    sh.Destroy()
+
+
+def test_build_sharded_c_abi_level14(lib):
+    """Level 14 through svo_build_sharded: 8 cube-local level-13 octant builds, rebased into one buffer."""
+    from oracle import oracle
+    mesh = scenes.random_soup(300, 77, 0.0005, 0.01)
+    sh = api.ShardedBuild.Create(mesh, 14, api.CONSERVATIVE_EXACT, devices=[0, 0], lib=lib)
+    fr = oracle.voxelize(mesh.positions, mesh.indices, mesh.draws, 14, oracle.CONSERVATIVE_EXACT)
+    assert len(fr) == sh.GetVoxelFragmentCount()
+    ow, _ = oracle.build_octree(fr, 14, cap_words=8 * (1 + len(fr) * 13))
+    d1, m1, w1 = oracle.canonicalise(sh.octree_to_host(), 14)
+    d2, m2, w2 = oracle.canonicalise(ow, 14)
+    assert (d1 == d2).all() and (m1 == m2).all() and ((w1 >> 24) == (w2 >> 24)).all()
+    sh.Destroy()
