@@ -383,8 +383,8 @@ def run_ours(args):
         roofline = None
         if sort_passes and phases_acc["sort_passes"] > 0:
             per_launch_ms = phases_acc["sort_passes"] / args.steps / sort_passes
-            # one read + one write of every 8-byte fragment per onesweep pass (N > 1: the fragments of rank 0's slab)
-            alg_bytes = 16.0 * (frags if single else sh.fragment_count_local())
+            # one read + one write of every 8-byte fragment per onesweep pass (N > 1: the fragments of rank 0's first part)
+            alg_bytes = 16.0 * (frags if single else sh.vox[0].GetVoxelFragmentCount())
             achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")

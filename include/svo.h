@@ -174,10 +174,16 @@ SVO_API int svo_builder_build(svo_builder *b, void *stream);
  *                          skip_root = 1: blocks 1.. are written from d_dst[0] on with pointers already valid for a
  *                          buffer in which d_dst sits at word offset pointer_bias_words; the 8 root words are kept
  *                          aside (svo_builder_root_words) so that the caller can merge several subtrees' roots.
+ *                          skip_root = 2: the same one level deeper -- the root block AND the depth-1 blocks (1 + N_1
+ *                          blocks, N_1 = level_counts[1] <= 8) are kept aside (svo_builder_top_words; the depth-1 blocks
+ *                          follow the root's non-empty slots in order), blocks 1 + N_1 .. are written from d_dst[0] on.
+ *                          Parts of the grid cut at depth-2 cell borders can then be built separately (several per GPU,
+ *                          emitted while the next one is being built) and their top blocks summed.
  * This is the fused "emit + transfer": the kernel that produces the words stores them across NVLink. */
 SVO_API int svo_builder_prepare(svo_builder *b, void *stream);
 SVO_API int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *stream);
 SVO_API int svo_builder_root_words(svo_builder *b, uint32_t out[8], void *stream);
+SVO_API int svo_builder_top_words(svo_builder *b, uint32_t out[72], uint32_t *n_blocks, void *stream);
 SVO_API uint32_t svo_builder_level(const svo_builder *b); /* OctreeBuilder::GetLevel */
 /* OctreeBuilder::GetOctreeRange (src/OctreeBuilder.hpp:42, src/OctreeBuilder.cpp:212-214): bytes. */
 SVO_API uint64_t svo_builder_octree_range_bytes(const svo_builder *b);

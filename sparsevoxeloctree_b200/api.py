@@ -81,6 +81,7 @@ SYMBOLS = [
     ("svo_builder_prepare", C.c_int, [_P, _P]),
     ("svo_builder_emit_to", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
     ("svo_builder_root_words", C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
+    ("svo_builder_top_words", C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
     ("svo_builder_level", C.c_uint32, [_P]),
     ("svo_builder_octree_range_bytes", C.c_uint64, [_P]),
     ("svo_builder_octree", _P, [_P]),
@@ -426,9 +427,16 @@ class OctreeBuilder:
         """Phase 1 of CmdBuild: everything but the node-word emission; sizes are known afterwards."""
         self.lib.check(self.lib.dll.svo_builder_prepare(self._h, _stream_ptr(stream)))
 
-    def EmitTo(self, d_dst: int, pointer_bias_words: int = 0, skip_root: bool = False, stream=None):
-        """Phase 2: write the node words into caller-provided device memory (possibly a peer GPU's)."""
-        self.lib.check(self.lib.dll.svo_builder_emit_to(self._h, d_dst, pointer_bias_words, 1 if skip_root else 0, _stream_ptr(stream)))
+    def EmitTo(self, d_dst: int, pointer_bias_words: int = 0, skip_root=False, stream=None):
+        """Phase 2: write the node words into caller-provided device memory (possibly a peer GPU's).
+        skip_root: False / True, or 2 to keep the root block and the depth-1 blocks aside (TopWords)."""
+        self.lib.check(self.lib.dll.svo_builder_emit_to(self._h, d_dst, pointer_bias_words, int(skip_root), _stream_ptr(stream)))
+
+    def TopWords(self, stream=None) -> np.ndarray:
+        """The blocks kept aside by EmitTo(skip_root=1 or 2): uint32 [n_blocks, 8], the root block first."""
+        out, n = (C.c_uint32 * 72)(), C.c_uint32()
+        self.lib.check(self.lib.dll.svo_builder_top_words(self._h, out, C.byref(n), _stream_ptr(stream)))
+        return np.array(list(out), dtype=np.uint32)[: 8 * n.value].reshape(n.value, 8)
 
     def RootWords(self, stream=None) -> np.ndarray:
         out = (C.c_uint32 * 8)()

@@ -314,8 +314,9 @@ struct EmitParams {
 	const unsigned char *slot[MAX_LEVEL + 1]; // [d]: per depth-d node, its child slot
 	const uint32_t *leaf;                     // leaf words of the depth-`level` nodes
 	// placement: block g is written at words[(g - block_shift) * 8]; a child pointer to block c is
-	// (c - block_shift) * 8 + ptr_bias.  block_shift = 1 sends the root block (g = 0) to root_dst instead, so a
-	// subtree can be emitted straight into a larger (possibly peer-GPU) buffer at word offset ptr_bias.
+	// (c - block_shift) * 8 + ptr_bias.  block_shift > 0 sends the first block_shift blocks (the root block, or the root
+	// block and the depth-1 blocks) to root_dst instead, so that a subtree can be emitted straight into a larger (possibly
+	// peer-GPU) buffer at word offset ptr_bias and its top blocks merged with those of other subtrees.
 	uint32_t block_shift, ptr_bias;
 	uint32_t *root_dst;
 };
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(EMITO_BLOCK) k_emit_octree(EmitParams ep, uint
 			}
 		}
 	}
-	if (ep.block_shift && g == 0) { // the root block of a subtree that is stitched elsewhere
-		uint4 *r = reinterpret_cast<uint4 *>(ep.root_dst);
+	if (g < ep.block_shift) { // a top block of a subtree that is stitched elsewhere
+		uint4 *r = reinterpret_cast<uint4 *>(ep.root_dst + g * 8);
 		r[0] = make_uint4(w[0], w[1], w[2], w[3]);
 		r[1] = make_uint4(w[4], w[5], w[6], w[7]);
 	}

@@ -158,7 +158,8 @@ struct svo_builder {
 	bool prepared = false;  // sort / reduce / levels done, sizes known: ready for an emit
 	bool emitted = false;   // svo_builder_emit_to has run after the last prepare (phase times are complete)
 	EmitParams ep{};
-	DevBuf<uint32_t> root_scratch; // svo_builder_emit_to(skip_root): the root block goes here
+	DevBuf<uint32_t> root_scratch; // svo_builder_emit_to(skip_root): the top blocks go here
+	uint32_t top_blocks = 0;       // how many (1, or 1 + depth-1 nodes)
 	// svo_builder_export_fd: the node words in exportable (cuMemCreate) memory
 	unsigned long long export_va = 0, export_handle = 0, export_size = 0;
 	cudaEvent_t ev[SVO_PHASE_COUNT + 1] = {};
@@ -886,10 +887,12 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 // already valid in a buffer where d_dst sits at word offset pointer_bias_words.  d_dst may be peer memory.
 static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_root, cudaStream_t s) {
 	EmitParams ep = b->ep;
-	ep.block_shift = skip_root ? 1u : 0u;
+	// skip_root: 0 = whole tree; 1 = the root block is kept aside; 2 = the root block and the depth-1 blocks are
+	ep.block_shift = skip_root == 0 ? 0u : (skip_root == 1 ? 1u : 1u + (uint32_t)b->h_counts[1]);
 	ep.ptr_bias = bias;
+	b->top_blocks = ep.block_shift;
 	if (skip_root) {
-		SVO_TRY(b->root_scratch.reserve(8, s));
+		SVO_TRY(b->root_scratch.reserve(9 * 8, s));
 		ep.root_dst = b->root_scratch.p;
 	}
 	if (b->h_counts[b->level] == 0) { // empty scene: a zeroed root block
@@ -909,6 +912,8 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *stream) {
 	if (!b || !d_dst) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_to: null argument");
 	if (!b->prepared) return fail(SVO_ERR_NOT_READY, "svo_builder_emit_to: prepare first");
+	if (skip_root < 0 || skip_root > 2 || (skip_root == 2 && b->level < 3))
+		return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_to: skip_root is 0, 1 or 2 (2 needs level >= 3)");
 	if ((uint64_t)pointer_bias_words + b->range_bytes / 4 >= (1ull << 30))
 		return fail(SVO_ERR_CAPACITY, "biased child pointers would exceed 30 bits (octree.glsl:110)");
 	DeviceGuard guard(b->device);
@@ -916,6 +921,16 @@ int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_w
 	SVO_TRY(emit_into(b, d_dst, pointer_bias_words, skip_root, (cudaStream_t)stream));
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], (cudaStream_t)stream)); // svo_builder_last_ms covers prepare + emit_to as well
 	b->emitted = true;
+	return SVO_OK;
+}
+
+int svo_builder_top_words(svo_builder *b, uint32_t out[72], uint32_t *n_blocks, void *stream) {
+	if (!b || !out || !n_blocks) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (!b->root_scratch.p || !b->top_blocks) return fail(SVO_ERR_NOT_READY, "svo_builder_top_words: emit with skip_root first");
+	DeviceGuard guard(b->device);
+	*n_blocks = b->top_blocks;
+	SVO_CUDA_TRY(cudaMemcpyAsync(out, b->root_scratch.p, (size_t)b->top_blocks * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	SVO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
 	return SVO_OK;
 }
 

@@ -19,6 +19,8 @@ single-GPU tree bit for bit.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 ROOT_WORDS = 8
@@ -71,6 +73,61 @@ def root_block(bases, words_per_octant) -> np.ndarray:
     return out
 
 
+HEADER_WORDS = 72  # pipelined slab mode: root block + the 8 depth-1 blocks at fixed places, the parts' bodies behind them
+
+
+def sub_windows(rank: int, world: int, level: int, n_sub: int):
+    """The slab of `rank` cut into n_sub (1, 2 or 4) boxes along y (and z) at multiples of res/4 -- depth-2 cell borders,
+    so that parts built separately share nothing below the depth-1 blocks (svo_builder_emit_to, skip_root = 2)."""
+    if n_sub not in (1, 2, 4):
+        raise ValueError("n_sub must be 1, 2 or 4")
+    lo, hi = slab_window(rank, world, level)
+    boxes = [(list(lo), list(hi))]
+    for axis in ((1,) if n_sub == 2 else (1, 2) if n_sub == 4 else ()):
+        out = []
+        for blo, bhi in boxes:
+            mid = (blo[axis] + bhi[axis]) // 2
+            if mid % max(1, (1 << level) // 4):
+                raise ValueError("the cut is not on a depth-2 cell border (level too small)")
+            a_hi, b_lo = list(bhi), list(blo)
+            a_hi[axis], b_lo[axis] = mid, mid
+            out += [(blo, a_hi), (b_lo, bhi)]
+        boxes = out
+    return boxes
+
+
+def merge_top_blocks(tops) -> np.ndarray:
+    """tops: per separately built part, the blocks svo_builder_top_words returns (uint32 [1 + n1, 8]: its root block, then
+    its depth-1 blocks in the order of the root's non-empty slots; child pointers of the depth-1 blocks already final).
+    Returns the 72 header words: root block (pointing at the fixed depth-1 block places 8, 16, ... 64) + 8 depth-1
+    blocks, each the sum of the parts' blocks for that octant (the parts' depth-2 cells are disjoint)."""
+    header = np.zeros(HEADER_WORDS, dtype=np.uint64)
+    for t in tops:
+        t = np.asarray(t, dtype=np.uint32).reshape(-1, 8)
+        if len(t) == 0:
+            continue
+        octants = [o for o in range(8) if t[0][o]]
+        if len(octants) != len(t) - 1:
+            raise ValueError("top blocks do not match the root block")
+        for k, o in enumerate(octants):
+            header[8 * (1 + o): 8 * (2 + o)] += t[1 + k]
+            header[o] = 0x80000000 | (8 * (1 + o))
+    if (header >> np.uint64(32)).any():
+        raise ValueError("overlapping parts: a child slot was written twice")
+    return header.astype(np.uint32)
+
+
+def merge_headers(per_rank: np.ndarray) -> np.ndarray:
+    """per_rank: [world, 72] headers (merge_top_blocks of every rank's parts, all-gathered).  Depth-1 blocks are summed
+    (disjoint depth-2 cells), the root block takes the word of whichever ranks have the octant."""
+    h = np.asarray(per_rank, dtype=np.int64).reshape(-1, HEADER_WORDS)
+    header = h.sum(axis=0)
+    header[:8] = h[:, :8].max(axis=0)
+    if (header >> 32).any():
+        raise ValueError("overlapping parts: a child slot was written twice")
+    return header.astype(np.uint32)
+
+
 def rebase_words_numpy(words: np.ndarray, base: int) -> np.ndarray:
     """Host restatement of k_rebase_copy for the CPU (gloo) tests: add base to internal child pointers."""
     w = np.asarray(words, dtype=np.uint32).copy()
@@ -110,11 +167,14 @@ class ShardedSVO:
         # build over the window made of its octants, in global coordinates, and emits its node words straight into
         # rank 0's buffer.  Octant mode (level 14, or a single GPU): one cube-local build per octant.
         self.slab = self.world > 1 and 3 * level + 24 <= 64 and use_ipc
+        # the slab is built as n_sub separate parts cut at depth-2 cell borders: the node words of part k cross NVLink
+        # while part k + 1 is being voxelized and sorted
+        self.n_sub = int(os.environ.get("SVO_SUBSLABS", "2")) if self.slab and level >= 3 else 1
         if self.slab:
-            lo, hi = slab_window(self.rank, self.world, level)
-            v = api.Voxelizer.CreateWindowed(self.scene, level, mode, lo, hi)
-            self.vox.append(v)
-            self.builders.append(api.OctreeBuilder.Create(v))
+            for lo, hi in sub_windows(self.rank, self.world, level, self.n_sub):
+                v = api.Voxelizer.CreateWindowed(self.scene, level, mode, lo, hi)
+                self.vox.append(v)
+                self.builders.append(api.OctreeBuilder.Create(v))
         else:
             for o in self.octants:
                 v = api.Voxelizer.Create(self.scene, level, mode, shard=(1, octant_cube(o)))
@@ -159,36 +219,50 @@ class ShardedSVO:
         self.final, self.final_cap, self.peer_final = (ar["ptr"] if self.rank == 0 else None), ar["cap"], ar["peer"]
 
     def _step_slab(self, stream):
-        """Slab mode: one build per rank; the emit kernel itself stores the node words into rank 0's buffer over
-        NVLink with final child pointers (fused emit + transfer); rank 0 merges the 8-word root blocks."""
+        """Slab mode: every rank builds its slab as n_sub parts; as soon as a part's sizes are known (one small
+        all_gather) its emit kernel stores the node words, child pointers already final, into rank 0's buffer over
+        NVLink on a second stream -- while the rank voxelizes and sorts its next part.  Layout: 72-word header (root
+        block + 8 depth-1 blocks, merged by rank 0 from the parts' top blocks), then the bodies part by part."""
         torch, dist = self.torch, self.dist
-        v, b = self.vox[0], self.builders[0]
-        v.CmdVoxelize(stream)
-        b.Prepare(stream)
-        body = b.GetOctreeRange() // 4 - ROOT_WORDS if b.GetLeafCount() else 0   # node words below the root block
-        mine = torch.tensor([body], dtype=torch.int64, device=self.tdev)
-        bodies = torch.zeros(self.world, dtype=torch.int64, device=self.tdev)
-        dist.all_gather_into_tensor(bodies, mine)
-        bodies = [int(x) for x in bodies.cpu().tolist()]
-        base = ROOT_WORDS + sum(bodies[: self.rank])
-        total = ROOT_WORDS + sum(bodies)
-        if total >= 1 << 30:
-            raise OverflowError("stitched octree needs >= 2^30 words: 30-bit child pointers cannot address it")
-        self._ensure_final(total)
-        roots = torch.zeros(self.world * ROOT_WORDS, dtype=torch.int64, device=self.tdev)
-        my_root = np.zeros(ROOT_WORDS, dtype=np.uint32)
-        if body:
-            dst = (self.final if self.rank == 0 else self.peer_final) + base * 4
-            b.EmitTo(dst, base, True, stream)
-            my_root = b.RootWords(stream)
-        dist.all_gather_into_tensor(roots, torch.from_numpy(my_root.astype(np.int64)).to(self.tdev))
-        self.total_words, self.slab_bodies = total, bodies
+        if self.push_stream is None:
+            self.push_stream = torch.cuda.Stream(self.tdev)
+        mine = torch.zeros(1, dtype=torch.int64, device=self.tdev)
+        gathered = torch.zeros(self.world, dtype=torch.int64, device=self.tdev)
+        run, placed, overflow = HEADER_WORDS, [], self.final_cap == 0
+        for v, b in zip(self.vox, self.builders):
+            v.CmdVoxelize(stream)
+            b.Prepare(stream)  # ends with the size read-back: the stream is idle afterwards
+            body = b.GetOctreeRange() // 4 - 8 * (1 + b.GetLevelCounts()[1]) if b.GetLeafCount() else 0
+            mine.fill_(body)
+            dist.all_gather_into_tensor(gathered, mine)
+            bodies = [int(x) for x in gathered.cpu().tolist()]
+            base = run + sum(bodies[: self.rank])
+            run += sum(bodies)
+            if run >= 1 << 30:
+                raise OverflowError("stitched octree needs >= 2^30 words: 30-bit child pointers cannot address it")
+            overflow = overflow or run > self.final_cap  # (the same on every rank: all see the same sizes)
+            if body:
+                placed.append((b, base))
+                if not overflow:
+                    dst = (self.final if self.rank == 0 else self.peer_final) + base * 4
+                    b.EmitTo(dst, base, 2, self.push_stream)
+        if overflow:  # first step, or the tree outgrew the arena: size it now and emit everything (again)
+            self.push_stream.synchronize()
+            self._ensure_final(run)
+            for b, base in placed:
+                dst = (self.final if self.rank == 0 else self.peer_final) + base * 4
+                b.EmitTo(dst, base, 2, self.push_stream)
+        tops = [b.TopWords(self.push_stream) for b, _ in placed]  # (waits for this rank's stores)
+        local = torch.from_numpy(merge_top_blocks(tops).astype(np.int64)).to(self.tdev)
+        headers = torch.zeros(self.world * HEADER_WORDS, dtype=torch.int64, device=self.tdev)
+        dist.all_gather_into_tensor(headers, local)
+        self.total_words = run
         if self.rank == 0:
-            rb = roots.cpu().numpy().reshape(self.world, ROOT_WORDS).sum(axis=0).astype(np.uint32)  # disjoint octants
-            self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, rb.ctypes.data, rb.nbytes, 0))
+            header = merge_headers(headers.cpu().numpy())
+            self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, header.ctypes.data, header.nbytes, 0))
         torch.cuda.synchronize(self.tdev)
         dist.barrier()  # remote stores into rank 0's buffer are complete
-        return total * 4
+        return run * 4
 
     def step(self, stream=None):
         """One sharded build: local subtrees, size exchange, fused rebase + gather, root block on rank 0."""

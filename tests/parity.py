@@ -106,3 +106,37 @@ def check_against_oracle(lib, mesh, level, mode, shard=None, device=0, stream=No
     info = dict(fragments=len(frags), leaves=counts[key_level], range=rng, counts=counts)
     builder.Destroy(), vox.Destroy(), scene.Destroy()
     return info
+
+
+def depth2_parts_check(lib, world, n_sub, mesh, level, mode=api.CONSERVATIVE_EXACT):
+    """Builds the scene as world * n_sub separately built parts (sharded.sub_windows) assembled in one arena the way the
+    pipelined multi-GPU path does, and compares with the whole-grid build (canonical, colours included)."""
+    from sparsevoxeloctree_b200 import sharded
+    scene = api.Scene.Create(mesh, lib=lib)
+    parts, bodies, tops = [], [], []
+    for r in range(world):
+        for lo, hi in sharded.sub_windows(r, world, level, n_sub):
+            v = api.Voxelizer.CreateWindowed(scene, level, mode, lo, hi)
+            b = api.OctreeBuilder.Create(v)
+            v.CmdVoxelize()
+            b.Prepare()
+            counts = b.GetLevelCounts() if b.GetLeafCount() else None
+            parts.append((v, b))
+            bodies.append(b.GetOctreeRange() // 4 - 8 * (1 + counts[1]) if counts else 0)
+    total = sharded.HEADER_WORDS + sum(bodies)
+    arena = lib.malloc(total * 4)
+    for k, (v, b) in enumerate(parts):
+        base = sharded.HEADER_WORDS + sum(bodies[:k])
+        if b.GetLeafCount():
+            b.EmitTo(arena + base * 4, base, 2)
+            tops.append(b.TopWords())
+    header = sharded.merge_top_blocks(tops)
+    lib.check(lib.dll.svo_memcpy_h2d(0, arena, header.ctypes.data, header.nbytes, 0))
+    lib.check(lib.dll.svo_stream_synchronize(0, 0))
+    stitched = lib.to_host(arena, np.uint32, total)
+    _, vox, builder = api.build_svo(mesh, level, mode, lib=lib)
+    assert_same_tree(stitched, builder.octree_to_host(), level)
+    assert sum(v.GetVoxelFragmentCount() for v, _ in parts) == vox.GetVoxelFragmentCount()
+    lib.free(arena)
+    for v, b in parts:
+        b.Destroy(), v.Destroy()

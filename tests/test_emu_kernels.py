@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu
 import build_emu  # noqa: E402
 
 from sparsevoxeloctree_b200 import api, scenes  # noqa: E402
-from tests.parity import check_against_oracle  # noqa: E402
+from tests.parity import check_against_oracle, depth2_parts_check as _depth2_parts_check  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -200,3 +200,10 @@ def test_build_sharded_c_abi_logic(emu, n_dev):
     assert sh.GetOctreeRange() == builder.GetOctreeRange() and sh.GetLeafCount() == builder.GetLeafCount()
     assert_same_tree(sh.octree_to_host(), builder.octree_to_host(), 6)
     sh.Destroy()
+
+
+@pytest.mark.parametrize("world,n_sub", [(2, 2), (8, 2), (4, 4)])
+def test_depth2_parts_assemble_the_whole_tree(emu, world, n_sub):
+    """Pipelined slab mode on one (emulated) device: every rank's slab cut into parts at depth-2 cell borders, each part
+    built on its own and emitted with skip_root = 2 behind a 72-word header; the merged header + bodies = the whole tree."""
+    _depth2_parts_check(emu, world, n_sub, scenes.random_soup(250, 23, 0.02, 0.9), 6)

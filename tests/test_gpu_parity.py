@@ -416,3 +416,11 @@ def test_build_sharded_c_abi_level14(lib):
     d2, m2, w2 = oracle.canonicalise(ow, 14)
     assert (d1 == d2).all() and (m1 == m2).all() and ((w1 >> 24) == (w2 >> 24)).all()
     sh.Destroy()
+
+
+@pytest.mark.parametrize("world,n_sub", [(2, 2), (4, 2), (8, 2), (8, 4)])
+def test_depth2_parts_assemble_the_whole_tree_gpu(lib, world, n_sub):
+    """The pipelined multi-GPU layout on ONE device: each rank's slab as n_sub parts cut at depth-2 cell borders, emitted
+    with skip_root = 2 behind the 72-word header; merged header + bodies must equal the whole-grid tree."""
+    from tests.parity import depth2_parts_check
+    depth2_parts_check(lib, world, n_sub, scenes.random_soup(700, 53, 0.01, 1.2), 9)

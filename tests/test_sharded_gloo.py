@@ -95,3 +95,27 @@ def test_plan_and_root_block():
         sharded.plan_offsets([1 << 29] * 2 + [0] * 6)
     w = np.array([0x80000008, 0xC1000005, 0, 0x80000010], np.uint32)
     assert sharded.rebase_words_numpy(w, 64).tolist() == [0x80000048, 0xC1000005, 0, 0x80000050]
+
+
+def test_sub_windows_and_header_merge():
+    # the slab of a rank cut at depth-2 cell borders: 2 parts along y, 4 along y and z
+    assert sharded.sub_windows(1, 2, 5, 2) == [([16, 0, 0], [32, 16, 32]), ([16, 16, 0], [32, 32, 32])]
+    boxes = sharded.sub_windows(5, 8, 6, 4)   # octant (1, 0, 1) of a 64^3 grid
+    assert boxes == [([32, 0, 32], [64, 16, 48]), ([32, 0, 48], [64, 16, 64]), ([32, 16, 32], [64, 32, 48]), ([32, 16, 48], [64, 32, 64])]
+    for world in (2, 4, 8):
+        for n_sub in (1, 2, 4):
+            vol = sum(int(np.prod(np.array(hi) - np.array(lo))) for r in range(world) for lo, hi in sharded.sub_windows(r, world, 7, n_sub))
+            assert vol == 128 ** 3  # the parts tile the grid
+    with pytest.raises(ValueError):
+        sharded.sub_windows(0, 8, 6, 3)       # 1, 2 or 4 parts
+    # two parts of octant 3 (different depth-2 cells) and one of octant 5, built separately
+    a = np.zeros((2, 8), np.uint32); a[0, 3] = 0x80000008; a[1, 0] = 0x80000100; a[1, 2] = 0x80000108
+    b = np.zeros((2, 8), np.uint32); b[0, 3] = 0x80000008; b[1, 5] = 0x80000200
+    c = np.zeros((2, 8), np.uint32); c[0, 5] = 0x80000008; c[1, 7] = 0x80000300
+    h0, h1 = sharded.merge_top_blocks([a, b]), sharded.merge_top_blocks([c])
+    hdr = sharded.merge_headers(np.stack([h0, h1]))
+    assert hdr[3] == 0x80000000 | 32 and hdr[5] == 0x80000000 | 48 and not hdr[[0, 1, 2, 4, 6, 7]].any()
+    assert hdr[32:40].tolist() == [0x80000100, 0, 0x80000108, 0, 0, 0x80000200, 0, 0]
+    assert hdr[48:56].tolist() == [0, 0, 0, 0, 0, 0, 0, 0x80000300]
+    with pytest.raises(ValueError):
+        sharded.merge_top_blocks([a, a])      # the same child slot from two parts
