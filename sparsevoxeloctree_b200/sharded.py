@@ -190,6 +190,11 @@ class ShardedSVO:
         self.words = [0] * 8
         self.stage = None
         self.push_stream = None
+        # pipelined slab mode, ranks > 0: staging buffer per part (cached per process like the arena: cudaMalloc is slow)
+        # how a part's node words reach rank 0: "copy" = emitted into local memory, then one asynchronous device-to-device
+        # copy (the copy engine moves them while the SMs build the next part); "store" = the emit kernel stores them
+        # over NVLink itself (no staging, but the kernel holds its SM slots for the duration of the transfer)
+        self.push_mode = os.environ.get("SVO_PUSH", "copy")
         self.pipelined = True  # overlap the NVLink push of one octant with the build of the next (steady state)
 
     # -- rank 0 owns a grow-only arena for the stitched tree (like the reference's up-front octree buffer).
@@ -197,6 +202,8 @@ class ShardedSVO:
     #    and the IPC mapping.  Every rank sees the same total, so all ranks take the same branch: no collective
     #    is needed unless the arena really has to grow.
     _ARENA = {}  # device -> dict(ptr, cap, peer)
+    _STAGE = {}  # (device, part) -> (ptr, capacity in words)
+    _PUSH_STREAM = {}  # device -> torch stream
 
     def _ensure_final(self, words: int):
         dist = self.dist
@@ -225,7 +232,7 @@ class ShardedSVO:
         block + 8 depth-1 blocks, merged by rank 0 from the parts' top blocks), then the bodies part by part."""
         torch, dist = self.torch, self.dist
         if self.push_stream is None:
-            self.push_stream = torch.cuda.Stream(self.tdev)
+            self.push_stream = ShardedSVO._PUSH_STREAM.setdefault(self.device, torch.cuda.Stream(self.tdev))
         mine = torch.zeros(1, dtype=torch.int64, device=self.tdev)
         gathered = torch.zeros(self.world, dtype=torch.int64, device=self.tdev)
         run, placed, overflow = HEADER_WORDS, [], self.final_cap == 0
@@ -242,17 +249,15 @@ class ShardedSVO:
                 raise OverflowError("stitched octree needs >= 2^30 words: 30-bit child pointers cannot address it")
             overflow = overflow or run > self.final_cap  # (the same on every rank: all see the same sizes)
             if body:
-                placed.append((b, base))
+                placed.append((b, base, body))
                 if not overflow:
-                    dst = (self.final if self.rank == 0 else self.peer_final) + base * 4
-                    b.EmitTo(dst, base, 2, self.push_stream)
+                    self._push_part(b, base, body, stream)
         if overflow:  # first step, or the tree outgrew the arena: size it now and emit everything (again)
             self.push_stream.synchronize()
             self._ensure_final(run)
-            for b, base in placed:
-                dst = (self.final if self.rank == 0 else self.peer_final) + base * 4
-                b.EmitTo(dst, base, 2, self.push_stream)
-        tops = [b.TopWords(self.push_stream) for b, _ in placed]  # (waits for this rank's stores)
+            for b, base, body in placed:
+                self._push_part(b, base, body, stream)
+        tops = [b.TopWords(self.push_stream) for b, _, _ in placed]  # (waits for this rank's stores)
         local = torch.from_numpy(merge_top_blocks(tops).astype(np.int64)).to(self.tdev)
         headers = torch.zeros(self.world * HEADER_WORDS, dtype=torch.int64, device=self.tdev)
         dist.all_gather_into_tensor(headers, local)
@@ -263,6 +268,30 @@ class ShardedSVO:
         torch.cuda.synchronize(self.tdev)
         dist.barrier()  # remote stores into rank 0's buffer are complete
         return run * 4
+
+    def _push_part(self, b, base, body, stream):
+        """Node words of a prepared part -> words [base, base + body) of rank 0's buffer, child pointers final."""
+        torch = self.torch
+        if self.rank == 0:
+            b.EmitTo(self.final + base * 4, base, 2, stream)  # local: straight into the stitched buffer
+            self.push_stream.wait_stream(stream if stream is not None else torch.cuda.current_stream(self.tdev))
+            return
+        dst = self.peer_final + base * 4
+        if self.push_mode == "store":
+            b.EmitTo(dst, base, 2, self.push_stream)
+            return
+        key = (self.device, self.builders.index(b))
+        buf, cap = ShardedSVO._STAGE.get(key, (0, 0))
+        if cap < body:
+            if buf:
+                self.torch.cuda.synchronize(self.tdev)
+                self.lib.free(buf, self.device)
+            cap = body + body // 8
+            buf = self.lib.malloc(cap * 4, self.device)
+            ShardedSVO._STAGE[key] = (buf, cap)
+        b.EmitTo(buf, base, 2, stream)  # fast local emit on the build stream ...
+        self.push_stream.wait_stream(stream if stream is not None else torch.cuda.current_stream(self.tdev))
+        self.lib.check(self.lib.dll.svo_memcpy_d2d(self.device, dst, buf, body * 4, int(self.push_stream.cuda_stream)))  # ... DMA over NVLink
 
     def step(self, stream=None):
         """One sharded build: local subtrees, size exchange, fused rebase + gather, root block on rank 0."""
