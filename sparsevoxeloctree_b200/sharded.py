@@ -169,7 +169,9 @@ class ShardedSVO:
         self.slab = self.world > 1 and 3 * level + 24 <= 64 and use_ipc
         # the slab is built as n_sub separate parts cut at depth-2 cell borders: the node words of part k cross NVLink
         # while part k + 1 is being voxelized and sorted
-        self.n_sub = int(os.environ.get("SVO_SUBSLABS", "2")) if self.slab and level >= 3 else 1
+        # (measured on 2 B200, C4: 1 part 4.83 ms, 2 parts 4.81 ms, 4 parts 5.33 ms -- what the overlap wins, the smaller
+        # sorts lose; one part stays the default)
+        self.n_sub = int(os.environ.get("SVO_SUBSLABS", "1")) if self.slab and level >= 3 else 1
         if self.slab:
             for lo, hi in sub_windows(self.rank, self.world, level, self.n_sub):
                 v = api.Voxelizer.CreateWindowed(self.scene, level, mode, lo, hi)
@@ -194,7 +196,8 @@ class ShardedSVO:
         # how a part's node words reach rank 0: "copy" = emitted into local memory, then one asynchronous device-to-device
         # copy (the copy engine moves them while the SMs build the next part); "store" = the emit kernel stores them
         # over NVLink itself (no staging, but the kernel holds its SM slots for the duration of the transfer)
-        self.push_mode = os.environ.get("SVO_PUSH", "copy")
+        # (2 B200, C4, one part: store 4.83 ms, copy 5.31 ms)
+        self.push_mode = os.environ.get("SVO_PUSH", "store")
         self.pipelined = True  # overlap the NVLink push of one octant with the build of the next (steady state)
 
     # -- rank 0 owns a grow-only arena for the stitched tree (like the reference's up-front octree buffer).
