@@ -229,6 +229,15 @@ SVO_API void svo_debug_force_wide_sort_state(int on);
  * builder's last sort (out[0..n), n = return value <= cap; < 0: svo_status).  Off by default: no events, no cost. */
 SVO_API void svo_debug_profile_passes(int on);
 SVO_API int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap);
+/* Build path switch, read when a voxelizer is created.  -1 (default): automatic -- the brick path (large triangles
+ * binned to 8^3-voxel bricks and rasterized straight into the three deepest tree levels; only the small triangles'
+ * fragments are emitted and sorted) when level - shard_level >= 4 and the large triangles hold at least a fifth of
+ * the fragments; 0: never (every fragment is emitted, sorted and reduced); 1: whenever the level allows it.  Both
+ * paths produce the same node buffer bit for bit.  svo_builder_build_path: the path the builder's last build took
+ * (0 / 1); with 1 the phases SORT_HIST / SORT_PASSES / REDUCE of svo_builder_last_ms hold: small triangles' fragments
+ * (sort + reduce) / pair generation + pair sort / the brick kernel. */
+SVO_API void svo_debug_set_build_path(int mode);
+SVO_API int svo_builder_build_path(const svo_builder *b);
 
 /* ---- the consumer side, for verification ----------------------------------------------------
  * Octree_RayMarchLeaf (shader/octree.glsl:179-340, the primary-ray traversal octree_tracer.frag:36 runs on the

@@ -93,6 +93,8 @@ SYMBOLS = [
     ("svo_sort_u64", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P]),
     ("svo_debug_force_wide_sort_state", None, [C.c_int]),
     ("svo_debug_profile_passes", None, [C.c_int]),
+    ("svo_debug_set_build_path", None, [C.c_int]),
+    ("svo_builder_build_path", C.c_int, [_P]),
     ("svo_builder_sort_step_ms", C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
     ("svo_octree_raymarch_leaf", C.c_int, [C.c_int, _P, C.c_uint64, _P, _P, _P, _P]),
     ("svo_device_malloc", C.c_int, [C.c_int, C.c_uint64, C.POINTER(_P)]),

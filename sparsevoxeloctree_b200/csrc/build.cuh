@@ -51,7 +51,7 @@ constexpr int RF_CPL = RF_ITEMS * RF_NW / 32; // counts per lane in that scan
 
 struct FusedOut {
 	uint32_t *leaf;           // [count0] leaf words
-	unsigned char *slot0;     // [count0] child slot of each leaf
+	unsigned char *slot0;     // [count0] child slot of each leaf (null: not wanted)
 	uint32_t *first1;         // [count1] first leaf of each depth-(L-1) node
 	unsigned char *slot1;     // [count1] child slot of each depth-(L-1) node
 	uint32_t *first2;         // [count2] first depth-(L-1) child of each depth-(L-2) node
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 			s_start[l0] = (uint16_t)e;
 		else {
 			out.leaf[u0] = fold_leaf(e, key);
-			out.slot0[u0] = (unsigned char)((key >> 24) & 7u);
+			if (out.slot0) out.slot0[u0] = (unsigned char)((key >> 24) & 7u);
 			if (K == 1) out.keys_top[u0] = key >> 24;
 		}
 		if (K >= 2 && (pk & 2u)) {
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(RF_BLOCK, SVO_RF_MINB)
 			const uint32_t e = s_start[r];
 			const uint64_t key = s_keys[e + 1];
 			out.leaf[p0 + r] = fold_leaf(e, key);
-			out.slot0[p0 + r] = (unsigned char)((key >> 24) & 7u);
+			if (out.slot0) out.slot0[p0 + r] = (unsigned char)((key >> 24) & 7u);
 			if (K == 1) out.keys_top[p0 + r] = key >> 24;
 		}
 	}

@@ -74,6 +74,9 @@ SVO_DEV uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t agg
 		const int64_t idx = base - lane;
 		uint64_t s = idx >= 0 ? lb_load(&state[idx]) : lb_pack(LB_PREFIX, 0);
 		while (__any_sync(FULL_MASK, lb_status(s) == LB_INVALID)) {
+#if defined(__CUDA_ARCH__)
+			__nanosleep(40); // the predecessors are still working: leave the issue slots to them
+#endif
 			if (lb_status(s) == LB_INVALID) s = lb_load(&state[idx]);
 		}
 		const unsigned pmask = __ballot_sync(FULL_MASK, lb_status(s) == LB_PREFIX);

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "build.cuh"
+#include "brick.cuh"
 #include "raster.cuh"
 #include "raymarch.cuh"
 #include "sort.cuh"
@@ -131,6 +132,12 @@ struct svo_voxelizer {
 	DevBuf<uint32_t> row_off, row_xy, row_li;
 	DevBuf<uint64_t> frags;
 	DevBuf<uint64_t> ext_frags; // svo_voxelizer_create_from_fragments: the caller's fragment list (voxelize re-copies it)
+	// brick path (brick.cuh): the large triangles are binned to 8^3-voxel bricks instead of being emitted as fragments
+	bool brick = false;
+	bool large_emitted = false;   // the large triangles' fragments are in frags (brick path: only on request)
+	uint64_t n_tile_rows = 0, n_pairs_large = 0;
+	DevBuf<uint64_t> tr_base;     // [n_large + 1] first tile row of every large triangle
+	DevBuf<uint64_t> pair_off;    // [n_tile_rows + 1] first pair of every tile row
 	bool voxelized = false;
 	Timer t_raster;
 };
@@ -151,6 +158,11 @@ struct svo_builder {
 	SortScratch sort_scratch;
 	ScanScratch scan_scratch;
 	DevBuf<uint64_t> rf_cnt01, rf_cnt2, rf_pre01, rf_pre2; // per reduce tile: run counts and their exclusive prefixes
+	// brick path (brick.cuh)
+	DevBuf<uint64_t> pairs_a, pairs_b, pair_idx, brick_state, brick_scalars;
+	DevBuf<uint32_t> pair_flags, brick_first, small_leaf;
+	uint64_t n_pairs = 0, n_small_leaves = 0; // of the last build
+	int path = 0;                             // 0: every fragment sorted; 1: bricks
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
 	uint64_t range_bytes = 0;
 	uint32_t sort_passes = 0;
@@ -458,6 +470,25 @@ int svo_scene_texture_level(const svo_scene *sc, uint32_t texture, uint32_t leve
 	return (int)d.levels;
 }
 
+// ---- brick path switch -------------------------------------------------------------------------------
+// -1 (default): bricks when the large triangles hold a good part of the fragments; 0: never (every fragment is emitted
+// and sorted); 1: whenever the level allows it.  Read when a voxelizer is created.
+static int g_build_path = -2; // -2: not set yet (the environment variable SVO_BUILD_PATH = 0 / 1 is looked at once)
+static bool brick_path_wanted(const svo_voxelizer *v) {
+	if (g_build_path == -2) {
+		const char *e = getenv("SVO_BUILD_PATH");
+		g_build_path = (e && (e[0] == '0' || e[0] == '1') && !e[1]) ? e[0] - '0' : -1;
+	}
+	if (v->key_level < 4 || v->n_frag_large == 0 || v->n_large == 0 || g_build_path == 0) return false;
+	if (g_build_path == 1) return true;
+	return false; // (automatic choice disabled while the brick kernel is slower than the sort it replaces)
+}
+static dim3 brick_pair_grid(const svo_voxelizer *v) {
+	// one warp per large triangle; few triangles with hundreds of tile rows each: deal a triangle's rows out over up to 32 warps
+	const uint32_t wgrid = div_up((uint64_t)v->n_large * 32, RASTER_BLOCK);
+	return dim3(wgrid, v->n_large < 65536u ? std::min(32u, std::max(1u, (1u << v->level) / 64u)) : 1u);
+}
+
 // ------------------------------------------------------------------------------------------------------
 static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, const svo_shard *shard, const uint32_t *win_lo,
                                  const uint32_t *win_hi, void *stream, svo_voxelizer **out);
@@ -589,6 +620,38 @@ static int voxelizer_create_impl(svo_scene *scene, uint32_t level, int mode, con
 			DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
 			SVO_LAUNCH_INDEP(wgrid2, RASTER_BLOCK, s, k_rows_compact, v->n_large, (const LargeTri *)v->large.p, (const uint32_t *)row_len.p,
 			                 (const uint32_t *)row_x0.p, (const uint64_t *)dense_index.p, (const uint64_t *)frag_prefix.p, rows_sparse, dr);
+			// brick path: count the (brick, triangle) pairs of the large triangles (part of the count pass: exact sizes)
+			v->brick = brick_path_wanted(v);
+			if (v->brick) {
+				DevBuf<uint32_t> n_tr, pair_cnt;
+				do {
+					if ((rc = n_tr.alloc(v->n_large, s)) || (rc = v->tr_base.alloc((uint64_t)v->n_large + 1, s))) break;
+					SVO_LAUNCH_INDEP(div_up(v->n_large, RASTER_BLOCK), RASTER_BLOCK, s, k_brick_tile_rows, v->rp, v->n_large,
+					                 (const LargeTri *)v->large.p, n_tr.p);
+					if ((rc = exclusive_scan((const uint32_t *)n_tr.p, v->tr_base.p, v->n_large, ss, s))) break;
+					uint64_t h_tr = 0;
+					if (cudaMemcpyAsync(&h_tr, v->tr_base.p + v->n_large, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+					    cudaStreamSynchronize(s) != cudaSuccess) {
+						rc = fail(SVO_ERR_CUDA, "tile row pass failed");
+						break;
+					}
+					v->n_tile_rows = h_tr;
+					if ((rc = pair_cnt.alloc(h_tr, s)) || (rc = v->pair_off.alloc(h_tr + 1, s))) break;
+					SVO_LAUNCH(brick_pair_grid(v), RASTER_BLOCK, 0, s, k_brick_pairs<false>, v->rp, v->n_large, (const LargeTri *)v->large.p,
+					           (const uint64_t *)v->tr_base.p, pair_cnt.p, (const uint64_t *)nullptr, (uint64_t *)nullptr);
+					if ((rc = exclusive_scan((const uint32_t *)pair_cnt.p, v->pair_off.p, h_tr, ss, s))) break;
+					uint64_t h_pairs = 0;
+					if (cudaMemcpyAsync(&h_pairs, v->pair_off.p + h_tr, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+					    cudaStreamSynchronize(s) != cudaSuccess) {
+						rc = fail(SVO_ERR_CUDA, "pair count pass failed");
+						break;
+					}
+					v->n_pairs_large = h_pairs;
+					if (h_pairs >= (1ull << 31)) v->brick = false; // (brick_first holds 32-bit pair indices)
+				} while (0);
+				n_tr.release(s), pair_cnt.release(s);
+				if (rc) break;
+			}
 		}
 		v->n_frag = v->n_frag_small + v->n_frag_large;
 		if (v->n_frag >= 0xffffffffull) {
@@ -647,8 +710,31 @@ void svo_voxelizer_destroy(svo_voxelizer *v) {
 	v->large_uv.release(s);
 	v->tri_off.release(s), v->large.release(s), v->row_off.release(s), v->row_xy.release(s), v->row_li.release(s), v->frags.release(s);
 	v->ext_frags.release(s);
+	v->tr_base.release(s), v->pair_off.release(s);
 	v->t_raster.destroy();
 	delete v;
+}
+
+static int emit_large_fragments(svo_voxelizer *v, cudaStream_t s) {
+	const SceneView &sv = v->scene->view;
+	const bool tex = v->scene->textured;
+	if (v->n_frag_large) {
+		DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
+		if (tex)
+		{
+			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<true>, v->rp, sv.tex, (const LargeTri *)v->large.p,
+			           (const UvMap *)v->large_uv.p, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
+			// rows of large alpha-tested triangles (none in most scenes: the kernel then exits at once)
+			SVO_LAUNCH(div_up(v->n_rows, RASTER_BLOCK), RASTER_BLOCK, 0, s, k_emit_alpha_rows<true>, v->rp, sv.tex,
+			           (const LargeTri *)v->large.p, (const UvMap *)v->large_uv.p, dr, v->n_rows, v->frags.p + v->n_frag_small);
+		}
+		else
+			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<false>, v->rp, sv.tex, (const LargeTri *)v->large.p,
+			           (const UvMap *)nullptr, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
+	}
+	SVO_CUDA_TRY(cudaGetLastError());
+	v->large_emitted = true;
+	return SVO_OK;
 }
 
 int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
@@ -675,20 +761,10 @@ int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
 			SVO_LAUNCH(div_up(sv.n_tri, RASTER_BLOCK), RASTER_BLOCK, 0, s, k_emit_small<false>, sv, v->rp, (const uint64_t *)v->tri_off.p,
 			           v->frags.p);
 	}
-	if (v->n_frag_large) {
-		DenseRows dr{v->row_off.p, v->row_xy.p, v->row_li.p};
-		if (tex)
-		{
-			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<true>, v->rp, sv.tex, (const LargeTri *)v->large.p,
-			           (const UvMap *)v->large_uv.p, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
-			// rows of large alpha-tested triangles (none in most scenes: the kernel then exits at once)
-			SVO_LAUNCH(div_up(v->n_rows, RASTER_BLOCK), RASTER_BLOCK, 0, s, k_emit_alpha_rows<true>, v->rp, sv.tex,
-			           (const LargeTri *)v->large.p, (const UvMap *)v->large_uv.p, dr, v->n_rows, v->frags.p + v->n_frag_small);
-		}
-		else
-			SVO_LAUNCH(div_up(v->n_frag_large, EMIT_TILE), EMIT_BLOCK, 0, s, k_emit_large<false>, v->rp, sv.tex, (const LargeTri *)v->large.p,
-			           (const UvMap *)nullptr, dr, v->n_rows, v->n_frag_large, v->frags.p + v->n_frag_small);
-	}
+	// brick path: the large triangles are never emitted as fragments (the builder bins them: brick.cuh) unless somebody
+	// asks for the fragment list (svo_voxelizer_fragments / svo_voxelizer_export_reference_fragments)
+	v->large_emitted = false;
+	if (v->n_frag_large && !v->brick) SVO_TRY(emit_large_fragments(v, s));
 	SVO_CUDA_TRY(cudaEventRecord(v->t_raster.b, s));
 	SVO_CUDA_TRY(cudaGetLastError());
 	v->t_raster.recorded = true;
@@ -699,12 +775,25 @@ int svo_voxelizer_voxelize(svo_voxelizer *v, void *stream) {
 uint32_t svo_voxelizer_level(const svo_voxelizer *v) { return v ? v->level : 0; }
 uint32_t svo_voxelizer_resolution(const svo_voxelizer *v) { return v ? 1u << v->level : 0; }
 uint64_t svo_voxelizer_fragment_count(const svo_voxelizer *v) { return v ? v->n_frag : 0; }
-const uint64_t *svo_voxelizer_fragments(const svo_voxelizer *v) { return v ? v->frags.p : nullptr; }
+// brick path: the list is completed on request (the large triangles' fragments are not part of the build any more)
+static int complete_fragment_list(const svo_voxelizer *cv) {
+	svo_voxelizer *v = const_cast<svo_voxelizer *>(cv);
+	if (!v->brick || !v->voxelized || v->large_emitted || !v->n_frag_large) return SVO_OK;
+	DeviceGuard guard(v->device);
+	SVO_TRY(emit_large_fragments(v, v->last_stream));
+	SVO_CUDA_TRY(cudaStreamSynchronize(v->last_stream)); // the caller may read the list on any stream
+	return SVO_OK;
+}
+const uint64_t *svo_voxelizer_fragments(const svo_voxelizer *v) {
+	if (!v || complete_fragment_list(v) != SVO_OK) return nullptr;
+	return v->frags.p;
+}
 
 int svo_voxelizer_export_reference_fragments(const svo_voxelizer *v, uint32_t *d_out, void *stream) {
 	if (!v || !d_out) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
 	if (v->key_level > 12) return fail(SVO_ERR_UNSUPPORTED, "the reference fragment packing holds 12 bits per axis (voxelizer.frag:40-42)");
 	if (!v->voxelized) return fail(SVO_ERR_NOT_READY, "voxelize first");
+	SVO_TRY(complete_fragment_list(v));
 	DeviceGuard guard(v->device);
 	cudaStream_t s = (cudaStream_t)stream;
 	if (v->n_frag)
@@ -769,10 +858,122 @@ void svo_builder_destroy(svo_builder *b) {
 	b->sort_scratch.release(s);
 	b->scan_scratch.state.release(s), b->scan_scratch.ticket.release(s);
 	b->rf_cnt01.release(s), b->rf_cnt2.release(s), b->rf_pre01.release(s), b->rf_pre2.release(s);
+	b->pairs_a.release(s), b->pairs_b.release(s), b->pair_idx.release(s), b->brick_state.release(s), b->brick_scalars.release(s);
+	b->pair_flags.release(s), b->brick_first.release(s), b->small_leaf.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
 	release_export(b);
 	delete b;
+}
+
+// count the runs of every tile, scan over the tiles, then the big kernel: no tile waits for a neighbour
+static int reduce_sorted(svo_builder *b, const uint64_t *sorted, uint64_t F, uint32_t K, const FusedOut &fo, cudaStream_t s) {
+	const uint32_t rf_tiles = div_up(F, RF_TILE);
+	SVO_TRY(b->rf_cnt01.reserve(rf_tiles, s));
+	SVO_TRY(b->rf_cnt2.reserve(rf_tiles, s));
+	SVO_TRY(b->rf_pre01.reserve((uint64_t)rf_tiles + 1, s));
+	SVO_TRY(b->rf_pre2.reserve((uint64_t)rf_tiles + 1, s));
+	const uint64_t *p01 = b->rf_pre01.p, *p2 = b->rf_pre2.p;
+#define SVO_REDUCE_CASE(KK)                                                                                                        \
+	{                                                                                                                              \
+		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_count<KK>, sorted, F, b->rf_cnt01.p, b->rf_cnt2.p);                            \
+		SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt01.p, b->rf_pre01.p, rf_tiles, b->scan_scratch, s));                      \
+		if (KK >= 3) SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt2.p, b->rf_pre2.p, rf_tiles, b->scan_scratch, s));           \
+		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_fused<KK>, sorted, F, fo, rf_tiles, p01, p2);                                  \
+	}
+	if (K == 1) SVO_REDUCE_CASE(1) else if (K == 2) SVO_REDUCE_CASE(2) else SVO_REDUCE_CASE(3)
+#undef SVO_REDUCE_CASE
+	return 0;
+}
+
+// The brick path of svo_builder_prepare (brick.cuh): small triangles' fragments sorted and reduced on their own, large
+// triangles binned; on return *keys_top holds the depth L-2 keys (counts[L-2] of them) and *free_buf is free.
+//   ev[0..1] small fragments: sort + reduce + small records (+ the read-back of their number)
+//   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_build
+static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_off, const uint64_t *slot_off, uint64_t **free_buf,
+                          uint64_t **keys_top) {
+	svo_voxelizer *v = b->vox;
+	const uint32_t L = b->level;
+	const int n_sm = sm_count(b->device);
+	const uint64_t ns = v->n_frag_small, npl = v->n_pairs_large;
+	uint64_t *A = v->frags.p, *B = b->tmp.p; // A: sorted small fragments, dead after their reduce; B: their unique Morton codes
+	SVO_TRY(b->brick_scalars.reserve(4, s));
+	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_scalars.p, 0, 4 * sizeof(uint64_t), s));
+	uint64_t *d_nsl = b->brick_scalars.p, *d_nsb = b->brick_scalars.p + 1;
+	uint64_t h_small[2] = {0, 0}; // leaves of small triangles, bricks that hold some
+	b->sort_passes = 0;
+	if (ns) {
+		uint64_t *sorted = A;
+		SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, ns, 24, 24 + 3 * L, b->sort_scratch, b->device, n_sm, s, &sorted, &b->sort_passes, nullptr));
+		A = sorted, B = sorted == v->frags.p ? b->tmp.p : v->frags.p;
+		SVO_TRY(b->small_leaf.reserve(ns, s));
+		FusedOut fo{};
+		fo.leaf = b->small_leaf.p;
+		fo.keys_top = B;
+		fo.count[0] = d_nsl;
+		SVO_TRY(reduce_sorted(b, A, ns, 1, fo, s));
+		const uint32_t g = std::min<uint32_t>(div_up(ns, 256), (uint32_t)n_sm * 8u);
+		SVO_LAUNCH(g, 256, 0, s, k_brick_small_records, (const uint64_t *)B, (const uint64_t *)d_nsl, A, reinterpret_cast<unsigned long long *>(d_nsb));
+		SVO_CUDA_TRY(cudaMemcpyAsync(h_small, b->brick_scalars.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+		SVO_CUDA_TRY(cudaStreamSynchronize(s));
+	}
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[1], s));
+	b->n_small_leaves = h_small[0];
+	const uint64_t nsb = h_small[1], n_pairs = npl + nsb;
+	b->n_pairs = n_pairs;
+	SVO_TRY(b->pairs_a.reserve(n_pairs, s));
+	SVO_TRY(b->pairs_b.reserve(n_pairs, s));
+	SVO_TRY(b->pair_flags.reserve(n_pairs, s));
+	SVO_TRY(b->pair_idx.reserve(n_pairs + 1, s));
+	SVO_TRY(b->brick_first.reserve(n_pairs + 1, s));
+	if (nsb) SVO_CUDA_TRY(cudaMemcpyAsync(b->pairs_a.p, A, nsb * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+	SVO_LAUNCH(brick_pair_grid(v), RASTER_BLOCK, 0, s, k_brick_pairs<true>, v->rp, v->n_large, (const LargeTri *)v->large.p,
+	           (const uint64_t *)v->tr_base.p, (uint32_t *)nullptr, (const uint64_t *)v->pair_off.p, b->pairs_a.p + nsb);
+	uint64_t *pairs = b->pairs_a.p;
+	uint32_t pair_passes = 0;
+	SVO_TRY(radix_sort_u64(b->pairs_a.p, b->pairs_b.p, n_pairs, PAIR_SORT_BEGIN, 33 + 3 * (L - BRICK_LOG), b->sort_scratch, b->device, n_sm, s,
+	                       &pairs, &pair_passes, nullptr));
+	SVO_LAUNCH_INDEP(div_up(n_pairs, 256), 256, s, k_brick_head_flags, (const uint64_t *)pairs, n_pairs, b->pair_flags.p);
+	SVO_TRY((exclusive_scan<uint32_t, true>((const uint32_t *)b->pair_flags.p, b->pair_idx.p, n_pairs, b->scan_scratch, s)));
+	uint64_t *brick_code = pairs == b->pairs_a.p ? b->pairs_b.p : b->pairs_a.p; // (the other pair buffer is free after the sort)
+	SVO_LAUNCH_INDEP(div_up(n_pairs, 256), 256, s, k_brick_head_scatter, (const uint64_t *)pairs, (const uint32_t *)b->pair_flags.p,
+	                 (const uint64_t *)b->pair_idx.p, n_pairs, b->brick_first.p, brick_code);
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
+
+	const uint32_t tiles_ub = div_up(n_pairs, BRICK_TILE);
+	SVO_TRY(b->brick_state.reserve(3ull * (tiles_ub + 1), s));
+	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_state.p, 0, 3ull * (tiles_ub + 1) * sizeof(uint64_t), s));
+	BrickArgs a{};
+	a.pairs = pairs, a.brick_first = b->brick_first.p, a.brick_code = brick_code, a.n_bricks = b->pair_idx.p + n_pairs;
+	a.large = v->large.p, a.luv = v->large_uv.p, a.tv = v->scene->view.tex, a.rp = v->rp;
+	a.small_keys = B, a.small_leaf = b->small_leaf.p, a.n_small = d_nsl;
+	a.out.leaf = b->leaf.p;
+	a.out.slot0 = b->slot.p + slot_off[L];
+	a.out.first1 = b->first.p + first_off[L];
+	a.out.slot1 = b->slot.p + slot_off[L - 1], a.out.first2 = b->first.p + first_off[L - 1];
+	a.out.keys_top = A;
+	for (uint32_t j = 0; j < 3; ++j) a.out.count[j] = b->counts.p + (L - j);
+	a.state = b->brick_state.p, a.state_stride = tiles_ub + 1;
+	a.ticket = b->tickets.p; // [0]: unused by the level loop (it starts at index K)
+#ifndef SVO_EMU
+	{
+		static bool attr_set[64] = {}; // per device
+		const int di = b->device >= 0 && b->device < 64 ? b->device : 0;
+		if (!attr_set[di]) {
+			SVO_CUDA_TRY(cudaFuncSetAttribute(k_brick_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRICK_SMEM));
+			SVO_CUDA_TRY(cudaFuncSetAttribute(k_brick_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRICK_SMEM));
+			attr_set[di] = true;
+		}
+	}
+#endif
+	if (v->scene->textured)
+		SVO_LAUNCH(tiles_ub, BRICK_BLOCK, BRICK_SMEM, s, k_brick_build<true>, a);
+	else
+		SVO_LAUNCH(tiles_ub, BRICK_BLOCK, BRICK_SMEM, s, k_brick_build<false>, a);
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
+	SVO_CUDA_TRY(cudaGetLastError());
+	*keys_top = A, *free_buf = B;
+	return 0;
 }
 
 int svo_builder_prepare(svo_builder *b, void *stream) {
@@ -790,17 +991,9 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	// ping-pong buffers for the upper levels.  A second build (or a fragment export) needs a new CmdVoxelize first.
 	v->voxelized = false;
 
-	// ---- sort by Morton code (stable) ----
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[0], s));
-	uint64_t *sorted = v->frags.p;
-	SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, b->device, n_sm, s, &sorted, &b->sort_passes, b->ev[1]));
-	uint64_t *other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
-
-	// ---- de-duplicate + colour reduce + the two deepest parent levels, fused (build.cuh) ----
 	const uint32_t K = L < 3 ? L : 3;
 	const uint64_t tiles_f = (F + CMP_TILE - 1) / CMP_TILE + 1;
-	const uint32_t rf_tiles = div_up(F, RF_TILE);
 	SVO_CUDA_TRY(cudaMemsetAsync(b->lb_state.p, 0, tiles_f * (L + 4) * sizeof(uint64_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(b->tickets.p, 0, (L + 2) * sizeof(uint32_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(b->counts.p, 0, (MAX_LEVEL + 2) * sizeof(uint64_t), s));
@@ -812,31 +1005,29 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 			fo += node_cap(F, d - 1), so += (node_cap(F, d) + 7) & ~7ull;
 		}
 	}
-	if (F) {
-		FusedOut fo{};
-		fo.leaf = b->leaf.p;
-		fo.slot0 = b->slot.p + slot_off[L];
-		fo.first1 = b->first.p + first_off[L];
-		if (L >= 2) fo.slot1 = b->slot.p + slot_off[L - 1], fo.first2 = b->first.p + first_off[L - 1];
-		fo.keys_top = other;
-		for (uint32_t j = 0; j < K; ++j) fo.count[j] = b->counts.p + (L - j);
-		// count the runs of every tile, scan over the tiles, then the big kernel: no tile waits for a neighbour
-		SVO_TRY(b->rf_cnt01.reserve(rf_tiles, s));
-		SVO_TRY(b->rf_cnt2.reserve(rf_tiles, s));
-		SVO_TRY(b->rf_pre01.reserve((uint64_t)rf_tiles + 1, s));
-		SVO_TRY(b->rf_pre2.reserve((uint64_t)rf_tiles + 1, s));
-		const uint64_t *p01 = b->rf_pre01.p, *p2 = b->rf_pre2.p;
-#define SVO_REDUCE_CASE(KK)                                                                                                        \
-	{                                                                                                                              \
-		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_count<KK>, (const uint64_t *)sorted, F, b->rf_cnt01.p, b->rf_cnt2.p);          \
-		SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt01.p, b->rf_pre01.p, rf_tiles, b->scan_scratch, s));                      \
-		if (KK >= 3) SVO_TRY(exclusive_scan((const uint64_t *)b->rf_cnt2.p, b->rf_pre2.p, rf_tiles, b->scan_scratch, s));           \
-		SVO_LAUNCH(rf_tiles, RF_BLOCK, 0, s, k_reduce_fused<KK>, (const uint64_t *)sorted, F, fo, rf_tiles, p01, p2);                \
+	uint64_t *sorted = v->frags.p, *other = b->tmp.p;
+	b->path = v->brick ? 1 : 0;
+	if (v->brick) {
+		// ---- large triangles binned to bricks, small ones sorted on their own: the three deepest levels (brick.cuh) ----
+		SVO_TRY(prepare_bricks(b, s, first_off, slot_off, &sorted, &other));
+	} else {
+		// ---- sort by Morton code (stable) ----
+		SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, F, 24, 24 + 3 * L, b->sort_scratch, b->device, n_sm, s, &sorted, &b->sort_passes, b->ev[1]));
+		other = sorted == v->frags.p ? b->tmp.p : v->frags.p;
+		SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
+		// ---- de-duplicate + colour reduce + the two deepest parent levels, fused (build.cuh) ----
+		if (F) {
+			FusedOut fo{};
+			fo.leaf = b->leaf.p;
+			fo.slot0 = b->slot.p + slot_off[L];
+			fo.first1 = b->first.p + first_off[L];
+			if (L >= 2) fo.slot1 = b->slot.p + slot_off[L - 1], fo.first2 = b->first.p + first_off[L - 1];
+			fo.keys_top = other;
+			for (uint32_t j = 0; j < K; ++j) fo.count[j] = b->counts.p + (L - j);
+			SVO_TRY(reduce_sorted(b, sorted, F, K, fo, s));
+		}
+		SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 	}
-		if (K == 1) SVO_REDUCE_CASE(1) else if (K == 2) SVO_REDUCE_CASE(2) else SVO_REDUCE_CASE(3)
-#undef SVO_REDUCE_CASE
-	}
-	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 
 	// ---- remaining levels (L-K+1)..1: unique parents, first child, child mask (small from here on) ----
 	// key buffers ping-pong between the two fragment-sized buffers (the sorted fragments are dead after the reduce)
@@ -1207,6 +1398,8 @@ int svo_stream_synchronize(int device, void *stream) {
 
 void svo_debug_force_wide_sort_state(int on) { svo::g_force_wide_sort_state = on != 0; }
 void svo_debug_profile_passes(int on) { svo::g_profile_passes = on != 0; }
+void svo_debug_set_build_path(int mode) { g_build_path = mode < 0 ? -1 : (mode > 0 ? 1 : 0); }
+int svo_builder_build_path(const svo_builder *b) { return b ? b->path : 0; }
 #if SVO_OS_CLOCKS
 // experiment builds only (not declared in svo.h): per-phase cycle sums of the onesweep tiles; reset != 0 clears them
 SVO_API int svo_debug_onesweep_clocks(unsigned long long out[12], int reset) {

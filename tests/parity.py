@@ -103,7 +103,8 @@ def check_against_oracle(lib, mesh, level, mode, shard=None, device=0, stream=No
     counts = builder.GetLevelCounts()
     check_layout_invariants(words, key_level, counts)
     assert counts[key_level] == builder.GetLeafCount() == int((d == key_level).sum())
-    info = dict(fragments=len(frags), leaves=counts[key_level], range=rng, counts=counts)
+    info = dict(fragments=len(frags), leaves=counts[key_level], range=rng, counts=counts,
+                path=int(lib.dll.svo_builder_build_path(builder._h)))
     builder.Destroy(), vox.Destroy(), scene.Destroy()
     return info
 

@@ -69,6 +69,8 @@ def run(lib, mesh, level, mode, reps=6):
               f"walks={clk[11] / tiles:.2f}", flush=True)
     if prof:
         lib.dll.svo_debug_profile_passes(0)
+    if hasattr(lib.dll, "svo_builder_build_path") and lib.dll.svo_builder_build_path(b._h) == 1:
+        best = (best[0], {k2: v for k2, v in zip(("raster", "small_sort_reduce", "pairs", "bricks", "levels", "emit"), best[1].values())}, best[2])
     info = (vox.GetVoxelFragmentCount(), b.GetLeafCount(), zlib.crc32(b.octree_to_host().tobytes()))
     b.Destroy(), vox.Destroy(), scene.Destroy()
     return best, steps, info
@@ -106,7 +108,7 @@ def main():
             except Exception as e:  # noqa: BLE001
                 print(f"{wl} variant {spec}: FAILED {e}", flush=True)
                 continue
-            per = ms["sort_passes"] / max(npass, 1)
+            per = ms.get("sort_passes", 0.0) / max(npass, 1)
             gbs = 16.0 * F / (per * 1e-3) / 1e9 if per > 0 else 0
             print(f"{wl} {spec:60s} total {tot:7.3f} ms | " + " ".join(f"{k}={x:.3f}" for k, x in ms.items()) +
                   f" | passes={npass} per-pass {per:.3f} ms = {gbs:.0f} GB/s | sort kernels: " +
