@@ -27,7 +27,7 @@ namespace svo {
 
 constexpr int BRICK_LOG = 3;                // 8^3 voxels: three tree levels inside a brick
 constexpr int BRICK_CELLS = 512;
-constexpr int BRICK_WARPS = 8, BRICK_BLOCK = BRICK_WARPS * 32; // one warp per brick
+constexpr int BRICK_WARPS = 8, BRICK_BLOCK = BRICK_WARPS * 32; // a warp works on one brick at a time
 
 // A pair word: brick Morton code << 33 | is_large << 32 | payload.  payload = index of the large triangle, or (small
 // record, is_large = 0: sorts first inside its brick) the index of the brick's first leaf in the small-leaf list.
@@ -183,10 +183,21 @@ struct BrickArgs {
 	const uint64_t *small_keys; // leaves of the small triangles: sorted unique Morton codes, leaf words, how many
 	const uint32_t *small_leaf;
 	const uint64_t *n_small;
-	FusedOut out;          // the three deepest levels, as k_reduce_fused<3> leaves them
-	uint64_t *state;       // 3 look-back chains (leaves, depth L-1, depth L-2 nodes) of state_stride words each, zeroed
-	uint64_t state_stride;
-	uint32_t *ticket;      // zeroed
+	// per brick (arrays sized for the upper bound "number of pairs"; entries past n_bricks stay zero)
+	uint32_t *bound;        // leaves the brick can hold at most
+	const uint64_t *toff;   // exclusive scan of bound[]: the brick's first slot in temp
+	uint32_t *temp;         // leaf words, dense inside every brick, in Morton order
+	uint32_t *bits;         // [16] occupancy of the brick's 512 cells; byte j = child mask of its depth L-1 node j
+	uint32_t *cnt[3];       // leaves, depth L-1 nodes, depth L-2 nodes of the brick
+	const uint64_t *rank[3]; // exclusive scans of cnt[] (rank[j][n] = total)
+	uint64_t n_bound;       // entries of the per-brick arrays
+	// the three deepest levels for k_emit_octree / k_parent_compact
+	uint32_t *first1;        // per depth L-1 node: position of its first leaf in temp
+	unsigned char *mask1;    // per depth L-1 node: child mask
+	unsigned char *slot1;    // per depth L-1 node: child slot
+	uint32_t *first2;        // per depth L-2 node: index of its first depth L-1 child
+	uint64_t *keys_top;      // per depth L-2 node: Morton code
+	uint64_t *count[3];      // device scalars: leaves, depth L-1, depth L-2 nodes
 };
 
 SVO_DEV uint32_t spread3(uint32_t v) { return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4); } // 3 bits -> every third bit
@@ -198,42 +209,52 @@ SVO_DEV uint32_t nonzero_bytes4(uint32_t b) {
 	return ((t & 0x01010101u) * 0x01020408u) >> 24;
 }
 
-// One warp rasterizes BRICK_BPW consecutive bricks, each into its own grid; a block = BRICK_TILE consecutive bricks = one
-// element ("tile", numbered by a ticket) of the three output scans.  The scans' look-back runs once per tile, between
-// the rasterization and the write-out (measured with one brick per warp: 39 % of the warp time was spent at that
-// barrier; several bricks per warp amortise it).
+// leaves a brick can hold at most: 64 per large triangle (8 x 8 pixels, one voxel each) + its small triangles' leaves
+__global__ void __launch_bounds__(256) k_brick_bounds(BrickArgs a) {
+	const uint64_t brick = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	if (brick >= *a.n_bricks) return;
+	const uint32_t p0 = a.brick_first[brick], p1 = a.brick_first[brick + 1];
+	const uint64_t pr = a.pairs[p0];
+	uint32_t n = (p1 - p0) * 64u;
+	if (!((pr >> 32) & 1ull)) { // a small record (the brick's first pair)
+		n -= 64u;
+		const uint64_t ns = *a.n_small, code = pr >> 33;
+		for (uint64_t i = (uint32_t)pr; i < ns && (a.small_keys[i] >> (3 * BRICK_LOG)) == code; ++i) ++n;
+	}
+	a.bound[brick] = n < (uint32_t)BRICK_CELLS ? n : (uint32_t)BRICK_CELLS;
+}
+
+// One warp rasterizes BRICK_BPW consecutive bricks, one after the other, into its 512-cell grid; nothing is shared
+// between warps and no warp waits for another one: what a brick needs from its neighbours (the ranks of its nodes in the
+// level arrays) is left to k_brick_nodes, after three scans over the per-brick counts.
 #ifndef SVO_BRICK_BPW
 #define SVO_BRICK_BPW 4
 #endif
-constexpr int BRICK_BPW = SVO_BRICK_BPW, BRICK_TILE = BRICK_WARPS * BRICK_BPW;
-constexpr size_t BRICK_SMEM = (size_t)BRICK_TILE * BRICK_CELLS * 4;
+constexpr int BRICK_BPW = SVO_BRICK_BPW;
 constexpr int LT_WORDS = (int)(sizeof(LargeTri) / 8);
 static_assert(sizeof(LargeTri) % 8 == 0 && LT_WORDS <= 32 && BRICK_BPW < 32, "a LargeTri is staged by one warp, 8 bytes per lane");
 
-template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_build(BrickArgs a) {
-	SVO_DYN_SMEM(uint32_t, s_grid);                        // [BRICK_TILE][512] leaf words, 0 = empty
-	__shared__ uint32_t s_bal[BRICK_TILE][BRICK_CELLS / 32]; // occupancy of every grid, 32 cells per word
-	__shared__ uint32_t s_cnt[3][BRICK_WARPS];
-	__shared__ uint64_t s_base[3][BRICK_WARPS];
-	__shared__ uint32_t s_ticket;
-	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the triangle being rasterized, per warp and brick slot
+template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raster(BrickArgs a) {
+	__shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS];         // leaf words; valid where the cell's bit is set
+	__shared__ uint32_t s_bits[BRICK_WARPS][BRICK_CELLS / 32];
+	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the first triangle of every brick of the warp
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint64_t nb = *a.n_bricks;
-	const uint32_t n_tiles = (uint32_t)((nb + BRICK_TILE - 1) / BRICK_TILE);
-	const uint32_t tile = take_ticket(a.ticket, &s_ticket);
-	if (tile >= n_tiles) return; // (the grid is sized from the number of pairs, an upper bound)
+	const uint64_t brick0 = ((uint64_t)blockIdx.x * BRICK_WARPS + warp) * BRICK_BPW;
+	if (brick0 >= nb) return; // whole warp (no block barrier in this kernel)
+	uint32_t *g = s_grid[warp], *bits = s_bits[warp];
 	const uint32_t sx3 = spread3((uint32_t)lane & 7u), sy3a = spread3((uint32_t)lane >> 3), sy3b = spread3(((uint32_t)lane >> 3) + 4u);
 
 	// The metadata of the warp's bricks is fetched up front, lane q for brick q -- first pair index, Morton code, first
-	// pair -- and the first triangle of every brick is staged in shared memory by 22 lanes at once: three dependent
-	// round trips per BRICK_BPW bricks instead of four per brick (the kernel is bound by these latencies, not by HBM).
-	const uint64_t brick0 = (uint64_t)tile * BRICK_TILE + (uint32_t)(warp * BRICK_BPW);
+	// pair, slot in temp -- and the first triangle of every brick is staged in shared memory by 22 lanes at once: three
+	// dependent round trips per BRICK_BPW bricks instead of four per brick (this kernel is bound by latency, not by HBM).
 	uint32_t pf = 0;
-	uint64_t code = 0, pr_first = 0;
+	uint64_t code = 0, pr_first = 0, tof = 0;
 	if (lane <= BRICK_BPW && brick0 + lane <= nb) pf = a.brick_first[brick0 + lane];
 	if (lane < BRICK_BPW && brick0 + lane < nb) {
 		code = a.brick_code[brick0 + lane];
+		tof = a.toff[brick0 + lane];
 		pr_first = a.pairs[pf];
 	}
 #pragma unroll
@@ -243,26 +264,16 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_build
 			s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + (uint32_t)pr)[lane];
 	}
 
-	uint32_t c0q[BRICK_BPW]; // leaves per brick
-	uint64_t n1q[BRICK_BPW]; // occupancy of the brick's 64 depth L-1 nodes (bit = cell index >> 3)
-	uint64_t idq[BRICK_BPW]; // Morton code of the brick
-	uint32_t t0 = 0, t1 = 0, t2 = 0;
-#pragma unroll
+#pragma unroll 1
 	for (int q = 0; q < BRICK_BPW; ++q) {
 		const uint64_t brick = brick0 + q;
-		uint32_t *g = s_grid + (size_t)(warp * BRICK_BPW + q) * BRICK_CELLS;
-		{
-			uint4 *g4 = reinterpret_cast<uint4 *>(g);
-#pragma unroll
-			for (int k = 0; k < BRICK_CELLS / 128; ++k) g4[k * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-		}
+		if (brick >= nb) break; // warp-uniform
+		if (lane < BRICK_CELLS / 32) bits[lane] = 0u;
 		__syncwarp();
-		c0q[q] = 0, n1q[q] = 0, idq[q] = 0;
 		const uint32_t p0 = __shfl_sync(FULL_MASK, pf, q), p1 = __shfl_sync(FULL_MASK, pf, q + 1);
 		const uint64_t brick_id = __shfl_sync(FULL_MASK, code, q);
 		const uint64_t pr0 = __shfl_sync(FULL_MASK, pr_first, q);
-		if (brick >= nb) continue; // warp-uniform
-		idq[q] = brick_id;
+		const uint64_t to = __shfl_sync(FULL_MASK, tof, q);
 		const uint32_t bx = compact1by2_10((uint32_t)brick_id), by = compact1by2_10((uint32_t)(brick_id >> 1)),
 		               bz = compact1by2_10((uint32_t)(brick_id >> 2));
 		for (uint32_t p = p0; p < p1; ++p) {
@@ -274,7 +285,11 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_build
 					bool ok = i < ns;
 					uint64_t key = 0;
 					if (ok) key = a.small_keys[i], ok = (key >> (3 * BRICK_LOG)) == brick_id;
-					if (ok) g[(uint32_t)key & (BRICK_CELLS - 1)] = a.small_leaf[i];
+					if (ok) {
+						const uint32_t cell = (uint32_t)key & (BRICK_CELLS - 1);
+						g[cell] = a.small_leaf[i];
+						atomicOr(&bits[cell >> 5], 1u << (cell & 31u));
+					}
 					if (!__all_sync(FULL_MASK, ok)) break;
 				}
 			} else {
@@ -310,75 +325,69 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_build
 					}
 					if (ok) {
 						const uint32_t cell = (sx3 << wx) | ((h ? sy3b : sy3a) << wy) | (spread3(dz) << axis);
-						const uint32_t w = g[cell];
-						g[cell] = w ? leaf_accumulate(w, rgb) : leaf_first(rgb);
+						const uint32_t bit = 1u << (cell & 31u);
+						const uint32_t old = atomicOr(&bits[cell >> 5], bit);
+						g[cell] = (old & bit) ? leaf_accumulate(g[cell], rgb) : leaf_first(rgb);
 					}
 				}
 			}
 			__syncwarp();
 		}
-		// occupancy, 32 cells at a time (cell index = Morton code inside the brick = output order)
-		uint32_t c0 = 0;
-		uint64_t n1 = 0;
-#pragma unroll
-		for (int k = 0; k < BRICK_CELLS / 32; ++k) {
-			const uint32_t b = __ballot_sync(FULL_MASK, g[k * 32 + lane] != 0u);
-			if (lane == 0) s_bal[warp * BRICK_BPW + q][k] = b;
-			if (b) { // warp-uniform
-				c0 += (uint32_t)__popc(b);
-				n1 |= (uint64_t)nonzero_bytes4(b) << (4 * k);
-			}
+		// the brick's occupancy (lane k < 16 holds word k), its counts, and its leaves in cell order = Morton order
+		const uint32_t bw = lane < BRICK_CELLS / 32 ? bits[lane] : 0u;
+		const uint32_t pc = (uint32_t)__popc(bw);
+		const uint32_t inc = warp_inclusive_sum(pc, lane);
+		const uint32_t nb4 = nonzero_bytes4(bw); // the word's 4 depth L-1 nodes
+		const uint32_t c1 = warp_sum((uint32_t)__popc(nb4));
+		const uint32_t pair_any = nb4 | __shfl_down_sync(FULL_MASK, nb4, 1); // words 2m, 2m+1 = one depth L-2 node
+		const uint32_t c2 = (uint32_t)__popc(__ballot_sync(FULL_MASK, !(lane & 1) && pair_any != 0u));
+		const unsigned wm = __ballot_sync(FULL_MASK, bw != 0u);
+		if (lane < BRICK_CELLS / 32) a.bits[brick * (BRICK_CELLS / 32) + lane] = bw;
+		if (lane == 31) a.cnt[0][brick] = inc, a.cnt[1][brick] = c1, a.cnt[2][brick] = c2;
+		for (unsigned m = wm; m; m &= m - 1u) { // warp-uniform
+			const int k = __ffs((int)m) - 1;
+			const uint32_t b = __shfl_sync(FULL_MASK, bw, k), ex = __shfl_sync(FULL_MASK, inc - pc, k);
+			if ((b >> lane) & 1u) a.temp[to + ex + (uint32_t)__popc(b & lt_mask)] = g[k * 32 + lane];
 		}
-		c0q[q] = c0, n1q[q] = n1;
-		t0 += c0, t1 += (uint32_t)__popcll(n1);
-		t2 += (uint32_t)__popc(nonzero_bytes4((uint32_t)n1) | (nonzero_bytes4((uint32_t)(n1 >> 32)) << 4));
+		__syncwarp(); // the grid and the bits are reused by the next brick
 	}
-	if (lane == 0) s_cnt[0][warp] = t0, s_cnt[1][warp] = t1, s_cnt[2][warp] = t2;
-	__syncthreads();
-	if (warp < 3) { // one look-back chain per output array; lane w also turns the warps' counts into their offsets
-		const uint32_t mine = lane < BRICK_WARPS ? s_cnt[warp][lane] : 0u;
-		const uint32_t inc = warp_inclusive_sum(mine, lane);
-		const uint64_t total = __shfl_sync(FULL_MASK, inc, 31);
-		const uint64_t excl = lookback_exclusive(a.state + (uint64_t)warp * a.state_stride, tile, total, lane);
-		if (lane < BRICK_WARPS) s_base[warp][lane] = excl + inc - mine;
-		if (lane == 0 && tile == n_tiles - 1) *a.out.count[warp] = excl + total;
-	}
-	__syncthreads();
-	if (t0 == 0u) return; // warp-uniform (no barrier follows)
-	uint64_t base0 = s_base[0][warp], base1 = s_base[1][warp], base2 = s_base[2][warp];
+}
 
+// The ranks of a brick's nodes are known (scans of the per-brick counts): write the level arrays of the three deepest
+// levels.  One warp per brick; lane j and j + 32 own the depth L-1 nodes j, j + 32, lanes 0..7 the depth L-2 nodes.
+__global__ void __launch_bounds__(BRICK_BLOCK) k_brick_nodes(BrickArgs a) {
+	const int lane = threadIdx.x & 31;
+	const uint64_t brick = ((uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x) >> 5;
+	const uint64_t nb = *a.n_bricks;
+	if (brick == 0 && lane < 3) *a.count[lane] = a.rank[lane][a.n_bound];
+	if (brick >= nb) return;
+	const uint32_t bw = lane < BRICK_CELLS / 32 ? a.bits[brick * (BRICK_CELLS / 32) + lane] : 0u;
+	const uint32_t pc = (uint32_t)__popc(bw);
+	const uint32_t ex = warp_inclusive_sum(pc, lane) - pc; // leaves of the brick in front of word `lane`
+	const uint32_t nb4 = nonzero_bytes4(bw);
+	// n1: bit j = depth L-1 node j (cells 8j .. 8j+7) is occupied
+	const uint32_t n1_lo = __reduce_or_sync(FULL_MASK, lane < 8 ? nb4 << (4 * lane) : 0u);
+	const uint32_t n1_hi = __reduce_or_sync(FULL_MASK, (lane >= 8 && lane < 16) ? nb4 << (4 * (lane - 8)) : 0u);
+	const uint64_t n1 = (uint64_t)n1_lo | ((uint64_t)n1_hi << 32);
+	const uint32_t n2 = nonzero_bytes4(n1_lo) | (nonzero_bytes4(n1_hi) << 4);
+	const uint64_t to = a.toff[brick], r1 = a.rank[1][brick], r2 = a.rank[2][brick];
+	const uint64_t code = a.brick_code[brick];
 #pragma unroll
-	for (int q = 0; q < BRICK_BPW; ++q) {
-		const uint64_t n1 = n1q[q];
-		if (n1 == 0ull) continue; // warp-uniform
-		const uint32_t *g = s_grid + (size_t)(warp * BRICK_BPW + q) * BRICK_CELLS;
-		const uint32_t n2 = nonzero_bytes4((uint32_t)n1) | (nonzero_bytes4((uint32_t)(n1 >> 32)) << 4); // depth L-2 nodes
-		uint32_t run0 = 0;
-		for (int k = 0; k < BRICK_CELLS / 32; ++k) {
-			const uint32_t nm = (uint32_t)(n1 >> (4 * k)) & 0xfu; // the depth L-1 nodes of cells 32k .. 32k+31
-			if (!nm) continue;                                    // warp-uniform
-			const uint32_t b = s_bal[warp * BRICK_BPW + q][k];
-			const uint32_t run1 = (uint32_t)__popcll(n1 & ((1ull << (4 * k)) - 1ull));
-			if ((b >> lane) & 1u) {
-				const uint64_t u = base0 + run0 + (uint32_t)__popc(b & lt_mask);
-				a.out.leaf[u] = g[k * 32 + lane];
-				a.out.slot0[u] = (unsigned char)(lane & 7);
-			}
-			if (lane < 4 && ((nm >> lane) & 1u)) {
-				const uint64_t u1 = base1 + run1 + (uint32_t)__popc(nm & lt_mask);
-				a.out.first1[u1] = (uint32_t)(base0 + run0 + (uint32_t)__popc(b & ((1u << (8 * lane)) - 1u)));
-				a.out.slot1[u1] = (unsigned char)((k * 4 + lane) & 7);
-			}
-			// the first occupied word of a depth L-2 node (64 cells = words 2m, 2m+1) also writes that node
-			if (lane == 0 && (!(k & 1) || !((n1 >> (4 * (k - 1))) & 0xfull))) {
-				const uint32_t m = (uint32_t)k >> 1;
-				const uint64_t u2 = base2 + (uint32_t)__popc(n2 & ((1u << m) - 1u));
-				a.out.first2[u2] = (uint32_t)(base1 + run1);
-				a.out.keys_top[u2] = (idq[q] << 3) | (uint64_t)m;
-			}
-			run0 += (uint32_t)__popc(b);
+	for (int h = 0; h < 2; ++h) {
+		const int j = lane + 32 * h, k = j >> 2, by = j & 3;
+		const uint32_t bwk = __shfl_sync(FULL_MASK, bw, k), exk = __shfl_sync(FULL_MASK, ex, k);
+		const uint32_t m = (bwk >> (8 * by)) & 0xffu;
+		if (m) {
+			const uint64_t u1 = r1 + (uint32_t)__popcll(n1 & ((1ull << j) - 1ull));
+			a.first1[u1] = (uint32_t)(to + exk + (uint32_t)__popc(bwk & ((1u << (8 * by)) - 1u)));
+			a.mask1[u1] = (unsigned char)m;
+			a.slot1[u1] = (unsigned char)(j & 7);
 		}
-		base0 += c0q[q], base1 += (uint32_t)__popcll(n1), base2 += (uint32_t)__popc(n2);
+	}
+	if (lane < 8 && ((n2 >> lane) & 1u)) {
+		const uint64_t u2 = r2 + (uint32_t)__popc(n2 & ((1u << lane) - 1u));
+		a.first2[u2] = (uint32_t)(r1 + (uint32_t)__popcll(n1 & ((1ull << (8 * lane)) - 1ull)));
+		a.keys_top[u2] = (code << 3) | (uint64_t)lane;
 	}
 }
 

@@ -159,8 +159,8 @@ struct svo_builder {
 	ScanScratch scan_scratch;
 	DevBuf<uint64_t> rf_cnt01, rf_cnt2, rf_pre01, rf_pre2; // per reduce tile: run counts and their exclusive prefixes
 	// brick path (brick.cuh)
-	DevBuf<uint64_t> pairs_a, pairs_b, pair_idx, brick_state, brick_scalars;
-	DevBuf<uint32_t> pair_flags, brick_first, small_leaf;
+	DevBuf<uint64_t> pairs_a, pairs_b, pair_idx, brick_u64, brick_scalars;
+	DevBuf<uint32_t> pair_flags, brick_first, small_leaf, brick_u32, brick_temp;
 	uint64_t n_pairs = 0, n_small_leaves = 0; // of the last build
 	int path = 0;                             // 0: every fragment sorted; 1: bricks
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
@@ -481,7 +481,9 @@ static bool brick_path_wanted(const svo_voxelizer *v) {
 	}
 	if (v->key_level < 4 || v->n_frag_large == 0 || v->n_large == 0 || g_build_path == 0) return false;
 	if (g_build_path == 1) return true;
-	return false; // (automatic choice disabled while the brick kernel is slower than the sort it replaces)
+	// enough large-triangle fragments to pay for the path's extra launches (a Sponza-sized build of 5e6 fragments is
+	// launch bound: 0.38 ms sorted, 0.57 ms binned), and at least a fifth of all fragments
+	return v->n_frag_large >= (8ull << 20) && v->n_frag_large * 4 >= v->n_frag_small;
 }
 static dim3 brick_pair_grid(const svo_voxelizer *v) {
 	// one warp per large triangle; few triangles with hundreds of tile rows each: deal a triangle's rows out over up to 32 warps
@@ -858,8 +860,8 @@ void svo_builder_destroy(svo_builder *b) {
 	b->sort_scratch.release(s);
 	b->scan_scratch.state.release(s), b->scan_scratch.ticket.release(s);
 	b->rf_cnt01.release(s), b->rf_cnt2.release(s), b->rf_pre01.release(s), b->rf_pre2.release(s);
-	b->pairs_a.release(s), b->pairs_b.release(s), b->pair_idx.release(s), b->brick_state.release(s), b->brick_scalars.release(s);
-	b->pair_flags.release(s), b->brick_first.release(s), b->small_leaf.release(s);
+	b->pairs_a.release(s), b->pairs_b.release(s), b->pair_idx.release(s), b->brick_u64.release(s), b->brick_scalars.release(s);
+	b->pair_flags.release(s), b->brick_first.release(s), b->small_leaf.release(s), b->brick_u32.release(s), b->brick_temp.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
 	release_export(b);
@@ -889,7 +891,7 @@ static int reduce_sorted(svo_builder *b, const uint64_t *sorted, uint64_t F, uin
 // The brick path of svo_builder_prepare (brick.cuh): small triangles' fragments sorted and reduced on their own, large
 // triangles binned; on return *keys_top holds the depth L-2 keys (counts[L-2] of them) and *free_buf is free.
 //   ev[0..1] small fragments: sort + reduce + small records (+ the read-back of their number)
-//   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_build
+//   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_raster, scans, k_brick_nodes
 static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_off, const uint64_t *slot_off, uint64_t **free_buf,
                           uint64_t **keys_top) {
 	svo_voxelizer *v = b->vox;
@@ -940,36 +942,41 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	                 (const uint64_t *)b->pair_idx.p, n_pairs, b->brick_first.p, brick_code);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
 
-	const uint32_t tiles_ub = div_up(n_pairs, BRICK_TILE);
-	SVO_TRY(b->brick_state.reserve(3ull * (tiles_ub + 1), s));
-	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_state.p, 0, 3ull * (tiles_ub + 1) * sizeof(uint64_t), s));
+	// per-brick arrays are sized for the upper bound "one brick per pair"; entries past the real number of bricks stay 0
+	const uint64_t nbd = n_pairs;
+	const uint64_t temp_cap = 64ull * npl + b->n_small_leaves;
+	if (temp_cap >= (1ull << 32)) return fail(SVO_ERR_CAPACITY, "brick path: more than 2^32 leaf slots");
+	SVO_TRY(b->brick_u32.reserve(nbd * (1 + 3 + BRICK_CELLS / 32), s));
+	SVO_TRY(b->brick_u64.reserve((nbd + 1) * 4, s));
+	SVO_TRY(b->brick_temp.reserve(temp_cap, s));
+	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_u32.p, 0, nbd * 4 * sizeof(uint32_t), s)); // bound + the three counts
 	BrickArgs a{};
 	a.pairs = pairs, a.brick_first = b->brick_first.p, a.brick_code = brick_code, a.n_bricks = b->pair_idx.p + n_pairs;
 	a.large = v->large.p, a.luv = v->large_uv.p, a.tv = v->scene->view.tex, a.rp = v->rp;
 	a.small_keys = B, a.small_leaf = b->small_leaf.p, a.n_small = d_nsl;
-	a.out.leaf = b->leaf.p;
-	a.out.slot0 = b->slot.p + slot_off[L];
-	a.out.first1 = b->first.p + first_off[L];
-	a.out.slot1 = b->slot.p + slot_off[L - 1], a.out.first2 = b->first.p + first_off[L - 1];
-	a.out.keys_top = A;
-	for (uint32_t j = 0; j < 3; ++j) a.out.count[j] = b->counts.p + (L - j);
-	a.state = b->brick_state.p, a.state_stride = tiles_ub + 1;
-	a.ticket = b->tickets.p; // [0]: unused by the level loop (it starts at index K)
-#ifndef SVO_EMU
-	{
-		static bool attr_set[64] = {}; // per device
-		const int di = b->device >= 0 && b->device < 64 ? b->device : 0;
-		if (!attr_set[di]) {
-			SVO_CUDA_TRY(cudaFuncSetAttribute(k_brick_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRICK_SMEM));
-			SVO_CUDA_TRY(cudaFuncSetAttribute(k_brick_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRICK_SMEM));
-			attr_set[di] = true;
-		}
-	}
-#endif
+	a.bound = b->brick_u32.p;
+	for (int j = 0; j < 3; ++j) a.cnt[j] = b->brick_u32.p + nbd * (1 + j);
+	a.bits = b->brick_u32.p + nbd * 4;
+	uint64_t *toff = b->brick_u64.p;
+	a.toff = toff;
+	for (int j = 0; j < 3; ++j) a.rank[j] = b->brick_u64.p + (nbd + 1) * (1 + j);
+	a.n_bound = nbd;
+	a.temp = b->brick_temp.p;
+	a.first1 = b->first.p + first_off[L];
+	a.mask1 = b->slot.p + slot_off[L]; // (the leaves' slot array of the fragment path: one byte per leaf, free here)
+	a.slot1 = b->slot.p + slot_off[L - 1], a.first2 = b->first.p + first_off[L - 1];
+	a.keys_top = A;
+	for (uint32_t j = 0; j < 3; ++j) a.count[j] = b->counts.p + (L - j);
+	SVO_LAUNCH_INDEP(div_up(nbd, 256), 256, s, k_brick_bounds, a);
+	SVO_TRY(exclusive_scan((const uint32_t *)a.bound, toff, nbd, b->scan_scratch, s));
+	const uint32_t rgrid = div_up(nbd, (uint64_t)BRICK_WARPS * BRICK_BPW);
 	if (v->scene->textured)
-		SVO_LAUNCH(tiles_ub, BRICK_BLOCK, BRICK_SMEM, s, k_brick_build<true>, a);
+		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<true>, a);
 	else
-		SVO_LAUNCH(tiles_ub, BRICK_BLOCK, BRICK_SMEM, s, k_brick_build<false>, a);
+		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
+	for (int j = 0; j < 3; ++j)
+		SVO_TRY(exclusive_scan((const uint32_t *)a.cnt[j], b->brick_u64.p + (nbd + 1) * (1 + j), nbd, b->scan_scratch, s));
+	SVO_LAUNCH(div_up(nbd * 32, BRICK_BLOCK), BRICK_BLOCK, 0, s, k_brick_nodes, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 	SVO_CUDA_TRY(cudaGetLastError());
 	*keys_top = A, *free_buf = B;
@@ -1067,6 +1074,10 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 		ep.slot[d] = b->slot.p + slot_off[d];
 	}
 	ep.leaf = b->leaf.p;
+	if (b->path == 1) { // brick path: the leaves stay where the bricks put them; depth L-1 nodes carry a child mask instead
+		ep.leaf = b->brick_temp.p;
+		ep.leaf_mask = b->slot.p + slot_off[L];
+	}
 	b->range_bytes = blocks * 8 * sizeof(uint32_t); // (counter + 1) * 8 * 4, src/OctreeBuilder.cpp:212-214
 	b->prepared = true;
 	return SVO_OK;
