@@ -256,6 +256,7 @@ def run_ours(args):
     # -------- device-resident arm: inputs already in HBM, handles created (count pass done) ----------------
     phases_acc = {k: 0.0 for k in api.PHASES}
     sort_passes = 0
+    brick_acc, brick_counts, build_path = {"raster": 0.0, "scans": 0.0, "nodes": 0.0}, None, 0
     # one device holds levels <= 13 in a 64-bit fragment; level 14 runs as 8 cube-local octant builds ("virtual shards")
     single = world == 1 and level <= 13
     if single:
@@ -285,14 +286,20 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         step()
+        bld = None
         if single:  # per-phase cudaEvent times recorded by the library on the same stream
-            ms, sort_passes = builder.LastMs()
-            for k in api.PHASES:
-                phases_acc[k] += ms[k]
+            bld = builder
         elif rank == 0 and getattr(sh, "slab", False) and sh.builders and sh.builders[0].GetLeafCount():
-            ms, sort_passes = sh.builders[0].LastMs()  # rank 0's own slab (the roofline line below describes this rank)
+            bld = sh.builders[0]  # rank 0's own slab (the roofline line below describes this rank)
+        if bld is not None:
+            ms, sort_passes = bld.LastMs()
             for k in api.PHASES:
                 phases_acc[k] += ms[k]
+            build_path = bld.BuildPath()
+            if build_path == 1:
+                brick_counts, bms = bld.BrickStats()
+                for k in brick_acc:
+                    brick_acc[k] += bms[k]
     e1.record(stream)
     barrier()
     launches = int(lib.dll.svo_launch_count()) - launches0
@@ -380,26 +387,49 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        roofline = None
-        if sort_passes and phases_acc["sort_passes"] > 0:
+        roofline, kernels = None, None
+        frags_rank0 = frags if single else sh.vox[0].GetVoxelFragmentCount()
+        traffic_db = {}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic_db = json.load(f)
+            except Exception:
+                traffic_db = {}
+        if build_path == 1 and brick_acc["raster"] > 0:
+            # Brick path: the large triangles never become fragments; the dominant kernel is k_brick_raster.  Its
+            # algorithmic bytes: one 8-byte pair per (brick, triangle), per brick its table entries (first pair 4, code 8,
+            # temp slot 8) in and occupancy bits 64 + counts 12 out, and one 4-byte leaf word out per leaf.
+            per_launch_ms = brick_acc["raster"] / args.steps
+            leaves_rank0 = leaves if single else sh.builders[0].GetLeafCount()
+            alg_bytes = 8.0 * brick_counts["pairs"] + 96.0 * brick_counts["bricks"] + 4.0 * leaves_rank0
+            achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+            t = traffic_db.get("k_brick_raster", {})
+            roofline = {"bound": "hbm", "kernel": "k_brick_raster", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": t.get("dram_bytes_per_launch") if single else None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
+                        "launches_per_step": 1, "rank": 0,
+                        "limiter": "instruction issue, not HBM: the kernel rasterizes 64 pixels per (brick, triangle) pair with exact "
+                                   "64-bit edge functions and an fp64 depth plane and moves ~6 bytes per fragment",
+                        "issue_slots_busy_pct": t.get("issue_slots_busy_pct"),
+                        "pairs": brick_counts["pairs"], "bricks": brick_counts["bricks"]}
+            # the step's memory-bound kernel next to it: k_emit_octree writes every 32-byte node block once and reads the
+            # leaf words (4 B), and per depth L-1 node first (4 B) + mask (1 B) + slot (1 B)
+            emit_ms = phases_acc["emit"] / args.steps
+            emit_bytes = float(octree_bytes) + 4.0 * leaves_rank0
+            kernels = [{"kernel": "k_emit_octree", "ms": emit_ms, "algorithmic_bytes": emit_bytes,
+                        "achieved_gbs": emit_bytes / (emit_ms * 1e-3) / 1e9, "frac_of_hbm_peak": emit_bytes / (emit_ms * 1e-3) / 1e9 / peak,
+                        "note": "phase time: includes the size read-back in front of the launch"}] if single and emit_ms > 0 else None
+        elif sort_passes and phases_acc["sort_passes"] > 0:
             per_launch_ms = phases_acc["sort_passes"] / args.steps / sort_passes
             # one read + one write of every 8-byte fragment per onesweep pass (N > 1: the fragments of rank 0's first part)
-            alg_bytes = 16.0 * (frags if single else sh.vox[0].GetVoxelFragmentCount())
+            alg_bytes = 16.0 * frags_rank0
             achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tp):
-                try:
-                    with open(tp) as f:
-                        traffic = json.load(f).get("k_onesweep_pass", {}).get("dram_bytes_per_launch")
-                except Exception:
-                    traffic = None
             roofline = {"bound": "hbm", "kernel": "k_onesweep_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
+                        "frac": achieved / peak, "traffic": traffic_db.get("k_onesweep_pass", {}).get("dram_bytes_per_launch") if single else None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
                         "launches_per_step": sort_passes, "rank": 0}
-            if not single:
-                roofline["traffic"] = None  # the ncu capture is of the single-GPU launch
         cpu_baseline, parity = None, None
         if single and not args.no_cpu_baseline:
             keep = {}
@@ -419,8 +449,11 @@ def run_ours(args):
                                       f"octant-sharded x{world}, NVLink subtree gather")
                                       + (f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})" if world > 1 else "")},
             "build_ms": ms_per_step,
-            "phases_ms": {k: v / args.steps for k, v in phases_acc.items()} if sort_passes else None,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_check": parity, "stitch_check": stitch,
+            "build_path": "bricks" if build_path == 1 else "fragment sort",
+            "phases_ms": ({(api.BRICK_PHASES[i] if build_path == 1 else k): phases_acc[k] / args.steps for i, k in enumerate(api.PHASES)}
+                          if (sort_passes or build_path == 1) else None),
+            "brick_ms": {k: v / args.steps for k, v in brick_acc.items()} if build_path == 1 else None,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity_check": parity, "stitch_check": stitch,
             "e2e": {"value": leaves / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "note": "host wall clock around pinned-host mesh -> Scene/Voxelizer(count pass)/OctreeBuilder create -> "

@@ -25,6 +25,8 @@ LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
 
 CENTER, CONSERVATIVE_EXACT, CONSERVATIVE_DILATE = 0, 1, 2
 PHASES = ("raster", "sort_hist", "sort_passes", "reduce", "levels", "emit")
+# what the same six slots hold after a build on the brick path (svo_builder_build_path() == 1)
+BRICK_PHASES = ("raster_small", "small_sort_reduce", "pairs", "bricks", "levels", "emit")
 
 
 class SvoError(RuntimeError):
@@ -95,6 +97,7 @@ SYMBOLS = [
     ("svo_debug_profile_passes", None, [C.c_int]),
     ("svo_debug_set_build_path", None, [C.c_int]),
     ("svo_builder_build_path", C.c_int, [_P]),
+    ("svo_builder_brick_stats", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
     ("svo_builder_sort_step_ms", C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
     ("svo_octree_raymarch_leaf", C.c_int, [C.c_int, _P, C.c_uint64, _P, _P, _P, _P]),
     ("svo_device_malloc", C.c_int, [C.c_int, C.c_uint64, C.POINTER(_P)]),
@@ -470,6 +473,18 @@ class OctreeBuilder:
         np_ = C.c_uint32()
         self.lib.check(self.lib.dll.svo_builder_last_ms(self._h, ms, C.byref(np_)))
         return {k: float(ms[i]) for i, k in enumerate(PHASES)}, int(np_.value)
+
+    def BuildPath(self) -> int:
+        """0: every fragment emitted, sorted and reduced; 1: large triangles binned to bricks (brick.cuh)."""
+        return int(self.lib.dll.svo_builder_build_path(self._h))
+
+    def BrickStats(self):
+        """({pairs, bricks, small_leaves}, {raster, scans, nodes} in ms) of the last brick-path build."""
+        c = (C.c_uint64 * 3)()
+        ms = (C.c_float * 3)()
+        self.lib.check(self.lib.dll.svo_builder_brick_stats(self._h, c, ms))
+        return (dict(pairs=int(c[0]), bricks=int(c[1]), small_leaves=int(c[2])),
+                dict(raster=float(ms[0]), scans=float(ms[1]), nodes=float(ms[2])))
 
     def SortStepMs(self):
         """Milliseconds of each kernel of the last sort (needs svo_debug_profile_passes(1) before the build)."""

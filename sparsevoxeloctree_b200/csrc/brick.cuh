@@ -167,14 +167,19 @@ __global__ void __launch_bounds__(256)
                          uint32_t *__restrict__ brick_first, uint64_t *__restrict__ brick_code) {
 	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	if (i >= n) return;
-	if (flags[i]) brick_first[idx[i]] = (uint32_t)i, brick_code[idx[i]] = pairs[i] >> 33;
+	if (flags[i]) { // Morton code of the brick in bits 0..29, its coordinates (10 bits each) from bit 32
+		const uint64_t m = pairs[i] >> 33;
+		brick_first[idx[i]] = (uint32_t)i;
+		brick_code[idx[i]] = m | ((uint64_t)compact1by2_10((uint32_t)m) << 32) | ((uint64_t)compact1by2_10((uint32_t)(m >> 1)) << 42) |
+		                     ((uint64_t)compact1by2_10((uint32_t)(m >> 2)) << 52);
+	}
 	if (i == n - 1) brick_first[idx[n]] = (uint32_t)n; // idx[n] = number of bricks
 }
 
 struct BrickArgs {
 	const uint64_t *pairs;       // sorted by brick (stable)
 	const uint32_t *brick_first; // [n_bricks + 1] first pair of every brick
-	const uint64_t *brick_code;  // [n_bricks] Morton code of every brick
+	const uint64_t *brick_code;  // [n_bricks] Morton code of every brick (bits 0..29) and its x, y, z (bits 32.., 42.., 52..)
 	const uint64_t *n_bricks;    // device scalar
 	const LargeTri *large;
 	const UvMap *luv;
@@ -188,7 +193,7 @@ struct BrickArgs {
 	const uint64_t *toff;   // exclusive scan of bound[]: the brick's first slot in temp
 	uint32_t *temp;         // leaf words, dense inside every brick, in Morton order
 	uint32_t *bits;         // [16] occupancy of the brick's 512 cells; byte j = child mask of its depth L-1 node j
-	uint32_t *cnt[3];       // leaves, depth L-1 nodes, depth L-2 nodes of the brick
+	uint32_t *cnt[3];       // leaves, depth L-1 nodes, depth L-2 nodes of the brick (three consecutive arrays of n_bound)
 	const uint64_t *rank[3]; // exclusive scans of cnt[] (rank[j][n] = total)
 	uint64_t n_bound;       // entries of the per-brick arrays
 	// the three deepest levels for k_emit_octree / k_parent_compact
@@ -200,7 +205,14 @@ struct BrickArgs {
 	uint64_t *count[3];      // device scalars: leaves, depth L-1, depth L-2 nodes
 };
 
-SVO_DEV uint32_t spread3(uint32_t v) { return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4); } // 3 bits -> every third bit
+// 3 bits -> every third bit (0, 1, 8, 9, 64, 65, 72, 73): one byte permute picks the entry of a table held in two registers
+SVO_DEV uint32_t spread3(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(0x09080100u, 0x49484140u, v);
+#else
+	return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4);
+#endif
+}
 // bit i of the result = byte i of b is not zero
 SVO_DEV uint32_t nonzero_bytes4(uint32_t b) {
 	uint32_t t = b | (b >> 4);
@@ -228,40 +240,53 @@ __global__ void __launch_bounds__(256) k_brick_bounds(BrickArgs a) {
 // between warps and no warp waits for another one: what a brick needs from its neighbours (the ranks of its nodes in the
 // level arrays) is left to k_brick_nodes, after three scans over the per-brick counts.
 #ifndef SVO_BRICK_BPW
-#define SVO_BRICK_BPW 4
+#define SVO_BRICK_BPW 8
 #endif
 constexpr int BRICK_BPW = SVO_BRICK_BPW;
 constexpr int LT_WORDS = (int)(sizeof(LargeTri) / 8);
 static_assert(sizeof(LargeTri) % 8 == 0 && LT_WORDS <= 32 && BRICK_BPW < 32, "a LargeTri is staged by one warp, 8 bytes per lane");
 
+// coverage of pixel (X + dx, Y + dy), 0 <= dx, dy < 8: the three edge functions (pixel_covered) evaluated at (X, Y) and
+// stepped -- ea = 256 A, eb = 256 B with 32-bit A, B (tri_setup), so the step 256 (A dx + B dy) is one 32-bit product sum
+SVO_DEV void brick_edges(const TriSetup &ts, int32_t X, int32_t Y, int32_t dx, int32_t dy, int64_t (&e)[3]) {
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		const int64_t e0 = ts.ea[i] * (int64_t)X + ts.eb[i] * (int64_t)Y + ts.ec[i];
+		const int32_t step = (int32_t)(ts.ea[i] >> 8) * dx + (int32_t)(ts.eb[i] >> 8) * dy;
+		e[i] = e0 + ((int64_t)step << 8);
+	}
+}
+
 template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raster(BrickArgs a) {
 	__shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS];         // leaf words; valid where the cell's bit is set
 	__shared__ uint32_t s_bits[BRICK_WARPS][BRICK_CELLS / 32];
 	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the first triangle of every brick of the warp
+	__align__(16) __shared__ uint64_t s_meta[BRICK_WARPS][BRICK_BPW][4];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint64_t nb = *a.n_bricks;
 	const uint64_t brick0 = ((uint64_t)blockIdx.x * BRICK_WARPS + warp) * BRICK_BPW;
 	if (brick0 >= nb) return; // whole warp (no block barrier in this kernel)
 	uint32_t *g = s_grid[warp], *bits = s_bits[warp];
-	const uint32_t sx3 = spread3((uint32_t)lane & 7u), sy3a = spread3((uint32_t)lane >> 3), sy3b = spread3(((uint32_t)lane >> 3) + 4u);
+	const int32_t dx = lane & 7, dy = lane >> 3;
+	const uint32_t sx3 = spread3((uint32_t)dx), sy3a = spread3((uint32_t)dy), sy3b = spread3((uint32_t)dy + 4u);
 
-	// The metadata of the warp's bricks is fetched up front, lane q for brick q -- first pair index, Morton code, first
-	// pair, slot in temp -- and the first triangle of every brick is staged in shared memory by 22 lanes at once: three
-	// dependent round trips per BRICK_BPW bricks instead of four per brick (this kernel is bound by latency, not by HBM).
-	uint32_t pf = 0;
-	uint64_t code = 0, pr_first = 0, tof = 0;
-	if (lane <= BRICK_BPW && brick0 + lane <= nb) pf = a.brick_first[brick0 + lane];
+	// The metadata of the warp's bricks is fetched up front, lane q for brick q -- pair range, Morton code, first pair,
+	// slot in temp -- and the first triangle of every brick is staged in shared memory by 22 lanes at once: three
+	// dependent round trips per BRICK_BPW bricks instead of four per brick (latency, not HBM, is what this kernel waits for).
 	if (lane < BRICK_BPW && brick0 + lane < nb) {
-		code = a.brick_code[brick0 + lane];
-		tof = a.toff[brick0 + lane];
-		pr_first = a.pairs[pf];
+		const uint32_t p0 = a.brick_first[brick0 + lane], p1 = a.brick_first[brick0 + lane + 1];
+		uint64_t *m = s_meta[warp][lane];
+		m[0] = (uint64_t)p0 | ((uint64_t)p1 << 32);
+		m[1] = a.brick_code[brick0 + lane];
+		m[2] = a.pairs[p0];
+		m[3] = a.toff[brick0 + lane];
 	}
+	__syncwarp();
 #pragma unroll
 	for (int q = 0; q < BRICK_BPW; ++q) {
-		const uint64_t pr = __shfl_sync(FULL_MASK, pr_first, q);
-		if (brick0 + q < nb && ((pr >> 32) & 1ull) && lane < LT_WORDS)
-			s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + (uint32_t)pr)[lane];
+		if (brick0 + q >= nb) break;
+		const uint64_t pr = s_meta[warp][q][2];
+		if (((pr >> 32) & 1ull) && lane < LT_WORDS) s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + (uint32_t)pr)[lane];
 	}
 
 #pragma unroll 1
@@ -270,12 +295,15 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 		if (brick >= nb) break; // warp-uniform
 		if (lane < BRICK_CELLS / 32) bits[lane] = 0u;
 		__syncwarp();
-		const uint32_t p0 = __shfl_sync(FULL_MASK, pf, q), p1 = __shfl_sync(FULL_MASK, pf, q + 1);
-		const uint64_t brick_id = __shfl_sync(FULL_MASK, code, q);
-		const uint64_t pr0 = __shfl_sync(FULL_MASK, pr_first, q);
-		const uint64_t to = __shfl_sync(FULL_MASK, tof, q);
-		const uint32_t bx = compact1by2_10((uint32_t)brick_id), by = compact1by2_10((uint32_t)(brick_id >> 1)),
-		               bz = compact1by2_10((uint32_t)(brick_id >> 2));
+		const ulonglong2 m01 = *reinterpret_cast<const ulonglong2 *>(&s_meta[warp][q][0]);
+		const ulonglong2 m23 = *reinterpret_cast<const ulonglong2 *>(&s_meta[warp][q][2]);
+		const uint32_t p0 = (uint32_t)m01.x, p1 = (uint32_t)(m01.x >> 32);
+		const uint64_t brick_id = m01.y & 0x3fffffffull, pr0 = m23.x;
+		const uint32_t bxyz = (uint32_t)(m01.y >> 32);
+		const uint32_t to = (uint32_t)m23.y; // (the host checks that temp has fewer than 2^32 slots)
+		// first voxel of the brick, full-grid coordinates
+		const uint32_t vb0 = a.rp.origin[0] + 8u * (bxyz & 1023u), vb1 = a.rp.origin[1] + 8u * ((bxyz >> 10) & 1023u),
+		               vb2 = a.rp.origin[2] + 8u * (bxyz >> 20);
 		for (uint32_t p = p0; p < p1; ++p) {
 			const uint64_t pr = p == p0 ? pr0 : a.pairs[p]; // warp-uniform
 			if (!((pr >> 32) & 1ull)) {
@@ -293,8 +321,8 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 					if (!__all_sync(FULL_MASK, ok)) break;
 				}
 			} else {
-				// one large triangle: the brick's 8x8 pixels, two per lane; a triangle puts at most one fragment into a
-				// voxel, so the read-modify-write of a cell needs no atomics, and triangles follow each other in order
+				// one large triangle: the brick's 8x8 pixels, two per lane (rows dy and dy + 4); a triangle puts at most one
+				// fragment into a voxel, so the fold of a cell needs no atomics, and triangles follow each other in order
 				const uint32_t li = (uint32_t)pr;
 				if (p != p0) { // (the first pair's triangle is staged already)
 					if (lane < LT_WORDS) s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + li)[lane];
@@ -305,16 +333,21 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 				const uint32_t axis = ts.axis;
 				uint32_t wx, wy;
 				screen_axes(axis, wx, wy);
-				const uint32_t tcx = wx == 0u ? bx : (wx == 1u ? by : bz), tcy = wy == 0u ? bx : (wy == 1u ? by : bz);
-				const uint32_t tcz = axis == 0u ? bx : (axis == 1u ? by : bz);
-				const int32_t px = (int32_t)(pick3(a.rp.origin, wx) + tcx * 8u) + (lane & 7);
-				const int32_t py0 = (int32_t)(pick3(a.rp.origin, wy) + tcy * 8u) + (lane >> 3);
-				const uint32_t z_base = pick3(a.rp.origin, axis) + tcz * 8u;
+				const int32_t X = (int32_t)(wx == 0u ? vb0 : (wx == 1u ? vb1 : vb2)), Y = (int32_t)(wy == 0u ? vb0 : (wy == 1u ? vb1 : vb2));
+				const uint32_t z_base = axis == 0u ? vb0 : (axis == 1u ? vb1 : vb2);
+				const int32_t px = X + dx;
 				const uint32_t tex = TEX ? lt.textured : 0u;
+				int64_t e[3];
+				brick_edges(ts, X, Y, dx, dy, e);
+				const bool in_x = px >= ts.px0 && px <= ts.px1;
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
-					const int32_t py = py0 + 4 * h;
-					bool ok = px >= ts.px0 && px <= ts.px1 && py >= ts.py0 && py <= ts.py1 && pixel_covered(ts, px, py);
+					const int32_t py = Y + dy + 4 * h;
+					if (h) {
+#pragma unroll
+						for (int i = 0; i < 3; ++i) e[i] += ts.eb[i] * 4; // four rows down
+					}
+					bool ok = in_x && py >= ts.py0 && py <= ts.py1 && (e[0] | e[1] | e[2]) >= 0;
 					uint32_t uz = 0, rgb = lt.rgb;
 					ok = ok && pixel_fragment(ts, a.rp.res, px, py, uz);
 					const uint32_t dz = uz - z_base;
@@ -333,61 +366,78 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 			}
 			__syncwarp();
 		}
-		// the brick's occupancy (lane k < 16 holds word k), its counts, and its leaves in cell order = Morton order
+		// the brick's occupancy (lane k < 16 holds word k) and its counts
 		const uint32_t bw = lane < BRICK_CELLS / 32 ? bits[lane] : 0u;
-		const uint32_t pc = (uint32_t)__popc(bw);
-		const uint32_t inc = warp_inclusive_sum(pc, lane);
 		const uint32_t nb4 = nonzero_bytes4(bw); // the word's 4 depth L-1 nodes
 		const uint32_t c1 = warp_sum((uint32_t)__popc(nb4));
 		const uint32_t pair_any = nb4 | __shfl_down_sync(FULL_MASK, nb4, 1); // words 2m, 2m+1 = one depth L-2 node
 		const uint32_t c2 = (uint32_t)__popc(__ballot_sync(FULL_MASK, !(lane & 1) && pair_any != 0u));
-		const unsigned wm = __ballot_sync(FULL_MASK, bw != 0u);
 		if (lane < BRICK_CELLS / 32) a.bits[brick * (BRICK_CELLS / 32) + lane] = bw;
-		if (lane == 31) a.cnt[0][brick] = inc, a.cnt[1][brick] = c1, a.cnt[2][brick] = c2;
-		for (unsigned m = wm; m; m &= m - 1u) { // warp-uniform
-			const int k = __ffs((int)m) - 1;
-			const uint32_t b = __shfl_sync(FULL_MASK, bw, k), ex = __shfl_sync(FULL_MASK, inc - pc, k);
-			if ((b >> lane) & 1u) a.temp[to + ex + (uint32_t)__popc(b & lt_mask)] = g[k * 32 + lane];
+		// its leaves in cell order = Morton order: lane l owns cells 16 l .. 16 l + 15 (half a word) and writes them one
+		// after the other behind those of the lanes below
+		uint32_t hw = (bits[lane >> 1] >> (16 * (lane & 1))) & 0xffffu;
+		const uint32_t hc = (uint32_t)__popc(hw);
+		const uint32_t hinc = warp_inclusive_sum(hc, lane);
+		if (lane == 31) a.cnt[0][brick] = hinc, a.cnt[1][brick] = c1, a.cnt[2][brick] = c2;
+		uint32_t *dst = a.temp + (to + hinc - hc);
+		const uint32_t *src = g + 16 * lane;
+		while (hw) {
+			const int c = __ffs((int)hw) - 1;
+			hw &= hw - 1u;
+			*dst++ = src[c];
 		}
 		__syncwarp(); // the grid and the bits are reused by the next brick
 	}
 }
 
 // The ranks of a brick's nodes are known (scans of the per-brick counts): write the level arrays of the three deepest
-// levels.  One warp per brick; lane j and j + 32 own the depth L-1 nodes j, j + 32, lanes 0..7 the depth L-2 nodes.
+// levels.  16 lanes per brick: lane k owns occupancy word k = the depth L-1 nodes 4k .. 4k+3; lanes 0..7 also own the
+// depth L-2 nodes.
 __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_nodes(BrickArgs a) {
-	const int lane = threadIdx.x & 31;
-	const uint64_t brick = ((uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x) >> 5;
+	const uint64_t tid = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
+	const uint64_t brick = tid >> 4;
+	const int sub = threadIdx.x & 15;
 	const uint64_t nb = *a.n_bricks;
-	if (brick == 0 && lane < 3) *a.count[lane] = a.rank[lane][a.n_bound];
-	if (brick >= nb) return;
-	const uint32_t bw = lane < BRICK_CELLS / 32 ? a.bits[brick * (BRICK_CELLS / 32) + lane] : 0u;
+	if (tid < 3) *a.count[tid] = a.rank[tid][a.n_bound];
+	const bool valid = brick < nb;
+	const uint32_t bw = valid ? a.bits[brick * (BRICK_CELLS / 32) + sub] : 0u;
 	const uint32_t pc = (uint32_t)__popc(bw);
-	const uint32_t ex = warp_inclusive_sum(pc, lane) - pc; // leaves of the brick in front of word `lane`
+	uint32_t inc = pc;
+#pragma unroll
+	for (int d = 1; d < 16; d <<= 1) {
+		const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d, 16);
+		if (sub >= d) inc += o;
+	}
 	const uint32_t nb4 = nonzero_bytes4(bw);
-	// n1: bit j = depth L-1 node j (cells 8j .. 8j+7) is occupied
-	const uint32_t n1_lo = __reduce_or_sync(FULL_MASK, lane < 8 ? nb4 << (4 * lane) : 0u);
-	const uint32_t n1_hi = __reduce_or_sync(FULL_MASK, (lane >= 8 && lane < 16) ? nb4 << (4 * (lane - 8)) : 0u);
+	// n1: bit j = depth L-1 node j (cells 8j .. 8j+7) is occupied -- OR over the brick's 16 lanes
+	uint32_t n1_lo = sub < 8 ? nb4 << (4 * sub) : 0u, n1_hi = sub >= 8 ? nb4 << (4 * (sub - 8)) : 0u;
+#pragma unroll
+	for (int d = 8; d > 0; d >>= 1) {
+		n1_lo |= __shfl_xor_sync(FULL_MASK, n1_lo, d, 16);
+		n1_hi |= __shfl_xor_sync(FULL_MASK, n1_hi, d, 16);
+	}
+	if (!valid || (n1_lo | n1_hi) == 0u) return; // (no collective below)
 	const uint64_t n1 = (uint64_t)n1_lo | ((uint64_t)n1_hi << 32);
 	const uint32_t n2 = nonzero_bytes4(n1_lo) | (nonzero_bytes4(n1_hi) << 4);
-	const uint64_t to = a.toff[brick], r1 = a.rank[1][brick], r2 = a.rank[2][brick];
-	const uint64_t code = a.brick_code[brick];
+	const uint32_t r1 = (uint32_t)a.rank[1][brick];
+	if (bw) {
+		const uint32_t first = (uint32_t)a.toff[brick] + inc - pc; // temp slot of the word's first leaf
+		uint32_t u1 = r1 + (uint32_t)__popcll(n1 & ((1ull << (4 * sub)) - 1ull));
 #pragma unroll
-	for (int h = 0; h < 2; ++h) {
-		const int j = lane + 32 * h, k = j >> 2, by = j & 3;
-		const uint32_t bwk = __shfl_sync(FULL_MASK, bw, k), exk = __shfl_sync(FULL_MASK, ex, k);
-		const uint32_t m = (bwk >> (8 * by)) & 0xffu;
-		if (m) {
-			const uint64_t u1 = r1 + (uint32_t)__popcll(n1 & ((1ull << j) - 1ull));
-			a.first1[u1] = (uint32_t)(to + exk + (uint32_t)__popc(bwk & ((1u << (8 * by)) - 1u)));
-			a.mask1[u1] = (unsigned char)m;
-			a.slot1[u1] = (unsigned char)(j & 7);
+		for (int by = 0; by < 4; ++by) {
+			const uint32_t m = (bw >> (8 * by)) & 0xffu;
+			if (m) {
+				a.first1[u1] = first + (uint32_t)__popc(bw & ((1u << (8 * by)) - 1u));
+				a.mask1[u1] = (unsigned char)m;
+				a.slot1[u1] = (unsigned char)((4 * sub + by) & 7);
+				++u1;
+			}
 		}
 	}
-	if (lane < 8 && ((n2 >> lane) & 1u)) {
-		const uint64_t u2 = r2 + (uint32_t)__popc(n2 & ((1u << lane) - 1u));
-		a.first2[u2] = (uint32_t)(r1 + (uint32_t)__popcll(n1 & ((1ull << (8 * lane)) - 1ull)));
-		a.keys_top[u2] = (code << 3) | (uint64_t)lane;
+	if (sub < 8 && ((n2 >> sub) & 1u)) {
+		const uint64_t u2 = a.rank[2][brick] + (uint32_t)__popc(n2 & ((1u << sub) - 1u));
+		a.first2[u2] = r1 + (uint32_t)__popcll(n1 & ((1ull << (8 * sub)) - 1ull));
+		a.keys_top[u2] = ((a.brick_code[brick] & 0x3fffffffull) << 3) | (uint64_t)sub;
 	}
 }
 

@@ -161,7 +161,8 @@ struct svo_builder {
 	// brick path (brick.cuh)
 	DevBuf<uint64_t> pairs_a, pairs_b, pair_idx, brick_u64, brick_scalars;
 	DevBuf<uint32_t> pair_flags, brick_first, small_leaf, brick_u32, brick_temp;
-	uint64_t n_pairs = 0, n_small_leaves = 0; // of the last build
+	uint64_t n_pairs = 0, n_small_leaves = 0, n_bricks = 0; // of the last build
+	cudaEvent_t ev_brick[3] = {};                            // around k_brick_raster and the scans
 	int path = 0;                             // 0: every fragment sorted; 1: bricks
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
 	uint64_t range_bytes = 0;
@@ -830,6 +831,8 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 	do {
 		for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 			if (cudaEventCreate(&b->ev[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
+		for (int i = 0; i < 3; ++i)
+			if (cudaEventCreate(&b->ev_brick[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
 		if (rc) break;
 		const uint64_t F = vox->n_frag;
 		if ((rc = b->tmp.alloc(F, s)) || (rc = b->leaf.alloc(F, s)) || (rc = b->counts.alloc(MAX_LEVEL + 2, s))) break;
@@ -864,6 +867,8 @@ void svo_builder_destroy(svo_builder *b) {
 	b->pair_flags.release(s), b->brick_first.release(s), b->small_leaf.release(s), b->brick_u32.release(s), b->brick_temp.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+	for (int i = 0; i < 3; ++i)
+		if (b->ev_brick[i]) cudaEventDestroy(b->ev_brick[i]);
 	release_export(b);
 	delete b;
 }
@@ -970,13 +975,16 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	SVO_LAUNCH_INDEP(div_up(nbd, 256), 256, s, k_brick_bounds, a);
 	SVO_TRY(exclusive_scan((const uint32_t *)a.bound, toff, nbd, b->scan_scratch, s));
 	const uint32_t rgrid = div_up(nbd, (uint64_t)BRICK_WARPS * BRICK_BPW);
+	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[0], s));
 	if (v->scene->textured)
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<true>, a);
 	else
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
+	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[1], s));
 	for (int j = 0; j < 3; ++j)
 		SVO_TRY(exclusive_scan((const uint32_t *)a.cnt[j], b->brick_u64.p + (nbd + 1) * (1 + j), nbd, b->scan_scratch, s));
-	SVO_LAUNCH(div_up(nbd * 32, BRICK_BLOCK), BRICK_BLOCK, 0, s, k_brick_nodes, a);
+	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[2], s));
+	SVO_LAUNCH(div_up(nbd * 16, BRICK_BLOCK), BRICK_BLOCK, 0, s, k_brick_nodes, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 	SVO_CUDA_TRY(cudaGetLastError());
 	*keys_top = A, *free_buf = B;
@@ -1056,6 +1064,8 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 
 	// ---- exact sizing: the one host round trip of the build ----
 	SVO_CUDA_TRY(cudaMemcpyAsync(b->h_counts, b->counts.p, (L + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+	b->n_bricks = 0;
+	if (b->path == 1) SVO_CUDA_TRY(cudaMemcpyAsync(&b->n_bricks, b->pair_idx.p + b->n_pairs, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
 	SVO_CUDA_TRY(cudaStreamSynchronize(s));
 	EmitParams &ep = b->ep;
 	ep = EmitParams{};
@@ -1411,6 +1421,17 @@ void svo_debug_force_wide_sort_state(int on) { svo::g_force_wide_sort_state = on
 void svo_debug_profile_passes(int on) { svo::g_profile_passes = on != 0; }
 void svo_debug_set_build_path(int mode) { g_build_path = mode < 0 ? -1 : (mode > 0 ? 1 : 0); }
 int svo_builder_build_path(const svo_builder *b) { return b ? b->path : 0; }
+int svo_builder_brick_stats(svo_builder *b, uint64_t counts[3], float ms[3]) {
+	if (!b || !counts || !ms) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
+	if (!(b->built || b->prepared) || b->path != 1) return fail(SVO_ERR_NOT_READY, "svo_builder_brick_stats: no brick build");
+	DeviceGuard guard(b->device);
+	counts[0] = b->n_pairs, counts[1] = b->n_bricks, counts[2] = b->n_small_leaves;
+	SVO_CUDA_TRY(cudaEventSynchronize(b->ev[3]));
+	SVO_CUDA_TRY(cudaEventElapsedTime(&ms[0], b->ev_brick[0], b->ev_brick[1]));
+	SVO_CUDA_TRY(cudaEventElapsedTime(&ms[1], b->ev_brick[1], b->ev_brick[2]));
+	SVO_CUDA_TRY(cudaEventElapsedTime(&ms[2], b->ev_brick[2], b->ev[3]));
+	return SVO_OK;
+}
 #if SVO_OS_CLOCKS
 // experiment builds only (not declared in svo.h): per-phase cycle sums of the onesweep tiles; reset != 0 clears them
 SVO_API int svo_debug_onesweep_clocks(unsigned long long out[12], int reset) {
