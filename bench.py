@@ -256,7 +256,7 @@ def run_ours(args):
     # -------- device-resident arm: inputs already in HBM, handles created (count pass done) ----------------
     phases_acc = {k: 0.0 for k in api.PHASES}
     sort_passes = 0
-    brick_acc, brick_counts, build_path = {"raster": 0.0, "scans": 0.0, "nodes": 0.0}, None, 0
+    brick_acc, brick_counts, build_path = {"raster": 0.0, "scans": 0.0, "keys": 0.0}, None, 0
     # one device holds levels <= 13 in a 64-bit fragment; level 14 runs as 8 cube-local octant builds ("virtual shards")
     single = world == 1 and level <= 13
     if single:
@@ -399,11 +399,12 @@ def run_ours(args):
                 traffic_db = {}
         if build_path == 1 and brick_acc["raster"] > 0:
             # Brick path: the large triangles never become fragments; the dominant kernel is k_brick_raster.  Its
-            # algorithmic bytes: one 8-byte pair per (brick, triangle), per brick its table entries (first pair 4, code 8,
-            # temp slot 8) in and occupancy bits 64 + counts 12 out, and one 4-byte leaf word out per leaf.
+            # algorithmic bytes: one 8-byte pair per (brick, triangle) in; per brick its table entries (first pair 4, code 8)
+            # in and its record 16 + counts 12 out; one finished 32-byte leaf block out per depth L-1 node.
             per_launch_ms = brick_acc["raster"] / args.steps
-            leaves_rank0 = leaves if single else sh.builders[0].GetLeafCount()
-            alg_bytes = 8.0 * brick_counts["pairs"] + 96.0 * brick_counts["bricks"] + 4.0 * leaves_rank0
+            bld0 = builder if single else sh.builders[0]
+            leaves_rank0 = bld0.GetLeafCount()
+            alg_bytes = 8.0 * brick_counts["pairs"] + 40.0 * brick_counts["bricks"] + 32.0 * bld0.GetLevelCounts()[level - 1 if single else bld0.GetLevel() - 1]
             achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
             t = traffic_db.get("k_brick_raster", {})
             roofline = {"bound": "hbm", "kernel": "k_brick_raster", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -411,14 +412,14 @@ def run_ours(args):
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
                         "launches_per_step": 1, "rank": 0,
                         "limiter": "instruction issue, not HBM: the kernel rasterizes 64 pixels per (brick, triangle) pair with exact "
-                                   "64-bit edge functions and an fp64 depth plane and moves ~6 bytes per fragment",
+                                   "64-bit edge functions and an fp64 depth plane and moves ~9 bytes per fragment",
                         "issue_slots_busy_pct": t.get("issue_slots_busy_pct"),
                         "pairs": brick_counts["pairs"], "bricks": brick_counts["bricks"]}
-            # the step's memory-bound kernel next to it: k_emit_octree writes every 32-byte node block once and reads the
-            # leaf words (4 B), and per depth L-1 node first (4 B) + mask (1 B) + slot (1 B)
+            # the step's memory-bound kernel next to it: k_brick_emit copies every leaf block (32 B in, 32 B out) and writes the
+            # pointer blocks of the depth L-2 nodes; with the small k_emit_octree of the upper levels it writes the whole buffer
             emit_ms = phases_acc["emit"] / args.steps
-            emit_bytes = float(octree_bytes) + 4.0 * leaves_rank0
-            kernels = [{"kernel": "k_emit_octree", "ms": emit_ms, "algorithmic_bytes": emit_bytes,
+            emit_bytes = float(octree_bytes) + 32.0 * bld0.GetLevelCounts()[level - 1 if single else bld0.GetLevel() - 1]
+            kernels = [{"kernel": "k_brick_emit (+ k_emit_octree for the upper levels)", "ms": emit_ms, "algorithmic_bytes": emit_bytes,
                         "achieved_gbs": emit_bytes / (emit_ms * 1e-3) / 1e9, "frac_of_hbm_peak": emit_bytes / (emit_ms * 1e-3) / 1e9 / peak,
                         "note": "phase time: includes the size read-back in front of the launch"}] if single and emit_ms > 0 else None
         elif sort_passes and phases_acc["sort_passes"] > 0:

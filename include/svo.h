@@ -239,7 +239,7 @@ SVO_API int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap);
 SVO_API void svo_debug_set_build_path(int mode);
 SVO_API int svo_builder_build_path(const svo_builder *b);
 /* Brick path only, after a build: counts = { (brick, triangle) pairs incl. small records, bricks, leaves of small
- * triangles }, ms = { k_brick_raster, the three rank scans, k_brick_nodes } of the last build (cudaEvents). */
+ * triangles }, ms = { k_brick_raster, the three rank scans, k_brick_keys } of the last build (cudaEvents). */
 SVO_API int svo_builder_brick_stats(svo_builder *b, uint64_t counts[3], float ms[3]);
 
 /* ---- the consumer side, for verification ----------------------------------------------------

@@ -30,10 +30,11 @@ constexpr int BRICK_CELLS = 512;
 constexpr int BRICK_WARPS = 8, BRICK_BLOCK = BRICK_WARPS * 32; // a warp works on one brick at a time
 
 // A pair word: brick Morton code << 33 | is_large << 32 | payload.  payload = index of the large triangle, or (small
-// record, is_large = 0: sorts first inside its brick) the index of the brick's first leaf in the small-leaf list.
+// record, is_large = 0: first inside its brick) the index of the brick's first leaf in the small-leaf list.
 SVO_HD inline uint64_t pair_large(uint64_t brick, uint32_t li) { return (brick << 33) | (1ull << 32) | (uint64_t)li; }
 SVO_HD inline uint64_t pair_small(uint64_t brick, uint32_t first) { return (brick << 33) | (uint64_t)first; }
-constexpr uint32_t PAIR_SORT_BEGIN = 32; // sorted bits: [32, 33 + 3 * (level - 3))
+constexpr uint32_t PAIR_SORT_BEGIN = 33; // sorted bits: [33, 33 + 3 * (level - 3)) -- the brick code only: small records are put in front
+                                         // of the large pairs before the (stable) sort, so they stay first inside their brick
 
 SVO_HD inline void screen_axes(uint32_t axis, uint32_t &wx, uint32_t &wy) { // world axes of screen x / y (voxelizer.frag:24)
 	wx = axis == 0u ? 1u : (axis == 1u ? 2u : 0u);
@@ -189,19 +190,12 @@ struct BrickArgs {
 	const uint32_t *small_leaf;
 	const uint64_t *n_small;
 	// per brick (arrays sized for the upper bound "number of pairs"; entries past n_bricks stay zero)
-	uint32_t *bound;        // leaves the brick can hold at most
-	const uint64_t *toff;   // exclusive scan of bound[]: the brick's first slot in temp
-	uint32_t *temp;         // leaf words, dense inside every brick, in Morton order
-	uint32_t *bits;         // [16] occupancy of the brick's 512 cells; byte j = child mask of its depth L-1 node j
+	uint32_t *temp;         // [512] the 8-word leaf blocks of the brick's depth L-1 nodes, dense, in Morton order
+	uint4 *rec;             // x, y: occupancy of the depth L-1 nodes 2l (bit l of x) and 2l+1 (bit l of y); z: of the 8 depth L-2 nodes
 	uint32_t *cnt[3];       // leaves, depth L-1 nodes, depth L-2 nodes of the brick (three consecutive arrays of n_bound)
 	const uint64_t *rank[3]; // exclusive scans of cnt[] (rank[j][n] = total)
 	uint64_t n_bound;       // entries of the per-brick arrays
-	// the three deepest levels for k_emit_octree / k_parent_compact
-	uint32_t *first1;        // per depth L-1 node: position of its first leaf in temp
-	unsigned char *mask1;    // per depth L-1 node: child mask
-	unsigned char *slot1;    // per depth L-1 node: child slot
-	uint32_t *first2;        // per depth L-2 node: index of its first depth L-1 child
-	uint64_t *keys_top;      // per depth L-2 node: Morton code
+	uint64_t *keys_top;      // per depth L-2 node: Morton code (what k_parent_compact builds the upper levels from)
 	uint64_t *count[3];      // device scalars: leaves, depth L-1, depth L-2 nodes
 };
 
@@ -221,24 +215,9 @@ SVO_DEV uint32_t nonzero_bytes4(uint32_t b) {
 	return ((t & 0x01010101u) * 0x01020408u) >> 24;
 }
 
-// leaves a brick can hold at most: 64 per large triangle (8 x 8 pixels, one voxel each) + its small triangles' leaves
-__global__ void __launch_bounds__(256) k_brick_bounds(BrickArgs a) {
-	const uint64_t brick = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-	if (brick >= *a.n_bricks) return;
-	const uint32_t p0 = a.brick_first[brick], p1 = a.brick_first[brick + 1];
-	const uint64_t pr = a.pairs[p0];
-	uint32_t n = (p1 - p0) * 64u;
-	if (!((pr >> 32) & 1ull)) { // a small record (the brick's first pair)
-		n -= 64u;
-		const uint64_t ns = *a.n_small, code = pr >> 33;
-		for (uint64_t i = (uint32_t)pr; i < ns && (a.small_keys[i] >> (3 * BRICK_LOG)) == code; ++i) ++n;
-	}
-	a.bound[brick] = n < (uint32_t)BRICK_CELLS ? n : (uint32_t)BRICK_CELLS;
-}
-
 // One warp rasterizes BRICK_BPW consecutive bricks, one after the other, into its 512-cell grid; nothing is shared
 // between warps and no warp waits for another one: what a brick needs from its neighbours (the ranks of its nodes in the
-// level arrays) is left to k_brick_nodes, after three scans over the per-brick counts.
+// level arrays) is left to k_brick_keys / k_brick_emit, after three scans over the per-brick counts.
 #ifndef SVO_BRICK_BPW
 #define SVO_BRICK_BPW 8
 #endif
@@ -258,7 +237,7 @@ SVO_DEV void brick_edges(const TriSetup &ts, int32_t X, int32_t Y, int32_t dx, i
 }
 
 template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raster(BrickArgs a) {
-	__shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS];         // leaf words; valid where the cell's bit is set
+	__align__(16) __shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS]; // leaf words; valid where the cell's bit is set
 	__shared__ uint32_t s_bits[BRICK_WARPS][BRICK_CELLS / 32];
 	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the first triangle of every brick of the warp
 	__align__(16) __shared__ uint64_t s_meta[BRICK_WARPS][BRICK_BPW][4];
@@ -271,7 +250,7 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 	const uint32_t sx3 = spread3((uint32_t)dx), sy3a = spread3((uint32_t)dy), sy3b = spread3((uint32_t)dy + 4u);
 
 	// The metadata of the warp's bricks is fetched up front, lane q for brick q -- pair range, Morton code, first pair,
-	// slot in temp -- and the first triangle of every brick is staged in shared memory by 22 lanes at once: three
+	// -- and the first triangle of every brick is staged in shared memory by 22 lanes at once: three
 	// dependent round trips per BRICK_BPW bricks instead of four per brick (latency, not HBM, is what this kernel waits for).
 	if (lane < BRICK_BPW && brick0 + lane < nb) {
 		const uint32_t p0 = a.brick_first[brick0 + lane], p1 = a.brick_first[brick0 + lane + 1];
@@ -279,7 +258,7 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 		m[0] = (uint64_t)p0 | ((uint64_t)p1 << 32);
 		m[1] = a.brick_code[brick0 + lane];
 		m[2] = a.pairs[p0];
-		m[3] = a.toff[brick0 + lane];
+		m[3] = 0;
 	}
 	__syncwarp();
 #pragma unroll
@@ -300,7 +279,6 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 		const uint32_t p0 = (uint32_t)m01.x, p1 = (uint32_t)(m01.x >> 32);
 		const uint64_t brick_id = m01.y & 0x3fffffffull, pr0 = m23.x;
 		const uint32_t bxyz = (uint32_t)(m01.y >> 32);
-		const uint32_t to = (uint32_t)m23.y; // (the host checks that temp has fewer than 2^32 slots)
 		// first voxel of the brick, full-grid coordinates
 		const uint32_t vb0 = a.rp.origin[0] + 8u * (bxyz & 1023u), vb1 = a.rp.origin[1] + 8u * ((bxyz >> 10) & 1023u),
 		               vb2 = a.rp.origin[2] + 8u * (bxyz >> 20);
@@ -366,78 +344,94 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 			}
 			__syncwarp();
 		}
-		// the brick's occupancy (lane k < 16 holds word k) and its counts
-		const uint32_t bw = lane < BRICK_CELLS / 32 ? bits[lane] : 0u;
-		const uint32_t nb4 = nonzero_bytes4(bw); // the word's 4 depth L-1 nodes
-		const uint32_t c1 = warp_sum((uint32_t)__popc(nb4));
-		const uint32_t pair_any = nb4 | __shfl_down_sync(FULL_MASK, nb4, 1); // words 2m, 2m+1 = one depth L-2 node
-		const uint32_t c2 = (uint32_t)__popc(__ballot_sync(FULL_MASK, !(lane & 1) && pair_any != 0u));
-		if (lane < BRICK_CELLS / 32) a.bits[brick * (BRICK_CELLS / 32) + lane] = bw;
-		// its leaves in cell order = Morton order: lane l owns cells 16 l .. 16 l + 15 (half a word) and writes them one
-		// after the other behind those of the lanes below
-		uint32_t hw = (bits[lane >> 1] >> (16 * (lane & 1))) & 0xffffu;
-		const uint32_t hc = (uint32_t)__popc(hw);
-		const uint32_t hinc = warp_inclusive_sum(hc, lane);
-		if (lane == 31) a.cnt[0][brick] = hinc, a.cnt[1][brick] = c1, a.cnt[2][brick] = c2;
-		uint32_t *dst = a.temp + (to + hinc - hc);
-		const uint32_t *src = g + 16 * lane;
-		while (hw) {
-			const int c = __ffs((int)hw) - 1;
-			hw &= hw - 1u;
-			*dst++ = src[c];
+		// The brick's depth L-1 nodes: lane l owns cells 16 l .. 16 l + 15 = the nodes 2l and 2l + 1.  Every occupied node
+		// leaves its finished 8-word block (leaf words, zeros for empty children) in temp, at its rank inside the brick.
+		const uint32_t hw = (bits[lane >> 1] >> (16 * (lane & 1))) & 0xffffu;
+		const bool o0 = (hw & 0xffu) != 0u, o1 = (hw >> 8) != 0u;
+		const uint32_t b0 = __ballot_sync(FULL_MASK, o0), b1 = __ballot_sync(FULL_MASK, o1);
+		const uint32_t c0 = warp_sum((uint32_t)__popc(hw));
+		const uint32_t n2 = __ballot_sync(FULL_MASK, lane < 8 && (((b0 | b1) >> (4 * lane)) & 0xfu) != 0u); // 8 nodes = 4 lanes
+		if (lane == 0) {
+			a.rec[brick] = make_uint4(b0, b1, n2, 0u);
+			a.cnt[0][brick] = c0, a.cnt[1][brick] = (uint32_t)(__popc(b0) + __popc(b1)), a.cnt[2][brick] = (uint32_t)__popc(n2);
+		}
+		if (hw) {
+			const uint32_t lt = (1u << lane) - 1u;
+			uint32_t rank = (uint32_t)(__popc(b0 & lt) + __popc(b1 & lt));
+			uint4 *dst = reinterpret_cast<uint4 *>(a.temp + brick * BRICK_CELLS);
+			const uint4 *src = reinterpret_cast<const uint4 *>(g + 16 * lane);
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const uint32_t m = (hw >> (8 * h)) & 0xffu;
+				if (m) {
+					uint4 lo = src[2 * h], hi = src[2 * h + 1];
+					lo.x = m & 1u ? lo.x : 0u, lo.y = m & 2u ? lo.y : 0u, lo.z = m & 4u ? lo.z : 0u, lo.w = m & 8u ? lo.w : 0u;
+					hi.x = m & 16u ? hi.x : 0u, hi.y = m & 32u ? hi.y : 0u, hi.z = m & 64u ? hi.z : 0u, hi.w = m & 128u ? hi.w : 0u;
+					dst[2 * rank] = lo, dst[2 * rank + 1] = hi;
+					++rank;
+				}
+			}
 		}
 		__syncwarp(); // the grid and the bits are reused by the next brick
 	}
 }
 
-// The ranks of a brick's nodes are known (scans of the per-brick counts): write the level arrays of the three deepest
-// levels.  16 lanes per brick: lane k owns occupancy word k = the depth L-1 nodes 4k .. 4k+3; lanes 0..7 also own the
-// depth L-2 nodes.
-__global__ void __launch_bounds__(BRICK_BLOCK) k_brick_nodes(BrickArgs a) {
+// rank of the depth L-1 node `node` (0..63) among the brick's occupied ones; node 2l is bit l of x, node 2l+1 bit l of y
+SVO_DEV uint32_t brick_node_rank(uint32_t x, uint32_t y, uint32_t node) {
+	const uint32_t l = node >> 1, below = (1u << l) - 1u;
+	return (uint32_t)(__popc(x & below) + __popc(y & below)) + ((node & 1u) ? ((x >> l) & 1u) : 0u);
+}
+
+// The ranks of a brick's nodes are known (scans of the per-brick counts): the Morton codes of the depth L-2 nodes, in
+// order, are what the upper levels are built from (k_parent_compact); and the node counts of the three deepest levels.
+// 8 lanes per brick.
+__global__ void __launch_bounds__(BRICK_BLOCK) k_brick_keys(BrickArgs a) {
+	const uint64_t tid = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
+	const uint64_t brick = tid >> 3;
+	const uint32_t m = threadIdx.x & 7u;
+	if (tid < 3) *a.count[tid] = a.rank[tid][a.n_bound];
+	if (brick >= *a.n_bricks) return;
+	const uint32_t n2 = a.rec[brick].z;
+	if ((n2 >> m) & 1u)
+		a.keys_top[a.rank[2][brick] + (uint32_t)__popc(n2 & ((1u << m) - 1u))] = ((a.brick_code[brick] & 0x3fffffffull) << 3) | (uint64_t)m;
+}
+
+// Node words of the two deepest windows, straight from the bricks (the bulk of the node buffer): the 8-word blocks of
+// a brick's depth L-1 nodes (leaf words: a copy of the brick's part of temp) and of its depth L-2 nodes (pointers to
+// the former) are consecutive in their windows, at the brick's ranks.  Placement as in k_emit_octree: block g ->
+// words[(g - block_shift) * 8], a pointer to block c is (c - block_shift) * 8 + ptr_bias.  16 lanes per brick.
+struct BrickEmit {
+	uint64_t block_l1, block_l; // first block of the window that holds the children of the depth L-2 / of the depth L-1 nodes
+	uint32_t block_shift, ptr_bias;
+};
+__global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEmit be, uint32_t *__restrict__ words) {
 	const uint64_t tid = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
 	const uint64_t brick = tid >> 4;
-	const int sub = threadIdx.x & 15;
-	const uint64_t nb = *a.n_bricks;
-	if (tid < 3) *a.count[tid] = a.rank[tid][a.n_bound];
-	const bool valid = brick < nb;
-	const uint32_t bw = valid ? a.bits[brick * (BRICK_CELLS / 32) + sub] : 0u;
-	const uint32_t pc = (uint32_t)__popc(bw);
-	uint32_t inc = pc;
-#pragma unroll
-	for (int d = 1; d < 16; d <<= 1) {
-		const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d, 16);
-		if (sub >= d) inc += o;
+	const uint32_t sub = threadIdx.x & 15u;
+	if (brick >= *a.n_bricks) return;
+	const uint4 rec = a.rec[brick];
+	const uint32_t c1 = (uint32_t)(__popc(rec.x) + __popc(rec.y));
+	if (c1 == 0u) return;
+	const uint64_t r1 = a.rank[1][brick];
+	const uint64_t g1 = be.block_l + r1 - be.block_shift; // where the brick's first leaf block goes
+	{
+		const uint4 *src = reinterpret_cast<const uint4 *>(a.temp + brick * BRICK_CELLS);
+		uint4 *dst = reinterpret_cast<uint4 *>(words + g1 * 8);
+		for (uint32_t i = sub; i < 2u * c1; i += 16u) dst[i] = src[i]; // 16-byte pieces, consecutive lanes consecutive pieces
 	}
-	const uint32_t nb4 = nonzero_bytes4(bw);
-	// n1: bit j = depth L-1 node j (cells 8j .. 8j+7) is occupied -- OR over the brick's 16 lanes
-	uint32_t n1_lo = sub < 8 ? nb4 << (4 * sub) : 0u, n1_hi = sub >= 8 ? nb4 << (4 * (sub - 8)) : 0u;
+	if (sub < 8u && ((rec.z >> sub) & 1u)) { // a depth L-2 node: one block of pointers to its children's blocks
+		uint32_t c = (uint32_t)g1 + brick_node_rank(rec.x, rec.y, 8u * sub);
+		uint32_t w[8];
 #pragma unroll
-	for (int d = 8; d > 0; d >>= 1) {
-		n1_lo |= __shfl_xor_sync(FULL_MASK, n1_lo, d, 16);
-		n1_hi |= __shfl_xor_sync(FULL_MASK, n1_hi, d, 16);
-	}
-	if (!valid || (n1_lo | n1_hi) == 0u) return; // (no collective below)
-	const uint64_t n1 = (uint64_t)n1_lo | ((uint64_t)n1_hi << 32);
-	const uint32_t n2 = nonzero_bytes4(n1_lo) | (nonzero_bytes4(n1_hi) << 4);
-	const uint32_t r1 = (uint32_t)a.rank[1][brick];
-	if (bw) {
-		const uint32_t first = (uint32_t)a.toff[brick] + inc - pc; // temp slot of the word's first leaf
-		uint32_t u1 = r1 + (uint32_t)__popcll(n1 & ((1ull << (4 * sub)) - 1ull));
-#pragma unroll
-		for (int by = 0; by < 4; ++by) {
-			const uint32_t m = (bw >> (8 * by)) & 0xffu;
-			if (m) {
-				a.first1[u1] = first + (uint32_t)__popc(bw & ((1u << (8 * by)) - 1u));
-				a.mask1[u1] = (unsigned char)m;
-				a.slot1[u1] = (unsigned char)((4 * sub + by) & 7);
-				++u1;
-			}
+		for (int sl = 0; sl < 8; ++sl) {
+			const uint32_t node = 8u * sub + (uint32_t)sl;
+			const bool occ = (((node & 1u) ? rec.y : rec.x) >> (node >> 1)) & 1u;
+			w[sl] = occ ? (0x80000000u | ((c++ << 3) + be.ptr_bias)) : 0u;
 		}
-	}
-	if (sub < 8 && ((n2 >> sub) & 1u)) {
-		const uint64_t u2 = a.rank[2][brick] + (uint32_t)__popc(n2 & ((1u << sub) - 1u));
-		a.first2[u2] = r1 + (uint32_t)__popcll(n1 & ((1ull << (8 * sub)) - 1ull));
-		a.keys_top[u2] = ((a.brick_code[brick] & 0x3fffffffull) << 3) | (uint64_t)sub;
+		const uint64_t g = be.block_l1 + a.rank[2][brick] + (uint32_t)__popc(rec.z & ((1u << sub) - 1u)) - be.block_shift;
+		uint4 *o = reinterpret_cast<uint4 *>(words + g * 8);
+		o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+		o[1] = make_uint4(w[4], w[5], w[6], w[7]);
 	}
 }
 

@@ -313,9 +313,6 @@ struct EmitParams {
 	const uint32_t *first[MAX_LEVEL + 1];     // [d]: per depth-(d-1) node, index of its first child among the depth-d nodes
 	const unsigned char *slot[MAX_LEVEL + 1]; // [d]: per depth-d node, its child slot
 	const uint32_t *leaf;                     // leaf words of the depth-`level` nodes
-	// brick path (brick.cuh): first[level][j] is the position of node j's first leaf in `leaf` (dense per brick only) and
-	// leaf_mask[j] its child mask; null: leaves are dense and slot[level] holds their child slots
-	const unsigned char *leaf_mask;
 	// placement: block g is written at words[(g - block_shift) * 8]; a child pointer to block c is
 	// (c - block_shift) * 8 + ptr_bias.  block_shift > 0 sends the first block_shift blocks (the root block, or the root
 	// block and the depth-1 blocks) to root_dst instead, so that a subtree can be emitted straight into a larger (possibly
@@ -347,16 +344,12 @@ __global__ void __launch_bounds__(EMITO_BLOCK) k_emit_octree(EmitParams ep, uint
 		const unsigned char *slot = ep.slot[d];
 		const uint32_t c0 = first[j];
 		const bool leaf_level = d == ep.level;
+		const uint32_t c1 = j + 1 < ep.count[d - 1] ? first[j + 1] : (uint32_t)ep.count[d];
+		const uint32_t nc = c1 - c0; // 1..8 children, contiguous, slots ascending
 		uint32_t m = 0;
-		if (leaf_level && ep.leaf_mask)
-			m = ep.leaf_mask[j];
-		else {
-			const uint32_t c1 = j + 1 < ep.count[d - 1] ? first[j + 1] : (uint32_t)ep.count[d];
-			const uint32_t nc = c1 - c0; // 1..8 children, contiguous, slots ascending
 #pragma unroll
-			for (int q = 0; q < 8; ++q)
-				if ((uint32_t)q < nc) m |= 1u << slot[c0 + q];
-		}
+		for (int q = 0; q < 8; ++q)
+			if ((uint32_t)q < nc) m |= 1u << slot[c0 + q];
 		const uint64_t child_base = ep.block_base[d + 1];
 		uint32_t c = c0;
 #pragma unroll

@@ -164,6 +164,7 @@ struct svo_builder {
 	uint64_t n_pairs = 0, n_small_leaves = 0, n_bricks = 0; // of the last build
 	cudaEvent_t ev_brick[3] = {};                            // around k_brick_raster and the scans
 	int path = 0;                             // 0: every fragment sorted; 1: bricks
+	BrickArgs brick_args{};                   // the arrays of the last brick build
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
 	uint64_t range_bytes = 0;
 	uint32_t sort_passes = 0;
@@ -896,7 +897,7 @@ static int reduce_sorted(svo_builder *b, const uint64_t *sorted, uint64_t F, uin
 // The brick path of svo_builder_prepare (brick.cuh): small triangles' fragments sorted and reduced on their own, large
 // triangles binned; on return *keys_top holds the depth L-2 keys (counts[L-2] of them) and *free_buf is free.
 //   ev[0..1] small fragments: sort + reduce + small records (+ the read-back of their number)
-//   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_raster, scans, k_brick_nodes
+//   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_raster, scans, k_brick_keys
 static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_off, const uint64_t *slot_off, uint64_t **free_buf,
                           uint64_t **keys_top) {
 	svo_voxelizer *v = b->vox;
@@ -949,31 +950,31 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 
 	// per-brick arrays are sized for the upper bound "one brick per pair"; entries past the real number of bricks stay 0
 	const uint64_t nbd = n_pairs;
-	const uint64_t temp_cap = 64ull * npl + b->n_small_leaves;
-	if (temp_cap >= (1ull << 32)) return fail(SVO_ERR_CAPACITY, "brick path: more than 2^32 leaf slots");
-	SVO_TRY(b->brick_u32.reserve(nbd * (1 + 3 + BRICK_CELLS / 32), s));
-	SVO_TRY(b->brick_u64.reserve((nbd + 1) * 4, s));
-	SVO_TRY(b->brick_temp.reserve(temp_cap, s));
-	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_u32.p, 0, nbd * 4 * sizeof(uint32_t), s)); // bound + the three counts
+	{
+		size_t free_b = 0, total_b = 0;
+		const uint64_t need = nbd * BRICK_CELLS * sizeof(uint32_t);
+#ifndef SVO_EMU
+		if (need > b->brick_temp.n * sizeof(uint32_t) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need > free_b)
+			return fail(SVO_ERR_CAPACITY, "brick path: not enough device memory for 2 KB of leaf blocks per brick (SVO_BUILD_PATH=0 sorts every fragment instead)");
+#else
+		(void)free_b, (void)total_b, (void)need;
+#endif
+	}
+	SVO_TRY(b->brick_u32.reserve(nbd * (3 + 4) + 4, s));
+	SVO_TRY(b->brick_u64.reserve((nbd + 1) * 3, s));
+	SVO_TRY(b->brick_temp.reserve(nbd * BRICK_CELLS, s));
+	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_u32.p, 0, nbd * 3 * sizeof(uint32_t), s)); // the three counts
 	BrickArgs a{};
 	a.pairs = pairs, a.brick_first = b->brick_first.p, a.brick_code = brick_code, a.n_bricks = b->pair_idx.p + n_pairs;
 	a.large = v->large.p, a.luv = v->large_uv.p, a.tv = v->scene->view.tex, a.rp = v->rp;
 	a.small_keys = B, a.small_leaf = b->small_leaf.p, a.n_small = d_nsl;
-	a.bound = b->brick_u32.p;
-	for (int j = 0; j < 3; ++j) a.cnt[j] = b->brick_u32.p + nbd * (1 + j);
-	a.bits = b->brick_u32.p + nbd * 4;
-	uint64_t *toff = b->brick_u64.p;
-	a.toff = toff;
-	for (int j = 0; j < 3; ++j) a.rank[j] = b->brick_u64.p + (nbd + 1) * (1 + j);
+	for (int j = 0; j < 3; ++j) a.cnt[j] = b->brick_u32.p + nbd * j;
+	a.rec = reinterpret_cast<uint4 *>(b->brick_u32.p + ((nbd * 3 + 3) & ~3ull)); // (16-byte aligned: the pool hands out 256-byte aligned blocks)
+	for (int j = 0; j < 3; ++j) a.rank[j] = b->brick_u64.p + (nbd + 1) * j;
 	a.n_bound = nbd;
 	a.temp = b->brick_temp.p;
-	a.first1 = b->first.p + first_off[L];
-	a.mask1 = b->slot.p + slot_off[L]; // (the leaves' slot array of the fragment path: one byte per leaf, free here)
-	a.slot1 = b->slot.p + slot_off[L - 1], a.first2 = b->first.p + first_off[L - 1];
 	a.keys_top = A;
 	for (uint32_t j = 0; j < 3; ++j) a.count[j] = b->counts.p + (L - j);
-	SVO_LAUNCH_INDEP(div_up(nbd, 256), 256, s, k_brick_bounds, a);
-	SVO_TRY(exclusive_scan((const uint32_t *)a.bound, toff, nbd, b->scan_scratch, s));
 	const uint32_t rgrid = div_up(nbd, (uint64_t)BRICK_WARPS * BRICK_BPW);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[0], s));
 	if (v->scene->textured)
@@ -982,9 +983,10 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[1], s));
 	for (int j = 0; j < 3; ++j)
-		SVO_TRY(exclusive_scan((const uint32_t *)a.cnt[j], b->brick_u64.p + (nbd + 1) * (1 + j), nbd, b->scan_scratch, s));
+		SVO_TRY(exclusive_scan((const uint32_t *)a.cnt[j], b->brick_u64.p + (nbd + 1) * j, nbd, b->scan_scratch, s));
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[2], s));
-	SVO_LAUNCH(div_up(nbd * 16, BRICK_BLOCK), BRICK_BLOCK, 0, s, k_brick_nodes, a);
+	SVO_LAUNCH_INDEP(div_up(nbd * 8, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_keys, a);
+	b->brick_args = a; // k_brick_emit (after the sizes are known) works on the same arrays
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 	SVO_CUDA_TRY(cudaGetLastError());
 	*keys_top = A, *free_buf = B;
@@ -1084,10 +1086,7 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 		ep.slot[d] = b->slot.p + slot_off[d];
 	}
 	ep.leaf = b->leaf.p;
-	if (b->path == 1) { // brick path: the leaves stay where the bricks put them; depth L-1 nodes carry a child mask instead
-		ep.leaf = b->brick_temp.p;
-		ep.leaf_mask = b->slot.p + slot_off[L];
-	}
+	if (b->path == 1) ep.total_blocks = ep.block_base[L - 1]; // the two deepest windows are written brick by brick (k_brick_emit)
 	b->range_bytes = blocks * 8 * sizeof(uint32_t); // (counter + 1) * 8 * 4, src/OctreeBuilder.cpp:212-214
 	b->prepared = true;
 	return SVO_OK;
@@ -1116,6 +1115,10 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_staged, ep, d_dst);
 		else
 			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_direct, ep, d_dst);
+		if (b->path == 1) {
+			BrickEmit be{ep.block_base[b->level - 1], ep.block_base[b->level], ep.block_shift, ep.ptr_bias};
+			SVO_LAUNCH_INDEP(div_up(b->brick_args.n_bound * 16, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_emit, b->brick_args, be, d_dst);
+		}
 	}
 	SVO_CUDA_TRY(cudaGetLastError());
 	return SVO_OK;
