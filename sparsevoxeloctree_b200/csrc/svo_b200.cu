@@ -950,19 +950,9 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 
 	// per-brick arrays are sized for the upper bound "one brick per pair"; entries past the real number of bricks stay 0
 	const uint64_t nbd = n_pairs;
-	{
-		size_t free_b = 0, total_b = 0;
-		const uint64_t need = nbd * BRICK_CELLS * sizeof(uint32_t);
-#ifndef SVO_EMU
-		if (need > b->brick_temp.n * sizeof(uint32_t) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need > free_b)
-			return fail(SVO_ERR_CAPACITY, "brick path: not enough device memory for 2 KB of leaf blocks per brick (SVO_BUILD_PATH=0 sorts every fragment instead)");
-#else
-		(void)free_b, (void)total_b, (void)need;
-#endif
-	}
 	SVO_TRY(b->brick_u32.reserve(nbd * (3 + 4) + 4, s));
 	SVO_TRY(b->brick_u64.reserve((nbd + 1) * 3, s));
-	SVO_TRY(b->brick_temp.reserve(nbd * BRICK_CELLS, s));
+	SVO_TRY(b->brick_temp.reserve(nbd * BRICK_CELLS, s)); // 2 KB per brick (fails with SVO_ERR_CUDA when the device cannot hold it: SVO_BUILD_PATH=0 sorts every fragment instead)
 	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_u32.p, 0, nbd * 3 * sizeof(uint32_t), s)); // the three counts
 	BrickArgs a{};
 	a.pairs = pairs, a.brick_first = b->brick_first.p, a.brick_code = brick_code, a.n_bricks = b->pair_idx.p + n_pairs;

@@ -105,6 +105,33 @@ def test_textured_path_against_reference_shaders_end_to_end(emu):
     cuda_textured_path_like_reference(emu)
 
 
+@pytest.mark.parametrize("case", ["soup", "dilate", "textured", "shard", "stack"])
+def test_brick_path_logic(emu, case):
+    """brick.cuh on the emulator: pair generation, pair sort, k_brick_raster (shared-memory grids, folds in triangle
+    order, leaf blocks), the rank scans and k_brick_emit -- against the oracle, with the path forced."""
+    emu.dll.svo_debug_set_build_path(1)
+    try:
+        if case == "soup":
+            info = check_against_oracle(emu, scenes.random_soup(60, 6, 0.01, 1.5), 7, api.CONSERVATIVE_EXACT)
+        elif case == "dilate":
+            info = check_against_oracle(emu, scenes.random_soup(50, 7, 0.01, 1.2), 6, api.CONSERVATIVE_DILATE)
+        elif case == "textured":
+            info = check_against_oracle(emu, scenes.textured_soup(40, 11, size_hi=1.0), 6, api.CENTER)
+        elif case == "shard":
+            info = check_against_oracle(emu, scenes.random_soup(50, 3, 0.01, 1.5), 6, api.CONSERVATIVE_EXACT, shard=(1, (1, 0, 1)))
+        else:  # several large triangles through the same voxels
+            rng = np.random.default_rng(5)
+            pos = (rng.uniform(-0.05, 0.05, (8, 1, 3)) + rng.uniform(-0.7, 0.7, (8, 3, 3))).reshape(-1, 3).astype(np.float32)
+            pos[:, 1] *= 0.05
+            idx = np.arange(len(pos), dtype=np.uint32)
+            draws = np.array([(0, 12, 0xFFFFFFFF, 0x00FF2010), (12, 12, 0xFFFFFFFF, 0x0010C0FF)], scenes.DRAW_DTYPE)
+            info = check_against_oracle(emu, scenes.Mesh(pos, idx, draws, "stack"), 6, api.CONSERVATIVE_EXACT)
+            assert info["fragments"] > info["leaves"]
+        assert info["path"] == 1
+    finally:
+        emu.dll.svo_debug_set_build_path(-1)
+
+
 def test_empty_scene(emu):
     m = scenes.Mesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), np.zeros(0, scenes.DRAW_DTYPE), "empty")
     info = check_against_oracle(emu, m, 4, api.CENTER)
