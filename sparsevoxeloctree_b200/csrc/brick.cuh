@@ -139,10 +139,12 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 __global__ void __launch_bounds__(256)
     k_brick_small_records(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ n_ptr, uint64_t *__restrict__ records,
                           unsigned long long *__restrict__ n_records) {
+	__shared__ uint32_t s_warp[8];
+	__shared__ unsigned long long s_base;
 	const uint64_t n = *n_ptr;
-	const int lane = threadIdx.x & 31;
-	for (uint64_t i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) & ~31ull; i0 < n; i0 += (uint64_t)gridDim.x * 256) {
-		const uint64_t i = i0 + lane;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (uint64_t i0 = (uint64_t)blockIdx.x * 256; i0 < n; i0 += (uint64_t)gridDim.x * 256) { // block-uniform
+		const uint64_t i = i0 + threadIdx.x;
 		bool head = false;
 		uint64_t brick = 0;
 		if (i < n) {
@@ -150,10 +152,20 @@ __global__ void __launch_bounds__(256)
 			head = i == 0 || (keys[i - 1] >> (3 * BRICK_LOG)) != brick;
 		}
 		const unsigned b = __ballot_sync(FULL_MASK, head);
-		uint64_t pos = 0;
-		if (lane == 0 && b) pos = atomicAdd(n_records, (unsigned long long)__popc(b));
-		pos = __shfl_sync(FULL_MASK, pos, 0);
-		if (head) records[pos + __popc(b & ((1u << lane) - 1u))] = pair_small(brick, (uint32_t)i);
+		if (lane == 0) s_warp[warp] = (uint32_t)__popc(b);
+		__syncthreads();
+		if (threadIdx.x == 0) { // one global atomic per 256 keys
+			uint32_t t = 0;
+			for (int w = 0; w < 8; ++w) {
+				const uint32_t c = s_warp[w];
+				s_warp[w] = t;
+				t += c;
+			}
+			s_base = t ? atomicAdd(n_records, (unsigned long long)t) : 0ull;
+		}
+		__syncthreads();
+		if (head) records[s_base + s_warp[warp] + (uint32_t)__popc(b & ((1u << lane) - 1u))] = pair_small(brick, (uint32_t)i);
+		__syncthreads();
 	}
 }
 
@@ -384,16 +396,16 @@ SVO_DEV uint32_t brick_node_rank(uint32_t x, uint32_t y, uint32_t node) {
 
 // The ranks of a brick's nodes are known (scans of the per-brick counts): the Morton codes of the depth L-2 nodes, in
 // order, are what the upper levels are built from (k_parent_compact); and the node counts of the three deepest levels.
-// 8 lanes per brick.
+// One thread per brick.
 __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_keys(BrickArgs a) {
-	const uint64_t tid = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
-	const uint64_t brick = tid >> 3;
-	const uint32_t m = threadIdx.x & 7u;
-	if (tid < 3) *a.count[tid] = a.rank[tid][a.n_bound];
+	const uint64_t brick = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
+	if (brick < 3) *a.count[brick] = a.rank[brick][a.n_bound];
 	if (brick >= *a.n_bricks) return;
-	const uint32_t n2 = a.rec[brick].z;
-	if ((n2 >> m) & 1u)
-		a.keys_top[a.rank[2][brick] + (uint32_t)__popc(n2 & ((1u << m) - 1u))] = ((a.brick_code[brick] & 0x3fffffffull) << 3) | (uint64_t)m;
+	uint32_t n2 = a.rec[brick].z;
+	if (!n2) return;
+	uint64_t *dst = a.keys_top + a.rank[2][brick];
+	const uint64_t code = (a.brick_code[brick] & 0x3fffffffull) << 3;
+	for (; n2; n2 &= n2 - 1u) *dst++ = code | (uint64_t)(__ffs((int)n2) - 1);
 }
 
 // Node words of the two deepest windows, straight from the bricks (the bulk of the node buffer): the 8-word blocks of

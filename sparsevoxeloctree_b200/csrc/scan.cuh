@@ -109,12 +109,16 @@ constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_IT
 // NONZERO = false: f(v) = v; NONZERO = true: f(v) = (v != 0), i.e. the scan numbers the non-zero entries.
 // (Two counters are never packed into one scanned word: the look-back keeps 62 value bits per tile, so a packed
 // count << 40 | sum silently wrapped at 2^22 counted entries.)
+// gridDim.y > 1: that many independent scans in one launch -- scan y reads in + y * in_stride, writes out + y *
+// out_stride and uses its own look-back chain (state + y * state_stride) and ticket (ticket + y).
 template <class InT, bool NONZERO>
 __global__ void __launch_bounds__(SCAN_BLOCK)
-    k_exclusive_scan(const InT *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket) {
+    k_exclusive_scan(const InT *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket,
+                     uint64_t in_stride, uint64_t out_stride, uint64_t state_stride) {
 	__shared__ uint64_t s_warp[SCAN_BLOCK / 32 + 1];
 	__shared__ uint32_t s_ticket;
 	__shared__ uint64_t s_prefix;
+	in += blockIdx.y * in_stride, out += blockIdx.y * out_stride, state += blockIdx.y * state_stride, ticket += blockIdx.y;
 	const uint32_t tile = take_ticket(ticket, &s_ticket);
 	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
 	InT v[SCAN_ITEMS];
@@ -157,7 +161,22 @@ inline int exclusive_scan(const InT *in, uint64_t *out, uint64_t n, ScanScratch 
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (tiles + 1) * sizeof(uint64_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, sizeof(uint32_t), s));
 	auto k = k_exclusive_scan<InT, NONZERO>;
-	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p);
+	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p, (uint64_t)0, (uint64_t)0, (uint64_t)0);
+	SVO_CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+// `count` scans of n elements each in one launch: input arrays in_stride apart, outputs (n + 1 entries) out_stride apart
+template <class InT>
+inline int exclusive_scan_multi(const InT *in, uint64_t in_stride, uint64_t *out, uint64_t out_stride, uint64_t n, uint32_t count,
+                                ScanScratch &sc, cudaStream_t s) {
+	const uint32_t tiles = n ? div_up(n, SCAN_TILE) : 1;
+	SVO_TRY(sc.state.reserve((uint64_t)(tiles + 1) * count, s));
+	SVO_TRY(sc.ticket.reserve(count, s));
+	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (uint64_t)(tiles + 1) * count * sizeof(uint64_t), s));
+	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, count * sizeof(uint32_t), s));
+	auto k = k_exclusive_scan<InT, false>;
+	SVO_LAUNCH(dim3(tiles, count), SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p, in_stride, out_stride, (uint64_t)(tiles + 1));
 	SVO_CUDA_TRY(cudaGetLastError());
 	return 0;
 }

@@ -488,9 +488,10 @@ static bool brick_path_wanted(const svo_voxelizer *v) {
 	return v->n_frag_large >= (8ull << 20) && v->n_frag_large * 4 >= v->n_frag_small;
 }
 static dim3 brick_pair_grid(const svo_voxelizer *v) {
-	// one warp per large triangle; few triangles with hundreds of tile rows each: deal a triangle's rows out over up to 32 warps
+	// one warp per large triangle; few triangles with hundreds of tile rows each: deal a triangle's rows out over up to 256 warps
+	// (a wall has 512 rows of 512 tiles)
 	const uint32_t wgrid = div_up((uint64_t)v->n_large * 32, RASTER_BLOCK);
-	return dim3(wgrid, v->n_large < 65536u ? std::min(32u, std::max(1u, (1u << v->level) / 64u)) : 1u);
+	return dim3(wgrid, v->n_large < 65536u ? std::min(256u, std::max(1u, (1u << v->level) / 16u)) : 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -972,10 +973,9 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	else
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[1], s));
-	for (int j = 0; j < 3; ++j)
-		SVO_TRY(exclusive_scan((const uint32_t *)a.cnt[j], b->brick_u64.p + (nbd + 1) * j, nbd, b->scan_scratch, s));
+	SVO_TRY(exclusive_scan_multi((const uint32_t *)a.cnt[0], nbd, b->brick_u64.p, nbd + 1, nbd, 3, b->scan_scratch, s)); // three scans, one launch
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[2], s));
-	SVO_LAUNCH_INDEP(div_up(nbd * 8, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_keys, a);
+	SVO_LAUNCH_INDEP(div_up(nbd, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_keys, a);
 	b->brick_args = a; // k_brick_emit (after the sizes are known) works on the same arrays
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 	SVO_CUDA_TRY(cudaGetLastError());
