@@ -203,8 +203,8 @@ struct BrickArgs {
 	const uint64_t *n_small;
 	// per brick (arrays sized for the upper bound "number of pairs"; entries past n_bricks stay zero)
 	uint32_t *temp;         // [512] the 8-word leaf blocks of the brick's depth L-1 nodes, dense, in Morton order
-	uint4 *rec;             // x, y: occupancy of the depth L-1 nodes 2l (bit l of x) and 2l+1 (bit l of y); z: of the 8 depth L-2 nodes
-	uint32_t *cnt[3];       // leaves, depth L-1 nodes, depth L-2 nodes of the brick (three consecutive arrays of n_bound)
+	uint4 *rec;             // x, y: occupancy of the depth L-1 nodes 2l (bit l of x) and 2l+1 (bit l of y); z: of the 8 depth L-2 nodes;
+	                        // w: number of leaves | depth L-1 nodes << 10 | depth L-2 nodes << 17 (zeroed: bricks past n_bricks count 0)
 	const uint64_t *rank[3]; // exclusive scans of cnt[] (rank[j][n] = total)
 	uint64_t n_bound;       // entries of the per-brick arrays
 	uint64_t *keys_top;      // per depth L-2 node: Morton code (what k_parent_compact builds the upper levels from)
@@ -249,7 +249,7 @@ SVO_DEV void brick_edges(const TriSetup &ts, int32_t X, int32_t Y, int32_t dx, i
 }
 
 template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raster(BrickArgs a) {
-	__align__(16) __shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS]; // leaf words; valid where the cell's bit is set
+	__align__(16) __shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS]; // leaf words (zeroed per brick; bits: which cells have a first writer)
 	__shared__ uint32_t s_bits[BRICK_WARPS][BRICK_CELLS / 32];
 	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the first triangle of every brick of the warp
 	__align__(16) __shared__ uint64_t s_meta[BRICK_WARPS][BRICK_BPW][4];
@@ -285,6 +285,11 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 		const uint64_t brick = brick0 + q;
 		if (brick >= nb) break; // warp-uniform
 		if (lane < BRICK_CELLS / 32) bits[lane] = 0u;
+		{ // (empty cells must read as zero when the finished blocks are copied out below)
+			uint4 *g4 = reinterpret_cast<uint4 *>(g);
+#pragma unroll
+			for (int k = 0; k < BRICK_CELLS / 128; ++k) g4[k * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+		}
 		__syncwarp();
 		const ulonglong2 m01 = *reinterpret_cast<const ulonglong2 *>(&s_meta[warp][q][0]);
 		const ulonglong2 m23 = *reinterpret_cast<const ulonglong2 *>(&s_meta[warp][q][2]);
@@ -363,10 +368,8 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 		const uint32_t b0 = __ballot_sync(FULL_MASK, o0), b1 = __ballot_sync(FULL_MASK, o1);
 		const uint32_t c0 = warp_sum((uint32_t)__popc(hw));
 		const uint32_t n2 = __ballot_sync(FULL_MASK, lane < 8 && (((b0 | b1) >> (4 * lane)) & 0xfu) != 0u); // 8 nodes = 4 lanes
-		if (lane == 0) {
-			a.rec[brick] = make_uint4(b0, b1, n2, 0u);
-			a.cnt[0][brick] = c0, a.cnt[1][brick] = (uint32_t)(__popc(b0) + __popc(b1)), a.cnt[2][brick] = (uint32_t)__popc(n2);
-		}
+		if (lane == 0) // w: the brick's counts (leaves 10 bits, depth L-1 nodes 7 bits, depth L-2 nodes 4 bits) for the rank scans
+			a.rec[brick] = make_uint4(b0, b1, n2, c0 | ((uint32_t)(__popc(b0) + __popc(b1)) << 10) | ((uint32_t)__popc(n2) << 17));
 		if (hw) {
 			const uint32_t lt = (1u << lane) - 1u;
 			uint32_t rank = (uint32_t)(__popc(b0 & lt) + __popc(b1 & lt));
@@ -376,10 +379,7 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raste
 			for (int h = 0; h < 2; ++h) {
 				const uint32_t m = (hw >> (8 * h)) & 0xffu;
 				if (m) {
-					uint4 lo = src[2 * h], hi = src[2 * h + 1];
-					lo.x = m & 1u ? lo.x : 0u, lo.y = m & 2u ? lo.y : 0u, lo.z = m & 4u ? lo.z : 0u, lo.w = m & 8u ? lo.w : 0u;
-					hi.x = m & 16u ? hi.x : 0u, hi.y = m & 32u ? hi.y : 0u, hi.z = m & 64u ? hi.z : 0u, hi.w = m & 128u ? hi.w : 0u;
-					dst[2 * rank] = lo, dst[2 * rank + 1] = hi;
+					dst[2 * rank] = src[2 * h], dst[2 * rank + 1] = src[2 * h + 1];
 					++rank;
 				}
 			}

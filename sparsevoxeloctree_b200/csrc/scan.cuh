@@ -109,16 +109,12 @@ constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_IT
 // NONZERO = false: f(v) = v; NONZERO = true: f(v) = (v != 0), i.e. the scan numbers the non-zero entries.
 // (Two counters are never packed into one scanned word: the look-back keeps 62 value bits per tile, so a packed
 // count << 40 | sum silently wrapped at 2^22 counted entries.)
-// gridDim.y > 1: that many independent scans in one launch -- scan y reads in + y * in_stride, writes out + y *
-// out_stride and uses its own look-back chain (state + y * state_stride) and ticket (ticket + y).
 template <class InT, bool NONZERO>
 __global__ void __launch_bounds__(SCAN_BLOCK)
-    k_exclusive_scan(const InT *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket,
-                     uint64_t in_stride, uint64_t out_stride, uint64_t state_stride) {
+    k_exclusive_scan(const InT *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket) {
 	__shared__ uint64_t s_warp[SCAN_BLOCK / 32 + 1];
 	__shared__ uint32_t s_ticket;
 	__shared__ uint64_t s_prefix;
-	in += blockIdx.y * in_stride, out += blockIdx.y * out_stride, state += blockIdx.y * state_stride, ticket += blockIdx.y;
 	const uint32_t tile = take_ticket(ticket, &s_ticket);
 	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
 	InT v[SCAN_ITEMS];
@@ -147,6 +143,42 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 	if (n == 0 && tile == 0 && threadIdx.x == 0) out[0] = 0;
 }
 
+// The three rank scans of the brick path in one launch: element i of scan y (= blockIdx.y) is a bit field of word w of
+// the 16-byte brick record i (leaves: bits 0..9, depth L-1 nodes: 10..16, depth L-2 nodes: 17..20).
+__global__ void __launch_bounds__(SCAN_BLOCK)
+    k_exclusive_scan_brick_counts(const uint4 *__restrict__ rec, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket,
+                                  uint64_t out_stride, uint64_t state_stride) {
+	__shared__ uint64_t s_warp[SCAN_BLOCK / 32 + 1];
+	__shared__ uint32_t s_ticket;
+	__shared__ uint64_t s_prefix;
+	const uint32_t y = blockIdx.y;
+	const uint32_t shift = y == 0u ? 0u : (y == 1u ? 10u : 17u), mask = y == 0u ? 0x3ffu : (y == 1u ? 0x7fu : 0xfu);
+	out += y * out_stride, state += y * state_stride, ticket += y;
+	const uint32_t tile = take_ticket(ticket, &s_ticket);
+	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+	uint64_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		v[i] = base + i < n ? (rec[base + i].w >> shift) & mask : 0u;
+		sum += v[i];
+	}
+	uint64_t total;
+	uint64_t excl = block_exclusive_sum<SCAN_BLOCK, uint64_t>(sum, total, s_warp);
+	if (threadIdx.x < 32) {
+		uint64_t p = lookback_exclusive(state, tile, total, threadIdx.x);
+		if (threadIdx.x == 0) s_prefix = p;
+	}
+	__syncthreads();
+	uint64_t run = s_prefix + excl;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		if (base + i < n) out[base + i] = run;
+		run += v[i];
+	}
+	if (n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = run;
+}
+
 struct ScanScratch {
 	DevBuf<uint64_t> state;
 	DevBuf<uint32_t> ticket;
@@ -161,22 +193,18 @@ inline int exclusive_scan(const InT *in, uint64_t *out, uint64_t n, ScanScratch 
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (tiles + 1) * sizeof(uint64_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, sizeof(uint32_t), s));
 	auto k = k_exclusive_scan<InT, NONZERO>;
-	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p, (uint64_t)0, (uint64_t)0, (uint64_t)0);
+	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p);
 	SVO_CUDA_TRY(cudaGetLastError());
 	return 0;
 }
 
-// `count` scans of n elements each in one launch: input arrays in_stride apart, outputs (n + 1 entries) out_stride apart
-template <class InT>
-inline int exclusive_scan_multi(const InT *in, uint64_t in_stride, uint64_t *out, uint64_t out_stride, uint64_t n, uint32_t count,
-                                ScanScratch &sc, cudaStream_t s) {
+inline int exclusive_scan_brick_counts(const uint4 *rec, uint64_t *out, uint64_t out_stride, uint64_t n, ScanScratch &sc, cudaStream_t s) {
 	const uint32_t tiles = n ? div_up(n, SCAN_TILE) : 1;
-	SVO_TRY(sc.state.reserve((uint64_t)(tiles + 1) * count, s));
-	SVO_TRY(sc.ticket.reserve(count, s));
-	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (uint64_t)(tiles + 1) * count * sizeof(uint64_t), s));
-	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, count * sizeof(uint32_t), s));
-	auto k = k_exclusive_scan<InT, false>;
-	SVO_LAUNCH(dim3(tiles, count), SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p, in_stride, out_stride, (uint64_t)(tiles + 1));
+	SVO_TRY(sc.state.reserve((uint64_t)(tiles + 1) * 3, s));
+	SVO_TRY(sc.ticket.reserve(3, s));
+	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (uint64_t)(tiles + 1) * 3 * sizeof(uint64_t), s));
+	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, 3 * sizeof(uint32_t), s));
+	SVO_LAUNCH(dim3(tiles, 3), SCAN_BLOCK, 0, s, k_exclusive_scan_brick_counts, rec, out, n, sc.state.p, sc.ticket.p, out_stride, (uint64_t)(tiles + 1));
 	SVO_CUDA_TRY(cudaGetLastError());
 	return 0;
 }

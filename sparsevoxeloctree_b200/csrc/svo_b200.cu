@@ -951,16 +951,15 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 
 	// per-brick arrays are sized for the upper bound "one brick per pair"; entries past the real number of bricks stay 0
 	const uint64_t nbd = n_pairs;
-	SVO_TRY(b->brick_u32.reserve(nbd * (3 + 4) + 4, s));
+	SVO_TRY(b->brick_u32.reserve(nbd * 4, s));
 	SVO_TRY(b->brick_u64.reserve((nbd + 1) * 3, s));
 	SVO_TRY(b->brick_temp.reserve(nbd * BRICK_CELLS, s)); // 2 KB per brick (fails with SVO_ERR_CUDA when the device cannot hold it: SVO_BUILD_PATH=0 sorts every fragment instead)
-	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_u32.p, 0, nbd * 3 * sizeof(uint32_t), s)); // the three counts
+	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_u32.p, 0, nbd * 4 * sizeof(uint32_t), s)); // the records (their counts: w)
 	BrickArgs a{};
 	a.pairs = pairs, a.brick_first = b->brick_first.p, a.brick_code = brick_code, a.n_bricks = b->pair_idx.p + n_pairs;
 	a.large = v->large.p, a.luv = v->large_uv.p, a.tv = v->scene->view.tex, a.rp = v->rp;
 	a.small_keys = B, a.small_leaf = b->small_leaf.p, a.n_small = d_nsl;
-	for (int j = 0; j < 3; ++j) a.cnt[j] = b->brick_u32.p + nbd * j;
-	a.rec = reinterpret_cast<uint4 *>(b->brick_u32.p + ((nbd * 3 + 3) & ~3ull)); // (16-byte aligned: the pool hands out 256-byte aligned blocks)
+	a.rec = reinterpret_cast<uint4 *>(b->brick_u32.p); // (16-byte aligned: the pool hands out 256-byte aligned blocks)
 	for (int j = 0; j < 3; ++j) a.rank[j] = b->brick_u64.p + (nbd + 1) * j;
 	a.n_bound = nbd;
 	a.temp = b->brick_temp.p;
@@ -973,7 +972,7 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	else
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[1], s));
-	SVO_TRY(exclusive_scan_multi((const uint32_t *)a.cnt[0], nbd, b->brick_u64.p, nbd + 1, nbd, 3, b->scan_scratch, s)); // three scans, one launch
+	SVO_TRY(exclusive_scan_brick_counts(a.rec, b->brick_u64.p, nbd + 1, nbd, b->scan_scratch, s)); // three scans, one launch
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[2], s));
 	SVO_LAUNCH_INDEP(div_up(nbd, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_keys, a);
 	b->brick_args = a; // k_brick_emit (after the sizes are known) works on the same arrays
