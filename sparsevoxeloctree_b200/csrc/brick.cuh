@@ -248,7 +248,10 @@ SVO_DEV void brick_edges(const TriSetup &ts, int32_t X, int32_t Y, int32_t dx, i
 	}
 }
 
-template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_raster(BrickArgs a) {
+#ifndef SVO_BRICK_MINB
+#define SVO_BRICK_MINB 4 // resident blocks per SM asked of the compiler (64 registers per thread)
+#endif
+template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MINB) k_brick_raster(BrickArgs a) {
 	__align__(16) __shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS]; // leaf words (zeroed per brick; bits: which cells have a first writer)
 	__shared__ uint32_t s_bits[BRICK_WARPS][BRICK_CELLS / 32];
 	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the first triangle of every brick of the warp
