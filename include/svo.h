@@ -140,7 +140,8 @@ SVO_API int svo_voxelizer_create_windowed(svo_scene *scene, uint32_t level, int 
                                           const uint32_t window_hi[3], void *stream, svo_voxelizer **out);
 SVO_API void svo_voxelizer_destroy(svo_voxelizer *vox);
 /* Voxelizer::CmdVoxelize (src/Voxelizer.hpp:49, src/Voxelizer.cpp:167-179): enqueues the fragment
- * emission on the stream (the reference records it into a command buffer). */
+ * emission on the stream (the reference records it into a command buffer).  On the brick path only the small
+ * triangles are emitted here (see svo_voxelizer_fragments). */
 SVO_API int svo_voxelizer_voxelize(svo_voxelizer *vox, void *stream);
 SVO_API uint32_t svo_voxelizer_level(const svo_voxelizer *vox);            /* Voxelizer::GetLevel */
 SVO_API uint32_t svo_voxelizer_resolution(const svo_voxelizer *vox);       /* Voxelizer::GetVoxelResolution */
@@ -151,7 +152,11 @@ SVO_API uint64_t svo_voxelizer_fragment_count(const svo_voxelizer *vox);   /* Vo
  * The list is valid between svo_voxelizer_voxelize() and the next svo_builder_build()/prepare() on this voxelizer:
  * the build CONSUMES it (sorts it in place and reuses the storage), unlike the reference's CmdBuild, which only reads
  * it.  After a build, svo_voxelizer_export_reference_fragments() and a second build return SVO_ERR_NOT_READY until
- * svo_voxelizer_voxelize() has run again. */
+ * svo_voxelizer_voxelize() has run again.
+ * Brick path (svo_debug_set_build_path): svo_voxelizer_voxelize() emits only the small triangles' fragments -- the
+ * builder bins the large triangles and never needs theirs.  This call (and svo_voxelizer_export_reference_fragments)
+ * then completes the list first: it enqueues the large triangles' emission on the voxelizer's last stream and waits
+ * for it, so the returned list is whole and may be read on any stream. */
 SVO_API const uint64_t *svo_voxelizer_fragments(const svo_voxelizer *vox);
 /* The reference's own fragment packing (shader/voxelizer.frag:40-42, uvec2 per fragment, levels
  * <= 12): converts the fragment list into d_out (DEVICE, fragment_count * 8 bytes) on the stream. */

@@ -929,6 +929,7 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[1], s));
 	b->n_small_leaves = h_small[0];
 	const uint64_t nsb = h_small[1], n_pairs = npl + nsb;
+	if (n_pairs >= (1ull << 32)) return fail(SVO_ERR_CAPACITY, "brick path: more than 2^32-1 (brick, triangle) pairs");
 	b->n_pairs = n_pairs;
 	SVO_TRY(b->pairs_a.reserve(n_pairs, s));
 	SVO_TRY(b->pairs_b.reserve(n_pairs, s));
