@@ -32,6 +32,12 @@ constexpr int BRICK_WARPS = 8, BRICK_BLOCK = BRICK_WARPS * 32; // a warp works o
 // A pair word: brick Morton code << 33 | is_large << 32 | payload.  payload = index of the large triangle, or (small
 // record, is_large = 0: first inside its brick) the index of the brick's first leaf in the small-leaf list.
 SVO_HD inline uint64_t pair_large(uint64_t brick, uint32_t li) { return (brick << 33) | (1ull << 32) | (uint64_t)li; }
+// Payload of a large pair: triangle index in bits 0..25; bit 31 = FLAT: the triangle covers all 64 pixels of the brick's
+// footprint with one and the same depth voxel (bits 28..30: that voxel's position inside the brick; bits 26..27: the
+// triangle's dominant axis) and takes its colour from the draw -- the whole content of such a pair is known without
+// looking at a single pixel.  Walls and floors parallel to the grid are made of such pairs.
+constexpr uint32_t PAIR_LI_MASK = 0x03ffffffu, PAIR_FLAT = 0x80000000u;
+SVO_HD inline uint32_t pair_flat_bits(uint32_t axis, uint32_t dz) { return PAIR_FLAT | (dz << 28) | (axis << 26); }
 SVO_HD inline uint64_t pair_small(uint64_t brick, uint32_t first) { return (brick << 33) | (uint64_t)first; }
 constexpr uint32_t PAIR_SORT_BEGIN = 33; // sorted bits: [33, 33 + 3 * (level - 3)) -- the brick code only: small records are put in front
                                          // of the large pairs before the (stable) sort, so they stay first inside their brick
@@ -76,6 +82,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 	const int32_t t0 = (ts.py0 - oy) >> BRICK_LOG;
 	const int32_t ntr = ((ts.py1 - oy) >> BRICK_LOG) - t0 + 1;
 	const uint64_t base = tr_base[li];
+	const bool flat_ok = EMIT && large[li].textured == 0u && li <= PAIR_LI_MASK; // (textured triangles: the colour varies per pixel)
 	for (int32_t tr = (int32_t)blockIdx.y; tr < ntr; tr += (int32_t)gridDim.y) {
 		const int32_t ty = t0 + tr;
 		int32_t xlo = 0x7fffffff, xhi = -0x7fffffff;
@@ -102,11 +109,21 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 			uint64_t o = EMIT ? pair_off[base + tr] : 0;
 			for (int32_t tb = tx0; tb <= tx1; tb += 32) {
 				const int32_t tx = tb + lane;
-				uint32_t cnt = 0, zb0 = 0;
+				uint32_t cnt = 0, zb0 = 0, flat = 0;
 				if (tx <= tx1) {
 					const int32_t ax = tmax(xlo, ox + tx * 8), bx = tmin(xhi, ox + tx * 8 + 7);
 					const uint32_t u0 = pixel_depth_row(ts, rp.res, ax, r_lo), u1 = pixel_depth_row(ts, rp.res, bx, r_lo);
 					const uint32_t u2 = pixel_depth_row(ts, rp.res, ax, r_hi), u3 = pixel_depth_row(ts, rp.res, bx, r_hi);
+					if (EMIT && flat_ok && bx - ax == 7 && yhi - ylo == 7) {
+						// FLAT: the four corner pixels of the whole 8 x 8 tile are covered and give fragments with the same depth
+						// voxel.  The edge functions are linear and the depth voxel is monotone in x and in y, so every pixel of
+						// the tile is then covered, passes the depth clip / window like the corners, and lands in that voxel.
+						uint32_t c0, c1, c2, c3;
+						const bool all = pixel_covered(ts, ax, ylo) && pixel_covered(ts, bx, ylo) && pixel_covered(ts, ax, yhi) && pixel_covered(ts, bx, yhi) &&
+						                 pixel_fragment(ts, rp.res, ax, ylo, c0) && pixel_fragment(ts, rp.res, bx, ylo, c1) &&
+						                 pixel_fragment(ts, rp.res, ax, yhi, c2) && pixel_fragment(ts, rp.res, bx, yhi, c3);
+						if (all && c0 == c1 && c0 == c2 && c0 == c3) flat = pair_flat_bits(axis, (c0 - oz) & 7u);
+					}
 					uint32_t umin = tmin(tmin(u0, u1), tmin(u2, u3)), umax = tmax(tmax(u0, u1), tmax(u2, u3));
 					bool any = true;
 					if (ts.cull_depth) { // the shard's depth window (fragments outside are dropped)
@@ -124,7 +141,7 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 					for (uint32_t q = 0; q < cnt; ++q) {
 						uint32_t bx, by, bz;
 						unswizzle(axis, (uint32_t)tx, (uint32_t)ty, zb0 + q, bx, by, bz);
-						pairs[w++] = pair_large(morton3(bx, by, bz), li);
+						pairs[w++] = pair_large(morton3(bx, by, bz), li | flat); // (a flat tile has one depth brick: cnt = 1)
 					}
 				}
 				total += __shfl_sync(FULL_MASK, inc, 31);
@@ -272,21 +289,49 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 		uint64_t *m = s_meta[warp][lane];
 		m[0] = (uint64_t)p0 | ((uint64_t)p1 << 32);
 		m[1] = a.brick_code[brick0 + lane];
-		m[2] = a.pairs[p0];
-		m[3] = 0;
+		const uint64_t pr = a.pairs[p0];
+		m[2] = pr;
+		// a brick whose only pair is FLAT needs nothing of its triangle but the colour
+		const bool solo_flat = p1 - p0 == 1u && ((pr >> 32) & 1ull) && ((uint32_t)pr & PAIR_FLAT);
+		m[3] = solo_flat ? (1ull << 32) | a.large[(uint32_t)pr & PAIR_LI_MASK].rgb : 0ull;
 	}
 	__syncwarp();
 #pragma unroll
 	for (int q = 0; q < BRICK_BPW; ++q) {
 		if (brick0 + q >= nb) break;
 		const uint64_t pr = s_meta[warp][q][2];
-		if (((pr >> 32) & 1ull) && lane < LT_WORDS) s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + (uint32_t)pr)[lane];
+		if (((pr >> 32) & 1ull) && !(s_meta[warp][q][3] >> 32) && lane < LT_WORDS)
+			s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + ((uint32_t)pr & PAIR_LI_MASK))[lane];
 	}
 
 #pragma unroll 1
 	for (int q = 0; q < BRICK_BPW; ++q) {
 		const uint64_t brick = brick0 + q;
 		if (brick >= nb) break; // warp-uniform
+		if (s_meta[warp][q][3] >> 32) { // warp-uniform
+			// The brick's only pair is FLAT: 64 voxels in one plane of the brick, one fragment each, all of the draw's
+			// colour.  Its 16 depth L-1 nodes (4 x 4 in the plane) hold four leaves each, in the same slots: 16 identical
+			// blocks; the record follows from the axis and the plane's position.  No pixel is looked at.
+			const uint32_t pl = (uint32_t)s_meta[warp][q][2], leaf = leaf_first((uint32_t)s_meta[warp][q][3]);
+			const uint32_t axis = (pl >> 26) & 3u, dz = (pl >> 28) & 7u;
+			uint32_t wx, wy;
+			screen_axes(axis, wx, wy);
+			uint32_t xb = 0, yb = 0, n2b = 0;
+			if (lane < 16) { // node (lane & 3, lane >> 2) of the plane: Morton index inside the brick, two bits per axis
+				const uint32_t nx = (uint32_t)lane & 3u, ny = (uint32_t)lane >> 2, nd = dz >> 1;
+				const uint32_t j = (((nx & 1u) | ((nx & 2u) << 2)) << wx) | (((ny & 1u) | ((ny & 2u) << 2)) << wy) | (((nd & 1u) | ((nd & 2u) << 2)) << axis);
+				if (j & 1u) yb = 1u << (j >> 1); else xb = 1u << (j >> 1);
+			}
+			if (lane < 4) n2b = 1u << ((((uint32_t)lane & 1u) << wx) | (((uint32_t)lane >> 1) << wy) | ((dz >> 2) << axis));
+			xb = __reduce_or_sync(FULL_MASK, xb), yb = __reduce_or_sync(FULL_MASK, yb), n2b = __reduce_or_sync(FULL_MASK, n2b);
+			if (lane == 0) a.rec[brick] = make_uint4(xb, yb, n2b, 64u | (16u << 10) | (4u << 17));
+			const uint32_t s0 = ((uint32_t)lane & 1u) * 4u, par = dz & 1u; // this lane's 16 bytes: slots s0 .. s0 + 3 of block lane / 2
+			uint4 v;
+			v.x = (((s0 + 0u) >> axis) & 1u) == par ? leaf : 0u, v.y = (((s0 + 1u) >> axis) & 1u) == par ? leaf : 0u;
+			v.z = (((s0 + 2u) >> axis) & 1u) == par ? leaf : 0u, v.w = (((s0 + 3u) >> axis) & 1u) == par ? leaf : 0u;
+			reinterpret_cast<uint4 *>(a.temp + brick * BRICK_CELLS)[lane] = v;
+			continue;
+		}
 		if (lane < BRICK_CELLS / 32) bits[lane] = 0u;
 		{ // (empty cells must read as zero when the finished blocks are copied out below)
 			uint4 *g4 = reinterpret_cast<uint4 *>(g);
@@ -321,7 +366,7 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 			} else {
 				// one large triangle: the brick's 8x8 pixels, two per lane (rows dy and dy + 4); a triangle puts at most one
 				// fragment into a voxel, so the fold of a cell needs no atomics, and triangles follow each other in order
-				const uint32_t li = (uint32_t)pr;
+				const uint32_t li = (uint32_t)pr & PAIR_LI_MASK;
 				if (p != p0) { // (the first pair's triangle is staged already)
 					if (lane < LT_WORDS) s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + li)[lane];
 					__syncwarp();

@@ -481,7 +481,7 @@ static bool brick_path_wanted(const svo_voxelizer *v) {
 		const char *e = getenv("SVO_BUILD_PATH");
 		g_build_path = (e && (e[0] == '0' || e[0] == '1') && !e[1]) ? e[0] - '0' : -1;
 	}
-	if (v->key_level < 4 || v->n_frag_large == 0 || v->n_large == 0 || g_build_path == 0) return false;
+	if (v->key_level < 4 || v->n_frag_large == 0 || v->n_large == 0 || v->n_large > PAIR_LI_MASK || g_build_path == 0) return false;
 	if (g_build_path == 1) return true;
 	// enough large-triangle fragments to pay for the path's extra launches (a Sponza-sized build of 5e6 fragments is
 	// launch bound: 0.38 ms sorted, 0.57 ms binned), and at least a fifth of all fragments
