@@ -37,6 +37,9 @@ SVO_HD inline uint64_t pair_large(uint64_t brick, uint32_t li) { return (brick <
 // triangle's dominant axis) and takes its colour from the draw -- the whole content of such a pair is known without
 // looking at a single pixel.  Walls and floors parallel to the grid are made of such pairs.
 constexpr uint32_t PAIR_LI_MASK = 0x03ffffffu, PAIR_FLAT = 0x80000000u;
+// brick record, word w: counts in bits 0..20; bit 21 = the brick is one flat pair (axis: bits 22..23, depth parity: bit 24,
+// colour: word z bits 8..31) -- its leaf blocks are not in temp
+constexpr uint32_t REC_FLAT = 1u << 21;
 SVO_HD inline uint32_t pair_flat_bits(uint32_t axis, uint32_t dz) { return PAIR_FLAT | (dz << 28) | (axis << 26); }
 SVO_HD inline uint64_t pair_small(uint64_t brick, uint32_t first) { return (brick << 33) | (uint64_t)first; }
 constexpr uint32_t PAIR_SORT_BEGIN = 33; // sorted bits: [33, 33 + 3 * (level - 3)) -- the brick code only: small records are put in front
@@ -220,8 +223,9 @@ struct BrickArgs {
 	const uint64_t *n_small;
 	// per brick (arrays sized for the upper bound "number of pairs"; entries past n_bricks stay zero)
 	uint32_t *temp;         // [512] the 8-word leaf blocks of the brick's depth L-1 nodes, dense, in Morton order
-	uint4 *rec;             // x, y: occupancy of the depth L-1 nodes 2l (bit l of x) and 2l+1 (bit l of y); z: of the 8 depth L-2 nodes;
-	                        // w: number of leaves | depth L-1 nodes << 10 | depth L-2 nodes << 17 (zeroed: bricks past n_bricks count 0)
+	uint4 *rec;             // x, y: occupancy of the depth L-1 nodes 2l (bit l of x) and 2l+1 (bit l of y); z bits 0..7: of the 8 depth
+	                        // L-2 nodes; w: number of leaves | depth L-1 nodes << 10 | depth L-2 nodes << 17 (zeroed: bricks past
+	                        // n_bricks count 0); flat bricks: see REC_FLAT
 	const uint64_t *rank[3]; // exclusive scans of cnt[] (rank[j][n] = total)
 	uint64_t n_bound;       // entries of the per-brick arrays
 	uint64_t *keys_top;      // per depth L-2 node: Morton code (what k_parent_compact builds the upper levels from)
@@ -311,8 +315,9 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 		if (s_meta[warp][q][3] >> 32) { // warp-uniform
 			// The brick's only pair is FLAT: 64 voxels in one plane of the brick, one fragment each, all of the draw's
 			// colour.  Its 16 depth L-1 nodes (4 x 4 in the plane) hold four leaves each, in the same slots: 16 identical
-			// blocks; the record follows from the axis and the plane's position.  No pixel is looked at.
-			const uint32_t pl = (uint32_t)s_meta[warp][q][2], leaf = leaf_first((uint32_t)s_meta[warp][q][3]);
+			// blocks, described completely by the record (occupancy from the axis and the plane's position, colour, slot
+			// parity).  No pixel is looked at, nothing but 16 bytes is written.
+			const uint32_t pl = (uint32_t)s_meta[warp][q][2], rgb = (uint32_t)s_meta[warp][q][3] & 0xffffffu;
 			const uint32_t axis = (pl >> 26) & 3u, dz = (pl >> 28) & 7u;
 			uint32_t wx, wy;
 			screen_axes(axis, wx, wy);
@@ -324,12 +329,9 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 			}
 			if (lane < 4) n2b = 1u << ((((uint32_t)lane & 1u) << wx) | (((uint32_t)lane >> 1) << wy) | ((dz >> 2) << axis));
 			xb = __reduce_or_sync(FULL_MASK, xb), yb = __reduce_or_sync(FULL_MASK, yb), n2b = __reduce_or_sync(FULL_MASK, n2b);
-			if (lane == 0) a.rec[brick] = make_uint4(xb, yb, n2b, 64u | (16u << 10) | (4u << 17));
-			const uint32_t s0 = ((uint32_t)lane & 1u) * 4u, par = dz & 1u; // this lane's 16 bytes: slots s0 .. s0 + 3 of block lane / 2
-			uint4 v;
-			v.x = (((s0 + 0u) >> axis) & 1u) == par ? leaf : 0u, v.y = (((s0 + 1u) >> axis) & 1u) == par ? leaf : 0u;
-			v.z = (((s0 + 2u) >> axis) & 1u) == par ? leaf : 0u, v.w = (((s0 + 3u) >> axis) & 1u) == par ? leaf : 0u;
-			reinterpret_cast<uint4 *>(a.temp + brick * BRICK_CELLS)[lane] = v;
+			// (no leaf blocks in temp: k_brick_emit writes the 16 identical blocks from the record -- z: colour << 8, w: flags)
+			if (lane == 0)
+				a.rec[brick] = make_uint4(xb, yb, n2b | (rgb << 8), 64u | (16u << 10) | (4u << 17) | REC_FLAT | (axis << 22) | ((dz & 1u) << 24));
 			continue;
 		}
 		if (lane < BRICK_CELLS / 32) bits[lane] = 0u;
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_keys(BrickArgs a) {
 	const uint64_t brick = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
 	if (brick < 3) *a.count[brick] = a.rank[brick][a.n_bound];
 	if (brick >= *a.n_bricks) return;
-	uint32_t n2 = a.rec[brick].z;
+	uint32_t n2 = a.rec[brick].z & 0xffu;
 	if (!n2) return;
 	uint64_t *dst = a.keys_top + a.rank[2][brick];
 	const uint64_t code = (a.brick_code[brick] & 0x3fffffffull) << 3;
@@ -474,12 +476,20 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEm
 	if (c1 == 0u) return;
 	const uint64_t r1 = a.rank[1][brick];
 	const uint64_t g1 = be.block_l + r1 - be.block_shift; // where the brick's first leaf block goes
-	{
+	uint4 *dst = reinterpret_cast<uint4 *>(words + g1 * 8);
+	if (rec.w & REC_FLAT) { // 16 identical blocks: slot s holds the leaf iff its bit `axis` equals the plane's depth parity
+		const uint32_t axis = (rec.w >> 22) & 3u, par = (rec.w >> 24) & 1u, leaf = leaf_first(rec.z >> 8);
+		const uint32_t s0 = (sub & 1u) * 4u; // pieces sub and sub + 16: the same half (slots s0 .. s0 + 3) of blocks sub / 2 and sub / 2 + 8
+		uint4 v;
+		v.x = (((s0 + 0u) >> axis) & 1u) == par ? leaf : 0u, v.y = (((s0 + 1u) >> axis) & 1u) == par ? leaf : 0u;
+		v.z = (((s0 + 2u) >> axis) & 1u) == par ? leaf : 0u, v.w = (((s0 + 3u) >> axis) & 1u) == par ? leaf : 0u;
+		dst[sub] = v, dst[sub + 16u] = v;
+	} else {
 		const uint4 *src = reinterpret_cast<const uint4 *>(a.temp + brick * BRICK_CELLS);
-		uint4 *dst = reinterpret_cast<uint4 *>(words + g1 * 8);
 		for (uint32_t i = sub; i < 2u * c1; i += 16u) dst[i] = src[i]; // 16-byte pieces, consecutive lanes consecutive pieces
 	}
-	if (sub < 8u && ((rec.z >> sub) & 1u)) { // a depth L-2 node: one block of pointers to its children's blocks
+	const uint32_t n2 = rec.z & 0xffu;
+	if (sub < 8u && ((n2 >> sub) & 1u)) { // a depth L-2 node: one block of pointers to its children's blocks
 		uint32_t c = (uint32_t)g1 + brick_node_rank(rec.x, rec.y, 8u * sub);
 		uint32_t w[8];
 #pragma unroll
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEm
 			const bool occ = (((node & 1u) ? rec.y : rec.x) >> (node >> 1)) & 1u;
 			w[sl] = occ ? (0x80000000u | ((c++ << 3) + be.ptr_bias)) : 0u;
 		}
-		const uint64_t g = be.block_l1 + a.rank[2][brick] + (uint32_t)__popc(rec.z & ((1u << sub) - 1u)) - be.block_shift;
+		const uint64_t g = be.block_l1 + a.rank[2][brick] + (uint32_t)__popc(n2 & ((1u << sub) - 1u)) - be.block_shift;
 		uint4 *o = reinterpret_cast<uint4 *>(words + g * 8);
 		o[0] = make_uint4(w[0], w[1], w[2], w[3]);
 		o[1] = make_uint4(w[4], w[5], w[6], w[7]);

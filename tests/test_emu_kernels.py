@@ -105,7 +105,7 @@ def test_textured_path_against_reference_shaders_end_to_end(emu):
     cuda_textured_path_like_reference(emu)
 
 
-@pytest.mark.parametrize("case", ["soup", "dilate", "textured", "shard", "stack"])
+@pytest.mark.parametrize("case", ["soup", "dilate", "textured", "shard", "stack", "room"])
 def test_brick_path_logic(emu, case):
     """brick.cuh on the emulator: pair generation, pair sort, k_brick_raster (shared-memory grids, folds in triangle
     order, leaf blocks), the rank scans and k_brick_emit -- against the oracle, with the path forced."""
@@ -119,6 +119,9 @@ def test_brick_path_logic(emu, case):
             info = check_against_oracle(emu, scenes.textured_soup(40, 11, size_hi=1.0), 6, api.CENTER)
         elif case == "shard":
             info = check_against_oracle(emu, scenes.random_soup(50, 3, 0.01, 1.5), 6, api.CONSERVATIVE_EXACT, shard=(1, (1, 0, 1)))
+        elif case == "room":  # walls parallel to the grid: flat pairs, bricks written from their record alone
+            info = check_against_oracle(emu, scenes.living_room_like(n_boxes=2, n_small=30, level=6), 6, api.CONSERVATIVE_EXACT)
+            assert info["fragments"] > 15000
         else:  # several large triangles through the same voxels
             rng = np.random.default_rng(5)
             pos = (rng.uniform(-0.05, 0.05, (8, 1, 3)) + rng.uniform(-0.7, 0.7, (8, 3, 3))).reshape(-1, 3).astype(np.float32)
