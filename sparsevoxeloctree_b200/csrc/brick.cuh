@@ -228,6 +228,8 @@ struct BrickArgs {
 	                        // n_bricks count 0); flat bricks: see REC_FLAT
 	const uint64_t *rank[3]; // exclusive scans of cnt[] (rank[j][n] = total)
 	uint64_t n_bound;       // entries of the per-brick arrays
+	uint32_t *slow_list;     // the bricks k_brick_raster has to rasterize (all but the flat ones), in any order
+	unsigned long long *n_slow; // how many (zeroed)
 	uint64_t *keys_top;      // per depth L-2 node: Morton code (what k_parent_compact builds the upper levels from)
 	uint64_t *count[3];      // device scalars: leaves, depth L-1, depth L-2 nodes
 };
@@ -269,6 +271,48 @@ SVO_DEV void brick_edges(const TriSetup &ts, int32_t X, int32_t Y, int32_t dx, i
 	}
 }
 
+// Bricks whose only pair is FLAT, one thread per brick: 64 voxels in one plane of the brick, one fragment each, all of
+// the draw's colour.  The 16 depth L-1 nodes (4 x 4 in the plane) hold four leaves each, in the same slots: 16
+// identical blocks, described completely by the 16-byte record written here (occupancy from the axis and the plane's
+// position, colour, slot parity -- REC_FLAT); k_brick_emit generates the blocks.  No pixel is looked at, the triangle
+// record is not read beyond its colour; all other bricks are put on k_brick_raster's list.
+SVO_DEV bool brick_is_solo_flat(uint32_t p0, uint32_t p1, uint64_t first_pair) {
+	return p1 - p0 == 1u && ((first_pair >> 32) & 1ull) && ((uint32_t)first_pair & PAIR_FLAT);
+}
+__global__ void __launch_bounds__(256) k_brick_flat(BrickArgs a) {
+	const uint64_t brick = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const bool valid = brick < *a.n_bricks;
+	uint32_t p0 = 0, p1 = 0;
+	uint64_t pr = 0;
+	if (valid) p0 = a.brick_first[brick], p1 = a.brick_first[brick + 1], pr = a.pairs[p0];
+	const bool flat = valid && brick_is_solo_flat(p0, p1, pr);
+	{ // every other brick goes on the raster kernel's list (one atomic per warp)
+		const unsigned slow = __ballot_sync(FULL_MASK, valid && !flat);
+		unsigned long long pos = 0;
+		if (lane == 0 && slow) pos = atomicAdd(a.n_slow, (unsigned long long)__popc(slow));
+		pos = __shfl_sync(FULL_MASK, pos, 0);
+		if (valid && !flat) a.slow_list[pos + (uint32_t)__popc(slow & ((1u << lane) - 1u))] = (uint32_t)brick;
+	}
+	if (!flat) return;
+	const uint32_t pl = (uint32_t)pr, rgb = a.large[pl & PAIR_LI_MASK].rgb & 0xffffffu;
+	const uint32_t axis = (pl >> 26) & 3u, dz = (pl >> 28) & 7u;
+	uint32_t wx, wy;
+	screen_axes(axis, wx, wy);
+	// the plane's 4 x 4 nodes: Morton index inside the brick with two bits per axis; node 2l -> bit l of x, 2l + 1 -> bit l of y
+	const uint32_t nd = dz >> 1, jd = ((nd & 1u) | ((nd & 2u) << 2)) << axis;
+	uint32_t xb = 0, yb = 0, n2b = 0;
+#pragma unroll
+	for (uint32_t k = 0; k < 16u; ++k) {
+		const uint32_t nx = k & 3u, ny = k >> 2;
+		const uint32_t j = (((nx & 1u) | ((nx & 2u) << 2)) << wx) | (((ny & 1u) | ((ny & 2u) << 2)) << wy) | jd;
+		if (j & 1u) yb |= 1u << (j >> 1); else xb |= 1u << (j >> 1);
+	}
+#pragma unroll
+	for (uint32_t k = 0; k < 4u; ++k) n2b |= 1u << (((k & 1u) << wx) | ((k >> 1) << wy) | ((dz >> 2) << axis));
+	a.rec[brick] = make_uint4(xb, yb, n2b | (rgb << 8), 64u | (16u << 10) | (4u << 17) | REC_FLAT | (axis << 22) | ((dz & 1u) << 24));
+}
+
 #ifndef SVO_BRICK_MINB
 #define SVO_BRICK_MINB 4 // resident blocks per SM asked of the compiler (64 registers per thread)
 #endif
@@ -278,62 +322,38 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the first triangle of every brick of the warp
 	__align__(16) __shared__ uint64_t s_meta[BRICK_WARPS][BRICK_BPW][4];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint64_t nb = *a.n_bricks;
-	const uint64_t brick0 = ((uint64_t)blockIdx.x * BRICK_WARPS + warp) * BRICK_BPW;
+	const uint64_t nb = *a.n_slow; // bricks on the list (k_brick_flat)
+	const uint64_t brick0 = ((uint64_t)blockIdx.x * BRICK_WARPS + warp) * BRICK_BPW; // the warp's first list entry
 	if (brick0 >= nb) return; // whole warp (no block barrier in this kernel)
 	uint32_t *g = s_grid[warp], *bits = s_bits[warp];
 	const int32_t dx = lane & 7, dy = lane >> 3;
 	const uint32_t sx3 = spread3((uint32_t)dx), sy3a = spread3((uint32_t)dy), sy3b = spread3((uint32_t)dy + 4u);
 
-	// The metadata of the warp's bricks is fetched up front, lane q for brick q -- pair range, Morton code, first pair,
+	// The metadata of the warp's bricks is fetched up front, lane q for list entry q -- brick, pair range, Morton code, first pair,
 	// -- and the first triangle of every brick is staged in shared memory by 22 lanes at once: three
 	// dependent round trips per BRICK_BPW bricks instead of four per brick (latency, not HBM, is what this kernel waits for).
 	if (lane < BRICK_BPW && brick0 + lane < nb) {
-		const uint32_t p0 = a.brick_first[brick0 + lane], p1 = a.brick_first[brick0 + lane + 1];
+		const uint32_t brick = a.slow_list[brick0 + lane];
+		const uint32_t p0 = a.brick_first[brick], p1 = a.brick_first[brick + 1];
 		uint64_t *m = s_meta[warp][lane];
 		m[0] = (uint64_t)p0 | ((uint64_t)p1 << 32);
-		m[1] = a.brick_code[brick0 + lane];
-		const uint64_t pr = a.pairs[p0];
-		m[2] = pr;
-		// a brick whose only pair is FLAT needs nothing of its triangle but the colour
-		const bool solo_flat = p1 - p0 == 1u && ((pr >> 32) & 1ull) && ((uint32_t)pr & PAIR_FLAT);
-		m[3] = solo_flat ? (1ull << 32) | a.large[(uint32_t)pr & PAIR_LI_MASK].rgb : 0ull;
+		m[1] = a.brick_code[brick];
+		m[2] = a.pairs[p0];
+		m[3] = brick;
 	}
 	__syncwarp();
 #pragma unroll
 	for (int q = 0; q < BRICK_BPW; ++q) {
 		if (brick0 + q >= nb) break;
 		const uint64_t pr = s_meta[warp][q][2];
-		if (((pr >> 32) & 1ull) && !(s_meta[warp][q][3] >> 32) && lane < LT_WORDS)
+		if (((pr >> 32) & 1ull) && lane < LT_WORDS)
 			s_tri[warp][q][lane] = reinterpret_cast<const uint64_t *>(a.large + ((uint32_t)pr & PAIR_LI_MASK))[lane];
 	}
 
 #pragma unroll 1
 	for (int q = 0; q < BRICK_BPW; ++q) {
-		const uint64_t brick = brick0 + q;
-		if (brick >= nb) break; // warp-uniform
-		if (s_meta[warp][q][3] >> 32) { // warp-uniform
-			// The brick's only pair is FLAT: 64 voxels in one plane of the brick, one fragment each, all of the draw's
-			// colour.  Its 16 depth L-1 nodes (4 x 4 in the plane) hold four leaves each, in the same slots: 16 identical
-			// blocks, described completely by the record (occupancy from the axis and the plane's position, colour, slot
-			// parity).  No pixel is looked at, nothing but 16 bytes is written.
-			const uint32_t pl = (uint32_t)s_meta[warp][q][2], rgb = (uint32_t)s_meta[warp][q][3] & 0xffffffu;
-			const uint32_t axis = (pl >> 26) & 3u, dz = (pl >> 28) & 7u;
-			uint32_t wx, wy;
-			screen_axes(axis, wx, wy);
-			uint32_t xb = 0, yb = 0, n2b = 0;
-			if (lane < 16) { // node (lane & 3, lane >> 2) of the plane: Morton index inside the brick, two bits per axis
-				const uint32_t nx = (uint32_t)lane & 3u, ny = (uint32_t)lane >> 2, nd = dz >> 1;
-				const uint32_t j = (((nx & 1u) | ((nx & 2u) << 2)) << wx) | (((ny & 1u) | ((ny & 2u) << 2)) << wy) | (((nd & 1u) | ((nd & 2u) << 2)) << axis);
-				if (j & 1u) yb = 1u << (j >> 1); else xb = 1u << (j >> 1);
-			}
-			if (lane < 4) n2b = 1u << ((((uint32_t)lane & 1u) << wx) | (((uint32_t)lane >> 1) << wy) | ((dz >> 2) << axis));
-			xb = __reduce_or_sync(FULL_MASK, xb), yb = __reduce_or_sync(FULL_MASK, yb), n2b = __reduce_or_sync(FULL_MASK, n2b);
-			// (no leaf blocks in temp: k_brick_emit writes the 16 identical blocks from the record -- z: colour << 8, w: flags)
-			if (lane == 0)
-				a.rec[brick] = make_uint4(xb, yb, n2b | (rgb << 8), 64u | (16u << 10) | (4u << 17) | REC_FLAT | (axis << 22) | ((dz & 1u) << 24));
-			continue;
-		}
+		if (brick0 + q >= nb) break; // warp-uniform
+		const uint64_t brick = s_meta[warp][q][3];
 		if (lane < BRICK_CELLS / 32) bits[lane] = 0u;
 		{ // (empty cells must read as zero when the finished blocks are copied out below)
 			uint4 *g4 = reinterpret_cast<uint4 *>(g);

@@ -966,8 +966,11 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	a.temp = b->brick_temp.p;
 	a.keys_top = A;
 	for (uint32_t j = 0; j < 3; ++j) a.count[j] = b->counts.p + (L - j);
+	a.slow_list = b->pair_flags.p; // (the head flags are dead once the brick table exists: n_pairs words)
+	a.n_slow = reinterpret_cast<unsigned long long *>(b->brick_scalars.p + 2);
 	const uint32_t rgrid = div_up(nbd, (uint64_t)BRICK_WARPS * BRICK_BPW);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[0], s));
+	SVO_LAUNCH(div_up(nbd, 256), 256, 0, s, k_brick_flat, a);
 	if (v->scene->textured)
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<true>, a);
 	else
