@@ -256,7 +256,7 @@ def run_ours(args):
     # -------- device-resident arm: inputs already in HBM, handles created (count pass done) ----------------
     phases_acc = {k: 0.0 for k in api.PHASES}
     sort_passes = 0
-    brick_acc, brick_counts, build_path = {"raster": 0.0, "scans": 0.0, "keys": 0.0}, None, 0
+    brick_acc, brick_counts, build_path = {"raster": 0.0, "scans": 0.0, "keys": 0.0, "emit": 0.0}, None, 0
     # one device holds levels <= 13 in a 64-bit fragment; level 14 runs as 8 cube-local octant builds ("virtual shards")
     single = world == 1 and level <= 13
     if single:
@@ -398,30 +398,38 @@ def run_ours(args):
             except Exception:
                 traffic_db = {}
         if build_path == 1 and brick_acc["raster"] > 0:
-            # Brick path: the large triangles never become fragments; the dominant kernel is k_brick_raster.  Its
-            # algorithmic bytes: one 8-byte pair per (brick, triangle) in; per brick its table entries (first pair 4, code 8)
-            # in and its record 16 + counts 12 out; one finished 32-byte leaf block out per depth L-1 node.
-            per_launch_ms = brick_acc["raster"] / args.steps
+            # Brick path: the large triangles never become fragments.  Its two big kernels (cudaEvents around each):
+            #  k_brick_emit   HBM bound.  Algorithmic bytes: every 32-byte block of the two deepest windows written once
+            #                 (leaf blocks: N1, pointer blocks: N2); in: per brick its record (16) and two ranks (16), and the
+            #                 leaf blocks of the bricks that were rasterized (flat bricks -- one triangle, one depth voxel:
+            #                 64 leaves in 16 identical blocks -- are generated from their record).
+            #  k_brick_raster (+ k_brick_flat) instruction bound.  8-byte pairs and per-brick table entries (first pair 4,
+            #                 code 8) in, record 16 out, 32-byte leaf blocks out for the rasterized bricks.
             bld0 = builder if single else sh.builders[0]
-            leaves_rank0 = bld0.GetLeafCount()
-            alg_bytes = 8.0 * brick_counts["pairs"] + 40.0 * brick_counts["bricks"] + 32.0 * bld0.GetLevelCounts()[level - 1 if single else bld0.GetLevel() - 1]
-            achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-            t = traffic_db.get("k_brick_raster", {})
-            roofline = {"bound": "hbm", "kernel": "k_brick_raster", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": t.get("dram_bytes_per_launch") if single else None,
-                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
-                        "launches_per_step": 1, "rank": 0,
-                        "limiter": "instruction issue, not HBM: the kernel rasterizes 64 pixels per (brick, triangle) pair with exact "
-                                   "64-bit edge functions and an fp64 depth plane and moves ~9 bytes per fragment",
-                        "issue_slots_busy_pct": t.get("issue_slots_busy_pct"),
-                        "pairs": brick_counts["pairs"], "bricks": brick_counts["bricks"]}
-            # the step's memory-bound kernel next to it: k_brick_emit copies every leaf block (32 B in, 32 B out) and writes the
-            # pointer blocks of the depth L-2 nodes; with the small k_emit_octree of the upper levels it writes the whole buffer
-            emit_ms = phases_acc["emit"] / args.steps
-            emit_bytes = float(octree_bytes) + 32.0 * bld0.GetLevelCounts()[level - 1 if single else bld0.GetLevel() - 1]
-            kernels = [{"kernel": "k_brick_emit (+ k_emit_octree for the upper levels)", "ms": emit_ms, "algorithmic_bytes": emit_bytes,
-                        "achieved_gbs": emit_bytes / (emit_ms * 1e-3) / 1e9, "frac_of_hbm_peak": emit_bytes / (emit_ms * 1e-3) / 1e9 / peak,
-                        "note": "phase time: includes the size read-back in front of the launch"}] if single and emit_ms > 0 else None
+            lc = bld0.GetLevelCounts()
+            kl = bld0.GetLevel()
+            n1, n2 = lc[kl - 1], lc[kl - 2]
+            flat = brick_counts["bricks"] - brick_counts["raster_bricks"]
+            raster_blocks = n1 - 16 * flat
+            emit_ms, raster_ms = brick_acc["emit"] / args.steps, brick_acc["raster"] / args.steps
+            emit_bytes = 32.0 * (n1 + n2) + 32.0 * brick_counts["bricks"] + 32.0 * raster_blocks
+            raster_bytes = 8.0 * brick_counts["pairs"] + 28.0 * brick_counts["bricks"] + 32.0 * raster_blocks
+            t_emit, t_raster = traffic_db.get("k_brick_emit", {}), traffic_db.get("k_brick_raster", {})
+            k_emit = {"bound": "hbm", "kernel": "k_brick_emit", "achieved": emit_bytes / (emit_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": emit_bytes / (emit_ms * 1e-3) / 1e9 / peak, "traffic": t_emit.get("dram_bytes_per_launch") if single else None,
+                      "peak_source": peak_src, "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms, "launches_per_step": 1,
+                      "rank": 0}
+            k_raster = {"bound": "hbm", "kernel": "k_brick_flat + k_brick_raster", "achieved": raster_bytes / (raster_ms * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": raster_bytes / (raster_ms * 1e-3) / 1e9 / peak,
+                        "traffic": t_raster.get("dram_bytes_per_launch") if single else None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": raster_bytes, "launch_ms": raster_ms, "launches_per_step": 1, "rank": 0,
+                        "limiter": "instruction issue / per-warp latency, not HBM: 64 exact pixel tests (64-bit edge functions, fp64 depth) "
+                                   "per (brick, triangle) pair that is not flat",
+                        "issue_slots_busy_pct": t_raster.get("issue_slots_busy_pct")}
+            for k in (k_emit, k_raster):
+                k.update(pairs=brick_counts["pairs"], bricks=brick_counts["bricks"], flat_bricks=flat)
+            roofline, other = (k_emit, k_raster) if emit_ms >= raster_ms else (k_raster, k_emit)  # the dominant kernel first
+            kernels = [other]
         elif sort_passes and phases_acc["sort_passes"] > 0:
             per_launch_ms = phases_acc["sort_passes"] / args.steps / sort_passes
             # one read + one write of every 8-byte fragment per onesweep pass (N > 1: the fragments of rank 0's first part)

@@ -243,9 +243,10 @@ SVO_API int svo_builder_sort_step_ms(svo_builder *b, float *out, uint32_t cap);
  * (sort + reduce) / pair generation + pair sort / the brick kernel. */
 SVO_API void svo_debug_set_build_path(int mode);
 SVO_API int svo_builder_build_path(const svo_builder *b);
-/* Brick path only, after a build: counts = { (brick, triangle) pairs incl. small records, bricks, leaves of small
- * triangles }, ms = { k_brick_raster, the three rank scans, k_brick_keys } of the last build (cudaEvents). */
-SVO_API int svo_builder_brick_stats(svo_builder *b, uint64_t counts[3], float ms[3]);
+/* Brick path only, after a build (or prepare + emit_to): counts = { (brick, triangle) pairs incl. small records, bricks,
+ * leaves of small triangles, bricks that needed pixels (the others are flat: one triangle, one depth voxel) },
+ * ms = { k_brick_flat + k_brick_raster, the rank scans, k_brick_keys, k_brick_emit } of the last build (cudaEvents). */
+SVO_API int svo_builder_brick_stats(svo_builder *b, uint64_t counts[4], float ms[4]);
 
 /* ---- the consumer side, for verification ----------------------------------------------------
  * Octree_RayMarchLeaf (shader/octree.glsl:179-340, the primary-ray traversal octree_tracer.frag:36 runs on the

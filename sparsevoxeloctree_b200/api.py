@@ -479,12 +479,12 @@ class OctreeBuilder:
         return int(self.lib.dll.svo_builder_build_path(self._h))
 
     def BrickStats(self):
-        """({pairs, bricks, small_leaves}, {raster, scans, keys} in ms) of the last brick-path build."""
-        c = (C.c_uint64 * 3)()
-        ms = (C.c_float * 3)()
+        """({pairs, bricks, small_leaves, raster_bricks}, {raster, scans, keys, emit} in ms) of the last brick-path build."""
+        c = (C.c_uint64 * 4)()
+        ms = (C.c_float * 4)()
         self.lib.check(self.lib.dll.svo_builder_brick_stats(self._h, c, ms))
-        return (dict(pairs=int(c[0]), bricks=int(c[1]), small_leaves=int(c[2])),
-                dict(raster=float(ms[0]), scans=float(ms[1]), keys=float(ms[2])))
+        return (dict(pairs=int(c[0]), bricks=int(c[1]), small_leaves=int(c[2]), raster_bricks=int(c[3])),
+                dict(raster=float(ms[0]), scans=float(ms[1]), keys=float(ms[2]), emit=float(ms[3])))
 
     def SortStepMs(self):
         """Milliseconds of each kernel of the last sort (needs svo_debug_profile_passes(1) before the build)."""

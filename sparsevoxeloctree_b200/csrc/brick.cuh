@@ -481,15 +481,20 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_keys(BrickArgs a) {
 // Node words of the two deepest windows, straight from the bricks (the bulk of the node buffer): the 8-word blocks of
 // a brick's depth L-1 nodes (leaf words: a copy of the brick's part of temp) and of its depth L-2 nodes (pointers to
 // the former) are consecutive in their windows, at the brick's ranks.  Placement as in k_emit_octree: block g ->
-// words[(g - block_shift) * 8], a pointer to block c is (c - block_shift) * 8 + ptr_bias.  16 lanes per brick.
+// words[(g - block_shift) * 8], a pointer to block c is (c - block_shift) * 8 + ptr_bias.  BRICK_EMIT_LANES lanes per brick.
 struct BrickEmit {
 	uint64_t block_l1, block_l; // first block of the window that holds the children of the depth L-2 / of the depth L-1 nodes
 	uint32_t block_shift, ptr_bias;
 };
+#ifndef SVO_BRICK_EMIT_LANES
+#define SVO_BRICK_EMIT_LANES 8 // lanes per brick (8 or 16)
+#endif
+constexpr uint32_t BRICK_EMIT_LANES = SVO_BRICK_EMIT_LANES;
+static_assert(BRICK_EMIT_LANES == 8 || BRICK_EMIT_LANES == 16, "an even number of lanes >= the 8 depth L-2 nodes of a brick");
 __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEmit be, uint32_t *__restrict__ words) {
 	const uint64_t tid = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
-	const uint64_t brick = tid >> 4;
-	const uint32_t sub = threadIdx.x & 15u;
+	const uint64_t brick = tid / BRICK_EMIT_LANES;
+	const uint32_t sub = threadIdx.x % BRICK_EMIT_LANES;
 	if (brick >= *a.n_bricks) return;
 	const uint4 rec = a.rec[brick];
 	const uint32_t c1 = (uint32_t)(__popc(rec.x) + __popc(rec.y));
@@ -499,14 +504,15 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEm
 	uint4 *dst = reinterpret_cast<uint4 *>(words + g1 * 8);
 	if (rec.w & REC_FLAT) { // 16 identical blocks: slot s holds the leaf iff its bit `axis` equals the plane's depth parity
 		const uint32_t axis = (rec.w >> 22) & 3u, par = (rec.w >> 24) & 1u, leaf = leaf_first(rec.z >> 8);
-		const uint32_t s0 = (sub & 1u) * 4u; // pieces sub and sub + 16: the same half (slots s0 .. s0 + 3) of blocks sub / 2 and sub / 2 + 8
+		const uint32_t s0 = (sub & 1u) * 4u; // 16-byte piece i is half i & 1 (slots s0 .. s0 + 3) of block i / 2; the lane's pieces share it
 		uint4 v;
 		v.x = (((s0 + 0u) >> axis) & 1u) == par ? leaf : 0u, v.y = (((s0 + 1u) >> axis) & 1u) == par ? leaf : 0u;
 		v.z = (((s0 + 2u) >> axis) & 1u) == par ? leaf : 0u, v.w = (((s0 + 3u) >> axis) & 1u) == par ? leaf : 0u;
-		dst[sub] = v, dst[sub + 16u] = v;
+#pragma unroll
+		for (uint32_t i = 0; i < 32u; i += BRICK_EMIT_LANES) dst[i + sub] = v;
 	} else {
 		const uint4 *src = reinterpret_cast<const uint4 *>(a.temp + brick * BRICK_CELLS);
-		for (uint32_t i = sub; i < 2u * c1; i += 16u) dst[i] = src[i]; // 16-byte pieces, consecutive lanes consecutive pieces
+		for (uint32_t i = sub; i < 2u * c1; i += BRICK_EMIT_LANES) dst[i] = src[i]; // 16-byte pieces, consecutive lanes consecutive pieces
 	}
 	const uint32_t n2 = rec.z & 0xffu;
 	if (sub < 8u && ((n2 >> sub) & 1u)) { // a depth L-2 node: one block of pointers to its children's blocks

@@ -162,7 +162,8 @@ struct svo_builder {
 	DevBuf<uint64_t> pairs_a, pairs_b, pair_idx, brick_u64, brick_scalars;
 	DevBuf<uint32_t> pair_flags, brick_first, small_leaf, brick_u32, brick_temp;
 	uint64_t n_pairs = 0, n_small_leaves = 0, n_bricks = 0; // of the last build
-	cudaEvent_t ev_brick[3] = {};                            // around k_brick_raster and the scans
+	cudaEvent_t ev_brick[5] = {};                            // around k_brick_flat + k_brick_raster, the scans, k_brick_emit
+	uint64_t n_slow = 0;                                     // bricks that needed pixels (the others are flat)
 	int path = 0;                             // 0: every fragment sorted; 1: bricks
 	BrickArgs brick_args{};                   // the arrays of the last brick build
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
@@ -833,7 +834,7 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 	do {
 		for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 			if (cudaEventCreate(&b->ev[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
-		for (int i = 0; i < 3; ++i)
+		for (int i = 0; i < 5; ++i)
 			if (cudaEventCreate(&b->ev_brick[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
 		if (rc) break;
 		const uint64_t F = vox->n_frag;
@@ -869,7 +870,7 @@ void svo_builder_destroy(svo_builder *b) {
 	b->pair_flags.release(s), b->brick_first.release(s), b->small_leaf.release(s), b->brick_u32.release(s), b->brick_temp.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
-	for (int i = 0; i < 3; ++i)
+	for (int i = 0; i < 5; ++i)
 		if (b->ev_brick[i]) cudaEventDestroy(b->ev_brick[i]);
 	release_export(b);
 	delete b;
@@ -1060,7 +1061,10 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	// ---- exact sizing: the one host round trip of the build ----
 	SVO_CUDA_TRY(cudaMemcpyAsync(b->h_counts, b->counts.p, (L + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
 	b->n_bricks = 0;
-	if (b->path == 1) SVO_CUDA_TRY(cudaMemcpyAsync(&b->n_bricks, b->pair_idx.p + b->n_pairs, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+	if (b->path == 1) {
+		SVO_CUDA_TRY(cudaMemcpyAsync(&b->n_bricks, b->pair_idx.p + b->n_pairs, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+		SVO_CUDA_TRY(cudaMemcpyAsync(&b->n_slow, b->brick_scalars.p + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+	}
 	SVO_CUDA_TRY(cudaStreamSynchronize(s));
 	EmitParams &ep = b->ep;
 	ep = EmitParams{};
@@ -1110,7 +1114,9 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_direct, ep, d_dst);
 		if (b->path == 1) {
 			BrickEmit be{ep.block_base[b->level - 1], ep.block_base[b->level], ep.block_shift, ep.ptr_bias};
-			SVO_LAUNCH_INDEP(div_up(b->brick_args.n_bound * 16, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_emit, b->brick_args, be, d_dst);
+			SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[3], s));
+			SVO_LAUNCH_INDEP(div_up(b->brick_args.n_bound * BRICK_EMIT_LANES, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_emit, b->brick_args, be, d_dst);
+			SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[4], s));
 		}
 	}
 	SVO_CUDA_TRY(cudaGetLastError());
@@ -1417,15 +1423,16 @@ void svo_debug_force_wide_sort_state(int on) { svo::g_force_wide_sort_state = on
 void svo_debug_profile_passes(int on) { svo::g_profile_passes = on != 0; }
 void svo_debug_set_build_path(int mode) { g_build_path = mode < 0 ? -1 : (mode > 0 ? 1 : 0); }
 int svo_builder_build_path(const svo_builder *b) { return b ? b->path : 0; }
-int svo_builder_brick_stats(svo_builder *b, uint64_t counts[3], float ms[3]) {
+int svo_builder_brick_stats(svo_builder *b, uint64_t counts[4], float ms[4]) {
 	if (!b || !counts || !ms) return fail(SVO_ERR_INVALID_ARGUMENT, "null argument");
-	if (!(b->built || b->prepared) || b->path != 1) return fail(SVO_ERR_NOT_READY, "svo_builder_brick_stats: no brick build");
+	if (!(b->built || b->emitted) || b->path != 1) return fail(SVO_ERR_NOT_READY, "svo_builder_brick_stats: no brick build");
 	DeviceGuard guard(b->device);
-	counts[0] = b->n_pairs, counts[1] = b->n_bricks, counts[2] = b->n_small_leaves;
-	SVO_CUDA_TRY(cudaEventSynchronize(b->ev[3]));
+	counts[0] = b->n_pairs, counts[1] = b->n_bricks, counts[2] = b->n_small_leaves, counts[3] = b->n_slow;
+	SVO_CUDA_TRY(cudaEventSynchronize(b->ev_brick[4]));
 	SVO_CUDA_TRY(cudaEventElapsedTime(&ms[0], b->ev_brick[0], b->ev_brick[1]));
 	SVO_CUDA_TRY(cudaEventElapsedTime(&ms[1], b->ev_brick[1], b->ev_brick[2]));
 	SVO_CUDA_TRY(cudaEventElapsedTime(&ms[2], b->ev_brick[2], b->ev[3]));
+	SVO_CUDA_TRY(cudaEventElapsedTime(&ms[3], b->ev_brick[3], b->ev_brick[4]));
 	return SVO_OK;
 }
 #if SVO_OS_CLOCKS
