@@ -117,15 +117,23 @@ __global__ void __launch_bounds__(RASTER_BLOCK)
 					const int32_t ax = tmax(xlo, ox + tx * 8), bx = tmin(xhi, ox + tx * 8 + 7);
 					const uint32_t u0 = pixel_depth_row(ts, rp.res, ax, r_lo), u1 = pixel_depth_row(ts, rp.res, bx, r_lo);
 					const uint32_t u2 = pixel_depth_row(ts, rp.res, ax, r_hi), u3 = pixel_depth_row(ts, rp.res, bx, r_hi);
-					if (EMIT && flat_ok && bx - ax == 7 && yhi - ylo == 7) {
+					if (EMIT && flat_ok && bx - ax == 7 && yhi - ylo == 7 && u0 == u1 && u0 == u2 && u0 == u3) {
 						// FLAT: the four corner pixels of the whole 8 x 8 tile are covered and give fragments with the same depth
 						// voxel.  The edge functions are linear and the depth voxel is monotone in x and in y, so every pixel of
 						// the tile is then covered, passes the depth clip / window like the corners, and lands in that voxel.
-						uint32_t c0, c1, c2, c3;
-						const bool all = pixel_covered(ts, ax, ylo) && pixel_covered(ts, bx, ylo) && pixel_covered(ts, ax, yhi) && pixel_covered(ts, bx, yhi) &&
-						                 pixel_fragment(ts, rp.res, ax, ylo, c0) && pixel_fragment(ts, rp.res, bx, ylo, c1) &&
-						                 pixel_fragment(ts, rp.res, ax, yhi, c2) && pixel_fragment(ts, rp.res, bx, yhi, c3);
-						if (all && c0 == c1 && c0 == c2 && c0 == c3) flat = pair_flat_bits(axis, (c0 - oz) & 7u);
+						bool all = true;
+#pragma unroll
+						for (int i = 0; i < 3; ++i) { // pixel_covered at the corners: one evaluation, stepped 7 columns / 7 rows
+							const int64_t e = ts.ea[i] * (int64_t)ax + ts.eb[i] * (int64_t)ylo + ts.ec[i];
+							const int64_t ex = e + 7 * ts.ea[i], ey = e + 7 * ts.eb[i];
+							all = all && (e | ex | ey | (ex + 7 * ts.eb[i])) >= 0;
+						}
+						if (all && (ts.clip_z || ts.cull_depth)) { // fragments can be dropped: ask pixel_fragment itself
+							uint32_t c;
+							all = pixel_fragment(ts, rp.res, ax, ylo, c) && pixel_fragment(ts, rp.res, bx, ylo, c) &&
+							      pixel_fragment(ts, rp.res, ax, yhi, c) && pixel_fragment(ts, rp.res, bx, yhi, c);
+						}
+						if (all) flat = pair_flat_bits(axis, (u0 - oz) & 7u); // (u0 = the corners' depth voxel: pixel_depth_row is pixel_fragment's arithmetic)
 					}
 					uint32_t umin = tmin(tmin(u0, u1), tmin(u2, u3)), umax = tmax(tmax(u0, u1), tmax(u2, u3));
 					bool any = true;
@@ -189,24 +197,45 @@ __global__ void __launch_bounds__(256)
 	}
 }
 
-// first pair of every brick in the sorted pair list: flags, (scan by exclusive_scan<.., true>), scatter
-__global__ void __launch_bounds__(256) k_brick_head_flags(const uint64_t *__restrict__ pairs, uint64_t n, uint32_t *__restrict__ flags) {
-	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-	if (i >= n) return;
-	flags[i] = (i == 0 || (pairs[i] >> 33) != (pairs[i - 1] >> 33)) ? 1u : 0u;
-}
-__global__ void __launch_bounds__(256)
-    k_brick_head_scatter(const uint64_t *__restrict__ pairs, const uint32_t *__restrict__ flags, const uint64_t *__restrict__ idx, uint64_t n,
-                         uint32_t *__restrict__ brick_first, uint64_t *__restrict__ brick_code) {
-	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-	if (i >= n) return;
-	if (flags[i]) { // Morton code of the brick in bits 0..29, its coordinates (10 bits each) from bit 32
-		const uint64_t m = pairs[i] >> 33;
-		brick_first[idx[i]] = (uint32_t)i;
-		brick_code[idx[i]] = m | ((uint64_t)compact1by2_10((uint32_t)m) << 32) | ((uint64_t)compact1by2_10((uint32_t)(m >> 1)) << 42) |
-		                     ((uint64_t)compact1by2_10((uint32_t)(m >> 2)) << 52);
+// The brick table from the sorted pair list, in one pass (chained scan over the tiles, numbered by a ticket): entry u =
+// first pair of brick u and its code -- Morton code in bits 0..29, its coordinates (10 bits each) from bit 32 --,
+// brick_first[n_bricks] = n, *n_bricks.  state: tiles + 1 words, zeroed; ticket: zeroed.
+__global__ void __launch_bounds__(SCAN_BLOCK)
+    k_brick_heads(const uint64_t *__restrict__ pairs, uint64_t n, uint32_t *__restrict__ brick_first, uint64_t *__restrict__ brick_code,
+                  uint64_t *__restrict__ n_bricks, uint64_t *state, uint32_t *ticket) {
+	__shared__ uint64_t s_warp[SCAN_BLOCK / 32 + 1];
+	__shared__ uint32_t s_ticket;
+	__shared__ uint64_t s_prefix;
+	const uint32_t tile = take_ticket(ticket, &s_ticket);
+	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint64_t code[SCAN_ITEMS];
+	uint64_t prev = (base > 0 && base <= n) ? pairs[base - 1] >> 33 : ~0ull;
+	uint32_t heads = 0, cnt = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		code[i] = base + i < n ? pairs[base + i] >> 33 : prev;
+		if (base + i < n && code[i] != prev) heads |= 1u << i, ++cnt;
+		prev = code[i];
 	}
-	if (i == n - 1) brick_first[idx[n]] = (uint32_t)n; // idx[n] = number of bricks
+	uint64_t total;
+	const uint64_t excl = block_exclusive_sum<SCAN_BLOCK, uint64_t>((uint64_t)cnt, total, s_warp);
+	if (threadIdx.x < 32) {
+		const uint64_t p = lookback_exclusive(state, tile, total, threadIdx.x);
+		if (threadIdx.x == 0) s_prefix = p;
+	}
+	__syncthreads();
+	uint64_t u = s_prefix + excl;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		if ((heads >> i) & 1u) {
+			const uint64_t m = code[i];
+			brick_first[u] = (uint32_t)(base + i);
+			brick_code[u] = m | ((uint64_t)compact1by2_10((uint32_t)m) << 32) | ((uint64_t)compact1by2_10((uint32_t)(m >> 1)) << 42) |
+			                ((uint64_t)compact1by2_10((uint32_t)(m >> 2)) << 52);
+			++u;
+		}
+	}
+	if (n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS) brick_first[u] = (uint32_t)n, *n_bricks = u; // the thread that owns the last pair
 }
 
 struct BrickArgs {

@@ -143,40 +143,53 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 	if (n == 0 && tile == 0 && threadIdx.x == 0) out[0] = 0;
 }
 
-// The three rank scans of the brick path in one launch: element i of scan y (= blockIdx.y) is a bit field of word w of
-// the 16-byte brick record i (leaves: bits 0..9, depth L-1 nodes: 10..16, depth L-2 nodes: 17..20).
+// The three rank scans of the brick path in one pass over the 16-byte brick records: element i of scan y is a bit field
+// of word w of record i (leaves: bits 0..9, depth L-1 nodes: 10..16, depth L-2 nodes: 17..20).  One read of the records,
+// three look-back chains walked by warps 0, 1, 2 at the same time.
 __global__ void __launch_bounds__(SCAN_BLOCK)
     k_exclusive_scan_brick_counts(const uint4 *__restrict__ rec, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket,
                                   uint64_t out_stride, uint64_t state_stride) {
-	__shared__ uint64_t s_warp[SCAN_BLOCK / 32 + 1];
+	__shared__ uint32_t s_warp[3][SCAN_BLOCK / 32];
 	__shared__ uint32_t s_ticket;
-	__shared__ uint64_t s_prefix;
-	const uint32_t y = blockIdx.y;
-	const uint32_t shift = y == 0u ? 0u : (y == 1u ? 10u : 17u), mask = y == 0u ? 0x3ffu : (y == 1u ? 0x7fu : 0xfu);
-	out += y * out_stride, state += y * state_stride, ticket += y;
+	__shared__ uint64_t s_prefix[3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t tile = take_ticket(ticket, &s_ticket);
 	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-	uint32_t v[SCAN_ITEMS];
-	uint64_t sum = 0;
+	uint32_t w[SCAN_ITEMS];
+	uint32_t sum[3] = {0, 0, 0};
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; ++i) {
-		v[i] = base + i < n ? (rec[base + i].w >> shift) & mask : 0u;
-		sum += v[i];
+		w[i] = base + i < n ? rec[base + i].w : 0u;
+		sum[0] += w[i] & 0x3ffu, sum[1] += (w[i] >> 10) & 0x7fu, sum[2] += (w[i] >> 17) & 0xfu;
 	}
-	uint64_t total;
-	uint64_t excl = block_exclusive_sum<SCAN_BLOCK, uint64_t>(sum, total, s_warp);
-	if (threadIdx.x < 32) {
-		uint64_t p = lookback_exclusive(state, tile, total, threadIdx.x);
-		if (threadIdx.x == 0) s_prefix = p;
+	uint32_t inc[3];
+#pragma unroll
+	for (int y = 0; y < 3; ++y) {
+		inc[y] = warp_inclusive_sum(sum[y], lane);
+		if (lane == 31) s_warp[y][warp] = inc[y];
 	}
 	__syncthreads();
-	uint64_t run = s_prefix + excl;
-#pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; ++i) {
-		if (base + i < n) out[base + i] = run;
-		run += v[i];
+	if (warp < 3) { // warp y: the block's total of scan y, its look-back, and the warps' offsets
+		const uint32_t mine = lane < SCAN_BLOCK / 32 ? s_warp[warp][lane] : 0u;
+		const uint32_t winc = warp_inclusive_sum(mine, lane);
+		const uint64_t total = __shfl_sync(FULL_MASK, winc, 31);
+		const uint64_t p = lookback_exclusive(state + (uint64_t)warp * state_stride, tile, total, lane);
+		if (lane < SCAN_BLOCK / 32) s_warp[warp][lane] = winc - mine;
+		if (lane == 0) s_prefix[warp] = p;
 	}
-	if (n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = run;
+	__syncthreads();
+#pragma unroll
+	for (int y = 0; y < 3; ++y) {
+		uint64_t run = s_prefix[y] + s_warp[y][warp] + inc[y] - sum[y];
+		uint64_t *o = out + (uint64_t)y * out_stride;
+		const uint32_t shift = y == 0 ? 0u : (y == 1 ? 10u : 17u), mask = y == 0 ? 0x3ffu : (y == 1 ? 0x7fu : 0xfu);
+#pragma unroll
+		for (int i = 0; i < SCAN_ITEMS; ++i) {
+			if (base + i < n) o[base + i] = run;
+			run += (w[i] >> shift) & mask;
+		}
+		if (n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS) o[n] = run;
+	}
 }
 
 struct ScanScratch {
@@ -204,7 +217,7 @@ inline int exclusive_scan_brick_counts(const uint4 *rec, uint64_t *out, uint64_t
 	SVO_TRY(sc.ticket.reserve(3, s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (uint64_t)(tiles + 1) * 3 * sizeof(uint64_t), s));
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, 3 * sizeof(uint32_t), s));
-	SVO_LAUNCH(dim3(tiles, 3), SCAN_BLOCK, 0, s, k_exclusive_scan_brick_counts, rec, out, n, sc.state.p, sc.ticket.p, out_stride, (uint64_t)(tiles + 1));
+	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k_exclusive_scan_brick_counts, rec, out, n, sc.state.p, sc.ticket.p, out_stride, (uint64_t)(tiles + 1));
 	SVO_CUDA_TRY(cudaGetLastError());
 	return 0;
 }

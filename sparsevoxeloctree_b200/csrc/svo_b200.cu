@@ -159,7 +159,7 @@ struct svo_builder {
 	ScanScratch scan_scratch;
 	DevBuf<uint64_t> rf_cnt01, rf_cnt2, rf_pre01, rf_pre2; // per reduce tile: run counts and their exclusive prefixes
 	// brick path (brick.cuh)
-	DevBuf<uint64_t> pairs_a, pairs_b, pair_idx, brick_u64, brick_scalars;
+	DevBuf<uint64_t> pairs_a, pairs_b, brick_u64, brick_scalars;
 	DevBuf<uint32_t> pair_flags, brick_first, small_leaf, brick_u32, brick_temp;
 	uint64_t n_pairs = 0, n_small_leaves = 0, n_bricks = 0; // of the last build
 	cudaEvent_t ev_brick[5] = {};                            // around k_brick_flat + k_brick_raster, the scans, k_brick_emit
@@ -866,7 +866,7 @@ void svo_builder_destroy(svo_builder *b) {
 	b->sort_scratch.release(s);
 	b->scan_scratch.state.release(s), b->scan_scratch.ticket.release(s);
 	b->rf_cnt01.release(s), b->rf_cnt2.release(s), b->rf_pre01.release(s), b->rf_pre2.release(s);
-	b->pairs_a.release(s), b->pairs_b.release(s), b->pair_idx.release(s), b->brick_u64.release(s), b->brick_scalars.release(s);
+	b->pairs_a.release(s), b->pairs_b.release(s), b->brick_u64.release(s), b->brick_scalars.release(s);
 	b->pair_flags.release(s), b->brick_first.release(s), b->small_leaf.release(s), b->brick_u32.release(s), b->brick_temp.release(s);
 	for (int i = 0; i <= SVO_PHASE_COUNT; ++i)
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
@@ -935,7 +935,6 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	SVO_TRY(b->pairs_a.reserve(n_pairs, s));
 	SVO_TRY(b->pairs_b.reserve(n_pairs, s));
 	SVO_TRY(b->pair_flags.reserve(n_pairs, s));
-	SVO_TRY(b->pair_idx.reserve(n_pairs + 1, s));
 	SVO_TRY(b->brick_first.reserve(n_pairs + 1, s));
 	if (nsb) SVO_CUDA_TRY(cudaMemcpyAsync(b->pairs_a.p, A, nsb * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
 	SVO_LAUNCH(brick_pair_grid(v), RASTER_BLOCK, 0, s, k_brick_pairs<true>, v->rp, v->n_large, (const LargeTri *)v->large.p,
@@ -944,11 +943,17 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	uint32_t pair_passes = 0;
 	SVO_TRY(radix_sort_u64(b->pairs_a.p, b->pairs_b.p, n_pairs, PAIR_SORT_BEGIN, 33 + 3 * (L - BRICK_LOG), b->sort_scratch, b->device, n_sm, s,
 	                       &pairs, &pair_passes, nullptr));
-	SVO_LAUNCH_INDEP(div_up(n_pairs, 256), 256, s, k_brick_head_flags, (const uint64_t *)pairs, n_pairs, b->pair_flags.p);
-	SVO_TRY((exclusive_scan<uint32_t, true>((const uint32_t *)b->pair_flags.p, b->pair_idx.p, n_pairs, b->scan_scratch, s)));
 	uint64_t *brick_code = pairs == b->pairs_a.p ? b->pairs_b.p : b->pairs_a.p; // (the other pair buffer is free after the sort)
-	SVO_LAUNCH_INDEP(div_up(n_pairs, 256), 256, s, k_brick_head_scatter, (const uint64_t *)pairs, (const uint32_t *)b->pair_flags.p,
-	                 (const uint64_t *)b->pair_idx.p, n_pairs, b->brick_first.p, brick_code);
+	uint64_t *d_nbricks = b->brick_scalars.p + 3;
+	{
+		const uint32_t tiles = div_up(n_pairs, SCAN_TILE);
+		SVO_TRY(b->scan_scratch.state.reserve((uint64_t)tiles + 1, s));
+		SVO_TRY(b->scan_scratch.ticket.reserve(1, s));
+		SVO_CUDA_TRY(cudaMemsetAsync(b->scan_scratch.state.p, 0, ((uint64_t)tiles + 1) * sizeof(uint64_t), s));
+		SVO_CUDA_TRY(cudaMemsetAsync(b->scan_scratch.ticket.p, 0, sizeof(uint32_t), s));
+		SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k_brick_heads, (const uint64_t *)pairs, n_pairs, b->brick_first.p, brick_code, d_nbricks,
+		           b->scan_scratch.state.p, b->scan_scratch.ticket.p);
+	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[2], s));
 
 	// per-brick arrays are sized for the upper bound "one brick per pair"; entries past the real number of bricks stay 0
@@ -958,7 +963,7 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	SVO_TRY(b->brick_temp.reserve(nbd * BRICK_CELLS, s)); // 2 KB per brick (fails with SVO_ERR_CUDA when the device cannot hold it: SVO_BUILD_PATH=0 sorts every fragment instead)
 	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_u32.p, 0, nbd * 4 * sizeof(uint32_t), s)); // the records (their counts: w)
 	BrickArgs a{};
-	a.pairs = pairs, a.brick_first = b->brick_first.p, a.brick_code = brick_code, a.n_bricks = b->pair_idx.p + n_pairs;
+	a.pairs = pairs, a.brick_first = b->brick_first.p, a.brick_code = brick_code, a.n_bricks = d_nbricks;
 	a.large = v->large.p, a.luv = v->large_uv.p, a.tv = v->scene->view.tex, a.rp = v->rp;
 	a.small_keys = B, a.small_leaf = b->small_leaf.p, a.n_small = d_nsl;
 	a.rec = reinterpret_cast<uint4 *>(b->brick_u32.p); // (16-byte aligned: the pool hands out 256-byte aligned blocks)
@@ -967,7 +972,7 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	a.temp = b->brick_temp.p;
 	a.keys_top = A;
 	for (uint32_t j = 0; j < 3; ++j) a.count[j] = b->counts.p + (L - j);
-	a.slow_list = b->pair_flags.p; // (the head flags are dead once the brick table exists: n_pairs words)
+	a.slow_list = b->pair_flags.p; // (n_pairs words: at most one entry per brick)
 	a.n_slow = reinterpret_cast<unsigned long long *>(b->brick_scalars.p + 2);
 	const uint32_t rgrid = div_up(nbd, (uint64_t)BRICK_WARPS * BRICK_BPW);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[0], s));
@@ -1062,7 +1067,7 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	SVO_CUDA_TRY(cudaMemcpyAsync(b->h_counts, b->counts.p, (L + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
 	b->n_bricks = 0;
 	if (b->path == 1) {
-		SVO_CUDA_TRY(cudaMemcpyAsync(&b->n_bricks, b->pair_idx.p + b->n_pairs, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+		SVO_CUDA_TRY(cudaMemcpyAsync(&b->n_bricks, b->brick_scalars.p + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
 		SVO_CUDA_TRY(cudaMemcpyAsync(&b->n_slow, b->brick_scalars.p + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
 	}
 	SVO_CUDA_TRY(cudaStreamSynchronize(s));
