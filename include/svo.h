@@ -187,6 +187,26 @@ SVO_API int svo_builder_build(svo_builder *b, void *stream);
  * This is the fused "emit + transfer": the kernel that produces the words stores them across NVLink. */
 SVO_API int svo_builder_prepare(svo_builder *b, void *stream);
 SVO_API int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *stream);
+/* Compact gather (multi-GPU, brick path).  A tree built from wall-sized triangles is mostly "flat" bricks -- 16 identical
+ * leaf blocks that their 16-byte record describes completely -- and pointer blocks that follow from the records and two
+ * ranks per brick.  Instead of storing the finished node words across NVLink (svo_builder_emit_to: 11 bytes per leaf
+ * cross the link), a prepared build can send
+ *   - the node words of the windows above depth L-2 and the leaf blocks of the rasterized (not flat) bricks, to their
+ *     final places in d_dst, and
+ *   - 32 bytes per brick (record, rank of its first depth L-1 / depth L-2 node) to d_tables
+ *     (svo_builder_compact_bytes(b) bytes, 16-byte aligned; this or a peer GPU's memory),
+ * and the GPU that owns the destination buffer writes everything else itself at local HBM speed:
+ * svo_expand_compact(device, d_tables, plan, d_dst) with the same d_dst (as seen from that GPU) and the four plan words
+ * svo_builder_emit_compact_to returned (host values: ship them with the sizes).  Together the two calls write exactly what
+ * svo_builder_emit_to(b, d_dst, pointer_bias_words, skip_root) writes; the blocks kept aside (svo_builder_root_words /
+ * svo_builder_top_words) are the same.  svo_builder_compact_bytes is 0 for a build that took the fragment-sort path
+ * (no compact form: use svo_builder_emit_to).  The caller orders svo_expand_compact after the arrival of the tables
+ * (stream order on one device; a collective or an IPC event between processes).
+ * Replaces nothing in the reference (single device); the gather is north_star's "subtrees gathered to GPU 0". */
+SVO_API uint64_t svo_builder_compact_bytes(const svo_builder *b);
+SVO_API int svo_builder_emit_compact_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *d_tables,
+                                        uint64_t plan[4], void *stream);
+SVO_API int svo_expand_compact(int device, const void *d_tables, const uint64_t plan[4], uint32_t *d_dst, void *stream);
 SVO_API int svo_builder_root_words(svo_builder *b, uint32_t out[8], void *stream);
 SVO_API int svo_builder_top_words(svo_builder *b, uint32_t out[72], uint32_t *n_blocks, void *stream);
 SVO_API uint32_t svo_builder_level(const svo_builder *b); /* OctreeBuilder::GetLevel */

@@ -52,6 +52,13 @@ class svo_mesh(C.Structure):
                 ("texcoords", C.c_void_p), ("texcoord_stride_bytes", C.c_uint32)]
 
 
+def expand_compact(lib, device: int, d_tables: int, plan, d_dst: int, stream=None):
+    """The other half of OctreeBuilder.EmitCompactTo, on the GPU that owns d_dst: flat bricks' blocks and all pointer
+    blocks of the two deepest windows, from the tables alone."""
+    arr = (C.c_uint64 * 4)(*[int(v) for v in plan])
+    lib.check(lib.dll.svo_expand_compact(device, d_tables, arr, d_dst, _stream_ptr(stream)))
+
+
 class svo_shard(C.Structure):
     _fields_ = [("shard_level", C.c_uint32), ("cube_index", C.c_uint32 * 3)]
 
@@ -82,6 +89,9 @@ SYMBOLS = [
     ("svo_builder_build", C.c_int, [_P, _P]),
     ("svo_builder_prepare", C.c_int, [_P, _P]),
     ("svo_builder_emit_to", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
+    ("svo_builder_compact_bytes", C.c_uint64, [_P]),
+    ("svo_builder_emit_compact_to", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P, C.POINTER(C.c_uint64), _P]),
+    ("svo_expand_compact", C.c_int, [C.c_int, _P, C.POINTER(C.c_uint64), _P, _P]),
     ("svo_builder_root_words", C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
     ("svo_builder_top_words", C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
     ("svo_builder_level", C.c_uint32, [_P]),
@@ -436,6 +446,18 @@ class OctreeBuilder:
         """Phase 2: write the node words into caller-provided device memory (possibly a peer GPU's).
         skip_root: False / True, or 2 to keep the root block and the depth-1 blocks aside (TopWords)."""
         self.lib.check(self.lib.dll.svo_builder_emit_to(self._h, d_dst, pointer_bias_words, int(skip_root), _stream_ptr(stream)))
+
+    def CompactBytes(self) -> int:
+        """Bytes of the per-brick tables of the compact gather; 0 when the build has no compact form (fragment-sort path)."""
+        return int(self.lib.dll.svo_builder_compact_bytes(self._h))
+
+    def EmitCompactTo(self, d_dst: int, pointer_bias_words: int, skip_root, d_tables: int, stream=None):
+        """Phase 2 in compact form (brick path): upper windows and the rasterized bricks' leaf blocks go to d_dst, 32 bytes
+        per brick to d_tables; returns the four plan words expand_compact() needs on the GPU that owns d_dst."""
+        plan = (C.c_uint64 * 4)()
+        self.lib.check(self.lib.dll.svo_builder_emit_compact_to(self._h, d_dst, pointer_bias_words, int(skip_root), d_tables, plan,
+                                                                _stream_ptr(stream)))
+        return [int(v) for v in plan]
 
     def TopWords(self, stream=None) -> np.ndarray:
         """The blocks kept aside by EmitTo(skip_root=1 or 2): uint32 [n_blocks, 8], the root block first."""

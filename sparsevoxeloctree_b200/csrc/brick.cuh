@@ -511,9 +511,16 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_keys(BrickArgs a) {
 // a brick's depth L-1 nodes (leaf words: a copy of the brick's part of temp) and of its depth L-2 nodes (pointers to
 // the former) are consecutive in their windows, at the brick's ranks.  Placement as in k_emit_octree: block g ->
 // words[(g - block_shift) * 8], a pointer to block c is (c - block_shift) * 8 + ptr_bias.  BRICK_EMIT_LANES lanes per brick.
+// Which part of the work one launch does (BrickEmit::parts): a multi-GPU gather sends only what cannot be regenerated
+// -- the leaf blocks of the rasterized bricks (BRICK_EMIT_COPY, stored over NVLink) and the 32 bytes of record + ranks per
+// brick -- and the GPU that owns the stitched buffer generates the flat bricks' blocks and all pointer blocks itself, at
+// local HBM speed, from the records alone (BRICK_EMIT_FLAT | BRICK_EMIT_PTRS: a.rec and a.rank[1..2] are all that is read).
+constexpr uint32_t BRICK_EMIT_COPY = 1u, BRICK_EMIT_FLAT = 2u, BRICK_EMIT_PTRS = 4u, BRICK_EMIT_ALL = 7u;
 struct BrickEmit {
 	uint64_t block_l1, block_l; // first block of the window that holds the children of the depth L-2 / of the depth L-1 nodes
 	uint32_t block_shift, ptr_bias;
+	uint64_t n_bricks;
+	uint32_t parts;
 };
 #ifndef SVO_BRICK_EMIT_LANES
 #define SVO_BRICK_EMIT_LANES 8 // lanes per brick (8 or 16)
@@ -524,10 +531,11 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEm
 	const uint64_t tid = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
 	const uint64_t brick = tid / BRICK_EMIT_LANES;
 	const uint32_t sub = threadIdx.x % BRICK_EMIT_LANES;
-	if (brick >= *a.n_bricks) return;
+	if (brick >= be.n_bricks) return;
 	const uint4 rec = a.rec[brick];
 	const uint32_t c1 = (uint32_t)(__popc(rec.x) + __popc(rec.y));
 	if (c1 == 0u) return;
+	if (!(be.parts & ((rec.w & REC_FLAT) ? (BRICK_EMIT_FLAT | BRICK_EMIT_PTRS) : (BRICK_EMIT_COPY | BRICK_EMIT_PTRS)))) return;
 	const uint64_t r1 = a.rank[1][brick];
 	const uint64_t g1 = be.block_l + r1 - be.block_shift; // where the brick's first leaf block goes
 	uint4 *dst = reinterpret_cast<uint4 *>(words + g1 * 8);
@@ -537,14 +545,16 @@ __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEm
 		uint4 v;
 		v.x = (((s0 + 0u) >> axis) & 1u) == par ? leaf : 0u, v.y = (((s0 + 1u) >> axis) & 1u) == par ? leaf : 0u;
 		v.z = (((s0 + 2u) >> axis) & 1u) == par ? leaf : 0u, v.w = (((s0 + 3u) >> axis) & 1u) == par ? leaf : 0u;
+		if (be.parts & BRICK_EMIT_FLAT) {
 #pragma unroll
-		for (uint32_t i = 0; i < 32u; i += BRICK_EMIT_LANES) dst[i + sub] = v;
-	} else {
+			for (uint32_t i = 0; i < 32u; i += BRICK_EMIT_LANES) dst[i + sub] = v;
+		}
+	} else if (be.parts & BRICK_EMIT_COPY) {
 		const uint4 *src = reinterpret_cast<const uint4 *>(a.temp + brick * BRICK_CELLS);
 		for (uint32_t i = sub; i < 2u * c1; i += BRICK_EMIT_LANES) dst[i] = src[i]; // 16-byte pieces, consecutive lanes consecutive pieces
 	}
 	const uint32_t n2 = rec.z & 0xffu;
-	if (sub < 8u && ((n2 >> sub) & 1u)) { // a depth L-2 node: one block of pointers to its children's blocks
+	if ((be.parts & BRICK_EMIT_PTRS) && sub < 8u && ((n2 >> sub) & 1u)) { // a depth L-2 node: one block of pointers to its children's blocks
 		uint32_t c = (uint32_t)g1 + brick_node_rank(rec.x, rec.y, 8u * sub);
 		uint32_t w[8];
 #pragma unroll

@@ -1098,7 +1098,8 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 // block_index*8 + pointer_bias_words.  skip_root = 1 (multi-GPU stitch): blocks 1.. go to d_dst[0..) and the root
 // block to the builder's root scratch; child pointers are (block_index-1)*8 + pointer_bias_words, i.e. they are
 // already valid in a buffer where d_dst sits at word offset pointer_bias_words.  d_dst may be peer memory.
-static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_root, cudaStream_t s) {
+static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_root, cudaStream_t s, uint32_t brick_parts = BRICK_EMIT_ALL,
+                     uint64_t *plan = nullptr) {
 	EmitParams ep = b->ep;
 	// skip_root: 0 = whole tree; 1 = the root block is kept aside; 2 = the root block and the depth-1 blocks are
 	ep.block_shift = skip_root == 0 ? 0u : (skip_root == 1 ? 1u : 1u + (uint32_t)b->h_counts[1]);
@@ -1118,9 +1119,11 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 		else
 			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_direct, ep, d_dst);
 		if (b->path == 1) {
-			BrickEmit be{ep.block_base[b->level - 1], ep.block_base[b->level], ep.block_shift, ep.ptr_bias};
+			BrickEmit be{ep.block_base[b->level - 1], ep.block_base[b->level], ep.block_shift, ep.ptr_bias, b->n_bricks, brick_parts};
+			if (plan) plan[0] = be.n_bricks, plan[1] = be.block_l1, plan[2] = be.block_l, plan[3] = (uint64_t)be.block_shift | ((uint64_t)be.ptr_bias << 32);
 			SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[3], s));
-			SVO_LAUNCH_INDEP(div_up(b->brick_args.n_bound * BRICK_EMIT_LANES, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_emit, b->brick_args, be, d_dst);
+			if (b->n_bricks)
+				SVO_LAUNCH_INDEP(div_up(b->n_bricks * BRICK_EMIT_LANES, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_emit, b->brick_args, be, d_dst);
 			SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[4], s));
 		}
 	}
@@ -1140,6 +1143,53 @@ int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_w
 	SVO_TRY(emit_into(b, d_dst, pointer_bias_words, skip_root, (cudaStream_t)stream));
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], (cudaStream_t)stream)); // svo_builder_last_ms covers prepare + emit_to as well
 	b->emitted = true;
+	return SVO_OK;
+}
+
+// ---- compact gather (multi-GPU, brick path): see svo.h ----
+uint64_t svo_builder_compact_bytes(const svo_builder *b) {
+	return (b && b->prepared && b->path == 1 && b->h_counts[b->level]) ? b->n_bricks * 32ull : 0;
+}
+
+int svo_builder_emit_compact_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *d_tables, uint64_t plan[4],
+                                void *stream) {
+	if (!b || !d_dst || !d_tables || !plan) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_compact_to: null argument");
+	if (!b->prepared) return fail(SVO_ERR_NOT_READY, "svo_builder_emit_compact_to: prepare first");
+	if (!svo_builder_compact_bytes(b)) return fail(SVO_ERR_UNSUPPORTED, "svo_builder_emit_compact_to: the build did not take the brick path (use svo_builder_emit_to)");
+	if (skip_root < 0 || skip_root > 2 || (skip_root == 2 && b->level < 3))
+		return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_compact_to: skip_root is 0, 1 or 2 (2 needs level >= 3)");
+	if ((uint64_t)pointer_bias_words + b->range_bytes / 4 >= (1ull << 30))
+		return fail(SVO_ERR_CAPACITY, "biased child pointers would exceed 30 bits (octree.glsl:110)");
+	DeviceGuard guard(b->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	b->last_stream = s;
+	// upper windows + the leaf blocks of the rasterized bricks go to their final places; records and ranks to the tables
+	SVO_TRY(emit_into(b, d_dst, pointer_bias_words, skip_root, s, BRICK_EMIT_COPY, plan));
+	const uint64_t n = b->n_bricks;
+	char *t = static_cast<char *>(d_tables);
+	SVO_CUDA_TRY(cudaMemcpyAsync(t, b->brick_args.rec, n * 16, cudaMemcpyDefault, s));
+	SVO_CUDA_TRY(cudaMemcpyAsync(t + n * 16, b->brick_args.rank[1], n * 8, cudaMemcpyDefault, s));
+	SVO_CUDA_TRY(cudaMemcpyAsync(t + n * 24, b->brick_args.rank[2], n * 8, cudaMemcpyDefault, s));
+	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], s));
+	b->emitted = true;
+	return SVO_OK;
+}
+
+int svo_expand_compact(int device, const void *d_tables, const uint64_t plan[4], uint32_t *d_dst, void *stream) {
+	if (!d_tables || !plan || !d_dst) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_expand_compact: null argument");
+	const uint64_t n = plan[0];
+	if (!n) return SVO_OK;
+	if (reinterpret_cast<uintptr_t>(d_tables) % 16) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_expand_compact: the tables must be 16-byte aligned");
+	DeviceGuard guard(device);
+	const char *t = static_cast<const char *>(d_tables);
+	BrickArgs a{};
+	a.rec = reinterpret_cast<uint4 *>(const_cast<char *>(t));
+	a.rank[1] = reinterpret_cast<const uint64_t *>(t + n * 16);
+	a.rank[2] = reinterpret_cast<const uint64_t *>(t + n * 24);
+	BrickEmit be{plan[1], plan[2], (uint32_t)plan[3], (uint32_t)(plan[3] >> 32), n, BRICK_EMIT_FLAT | BRICK_EMIT_PTRS};
+	cudaStream_t s = (cudaStream_t)stream;
+	SVO_LAUNCH_INDEP(div_up(n * BRICK_EMIT_LANES, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_emit, a, be, d_dst);
+	SVO_CUDA_TRY(cudaGetLastError());
 	return SVO_OK;
 }
 
@@ -1210,7 +1260,6 @@ int svo_builder_last_ms(svo_builder *b, float *phase_ms, uint32_t *sort_passes) 
 }
 
 // ------------------------------------------------------------------------------------------------------
-static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_root, cudaStream_t s);
 int svo_builder_export_fd(svo_builder *b, int *fd, uint64_t *alloc_size, const uint32_t **d_ptr, void *stream) {
 	if (!b || !fd || !alloc_size) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_export_fd: null argument");
 	if (!b->prepared && !b->built) return fail(SVO_ERR_NOT_READY, "svo_builder_export_fd: prepare or build first");

@@ -198,6 +198,13 @@ class ShardedSVO:
         # over NVLink itself (no staging, but the kernel holds its SM slots for the duration of the transfer)
         # (2 B200, C4, one part: store 4.83 ms, copy 5.31 ms)
         self.push_mode = os.environ.get("SVO_PUSH", "store")
+        # compact gather (slab mode, parts built on the brick path): SVO_COMPACT=0 sends finished node words instead
+        self.compact = os.environ.get("SVO_COMPACT", "1") != "0"
+        self.stage_base, self.stage_cap = 0, 0
+        if self.slab:
+            ar = ShardedSVO._STAGE_ARENA.get((self.device, self.world))
+            if ar:
+                self.stage_base, self.stage_cap = (ar["ptr"] if self.rank == 0 else ar["peer"]), ar["cap"]
         self.pipelined = True  # overlap the NVLink push of one octant with the build of the next (steady state)
 
     # -- rank 0 owns a grow-only arena for the stitched tree (like the reference's up-front octree buffer).
@@ -206,6 +213,7 @@ class ShardedSVO:
     #    is needed unless the arena really has to grow.
     _ARENA = {}  # device -> dict(ptr, cap, peer)
     _STAGE = {}  # (device, part) -> (ptr, capacity in words)
+    _STAGE_ARENA = {}  # (device, world) -> dict(ptr, cap, peer): rank 0's staging area of the compact gather
     _PUSH_STREAM = {}  # device -> torch stream
 
     def _ensure_final(self, words: int):
@@ -228,61 +236,112 @@ class ShardedSVO:
             ar["cap"] = cap
         self.final, self.final_cap, self.peer_final = (ar["ptr"] if self.rank == 0 else None), ar["cap"], ar["peer"]
 
+    def _ensure_stage(self, nbytes: int):
+        """Rank 0's staging area for the per-brick tables of the compact gather (32 bytes per brick of every other rank),
+        mapped into the other ranks through CUDA IPC; cached and grow-only like the arena.  Collective when it grows."""
+        ar = ShardedSVO._STAGE_ARENA.setdefault((self.device, self.world), dict(ptr=0, cap=0, peer=0))
+        if nbytes > ar["cap"]:
+            cap = max(nbytes + nbytes // 4, 1 << 20)
+            if self.rank == 0:
+                if ar["ptr"]:
+                    self.lib.free(ar["ptr"], self.device)
+                ar["ptr"] = self.lib.malloc(cap, self.device)
+            handle = [self.lib.ipc_export(ar["ptr"], self.device) if self.rank == 0 else None]
+            self.dist.broadcast_object_list(handle, 0)
+            if self.rank != 0:
+                if ar["peer"]:
+                    self.lib.ipc_close(ar["peer"], self.device)
+                ar["peer"] = self.lib.ipc_open(handle[0], self.device)
+            ar["cap"] = cap
+        self.stage_base, self.stage_cap = (ar["ptr"] if self.rank == 0 else ar["peer"]), ar["cap"]
+
     def _step_slab(self, stream):
         """Slab mode: every rank builds its slab as n_sub parts; as soon as a part's sizes are known (one small
-        all_gather) its emit kernel stores the node words, child pointers already final, into rank 0's buffer over
-        NVLink on a second stream -- while the rank voxelizes and sorts its next part.  Layout: 72-word header (root
-        block + 8 depth-1 blocks, merged by rank 0 from the parts' top blocks), then the bodies part by part."""
+        all_gather) it is sent into rank 0's buffer over NVLink on a second stream -- while the rank voxelizes and sorts
+        its next part.  Layout: 72-word header (root block + 8 depth-1 blocks, merged by rank 0 from the parts' top
+        blocks), then the bodies part by part.
+
+        What crosses the link: a part built on the brick path goes in COMPACT form (svo_builder_emit_compact_to) -- the
+        windows above depth L-2 and the leaf blocks of the rasterized bricks to their final places, 32 bytes per brick
+        (record + two ranks) to a staging area on rank 0 -- and rank 0 generates the flat bricks' blocks and all pointer
+        blocks of the two deepest windows itself (svo_expand_compact) once the tables have arrived, at local HBM speed.
+        A part built on the fragment-sort path stores its finished node words (svo_builder_emit_to)."""
         torch, dist = self.torch, self.dist
         if self.push_stream is None:
             self.push_stream = ShardedSVO._PUSH_STREAM.setdefault(self.device, torch.cuda.Stream(self.tdev))
-        mine = torch.zeros(1, dtype=torch.int64, device=self.tdev)
+        mine = torch.zeros(1, dtype=torch.int64, device=self.tdev)  # body words | 256-byte units of tables << 32
         gathered = torch.zeros(self.world, dtype=torch.int64, device=self.tdev)
-        run, placed, overflow = HEADER_WORDS, [], self.final_cap == 0
-        for v, b in zip(self.vox, self.builders):
+        run, stage_run, placed = HEADER_WORDS, 0, []
+        overflow = self.final_cap == 0
+        plans = np.zeros((self.n_sub, 6), dtype=np.int64)  # per part: the four plan words, staging offset, base word
+        part_bases = []
+        for k, (v, b) in enumerate(zip(self.vox, self.builders)):
             v.CmdVoxelize(stream)
             b.Prepare(stream)  # ends with the size read-back: the stream is idle afterwards
             body = b.GetOctreeRange() // 4 - 8 * (1 + b.GetLevelCounts()[1]) if b.GetLeafCount() else 0
-            mine.fill_(body)
+            tables = (b.CompactBytes() + 255) // 256 * 256 if (self.compact and self.rank != 0 and body) else 0
+            mine.fill_(body | (tables // 256) << 32)
             dist.all_gather_into_tensor(gathered, mine)
-            bodies = [int(x) for x in gathered.cpu().tolist()]
+            g = [int(x) for x in gathered.cpu().tolist()]
+            bodies, stages = [x & 0xFFFFFFFF for x in g], [(x >> 32) * 256 for x in g]
             base = run + sum(bodies[: self.rank])
+            stage_off = stage_run + sum(stages[: self.rank])
+            part_bases.append([run + sum(bodies[:r]) for r in range(self.world)])
             run += sum(bodies)
+            stage_run += sum(stages)
             if run >= 1 << 30:
                 raise OverflowError("stitched octree needs >= 2^30 words: 30-bit child pointers cannot address it")
-            overflow = overflow or run > self.final_cap  # (the same on every rank: all see the same sizes)
+            # (the same on every rank: all see the same sizes)
+            overflow = overflow or run > self.final_cap or stage_run > self.stage_cap
             if body:
-                placed.append((b, base, body))
+                placed.append((k, b, base, body, stage_off if tables else None))
                 if not overflow:
-                    self._push_part(b, base, body, stream)
+                    plans[k] = self._push_part(b, base, body, stream, stage_off if tables else None)
         if overflow:  # first step, or the tree outgrew the arena: size it now and emit everything (again)
             self.push_stream.synchronize()
             self._ensure_final(run)
-            for b, base, body in placed:
-                self._push_part(b, base, body, stream)
-        tops = [b.TopWords(self.push_stream) for b, _, _ in placed]  # (waits for this rank's stores)
-        local = torch.from_numpy(merge_top_blocks(tops).astype(np.int64)).to(self.tdev)
-        headers = torch.zeros(self.world * HEADER_WORDS, dtype=torch.int64, device=self.tdev)
+            if stage_run > self.stage_cap:
+                self._ensure_stage(stage_run)
+            for k, b, base, body, stage_off in placed:
+                plans[k] = self._push_part(b, base, body, stream, stage_off)
+        tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]  # (waits for this rank's stores and copies)
+        width = HEADER_WORDS + 6 * self.n_sub
+        local = torch.from_numpy(np.concatenate([merge_top_blocks(tops).astype(np.int64), plans.reshape(-1)])).to(self.tdev)
+        headers = torch.zeros(self.world * width, dtype=torch.int64, device=self.tdev)
         dist.all_gather_into_tensor(headers, local)
         self.total_words = run
         if self.rank == 0:
-            header = merge_headers(headers.cpu().numpy())
+            # every rank entered this all_gather after its own stores and copies had completed: the tables are here
+            h = headers.cpu().numpy().reshape(self.world, width)
+            for r in range(1, self.world):
+                for k in range(self.n_sub):
+                    plan = h[r, HEADER_WORDS + 6 * k: HEADER_WORDS + 6 * k + 6]
+                    if plan[0]:
+                        self.api.expand_compact(self.lib, self.device, self.stage_base + int(plan[4]), [int(x) for x in plan[:4]],
+                                                self.final + int(plan[5]) * 4, stream)
+            header = merge_headers(h[:, :HEADER_WORDS])
             self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, header.ctypes.data, header.nbytes, 0))
         torch.cuda.synchronize(self.tdev)
         dist.barrier()  # remote stores into rank 0's buffer are complete
         return run * 4
 
-    def _push_part(self, b, base, body, stream):
-        """Node words of a prepared part -> words [base, base + body) of rank 0's buffer, child pointers final."""
+    def _push_part(self, b, base, body, stream, stage_off=None):
+        """Node words of a prepared part -> words [base, base + body) of rank 0's buffer, child pointers final.
+        stage_off: the part goes in compact form, its tables to that offset of rank 0's staging area.  Returns the part's
+        six plan words (zeros when nothing is left for rank 0 to expand)."""
         torch = self.torch
+        none = np.zeros(6, dtype=np.int64)
         if self.rank == 0:
             b.EmitTo(self.final + base * 4, base, 2, stream)  # local: straight into the stitched buffer
             self.push_stream.wait_stream(stream if stream is not None else torch.cuda.current_stream(self.tdev))
-            return
+            return none
         dst = self.peer_final + base * 4
+        if stage_off is not None:
+            plan = b.EmitCompactTo(dst, base, 2, self.stage_base + stage_off, self.push_stream)
+            return np.array(plan + [stage_off, base], dtype=np.uint64).astype(np.int64)
         if self.push_mode == "store":
             b.EmitTo(dst, base, 2, self.push_stream)
-            return
+            return none
         key = (self.device, self.builders.index(b))
         buf, cap = ShardedSVO._STAGE.get(key, (0, 0))
         if cap < body:
@@ -295,6 +354,7 @@ class ShardedSVO:
         b.EmitTo(buf, base, 2, stream)  # fast local emit on the build stream ...
         self.push_stream.wait_stream(stream if stream is not None else torch.cuda.current_stream(self.tdev))
         self.lib.check(self.lib.dll.svo_memcpy_d2d(self.device, dst, buf, body * 4, int(self.push_stream.cuda_stream)))  # ... DMA over NVLink
+        return none
 
     def step(self, stream=None):
         """One sharded build: local subtrees, size exchange, fused rebase + gather, root block on rank 0."""

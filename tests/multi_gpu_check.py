@@ -16,7 +16,8 @@ def main():
     lr = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    mesh = scenes.random_soup(800, 41, 0.01, 1.2)
+    # --room: walls parallel to the grid (flat bricks), what the compact gather of the slab mode is for
+    mesh = scenes.living_room_like(n_boxes=8, n_small=2000, level=9) if "--room" in sys.argv else scenes.random_soup(800, 41, 0.01, 1.2)
     level, mode = 9, api.CONSERVATIVE_EXACT
     sh = sharded.ShardedSVO(torch, dist, mesh, level, mode, lr, use_ipc="--no-ipc" not in sys.argv)
     for _ in range(2):

@@ -109,9 +109,11 @@ def check_against_oracle(lib, mesh, level, mode, shard=None, device=0, stream=No
     return info
 
 
-def depth2_parts_check(lib, world, n_sub, mesh, level, mode=api.CONSERVATIVE_EXACT):
+def depth2_parts_check(lib, world, n_sub, mesh, level, mode=api.CONSERVATIVE_EXACT, compact=False):
     """Builds the scene as world * n_sub separately built parts (sharded.sub_windows) assembled in one arena the way the
-    pipelined multi-GPU path does, and compares with the whole-grid build (canonical, colours included)."""
+    pipelined multi-GPU path does, and compares with the whole-grid build (canonical, colours included).
+    compact: parts that took the brick path go through the compact gather (EmitCompactTo into a staging area, then
+    expand_compact once every part has been sent), as the slab mode does between GPUs; returns how many parts did."""
     from sparsevoxeloctree_b200 import sharded
     scene = api.Scene.Create(mesh, lib=lib)
     parts, bodies, tops = [], [], []
@@ -126,11 +128,20 @@ def depth2_parts_check(lib, world, n_sub, mesh, level, mode=api.CONSERVATIVE_EXA
             bodies.append(b.GetOctreeRange() // 4 - 8 * (1 + counts[1]) if counts else 0)
     total = sharded.HEADER_WORDS + sum(bodies)
     arena = lib.malloc(total * 4)
+    stage_bytes = [(b.CompactBytes() + 255) // 256 * 256 if compact else 0 for _, b in parts]
+    stage = lib.malloc(max(sum(stage_bytes), 256))
+    pending = []
     for k, (v, b) in enumerate(parts):
         base = sharded.HEADER_WORDS + sum(bodies[:k])
         if b.GetLeafCount():
-            b.EmitTo(arena + base * 4, base, 2)
+            if stage_bytes[k]:
+                tables = stage + sum(stage_bytes[:k])
+                pending.append((tables, b.EmitCompactTo(arena + base * 4, base, 2, tables), arena + base * 4))
+            else:
+                b.EmitTo(arena + base * 4, base, 2)
             tops.append(b.TopWords())
+    for tables, plan, dst in pending:
+        api.expand_compact(lib, 0, tables, plan, dst)
     header = sharded.merge_top_blocks(tops)
     lib.check(lib.dll.svo_memcpy_h2d(0, arena, header.ctypes.data, header.nbytes, 0))
     lib.check(lib.dll.svo_stream_synchronize(0, 0))
@@ -139,5 +150,7 @@ def depth2_parts_check(lib, world, n_sub, mesh, level, mode=api.CONSERVATIVE_EXA
     assert_same_tree(stitched, builder.octree_to_host(), level)
     assert sum(v.GetVoxelFragmentCount() for v, _ in parts) == vox.GetVoxelFragmentCount()
     lib.free(arena)
+    lib.free(stage)
     for v, b in parts:
         b.Destroy(), v.Destroy()
+    return len(pending)

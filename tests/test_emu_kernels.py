@@ -237,3 +237,16 @@ def test_depth2_parts_assemble_the_whole_tree(emu, world, n_sub):
     """Pipelined slab mode on one (emulated) device: every rank's slab cut into parts at depth-2 cell borders, each part
     built on its own and emitted with skip_root = 2 behind a 72-word header; the merged header + bodies = the whole tree."""
     _depth2_parts_check(emu, world, n_sub, scenes.random_soup(250, 23, 0.02, 0.9), 6)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_compact_gather_assembles_the_whole_tree(emu, world):
+    """The compact gather of the slab mode (svo_builder_emit_compact_to + svo_expand_compact) on one emulated device:
+    every slab built on the brick path, upper windows and rasterized bricks' leaf blocks sent to their places, 32 bytes
+    per brick to a staging area, flat bricks and pointer blocks generated from the staged tables afterwards."""
+    emu.dll.svo_debug_set_build_path(1)
+    try:
+        n = _depth2_parts_check(emu, world, 1, scenes.living_room_like(n_boxes=2, n_small=30, level=6), 6, compact=True)
+        assert n >= world // 2
+    finally:
+        emu.dll.svo_debug_set_build_path(-1)

@@ -285,10 +285,11 @@ def test_two_rank_nccl_stitch(lib):
     if lib.dll.svo_device_count() < 2:
         pytest.skip("needs 2 GPUs (covered on CPU by tests/test_sharded_gloo.py and on 1 GPU by the virtual-shard test)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for extra in ([], ["--no-ipc"]):
+    # (--room with the brick path forced: the slabs cross in compact form, svo_builder_emit_compact_to + svo_expand_compact)
+    for extra, env in (([], {}), (["--no-ipc"], {}), (["--room"], {"SVO_BUILD_PATH": "1"})):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                "--master-port", "29611", os.path.join(root, "tests", "multi_gpu_check.py")] + extra
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, **env})
         assert r.returncode == 0 and "STITCH_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -424,3 +425,18 @@ def test_depth2_parts_assemble_the_whole_tree_gpu(lib, world, n_sub):
     with skip_root = 2 behind the 72-word header; merged header + bodies must equal the whole-grid tree."""
     from tests.parity import depth2_parts_check
     depth2_parts_check(lib, world, n_sub, scenes.random_soup(700, 53, 0.01, 1.2), 9)
+
+
+@pytest.mark.parametrize("world,n_sub", [(2, 1), (8, 1), (4, 2)])
+def test_compact_gather_assembles_the_whole_tree_gpu(lib, world, n_sub):
+    """The compact gather (svo_builder_emit_compact_to + svo_expand_compact) on ONE device, at a size where most bricks
+    are flat: slabs built on the brick path send their upper windows, the rasterized bricks' leaf blocks and 32 bytes per
+    brick; the flat bricks' blocks and all pointer blocks are generated from the staged tables.  Must equal the
+    whole-grid tree word for word after canonicalisation."""
+    from tests.parity import depth2_parts_check
+    lib.dll.svo_debug_set_build_path(1)
+    try:
+        n = depth2_parts_check(lib, world, n_sub, scenes.living_room_like(n_boxes=8, n_small=2000, level=9), 9, compact=True)
+        assert n >= world * n_sub // 2
+    finally:
+        lib.dll.svo_debug_set_build_path(-1)
