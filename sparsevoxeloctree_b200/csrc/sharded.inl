@@ -6,7 +6,9 @@
 // the collectives: with all devices in one address space the sizes are exchanged in host memory.
 //   levels <= 13 ("slab" mode): device k builds the voxel window made of its octants in global coordinates
 //       (svo_voxelizer_create_windowed + svo_builder_prepare), then emits its node words, child pointers already final,
-//       straight into the stitched buffer on devices[0] over NVLink peer access (svo_builder_emit_to, skip_root).
+//       straight into the stitched buffer on devices[0] over NVLink peer access (svo_builder_emit_to, skip_root).  A slab
+//       built on the brick path crosses in compact form (svo_builder_emit_compact_to: upper windows, the rasterized
+//       bricks' leaf blocks and 32 bytes per brick) and devices[0] generates the rest itself (svo_expand_compact).
 //   level 14 ("octant" mode; 42 Morton bits + 24 colour bits do not fit a 64-bit fragment): one cube-local level-13
 //       build per octant, round-robin over the devices; svo_builder_rebase_copy adds the subtree's base to every child
 //       pointer while storing into the stitched buffer.
@@ -23,6 +25,7 @@ struct ShardPart {
 	svo_builder *builder = nullptr;
 	uint64_t body_words = 0; // node words this part contributes behind the root block
 	uint64_t base_words = 0; // where they go in the stitched buffer
+	uint64_t compact_bytes = 0, stage_off = 0, plan[4] = {}; // slab mode, brick path, not on devices[0]: the compact gather
 	int rc = SVO_OK;
 	char err[256] = "";
 };
@@ -42,6 +45,8 @@ struct svo_sharded {
 	bool slab = false;
 	uint32_t *octree = nullptr; // on devices[0] (cudaMalloc: peers write into it)
 	uint64_t capacity_words = 0, total_words = 0;
+	char *stage = nullptr; // on devices[0]: the per-brick tables of the other devices' slabs (compact gather)
+	uint64_t stage_capacity = 0;
 	uint64_t n_frag = 0, n_leaf = 0;
 	float last_ms = 0.f;
 };
@@ -95,8 +100,21 @@ static int sharded_run(svo_sharded *sh) {
 	}
 	if (run >= (1ull << 30)) return fail(SVO_ERR_CAPACITY, "stitched octree needs >= 2^30 words: 30-bit child pointers cannot address it");
 	sh->total_words = run;
+	uint64_t stage_run = 0;
+	for (size_t k = 0; k < sh->parts.size(); ++k)
+		for (ShardPart &p : sh->parts[k]) {
+			p.compact_bytes = (sh->slab && k != 0 && p.body_words) ? (svo_builder_compact_bytes(p.builder) + 255) / 256 * 256 : 0;
+			p.stage_off = stage_run;
+			stage_run += p.compact_bytes;
+		}
 	{
 		DeviceGuard guard(sh->devices[0]);
+		if (stage_run > sh->stage_capacity) {
+			if (sh->stage) cudaFree(sh->stage);
+			sh->stage = nullptr;
+			sh->stage_capacity = stage_run + stage_run / 4;
+			SVO_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&sh->stage), sh->stage_capacity));
+		}
 		if (run > sh->capacity_words) {
 			if (sh->octree) cudaFree(sh->octree);
 			sh->octree = nullptr;
@@ -110,8 +128,10 @@ static int sharded_run(svo_sharded *sh) {
 		for (ShardPart &p : sh->parts[k]) {
 			if (!p.body_words) continue;
 			void *s = sh->streams[k];
-			const int rc = sh->slab ? svo_builder_emit_to(p.builder, dst + p.base_words, (uint32_t)p.base_words, 1, s)
-			                        : svo_builder_rebase_copy(p.builder, dst, p.base_words, (uint32_t)p.base_words, s);
+			const int rc = !sh->slab          ? svo_builder_rebase_copy(p.builder, dst, p.base_words, (uint32_t)p.base_words, s)
+			               : p.compact_bytes ? svo_builder_emit_compact_to(p.builder, dst + p.base_words, (uint32_t)p.base_words, 1,
+			                                                               sh->stage + p.stage_off, p.plan, s)
+			                                 : svo_builder_emit_to(p.builder, dst + p.base_words, (uint32_t)p.base_words, 1, s);
 			if (rc != SVO_OK) {
 				part_fail(p, rc);
 				return;
@@ -119,6 +139,11 @@ static int sharded_run(svo_sharded *sh) {
 		}
 		if (svo_stream_synchronize(sh->devices[k], sh->streams[k]) != SVO_OK && !sh->parts[k].empty()) part_fail(sh->parts[k][0], SVO_ERR_CUDA);
 	}));
+	// compact gather: the tables have arrived (every stream was synchronised above); devices[0] writes the flat bricks'
+	// leaf blocks and the pointer blocks of the two deepest windows of the other devices' slabs
+	for (ShardPart *p : order)
+		if (p->compact_bytes) SVO_TRY(svo_expand_compact(sh->devices[0], sh->stage + p->stage_off, p->plan, dst + p->base_words, sh->streams[0]));
+	SVO_TRY(svo_stream_synchronize(sh->devices[0], sh->streams[0]));
 	// the root block: slab mode merges the parts' root blocks (disjoint octants: a sum); octant mode points at the subtrees
 	uint32_t root[8] = {};
 	for (ShardPart *p : order) {
@@ -155,9 +180,10 @@ void svo_sharded_destroy(svo_sharded *sh) {
 			cudaStreamDestroy(sh->streams[k]);
 		}
 	}
-	if (sh->octree) {
+	if (sh->octree || sh->stage) {
 		DeviceGuard guard(sh->devices[0]);
-		cudaFree(sh->octree);
+		if (sh->octree) cudaFree(sh->octree);
+		if (sh->stage) cudaFree(sh->stage);
 	}
 	delete sh;
 }

@@ -232,6 +232,22 @@ def test_build_sharded_c_abi_logic(emu, n_dev):
     sh.Destroy()
 
 
+def test_build_sharded_c_abi_compact_gather(emu):
+    """svo_build_sharded with the slabs on the brick path: the slabs of devices 1.. cross in compact form."""
+    from tests.parity import assert_same_tree
+    mesh = scenes.living_room_like(n_boxes=2, n_small=30, level=6)
+    emu.dll.svo_debug_set_build_path(1)
+    try:
+        sh = api.ShardedBuild.Create(mesh, 6, api.CONSERVATIVE_EXACT, devices=[0] * 4, lib=emu)
+        _, vox, builder = api.build_svo(mesh, 6, api.CONSERVATIVE_EXACT, lib=emu)
+        assert builder.BuildPath() == 1
+    finally:
+        emu.dll.svo_debug_set_build_path(-1)
+    assert sh.GetOctreeRange() == builder.GetOctreeRange() and sh.GetLeafCount() == builder.GetLeafCount()
+    assert_same_tree(sh.octree_to_host(), builder.octree_to_host(), 6)
+    sh.Destroy()
+
+
 @pytest.mark.parametrize("world,n_sub", [(2, 2), (8, 2), (4, 4)])
 def test_depth2_parts_assemble_the_whole_tree(emu, world, n_sub):
     """Pipelined slab mode on one (emulated) device: every rank's slab cut into parts at depth-2 cell borders, each part

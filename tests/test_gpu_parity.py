@@ -405,6 +405,26 @@ def test_build_sharded_c_abi_on_one_device(lib, n_dev):
     sh.Destroy()
 
 
+def test_build_sharded_c_abi_compact_gather_gpu(lib):
+    """svo_build_sharded on a scene of wall-sized triangles, brick path forced: the slabs of 'devices' 1.. cross in compact
+    form (svo_builder_emit_compact_to) and are completed on devices[0] (svo_expand_compact)."""
+    from tests.parity import assert_same_tree
+    mesh = scenes.living_room_like(n_boxes=8, n_small=2000, level=9)
+    level, mode = 9, api.CONSERVATIVE_EXACT
+    lib.dll.svo_debug_set_build_path(1)
+    try:
+        sh = api.ShardedBuild.Create(mesh, level, mode, devices=[0] * 8, lib=lib)
+        _, vox, builder = api.build_svo(mesh, level, mode, lib=lib)
+        assert builder.BuildPath() == 1
+        assert sh.GetOctreeRange() == builder.GetOctreeRange() and sh.GetLeafCount() == builder.GetLeafCount()
+        assert_same_tree(sh.octree_to_host(), builder.octree_to_host(), level)
+        sh.Rebuild()
+        assert_same_tree(sh.octree_to_host(), builder.octree_to_host(), level)
+        sh.Destroy()
+    finally:
+        lib.dll.svo_debug_set_build_path(-1)
+
+
 def test_build_sharded_c_abi_level14(lib):
     """Level 14 through svo_build_sharded: 8 cube-local level-13 octant builds, rebased into one buffer."""
     from oracle import oracle
