@@ -523,51 +523,66 @@ struct BrickEmit {
 	uint32_t parts;
 };
 #ifndef SVO_BRICK_EMIT_LANES
-#define SVO_BRICK_EMIT_LANES 8 // lanes per brick (8 or 16)
+#define SVO_BRICK_EMIT_LANES 4 // lanes per brick
 #endif
 constexpr uint32_t BRICK_EMIT_LANES = SVO_BRICK_EMIT_LANES;
-static_assert(BRICK_EMIT_LANES == 8 || BRICK_EMIT_LANES == 16, "an even number of lanes >= the 8 depth L-2 nodes of a brick");
+static_assert(BRICK_EMIT_LANES == 1 || BRICK_EMIT_LANES == 2 || BRICK_EMIT_LANES == 4 || BRICK_EMIT_LANES == 8 || BRICK_EMIT_LANES == 16, "a power of two: lanes share the brick's 16..64 leaf blocks and 8 pointer blocks");
+// one 8-word block with a single 256-bit store (sm_100: STG.256); p is 32-byte aligned
+SVO_DEV void store_block(uint32_t *p, const uint4 &lo, const uint4 &hi) {
+#if defined(__CUDA_ARCH__) && !defined(SVO_EMIT_NO_V8)
+#ifndef SVO_EMIT_ST
+#define SVO_EMIT_ST "st.global.v8.b32"
+#endif
+	asm volatile(SVO_EMIT_ST " [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
+	             "r"(hi.y), "r"(hi.z), "r"(hi.w)
+	             : "memory");
+#else
+	reinterpret_cast<uint4 *>(p)[0] = lo, reinterpret_cast<uint4 *>(p)[1] = hi;
+#endif
+}
 __global__ void __launch_bounds__(BRICK_BLOCK) k_brick_emit(BrickArgs a, BrickEmit be, uint32_t *__restrict__ words) {
 	const uint64_t tid = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
 	const uint64_t brick = tid / BRICK_EMIT_LANES;
 	const uint32_t sub = threadIdx.x % BRICK_EMIT_LANES;
 	if (brick >= be.n_bricks) return;
+	// (all three loads are issued before anything depends on one of them: the kernel waits for latency, not for bandwidth)
 	const uint4 rec = a.rec[brick];
+	const uint64_t r1 = a.rank[1][brick], r2 = a.rank[2][brick];
 	const uint32_t c1 = (uint32_t)(__popc(rec.x) + __popc(rec.y));
 	if (c1 == 0u) return;
 	if (!(be.parts & ((rec.w & REC_FLAT) ? (BRICK_EMIT_FLAT | BRICK_EMIT_PTRS) : (BRICK_EMIT_COPY | BRICK_EMIT_PTRS)))) return;
-	const uint64_t r1 = a.rank[1][brick];
 	const uint64_t g1 = be.block_l + r1 - be.block_shift; // where the brick's first leaf block goes
-	uint4 *dst = reinterpret_cast<uint4 *>(words + g1 * 8);
+	uint32_t *dst = words + g1 * 8;
 	if (rec.w & REC_FLAT) { // 16 identical blocks: slot s holds the leaf iff its bit `axis` equals the plane's depth parity
 		const uint32_t axis = (rec.w >> 22) & 3u, par = (rec.w >> 24) & 1u, leaf = leaf_first(rec.z >> 8);
-		const uint32_t s0 = (sub & 1u) * 4u; // 16-byte piece i is half i & 1 (slots s0 .. s0 + 3) of block i / 2; the lane's pieces share it
-		uint4 v;
-		v.x = (((s0 + 0u) >> axis) & 1u) == par ? leaf : 0u, v.y = (((s0 + 1u) >> axis) & 1u) == par ? leaf : 0u;
-		v.z = (((s0 + 2u) >> axis) & 1u) == par ? leaf : 0u, v.w = (((s0 + 3u) >> axis) & 1u) == par ? leaf : 0u;
+		uint4 lo, hi;
+		lo.x = ((0u >> axis) & 1u) == par ? leaf : 0u, lo.y = ((1u >> axis) & 1u) == par ? leaf : 0u;
+		lo.z = ((2u >> axis) & 1u) == par ? leaf : 0u, lo.w = ((3u >> axis) & 1u) == par ? leaf : 0u;
+		hi.x = ((4u >> axis) & 1u) == par ? leaf : 0u, hi.y = ((5u >> axis) & 1u) == par ? leaf : 0u;
+		hi.z = ((6u >> axis) & 1u) == par ? leaf : 0u, hi.w = ((7u >> axis) & 1u) == par ? leaf : 0u;
 		if (be.parts & BRICK_EMIT_FLAT) {
 #pragma unroll
-			for (uint32_t i = 0; i < 32u; i += BRICK_EMIT_LANES) dst[i + sub] = v;
+			for (uint32_t i = 0; i < 16u; i += BRICK_EMIT_LANES) store_block(dst + 8u * (i + sub), lo, hi); // consecutive lanes consecutive blocks
 		}
 	} else if (be.parts & BRICK_EMIT_COPY) {
 		const uint4 *src = reinterpret_cast<const uint4 *>(a.temp + brick * BRICK_CELLS);
-		for (uint32_t i = sub; i < 2u * c1; i += BRICK_EMIT_LANES) dst[i] = src[i]; // 16-byte pieces, consecutive lanes consecutive pieces
+		for (uint32_t i = sub; i < c1; i += BRICK_EMIT_LANES) store_block(dst + 8u * i, src[2u * i], src[2u * i + 1u]);
 	}
 	const uint32_t n2 = rec.z & 0xffu;
-	if ((be.parts & BRICK_EMIT_PTRS) && sub < 8u && ((n2 >> sub) & 1u)) { // a depth L-2 node: one block of pointers to its children's blocks
-		uint32_t c = (uint32_t)g1 + brick_node_rank(rec.x, rec.y, 8u * sub);
+	if (!(be.parts & BRICK_EMIT_PTRS)) return;
+#pragma unroll
+	for (uint32_t nd = sub; nd < 8u; nd += BRICK_EMIT_LANES) { // a depth L-2 node: one block of pointers to its children's blocks
+		if (!((n2 >> nd) & 1u)) continue;
+		uint32_t c = (uint32_t)g1 + brick_node_rank(rec.x, rec.y, 8u * nd);
 		uint32_t w[8];
 #pragma unroll
 		for (int sl = 0; sl < 8; ++sl) {
-			const uint32_t node = 8u * sub + (uint32_t)sl;
+			const uint32_t node = 8u * nd + (uint32_t)sl;
 			const bool occ = (((node & 1u) ? rec.y : rec.x) >> (node >> 1)) & 1u;
 			w[sl] = occ ? (0x80000000u | ((c++ << 3) + be.ptr_bias)) : 0u;
 		}
-		const uint64_t g = be.block_l1 + a.rank[2][brick] + (uint32_t)__popc(n2 & ((1u << sub) - 1u)) - be.block_shift;
-		uint4 *o = reinterpret_cast<uint4 *>(words + g * 8);
-		o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-		o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+		const uint64_t g = be.block_l1 + r2 + (uint32_t)__popc(n2 & ((1u << nd) - 1u)) - be.block_shift;
+		store_block(words + g * 8, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
 	}
 }
-
 } // namespace svo
