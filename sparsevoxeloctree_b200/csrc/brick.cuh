@@ -281,7 +281,7 @@ SVO_DEV uint32_t nonzero_bytes4(uint32_t b) {
 
 // One warp rasterizes BRICK_BPW consecutive bricks, one after the other, into its 512-cell grid; nothing is shared
 // between warps and no warp waits for another one: what a brick needs from its neighbours (the ranks of its nodes in the
-// level arrays) is left to k_brick_keys / k_brick_emit, after three scans over the per-brick counts.
+// level arrays) is left to k_brick_ranks (three scans over the per-brick counts) and k_brick_emit.
 #ifndef SVO_BRICK_BPW
 #define SVO_BRICK_BPW 8
 #endif
@@ -493,18 +493,66 @@ SVO_DEV uint32_t brick_node_rank(uint32_t x, uint32_t y, uint32_t node) {
 	return (uint32_t)(__popc(x & below) + __popc(y & below)) + ((node & 1u) ? ((x >> l) & 1u) : 0u);
 }
 
-// The ranks of a brick's nodes are known (scans of the per-brick counts): the Morton codes of the depth L-2 nodes, in
-// order, are what the upper levels are built from (k_parent_compact); and the node counts of the three deepest levels.
-// One thread per brick.
-__global__ void __launch_bounds__(BRICK_BLOCK) k_brick_keys(BrickArgs a) {
-	const uint64_t brick = (uint64_t)blockIdx.x * BRICK_BLOCK + threadIdx.x;
-	if (brick < 3) *a.count[brick] = a.rank[brick][a.n_bound];
-	if (brick >= *a.n_bricks) return;
-	uint32_t n2 = a.rec[brick].z & 0xffu;
-	if (!n2) return;
-	uint64_t *dst = a.keys_top + a.rank[2][brick];
-	const uint64_t code = (a.brick_code[brick] & 0x3fffffffull) << 3;
-	for (; n2; n2 &= n2 - 1u) *dst++ = code | (uint64_t)(__ffs((int)n2) - 1);
+// The ranks of every brick's nodes in the three deepest levels: three exclusive scans over bit fields of word w of the
+// 16-byte records (leaves: bits 0..9, depth L-1 nodes: 10..16, depth L-2 nodes: 17..20) in one pass -- one read of the
+// records, three look-back chains walked by warps 0, 1, 2 at the same time; out[y * out_stride + i], entry n = total.
+// With its depth L-2 rank in hand a thread also writes the Morton codes of the brick's depth L-2 nodes, in order: what
+// the upper levels are built from (k_parent_compact); the totals are the node counts of the three deepest levels.
+__global__ void __launch_bounds__(SCAN_BLOCK)
+    k_brick_ranks(BrickArgs a, uint64_t *__restrict__ out, uint64_t out_stride, uint64_t *state, uint32_t *ticket, uint64_t state_stride) {
+	__shared__ uint32_t s_warp[3][SCAN_BLOCK / 32];
+	__shared__ uint32_t s_ticket;
+	__shared__ uint64_t s_prefix[3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t n = a.n_bound;
+	const uint32_t tile = take_ticket(ticket, &s_ticket);
+	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint32_t w[SCAN_ITEMS]; // the three counts (21 bits) | occupancy of the brick's 8 depth L-2 nodes << 21
+	uint32_t sum[3] = {0, 0, 0};
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		uint4 r = make_uint4(0u, 0u, 0u, 0u);
+		if (base + i < n) r = a.rec[base + i];
+		w[i] = (r.w & 0x1fffffu) | ((r.z & 0xffu) << 21);
+		sum[0] += w[i] & 0x3ffu, sum[1] += (w[i] >> 10) & 0x7fu, sum[2] += (w[i] >> 17) & 0xfu;
+	}
+	uint32_t inc[3];
+#pragma unroll
+	for (int y = 0; y < 3; ++y) {
+		inc[y] = warp_inclusive_sum(sum[y], lane);
+		if (lane == 31) s_warp[y][warp] = inc[y];
+	}
+	__syncthreads();
+	if (warp < 3) { // warp y: the block's total of scan y, its look-back, and the warps' offsets
+		const uint32_t mine = lane < SCAN_BLOCK / 32 ? s_warp[warp][lane] : 0u;
+		const uint32_t winc = warp_inclusive_sum(mine, lane);
+		const uint64_t total = __shfl_sync(FULL_MASK, winc, 31);
+		const uint64_t p = lookback_exclusive(state + (uint64_t)warp * state_stride, tile, total, lane);
+		if (lane < SCAN_BLOCK / 32) s_warp[warp][lane] = winc - mine;
+		if (lane == 0) s_prefix[warp] = p;
+	}
+	__syncthreads();
+	const bool last = n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS; // the thread that owns the last record
+#pragma unroll
+	for (int y = 0; y < 3; ++y) {
+		uint64_t run = s_prefix[y] + s_warp[y][warp] + inc[y] - sum[y];
+		uint64_t *o = out + (uint64_t)y * out_stride;
+		const uint32_t shift = y == 0 ? 0u : (y == 1 ? 10u : 17u), mask = y == 0 ? 0x3ffu : (y == 1 ? 0x7fu : 0xfu);
+#pragma unroll
+		for (int i = 0; i < SCAN_ITEMS; ++i) {
+			if (base + i < n) o[base + i] = run;
+			if (y == 2) {
+				uint32_t n2 = w[i] >> 21;
+				if (n2) { // (records past the last brick are zero)
+					uint64_t *dst = a.keys_top + run;
+					const uint64_t code = (a.brick_code[base + i] & 0x3fffffffull) << 3;
+					for (; n2; n2 &= n2 - 1u) *dst++ = code | (uint64_t)(__ffs((int)n2) - 1);
+				}
+			}
+			run += (w[i] >> shift) & mask;
+		}
+		if (last) o[n] = run, *a.count[y] = run;
+	}
 }
 
 // Node words of the two deepest windows, straight from the bricks (the bulk of the node buffer): the 8-word blocks of

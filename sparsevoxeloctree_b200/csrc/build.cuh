@@ -304,6 +304,53 @@ __global__ void __launch_bounds__(CMP_BLOCK)
 	}
 }
 
+// The levels near the root in ONE launch: a level of depth d has at most 8^d nodes, so from depth TAIL_DEPTH upwards a
+// single block walks level after level (what k_parent_compact does per level, without ticket, look-back and the launch
+// in between: 17 us per level on a B200, five levels).  Thread t owns a contiguous run of keys; keys ping-pong between
+// the two buffers through global memory (a block sees its own stores after __syncthreads).
+constexpr uint32_t TAIL_DEPTH = 5; // the tail starts with the keys of this depth (<= 32768)
+constexpr int TAIL_BLOCK = 1024;
+struct TailArgs {
+	uint64_t *keys[2];           // keys[0]: in (depth d0 keys), keys[1]: the other buffer
+	uint64_t *counts;            // counts[d], d = 0..level: device scalars (counts[d0] is valid on entry)
+	uint32_t *first[TAIL_DEPTH + 1];     // [d]: first_out of the step that consumes the depth-d keys
+	unsigned char *slot[TAIL_DEPTH + 1]; // [d]: slot_in of that step
+	uint32_t d0;
+};
+__global__ void __launch_bounds__(TAIL_BLOCK) k_parent_tail(TailArgs a) {
+	__shared__ uint64_t s_warp[TAIL_BLOCK / 32 + 1];
+	uint32_t cur = 0;
+	for (uint32_t d = a.d0; d >= 1; --d, cur ^= 1u) {
+		const uint64_t n = a.counts[d];
+		const uint64_t *kin = a.keys[cur];
+		uint64_t *kout = a.keys[cur ^ 1u];
+		const uint32_t per = (uint32_t)((n + TAIL_BLOCK - 1) / TAIL_BLOCK);
+		const uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+		uint64_t cnt = 0;
+		{
+			uint64_t prev = (lo > 0 && lo < n) ? kin[lo - 1] : 0;
+			for (uint64_t i = lo; i < hi; ++i) {
+				const uint64_t k = kin[i];
+				a.slot[d][i] = (unsigned char)(k & 7u);
+				cnt += (i == 0 || (k >> 3) != (prev >> 3)) ? 1u : 0u;
+				prev = k;
+			}
+		}
+		uint64_t total;
+		uint64_t u = block_exclusive_sum<TAIL_BLOCK, uint64_t>(cnt, total, s_warp);
+		{
+			uint64_t prev = (lo > 0 && lo < n) ? kin[lo - 1] : 0;
+			for (uint64_t i = lo; i < hi; ++i) {
+				const uint64_t k = kin[i];
+				if (i == 0 || (k >> 3) != (prev >> 3)) kout[u] = k >> 3, a.first[d][u] = (uint32_t)i, ++u;
+				prev = k;
+			}
+		}
+		if (threadIdx.x == 0) a.counts[d - 1] = total;
+		__syncthreads(); // kout and counts[d - 1] are read by the whole block in the next round
+	}
+}
+
 // ---- node words --------------------------------------------------------------------------------------------
 struct EmitParams {
 	uint32_t level;

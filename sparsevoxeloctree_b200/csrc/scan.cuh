@@ -58,10 +58,17 @@ SVO_DEV void lb_store(uint64_t *p, uint64_t v) { *reinterpret_cast<volatile uint
 inline int g_emu_lookback_aggregate_only = 0;
 #endif
 
-// Called by warp 0 of the block (all 32 lanes).  Publishes this tile's aggregate, walks back over the
-// predecessors' states 32 at a time, publishes the inclusive prefix and returns the exclusive prefix
-// (valid on every lane of warp 0).  state[] must be zero (LB_INVALID) when the kernel starts, and tiles
-// must be numbered in start order (dynamic ticket), which guarantees forward progress.
+// Called by one warp of the block (all 32 lanes).  Publishes this tile's aggregate, walks back over the
+// predecessors' states, publishes the inclusive prefix and returns the exclusive prefix (valid on every lane).
+// state[] must be zero (LB_INVALID) when the kernel starts, and tiles must be numbered in start order (dynamic
+// ticket), which guarantees forward progress.
+// A step of the walk looks at 32 * LB_WIDE predecessors: every lane has LB_WIDE independent loads in flight, so the
+// chain of a scan whose tiles all start together advances 32 * LB_WIDE tiles per memory round trip (with one state
+// per lane the three rank scans of 2.8e6 brick records -- 1350 tiles -- took 76 us, 42 round trips of the chain).
+#ifndef SVO_LB_WIDE
+#define SVO_LB_WIDE 4
+#endif
+constexpr int LB_WIDE = SVO_LB_WIDE;
 SVO_DEV uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t aggregate, int lane) {
 	if (tile == 0) {
 		if (lane == 0) lb_store(&state[0], lb_pack(LB_PREFIX, aggregate));
@@ -70,21 +77,29 @@ SVO_DEV uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t agg
 	if (lane == 0) lb_store(&state[tile], lb_pack(LB_AGGREGATE, aggregate));
 	uint64_t exclusive = 0;
 	int64_t base = (int64_t)tile - 1;
-	for (;;) {
-		const int64_t idx = base - lane;
-		uint64_t s = idx >= 0 ? lb_load(&state[idx]) : lb_pack(LB_PREFIX, 0);
-		while (__any_sync(FULL_MASK, lb_status(s) == LB_INVALID)) {
-#if defined(__CUDA_ARCH__)
-			__nanosleep(40); // the predecessors are still working: leave the issue slots to them
-#endif
-			if (lb_status(s) == LB_INVALID) s = lb_load(&state[idx]);
+	for (bool done = false; !done; base -= 32 * LB_WIDE) {
+		uint64_t s[LB_WIDE];
+#pragma unroll
+		for (int j = 0; j < LB_WIDE; ++j) { // nearest predecessors first: sub-window j holds tiles base - 32 j - lane
+			const int64_t idx = base - 32 * j - lane;
+			s[j] = idx >= 0 ? lb_load(&state[idx]) : lb_pack(LB_PREFIX, 0);
 		}
-		const unsigned pmask = __ballot_sync(FULL_MASK, lb_status(s) == LB_PREFIX);
-		const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
-		uint64_t v = lane <= first ? lb_value(s) : 0;
-		exclusive += warp_sum(v);
-		if (pmask) break;
-		base -= 32;
+#pragma unroll
+		for (int j = 0; j < LB_WIDE; ++j) {
+			if (done) break; // (warp-uniform)
+			const int64_t idx = base - 32 * j - lane;
+			while (__any_sync(FULL_MASK, lb_status(s[j]) == LB_INVALID)) {
+#if defined(__CUDA_ARCH__)
+				__nanosleep(40); // the predecessors are still working: leave the issue slots to them
+#endif
+				if (lb_status(s[j]) == LB_INVALID) s[j] = lb_load(&state[idx]);
+			}
+			const unsigned pmask = __ballot_sync(FULL_MASK, lb_status(s[j]) == LB_PREFIX);
+			const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
+			const uint64_t v = lane <= first ? lb_value(s[j]) : 0;
+			exclusive += warp_sum(v);
+			done = pmask != 0;
+		}
 	}
 #ifdef SVO_EMU
 	if (g_emu_lookback_aggregate_only) return exclusive;
@@ -143,55 +158,6 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 	if (n == 0 && tile == 0 && threadIdx.x == 0) out[0] = 0;
 }
 
-// The three rank scans of the brick path in one pass over the 16-byte brick records: element i of scan y is a bit field
-// of word w of record i (leaves: bits 0..9, depth L-1 nodes: 10..16, depth L-2 nodes: 17..20).  One read of the records,
-// three look-back chains walked by warps 0, 1, 2 at the same time.
-__global__ void __launch_bounds__(SCAN_BLOCK)
-    k_exclusive_scan_brick_counts(const uint4 *__restrict__ rec, uint64_t *__restrict__ out, uint64_t n, uint64_t *state, uint32_t *ticket,
-                                  uint64_t out_stride, uint64_t state_stride) {
-	__shared__ uint32_t s_warp[3][SCAN_BLOCK / 32];
-	__shared__ uint32_t s_ticket;
-	__shared__ uint64_t s_prefix[3];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t tile = take_ticket(ticket, &s_ticket);
-	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-	uint32_t w[SCAN_ITEMS];
-	uint32_t sum[3] = {0, 0, 0};
-#pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; ++i) {
-		w[i] = base + i < n ? rec[base + i].w : 0u;
-		sum[0] += w[i] & 0x3ffu, sum[1] += (w[i] >> 10) & 0x7fu, sum[2] += (w[i] >> 17) & 0xfu;
-	}
-	uint32_t inc[3];
-#pragma unroll
-	for (int y = 0; y < 3; ++y) {
-		inc[y] = warp_inclusive_sum(sum[y], lane);
-		if (lane == 31) s_warp[y][warp] = inc[y];
-	}
-	__syncthreads();
-	if (warp < 3) { // warp y: the block's total of scan y, its look-back, and the warps' offsets
-		const uint32_t mine = lane < SCAN_BLOCK / 32 ? s_warp[warp][lane] : 0u;
-		const uint32_t winc = warp_inclusive_sum(mine, lane);
-		const uint64_t total = __shfl_sync(FULL_MASK, winc, 31);
-		const uint64_t p = lookback_exclusive(state + (uint64_t)warp * state_stride, tile, total, lane);
-		if (lane < SCAN_BLOCK / 32) s_warp[warp][lane] = winc - mine;
-		if (lane == 0) s_prefix[warp] = p;
-	}
-	__syncthreads();
-#pragma unroll
-	for (int y = 0; y < 3; ++y) {
-		uint64_t run = s_prefix[y] + s_warp[y][warp] + inc[y] - sum[y];
-		uint64_t *o = out + (uint64_t)y * out_stride;
-		const uint32_t shift = y == 0 ? 0u : (y == 1 ? 10u : 17u), mask = y == 0 ? 0x3ffu : (y == 1 ? 0x7fu : 0xfu);
-#pragma unroll
-		for (int i = 0; i < SCAN_ITEMS; ++i) {
-			if (base + i < n) o[base + i] = run;
-			run += (w[i] >> shift) & mask;
-		}
-		if (n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS) o[n] = run;
-	}
-}
-
 struct ScanScratch {
 	DevBuf<uint64_t> state;
 	DevBuf<uint32_t> ticket;
@@ -207,17 +173,6 @@ inline int exclusive_scan(const InT *in, uint64_t *out, uint64_t n, ScanScratch 
 	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, sizeof(uint32_t), s));
 	auto k = k_exclusive_scan<InT, NONZERO>;
 	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k, in, out, n, sc.state.p, sc.ticket.p);
-	SVO_CUDA_TRY(cudaGetLastError());
-	return 0;
-}
-
-inline int exclusive_scan_brick_counts(const uint4 *rec, uint64_t *out, uint64_t out_stride, uint64_t n, ScanScratch &sc, cudaStream_t s) {
-	const uint32_t tiles = n ? div_up(n, SCAN_TILE) : 1;
-	SVO_TRY(sc.state.reserve((uint64_t)(tiles + 1) * 3, s));
-	SVO_TRY(sc.ticket.reserve(3, s));
-	SVO_CUDA_TRY(cudaMemsetAsync(sc.state.p, 0, (uint64_t)(tiles + 1) * 3 * sizeof(uint64_t), s));
-	SVO_CUDA_TRY(cudaMemsetAsync(sc.ticket.p, 0, 3 * sizeof(uint32_t), s));
-	SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k_exclusive_scan_brick_counts, rec, out, n, sc.state.p, sc.ticket.p, out_stride, (uint64_t)(tiles + 1));
 	SVO_CUDA_TRY(cudaGetLastError());
 	return 0;
 }

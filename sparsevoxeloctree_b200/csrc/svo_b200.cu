@@ -899,7 +899,7 @@ static int reduce_sorted(svo_builder *b, const uint64_t *sorted, uint64_t F, uin
 // The brick path of svo_builder_prepare (brick.cuh): small triangles' fragments sorted and reduced on their own, large
 // triangles binned; on return *keys_top holds the depth L-2 keys (counts[L-2] of them) and *free_buf is free.
 //   ev[0..1] small fragments: sort + reduce + small records (+ the read-back of their number)
-//   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_raster, scans, k_brick_keys
+//   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_flat, k_brick_raster, k_brick_ranks
 static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_off, const uint64_t *slot_off, uint64_t **free_buf,
                           uint64_t **keys_top) {
 	svo_voxelizer *v = b->vox;
@@ -982,9 +982,16 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	else
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[1], s));
-	SVO_TRY(exclusive_scan_brick_counts(a.rec, b->brick_u64.p, nbd + 1, nbd, b->scan_scratch, s)); // three scans, one launch
+	{ // ranks: three scans in one launch, which also writes the depth L-2 keys and the three node counts
+		const uint32_t tiles = div_up(nbd, SCAN_TILE);
+		SVO_TRY(b->scan_scratch.state.reserve((uint64_t)(tiles + 1) * 3, s));
+		SVO_TRY(b->scan_scratch.ticket.reserve(3, s));
+		SVO_CUDA_TRY(cudaMemsetAsync(b->scan_scratch.state.p, 0, (uint64_t)(tiles + 1) * 3 * sizeof(uint64_t), s));
+		SVO_CUDA_TRY(cudaMemsetAsync(b->scan_scratch.ticket.p, 0, 3 * sizeof(uint32_t), s));
+		SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k_brick_ranks, a, b->brick_u64.p, nbd + 1, b->scan_scratch.state.p, b->scan_scratch.ticket.p,
+		           (uint64_t)(tiles + 1));
+	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[2], s));
-	SVO_LAUNCH_INDEP(div_up(nbd, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_keys, a);
 	b->brick_args = a; // k_brick_emit (after the sizes are known) works on the same arrays
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[3], s));
 	SVO_CUDA_TRY(cudaGetLastError());
@@ -1049,7 +1056,8 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	// key buffers ping-pong between the two fragment-sized buffers (the sorted fragments are dead after the reduce)
 	const uint32_t pgrid = (uint32_t)n_sm * 4u;
 	uint64_t *kin = other, *kout = sorted;
-	for (uint32_t d = L - K + 1; d >= 1 && F; --d) {
+	uint32_t d = L - K + 1;
+	for (; d > TAIL_DEPTH && F; --d) {
 		const uint64_t in_cap8 = d >= 11 ? UINT64_MAX : (1ull << (3 * d));
 		const uint64_t in_cap = F < in_cap8 ? F : in_cap8;
 		const uint64_t tiles = (in_cap + CMP_TILE - 1) / CMP_TILE + 1;
@@ -1060,6 +1068,12 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 		uint64_t *t = kin;
 		kin = kout;
 		kout = t;
+	}
+	if (d >= 1 && F) { // the levels near the root (<= 8^TAIL_DEPTH keys): one single-block launch for all of them
+		TailArgs ta{};
+		ta.keys[0] = kin, ta.keys[1] = kout, ta.counts = b->counts.p, ta.d0 = d;
+		for (uint32_t e = 1; e <= d; ++e) ta.first[e] = b->first.p + first_off[e], ta.slot[e] = b->slot.p + slot_off[e];
+		SVO_LAUNCH(1, TAIL_BLOCK, 0, s, k_parent_tail, ta);
 	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[4], s));
 
