@@ -493,65 +493,76 @@ SVO_DEV uint32_t brick_node_rank(uint32_t x, uint32_t y, uint32_t node) {
 	return (uint32_t)(__popc(x & below) + __popc(y & below)) + ((node & 1u) ? ((x >> l) & 1u) : 0u);
 }
 
-// The ranks of every brick's nodes in the three deepest levels: three exclusive scans over bit fields of word w of the
-// 16-byte records (leaves: bits 0..9, depth L-1 nodes: 10..16, depth L-2 nodes: 17..20) in one pass -- one read of the
-// records, three look-back chains walked by warps 0, 1, 2 at the same time; out[y * out_stride + i], entry n = total.
-// With its depth L-2 rank in hand a thread also writes the Morton codes of the brick's depth L-2 nodes, in order: what
-// the upper levels are built from (k_parent_compact); the totals are the node counts of the three deepest levels.
+// The ranks of every brick's nodes in the two levels above the leaves, and the node counts of the three deepest levels:
+// three exclusive scans over bit fields of word w of the 16-byte records (leaves: bits 0..9, depth L-1 nodes: 10..16,
+// depth L-2 nodes: 17..20) in one pass.  Records are read striped (consecutive lanes consecutive records: 512 bytes per
+// warp load) and the three counts travel packed in one 64-bit word through the warp scans (a tile of 2048 bricks holds
+// < 2^21 leaves, < 2^18 and < 2^15 nodes); warps 0, 1, 2 walk the three look-back chains at the same time.  With its
+// depth L-2 rank in hand a thread also writes the Morton codes of the brick's depth L-2 nodes, in order: what the upper
+// levels are built from (k_parent_compact).  rank1 / rank2: n + 1 entries each (entry n = total).
+constexpr uint32_t RANK_SH1 = 21, RANK_SH2 = 42;
+constexpr uint64_t RANK_M0 = (1ull << RANK_SH1) - 1, RANK_M1 = (1ull << (RANK_SH2 - RANK_SH1)) - 1;
+static_assert(SCAN_TILE * 512ull <= RANK_M0 + 1 && SCAN_TILE * 64ull <= RANK_M1 + 1, "packed tile sums");
 __global__ void __launch_bounds__(SCAN_BLOCK)
-    k_brick_ranks(BrickArgs a, uint64_t *__restrict__ out, uint64_t out_stride, uint64_t *state, uint32_t *ticket, uint64_t state_stride) {
-	__shared__ uint32_t s_warp[3][SCAN_BLOCK / 32];
+    k_brick_ranks(BrickArgs a, uint64_t *__restrict__ rank1, uint64_t *__restrict__ rank2, uint64_t *state, uint32_t *ticket, uint64_t state_stride) {
+	constexpr int NW = SCAN_BLOCK / 32, NC = SCAN_ITEMS * NW; // (row, warp) cells of a tile
+	static_assert(NC % 32 == 0 && NC <= 128, "the cells are scanned by one warp");
+	__shared__ uint64_t s_cell[NC];
 	__shared__ uint32_t s_ticket;
 	__shared__ uint64_t s_prefix[3];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint64_t n = a.n_bound;
 	const uint32_t tile = take_ticket(ticket, &s_ticket);
-	const uint64_t base = (uint64_t)tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-	uint32_t w[SCAN_ITEMS]; // the three counts (21 bits) | occupancy of the brick's 8 depth L-2 nodes << 21
-	uint32_t sum[3] = {0, 0, 0};
+	const uint64_t base = (uint64_t)tile * SCAN_TILE + threadIdx.x;
+	uint64_t inc[SCAN_ITEMS]; // inclusive warp scan of the packed counts, row by row
+	uint32_t own[SCAN_ITEMS]; // the record's counts (21 bits) | occupancy of its 8 depth L-2 nodes << 21
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		const uint64_t e = base + (uint64_t)i * SCAN_BLOCK;
 		uint4 r = make_uint4(0u, 0u, 0u, 0u);
-		if (base + i < n) r = a.rec[base + i];
-		w[i] = (r.w & 0x1fffffu) | ((r.z & 0xffu) << 21);
-		sum[0] += w[i] & 0x3ffu, sum[1] += (w[i] >> 10) & 0x7fu, sum[2] += (w[i] >> 17) & 0xfu;
-	}
-	uint32_t inc[3];
-#pragma unroll
-	for (int y = 0; y < 3; ++y) {
-		inc[y] = warp_inclusive_sum(sum[y], lane);
-		if (lane == 31) s_warp[y][warp] = inc[y];
+		if (e < n) r = a.rec[e];
+		own[i] = (r.w & 0x1fffffu) | ((r.z & 0xffu) << 21);
+		const uint64_t p = (uint64_t)(r.w & 0x3ffu) | ((uint64_t)((r.w >> 10) & 0x7fu) << RANK_SH1) | ((uint64_t)((r.w >> 17) & 0xfu) << RANK_SH2);
+		inc[i] = warp_inclusive_sum(p, lane);
+		if (lane == 31) s_cell[i * NW + warp] = inc[i];
 	}
 	__syncthreads();
-	if (warp < 3) { // warp y: the block's total of scan y, its look-back, and the warps' offsets
-		const uint32_t mine = lane < SCAN_BLOCK / 32 ? s_warp[warp][lane] : 0u;
-		const uint32_t winc = warp_inclusive_sum(mine, lane);
-		const uint64_t total = __shfl_sync(FULL_MASK, winc, 31);
-		const uint64_t p = lookback_exclusive(state + (uint64_t)warp * state_stride, tile, total, lane);
-		if (lane < SCAN_BLOCK / 32) s_warp[warp][lane] = winc - mine;
+	if (warp == 0) { // exclusive scan of the cells, in element order (row-major); the tile's packed total is left in s_prefix[0]
+		constexpr int CPL = NC / 32;
+		uint64_t c[CPL], t = 0;
+#pragma unroll
+		for (int k = 0; k < CPL; ++k) c[k] = s_cell[lane * CPL + k], t += c[k];
+		const uint64_t tinc = warp_inclusive_sum(t, lane);
+		uint64_t run = tinc - t;
+#pragma unroll
+		for (int k = 0; k < CPL; ++k) s_cell[lane * CPL + k] = run, run += c[k];
+		if (lane == 31) s_prefix[0] = tinc;
+	}
+	__syncthreads();
+	const uint64_t total = s_prefix[0];
+	__syncthreads();
+	if (warp < 3) { // warp y walks the look-back chain of scan y
+		const uint64_t mine = warp == 0 ? (total & RANK_M0) : (warp == 1 ? ((total >> RANK_SH1) & RANK_M1) : (total >> RANK_SH2));
+		const uint64_t p = lookback_exclusive(state + (uint64_t)warp * state_stride, tile, mine, lane);
 		if (lane == 0) s_prefix[warp] = p;
 	}
 	__syncthreads();
-	const bool last = n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS; // the thread that owns the last record
+	const uint64_t p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2];
 #pragma unroll
-	for (int y = 0; y < 3; ++y) {
-		uint64_t run = s_prefix[y] + s_warp[y][warp] + inc[y] - sum[y];
-		uint64_t *o = out + (uint64_t)y * out_stride;
-		const uint32_t shift = y == 0 ? 0u : (y == 1 ? 10u : 17u), mask = y == 0 ? 0x3ffu : (y == 1 ? 0x7fu : 0xfu);
-#pragma unroll
-		for (int i = 0; i < SCAN_ITEMS; ++i) {
-			if (base + i < n) o[base + i] = run;
-			if (y == 2) {
-				uint32_t n2 = w[i] >> 21;
-				if (n2) { // (records past the last brick are zero)
-					uint64_t *dst = a.keys_top + run;
-					const uint64_t code = (a.brick_code[base + i] & 0x3fffffffull) << 3;
-					for (; n2; n2 &= n2 - 1u) *dst++ = code | (uint64_t)(__ffs((int)n2) - 1);
-				}
-			}
-			run += (w[i] >> shift) & mask;
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		const uint64_t e = base + (uint64_t)i * SCAN_BLOCK;
+		if (e > n) continue;
+		const uint64_t pk = s_cell[i * NW + warp] + inc[i] -
+		                    ((uint64_t)(own[i] & 0x3ffu) | ((uint64_t)((own[i] >> 10) & 0x7fu) << RANK_SH1) | ((uint64_t)((own[i] >> 17) & 0xfu) << RANK_SH2));
+		const uint64_t r0 = p0 + (pk & RANK_M0), r1 = p1 + ((pk >> RANK_SH1) & RANK_M1), r2 = p2 + (pk >> RANK_SH2);
+		rank1[e] = r1, rank2[e] = r2; // (e == n: the element behind the last record receives the totals)
+		if (e == n) *a.count[0] = r0, *a.count[1] = r1, *a.count[2] = r2;
+		uint32_t n2 = own[i] >> 21;
+		if (n2) { // (records past the last brick are zero)
+			uint64_t *dst = a.keys_top + r2;
+			const uint64_t code = (a.brick_code[e] & 0x3fffffffull) << 3;
+			for (; n2; n2 &= n2 - 1u) *dst++ = code | (uint64_t)(__ffs((int)n2) - 1);
 		}
-		if (last) o[n] = run, *a.count[y] = run;
 	}
 }
 

@@ -306,10 +306,11 @@ __global__ void __launch_bounds__(CMP_BLOCK)
 
 // The levels near the root in ONE launch: a level of depth d has at most 8^d nodes, so from depth TAIL_DEPTH upwards a
 // single block walks level after level (what k_parent_compact does per level, without ticket, look-back and the launch
-// in between: 17 us per level on a B200, five levels).  Thread t owns a contiguous run of keys; keys ping-pong between
-// the two buffers through global memory (a block sees its own stores after __syncthreads).
-constexpr uint32_t TAIL_DEPTH = 5; // the tail starts with the keys of this depth (<= 32768)
-constexpr int TAIL_BLOCK = 1024;
+// in between: 6.5 us per level on a B200).  Thread t owns TAIL_ITEMS consecutive keys, held in registers; keys ping-pong
+// between the two buffers through global memory (a block sees its own stores after __syncthreads).
+constexpr uint32_t TAIL_DEPTH = 4; // the tail starts with the keys of this depth (<= 4096)
+constexpr int TAIL_BLOCK = 1024, TAIL_ITEMS = 4;
+static_assert((1u << (3 * TAIL_DEPTH)) <= (uint32_t)TAIL_BLOCK * TAIL_ITEMS, "one block holds a whole level");
 struct TailArgs {
 	uint64_t *keys[2];           // keys[0]: in (depth d0 keys), keys[1]: the other buffer
 	uint64_t *counts;            // counts[d], d = 0..level: device scalars (counts[d0] is valid on entry)
@@ -318,34 +319,35 @@ struct TailArgs {
 	uint32_t d0;
 };
 __global__ void __launch_bounds__(TAIL_BLOCK) k_parent_tail(TailArgs a) {
-	__shared__ uint64_t s_warp[TAIL_BLOCK / 32 + 1];
+	__shared__ uint32_t s_warp[TAIL_BLOCK / 32 + 1];
 	uint32_t cur = 0;
+#pragma unroll 1
 	for (uint32_t d = a.d0; d >= 1; --d, cur ^= 1u) {
-		const uint64_t n = a.counts[d];
+		const uint32_t n = (uint32_t)a.counts[d];
 		const uint64_t *kin = a.keys[cur];
 		uint64_t *kout = a.keys[cur ^ 1u];
-		const uint32_t per = (uint32_t)((n + TAIL_BLOCK - 1) / TAIL_BLOCK);
-		const uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
-		uint64_t cnt = 0;
-		{
-			uint64_t prev = (lo > 0 && lo < n) ? kin[lo - 1] : 0;
-			for (uint64_t i = lo; i < hi; ++i) {
-				const uint64_t k = kin[i];
-				a.slot[d][i] = (unsigned char)(k & 7u);
-				cnt += (i == 0 || (k >> 3) != (prev >> 3)) ? 1u : 0u;
-				prev = k;
+		uint32_t *first = d == 1 ? a.first[1] : (d == 2 ? a.first[2] : (d == 3 ? a.first[3] : a.first[4]));
+		unsigned char *slot = d == 1 ? a.slot[1] : (d == 2 ? a.slot[2] : (d == 3 ? a.slot[3] : a.slot[4]));
+		static_assert(TAIL_DEPTH == 4, "the selects above");
+		const uint32_t lo = threadIdx.x * TAIL_ITEMS;
+		uint64_t k[TAIL_ITEMS], prev = 0;
+		if (lo > 0 && lo < n) prev = kin[lo - 1];
+#pragma unroll
+		for (int i = 0; i < TAIL_ITEMS; ++i) k[i] = lo + i < n ? kin[lo + i] : 0;
+		uint32_t heads = 0, cnt = 0;
+#pragma unroll
+		for (int i = 0; i < TAIL_ITEMS; ++i) {
+			if (lo + i < n) {
+				slot[lo + i] = (unsigned char)(k[i] & 7u);
+				if (lo + i == 0 || (k[i] >> 3) != (prev >> 3)) heads |= 1u << i, ++cnt;
 			}
+			prev = k[i];
 		}
-		uint64_t total;
-		uint64_t u = block_exclusive_sum<TAIL_BLOCK, uint64_t>(cnt, total, s_warp);
-		{
-			uint64_t prev = (lo > 0 && lo < n) ? kin[lo - 1] : 0;
-			for (uint64_t i = lo; i < hi; ++i) {
-				const uint64_t k = kin[i];
-				if (i == 0 || (k >> 3) != (prev >> 3)) kout[u] = k >> 3, a.first[d][u] = (uint32_t)i, ++u;
-				prev = k;
-			}
-		}
+		uint32_t total;
+		uint32_t u = block_exclusive_sum<TAIL_BLOCK, uint32_t>(cnt, total, s_warp);
+#pragma unroll
+		for (int i = 0; i < TAIL_ITEMS; ++i)
+			if ((heads >> i) & 1u) kout[u] = k[i] >> 3, first[u] = lo + i, ++u;
 		if (threadIdx.x == 0) a.counts[d - 1] = total;
 		__syncthreads(); // kout and counts[d - 1] are read by the whole block in the next round
 	}

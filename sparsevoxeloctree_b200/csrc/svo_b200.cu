@@ -983,13 +983,13 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[1], s));
 	{ // ranks: three scans in one launch, which also writes the depth L-2 keys and the three node counts
-		const uint32_t tiles = div_up(nbd, SCAN_TILE);
+		const uint32_t tiles = div_up(nbd + 1, SCAN_TILE); // (one element more than records: it receives the totals)
 		SVO_TRY(b->scan_scratch.state.reserve((uint64_t)(tiles + 1) * 3, s));
 		SVO_TRY(b->scan_scratch.ticket.reserve(3, s));
 		SVO_CUDA_TRY(cudaMemsetAsync(b->scan_scratch.state.p, 0, (uint64_t)(tiles + 1) * 3 * sizeof(uint64_t), s));
 		SVO_CUDA_TRY(cudaMemsetAsync(b->scan_scratch.ticket.p, 0, 3 * sizeof(uint32_t), s));
-		SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k_brick_ranks, a, b->brick_u64.p, nbd + 1, b->scan_scratch.state.p, b->scan_scratch.ticket.p,
-		           (uint64_t)(tiles + 1));
+		SVO_LAUNCH(tiles, SCAN_BLOCK, 0, s, k_brick_ranks, a, b->brick_u64.p + (nbd + 1), b->brick_u64.p + (nbd + 1) * 2, b->scan_scratch.state.p,
+		           b->scan_scratch.ticket.p, (uint64_t)(tiles + 1));
 	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[2], s));
 	b->brick_args = a; // k_brick_emit (after the sizes are known) works on the same arrays
