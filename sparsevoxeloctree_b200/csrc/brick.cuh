@@ -259,8 +259,11 @@ struct BrickArgs {
 	uint64_t n_bound;       // entries of the per-brick arrays
 	uint32_t *slow_list;     // the bricks k_brick_raster has to rasterize (all but the flat ones), in any order
 	unsigned long long *n_slow; // how many (zeroed)
-	uint64_t *keys_top;      // per depth L-2 node: Morton code (what k_parent_compact builds the upper levels from)
-	uint64_t *count[3];      // device scalars: leaves, depth L-1, depth L-2 nodes
+	uint64_t *keys_top;      // per non-empty brick = depth L-3 node: Morton code (what k_parent_compact builds the upper levels from)
+	uint32_t *first_l2;      // per depth L-3 node: index of its first depth L-2 child
+	unsigned char *slot_l2;  // per depth L-2 node: its child slot
+	uint64_t *count[3];      // device scalars: leaves (zeroed: accumulated), depth L-1, depth L-2 nodes
+	uint64_t *count3;        // depth L-3 nodes
 };
 
 // 3 bits -> every third bit (0, 1, 8, 9, 64, 65, 72, 73): one byte permute picks the entry of a table held in two registers
@@ -493,40 +496,49 @@ SVO_DEV uint32_t brick_node_rank(uint32_t x, uint32_t y, uint32_t node) {
 	return (uint32_t)(__popc(x & below) + __popc(y & below)) + ((node & 1u) ? ((x >> l) & 1u) : 0u);
 }
 
-// The ranks of every brick's nodes in the two levels above the leaves, and the node counts of the three deepest levels:
-// three exclusive scans over bit fields of word w of the 16-byte records (leaves: bits 0..9, depth L-1 nodes: 10..16,
-// depth L-2 nodes: 17..20) in one pass.  Records are read striped (consecutive lanes consecutive records: 512 bytes per
-// warp load) and the three counts travel packed in one 64-bit word through the warp scans (a tile of 2048 bricks holds
-// < 2^21 leaves, < 2^18 and < 2^15 nodes); warps 0, 1, 2 walk the three look-back chains at the same time.  With its
-// depth L-2 rank in hand a thread also writes the Morton codes of the brick's depth L-2 nodes, in order: what the upper
-// levels are built from (k_parent_compact).  rank1 / rank2: n + 1 entries each (entry n = total).
-constexpr uint32_t RANK_SH1 = 21, RANK_SH2 = 42;
-constexpr uint64_t RANK_M0 = (1ull << RANK_SH1) - 1, RANK_M1 = (1ull << (RANK_SH2 - RANK_SH1)) - 1;
-static_assert(SCAN_TILE * 512ull <= RANK_M0 + 1 && SCAN_TILE * 64ull <= RANK_M1 + 1, "packed tile sums");
+// The ranks of every brick's nodes in the two levels above the leaves, the node counts of the four deepest levels, and
+// the depth L-3 level itself (a brick IS a depth L-3 node): three exclusive scans over the 16-byte records -- depth L-1
+// nodes (bits 10..16 of word w), depth L-2 nodes (17..20), non-empty bricks -- in one pass.  Records are read striped
+// (consecutive lanes consecutive records: 512 bytes per warp load) and the three counts travel packed in one 64-bit
+// word through the warp scans (a tile of 2048 bricks holds <= 2^17, 2^14 and 2^11 of them); warps 0, 1, 2 walk the
+// three look-back chains at the same time; leaves are only counted.  With its ranks in hand a thread writes what
+// k_parent_compact would have derived from the depth L-2 keys: the brick's Morton code as a depth L-3 key, the index of
+// its first depth L-2 child and those children's slots.  rank1 / rank2: n + 1 entries each (entry n = total).
+constexpr uint32_t RANK_SH2 = 18, RANK_SH3 = 33;
+constexpr uint64_t RANK_M1 = (1ull << RANK_SH2) - 1, RANK_M2 = (1ull << (RANK_SH3 - RANK_SH2)) - 1;
+static_assert(SCAN_TILE * 64ull <= RANK_M1 && SCAN_TILE * 8ull <= RANK_M2, "packed tile sums");
 __global__ void __launch_bounds__(SCAN_BLOCK)
     k_brick_ranks(BrickArgs a, uint64_t *__restrict__ rank1, uint64_t *__restrict__ rank2, uint64_t *state, uint32_t *ticket, uint64_t state_stride) {
 	constexpr int NW = SCAN_BLOCK / 32, NC = SCAN_ITEMS * NW; // (row, warp) cells of a tile
 	static_assert(NC % 32 == 0 && NC <= 128, "the cells are scanned by one warp");
 	__shared__ uint64_t s_cell[NC];
 	__shared__ uint32_t s_ticket;
+	__shared__ unsigned long long s_leaves;
 	__shared__ uint64_t s_prefix[3];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint64_t n = a.n_bound;
 	const uint32_t tile = take_ticket(ticket, &s_ticket);
+	if (threadIdx.x == 0) s_leaves = 0;
 	const uint64_t base = (uint64_t)tile * SCAN_TILE + threadIdx.x;
 	uint64_t inc[SCAN_ITEMS]; // inclusive warp scan of the packed counts, row by row
-	uint32_t own[SCAN_ITEMS]; // the record's counts (21 bits) | occupancy of its 8 depth L-2 nodes << 21
+	uint32_t own[SCAN_ITEMS]; // the record's counts (bits 10..20) | occupancy of its 8 depth L-2 nodes << 21
+	uint32_t leaves = 0;
+	auto packed = [](uint32_t o) {
+		return (uint64_t)((o >> 10) & 0x7fu) | ((uint64_t)((o >> 17) & 0xfu) << RANK_SH2) | ((uint64_t)((o >> 21) != 0u) << RANK_SH3);
+	};
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; ++i) {
 		const uint64_t e = base + (uint64_t)i * SCAN_BLOCK;
 		uint4 r = make_uint4(0u, 0u, 0u, 0u);
 		if (e < n) r = a.rec[e];
-		own[i] = (r.w & 0x1fffffu) | ((r.z & 0xffu) << 21);
-		const uint64_t p = (uint64_t)(r.w & 0x3ffu) | ((uint64_t)((r.w >> 10) & 0x7fu) << RANK_SH1) | ((uint64_t)((r.w >> 17) & 0xfu) << RANK_SH2);
-		inc[i] = warp_inclusive_sum(p, lane);
+		own[i] = (r.w & 0x1ffc00u) | ((r.z & 0xffu) << 21);
+		leaves += r.w & 0x3ffu;
+		inc[i] = warp_inclusive_sum(packed(own[i]), lane);
 		if (lane == 31) s_cell[i * NW + warp] = inc[i];
 	}
+	leaves = warp_sum(leaves);
 	__syncthreads();
+	if (lane == 0 && leaves) atomicAdd(&s_leaves, (unsigned long long)leaves);
 	if (warp == 0) { // exclusive scan of the cells, in element order (row-major); the tile's packed total is left in s_prefix[0]
 		constexpr int CPL = NC / 32;
 		uint64_t c[CPL], t = 0;
@@ -540,28 +552,29 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 	}
 	__syncthreads();
 	const uint64_t total = s_prefix[0];
+	if (threadIdx.x == 0 && s_leaves) atomicAdd(reinterpret_cast<unsigned long long *>(a.count[0]), s_leaves);
 	__syncthreads();
 	if (warp < 3) { // warp y walks the look-back chain of scan y
-		const uint64_t mine = warp == 0 ? (total & RANK_M0) : (warp == 1 ? ((total >> RANK_SH1) & RANK_M1) : (total >> RANK_SH2));
+		const uint64_t mine = warp == 0 ? (total & RANK_M1) : (warp == 1 ? ((total >> RANK_SH2) & RANK_M2) : (total >> RANK_SH3));
 		const uint64_t p = lookback_exclusive(state + (uint64_t)warp * state_stride, tile, mine, lane);
 		if (lane == 0) s_prefix[warp] = p;
 	}
 	__syncthreads();
-	const uint64_t p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2];
+	const uint64_t p1 = s_prefix[0], p2 = s_prefix[1], p3 = s_prefix[2];
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; ++i) {
 		const uint64_t e = base + (uint64_t)i * SCAN_BLOCK;
 		if (e > n) continue;
-		const uint64_t pk = s_cell[i * NW + warp] + inc[i] -
-		                    ((uint64_t)(own[i] & 0x3ffu) | ((uint64_t)((own[i] >> 10) & 0x7fu) << RANK_SH1) | ((uint64_t)((own[i] >> 17) & 0xfu) << RANK_SH2));
-		const uint64_t r0 = p0 + (pk & RANK_M0), r1 = p1 + ((pk >> RANK_SH1) & RANK_M1), r2 = p2 + (pk >> RANK_SH2);
+		const uint64_t pk = s_cell[i * NW + warp] + inc[i] - packed(own[i]);
+		const uint64_t r1 = p1 + (pk & RANK_M1), r2 = p2 + ((pk >> RANK_SH2) & RANK_M2), r3 = p3 + (pk >> RANK_SH3);
 		rank1[e] = r1, rank2[e] = r2; // (e == n: the element behind the last record receives the totals)
-		if (e == n) *a.count[0] = r0, *a.count[1] = r1, *a.count[2] = r2;
+		if (e == n) *a.count[1] = r1, *a.count[2] = r2, *a.count3 = r3;
 		uint32_t n2 = own[i] >> 21;
-		if (n2) { // (records past the last brick are zero)
-			uint64_t *dst = a.keys_top + r2;
-			const uint64_t code = (a.brick_code[e] & 0x3fffffffull) << 3;
-			for (; n2; n2 &= n2 - 1u) *dst++ = code | (uint64_t)(__ffs((int)n2) - 1);
+		if (n2) { // a non-empty brick (records past the last brick are zero)
+			a.keys_top[r3] = a.brick_code[e] & 0x3fffffffull;
+			a.first_l2[r3] = (uint32_t)r2;
+			unsigned char *sl = a.slot_l2 + r2;
+			for (; n2; n2 &= n2 - 1u) *sl++ = (unsigned char)(__ffs((int)n2) - 1);
 		}
 	}
 }

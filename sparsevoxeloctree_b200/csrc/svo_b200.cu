@@ -897,7 +897,7 @@ static int reduce_sorted(svo_builder *b, const uint64_t *sorted, uint64_t F, uin
 }
 
 // The brick path of svo_builder_prepare (brick.cuh): small triangles' fragments sorted and reduced on their own, large
-// triangles binned; on return *keys_top holds the depth L-2 keys (counts[L-2] of them) and *free_buf is free.
+// triangles binned; on return *keys_top holds the depth L-3 keys (counts[L-3] of them: the non-empty bricks) and *free_buf is free.
 //   ev[0..1] small fragments: sort + reduce + small records (+ the read-back of their number)
 //   ev[1..2] pairs: generation, sort by brick, brick heads        ev[2..3] k_brick_flat, k_brick_raster, k_brick_ranks
 static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_off, const uint64_t *slot_off, uint64_t **free_buf,
@@ -972,6 +972,7 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	a.temp = b->brick_temp.p;
 	a.keys_top = A;
 	for (uint32_t j = 0; j < 3; ++j) a.count[j] = b->counts.p + (L - j);
+	a.count3 = b->counts.p + (L - 3), a.first_l2 = b->first.p + first_off[L - 2], a.slot_l2 = b->slot.p + slot_off[L - 2];
 	a.slow_list = b->pair_flags.p; // (n_pairs words: at most one entry per brick)
 	a.n_slow = reinterpret_cast<unsigned long long *>(b->brick_scalars.p + 2);
 	const uint32_t rgrid = div_up(nbd, (uint64_t)BRICK_WARPS * BRICK_BPW);
@@ -1056,7 +1057,7 @@ int svo_builder_prepare(svo_builder *b, void *stream) {
 	// key buffers ping-pong between the two fragment-sized buffers (the sorted fragments are dead after the reduce)
 	const uint32_t pgrid = (uint32_t)n_sm * 4u;
 	uint64_t *kin = other, *kout = sorted;
-	uint32_t d = L - K + 1;
+	uint32_t d = b->path == 1 ? L - 3 : L - K + 1; // (the brick path leaves the depth L-3 keys: a brick is a depth L-3 node)
 	for (; d > TAIL_DEPTH && F; --d) {
 		const uint64_t in_cap8 = d >= 11 ? UINT64_MAX : (1ull << (3 * d));
 		const uint64_t in_cap = F < in_cap8 ? F : in_cap8;
