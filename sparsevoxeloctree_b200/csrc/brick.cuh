@@ -352,7 +352,7 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 	__align__(16) __shared__ uint32_t s_grid[BRICK_WARPS][BRICK_CELLS]; // leaf words (zeroed per brick; bits: which cells have a first writer)
 	__shared__ uint32_t s_bits[BRICK_WARPS][BRICK_CELLS / 32];
 	__shared__ uint64_t s_tri[BRICK_WARPS][BRICK_BPW][LT_WORDS]; // the first triangle of every brick of the warp
-	__align__(16) __shared__ uint64_t s_meta[BRICK_WARPS][BRICK_BPW][4];
+	__align__(16) __shared__ uint64_t s_meta[BRICK_WARPS][BRICK_BPW][6];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint64_t nb = *a.n_slow; // bricks on the list (k_brick_flat)
 	const uint64_t brick0 = ((uint64_t)blockIdx.x * BRICK_WARPS + warp) * BRICK_BPW; // the warp's first list entry
@@ -372,6 +372,7 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 		m[1] = a.brick_code[brick];
 		m[2] = a.pairs[p0];
 		m[3] = brick;
+		m[4] = a.pairs[p1 - 1]; // the brick's small record, if it has one, is its last pair (the sort is stable, small records are appended)
 	}
 	__syncwarp();
 #pragma unroll
@@ -401,23 +402,28 @@ template <bool TEX> __global__ void __launch_bounds__(BRICK_BLOCK, SVO_BRICK_MIN
 		// first voxel of the brick, full-grid coordinates
 		const uint32_t vb0 = a.rp.origin[0] + 8u * (bxyz & 1023u), vb1 = a.rp.origin[1] + 8u * ((bxyz >> 10) & 1023u),
 		               vb2 = a.rp.origin[2] + 8u * (bxyz >> 20);
-		for (uint32_t p = p0; p < p1; ++p) {
-			const uint64_t pr = p == p0 ? pr0 : a.pairs[p]; // warp-uniform
-			if (!((pr >> 32) & 1ull)) {
-				// the brick's leaves of small triangles (they come first in fragment order): plain stores, cells are unique
-				const uint64_t ns = *a.n_small;
-				for (uint64_t i = (uint64_t)(uint32_t)pr + lane;; i += 32) {
-					bool ok = i < ns;
-					uint64_t key = 0;
-					if (ok) key = a.small_keys[i], ok = (key >> (3 * BRICK_LOG)) == brick_id;
-					if (ok) {
-						const uint32_t cell = (uint32_t)key & (BRICK_CELLS - 1);
-						g[cell] = a.small_leaf[i];
-						atomicOr(&bits[cell >> 5], 1u << (cell & 31u));
-					}
-					if (!__all_sync(FULL_MASK, ok)) break;
+		// The brick's leaves of small triangles come first in fragment order, its large triangles follow by id: the small
+		// record (the last pair) is handled before the others.
+		const uint64_t pr_last = s_meta[warp][q][4];
+		const uint32_t has_small = ((pr_last >> 32) & 1ull) ? 0u : 1u;
+		if (has_small) { // plain stores, cells are unique
+			const uint64_t ns = *a.n_small;
+			for (uint64_t i = (uint64_t)(uint32_t)pr_last + lane;; i += 32) {
+				bool ok = i < ns;
+				uint64_t key = 0;
+				if (ok) key = a.small_keys[i], ok = (key >> (3 * BRICK_LOG)) == brick_id;
+				if (ok) {
+					const uint32_t cell = (uint32_t)key & (BRICK_CELLS - 1);
+					g[cell] = a.small_leaf[i];
+					atomicOr(&bits[cell >> 5], 1u << (cell & 31u));
 				}
-			} else {
+				if (!__all_sync(FULL_MASK, ok)) break;
+			}
+			__syncwarp();
+		}
+		for (uint32_t p = p0; p < p1 - has_small; ++p) {
+			const uint64_t pr = p == p0 ? pr0 : a.pairs[p]; // warp-uniform
+			{
 				// one large triangle: the brick's 8x8 pixels, two per lane (rows dy and dy + 4); a triangle puts at most one
 				// fragment into a voxel, so the fold of a cell needs no atomics, and triangles follow each other in order
 				const uint32_t li = (uint32_t)pr & PAIR_LI_MASK;

@@ -167,6 +167,9 @@ struct svo_builder {
 	int path = 0;                             // 0: every fragment sorted; 1: bricks
 	BrickArgs brick_args{};                   // the arrays of the last brick build
 	uint64_t h_counts[MAX_LEVEL + 1] = {};
+	cudaStream_t aux = nullptr;   // second stream: work that does not depend on what the caller's stream is busy with
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	uint64_t *h_pinned = nullptr; // 8 words of page-locked host memory: read-backs the host does not block the stream for
 	uint64_t range_bytes = 0;
 	uint32_t sort_passes = 0;
 	bool built = false;     // the node words are in b->octree
@@ -836,6 +839,14 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 			if (cudaEventCreate(&b->ev[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
 		for (int i = 0; i < 5; ++i)
 			if (cudaEventCreate(&b->ev_brick[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
+		if (cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess)
+			rc = fail(SVO_ERR_CUDA, "cannot create the builder's auxiliary stream");
+#ifdef SVO_EMU
+		b->h_pinned = static_cast<uint64_t *>(calloc(8, sizeof(uint64_t)));
+#else
+		if (cudaMallocHost(reinterpret_cast<void **>(&b->h_pinned), 8 * sizeof(uint64_t)) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaMallocHost failed");
+#endif
 		if (rc) break;
 		const uint64_t F = vox->n_frag;
 		if ((rc = b->tmp.alloc(F, s)) || (rc = b->leaf.alloc(F, s)) || (rc = b->counts.alloc(MAX_LEVEL + 2, s))) break;
@@ -872,6 +883,14 @@ void svo_builder_destroy(svo_builder *b) {
 		if (b->ev[i]) cudaEventDestroy(b->ev[i]);
 	for (int i = 0; i < 5; ++i)
 		if (b->ev_brick[i]) cudaEventDestroy(b->ev_brick[i]);
+	if (b->aux) cudaStreamSynchronize(b->aux), cudaStreamDestroy(b->aux);
+	if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+	if (b->ev_join) cudaEventDestroy(b->ev_join);
+#ifdef SVO_EMU
+	free(b->h_pinned);
+#else
+	if (b->h_pinned) cudaFreeHost(b->h_pinned);
+#endif
 	release_export(b);
 	delete b;
 }
@@ -910,8 +929,20 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	SVO_TRY(b->brick_scalars.reserve(4, s));
 	SVO_CUDA_TRY(cudaMemsetAsync(b->brick_scalars.p, 0, 4 * sizeof(uint64_t), s));
 	uint64_t *d_nsl = b->brick_scalars.p, *d_nsb = b->brick_scalars.p + 1;
-	uint64_t h_small[2] = {0, 0}; // leaves of small triangles, bricks that hold some
+	uint64_t *h_small = b->h_pinned; // leaves of small triangles, bricks that hold some
+	h_small[0] = h_small[1] = 0;
 	b->sort_passes = 0;
+	// The pair list: the large triangles' pairs first (in triangle order), the small records behind them; the pair sort is
+	// stable, so a brick's small record ends up as its last pair (k_brick_raster handles it first).  The large pairs do
+	// not depend on the small chain: they are generated while the host waits for the small chain's two counts.
+	SVO_TRY(b->pairs_a.reserve(npl + ns, s)); // (at most one small record per small fragment)
+	if (npl) { // on the builder's second stream, next to the small chain
+		SVO_CUDA_TRY(cudaEventRecord(b->ev_fork, s));
+		SVO_CUDA_TRY(cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
+		SVO_LAUNCH(brick_pair_grid(v), RASTER_BLOCK, 0, b->aux, k_brick_pairs<true>, v->rp, v->n_large, (const LargeTri *)v->large.p,
+		           (const uint64_t *)v->tr_base.p, (uint32_t *)nullptr, (const uint64_t *)v->pair_off.p, b->pairs_a.p);
+		SVO_CUDA_TRY(cudaEventRecord(b->ev_join, b->aux));
+	}
 	if (ns) {
 		uint64_t *sorted = A;
 		SVO_TRY(radix_sort_u64(v->frags.p, b->tmp.p, ns, 24, 24 + 3 * L, b->sort_scratch, b->device, n_sm, s, &sorted, &b->sort_passes, nullptr));
@@ -923,22 +954,20 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 		fo.count[0] = d_nsl;
 		SVO_TRY(reduce_sorted(b, A, ns, 1, fo, s));
 		const uint32_t g = std::min<uint32_t>(div_up(ns, 256), (uint32_t)n_sm * 8u);
-		SVO_LAUNCH(g, 256, 0, s, k_brick_small_records, (const uint64_t *)B, (const uint64_t *)d_nsl, A, reinterpret_cast<unsigned long long *>(d_nsb));
+		SVO_LAUNCH(g, 256, 0, s, k_brick_small_records, (const uint64_t *)B, (const uint64_t *)d_nsl, b->pairs_a.p + npl,
+		           reinterpret_cast<unsigned long long *>(d_nsb));
 		SVO_CUDA_TRY(cudaMemcpyAsync(h_small, b->brick_scalars.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-		SVO_CUDA_TRY(cudaStreamSynchronize(s));
 	}
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[1], s));
+	if (npl) SVO_CUDA_TRY(cudaStreamWaitEvent(s, b->ev_join, 0));
+	if (ns) SVO_CUDA_TRY(cudaEventSynchronize(b->ev[1])); // (the two counts have arrived)
 	b->n_small_leaves = h_small[0];
 	const uint64_t nsb = h_small[1], n_pairs = npl + nsb;
 	if (n_pairs >= (1ull << 32)) return fail(SVO_ERR_CAPACITY, "brick path: more than 2^32-1 (brick, triangle) pairs");
 	b->n_pairs = n_pairs;
-	SVO_TRY(b->pairs_a.reserve(n_pairs, s));
 	SVO_TRY(b->pairs_b.reserve(n_pairs, s));
 	SVO_TRY(b->pair_flags.reserve(n_pairs, s));
 	SVO_TRY(b->brick_first.reserve(n_pairs + 1, s));
-	if (nsb) SVO_CUDA_TRY(cudaMemcpyAsync(b->pairs_a.p, A, nsb * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
-	SVO_LAUNCH(brick_pair_grid(v), RASTER_BLOCK, 0, s, k_brick_pairs<true>, v->rp, v->n_large, (const LargeTri *)v->large.p,
-	           (const uint64_t *)v->tr_base.p, (uint32_t *)nullptr, (const uint64_t *)v->pair_off.p, b->pairs_a.p + nsb);
 	uint64_t *pairs = b->pairs_a.p;
 	uint32_t pair_passes = 0;
 	SVO_TRY(radix_sort_u64(b->pairs_a.p, b->pairs_b.p, n_pairs, PAIR_SORT_BEGIN, 33 + 3 * (L - BRICK_LOG), b->sort_scratch, b->device, n_sm, s,
