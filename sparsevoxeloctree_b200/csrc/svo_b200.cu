@@ -1158,10 +1158,18 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 	} else {
 		auto k_direct = k_emit_octree<false>;
 		auto k_staged = k_emit_octree<true>;
+		// brick path: the upper windows (small) are written on the builder's second stream, next to k_brick_emit
+		cudaStream_t su = s;
+		if (b->path == 1 && b->n_bricks) {
+			su = b->aux;
+			SVO_CUDA_TRY(cudaEventRecord(b->ev_fork, s));
+			SVO_CUDA_TRY(cudaStreamWaitEvent(su, b->ev_fork, 0));
+		}
 		if (skip_root) // stitched into another (usually a peer GPU's) buffer
-			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_staged, ep, d_dst);
+			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, su, k_staged, ep, d_dst);
 		else
-			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, s, k_direct, ep, d_dst);
+			SVO_LAUNCH(div_up(ep.total_blocks, EMITO_BLOCK), EMITO_BLOCK, 0, su, k_direct, ep, d_dst);
+		if (su != s) SVO_CUDA_TRY(cudaEventRecord(b->ev_join, su));
 		if (b->path == 1) {
 			BrickEmit be{ep.block_base[b->level - 1], ep.block_base[b->level], ep.block_shift, ep.ptr_bias, b->n_bricks, brick_parts};
 			if (plan) plan[0] = be.n_bricks, plan[1] = be.block_l1, plan[2] = be.block_l, plan[3] = (uint64_t)be.block_shift | ((uint64_t)be.ptr_bias << 32);
@@ -1170,6 +1178,7 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 				SVO_LAUNCH_INDEP(div_up(b->n_bricks * BRICK_EMIT_LANES, BRICK_BLOCK), BRICK_BLOCK, s, k_brick_emit, b->brick_args, be, d_dst);
 			SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[4], s));
 		}
+		if (su != s) SVO_CUDA_TRY(cudaStreamWaitEvent(s, b->ev_join, 0));
 	}
 	SVO_CUDA_TRY(cudaGetLastError());
 	return SVO_OK;
