@@ -456,7 +456,10 @@ def run_ours(args):
                        "l2": "no flush needed: every step streams the fragment list (8 B x fragments, > 126 MB L2)",
                        "parallelism": "single GPU" if single else ("single GPU, 8 octant builds stitched (virtual shards)" if world == 1 else
                                       f"octant-sharded x{world}, NVLink subtree gather")
-                                      + (f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})" if world > 1 else "")},
+                                      + (f" ({'P2P stores via CUDA IPC' if not args.no_ipc else 'NCCL send/recv'})" if world > 1 else "")
+                                      + ("; slabs on the brick path cross in compact form (upper windows, rasterized bricks' leaf blocks, "
+                                         "32 B per brick) and GPU 0 expands the rest" if world > 1 and getattr(sh, "slab", False)
+                                         and getattr(sh, "compact", False) and build_path == 1 else "")},
             "build_ms": ms_per_step,
             "build_path": "bricks" if build_path == 1 else "fragment sort",
             "phases_ms": ({(api.BRICK_PHASES[i] if build_path == 1 else k): phases_acc[k] / args.steps for i, k in enumerate(api.PHASES)}

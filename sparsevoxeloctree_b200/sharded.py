@@ -201,6 +201,9 @@ class ShardedSVO:
         # compact gather (slab mode, parts built on the brick path): SVO_COMPACT=0 sends finished node words instead
         self.compact = os.environ.get("SVO_COMPACT", "1") != "0"
         self.stage_base, self.stage_cap = 0, 0
+        # SVO_SLAB_TRACE=1: host-side time stamps of every slab step (ms between: start, prepared, sizes exchanged, pushed,
+        # own stores complete, [rank 0: tables of all ranks here, expansions enqueued,] device idle)
+        self._trace = [] if os.environ.get("SVO_SLAB_TRACE") else None
         if self.slab:
             ar = ShardedSVO._STAGE_ARENA.get((self.device, self.world))
             if ar:
@@ -215,6 +218,7 @@ class ShardedSVO:
     _STAGE = {}  # (device, part) -> (ptr, capacity in words)
     _STAGE_ARENA = {}  # (device, world) -> dict(ptr, cap, peer): rank 0's staging area of the compact gather
     _PUSH_STREAM = {}  # device -> torch stream
+    _XCHG = {}  # (device, world, width) -> the exchange tensors of the slab mode
 
     def _ensure_final(self, words: int):
         dist = self.dist
@@ -267,26 +271,45 @@ class ShardedSVO:
         blocks of the two deepest windows itself (svo_expand_compact) once the tables have arrived, at local HBM speed.
         A part built on the fragment-sort path stores its finished node words (svo_builder_emit_to)."""
         torch, dist = self.torch, self.dist
+        import time
+        trace = self._trace
+        t = [time.perf_counter()] if trace is not None else None
+
+        def mark():
+            if t is not None:
+                t.append(time.perf_counter())
+
         if self.push_stream is None:
             self.push_stream = ShardedSVO._PUSH_STREAM.setdefault(self.device, torch.cuda.Stream(self.tdev))
-        mine = torch.zeros(1, dtype=torch.int64, device=self.tdev)  # body words | 256-byte units of tables << 32
-        gathered = torch.zeros(self.world, dtype=torch.int64, device=self.tdev)
+        width = HEADER_WORDS + 6 * self.n_sub
+        bufs = ShardedSVO._XCHG.get((self.device, self.world, width))
+        if bufs is None:  # exchange buffers, once per process: device tensors for the collectives, pinned host mirrors
+            bufs = dict(mine=torch.zeros(1, dtype=torch.int64, device=self.tdev),
+                        gathered=torch.zeros(self.world, dtype=torch.int64, device=self.tdev),
+                        gathered_h=torch.zeros(self.world, dtype=torch.int64).pin_memory(),
+                        local=torch.zeros(width, dtype=torch.int64, device=self.tdev),
+                        local_h=torch.zeros(width, dtype=torch.int64).pin_memory(),
+                        headers=torch.zeros(self.world * width, dtype=torch.int64, device=self.tdev),
+                        headers_h=torch.zeros(self.world * width, dtype=torch.int64).pin_memory())
+            ShardedSVO._XCHG[(self.device, self.world, width)] = bufs
+        mine, gathered = bufs["mine"], bufs["gathered"]
         run, stage_run, placed = HEADER_WORDS, 0, []
         overflow = self.final_cap == 0
         plans = np.zeros((self.n_sub, 6), dtype=np.int64)  # per part: the four plan words, staging offset, base word
-        part_bases = []
         for k, (v, b) in enumerate(zip(self.vox, self.builders)):
             v.CmdVoxelize(stream)
             b.Prepare(stream)  # ends with the size read-back: the stream is idle afterwards
+            mark()
             body = b.GetOctreeRange() // 4 - 8 * (1 + b.GetLevelCounts()[1]) if b.GetLeafCount() else 0
             tables = (b.CompactBytes() + 255) // 256 * 256 if (self.compact and self.rank != 0 and body) else 0
             mine.fill_(body | (tables // 256) << 32)
             dist.all_gather_into_tensor(gathered, mine)
-            g = [int(x) for x in gathered.cpu().tolist()]
+            bufs["gathered_h"].copy_(gathered)  # (device -> pinned host: returns when the values are there)
+            g = [int(x) for x in bufs["gathered_h"].tolist()]
+            mark()
             bodies, stages = [x & 0xFFFFFFFF for x in g], [(x >> 32) * 256 for x in g]
             base = run + sum(bodies[: self.rank])
             stage_off = stage_run + sum(stages[: self.rank])
-            part_bases.append([run + sum(bodies[:r]) for r in range(self.world)])
             run += sum(bodies)
             stage_run += sum(stages)
             if run >= 1 << 30:
@@ -304,15 +327,25 @@ class ShardedSVO:
                 self._ensure_stage(stage_run)
             for k, b, base, body, stage_off in placed:
                 plans[k] = self._push_part(b, base, body, stream, stage_off)
-        tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]  # (waits for this rank's stores and copies)
-        width = HEADER_WORDS + 6 * self.n_sub
-        local = torch.from_numpy(np.concatenate([merge_top_blocks(tops).astype(np.int64), plans.reshape(-1)])).to(self.tdev)
-        headers = torch.zeros(self.world * width, dtype=torch.int64, device=self.tdev)
-        dist.all_gather_into_tensor(headers, local)
+        mark()
+        tops = None
+        if self.rank != 0:
+            tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]  # (waits for this rank's stores and copies)
+            bufs["local_h"].copy_(torch.from_numpy(np.concatenate([merge_top_blocks(tops).astype(np.int64), plans.reshape(-1)])))
+            bufs["local"].copy_(bufs["local_h"], non_blocking=True)
+        mark()
+        # rank 0 contributes nothing to this exchange (it merges its own top blocks below), so it enters at once and waits
+        # for the other ranks while its own emit kernel is still running on the push stream
+        dist.all_gather_into_tensor(bufs["headers"], bufs["local"])
         self.total_words = run
         if self.rank == 0:
             # every rank entered this all_gather after its own stores and copies had completed: the tables are here
-            h = headers.cpu().numpy().reshape(self.world, width)
+            bufs["headers_h"].copy_(bufs["headers"])
+            mark()
+            h = bufs["headers_h"].numpy().reshape(self.world, width).copy()
+            tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]
+            h[0, :HEADER_WORDS] = merge_top_blocks(tops).astype(np.int64)
+            h[0, HEADER_WORDS:] = 0
             for r in range(1, self.world):
                 for k in range(self.n_sub):
                     plan = h[r, HEADER_WORDS + 6 * k: HEADER_WORDS + 6 * k + 6]
@@ -320,9 +353,14 @@ class ShardedSVO:
                         self.api.expand_compact(self.lib, self.device, self.stage_base + int(plan[4]), [int(x) for x in plan[:4]],
                                                 self.final + int(plan[5]) * 4, stream)
             header = merge_headers(h[:, :HEADER_WORDS])
-            self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, header.ctypes.data, header.nbytes, 0))
+            self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, header.ctypes.data, header.nbytes, self.api._stream_ptr(stream)))
+            mark()
+        # No barrier at the end: a rank's next step cannot touch rank 0's memory before the next step's first all_gather,
+        # which rank 0 joins only after this synchronize -- the other ranks are free to start voxelizing their next slab.
         torch.cuda.synchronize(self.tdev)
-        dist.barrier()  # remote stores into rank 0's buffer are complete
+        mark()
+        if trace is not None:
+            trace.append([1e3 * (b_ - a_) for a_, b_ in zip(t[:-1], t[1:])])
         return run * 4
 
     def _push_part(self, b, base, body, stream, stage_off=None):
@@ -332,8 +370,9 @@ class ShardedSVO:
         torch = self.torch
         none = np.zeros(6, dtype=np.int64)
         if self.rank == 0:
-            b.EmitTo(self.final + base * 4, base, 2, stream)  # local: straight into the stitched buffer
-            self.push_stream.wait_stream(stream if stream is not None else torch.cuda.current_stream(self.tdev))
+            # local: straight into the stitched buffer, on the push stream (the part's stream is idle after Prepare), so that
+            # the collectives on the caller's stream do not queue behind it
+            b.EmitTo(self.final + base * 4, base, 2, self.push_stream)
             return none
         dst = self.peer_final + base * 4
         if stage_off is not None:
@@ -475,6 +514,11 @@ class ShardedSVO:
         return self.lib.to_host(self.final, np.uint32, self.total_words, self.device)
 
     def destroy(self):
+        if self._trace and len(self._trace) > 3:
+            rows = [r for r in self._trace[2:] if len(r) == len(self._trace[-1])]
+            avg = [sum(c) / len(c) for c in zip(*rows)]
+            print(f"[slab trace] rank {self.rank}: " + " ".join(f"{x:.3f}" for x in avg) + f" | total {sum(avg):.3f} ms over {len(rows)} steps",
+                  file=__import__("sys").stderr, flush=True)
         for b in self.builders:
             b.Destroy()
         for v in self.vox:
