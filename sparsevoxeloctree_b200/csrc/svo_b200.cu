@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -196,6 +197,38 @@ static int fail(int code, const char *msg) {
 
 // Scene::load_textures (src/Scene.cpp:225-300): upload the base levels, build the mip chains on the device with
 // linear blits, and the lookup tables of texture.cuh.  Synchronous (host staging buffers live on this stack).
+// Small page-locked host slots (8 words each) for read-backs the host waits for through an event instead of blocking
+// the stream.  One allocation per process (cudaHostAlloc / cudaFreeHost per builder cost more than a small build and
+// synchronise the device); slots are handed out and taken back under a mutex.
+static std::mutex g_pin_mutex;
+static uint64_t *g_pin_base = nullptr;
+static std::vector<uint32_t> g_pin_free;
+constexpr uint32_t PIN_SLOTS = 4096, PIN_WORDS = 8;
+static uint64_t *pinned_slot_acquire() {
+	std::lock_guard<std::mutex> lock(g_pin_mutex);
+	if (!g_pin_base) {
+#ifdef SVO_EMU
+		g_pin_base = static_cast<uint64_t *>(calloc((size_t)PIN_SLOTS * PIN_WORDS, sizeof(uint64_t)));
+#else
+		if (cudaHostAlloc(reinterpret_cast<void **>(&g_pin_base), (size_t)PIN_SLOTS * PIN_WORDS * sizeof(uint64_t), cudaHostAllocPortable) != cudaSuccess) {
+			(void)cudaGetLastError();
+			g_pin_base = nullptr;
+		}
+#endif
+		if (!g_pin_base) return nullptr;
+		for (uint32_t i = PIN_SLOTS; i-- > 0;) g_pin_free.push_back(i);
+	}
+	if (g_pin_free.empty()) return nullptr;
+	const uint32_t i = g_pin_free.back();
+	g_pin_free.pop_back();
+	return g_pin_base + (size_t)i * PIN_WORDS;
+}
+static void pinned_slot_release(uint64_t *p) {
+	if (!p) return;
+	std::lock_guard<std::mutex> lock(g_pin_mutex);
+	g_pin_free.push_back((uint32_t)((p - g_pin_base) / PIN_WORDS));
+}
+
 static double srgb_to_linear(double x) { return x <= 0.04045 ? x / 12.92 : std::pow((x + 0.055) / 1.055, 2.4); }
 static int upload_textures(svo_scene *sc, const svo_mesh *mesh, cudaStream_t s) {
 	const uint32_t n = mesh->n_textures;
@@ -839,14 +872,8 @@ int svo_builder_create(svo_voxelizer *vox, void *stream, svo_builder **out) {
 			if (cudaEventCreate(&b->ev[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
 		for (int i = 0; i < 5; ++i)
 			if (cudaEventCreate(&b->ev_brick[i]) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaEventCreate failed");
-		if (cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-		    cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess)
-			rc = fail(SVO_ERR_CUDA, "cannot create the builder's auxiliary stream");
-#ifdef SVO_EMU
-		b->h_pinned = static_cast<uint64_t *>(calloc(8, sizeof(uint64_t)));
-#else
-		if (cudaMallocHost(reinterpret_cast<void **>(&b->h_pinned), 8 * sizeof(uint64_t)) != cudaSuccess) rc = fail(SVO_ERR_CUDA, "cudaMallocHost failed");
-#endif
+		b->h_pinned = pinned_slot_acquire();
+		if (!b->h_pinned) rc = fail(SVO_ERR_CUDA, "no page-locked host memory");
 		if (rc) break;
 		const uint64_t F = vox->n_frag;
 		if ((rc = b->tmp.alloc(F, s)) || (rc = b->leaf.alloc(F, s)) || (rc = b->counts.alloc(MAX_LEVEL + 2, s))) break;
@@ -886,11 +913,7 @@ void svo_builder_destroy(svo_builder *b) {
 	if (b->aux) cudaStreamSynchronize(b->aux), cudaStreamDestroy(b->aux);
 	if (b->ev_fork) cudaEventDestroy(b->ev_fork);
 	if (b->ev_join) cudaEventDestroy(b->ev_join);
-#ifdef SVO_EMU
-	free(b->h_pinned);
-#else
-	if (b->h_pinned) cudaFreeHost(b->h_pinned);
-#endif
+	pinned_slot_release(b->h_pinned);
 	release_export(b);
 	delete b;
 }
@@ -915,6 +938,15 @@ static int reduce_sorted(svo_builder *b, const uint64_t *sorted, uint64_t F, uin
 	return 0;
 }
 
+// the builder's second stream and its fork / join events, created on first use
+static int ensure_aux_stream(svo_builder *b) {
+	if (b->aux) return SVO_OK;
+	if (cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess)
+		return fail(SVO_ERR_CUDA, "cannot create the builder's auxiliary stream");
+	return SVO_OK;
+}
+
 // The brick path of svo_builder_prepare (brick.cuh): small triangles' fragments sorted and reduced on their own, large
 // triangles binned; on return *keys_top holds the depth L-3 keys (counts[L-3] of them: the non-empty bricks) and *free_buf is free.
 //   ev[0..1] small fragments: sort + reduce + small records (+ the read-back of their number)
@@ -937,6 +969,7 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	// not depend on the small chain: they are generated while the host waits for the small chain's two counts.
 	SVO_TRY(b->pairs_a.reserve(npl + ns, s)); // (at most one small record per small fragment)
 	if (npl) { // on the builder's second stream, next to the small chain
+		SVO_TRY(ensure_aux_stream(b));
 		SVO_CUDA_TRY(cudaEventRecord(b->ev_fork, s));
 		SVO_CUDA_TRY(cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
 		SVO_LAUNCH(brick_pair_grid(v), RASTER_BLOCK, 0, b->aux, k_brick_pairs<true>, v->rp, v->n_large, (const LargeTri *)v->large.p,
@@ -1161,6 +1194,7 @@ static int emit_into(svo_builder *b, uint32_t *d_dst, uint32_t bias, int skip_ro
 		// brick path: the upper windows (small) are written on the builder's second stream, next to k_brick_emit
 		cudaStream_t su = s;
 		if (b->path == 1 && b->n_bricks) {
+			SVO_TRY(ensure_aux_stream(b));
 			su = b->aux;
 			SVO_CUDA_TRY(cudaEventRecord(b->ev_fork, s));
 			SVO_CUDA_TRY(cudaStreamWaitEvent(su, b->ev_fork, 0));
