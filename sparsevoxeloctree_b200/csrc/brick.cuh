@@ -513,7 +513,10 @@ SVO_DEV uint32_t brick_node_rank(uint32_t x, uint32_t y, uint32_t node) {
 constexpr uint32_t RANK_SH2 = 18, RANK_SH3 = 33;
 constexpr uint64_t RANK_M1 = (1ull << RANK_SH2) - 1, RANK_M2 = (1ull << (RANK_SH3 - RANK_SH2)) - 1;
 static_assert(SCAN_TILE * 64ull <= RANK_M1 && SCAN_TILE * 8ull <= RANK_M2, "packed tile sums");
-__global__ void __launch_bounds__(SCAN_BLOCK)
+#ifndef SVO_RANKS_MINB
+#define SVO_RANKS_MINB 3
+#endif
+__global__ void __launch_bounds__(SCAN_BLOCK, SVO_RANKS_MINB)
     k_brick_ranks(BrickArgs a, uint64_t *__restrict__ rank1, uint64_t *__restrict__ rank2, uint64_t *state, uint32_t *ticket, uint64_t state_stride) {
 	constexpr int NW = SCAN_BLOCK / 32, NC = SCAN_ITEMS * NW; // (row, warp) cells of a tile
 	static_assert(NC % 32 == 0 && NC <= 128, "the cells are scanned by one warp");
@@ -560,6 +563,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 	const uint64_t total = s_prefix[0];
 	if (threadIdx.x == 0 && s_leaves) atomicAdd(reinterpret_cast<unsigned long long *>(a.count[0]), s_leaves);
 	__syncthreads();
+	// (the bricks' codes are fetched now: their latency passes while the look-back warps walk their chains)
+	uint32_t code[SCAN_ITEMS];
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		const uint64_t e = base + (uint64_t)i * SCAN_BLOCK;
+		code[i] = (own[i] >> 21) ? (uint32_t)a.brick_code[e] & 0x3fffffffu : 0u;
+	}
 	if (warp < 3) { // warp y walks the look-back chain of scan y
 		const uint64_t mine = warp == 0 ? (total & RANK_M1) : (warp == 1 ? ((total >> RANK_SH2) & RANK_M2) : (total >> RANK_SH3));
 		const uint64_t p = lookback_exclusive(state + (uint64_t)warp * state_stride, tile, mine, lane);
@@ -577,7 +587,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 		if (e == n) *a.count[1] = r1, *a.count[2] = r2, *a.count3 = r3;
 		uint32_t n2 = own[i] >> 21;
 		if (n2) { // a non-empty brick (records past the last brick are zero)
-			a.keys_top[r3] = a.brick_code[e] & 0x3fffffffull;
+			a.keys_top[r3] = code[i];
 			a.first_l2[r3] = (uint32_t)r2;
 			unsigned char *sl = a.slot_l2 + r2;
 			for (; n2; n2 &= n2 - 1u) *sl++ = (unsigned char)(__ffs((int)n2) - 1);
