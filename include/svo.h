@@ -202,8 +202,12 @@ SVO_API int svo_builder_emit_to(svo_builder *b, uint32_t *d_dst, uint32_t pointe
  * svo_builder_top_words) are the same.  svo_builder_compact_bytes is 0 for a build that took the fragment-sort path
  * (no compact form: use svo_builder_emit_to).  The caller orders svo_expand_compact after the arrival of the tables
  * (stream order on one device; a collective or an IPC event between processes).
- * Replaces nothing in the reference (single device); the gather is north_star's "subtrees gathered to GPU 0". */
+ * Replaces nothing in the reference (single device); the gather is north_star's "subtrees gathered to GPU 0".
+ * svo_builder_push_tables does the table part alone (and returns the plan words), svo_builder_emit_compact_to with
+ * d_tables = NULL the rest: a host that sends the tables first lets the owner of the buffer expand them while the
+ * other stores are still crossing the link. */
 SVO_API uint64_t svo_builder_compact_bytes(const svo_builder *b);
+SVO_API int svo_builder_push_tables(svo_builder *b, uint32_t pointer_bias_words, int skip_root, void *d_tables, uint64_t plan[4], void *stream);
 SVO_API int svo_builder_emit_compact_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *d_tables,
                                         uint64_t plan[4], void *stream);
 SVO_API int svo_expand_compact(int device, const void *d_tables, const uint64_t plan[4], uint32_t *d_dst, void *stream);

@@ -90,6 +90,7 @@ SYMBOLS = [
     ("svo_builder_prepare", C.c_int, [_P, _P]),
     ("svo_builder_emit_to", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
     ("svo_builder_compact_bytes", C.c_uint64, [_P]),
+    ("svo_builder_push_tables", C.c_int, [_P, C.c_uint32, C.c_int, _P, C.POINTER(C.c_uint64), _P]),
     ("svo_builder_emit_compact_to", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P, C.POINTER(C.c_uint64), _P]),
     ("svo_expand_compact", C.c_int, [C.c_int, _P, C.POINTER(C.c_uint64), _P, _P]),
     ("svo_builder_root_words", C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
@@ -451,12 +452,19 @@ class OctreeBuilder:
         """Bytes of the per-brick tables of the compact gather; 0 when the build has no compact form (fragment-sort path)."""
         return int(self.lib.dll.svo_builder_compact_bytes(self._h))
 
-    def EmitCompactTo(self, d_dst: int, pointer_bias_words: int, skip_root, d_tables: int, stream=None):
+    def EmitCompactTo(self, d_dst: int, pointer_bias_words: int, skip_root, d_tables, stream=None):
         """Phase 2 in compact form (brick path): upper windows and the rasterized bricks' leaf blocks go to d_dst, 32 bytes
-        per brick to d_tables; returns the four plan words expand_compact() needs on the GPU that owns d_dst."""
+        per brick to d_tables; returns the four plan words expand_compact() needs on the GPU that owns d_dst.
+        d_tables = None: the tables have been sent already (PushTables); returns None."""
         plan = (C.c_uint64 * 4)()
-        self.lib.check(self.lib.dll.svo_builder_emit_compact_to(self._h, d_dst, pointer_bias_words, int(skip_root), d_tables, plan,
-                                                                _stream_ptr(stream)))
+        self.lib.check(self.lib.dll.svo_builder_emit_compact_to(self._h, d_dst, pointer_bias_words, int(skip_root), d_tables or None,
+                                                                plan if d_tables else None, _stream_ptr(stream)))
+        return [int(v) for v in plan] if d_tables else None
+
+    def PushTables(self, pointer_bias_words: int, skip_root, d_tables: int, stream=None):
+        """The table part of EmitCompactTo alone (32 bytes per brick to d_tables); returns the four plan words."""
+        plan = (C.c_uint64 * 4)()
+        self.lib.check(self.lib.dll.svo_builder_push_tables(self._h, pointer_bias_words, int(skip_root), d_tables, plan, _stream_ptr(stream)))
         return [int(v) for v in plan]
 
     def TopWords(self, stream=None) -> np.ndarray:

@@ -1238,25 +1238,50 @@ uint64_t svo_builder_compact_bytes(const svo_builder *b) {
 	return (b && b->prepared && b->path == 1 && b->h_counts[b->level]) ? b->n_bricks * 32ull : 0;
 }
 
-int svo_builder_emit_compact_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *d_tables, uint64_t plan[4],
-                                void *stream) {
-	if (!b || !d_dst || !d_tables || !plan) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_compact_to: null argument");
-	if (!b->prepared) return fail(SVO_ERR_NOT_READY, "svo_builder_emit_compact_to: prepare first");
-	if (!svo_builder_compact_bytes(b)) return fail(SVO_ERR_UNSUPPORTED, "svo_builder_emit_compact_to: the build did not take the brick path (use svo_builder_emit_to)");
-	if (skip_root < 0 || skip_root > 2 || (skip_root == 2 && b->level < 3))
-		return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_compact_to: skip_root is 0, 1 or 2 (2 needs level >= 3)");
-	if ((uint64_t)pointer_bias_words + b->range_bytes / 4 >= (1ull << 30))
-		return fail(SVO_ERR_CAPACITY, "biased child pointers would exceed 30 bits (octree.glsl:110)");
-	DeviceGuard guard(b->device);
-	cudaStream_t s = (cudaStream_t)stream;
-	b->last_stream = s;
-	// upper windows + the leaf blocks of the rasterized bricks go to their final places; records and ranks to the tables
-	SVO_TRY(emit_into(b, d_dst, pointer_bias_words, skip_root, s, BRICK_EMIT_COPY, plan));
+static int compact_args_ok(svo_builder *b, const char *who, uint32_t pointer_bias_words, int skip_root) {
+	int rc = SVO_OK;
+	const char *why = nullptr;
+	if (!b->prepared) rc = SVO_ERR_NOT_READY, why = "prepare first";
+	else if (!svo_builder_compact_bytes(b)) rc = SVO_ERR_UNSUPPORTED, why = "the build did not take the brick path (use svo_builder_emit_to)";
+	else if (skip_root < 0 || skip_root > 2 || (skip_root == 2 && b->level < 3)) rc = SVO_ERR_INVALID_ARGUMENT, why = "skip_root is 0, 1 or 2 (2 needs level >= 3)";
+	else if ((uint64_t)pointer_bias_words + b->range_bytes / 4 >= (1ull << 30))
+		rc = SVO_ERR_CAPACITY, why = "biased child pointers would exceed 30 bits (octree.glsl:110)";
+	if (rc != SVO_OK) set_error("%s: %s", who, why);
+	return rc;
+}
+
+// records and ranks -> d_tables (three copies: 16 + 8 + 8 bytes per brick), and the plan words of svo_expand_compact
+static int push_tables(svo_builder *b, uint32_t bias, int skip_root, void *d_tables, uint64_t plan[4], cudaStream_t s) {
+	const uint32_t L = b->level;
+	const uint32_t shift = skip_root == 0 ? 0u : (skip_root == 1 ? 1u : 1u + (uint32_t)b->h_counts[1]);
+	plan[0] = b->n_bricks, plan[1] = b->ep.block_base[L - 1], plan[2] = b->ep.block_base[L], plan[3] = (uint64_t)shift | ((uint64_t)bias << 32);
 	const uint64_t n = b->n_bricks;
 	char *t = static_cast<char *>(d_tables);
 	SVO_CUDA_TRY(cudaMemcpyAsync(t, b->brick_args.rec, n * 16, cudaMemcpyDefault, s));
 	SVO_CUDA_TRY(cudaMemcpyAsync(t + n * 16, b->brick_args.rank[1], n * 8, cudaMemcpyDefault, s));
 	SVO_CUDA_TRY(cudaMemcpyAsync(t + n * 24, b->brick_args.rank[2], n * 8, cudaMemcpyDefault, s));
+	return SVO_OK;
+}
+
+int svo_builder_push_tables(svo_builder *b, uint32_t pointer_bias_words, int skip_root, void *d_tables, uint64_t plan[4], void *stream) {
+	if (!b || !d_tables || !plan) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_push_tables: null argument");
+	SVO_TRY(compact_args_ok(b, "svo_builder_push_tables", pointer_bias_words, skip_root));
+	DeviceGuard guard(b->device);
+	b->last_stream = (cudaStream_t)stream;
+	return push_tables(b, pointer_bias_words, skip_root, d_tables, plan, (cudaStream_t)stream);
+}
+
+int svo_builder_emit_compact_to(svo_builder *b, uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *d_tables, uint64_t plan[4],
+                                void *stream) {
+	if (!b || !d_dst || (d_tables && !plan)) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_builder_emit_compact_to: null argument");
+	SVO_TRY(compact_args_ok(b, "svo_builder_emit_compact_to", pointer_bias_words, skip_root));
+	DeviceGuard guard(b->device);
+	cudaStream_t s = (cudaStream_t)stream;
+	b->last_stream = s;
+	// records and ranks to the tables (first: the owner of the buffer can start on them while the rest is still crossing);
+	// the upper windows and the leaf blocks of the rasterized bricks go to their final places
+	if (d_tables) SVO_TRY(push_tables(b, pointer_bias_words, skip_root, d_tables, plan, s));
+	SVO_TRY(emit_into(b, d_dst, pointer_bias_words, skip_root, s, BRICK_EMIT_COPY, nullptr));
 	SVO_CUDA_TRY(cudaEventRecord(b->ev[5], s));
 	b->emitted = true;
 	return SVO_OK;

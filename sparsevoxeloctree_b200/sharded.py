@@ -202,8 +202,14 @@ class ShardedSVO:
         self.compact = os.environ.get("SVO_COMPACT", "1") != "0"
         self.stage_base, self.stage_cap = 0, 0
         # SVO_SLAB_TRACE=1: host-side time stamps of every slab step (ms between: start, prepared, sizes exchanged, pushed,
-        # own stores complete, [rank 0: tables of all ranks here, expansions enqueued,] device idle)
+        # [rank 0: tables of all ranks here,] plans exchanged (rank 0: expansions enqueued), own stores complete,
+        # [rank 0: top blocks of all ranks here, header written,] device idle)
         self._trace = [] if os.environ.get("SVO_SLAB_TRACE") else None
+        self._table_events = []  # one per part sent in compact form: its tables have arrived on rank 0
+        # SVO_DEFER_REST = 1 / 0: launch the other stores of a compact part after / before the plan exchange
+        # (default: after, when 4 or more ranks share rank 0's NVLink port)
+        self.defer_rest = {"1": True, "0": False}.get(os.environ.get("SVO_DEFER_REST", ""), self.world >= 4)
+        self._pending_rest = []  # parts whose tables are on their way and whose other stores have not been launched yet
         if self.slab:
             ar = ShardedSVO._STAGE_ARENA.get((self.device, self.world))
             if ar:
@@ -269,7 +275,11 @@ class ShardedSVO:
         windows above depth L-2 and the leaf blocks of the rasterized bricks to their final places, 32 bytes per brick
         (record + two ranks) to a staging area on rank 0 -- and rank 0 generates the flat bricks' blocks and all pointer
         blocks of the two deepest windows itself (svo_expand_compact) once the tables have arrived, at local HBM speed.
-        A part built on the fragment-sort path stores its finished node words (svo_builder_emit_to)."""
+        A part built on the fragment-sort path stores its finished node words (svo_builder_emit_to).
+
+        Three small exchanges per step: (1) per part, the sizes -> offsets; (2) the plan words of the compact parts, entered
+        when a rank's tables have arrived -> rank 0 starts expanding; (3) the top blocks, entered when a rank's stores have
+        completed -> rank 0 writes the merged header."""
         torch, dist = self.torch, self.dist
         import time
         trace = self._trace
@@ -281,17 +291,20 @@ class ShardedSVO:
 
         if self.push_stream is None:
             self.push_stream = ShardedSVO._PUSH_STREAM.setdefault(self.device, torch.cuda.Stream(self.tdev))
-        width = HEADER_WORDS + 6 * self.n_sub
-        bufs = ShardedSVO._XCHG.get((self.device, self.world, width))
+        width = HEADER_WORDS
+        bufs = ShardedSVO._XCHG.get((self.device, self.world, self.n_sub))
         if bufs is None:  # exchange buffers, once per process: device tensors for the collectives, pinned host mirrors
-            bufs = dict(mine=torch.zeros(1, dtype=torch.int64, device=self.tdev),
-                        gathered=torch.zeros(self.world, dtype=torch.int64, device=self.tdev),
-                        gathered_h=torch.zeros(self.world, dtype=torch.int64).pin_memory(),
-                        local=torch.zeros(width, dtype=torch.int64, device=self.tdev),
-                        local_h=torch.zeros(width, dtype=torch.int64).pin_memory(),
-                        headers=torch.zeros(self.world * width, dtype=torch.int64, device=self.tdev),
-                        headers_h=torch.zeros(self.world * width, dtype=torch.int64).pin_memory())
-            ShardedSVO._XCHG[(self.device, self.world, width)] = bufs
+            def dev(n):
+                return torch.zeros(n, dtype=torch.int64, device=self.tdev)
+
+            def pin(n):
+                return torch.zeros(n, dtype=torch.int64).pin_memory()
+
+            bufs = dict(mine=dev(1), gathered=dev(self.world), gathered_h=pin(self.world),
+                        plans=dev(6 * self.n_sub), plans_h=pin(6 * self.n_sub),
+                        plans_all=dev(self.world * 6 * self.n_sub), plans_all_h=pin(self.world * 6 * self.n_sub),
+                        local=dev(width), local_h=pin(width), headers=dev(self.world * width), headers_h=pin(self.world * width))
+            ShardedSVO._XCHG[(self.device, self.world, self.n_sub)] = bufs
         mine, gathered = bufs["mine"], bufs["gathered"]
         run, stage_run, placed = HEADER_WORDS, 0, []
         overflow = self.final_cap == 0
@@ -328,31 +341,49 @@ class ShardedSVO:
             for k, b, base, body, stage_off in placed:
                 plans[k] = self._push_part(b, base, body, stream, stage_off)
         mark()
-        tops = None
+        # -- second exchange: the plan words of the parts sent in compact form.  A rank enters it when its TABLES have
+        #    arrived on rank 0, and launches the kernels that store the upper windows and the rasterized bricks' leaf blocks
+        #    right behind it: rank 0 expands the tables while the rest crosses.
         if self.rank != 0:
-            tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]  # (waits for this rank's stores and copies)
-            bufs["local_h"].copy_(torch.from_numpy(np.concatenate([merge_top_blocks(tops).astype(np.int64), plans.reshape(-1)])))
-            bufs["local"].copy_(bufs["local_h"], non_blocking=True)
-        mark()
-        # rank 0 contributes nothing to this exchange (it merges its own top blocks below), so it enters at once and waits
-        # for the other ranks while its own emit kernel is still running on the push stream
-        dist.all_gather_into_tensor(bufs["headers"], bufs["local"])
-        self.total_words = run
+            for ev in self._table_events:
+                ev.synchronize()
+            bufs["plans_h"].copy_(torch.from_numpy(plans.reshape(-1)))
+            with torch.cuda.stream(self.push_stream):  # (the push stream waits for the collective: what follows on it runs after)
+                bufs["plans"].copy_(bufs["plans_h"], non_blocking=True)
+                dist.all_gather_into_tensor(bufs["plans_all"], bufs["plans"])
+            for b, dst, base in self._pending_rest:  # upper windows + the rasterized bricks' leaf blocks, to their final places
+                b.EmitCompactTo(dst, base, 2, None, self.push_stream)
+        else:
+            dist.all_gather_into_tensor(bufs["plans_all"], bufs["plans"])
+        self._table_events, self._pending_rest = [], []
         if self.rank == 0:
-            # every rank entered this all_gather after its own stores and copies had completed: the tables are here
-            bufs["headers_h"].copy_(bufs["headers"])
+            bufs["plans_all_h"].copy_(bufs["plans_all"])
             mark()
-            h = bufs["headers_h"].numpy().reshape(self.world, width).copy()
-            tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]
-            h[0, :HEADER_WORDS] = merge_top_blocks(tops).astype(np.int64)
-            h[0, HEADER_WORDS:] = 0
+            pl = bufs["plans_all_h"].numpy().reshape(self.world, self.n_sub, 6)
             for r in range(1, self.world):
                 for k in range(self.n_sub):
-                    plan = h[r, HEADER_WORDS + 6 * k: HEADER_WORDS + 6 * k + 6]
+                    plan = pl[r, k]
                     if plan[0]:
                         self.api.expand_compact(self.lib, self.device, self.stage_base + int(plan[4]), [int(x) for x in plan[:4]],
                                                 self.final + int(plan[5]) * 4, stream)
-            header = merge_headers(h[:, :HEADER_WORDS])
+        mark()
+        # -- third exchange: the parts' top blocks (root block + depth-1 blocks).  A rank enters it when all its stores have
+        #    completed, so it doubles as the completion signal; rank 0 contributes nothing (it merges its own top blocks
+        #    below) and enters at once.
+        if self.rank != 0:
+            tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]  # (waits for this rank's stores)
+            bufs["local_h"].copy_(torch.from_numpy(merge_top_blocks(tops).astype(np.int64)))
+            bufs["local"].copy_(bufs["local_h"], non_blocking=True)
+        mark()
+        dist.all_gather_into_tensor(bufs["headers"], bufs["local"])
+        self.total_words = run
+        if self.rank == 0:
+            bufs["headers_h"].copy_(bufs["headers"])
+            mark()
+            h = bufs["headers_h"].numpy().reshape(self.world, HEADER_WORDS).copy()
+            tops = [b.TopWords(self.push_stream) for _, b, _, _, _ in placed]
+            h[0] = merge_top_blocks(tops).astype(np.int64)
+            header = merge_headers(h)
             self.lib.check(self.lib.dll.svo_memcpy_h2d(self.device, self.final, header.ctypes.data, header.nbytes, self.api._stream_ptr(stream)))
             mark()
         # No barrier at the end: a rank's next step cannot touch rank 0's memory before the next step's first all_gather,
@@ -376,7 +407,16 @@ class ShardedSVO:
             return none
         dst = self.peer_final + base * 4
         if stage_off is not None:
-            plan = b.EmitCompactTo(dst, base, 2, self.stage_base + stage_off, self.push_stream)
+            plan = b.PushTables(base, 2, self.stage_base + stage_off, self.push_stream)  # the tables first ...
+            ev = torch.cuda.Event()
+            ev.record(self.push_stream)
+            self._table_events.append(ev)
+            if self.defer_rest:
+                # ... the kernels that store the rest are launched after the plan exchange (_step_slab): the collective's own
+                # messages would otherwise queue behind their stores on rank 0's NVLink port
+                self._pending_rest.append((b, dst, base))
+            else:
+                b.EmitCompactTo(dst, base, 2, None, self.push_stream)  # ... then the kernels that store the rest
             return np.array(plan + [stage_off, base], dtype=np.uint64).astype(np.int64)
         if self.push_mode == "store":
             b.EmitTo(dst, base, 2, self.push_stream)
