@@ -136,7 +136,12 @@ def depth2_parts_check(lib, world, n_sub, mesh, level, mode=api.CONSERVATIVE_EXA
         if b.GetLeafCount():
             if stage_bytes[k]:
                 tables = stage + sum(stage_bytes[:k])
-                pending.append((tables, b.EmitCompactTo(arena + base * 4, base, 2, tables), arena + base * 4))
+                if k % 2:  # the two-call form the slab mode uses: tables first, the other stores later
+                    plan = b.PushTables(base, 2, tables)
+                    assert b.EmitCompactTo(arena + base * 4, base, 2, None) is None
+                else:
+                    plan = b.EmitCompactTo(arena + base * 4, base, 2, tables)
+                pending.append((tables, plan, arena + base * 4))
             else:
                 b.EmitTo(arena + base * 4, base, 2)
             tops.append(b.TopWords())
