@@ -269,7 +269,7 @@ SVO_API void svo_debug_set_build_path(int mode);
 SVO_API int svo_builder_build_path(const svo_builder *b);
 /* Brick path only, after a build (or prepare + emit_to): counts = { (brick, triangle) pairs incl. small records, bricks,
  * leaves of small triangles, bricks that needed pixels (the others are flat: one triangle, one depth voxel) },
- * ms = { k_brick_flat + k_brick_raster, the rank scans, k_brick_keys, k_brick_emit } of the last build (cudaEvents). */
+ * ms = { k_brick_flat + k_brick_raster, k_brick_ranks, (nothing: the keys are written by k_brick_ranks), k_brick_emit } of the last build (cudaEvents). */
 SVO_API int svo_builder_brick_stats(svo_builder *b, uint64_t counts[4], float ms[4]);
 
 /* ---- the consumer side, for verification ----------------------------------------------------

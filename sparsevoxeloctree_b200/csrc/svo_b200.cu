@@ -1045,7 +1045,7 @@ static int prepare_bricks(svo_builder *b, cudaStream_t s, const uint64_t *first_
 	else
 		SVO_LAUNCH(rgrid, BRICK_BLOCK, 0, s, k_brick_raster<false>, a);
 	SVO_CUDA_TRY(cudaEventRecord(b->ev_brick[1], s));
-	{ // ranks: three scans in one launch, which also writes the depth L-2 keys and the three node counts
+	{ // ranks: three scans in one launch, which also writes the depth L-3 level (keys, first children, slots) and the four level counts
 		const uint32_t tiles = div_up(nbd + 1, SCAN_TILE); // (one element more than records: it receives the totals)
 		SVO_TRY(b->scan_scratch.state.reserve((uint64_t)(tiles + 1) * 3, s));
 		SVO_TRY(b->scan_scratch.ticket.reserve(3, s));
