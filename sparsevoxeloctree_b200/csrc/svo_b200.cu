@@ -218,7 +218,7 @@ static uint64_t *pinned_slot_acquire() {
 		if (!g_pin_base) return nullptr;
 		for (uint32_t i = PIN_SLOTS; i-- > 0;) g_pin_free.push_back(i);
 	}
-	if (g_pin_free.empty()) return nullptr;
+	if (g_pin_free.empty()) return new (std::nothrow) uint64_t[PIN_WORDS](); // (more handles than slots: pageable memory, still correct)
 	const uint32_t i = g_pin_free.back();
 	g_pin_free.pop_back();
 	return g_pin_base + (size_t)i * PIN_WORDS;
@@ -226,6 +226,10 @@ static uint64_t *pinned_slot_acquire() {
 static void pinned_slot_release(uint64_t *p) {
 	if (!p) return;
 	std::lock_guard<std::mutex> lock(g_pin_mutex);
+	if (!g_pin_base || p < g_pin_base || p >= g_pin_base + (size_t)PIN_SLOTS * PIN_WORDS) {
+		delete[] p;
+		return;
+	}
 	g_pin_free.push_back((uint32_t)((p - g_pin_base) / PIN_WORDS));
 }
 
