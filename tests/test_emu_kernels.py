@@ -266,3 +266,22 @@ def test_compact_gather_assembles_the_whole_tree(emu, world):
         assert n >= world // 2
     finally:
         emu.dll.svo_debug_set_build_path(-1)
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5])
+def test_low_levels_through_the_tail_kernel(emu, level):
+    """k_parent_tail walks every level above depth 4 in one single-block launch; at these levels it is the whole upper
+    part of the build (level 1: the leaves are the root's children, no tail at all)."""
+    check_against_oracle(emu, scenes.random_soup(40, 100 + level, 0.05, 1.2), level, api.CONSERVATIVE_EXACT)
+
+
+@pytest.mark.parametrize("level", [5, 6])
+def test_brick_path_at_its_lowest_levels(emu, level):
+    """Level 5 is the lowest level with large triangles (a candidate rectangle of more than 256 pixels needs a grid of more
+    than 16 x 16): k_brick_ranks writes depth 2 (the bricks), the tail kernel everything above."""
+    emu.dll.svo_debug_set_build_path(1)
+    try:
+        info = check_against_oracle(emu, scenes.random_soup(30, 200 + level, 0.3, 1.5), level, api.CONSERVATIVE_EXACT)
+        assert info["path"] == 1
+    finally:
+        emu.dll.svo_debug_set_build_path(-1)
