@@ -295,6 +295,23 @@ public:
 	int CmdBuild(Stream stream = nullptr) const { return svo_builder_build(m_handle, stream); }
 	uint64_t GetOctreeRange() const { return svo_builder_octree_range_bytes(m_handle); } // bytes, like VkDeviceSize
 	const uint32_t *GetOctree() const { return svo_builder_octree(m_handle); }           // device pointer
+	// The same build in two phases, for hosts that place the node words themselves (several GPUs, externally allocated
+	// memory; include/svo.h): Prepare, then EmitTo -- or, for a slab that took the brick path (CompactBytes() > 0), the
+	// compact gather: PushTables + EmitCompactTo on the sending GPU, ExpandCompact on the GPU that owns the buffer.
+	int Prepare(Stream stream = nullptr) const { return svo_builder_prepare(m_handle, stream); }
+	int EmitTo(uint32_t *d_dst, uint32_t pointer_bias_words = 0, int skip_root = 0, Stream stream = nullptr) const {
+		return svo_builder_emit_to(m_handle, d_dst, pointer_bias_words, skip_root, stream);
+	}
+	uint64_t CompactBytes() const { return svo_builder_compact_bytes(m_handle); }
+	int PushTables(uint32_t pointer_bias_words, int skip_root, void *d_tables, uint64_t plan[4], Stream stream = nullptr) const {
+		return svo_builder_push_tables(m_handle, pointer_bias_words, skip_root, d_tables, plan, stream);
+	}
+	int EmitCompactTo(uint32_t *d_dst, uint32_t pointer_bias_words, int skip_root, void *d_tables, uint64_t plan[4], Stream stream = nullptr) const {
+		return svo_builder_emit_compact_to(m_handle, d_dst, pointer_bias_words, skip_root, d_tables, plan, stream);
+	}
+	static int ExpandCompact(int device, const void *d_tables, const uint64_t plan[4], uint32_t *d_dst, Stream stream = nullptr) {
+		return svo_expand_compact(device, d_tables, plan, d_dst, stream);
+	}
 	// Queue-family ownership transfer (src/OctreeBuilder.cpp:215-220): nothing to record for a CUDA-produced buffer;
 	// the Vulkan side acquires external memory from VK_QUEUE_FAMILY_EXTERNAL.
 	void CmdTransferOctreeOwnership(Stream, uint32_t, uint32_t) const {}
