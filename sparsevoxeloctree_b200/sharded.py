@@ -335,6 +335,7 @@ class ShardedSVO:
                     plans[k] = self._push_part(b, base, body, stream, stage_off if tables else None)
         if overflow:  # first step, or the tree outgrew the arena: size it now and emit everything (again)
             self.push_stream.synchronize()
+            self._table_events, self._pending_rest = [], []  # (what was sent before the arena turned out too small is sent again)
             self._ensure_final(run)
             if stage_run > self.stage_cap:
                 self._ensure_stage(stage_run)
